@@ -1,0 +1,7 @@
+"""corb_slam_b200 - B200-native (sm_100a) hot path of CORB-SLAM behind the reference's own interfaces.
+
+Only what the path needs: csrc/ (CUDA kernels + the C ABI of libcorb_b200.so) and host-side mirrors of the
+reference classes that own the path (ORBextractor, ORBmatcher, ORBVocabulary, Optimizer).
+"""
+from ._lib import CorbError, KP_DTYPE, LIB_PATH  # noqa: F401
+from .orbextractor import ORBextractor  # noqa: F401

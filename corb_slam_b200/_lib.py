@@ -1,0 +1,79 @@
+"""ctypes loader of libcorb_b200.so (the C ABI declared in include/corb_b200.h).
+
+There is no fallback: if the shared library is missing the import fails, and every compute entry point fails
+with CORB_ERR_CUDA when no B200 is visible.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcorb_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STOPPED, ERR_IO = range(7)
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+
+class CorbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("corb_b200 error %d: %s" % (status, msg))
+        self.status = status
+
+
+def build(verbose=False):
+    """Compile libcorb_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building libcorb_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing - run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.corb_last_error.restype = C.c_char_p
+        L.corb_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.corb_orb_destroy.argtypes = [vp]
+        L.corb_orb_destroy.restype = None
+        L.corb_orb_levels.argtypes = [vp]
+        L.corb_orb_scale_factor.argtypes = [vp]
+        L.corb_orb_scale_factor.restype = C.c_float
+        L.corb_orb_tables.argtypes = [vp, f32p, f32p, f32p, f32p, i32p, i32p]
+        L.corb_orb_level_size.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32p, i32p]
+        L.corb_orb_capacity.argtypes = [vp, C.c_int, C.c_int]
+        L.corb_orb_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, i32p, C.POINTER(vp)]
+        L.corb_orb_extract_submit.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.corb_orb_extract_wait.argtypes = [vp, vp, vp, i32p, C.POINTER(vp)]
+        L.corb_orb_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+        L.corb_orb_sync.argtypes = [vp]
+        L.corb_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.corb_orb_device_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), i32p, i32p, i32p]
+        L.corb_orb_stream.argtypes = [vp]
+        L.corb_orb_stream.restype = vp
+        L.corb_orb_launches_per_extract.argtypes = [vp]
+        L.corb_orb_tap.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, i32p]
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != OK:
+        raise CorbError(status, lib().corb_last_error().decode("utf-8", "replace"))

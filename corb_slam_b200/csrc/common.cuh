@@ -1,0 +1,76 @@
+// Shared host/device helpers for libcorb_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/corb_b200.h"
+
+namespace corb {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define CORB_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            corb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return CORB_ERR_CUDA;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+#define CORB_CHECK(cond, code, ...)         \
+    do {                                    \
+        if (!(cond)) {                      \
+            corb::set_error(__VA_ARGS__);   \
+            return (code);                  \
+        }                                   \
+    } while (0)
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+static inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Block-wide exclusive scan of data[0..n) in shared memory, in place; returns the total to every thread.
+// `warp_tmp` must hold 33 ints of shared memory. All threads of the block must call it.
+__device__ __forceinline__ int block_excl_scan(int* data, int n, int* warp_tmp) {
+    const int nt = blockDim.x, t = threadIdx.x;
+    const int chunk = (n + nt - 1) / nt;
+    const int b = t * chunk, e = min(b + chunk, n);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += data[i];
+    // scan of per-thread sums
+    const int lane = t & 31, wid = t >> 5;
+    int v = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_tmp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = (nt + 31) >> 5;
+        int w = lane < nw ? warp_tmp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        warp_tmp[lane] = w;  // inclusive over warps
+        if (lane == 31) warp_tmp[32] = w;
+    }
+    __syncthreads();
+    int run = v - sum + (wid ? warp_tmp[wid - 1] : 0);  // exclusive prefix of this thread's chunk
+    const int total = warp_tmp[min((nt + 31) >> 5, 32) - 1];
+    for (int i = b; i < e; i++) {
+        int x = data[i];
+        data[i] = run;
+        run += x;
+    }
+    __syncthreads();
+    return total;
+}
+
+}  // namespace corb

@@ -1,0 +1,531 @@
+// C ABI of the ORB extractor: handle, per-image-size plan, CUDA graph, host staging.
+// Replaces ORBextractor (corbslam_client/include/ORBextractor.h:45-112, src/ORBextractor.cc:410-470,1043-1132).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "orb_kernels.cuh"
+
+namespace corb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static inline int cv_round_f(float v) { return (int)nearbyintf(v); }   // cvRound: round half to even
+static inline int cv_round_d(double v) { return (int)nearbyint(v); }
+
+}  // namespace corb
+
+using namespace corb;
+
+struct corb_orb {
+    // parameters and tables (ORBextractor.cc:410-470)
+    int nfeatures, nlevels, ini_th, min_th, device;
+    float scale_factor_f;
+    double scale_factor;  // the reference stores the float argument in a double member (ORBextractor.h:97)
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> quota;
+    int umax[16];
+
+    // plan for the current image size
+    int plan_w = 0, plan_h = 0;
+    OrbGeom geom;
+    OrbBuffers buf;
+    size_t pyr_bytes = 0;
+    int cand_total = 0;
+    int key_smem_cap = 0, oct_smem = 0;
+    std::vector<void*> dev_allocs;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int kernel_launches = 0;
+
+    // pinned host staging
+    uint8_t* h_img = nullptr;       // plan_w * plan_h
+    uint8_t* h_pyr = nullptr;       // pyr_bytes
+    corb_keypoint* h_kps = nullptr; // kp_cap
+    uint8_t* h_desc = nullptr;      // kp_cap * 32
+    int* h_scalars = nullptr;       // [0] count, [1] status
+    bool pending = false, pending_pyr = false, pending_empty = false;
+};
+
+static void free_plan(corb_orb* h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec), h->graph_exec = nullptr;
+    if (h->graph) cudaGraphDestroy(h->graph), h->graph = nullptr;
+    for (void* p : h->dev_allocs) cudaFree(p);
+    h->dev_allocs.clear();
+    if (h->h_img) cudaFreeHost(h->h_img), h->h_img = nullptr;
+    if (h->h_pyr) cudaFreeHost(h->h_pyr), h->h_pyr = nullptr;
+    if (h->h_kps) cudaFreeHost(h->h_kps), h->h_kps = nullptr;
+    if (h->h_desc) cudaFreeHost(h->h_desc), h->h_desc = nullptr;
+    if (h->h_scalars) cudaFreeHost(h->h_scalars), h->h_scalars = nullptr;
+    h->plan_w = h->plan_h = 0;
+}
+
+// Geometry of one level; returns false if the reference itself cannot process this size (empty FAST grid, nIni = 0).
+static bool level_geometry(const corb_orb* h, int l, int w, int hgt, LevelGeom* L) {
+    memset(L, 0, sizeof(*L));
+    L->w = cv_round_f((float)w * h->inv_scale[l]);  // ORBextractor.cc:1111-1112
+    L->h = cv_round_f((float)hgt * h->inv_scale[l]);
+    L->max_bx = L->w - kEdge + 3;
+    L->max_by = L->h - kEdge + 3;
+    const int width_i = L->max_bx - kBorder, height_i = L->max_by - kBorder;
+    if (width_i < 30 || height_i < 30) return false;
+    const float width = (float)width_i, height = (float)height_i, W = 30;  // :769-787
+    L->n_cols = (int)(width / W);
+    L->n_rows = (int)(height / W);
+    L->w_cell = (int)ceilf(width / L->n_cols);
+    L->h_cell = (int)ceilf(height / L->n_rows);
+    L->slot = ((L->w_cell + 1) / 2) * ((L->h_cell + 1) / 2);
+    L->quota = h->quota[l];
+    L->n_ini = (int)roundf((float)width_i / height_i);  // :543
+    if (L->n_ini < 1) return false;
+    L->h_x = (float)width_i / L->n_ini;
+    L->node_cap = L->quota + 3 > 4 * L->n_ini ? L->quota + 3 : 4 * L->n_ini;
+    L->scale = h->scale[l];
+    L->size = (float)(int)(kPatch * h->scale[l]);  // :837
+    return true;
+}
+
+static int capacity_for(const corb_orb* h, int w, int hgt) {
+    int cap = 0;
+    for (int l = 0; l < h->nlevels; l++) {
+        LevelGeom L;
+        if (!level_geometry(h, l, w, hgt, &L)) return -1;
+        cap += L.node_cap;
+    }
+    return cap;
+}
+
+template <typename T>
+static int dev_alloc(corb_orb* h, T** p, size_t n) {
+    void* q = nullptr;
+    CORB_CUDA(cudaMalloc(&q, n * sizeof(T) + 256));
+    h->dev_allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return CORB_OK;
+}
+
+static int record_graph(corb_orb* h);
+
+static int make_plan(corb_orb* h, int w, int hgt) {
+    if (h->plan_w == w && h->plan_h == hgt) return CORB_OK;
+    CORB_CUDA(cudaSetDevice(h->device));
+    if (h->stream) CORB_CUDA(cudaStreamSynchronize(h->stream));
+    free_plan(h);
+    OrbGeom& g = h->geom;
+    memset(&g, 0, sizeof(g));
+    g.n_levels = h->nlevels;
+    g.ini_th = h->ini_th;
+    g.min_th = h->min_th;
+    size_t img_off = 0;
+    int cell_base = 0, kp_base = 0, xtab = 0, ytab = 0, tiles = 0;
+    long long cand_base = 0;
+    for (int l = 0; l < h->nlevels; l++) {
+        LevelGeom& L = g.lv[l];
+        CORB_CHECK(level_geometry(h, l, w, hgt, &L), CORB_ERR_UNSUPPORTED,
+                   "image %dx%d: pyramid level %d is too small for the 30 px FAST grid", w, hgt, l);
+        CORB_CHECK(L.w <= 32767 && L.h <= 32767 && L.node_cap <= 65535, CORB_ERR_UNSUPPORTED, "image or feature count too large");
+        L.pitch = align_up(L.w, 128);
+        L.img_off = (int)img_off;
+        img_off += (size_t)L.pitch * L.h;
+        L.cell_base = cell_base;
+        cell_base += L.n_cols * L.n_rows;
+        L.cand_base = (int)cand_base;
+        cand_base += (long long)L.n_cols * L.n_rows * L.slot;
+        L.kp_base = kp_base;
+        kp_base += L.node_cap;
+        L.xtab_off = xtab;
+        L.ytab_off = ytab;
+        if (l > 0) { xtab += L.w; ytab += L.h; }
+        L.blur_tile_base = tiles;
+        L.blur_tiles_x = (L.w + 63) / 64;
+        tiles += L.blur_tiles_x * ((L.h + 15) / 16);
+    }
+    CORB_CHECK(img_off < (1u << 30) && cand_base < (1 << 24), CORB_ERR_UNSUPPORTED, "image too large");
+    g.n_cells = cell_base;
+    g.kp_cap = kp_base;
+    g.blur_tiles = tiles;
+    h->pyr_bytes = img_off;
+    h->cand_total = (int)cand_base;
+
+    // resize coefficient tables, built exactly as cv::resize builds them (double -> float -> short)
+    std::vector<int> xofs(xtab + 1), yofs(ytab + 1);
+    std::vector<short2> alpha(xtab + 1), beta(ytab + 1);
+    for (int l = 1; l < h->nlevels; l++) {
+        const LevelGeom &S = g.lv[l - 1], &D = g.lv[l];
+        const double scale_x = 1.0 / ((double)D.w / S.w), scale_y = 1.0 / ((double)D.h / S.h);
+        for (int dx = 0; dx < D.w; dx++) {
+            float fx = (float)((dx + 0.5) * scale_x - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0; sx = 0; }
+            if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+            xofs[D.xtab_off + dx] = sx;
+            alpha[D.xtab_off + dx] = make_short2((short)cv_round_f((1.f - fx) * 2048), (short)cv_round_f(fx * 2048));
+        }
+        for (int dy = 0; dy < D.h; dy++) {
+            float fy = (float)((dy + 0.5) * scale_y - 0.5);
+            int sy = (int)floorf(fy);
+            fy -= sy;
+            yofs[D.ytab_off + dy] = sy;
+            beta[D.ytab_off + dy] = make_short2((short)cv_round_f((1.f - fy) * 2048), (short)cv_round_f(fy * 2048));
+        }
+    }
+
+    OrbBuffers& b = h->buf;
+    memset(&b, 0, sizeof(b));
+    int rc;
+    int *d_xofs, *d_yofs;
+    short2 *d_alpha, *d_beta;
+#define A(ptr, n) if ((rc = dev_alloc(h, &(ptr), (n))) != CORB_OK) return rc
+    A(b.pyr, h->pyr_bytes);
+    A(b.blur, h->pyr_bytes);
+    A(d_xofs, xofs.size());
+    A(d_alpha, alpha.size());
+    A(d_yofs, yofs.size());
+    A(d_beta, beta.size());
+    A(b.cell_count, g.n_cells);
+    A(b.cand_xy, h->cand_total);
+    A(b.cand_r, h->cand_total);
+    A(b.cell_off, g.n_cells);
+    A(b.key_xy, h->cand_total);
+    A(b.key_r, h->cand_total);
+    A(b.key_node, h->cand_total);
+    A(b.lvl_kp, g.kp_cap);
+    A(b.level_count, kMaxLevels);
+    A(b.level_cand, kMaxLevels);
+    A(b.kps, g.kp_cap);
+    A(b.desc, (size_t)g.kp_cap * 32);
+    A(b.count, 1);
+    A(b.status, 1);
+#undef A
+    b.xofs = d_xofs; b.alpha = d_alpha; b.yofs = d_yofs; b.beta = d_beta;
+    CORB_CUDA(cudaMemcpy(d_xofs, xofs.data(), xofs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CORB_CUDA(cudaMemcpy(d_alpha, alpha.data(), alpha.size() * sizeof(short2), cudaMemcpyHostToDevice));
+    CORB_CUDA(cudaMemcpy(d_yofs, yofs.data(), yofs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CORB_CUDA(cudaMemcpy(d_beta, beta.data(), beta.size() * sizeof(short2), cudaMemcpyHostToDevice));
+    CORB_CUDA(cudaMemset(b.pyr, 0, h->pyr_bytes));
+    CORB_CUDA(cudaMemset(b.blur, 0, h->pyr_bytes));
+    CORB_CUDA(cudaMemset(b.status, 0, sizeof(int)));
+    CORB_CUDA(cudaMemset(b.count, 0, sizeof(int)));
+    CORB_CUDA(cudaMemset(b.level_count, 0, kMaxLevels * sizeof(int)));
+    CORB_CUDA(cudaMemset(b.level_cand, 0, kMaxLevels * sizeof(int)));
+
+    CORB_CUDA(cudaMallocHost(&h->h_img, (size_t)w * hgt));
+    CORB_CUDA(cudaMallocHost(&h->h_pyr, h->pyr_bytes));
+    CORB_CUDA(cudaMallocHost(&h->h_kps, sizeof(corb_keypoint) * g.kp_cap));
+    CORB_CUDA(cudaMallocHost(&h->h_desc, (size_t)g.kp_cap * 32));
+    CORB_CUDA(cudaMallocHost(&h->h_scalars, 4 * sizeof(int)));
+
+    // quadtree: keep a level's keys in shared memory when they fit (typical: 2-3 k keys), else global scratch
+    int max_cand_level = 0;
+    for (int l = 0; l < h->nlevels; l++) max_cand_level = std::max(max_cand_level, g.lv[l].n_cols * g.lv[l].n_rows * g.lv[l].slot);
+    h->key_smem_cap = std::min(max_cand_level, 12288);
+    cudaError_t e = prepare_octtree(g, h->key_smem_cap, &h->oct_smem);
+    if (e != cudaSuccess || h->oct_smem > 200 * 1024) {
+        set_error("quadtree kernel needs %d B of shared memory (nfeatures too large?): %s", h->oct_smem, cudaGetErrorString(e));
+        return e != cudaSuccess ? CORB_ERR_CUDA : CORB_ERR_UNSUPPORTED;
+    }
+    h->plan_w = w;
+    h->plan_h = hgt;
+    return record_graph(h);
+}
+
+// One CUDA graph per plan: resize chain -> { FAST cells -> quadtree | Gaussian blur } -> orientation + BRIEF.
+// The blur only depends on the pyramid, so it runs on a forked branch beside the FAST/quadtree critical path.
+static int record_graph(corb_orb* h) {
+    const OrbGeom& g = h->geom;
+    const OrbBuffers& b = h->buf;
+    CORB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    for (int l = 1; l < g.n_levels; l++) launch_resize(g, b, l, h->stream);
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+    launch_blur(g, b, h->stream2);
+    cudaEventRecord(h->ev_join, h->stream2);
+    launch_fast_cells(g, b, h->stream);
+    launch_octtree(g, b, h->key_smem_cap, h->oct_smem, h->stream);
+    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+    launch_orient_desc(g, b, h->stream);
+    CORB_CUDA(cudaStreamEndCapture(h->stream, &h->graph));
+    CORB_CUDA(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+    h->kernel_launches = (g.n_levels - 1) + 4;
+    return CORB_OK;
+}
+
+extern "C" {
+
+const char* corb_last_error(void) { return corb::get_error(); }
+int corb_version(void) { return 100; }
+int corb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int corb_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device, corb_orb** out) {
+    CORB_CHECK(out, CORB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    CORB_CHECK(nfeatures >= 1 && nlevels >= 1 && nlevels <= kMaxLevels && scale_factor > 1.f && ini_th >= 1 && min_th >= 1 &&
+                   ini_th <= 254 && min_th <= 254,
+               CORB_ERR_INVALID, "invalid ORB parameters (nfeatures %d, scale %g, levels %d, FAST %d/%d)", nfeatures,
+               (double)scale_factor, nlevels, ini_th, min_th);
+    int ndev = 0;
+    CORB_CUDA(cudaGetDeviceCount(&ndev));
+    CORB_CHECK(device >= 0 && device < ndev, CORB_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    corb_orb* h = new corb_orb;
+    h->nfeatures = nfeatures; h->nlevels = nlevels; h->ini_th = ini_th; h->min_th = min_th; h->device = device;
+    h->scale_factor_f = scale_factor;
+    h->scale_factor = scale_factor;
+    h->scale.resize(nlevels); h->inv_scale.resize(nlevels); h->sigma2.resize(nlevels); h->inv_sigma2.resize(nlevels);
+    h->scale[0] = 1.f; h->sigma2[0] = 1.f;
+    for (int i = 1; i < nlevels; i++) {
+        h->scale[i] = (float)(h->scale[i - 1] * h->scale_factor);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < nlevels; i++) {
+        h->inv_scale[i] = 1.0f / h->scale[i];
+        h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+    }
+    h->quota.resize(nlevels);
+    const float factor = (float)(1.0f / h->scale_factor);
+    float desired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        h->quota[l] = cv_round_f(desired);
+        sum += h->quota[l];
+        desired *= factor;
+    }
+    h->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    {  // umax (:452-469)
+        int v, v0;
+        const int vmax = (int)floorf(kHalfPatch * sqrtf(2.f) / 2 + 1), vmin = (int)ceilf(kHalfPatch * sqrtf(2.f) / 2);
+        const double hp2 = kHalfPatch * kHalfPatch;
+        for (v = 0; v <= vmax; ++v) h->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+        for (v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+            while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+            h->umax[v] = v0;
+            ++v0;
+        }
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        set_error("CUDA setup on device %d failed: %s", device, cudaGetErrorString(e));
+        corb_orb_destroy(h);
+        return CORB_ERR_CUDA;
+    }
+    *out = h;
+    return CORB_OK;
+}
+
+void corb_orb_destroy(corb_orb* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_plan(h);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int corb_orb_levels(const corb_orb* h) { return h ? h->nlevels : 0; }
+float corb_orb_scale_factor(const corb_orb* h) { return h ? h->scale_factor_f : 0.f; }
+
+int corb_orb_tables(const corb_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* quota, int* umax16) {
+    CORB_CHECK(h, CORB_ERR_INVALID, "handle is NULL");
+    for (int i = 0; i < h->nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->inv_scale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+        if (quota) quota[i] = h->quota[i];
+    }
+    if (umax16) memcpy(umax16, h->umax, sizeof(h->umax));
+    return CORB_OK;
+}
+
+int corb_orb_level_size(const corb_orb* h, int level, int w, int hgt, int* lw, int* lh) {
+    CORB_CHECK(h && level >= 0 && level < h->nlevels && lw && lh, CORB_ERR_INVALID, "bad argument");
+    *lw = cv_round_f((float)w * h->inv_scale[level]);
+    *lh = cv_round_f((float)hgt * h->inv_scale[level]);
+    return CORB_OK;
+}
+
+int corb_orb_capacity(const corb_orb* h, int w, int hgt) {
+    if (!h || w < 1 || hgt < 1) return -1;
+    return capacity_for(h, w, hgt);
+}
+
+static int enqueue_core(corb_orb* h) {
+    CORB_CUDA(cudaGraphLaunch(h->graph_exec, h->stream));
+    return CORB_OK;
+}
+
+int corb_orb_extract_submit(corb_orb* h, const uint8_t* img, int w, int hgt, int stride, int want_pyramid) {
+    CORB_CHECK(h, CORB_ERR_INVALID, "handle is NULL");
+    CORB_CHECK(!h->pending, CORB_ERR_INVALID, "a submitted extraction has not been waited for");
+    if (!img || w < 1 || hgt < 1) {  // empty image: the reference returns silently (ORBextractor.cc:1046)
+        h->pending = true;
+        h->pending_pyr = false;
+        h->pending_empty = true;
+        return CORB_OK;
+    }
+    CORB_CHECK(stride >= w, CORB_ERR_INVALID, "stride %d < width %d", stride, w);
+    CORB_CUDA(cudaSetDevice(h->device));
+    int rc = make_plan(h, w, hgt);
+    if (rc != CORB_OK) return rc;
+    const OrbGeom& g = h->geom;
+    if (stride == w) memcpy(h->h_img, img, (size_t)w * hgt);
+    else for (int y = 0; y < hgt; y++) memcpy(h->h_img + (size_t)y * w, img + (size_t)y * stride, w);
+    CORB_CUDA(cudaMemcpy2DAsync(h->buf.pyr, g.lv[0].pitch, h->h_img, w, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    rc = enqueue_core(h);
+    if (rc != CORB_OK) return rc;
+    CORB_CUDA(cudaMemcpyAsync(h->h_kps, h->buf.kps, sizeof(corb_keypoint) * g.kp_cap, cudaMemcpyDeviceToHost, h->stream));
+    CORB_CUDA(cudaMemcpyAsync(h->h_desc, h->buf.desc, (size_t)g.kp_cap * 32, cudaMemcpyDeviceToHost, h->stream));
+    CORB_CUDA(cudaMemcpyAsync(&h->h_scalars[0], h->buf.count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CORB_CUDA(cudaMemcpyAsync(&h->h_scalars[1], h->buf.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (want_pyramid)
+        CORB_CUDA(cudaMemcpyAsync(h->h_pyr, h->buf.pyr, h->pyr_bytes, cudaMemcpyDeviceToHost, h->stream));
+    h->pending = true;
+    h->pending_pyr = want_pyramid != 0;
+    h->pending_empty = false;
+    return CORB_OK;
+}
+
+int corb_orb_extract_wait(corb_orb* h, corb_keypoint* kps, uint8_t* desc, int* n, uint8_t* const* pyr_out) {
+    CORB_CHECK(h && n, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(h->pending, CORB_ERR_INVALID, "nothing was submitted");
+    h->pending = false;
+    if (h->pending_empty) {
+        *n = 0;
+        return CORB_OK;
+    }
+    CORB_CUDA(cudaSetDevice(h->device));
+    CORB_CUDA(cudaStreamSynchronize(h->stream));
+    CORB_CHECK(h->h_scalars[1] == 0, CORB_ERR_CAPACITY, "device-side consistency check %d failed", h->h_scalars[1]);
+    const int cnt = h->h_scalars[0];
+    CORB_CHECK(cnt >= 0 && cnt <= h->geom.kp_cap, CORB_ERR_CAPACITY, "keypoint count %d out of range", cnt);
+    *n = cnt;
+    if (kps) memcpy(kps, h->h_kps, sizeof(corb_keypoint) * cnt);
+    if (desc) memcpy(desc, h->h_desc, (size_t)cnt * 32);
+    if (pyr_out) {
+        CORB_CHECK(h->pending_pyr, CORB_ERR_INVALID, "pyramid requested at wait but not at submit");
+        for (int l = 0; l < h->nlevels; l++) {
+            if (!pyr_out[l]) continue;
+            const LevelGeom& L = h->geom.lv[l];
+            for (int y = 0; y < L.h; y++) memcpy(pyr_out[l] + (size_t)y * L.w, h->h_pyr + L.img_off + (size_t)y * L.pitch, L.w);
+        }
+    }
+    return CORB_OK;
+}
+
+int corb_orb_extract(corb_orb* h, const uint8_t* img, int w, int hgt, int stride, corb_keypoint* kps, uint8_t* desc, int* n,
+                     uint8_t* const* pyr_out) {
+    int rc = corb_orb_extract_submit(h, img, w, hgt, stride, pyr_out != nullptr);
+    if (rc != CORB_OK) return rc;
+    return corb_orb_extract_wait(h, kps, desc, n, pyr_out);
+}
+
+int corb_orb_extract_device(corb_orb* h, const uint8_t* d_img, int w, int hgt, int stride) {
+    CORB_CHECK(h && d_img && w >= 1 && hgt >= 1 && stride >= w, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(!h->pending, CORB_ERR_INVALID, "a submitted extraction has not been waited for");
+    CORB_CUDA(cudaSetDevice(h->device));
+    int rc = make_plan(h, w, hgt);
+    if (rc != CORB_OK) return rc;
+    CORB_CUDA(cudaMemcpy2DAsync(h->buf.pyr, h->geom.lv[0].pitch, d_img, stride, w, hgt, cudaMemcpyDeviceToDevice, h->stream));
+    return enqueue_core(h);
+}
+
+int corb_orb_sync(corb_orb* h) {
+    CORB_CHECK(h, CORB_ERR_INVALID, "handle is NULL");
+    CORB_CUDA(cudaSetDevice(h->device));
+    CORB_CUDA(cudaStreamSynchronize(h->stream));
+    return CORB_OK;
+}
+
+int corb_orb_device_results(const corb_orb* h, const corb_keypoint** d_kps, const uint8_t** d_desc, const int** d_count) {
+    CORB_CHECK(h && h->plan_w, CORB_ERR_INVALID, "no extraction has run on this handle");
+    if (d_kps) *d_kps = h->buf.kps;
+    if (d_desc) *d_desc = h->buf.desc;
+    if (d_count) *d_count = h->buf.count;
+    return CORB_OK;
+}
+
+int corb_orb_device_level(const corb_orb* h, int level, int blurred, const uint8_t** d_ptr, int* pitch, int* lw, int* lh) {
+    CORB_CHECK(h && h->plan_w && level >= 0 && level < h->nlevels, CORB_ERR_INVALID, "bad argument or no plan");
+    const LevelGeom& L = h->geom.lv[level];
+    if (d_ptr) *d_ptr = (blurred ? h->buf.blur : h->buf.pyr) + L.img_off;
+    if (pitch) *pitch = L.pitch;
+    if (lw) *lw = L.w;
+    if (lh) *lh = L.h;
+    return CORB_OK;
+}
+
+void* corb_orb_stream(const corb_orb* h) { return h ? (void*)h->stream : nullptr; }
+int corb_orb_launches_per_extract(const corb_orb* h) { return h ? h->kernel_launches : 0; }
+
+int corb_orb_tap(corb_orb* h, int what, int level, void* out, size_t out_bytes, int* n) {
+    CORB_CHECK(h && h->plan_w && level >= 0 && level < h->nlevels, CORB_ERR_INVALID, "bad argument or no plan");
+    CORB_CUDA(cudaSetDevice(h->device));
+    CORB_CUDA(cudaStreamSynchronize(h->stream));
+    const LevelGeom& L = h->geom.lv[level];
+    if (what == CORB_TAP_PYRAMID || what == CORB_TAP_BLURRED) {
+        CORB_CHECK(out && out_bytes >= (size_t)L.w * L.h, CORB_ERR_INVALID, "output buffer too small");
+        const uint8_t* src = (what == CORB_TAP_BLURRED ? h->buf.blur : h->buf.pyr) + L.img_off;
+        CORB_CUDA(cudaMemcpy2D(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+        if (n) *n = L.w * L.h;
+        return CORB_OK;
+    }
+    if (what == CORB_TAP_LEVEL_COUNT) {
+        CORB_CHECK(n, CORB_ERR_INVALID, "n is NULL");
+        CORB_CUDA(cudaMemcpy(n, h->buf.level_count + level, sizeof(int), cudaMemcpyDeviceToHost));
+        return CORB_OK;
+    }
+    if (what == CORB_TAP_CANDIDATES) {
+        CORB_CHECK(n, CORB_ERR_INVALID, "n is NULL");
+        const int n_cell = L.n_cols * L.n_rows;
+        std::vector<int> cc(n_cell);
+        CORB_CUDA(cudaMemcpy(cc.data(), h->buf.cell_count + L.cell_base, n_cell * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> xy((size_t)n_cell * L.slot);
+        std::vector<uint8_t> r((size_t)n_cell * L.slot);
+        CORB_CUDA(cudaMemcpy(xy.data(), h->buf.cand_xy + L.cand_base, xy.size() * 4, cudaMemcpyDeviceToHost));
+        CORB_CUDA(cudaMemcpy(r.data(), h->buf.cand_r + L.cand_base, r.size(), cudaMemcpyDeviceToHost));
+        int total = 0;
+        for (int c = 0; c < n_cell; c++) total += cc[c];
+        *n = total;
+        if (!out) return CORB_OK;
+        CORB_CHECK(out_bytes >= (size_t)total * 12, CORB_ERR_INVALID, "output buffer too small for %d candidates", total);
+        int32_t* o = (int32_t*)out;
+        for (int c = 0; c < n_cell; c++)
+            for (int e = 0; e < cc[c]; e++) {
+                const uint32_t v = xy[(size_t)c * L.slot + e];
+                *o++ = v & 0xffff;
+                *o++ = v >> 16;
+                *o++ = r[(size_t)c * L.slot + e];
+            }
+        return CORB_OK;
+    }
+    set_error("unknown tap %d", what);
+    return CORB_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,686 @@
+// ORB front-end kernels for sm_100a: pyramid resize, per-cell FAST-9/16 + NMS + threshold fallback, 7x7 Gaussian,
+// quadtree keypoint distribution, intensity-centroid orientation and steered BRIEF.
+//
+// Semantics follow corbslam_client/src/ORBextractor.cc (reference) and the OpenCV primitives it calls, as pinned by
+// the CPU oracle (oracle/orb_oracle.cpp); every kernel is integer/bit exact against it. The design is not a port:
+// the per-cell cv::FAST calls become one launch over all cells of all levels, the std::list quadtree becomes a
+// level-synchronous array algorithm in one CTA per pyramid level, and descriptors are one warp per keypoint.
+#include "common.cuh"
+#include "orb_kernels.cuh"
+
+namespace corb {
+
+__device__ __align__(16) const int8_t d_pattern[1024] = {
+#include "../../include/corb_brief_pattern.inc"
+};
+// umax of ORBextractor.cc:452-469 for HALF_PATCH_SIZE = 15 (the host recomputes it and checks equality)
+__device__ const int d_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// ------------------------------------------------------------------------------------------------ K1 resize
+// cv::resize INTER_LINEAR u8 (ORBextractor.cc:1120). Coefficient tables are built on the host exactly as OpenCV
+// builds them (double -> float -> short), so the kernel is pure integer arithmetic.
+__global__ void __launch_bounds__(256) k_resize(LevelGeom src, LevelGeom dst, const uint8_t* __restrict__ pyr_src,
+                                                uint8_t* __restrict__ pyr_dst, const int* __restrict__ xofs,
+                                                const short2* __restrict__ alpha, const int* __restrict__ yofs,
+                                                const short2* __restrict__ beta) {
+    const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int dy = blockIdx.y * 8 + threadIdx.y;
+    if (dy >= dst.h || dx0 >= dst.w) return;
+    const int sy = yofs[dy];
+    const int sy0 = min(max(sy, 0), src.h - 1), sy1 = min(max(sy + 1, 0), src.h - 1);
+    const short2 bb = beta[dy];
+    const uint8_t* s0 = pyr_src + (size_t)sy0 * src.pitch;
+    const uint8_t* s1 = pyr_src + (size_t)sy1 * src.pitch;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int dx = dx0 + k;
+        if (dx < dst.w) {
+            const int sx = xofs[dx];
+            const int sx1 = min(sx + 1, src.w - 1);
+            const short2 a = alpha[dx];
+            const int r0 = (int)s0[sx] * a.x + (int)s0[sx1] * a.y;
+            const int r1 = (int)s1[sx] * a.x + (int)s1[sx1] * a.y;
+            const int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
+            packed |= (uint32_t)(v & 0xff) << (8 * k);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(pyr_dst + (size_t)dy * dst.pitch + dx0) = packed;  // pitch % 128 == 0, dx0 % 4 == 0
+}
+
+void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s) {
+    const LevelGeom& src = g.lv[level - 1];
+    const LevelGeom& dst = g.lv[level];
+    dim3 block(32, 8), grid((dst.w + 127) / 128, (dst.h + 7) / 8);
+    k_resize<<<grid, block, 0, s>>>(src, dst, b.pyr + src.img_off, b.pyr + dst.img_off, b.xofs + dst.xtab_off,
+                                    b.alpha + dst.xtab_off, b.yofs + dst.ytab_off, b.beta + dst.ytab_off);
+}
+
+// ------------------------------------------------------------------------------------------------ K2 FAST per cell
+constexpr int kRoiPitch = 68;  // bytes per ROI row in shared memory (>= kCellRoiMax, multiple of 4)
+constexpr int kScDim = 62;     // valid area (<= 60) + 1 px zero border each side
+constexpr int kScPitch = 64;
+
+__device__ __forceinline__ bool run9(uint32_t m) {
+    m |= m << 16;
+    m &= m >> 1;
+    m &= m >> 2;
+    m &= m >> 4;
+    m &= m >> 1;
+    return (m & 0xffffu) != 0;
+}
+
+// FAST-9/16 response (max over the 16 nine-arcs of the arc minimum of |ring - centre|, minus 1) if the pixel is a
+// corner at threshold `th`, else 0.  == cv::FAST's cornerScore for every pixel cv::FAST(th) reports.
+__device__ __forceinline__ int fast_score_dev(const uint8_t* c, int th) {
+    constexpr int P = kRoiPitch;
+    const int v = c[0];
+    int r[16];
+    r[0] = c[3 * P];      r[1] = c[3 * P + 1];   r[2] = c[2 * P + 2];   r[3] = c[P + 3];
+    r[4] = c[3];          r[5] = c[-P + 3];      r[6] = c[-2 * P + 2];  r[7] = c[-3 * P + 1];
+    r[8] = c[-3 * P];     r[9] = c[-3 * P - 1];  r[10] = c[-2 * P - 2]; r[11] = c[-P - 3];
+    r[12] = c[-3];        r[13] = c[P - 3];      r[14] = c[2 * P - 2];  r[15] = c[3 * P - 1];
+    const int hi = v + th, lo = v - th;
+    uint32_t mb = 0, md = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mb |= (uint32_t)(r[k] > hi) << k;
+        md |= (uint32_t)(r[k] < lo) << k;
+    }
+    const bool bright = run9(mb);
+    if (!bright && !run9(md)) return 0;
+    // a bright and a dark nine-arc cannot coexist (9 + 9 > 16), so only one sign can produce a positive arc minimum
+    int e[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) e[k] = bright ? r[k] - v : v - r[k];
+    int m2[16], m4[16], m8[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m2[k] = min(e[k], e[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) m8[k] = min(m4[k], m4[(k + 4) & 15]);
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) best = max(best, min(m8[k], e[(k + 8) & 15]));
+    return best - 1;
+}
+
+// exclusive scan of one int per thread over the block (thread order); *total gets the block sum
+__device__ __forceinline__ int block_scan_values(int v, int* warp_tmp, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < nw ? warp_tmp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        warp_tmp[lane] = w;
+    }
+    __syncthreads();
+    const int base = wid ? warp_tmp[wid - 1] : 0;
+    *total = warp_tmp[nw - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+// One CTA per grid cell of ComputeKeyPointsOctTree (ORBextractor.cc:789-832), all levels in one launch.
+// The cell's ROI (wCell+6 x hCell+6) is staged in shared memory; FAST ignores a 3 px rim, so the valid areas of
+// neighbouring cells tile the level disjointly and NMS sees zeros outside its own cell, exactly like cv::FAST on the
+// ROI. The iniTh -> minTh fallback is decided per cell on the post-NMS count.
+__global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const uint8_t* __restrict__ pyr, int* __restrict__ cell_count,
+                                                    uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_r,
+                                                    int* __restrict__ status) {
+    __shared__ __align__(16) uint8_t roi[kCellRoiMax * kRoiPitch];
+    __shared__ __align__(16) uint8_t sc[kScDim * kScPitch];
+    __shared__ int warp_tmp[33];
+    const int tid = threadIdx.x;
+    const int cell = blockIdx.x;
+    int l = 0;
+    while (l + 1 < g.n_levels && cell >= g.lv[l + 1].cell_base) l++;
+    const LevelGeom L = g.lv[l];
+    const int c = cell - L.cell_base;
+    const int ci = c / L.n_cols, cj = c - ci * L.n_cols;
+    const int iniX = kBorder + cj * L.w_cell, iniY = kBorder + ci * L.h_cell;
+    const int maxX = min(iniX + L.w_cell + 6, L.max_bx), maxY = min(iniY + L.h_cell + 6, L.max_by);
+    const int rw = maxX - iniX, rh = maxY - iniY;
+    const int vw = rw - 6, vh = rh - 6;
+    if (vw <= 0 || vh <= 0) {  // covers the reference's skip rules (:795,:803) and ROIs cv::FAST cannot process
+        if (tid == 0) cell_count[cell] = 0;
+        return;
+    }
+    const uint8_t* src = pyr + L.img_off + (size_t)iniY * L.pitch + iniX;
+    for (int i = tid; i < rw * rh; i += 256) {
+        const int y = i / rw, x = i - y * rw;
+        roi[y * kRoiPitch + x] = src[(size_t)y * L.pitch + x];
+    }
+    for (int i = tid; i < kScDim * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    __syncthreads();
+    const int th_lo = min(g.ini_th, g.min_th);
+    const int npx = vw * vh;
+    for (int p = tid; p < npx; p += 256) {
+        const int y = p / vw, x = p - y * vw;
+        const int s = fast_score_dev(roi + (y + 3) * kRoiPitch + (x + 3), th_lo);
+        sc[(y + 1) * kScPitch + (x + 1)] = (uint8_t)s;
+    }
+    __syncthreads();
+    // strict 8-neighbour maxima of the (masked) score tile, this thread's contiguous raster chunk (<= 15 px)
+    const int chunk = (npx + 255) / 256;
+    const int p0 = tid * chunk, p1 = min(p0 + chunk, npx);
+    uint32_t m_ini = 0, m_min = 0;
+    for (int p = p0; p < p1; p++) {
+        const int y = p / vw, x = p - y * vw;
+        const uint8_t* q = sc + (y + 1) * kScPitch + (x + 1);
+        const int s = q[0];
+        if (s == 0) continue;
+        const bool mx = s > q[-kScPitch - 1] && s > q[-kScPitch] && s > q[-kScPitch + 1] && s > q[-1] && s > q[1] &&
+                        s > q[kScPitch - 1] && s > q[kScPitch] && s > q[kScPitch + 1];
+        if (mx) {
+            if (s >= g.ini_th) m_ini |= 1u << (p - p0);
+            if (s >= g.min_th) m_min |= 1u << (p - p0);
+        }
+    }
+    const int any_ini = __syncthreads_or(m_ini != 0);
+    const uint32_t m = any_ini ? m_ini : m_min;
+    int total;
+    int pos = block_scan_values(__popc(m), warp_tmp, &total);
+    if (total > L.slot) {  // impossible for strict 8-neighbour maxima; never truncate silently
+        if (tid == 0) { atomicExch(status, 101); cell_count[cell] = 0; }
+        return;
+    }
+    const int base = L.cand_base + c * L.slot;
+    for (int p = p0; p < p1; p++) {
+        if (m >> (p - p0) & 1u) {
+            const int y = p / vw, x = p - y * vw;
+            // coordinates relative to (minBorderX, minBorderY): FAST's ROI coordinate + j*wCell (:822-823)
+            cand_xy[base + pos] = (uint32_t)(x + 3 + cj * L.w_cell) | (uint32_t)(y + 3 + ci * L.h_cell) << 16;
+            cand_r[base + pos] = sc[(y + 1) * kScPitch + (x + 1)];
+            pos++;
+        }
+    }
+    if (tid == 0) cell_count[cell] = total;
+}
+
+void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
+    k_fast_cells<<<g.n_cells, 256, 0, s>>>(g, b.pyr, b.cell_count, b.cand_xy, b.cand_r, b.status);
+}
+
+// ------------------------------------------------------------------------------------------------ K5 Gaussian 7x7
+// cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on u8 (ORBextractor.cc:1086): fixed-point taps
+// {18,34,48,56,48,34,18}/256 on both axes, exact accumulation, one rounding (s + 2^15) >> 16.
+constexpr int kBlurTW = 64, kBlurTH = 16;
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * (n - 1) - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+    __shared__ uint8_t in[kBlurTH + 6][kBlurTW + 8];
+    __shared__ uint16_t hb[kBlurTH + 6][kBlurTW];
+    const int tid = threadIdx.x;
+    int l = 0;
+    while (l + 1 < g.n_levels && (int)blockIdx.x >= g.lv[l + 1].blur_tile_base) l++;
+    const LevelGeom L = g.lv[l];
+    const int t = blockIdx.x - L.blur_tile_base;
+    const int ty = t / L.blur_tiles_x, tx = t - ty * L.blur_tiles_x;
+    const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
+    const uint8_t* src = pyr + L.img_off;
+    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
+        const int yy = i / (kBlurTW + 6), xx = i - yy * (kBlurTW + 6);
+        const int gy = reflect101(min(max(y0 + yy - 3, -3), L.h + 2), L.h);
+        const int gx = reflect101(min(max(x0 + xx - 3, -3), L.w + 2), L.w);
+        in[yy][xx] = src[(size_t)gy * L.pitch + gx];
+    }
+    __syncthreads();
+    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
+        const int yy = i / kBlurTW, xx = i - yy * kBlurTW;
+        const uint8_t* p = &in[yy][xx];
+        hb[yy][xx] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    const int lx = (tid & 15) * 4, ly = tid >> 4;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gy < L.h && gx < L.w) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = lx + k;
+            const uint32_t acc = 18u * ((uint32_t)hb[ly][x] + hb[ly + 6][x]) + 34u * ((uint32_t)hb[ly + 1][x] + hb[ly + 5][x]) +
+                                 48u * ((uint32_t)hb[ly + 2][x] + hb[ly + 4][x]) + 56u * (uint32_t)hb[ly + 3][x];
+            packed |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(blur + L.img_off + (size_t)gy * L.pitch + gx) = packed;
+    }
+}
+
+void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
+    k_blur<<<g.blur_tiles, 256, 0, s>>>(g, b.pyr, b.blur);
+}
+
+// ------------------------------------------------------------------------------------------------ K3 quadtree
+// DistributeOctTree (ORBextractor.cc:539-763) as a level-synchronous array algorithm, one CTA per pyramid level.
+//
+// The reference keeps a std::list of nodes; every split pushes the non-empty children to the front (n1..n4) and
+// erases the parent. Storing nodes *in list order* makes the list implicit: after a step in which the processed
+// parents create T children in creation order 0..T-1, child j sits at position T-1-j and every unprocessed node
+// keeps its relative order behind them. A step therefore is: count keys per (node, quadrant) with shared-memory
+// atomics, scan, scatter. The near-quota phase (:660-733) sorts the freshly created expandable nodes by
+// (count, address) and splits from the back until the list reaches N; nodes created in one step have addresses
+// in creation order (canonical tie-break), i.e. reverse list position, so its processing order is
+// (count descending, position ascending) and the early stop is the first prefix whose size reaches N.
+constexpr int kOctThreads = 512;
+
+struct OctLayout {
+    int cntA, cntB, bndA, bndB, cc, procpos, scan, crank, krank, fresh, candf, warp_tmp, sh, keys_xy, keys_node, keys_r, total;
+};
+__host__ __device__ inline OctLayout oct_layout(int NC, int key_cap) {
+    OctLayout o;
+    int p = 0;
+    o.cntA = p; p += 4 * NC;
+    o.cntB = p; p += 4 * NC;
+    o.bndA = p; p += 8 * NC;
+    o.bndB = p; p += 8 * NC;
+    o.cc = p; p += 16 * NC;
+    o.procpos = p; p += 4 * NC;
+    o.scan = p; p += 4 * NC;
+    o.crank = p; p += 4 * NC;
+    o.krank = p; p += 4 * NC;
+    o.fresh = p; p += 2 * ((NC + 3) & ~3);  // fresh A and B
+    o.candf = p; p += (NC + 3) & ~3;
+    o.warp_tmp = p; p += 4 * 36;
+    o.sh = p; p += 4 * 8;
+    p = (p + 15) & ~15;
+    o.keys_xy = p; p += 4 * key_cap;
+    o.keys_node = p; p += 2 * ((key_cap + 1) & ~1);
+    o.keys_r = p; p += (key_cap + 3) & ~3;
+    o.total = (p + 15) & ~15;
+    return o;
+}
+
+int octtree_smem_bytes(const OrbGeom& g, int level, int key_smem_cap) {
+    return oct_layout(g.lv[level].node_cap, key_smem_cap).total;
+}
+
+__device__ __forceinline__ int quadrant_of(uint32_t xy, short4 b) {
+    const int x = xy & 0xffff, y = xy >> 16;
+    const int xm = b.x + ((b.z - b.x + 1) >> 1);  // UL.x + ceil((UR.x-UL.x)/2)   (:483)
+    const int ym = b.y + ((b.w - b.y + 1) >> 1);
+    return (x < xm ? 0 : 1) + (y < ym ? 0 : 2);   // n1,n2,n3,n4 (:511-524)
+}
+__device__ __forceinline__ short4 child_bounds(short4 b, int q) {
+    const short xm = (short)(b.x + ((b.z - b.x + 1) >> 1));
+    const short ym = (short)(b.y + ((b.w - b.y + 1) >> 1));
+    short4 c;
+    c.x = (q & 1) ? xm : b.x;
+    c.z = (q & 1) ? b.z : xm;
+    c.y = (q & 2) ? ym : b.y;
+    c.w = (q & 2) ? b.w : ym;
+    return c;
+}
+
+__global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b, int key_smem_cap) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int l = blockIdx.x;
+    const LevelGeom L = g.lv[l];
+    const int NC = L.node_cap, N = L.quota;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const OctLayout lay = oct_layout(NC, key_smem_cap);
+    int* cnt_cur = reinterpret_cast<int*>(smem + lay.cntA);
+    int* cnt_nxt = reinterpret_cast<int*>(smem + lay.cntB);
+    short4* bnd_cur = reinterpret_cast<short4*>(smem + lay.bndA);
+    short4* bnd_nxt = reinterpret_cast<short4*>(smem + lay.bndB);
+    int* cc = reinterpret_cast<int*>(smem + lay.cc);
+    int* procpos = reinterpret_cast<int*>(smem + lay.procpos);
+    int* scan = reinterpret_cast<int*>(smem + lay.scan);
+    int* crank = reinterpret_cast<int*>(smem + lay.crank);
+    int* krank = reinterpret_cast<int*>(smem + lay.krank);
+    uint8_t* fresh_cur = smem + lay.fresh;
+    uint8_t* fresh_nxt = fresh_cur + ((NC + 3) & ~3);
+    uint8_t* candf = smem + lay.candf;
+    int* warp_tmp = reinterpret_cast<int*>(smem + lay.warp_tmp);
+    volatile int* sh = reinterpret_cast<int*>(smem + lay.sh);
+
+    // ---- gather the level's candidates in the order vToDistributeKeys is built: cell row, cell column, raster
+    const int n_cell = L.n_cols * L.n_rows;
+    int* cell_off = b.cell_off + L.cell_base;
+    for (int i = tid; i < n_cell; i += nt) cell_off[i] = b.cell_count[L.cell_base + i];
+    __syncthreads();
+    const int M = block_excl_scan(cell_off, n_cell, warp_tmp);
+    uint32_t* kxy;
+    uint16_t* knode;
+    uint8_t* kr;
+    if (M <= key_smem_cap) {
+        kxy = reinterpret_cast<uint32_t*>(smem + lay.keys_xy);
+        knode = reinterpret_cast<uint16_t*>(smem + lay.keys_node);
+        kr = smem + lay.keys_r;
+    } else {
+        kxy = b.key_xy + L.cand_base;
+        knode = b.key_node + L.cand_base;
+        kr = b.key_r + L.cand_base;
+    }
+    {
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        for (int c = wid; c < n_cell; c += nw) {
+            const int n = b.cell_count[L.cell_base + c], off = cell_off[c];
+            const int src = L.cand_base + c * L.slot;
+            for (int e = lane; e < n; e += 32) {
+                kxy[off + e] = b.cand_xy[src + e];
+                kr[off + e] = b.cand_r[src + e];
+            }
+        }
+    }
+    if (tid == 0) b.level_cand[l] = M;
+    // ---- initial nodes (:542-589)
+    for (int i = tid; i < 4 * NC; i += nt) cc[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < M; k += nt) {
+        const int ni = (int)__fdiv_rn((float)(kxy[k] & 0xffff), L.h_x);
+        knode[k] = (uint16_t)ni;
+        atomicAdd(&cc[ni], 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < L.n_ini; i += nt) scan[i] = cc[i] > 0;
+    __syncthreads();
+    int s = block_excl_scan(scan, L.n_ini, warp_tmp);
+    for (int i = tid; i < L.n_ini; i += nt) {
+        if (cc[i] > 0) {
+            const int p = scan[i];
+            cnt_cur[p] = cc[i];
+            short4 bb;
+            bb.x = (short)(int)__fmul_rn(L.h_x, (float)i);
+            bb.z = (short)(int)__fmul_rn(L.h_x, (float)(i + 1));
+            bb.y = 0;
+            bb.w = (short)(L.max_by - kBorder);
+            bnd_cur[p] = bb;
+            fresh_cur[p] = 0;
+        }
+    }
+    for (int k = tid; k < M; k += nt) knode[k] = (uint16_t)scan[knode[k]];
+    __syncthreads();
+
+    bool finish = false, final_phase = false;
+    int guard = 0;
+    while (!finish) {
+        if (++guard > 4096) {
+            if (tid == 0) atomicExch(b.status, 102);
+            break;
+        }
+        const int prev = s;
+        // ---- processing order
+        int m;
+        if (!final_phase) {
+            for (int i = tid; i < s; i += nt) {
+                const int f = cnt_cur[i] > 1;
+                scan[i] = f;
+                candf[i] = (uint8_t)f;
+            }
+            __syncthreads();
+            m = block_excl_scan(scan, s, warp_tmp);
+            for (int i = tid; i < s; i += nt)
+                if (candf[i]) procpos[scan[i]] = i;
+        } else {
+            for (int i = tid; i < s; i += nt) {
+                const int f = fresh_cur[i] && cnt_cur[i] > 1;
+                scan[i] = f;
+                candf[i] = (uint8_t)f;
+            }
+            __syncthreads();
+            m = block_excl_scan(scan, s, warp_tmp);
+            for (int i = tid; i < s; i += nt)
+                if (candf[i]) krank[scan[i]] = i;  // candidates in position order (temporary)
+            __syncthreads();
+            for (int i = tid; i < m; i += nt) {
+                const int ci = cnt_cur[krank[i]];
+                int rank = 0;
+                for (int j = 0; j < m; j++) {
+                    const int cj = cnt_cur[krank[j]];
+                    rank += (cj > ci) || (cj == ci && j < i);
+                }
+                procpos[rank] = krank[i];
+            }
+        }
+        for (int i = tid; i < 4 * s; i += nt) cc[i] = 0;
+        for (int i = tid; i < s; i += nt) crank[i] = -1;
+        if (tid == 0) { sh[0] = m; sh[1] = 0; sh[2] = 0; }
+        __syncthreads();
+        // ---- keys per (node, quadrant)
+        for (int k = tid; k < M; k += nt) {
+            const int nd = knode[k];
+            if (candf[nd]) atomicAdd(&cc[nd * 4 + quadrant_of(kxy[k], bnd_cur[nd])], 1);
+        }
+        __syncthreads();
+        for (int r = tid; r < m; r += nt) {
+            const int* c4 = cc + procpos[r] * 4;
+            scan[r] = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0) - 1;
+        }
+        __syncthreads();
+        block_excl_scan(scan, m, warp_tmp);
+        if (final_phase) {  // first prefix whose list size reaches N (:728-729)
+            for (int r = tid; r < m; r += nt) {
+                const int* c4 = cc + procpos[r] * 4;
+                const int inc = scan[r] + (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0) - 1;
+                if (s + inc >= N && s + scan[r] < N) sh[0] = r + 1;
+            }
+            __syncthreads();
+        }
+        const int mproc = sh[0];
+        for (int r = tid; r < mproc; r += nt) {
+            const int nd = procpos[r];
+            crank[nd] = scan[r] + r;
+            if (r == mproc - 1) {
+                const int* c4 = cc + nd * 4;
+                sh[1] = scan[r] + r + (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+            }
+        }
+        __syncthreads();
+        const int T = sh[1];
+        for (int i = tid; i < s; i += nt) scan[i] = crank[i] < 0;
+        __syncthreads();
+        const int K = block_excl_scan(scan, s, warp_tmp);
+        if (T + K > NC) {  // cannot happen (list size is bounded by max(N + 2, 4 nIni)); never write out of bounds
+            if (tid == 0) atomicExch(b.status, 103);
+            s = 0;
+            break;
+        }
+        // ---- new list: children in reverse creation order, then the unprocessed nodes in their old order
+        int n_expand = 0;
+        for (int i = tid; i < s; i += nt) {
+            if (crank[i] >= 0) {
+                const short4 pb = bnd_cur[i];
+                int idx = crank[i];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int c = cc[i * 4 + q];
+                    if (c > 0) {
+                        const int np = T - 1 - idx;
+                        cnt_nxt[np] = c;
+                        bnd_nxt[np] = child_bounds(pb, q);
+                        fresh_nxt[np] = 1;
+                        n_expand += c > 1;
+                        idx++;
+                    }
+                }
+            } else {
+                const int np = T + scan[i];
+                cnt_nxt[np] = cnt_cur[i];
+                bnd_nxt[np] = bnd_cur[i];
+                fresh_nxt[np] = 0;
+                krank[i] = np;
+            }
+        }
+        if (n_expand) atomicAdd((int*)&sh[2], n_expand);
+        __syncthreads();
+        for (int k = tid; k < M; k += nt) {
+            const int nd = knode[k];
+            int np;
+            if (crank[nd] >= 0) {
+                const int q = quadrant_of(kxy[k], bnd_cur[nd]);
+                const int* c4 = cc + nd * 4;
+                int rank = 0;
+                if (q > 0) rank += c4[0] > 0;
+                if (q > 1) rank += c4[1] > 0;
+                if (q > 2) rank += c4[2] > 0;
+                np = T - 1 - (crank[nd] + rank);
+            } else {
+                np = krank[nd];
+            }
+            knode[k] = (uint16_t)np;
+        }
+        __syncthreads();
+        const int n_to_expand = sh[2];
+        { int* t = cnt_cur; cnt_cur = cnt_nxt; cnt_nxt = t; }
+        { short4* t = bnd_cur; bnd_cur = bnd_nxt; bnd_nxt = t; }
+        { uint8_t* t = fresh_cur; fresh_cur = fresh_nxt; fresh_nxt = t; }
+        s = T + K;
+        __syncthreads();
+        // ---- termination (:647-733)
+        if (s >= N || s == prev) finish = true;
+        else if (!final_phase && s + 3 * n_to_expand > N) final_phase = true;
+    }
+    // ---- keep the max-response key of every node, first in candidate order on ties (:738-757)
+    uint32_t* best = reinterpret_cast<uint32_t*>(cc);
+    for (int i = tid; i < s; i += nt) best[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < M; k += nt) atomicMax(&best[knode[k]], (uint32_t)kr[k] << 24 | (0xffffffu - (uint32_t)k));
+    __syncthreads();
+    for (int i = tid; i < s; i += nt) {
+        const int k = (int)(0xffffffu - (best[i] & 0xffffffu));
+        const uint32_t xy = kxy[k];
+        b.lvl_kp[L.kp_base + i] = make_uint2(((xy & 0xffff) + kBorder) | ((xy >> 16) + kBorder) << 16, kr[k]);
+    }
+    if (tid == 0) b.level_count[l] = s;
+}
+
+cudaError_t prepare_octtree(const OrbGeom& g, int key_smem_cap, int* smem_bytes_out) {
+    int bytes = 0;
+    for (int l = 0; l < g.n_levels; l++) bytes = max(bytes, octtree_smem_bytes(g, l, key_smem_cap));
+    *smem_bytes_out = bytes;
+    return cudaFuncSetAttribute(k_octtree, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int key_smem_cap, int smem_bytes, cudaStream_t s) {
+    k_octtree<<<g.n_levels, kOctThreads, smem_bytes, s>>>(g, b, key_smem_cap);
+}
+
+// ------------------------------------------------------------------------------------------------ K4 + K6
+// fastAtan2 (OpenCV scalar atan_f32): float32, evaluated without FMA contraction.
+__device__ __forceinline__ float fast_atan2_dev(float y, float x) {
+    const float scale = (float)(180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale, p5 = 0.1555786518463281f * scale,
+                p7 = -0.04432655554792128f * scale;  // folded at compile time in float, like the host compiler does
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// One warp per kept keypoint: IC_Angle on the un-blurred level (ORBextractor.cc:77-104), then the 256 steered BRIEF
+// tests on the blurred level (:107-146), then the epilogue of operator() (:1092-1101, :837-847).
+__global__ void __launch_bounds__(256) k_orient_desc(OrbGeom g, OrbBuffers b) {
+    __shared__ int8_t pat[1024];
+    for (int i = threadIdx.x; i < 256; i += 256) reinterpret_cast<int*>(pat)[i] = reinterpret_cast<const int*>(d_pattern)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wslot = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (wslot == 0 && lane == 0) {
+        int tot = 0;
+        for (int l = 0; l < g.n_levels; l++) tot += b.level_count[l];
+        *b.count = tot;
+    }
+    if (wslot >= g.kp_cap) return;
+    int l = 0, out_base = 0;
+    while (l + 1 < g.n_levels && wslot >= g.lv[l + 1].kp_base) {
+        out_base += b.level_count[l];
+        l++;
+    }
+    const LevelGeom L = g.lv[l];
+    const int pos = wslot - L.kp_base;
+    if (pos >= b.level_count[l]) return;
+    const uint2 kp = b.lvl_kp[wslot];
+    const int X = kp.x & 0xffff, Y = kp.x >> 16;
+    // ---- orientation: lane = column u in [-15,15]; pixel (u,v) is in the disc iff |u| <= umax[|v|]
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - kHalfPatch;
+        const uint8_t* c = b.pyr + L.img_off + (size_t)Y * L.pitch + X + u;
+        const int au = abs(u);
+#pragma unroll
+        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+            if (au <= d_umax[v < 0 ? -v : v]) {
+                const int val = c[v * L.pitch];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_dev((float)m01, (float)m10);
+    // ---- descriptor: lane = output byte; contract: cos/sin in double, rounded to float
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float rad = __fmul_rn(angle, factorPI);
+    const float ca = (float)cos((double)rad), sa = (float)sin((double)rad);
+    const uint8_t* cb = b.blur + L.img_off + (size_t)Y * L.pitch + X;
+    const int8_t* pp = pat + lane * 32;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int t[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const float px = (float)pp[(2 * k + j) * 2], py = (float)pp[(2 * k + j) * 2 + 1];
+            const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca)));
+            const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, ca), __fmul_rn(py, sa)));
+            t[j] = cb[iy * L.pitch + ix];
+        }
+        val |= (t[0] < t[1]) << k;
+    }
+    const int out = out_base + pos;
+    b.desc[(size_t)out * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        corb_keypoint o;
+        o.x = (float)X;
+        o.y = (float)Y;
+        if (l != 0) {
+            o.x = __fmul_rn(o.x, L.scale);
+            o.y = __fmul_rn(o.y, L.scale);
+        }
+        o.size = L.size;
+        o.angle = angle;
+        o.response = (float)kp.y;
+        o.octave = l;
+        o.class_id = -1;
+        b.kps[out] = o;
+    }
+}
+
+void launch_orient_desc(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
+    k_orient_desc<<<(g.kp_cap + 7) / 8, 256, 0, s>>>(g, b);
+}
+
+}  // namespace corb

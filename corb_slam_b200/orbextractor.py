@@ -1,0 +1,156 @@
+"""Host-side mirror of ORB_SLAM2::ORBextractor (reference: corbslam_client/include/ORBextractor.h:45-112) over the
+C ABI of libcorb_b200.so. Same constructor arguments, same call semantics, same getters; `mvImagePyramid` is filled
+on request (the reference exposes it as a public member that Frame::ComputeStereoMatches reads, Frame.cc:477).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, check, lib
+
+
+class ORBextractor:
+    HARRIS_SCORE = 0
+    FAST_SCORE = 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        h = C.c_void_p()
+        check(lib().corb_orb_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST),
+                                    int(device), C.byref(h)))
+        self._h = h
+        self.nlevels = int(nlevels)
+        n = self.nlevels
+        self._scale = np.empty(n, np.float32)
+        self._inv_scale = np.empty(n, np.float32)
+        self._sigma2 = np.empty(n, np.float32)
+        self._inv_sigma2 = np.empty(n, np.float32)
+        self.mnFeaturesPerLevel = np.empty(n, np.int32)
+        self.umax = np.empty(16, np.int32)
+        p = lambda a, t: a.ctypes.data_as(t)
+        check(lib().corb_orb_tables(h, p(self._scale, _lib.f32p), p(self._inv_scale, _lib.f32p), p(self._sigma2, _lib.f32p),
+                                    p(self._inv_sigma2, _lib.f32p), p(self.mnFeaturesPerLevel, _lib.i32p),
+                                    p(self.umax, _lib.i32p)))
+        self.mvImagePyramid = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().corb_orb_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # ---- getters (ORBextractor.h:63-85)
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return lib().corb_orb_scale_factor(self._h)
+
+    def GetScaleFactors(self):
+        return self._scale.copy()
+
+    def GetInverseScaleFactors(self):
+        return self._inv_scale.copy()
+
+    def GetScaleSigmaSquares(self):
+        return self._sigma2.copy()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._inv_sigma2.copy()
+
+    def level_size(self, level, w, h):
+        lw, lh = C.c_int32(), C.c_int32()
+        check(lib().corb_orb_level_size(self._h, level, w, h, C.byref(lw), C.byref(lh)))
+        return lw.value, lh.value
+
+    def capacity(self, w, h):
+        return lib().corb_orb_capacity(self._h, w, h)
+
+    # ---- operator() (ORBextractor.cc:1043-1105)
+    def submit(self, image, want_pyramid=False):
+        if image is None or image.size == 0:
+            self._shape = None
+            check(lib().corb_orb_extract_submit(self._h, None, 0, 0, 0, 0))
+            return
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise TypeError("image must be a 2-D uint8 array (CV_8UC1)")  # the reference asserts (:1050)
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        self._keep = image
+        self._shape = image.shape
+        self._want_pyr = bool(want_pyramid)
+        check(lib().corb_orb_extract_submit(self._h, image.ctypes.data, image.shape[1], image.shape[0], image.strides[0],
+                                            int(self._want_pyr)))
+
+    def wait(self):
+        if self._shape is None:
+            n = C.c_int32()
+            check(lib().corb_orb_extract_wait(self._h, None, None, C.byref(n), None))
+            self.mvImagePyramid = []
+            return np.zeros(0, KP_DTYPE), None  # descriptors.release() (:1064-1065)
+        h, w = self._shape
+        cap = self.capacity(w, h)
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int32()
+        pyr_ptrs = None
+        if self._want_pyr:
+            pyr = [np.empty(self.level_size(l, w, h)[::-1], np.uint8) for l in range(self.nlevels)]
+            pyr_ptrs = (C.c_void_p * self.nlevels)(*[a.ctypes.data for a in pyr])
+        check(lib().corb_orb_extract_wait(self._h, kps.ctypes.data, desc.ctypes.data, C.byref(n), pyr_ptrs))
+        if self._want_pyr:
+            self.mvImagePyramid = pyr
+        self._keep = None
+        if n.value == 0:
+            return kps[:0], None
+        return kps[:n.value], desc[:n.value]
+
+    def __call__(self, image, mask=None, want_pyramid=False):
+        """Returns (keypoints, descriptors): a structured array with cv::KeyPoint's fields and an (N,32) uint8 array
+        (None when no keypoint was found, mirroring `_descriptors.release()`). `mask` is ignored like in the reference."""
+        self.submit(image, want_pyramid)
+        return self.wait()
+
+    # ---- device-resident path (inputs already in HBM)
+    def extract_device(self, d_ptr, w, h, stride):
+        check(lib().corb_orb_extract_device(self._h, int(d_ptr), w, h, stride))
+
+    def sync(self):
+        check(lib().corb_orb_sync(self._h))
+
+    def stream(self):
+        return lib().corb_orb_stream(self._h)
+
+    def launches_per_extract(self):
+        return lib().corb_orb_launches_per_extract(self._h)
+
+    def device_results(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().corb_orb_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    # ---- stage taps for parity tests
+    def tap_image(self, level, blurred=False):
+        h, w = self._last_shape()
+        lw, lh = self.level_size(level, w, h)
+        out = np.empty((lh, lw), np.uint8)
+        check(lib().corb_orb_tap(self._h, 1 if blurred else 0, level, out.ctypes.data, out.nbytes, None))
+        return out
+
+    def tap_candidates(self, level):
+        n = C.c_int32()
+        check(lib().corb_orb_tap(self._h, 2, level, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 3), np.int32)
+        check(lib().corb_orb_tap(self._h, 2, level, out.ctypes.data, out.nbytes, C.byref(n)))
+        return out[:n.value]
+
+    def tap_level_count(self, level):
+        n = C.c_int32()
+        check(lib().corb_orb_tap(self._h, 3, level, None, 0, C.byref(n)))
+        return n.value
+
+    def _last_shape(self):
+        if getattr(self, "_shape", None) is None:
+            raise RuntimeError("no extraction has run")
+        return self._shape

@@ -1,0 +1,104 @@
+"""GPU parity of the ORB front end against the CPU oracle, stage by stage and end to end (bit-exact)."""
+import numpy as np
+import pytest
+
+import oracle
+from corb_slam_b200 import ORBextractor
+from corb_slam_b200.synth import stereo_frame
+
+pytestmark = pytest.mark.gpu
+
+PARAMS = (2000, 1.2, 8, 20, 7)  # KITTI00-02.yaml:38-51
+
+
+def _compare(img, params=PARAMS, stages=True):
+    ora = oracle.OrbExtractor(*params)
+    gpu = ORBextractor(*params)
+    okp, odesc = ora(img)
+    gkp, gdesc = gpu(img, want_pyramid=True)
+    h, w = img.shape
+    if stages:
+        for l in range(params[2]):
+            np.testing.assert_array_equal(gpu.tap_image(l), ora.pyramid(l), err_msg="pyramid level %d" % l)
+            np.testing.assert_array_equal(gpu.mvImagePyramid[l], ora.pyramid(l), err_msg="host pyramid level %d" % l)
+            np.testing.assert_array_equal(gpu.tap_candidates(l), ora.candidates(l), err_msg="candidates level %d" % l)
+            assert gpu.tap_level_count(l) == ora.level_count(l), "kept keypoints level %d" % l
+            ob = ora.blurred(l)
+            if ob is not None:
+                np.testing.assert_array_equal(gpu.tap_image(l, blurred=True), ob, err_msg="blurred level %d" % l)
+    assert len(gkp) == len(okp)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        np.testing.assert_array_equal(gkp[f], okp[f], err_msg=f)
+    np.testing.assert_array_equal(gkp["angle"].view(np.uint32), okp["angle"].view(np.uint32), err_msg="angle bits")
+    if len(okp):
+        np.testing.assert_array_equal(gdesc, odesc)
+    else:
+        assert gdesc is None
+    gpu.close()
+    return len(gkp)
+
+
+@pytest.mark.parametrize("seed", [1234, 1235, 1236])
+def test_synthetic_frames_bit_exact(seed):
+    left, right = stereo_frame(seed)
+    assert _compare(left) >= 2000
+    assert _compare(right, stages=False) >= 2000
+
+
+@pytest.mark.parametrize("size", [(1241, 376), (1226, 370), (640, 480), (752, 480)])
+def test_other_sizes(size):
+    left, _ = stereo_frame(7, w=size[0], h=size[1])
+    _compare(left)
+
+
+def test_noise_image_many_candidates():
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (375, 1242), dtype=np.uint8)
+    _compare(img)
+
+
+def test_flat_image_no_keypoints():
+    img = np.full((375, 1242), 77, np.uint8)
+    assert _compare(img) == 0
+
+
+def test_low_texture_threshold_fallback():
+    left, _ = stereo_frame(11)
+    img = (left.astype(np.int32) // 6 + 100).astype(np.uint8)  # contrast low enough that most cells need minThFAST
+    _compare(img)
+
+
+def test_few_features_and_levels():
+    left, _ = stereo_frame(5, w=640, h=480)
+    _compare(left, params=(300, 1.2, 4, 20, 7))
+    _compare(left, params=(1000, 1.5, 3, 12, 5))
+
+
+def test_empty_image_returns_nothing():
+    gpu = ORBextractor(*PARAMS)
+    kps, desc = gpu(np.zeros((0, 0), np.uint8))
+    assert len(kps) == 0 and desc is None
+    gpu.close()
+
+
+def test_strided_input_and_two_handles_concurrently():
+    import threading
+    left, right = stereo_frame(1240)
+    big = np.zeros((375, 1300), np.uint8)
+    big[:, :1242] = left
+    view = big[:, :1242]
+    ora = oracle.OrbExtractor(*PARAMS)
+    okl = ora(left)
+    okr = ora(right)
+    exl, exr = ORBextractor(*PARAMS), ORBextractor(*PARAMS)
+    res = {}
+    def run(name, ex, im):
+        for _ in range(5):
+            res[name] = ex(im)
+    t1 = threading.Thread(target=run, args=("l", exl, view))
+    t2 = threading.Thread(target=run, args=("r", exr, right))
+    t1.start(); t2.start(); t1.join(); t2.join()
+    for got, exp in ((res["l"], okl), (res["r"], okr)):
+        assert got[0].tobytes() == exp[0].tobytes()
+        np.testing.assert_array_equal(got[1], exp[1])
+    exl.close(); exr.close()
