@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the CORB-SLAM hot path on B200: synthetic 1242x375 stereo frames/s (BASELINE.json metric, config #2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One process per GPU (torchrun for N > 1); every rank is one `corbslam_client` stream pinned to its GPU (replicas:
+frames of different robots are independent), so scaling is weak and there is no data-path collective.
+A step = one stereo frame through ORBextractor::operator() for the left and the right image (Frame.cc:78-81).
+
+  value : frames/s with both images already resident in HBM and results left in HBM (CUDA-event timed per step,
+          L2 flushed between steps, max over ranks)
+  e2e   : frames/s through the reference-facing C-ABI call with HOST buffers (H2D image, D2H keypoints+descriptors
+          inside the timed region, wall clock)
+  --impl reference : the CPU oracle port of the reference path (the reference itself cannot be built here: no
+          OpenCV/Eigen/ROS), left and right image on two threads per client like Frame.cc:78-81.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1242, 375
+ORB_PARAMS = (2000, 1.2, 8, 20, 7)  # KITTI00-02.yaml:38-51
+N_POOL = 8  # distinct synthetic frames cycled through
+ALGO_BYTES_PER_IMAGE = W * H + 1441432 + 60 * 2000  # input + pyramid + 60 B per keypoint (K = 2000)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_extract_fps(n_frames, clients=1):
+    """Oracle port of the reference path: `clients` concurrent clients, each running left/right on two threads."""
+    import oracle
+    from corb_slam_b200.synth import stereo_frame, frame_seed
+    frames = [stereo_frame(frame_seed(i)) for i in range(min(n_frames, N_POOL))]
+    exs = [(oracle.OrbExtractor(*ORB_PARAMS), oracle.OrbExtractor(*ORB_PARAMS)) for _ in range(clients)]
+    for exl, exr in exs:
+        exl(frames[0][0]); exr(frames[0][1])
+
+    def client(exl, exr):
+        for i in range(n_frames):
+            l, r = frames[i % len(frames)]
+            t = threading.Thread(target=exr, args=(r,))
+            t.start()
+            exl(l)
+            t.join()
+
+    ths = [threading.Thread(target=client, args=e) for e in exs]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return clients * n_frames / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.gpus
+    total = 0.0
+    t_all = 0.0
+    per_step = max(4, min(32, args.sample_frames // max(1, args.steps)))
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_extract_fps(2, clients=n)
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(args.steps):
+        fps, dt = cpu_extract_fps(per_step, clients=n)
+        frames += n * per_step
+        t_all += dt
+    fps = frames / t_all
+    line = {
+        "impl": "reference", "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": n,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7",
+                   "clients": n, "frames_per_step": per_step},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 2 * n, "kind": "port",
+                         "sample": "%d stereo frames per client, %d client(s), L/R on two threads each (Frame.cc:78-81); "
+                                   "oracle port because the reference needs OpenCV/Eigen/ROS to build" % (per_step * args.steps, n),
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from corb_slam_b200 import ORBextractor
+    from corb_slam_b200.synth import stereo_frame, frame_seed
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    exl = ORBextractor(*ORB_PARAMS, device=local)
+    exr = ORBextractor(*ORB_PARAMS, device=local)
+    frames = [stereo_frame(frame_seed(i + 100 * rank)) for i in range(N_POOL)]
+    pinned = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()) for l, r in frames]
+    dev = [(a.cuda(), b.cuda()) for a, b in pinned]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    sl = torch.cuda.ExternalStream(exl.stream())
+    sr = torch.cuda.ExternalStream(exr.stream())
+
+    def step_device(i, ev0=None, ev1=None):
+        l, r = dev[i % N_POOL]
+        if ev0 is not None:
+            ev0.record(sl)
+            sr.wait_event(ev0)
+        exl.extract_device(l.data_ptr(), W, H, W)
+        exr.extract_device(r.data_ptr(), W, H, W)
+        if ev1 is not None:
+            evr = torch.cuda.Event()
+            evr.record(sr)
+            sl.wait_event(evr)
+            ev1.record(sl)
+
+    def step_host(i, pyr=False):
+        l, r = pinned[i % N_POOL]
+        exl.submit(l.numpy(), pyr)
+        exr.submit(r.numpy(), pyr)
+        kl = exl.wait()
+        kr = exr.wait()
+        return kl, kr
+
+    # ---- warm-up
+    for i in range(max(args.warmup, 3)):
+        step_device(i)
+        exl.sync(); exr.sync()
+        step_host(i)
+    # ---- HBM-resident throughput: per-step CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    evs = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_device(i, e0, e1)
+        evs.append((e0, e1))
+        exl.sync(); exr.sync()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- end to end through the C ABI with host buffers (wall clock; H2D + D2H inside)
+    barrier()
+    t0 = time.perf_counter()
+    nk = 0
+    for i in range(args.steps):
+        kl, kr = step_host(i)
+        nk += len(kl[0]) + len(kr[0])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(i, pyr=True)
+    e2e_pyr_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_pyr_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, e2e_pyr_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        # per-kernel times of one image (eager replay with events) for the roofline of the dominant kernel
+        exl.extract_device(dev[0][0].data_ptr(), W, H, W)
+        exl.sync()
+        prof = exl.profile(reps=20)
+        agg = {}
+        for name, ms in prof:
+            agg[name] = agg.get(name, 0.0) + ms
+        top = max(prof, key=lambda kv: kv[1])
+        pk, pk_kind = peaks()
+        achieved = ALGO_BYTES_PER_IMAGE / (top[1] * 1e-3) / 1e9
+        fps = world * args.steps / (dev_ms * 1e-3)
+        kp_per_frame = nk / max(1, args.steps)
+        h2d = 2 * W * H
+        d2h = int(kp_per_frame * 60) + 16
+        cpu_fps, cpu_dt = cpu_extract_fps(args.sample_frames, clients=1)
+        line = {
+            "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7",
+                       "clients_per_gpu": 1, "frame_pool": N_POOL, "l2": "flushed (256 MiB write) between timed steps",
+                       "timing": "CUDA events per step on the extractor streams, sum over steps, max over ranks"},
+            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "note": "corb_orb_extract_submit/_wait on two handles, host numpy in, host keypoints+descriptors out"},
+            "e2e_with_pyramid": {"value": world * args.steps / (e2e_pyr_ms * 1e-3), "unit": "frames/s",
+                                 "d2h_bytes_per_step": d2h + 2 * 1441432, "ms_per_step": e2e_pyr_ms / args.steps,
+                                 "note": "also copies mvImagePyramid to the host (needed while ComputeStereoMatches is on the CPU)"},
+            "gpu_launches": 2 * exl.launches_per_extract() * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_IMAGE, "kernel_ms": top[1],
+                         "whole_frame_frac": 2 * ALGO_BYTES_PER_IMAGE * fps / world / 1e9 / pk["hbm_gbs"],
+                         "per_kernel_ms": {k: round(v, 5) for k, v in agg.items()}},
+            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 2, "kind": "port",
+                             "sample": "%d stereo frames, oracle port, L/R on two threads (Frame.cc:78-81), %.1f s"
+                                       % (args.sample_frames, cpu_dt), "host_cores_available": os.cpu_count()},
+            "keypoints_per_frame": kp_per_frame,
+        }
+        print(json.dumps(line))
+    exl.close(); exr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sample-frames", type=int, default=200, help="stereo frames of the bounded CPU baseline sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,9 @@ def lib():
         L.corb_orb_stream.argtypes = [vp]
         L.corb_orb_stream.restype = vp
         L.corb_orb_launches_per_extract.argtypes = [vp]
+        L.corb_orb_profile.argtypes = [vp, C.c_int, f32p, C.c_int, i32p]
+        L.corb_orb_kernel_name.argtypes = [vp, C.c_int]
+        L.corb_orb_kernel_name.restype = C.c_char_p
         L.corb_orb_tap.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, i32p]
         _lib = L
     return _lib

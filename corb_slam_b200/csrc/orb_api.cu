@@ -480,6 +480,58 @@ int corb_orb_device_level(const corb_orb* h, int level, int blurred, const uint8
     return CORB_OK;
 }
 
+// Eager (non-graph) replay of the kernels of one extraction on the image currently in level 0, with a CUDA event
+// between consecutive launches: per-kernel device time for the roofline report. Order: resize 1..L-1, blur,
+// fast_cells, quadtree, orient_desc.
+int corb_orb_profile(corb_orb* h, int reps, float* ms, int cap, int* n) {
+    CORB_CHECK(h && h->plan_w && ms && n && reps >= 1, CORB_ERR_INVALID, "bad argument or no plan");
+    const OrbGeom& g = h->geom;
+    const int nk = (g.n_levels - 1) + 4;
+    CORB_CHECK(cap >= nk, CORB_ERR_INVALID, "need room for %d kernels", nk);
+    CORB_CUDA(cudaSetDevice(h->device));
+    std::vector<cudaEvent_t> ev(nk + 1);
+    for (auto& e : ev) CORB_CUDA(cudaEventCreate(&e));
+    for (int i = 0; i < nk; i++) ms[i] = 0.f;
+    for (int r = 0; r < reps; r++) {
+        int k = 0;
+        CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        for (int l = 1; l < g.n_levels; l++) {
+            launch_resize(g, h->buf, l, h->stream);
+            CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        }
+        launch_blur(g, h->buf, h->stream);
+        CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        launch_fast_cells(g, h->buf, h->stream);
+        CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        launch_octtree(g, h->buf, h->key_smem_cap, h->oct_smem, h->stream);
+        CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        launch_orient_desc(g, h->buf, h->stream);
+        CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        CORB_CUDA(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < nk; i++) {
+            float t = 0.f;
+            CORB_CUDA(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            ms[i] += t / reps;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    *n = nk;
+    return CORB_OK;
+}
+
+const char* corb_orb_kernel_name(const corb_orb* h, int i) {
+    if (!h) return "";
+    const int nr = h->nlevels - 1;
+    if (i < nr) return "k_resize";
+    switch (i - nr) {
+        case 0: return "k_blur";
+        case 1: return "k_fast_cells";
+        case 2: return "k_octtree";
+        case 3: return "k_orient_desc";
+    }
+    return "";
+}
+
 void* corb_orb_stream(const corb_orb* h) { return h ? (void*)h->stream : nullptr; }
 int corb_orb_launches_per_extract(const corb_orb* h) { return h ? h->kernel_launches : 0; }
 

@@ -130,6 +130,13 @@ class ORBextractor:
         check(lib().corb_orb_device_results(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def profile(self, reps=10):
+        """[(kernel name, ms)] per launch of one extraction, CUDA-event timed (eager replay, not the graph)."""
+        ms = np.zeros(64, np.float32)
+        n = C.c_int32()
+        check(lib().corb_orb_profile(self._h, reps, ms.ctypes.data_as(_lib.f32p), 64, C.byref(n)))
+        return [(lib().corb_orb_kernel_name(self._h, i).decode(), float(ms[i])) for i in range(n.value)]
+
     # ---- stage taps for parity tests
     def tap_image(self, level, blurred=False):
         h, w = self._last_shape()

@@ -98,6 +98,11 @@ CORB_API void* corb_orb_stream(const corb_orb* h);
 /* number of kernel launches one extraction enqueues (graph nodes that are kernels) */
 CORB_API int corb_orb_launches_per_extract(const corb_orb* h);
 
+/* Per-kernel device time (ms, averaged over `reps` eager replays with CUDA events between launches) of one extraction
+ * of the image currently resident; *n kernels in launch order, named by corb_orb_kernel_name(). For roofline reports. */
+CORB_API int corb_orb_profile(corb_orb* h, int reps, float* ms, int cap, int* n);
+CORB_API const char* corb_orb_kernel_name(const corb_orb* h, int i);
+
 /* Stage taps of the last extraction, for stage-wise parity tests against the oracle.
  *   CORB_TAP_PYRAMID / CORB_TAP_BLURRED : out = lw*lh bytes (dense)
  *   CORB_TAP_CANDIDATES                 : out = int32 triplets (x, y, response) relative to (16,16), in the order
