@@ -5,3 +5,5 @@ reference classes that own the path (ORBextractor, ORBmatcher, ORBVocabulary, Op
 """
 from ._lib import CorbError, KP_DTYPE, LIB_PATH  # noqa: F401
 from .orbextractor import ORBextractor  # noqa: F401
+from .orbmatcher import ORBmatcher, BowFeatures  # noqa: F401
+from .orbvocabulary import ORBVocabulary  # noqa: F401

@@ -24,6 +24,12 @@ f64p = C.POINTER(C.c_double)
 vp = C.c_void_p
 
 
+class BowSide(C.Structure):
+    """corb_bow_side (include/corb_b200.h)."""
+    _fields_ = [("desc", vp), ("n", C.c_int32), ("fv_nodes", vp), ("fv_off", vp), ("fv_idx", vp), ("fv_n", C.c_int32),
+                ("valid", vp), ("angles", vp)]
+
+
 class CorbError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__("corb_b200 error %d: %s" % (status, msg))
@@ -73,6 +79,27 @@ def lib():
         L.corb_orb_kernel_name.argtypes = [vp, C.c_int]
         L.corb_orb_kernel_name.restype = C.c_char_p
         L.corb_orb_tap.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t, i32p]
+        u32p = C.POINTER(C.c_uint32)
+        L.corb_matcher_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.corb_matcher_destroy.argtypes = [vp]
+        L.corb_matcher_destroy.restype = None
+        L.corb_matcher_sync.argtypes = [vp]
+        L.corb_matcher_stream.argtypes = [vp]
+        L.corb_matcher_stream.restype = vp
+        L.corb_hamming_pairs.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp]
+        L.corb_bow_match.argtypes = [vp, C.c_int, C.POINTER(BowSide), C.POINTER(BowSide), C.c_float, C.c_int, vp, i32p]
+        L.corb_bow_match_batch.argtypes = [vp, C.c_int, C.c_int, C.POINTER(BowSide), C.POINTER(BowSide), C.c_float, C.c_int,
+                                           C.POINTER(vp), i32p]
+        L.corb_bow_match_batch_device.argtypes = [vp, C.c_int, C.c_int, C.POINTER(BowSide), C.POINTER(BowSide), C.c_float,
+                                                  C.c_int, C.POINTER(vp), vp]
+        L.corb_voc_load_text.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.corb_voc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
+        L.corb_voc_destroy.argtypes = [vp]
+        L.corb_voc_destroy.restype = None
+        L.corb_voc_info.argtypes = [vp] + [i32p] * 6
+        L.corb_voc_transform_features.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
+        L.corb_voc_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, i32p, vp, vp, vp, i32p]
+        L.corb_bow_score_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), vp, vp]
         _lib = L
     return _lib
 

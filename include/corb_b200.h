@@ -111,6 +111,90 @@ CORB_API const char* corb_orb_kernel_name(const corb_orb* h, int i);
 enum { CORB_TAP_PYRAMID = 0, CORB_TAP_BLURRED = 1, CORB_TAP_CANDIDATES = 2, CORB_TAP_LEVEL_COUNT = 3 };
 CORB_API int corb_orb_tap(corb_orb* h, int what, int level, void* out, size_t out_bytes, int* n);
 
+/* ------------------------------------------------------------------------------------------------ descriptor matching */
+
+/* Workspace for the matching entry points (device buffers + stream). One per calling thread: Tracking, LoopClosing and
+ * the server's fuse thread call SearchByBoW concurrently. */
+typedef struct corb_matcher corb_matcher;
+CORB_API int corb_matcher_create(int device, corb_matcher** out);
+CORB_API void corb_matcher_destroy(corb_matcher* m);
+
+/* ORBmatcher::DescriptorDistance [ORBmatcher.cc:1792-1808], batched: out[i] = Hamming(A[pairs[2i]], B[pairs[2i+1]])
+ * over 256-bit descriptors stored as 32-byte rows. Scalar callers keep the inline host popcount. */
+CORB_API int corb_hamming_pairs(corb_matcher* m, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* pairs,
+                                int n, int32_t* out);
+
+/* One side of a SearchByBoW call, flattened by the shim:
+ *   desc/n            mDescriptors (n x 32 bytes)
+ *   fv_*              DBoW2::FeatureVector as CSR: fv_nodes[fv_n] ascending node ids, fv_off[fv_n+1], fv_idx[] feature
+ *                     indices in the order FeatureVector::addFeature appended them
+ *   valid             per feature: MapPoint* != NULL && !isBad()  (NULL = all valid)
+ *   angles            per feature keypoint angle in degrees (mvKeysUn / mvKeys as the variant prescribes); may be NULL
+ *                     when check_ori == 0 */
+typedef struct {
+    const uint8_t* desc;
+    int32_t n;
+    const uint32_t* fv_nodes;
+    const int32_t* fv_off;
+    const uint32_t* fv_idx;
+    int32_t fv_n;
+    const uint8_t* valid;
+    const float* angles;
+} corb_bow_side;
+
+enum {
+    CORB_BOW_KF_FRAME = 0,  /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...)        [ORBmatcher.cc:162-291] */
+    CORB_BOW_KF_SERVER = 1, /* ORBmatcher::SearchByBoWInServer(KeyFrame*, KeyFrame*)  [ORBmatcher.cc:294-423] */
+    CORB_BOW_KF_KF = 2      /* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)     [ORBmatcher.cc:657-790] */
+};
+
+/* A = the keyframe whose MapPoints are handed out (pKF / pKF1), B = Frame F / KeyFrame F / pKF2.
+ * Variants 0,1: match has B->n entries, match[b] = index of the A feature whose MapPoint goes to b, or -1.
+ * Variant 2   : match has A->n entries, match[a] = index of the matched B feature, or -1; B->valid is honoured.
+ * nnratio / check_ori = ORBmatcher(nnratio, checkOri) [ORBmatcher.cc:41]. *nmatches = the reference's return value. */
+CORB_API int corb_bow_match(corb_matcher* m, int variant, const corb_bow_side* A, const corb_bow_side* B, float nnratio,
+                            int check_ori, int32_t* match, int32_t* nmatches);
+/* The same for ncalls independent (A[i], B[i]) pairs in one launch (relocalisation candidates, Tracking.cc:1405;
+ * map-fusion candidates, MapFusion.cpp:691). match[i] / nmatches[i] as above. */
+CORB_API int corb_bow_match_batch(corb_matcher* m, int variant, int ncalls, const corb_bow_side* A, const corb_bow_side* B,
+                                  float nnratio, int check_ori, int32_t* const* match, int32_t* nmatches);
+/* Device-resident form of the batch: every pointer inside A[i], B[i] and match[i] is a device pointer; results stay in
+ * HBM (d_nmatches[ncalls] on the device). Enqueued on the matcher's stream; corb_matcher_sync() waits. */
+CORB_API int corb_bow_match_batch_device(corb_matcher* m, int variant, int ncalls, const corb_bow_side* A,
+                                         const corb_bow_side* B, float nnratio, int check_ori, int32_t* const* d_match,
+                                         int32_t* d_nmatches);
+CORB_API int corb_matcher_sync(corb_matcher* m);
+CORB_API void* corb_matcher_stream(const corb_matcher* m);
+
+/* ------------------------------------------------------------------------------------------------ DBoW2 vocabulary */
+
+typedef struct corb_voc corb_voc;
+
+/* ORBVocabulary::loadFromTextFile [TemplatedVocabulary.h:1338-1424; System.cc:59-68]. The tree is uploaded once
+ * (about 35 MB for ORBvoc.txt: 1 082 073 nodes) and is read-only afterwards. Only L1_NORM scoring with TF_IDF or TF
+ * weighting is supported (ORBvoc.txt's header is "10 6 0 0"). */
+CORB_API int corb_voc_load_text(const char* path, int device, corb_voc** out);
+/* Same from arrays: nodes 1..n in DBoW2 id order (parent id, leaf flag, 32-byte descriptor, weight). */
+CORB_API int corb_voc_create(int k, int L, int scoring, int weighting, int n, const int32_t* parent, const uint8_t* is_leaf,
+                             const uint8_t* desc, const double* weight, int device, corb_voc** out);
+CORB_API void corb_voc_destroy(corb_voc* v);
+CORB_API int corb_voc_info(const corb_voc* v, int* k, int* L, int* scoring, int* weighting, int* n_nodes, int* n_words);
+
+/* TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) for n features [:1218-1259]:
+ * word id, word weight (idf) and the id of the ancestor node at level L-levelsup, per feature. */
+CORB_API int corb_voc_transform_features(corb_voc* v, const uint8_t* desc, int n, int levelsup, uint32_t* word_id,
+                                         double* weight, uint32_t* node_id);
+/* TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) [:1127-1194; Frame.cc:404,
+ * KeyFrame.cc:75]: the descent runs on the GPU, the two maps are rebuilt on the host in feature order so the fp64
+ * sums are bit-identical. bow_* need n entries, fv_nodes n, fv_off n+1, fv_idx n. */
+CORB_API int corb_voc_transform(corb_voc* v, const uint8_t* desc, int n, int levelsup, uint32_t* bow_words, double* bow_vals,
+                                int* n_bow, uint32_t* fv_nodes, int32_t* fv_off, uint32_t* fv_idx, int* n_fv);
+/* ORBVocabulary::score(v1, v2) = L1Scoring::score [ScoringObject.cpp:23-68; KeyFrameDatabase.cc:128,238,345], one
+ * query against ncand candidates in one launch. BowVectors are sorted (word id, value) lists. */
+CORB_API int corb_bow_score_batch(corb_voc* v, const uint32_t* q_words, const double* q_vals, int nq, int ncand,
+                                  const uint32_t* const* c_words, const double* const* c_vals, const int32_t* c_n,
+                                  double* scores);
+
 #ifdef __cplusplus
 }
 #endif
