@@ -91,8 +91,8 @@ class Vocabulary:
         return cls(_lib().oracle_voc_load_text(path.encode()))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            _lib().oracle_voc_destroy(self._h)
+        if getattr(self, "_h", None) and _L is not None:
+            _L.oracle_voc_destroy(self._h)
             self._h = None
 
     def export(self):

@@ -19,7 +19,7 @@ def _features(rng, n, base=None, flip_bits=12):
     """n random descriptors; if `base` is given, noisy copies of it (a second view of the same scene)."""
     if base is None:
         return rng.integers(0, 256, (n, 32), dtype=np.uint8)
-    d = base[rng.permutation(len(base))[:n]].copy()
+    d = base[rng.integers(0, len(base), n)].copy()
     for i in range(n):
         for b in rng.integers(0, 256, rng.integers(0, flip_bits)):
             d[i, b >> 3] ^= 1 << (b & 7)
@@ -71,7 +71,7 @@ def test_search_by_bow_bit_exact(variant, check_ori, ratio):
         got, gn = m._batch(variant, [_mk(BowFeatures, sA)], [_mk(BowFeatures, sB)])[0]
         assert gn == en
         np.testing.assert_array_equal(got, exp)
-        assert en > 50, "test data should produce matches"
+        assert en > 10, "test data should produce matches"
     m.close()
 
 
