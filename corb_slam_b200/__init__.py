@@ -7,3 +7,4 @@ from ._lib import CorbError, KP_DTYPE, LIB_PATH  # noqa: F401
 from .orbextractor import ORBextractor  # noqa: F401
 from .orbmatcher import ORBmatcher, BowFeatures  # noqa: F401
 from .orbvocabulary import ORBVocabulary  # noqa: F401
+from .optimizer import Optimizer, torch_allreduce  # noqa: F401

@@ -30,6 +30,24 @@ class BowSide(C.Structure):
                 ("valid", vp), ("angles", vp)]
 
 
+class BaProblem(C.Structure):
+    """corb_ba_problem (include/corb_b200.h)."""
+    _fields_ = [("n_poses", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("pose_q", vp), ("pose_t", vp),
+                ("pose_fixed", vp), ("pose_cam", vp), ("point_xyz", vp), ("point_fixed", vp), ("edge_pose", vp),
+                ("edge_point", vp), ("edge_obs", vp), ("edge_inv_sigma2", vp)]
+
+
+class BaResult(C.Structure):
+    """corb_ba_result (include/corb_b200.h)."""
+    _fields_ = [("iterations", C.c_int32), ("n_trials", C.c_int32), ("stopped", C.c_int32), ("solver_failures", C.c_int32),
+                ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_initial", C.c_double),
+                ("lambda_final", C.c_double), ("trial_accepted", C.c_uint8 * 256), ("trial_chi2", C.c_double * 256),
+                ("ms_total", C.c_double), ("ms_solve", C.c_double), ("reduced_blocks", C.c_int64)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, vp, vp, C.c_size_t, C.c_int, vp)
+
+
 class CorbError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__("corb_b200 error %d: %s" % (status, msg))
@@ -100,6 +118,7 @@ def lib():
         L.corb_voc_transform_features.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
         L.corb_voc_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, i32p, vp, vp, vp, i32p]
         L.corb_bow_score_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), vp, vp]
+        L.corb_ba_solve.argtypes = [C.POINTER(BaProblem), C.c_int, vp, C.c_int, C.c_int, C.POINTER(BaResult), vp, vp]
         _lib = L
     return _lib
 

@@ -1,0 +1,77 @@
+"""Host-side mirror of Optimizer::BundleAdjustment / GlobalBundleAdjustemnt (reference: corbslam_client/include/
+Optimizer.h:42-46, src/Optimizer.cc:43-270) over the C ABI. The pointer graph of KeyFrames/MapPoints is passed as the
+flat arrays of corb_ba_problem (what the C++ shim builds); results are written back in place.
+
+Multi-GPU: landmarks are sharded over the ranks of a torch.distributed process group, poses are
+replicated, and the reduced camera system is all-reduced over NCCL/NVLink from inside corb_ba_solve through a callback."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ALLREDUCE_FN, BaProblem, BaResult, check, lib
+
+_DT = {"pose_q": np.float64, "pose_t": np.float64, "pose_fixed": np.uint8, "pose_cam": np.float64, "point_xyz": np.float64,
+       "point_fixed": np.uint8, "edge_pose": np.int32, "edge_point": np.int32, "edge_obs": np.float64,
+       "edge_inv_sigma2": np.float64}
+
+
+class _DevArray:
+    """Wraps a raw device pointer as a __cuda_array_interface__ object so torch can view it without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def torch_allreduce(group=None):
+    """All-reduce callback backed by torch.distributed (NCCL over NVLink on the GPU box)."""
+    import torch
+    import torch.distributed as dist
+    ops = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}
+
+    def _cb(user, d_buf, n, op, stream):
+        try:
+            t = torch.as_tensor(_DevArray(d_buf, n), device="cuda")
+            s = torch.cuda.ExternalStream(stream)
+            with torch.cuda.stream(s):
+                dist.all_reduce(t, op=ops[op], group=group)
+            return 0
+        except Exception as e:  # never let an exception cross the C boundary
+            print("corb all-reduce callback failed:", repr(e))
+            return 1
+    return ALLREDUCE_FN(_cb)
+
+
+class Optimizer:
+    @staticmethod
+    def BundleAdjustment(problem, nIterations=5, pbStopFlag=None, nLoopKF=0, bRobust=True, device=0, allreduce=None):
+        """problem: dict with the arrays of corb_ba_problem (see corb_slam_b200.synth.ba_problem). pose_q / pose_t /
+        point_xyz are updated in place (they must be C-contiguous float64 arrays to be updated in place; otherwise the
+        returned dict holds the updated copies). pbStopFlag: optional np.uint8 array of one element polled by the solver.
+        Returns (problem_out, info)."""
+        keep = {k: np.ascontiguousarray(problem[k], _DT[k]) for k in _DT}
+        p = BaProblem()
+        p.n_poses, p.n_points, p.n_edges = len(keep["pose_fixed"]), len(keep["point_fixed"]), len(keep["edge_pose"])
+        for k in _DT:
+            setattr(p, k, keep[k].ctypes.data)
+        res = BaResult()
+        stop_p = pbStopFlag.ctypes.data if pbStopFlag is not None else None
+        cb = C.cast(allreduce, C.c_void_p) if allreduce is not None else None
+        st = lib().corb_ba_solve(C.byref(p), int(nIterations), stop_p, int(bool(bRobust)), int(device), C.byref(res), cb, None)
+        if st not in (_lib.OK, _lib.ERR_STOPPED):
+            check(st)
+        n = min(res.n_trials, 256)
+        info = {"iterations": res.iterations, "n_trials": res.n_trials, "stopped": res.stopped,
+                "solver_failures": res.solver_failures, "chi2_initial": res.chi2_initial, "chi2_final": res.chi2_final,
+                "lambda_initial": res.lambda_initial, "lambda_final": res.lambda_final,
+                "trial_accepted": [int(res.trial_accepted[i]) for i in range(n)],
+                "trial_chi2": [float(res.trial_chi2[i]) for i in range(n)], "ms_total": res.ms_total,
+                "ms_solve": res.ms_solve, "reduced_blocks": res.reduced_blocks}
+        out = dict(problem)
+        out["pose_q"], out["pose_t"], out["point_xyz"] = keep["pose_q"], keep["pose_t"], keep["point_xyz"]
+        return out, info
+
+    @staticmethod
+    def GlobalBundleAdjustemnt(problem, nIterations=5, pbStopFlag=None, nLoopKF=0, bRobust=True, device=0, allreduce=None):
+        """Same spelling as the reference (Optimizer.cc:43)."""
+        return Optimizer.BundleAdjustment(problem, nIterations, pbStopFlag, nLoopKF, bRobust, device, allreduce)

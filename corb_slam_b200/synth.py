@@ -31,3 +31,115 @@ def stereo_frame(seed, w=1242, h=375, disparity=8):
 
 def frame_seed(idx):
     return 1234 + idx
+
+
+# --------------------------------------------------------------------------------------------- global BA problem
+KITTI_CAM = (718.856, 718.856, 607.1928, 185.2157, 386.1448)  # fx fy cx cy bf  (KITTI00-02.yaml:8-11,25)
+
+
+def _quat_from_yaw_pitch(yaw, pitch):
+    """(x,y,z,w) of R = Ry(yaw) * Rx(pitch)."""
+    cy, sy, cp, sp = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2)
+    # q_y = (0, sy, 0, cy), q_x = (sp, 0, 0, cp); q = q_y * q_x
+    return np.stack([cy * sp, sy * cp, -sy * sp, cy * cp], -1)
+
+
+def _quat_to_R(q):
+    x, y, z, w = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    R = np.empty(q.shape[:-1] + (3, 3))
+    R[..., 0, 0] = 1 - 2 * (y * y + z * z); R[..., 0, 1] = 2 * (x * y - z * w); R[..., 0, 2] = 2 * (x * z + y * w)
+    R[..., 1, 0] = 2 * (x * y + z * w); R[..., 1, 1] = 1 - 2 * (x * x + z * z); R[..., 1, 2] = 2 * (y * z - x * w)
+    R[..., 2, 0] = 2 * (x * z - y * w); R[..., 2, 1] = 2 * (y * z + x * w); R[..., 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def ba_problem(n_poses=2000, n_points=200000, seed=7, obs_per_point=5, n_fusion=40, stereo_fraction=0.8, perturb=True):
+    """Synthetic global-BA problem of SURVEY.md §8d: a 1 m/keyframe "street" trajectory, landmarks seen by
+    `obs_per_point` consecutive keyframes, KITTI intrinsics, 1 px observation noise, octave-dependent information,
+    `n_fusion` long-range observations (map-fusion / loop-closure links), first keyframe fixed.
+
+    Returns a dict of numpy arrays in the layout of corb_ba_problem (include/corb_b200.h)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, bf = KITTI_CAM
+    P, L = n_poses, n_points
+    # ground-truth poses: camera looks along +Z of the world, small yaw/pitch wobble
+    yaw = rng.normal(0, np.deg2rad(1.0), P)
+    pitch = rng.normal(0, np.deg2rad(0.3), P)
+    q_wc = _quat_from_yaw_pitch(yaw, pitch)               # camera -> world
+    C = np.stack([rng.normal(0, 0.05, P), rng.normal(0, 0.02, P), np.arange(P) * 1.0], -1)
+    R_wc = _quat_to_R(q_wc)
+    q_cw = q_wc * np.array([-1.0, -1.0, -1.0, 1.0])        # world -> camera (conjugate)
+    R_cw = np.transpose(R_wc, (0, 2, 1))
+    t_cw = -np.einsum("pij,pj->pi", R_cw, C)
+    # landmarks: pixel + depth in the nearest observer, back-projected
+    k = rng.integers(0, P, L)
+    u = rng.uniform(20, 1221, L); v = rng.uniform(20, 356, L); d = rng.uniform(5.0, 30.0, L)
+    Xc = np.stack([(u - cx) * d / fx, (v - cy) * d / fy, d], -1)
+    Xw = np.einsum("lij,lj->li", R_wc[k], Xc) + C[k]
+    ep, el = [], []
+    for j in range(obs_per_point):
+        pi = k - j
+        ok = pi >= 0
+        ep.append(pi[ok]); el.append(np.nonzero(ok)[0])
+    if n_fusion > 0:  # long-range links make the reduced camera system non-banded
+        lm = rng.choice(L, size=min(n_fusion, L), replace=False)
+        far = k[lm] - rng.integers(max(P // 4, obs_per_point + 1), max(P // 2, obs_per_point + 2), len(lm))
+        ok = far >= 0
+        ep.append(far[ok]); el.append(lm[ok])
+    edge_pose = np.concatenate(ep).astype(np.int32)
+    edge_point = np.concatenate(el).astype(np.int32)
+    order = np.lexsort((edge_pose, edge_point))            # MapPoint-major like Optimizer.cc:106-197
+    edge_pose, edge_point = edge_pose[order], edge_point[order]
+    E = len(edge_pose)
+    Xc_e = np.einsum("eij,ej->ei", R_cw[edge_pose], Xw[edge_point]) + t_cw[edge_pose]
+    z = Xc_e[:, 2]
+    assert (z > 1.0).all()
+    pu = fx * Xc_e[:, 0] / z + cx + rng.normal(0, 1.0, E)
+    pv = fy * Xc_e[:, 1] / z + cy + rng.normal(0, 1.0, E)
+    pr = pu - bf / z + rng.normal(0, 1.0, E)
+    mono = rng.random(E) >= stereo_fraction
+    pr[mono] = -1.0
+    # measurements are float32 in the reference (cv::KeyPoint, mvuRight)
+    obs = np.stack([pu, pv, pr], -1).astype(np.float32).astype(np.float64)
+    octave = rng.integers(0, 8, E)
+    sigma2 = np.cumprod(np.concatenate([[1.0], np.full(7, 1.2)])).astype(np.float32) ** 2
+    inv_sigma2 = (np.float32(1.0) / sigma2.astype(np.float32))[octave].astype(np.float64)
+    pose_q, pose_t, pts = q_cw.copy(), t_cw.copy(), Xw.copy()
+    if perturb:
+        dC = rng.normal(0, 0.05, (P, 3))
+        dyaw = rng.normal(0, np.deg2rad(0.5), P); dpitch = rng.normal(0, np.deg2rad(0.5), P)
+        q_wc_n = _quat_from_yaw_pitch(yaw + dyaw, pitch + dpitch)
+        Cn = C + dC
+        q_wc_n[0], Cn[0] = q_wc[0], C[0]                   # the fixed keyframe keeps its pose
+        R_cw_n = np.transpose(_quat_to_R(q_wc_n), (0, 2, 1))
+        pose_q = q_wc_n * np.array([-1.0, -1.0, -1.0, 1.0])
+        pose_t = -np.einsum("pij,pj->pi", R_cw_n, Cn)
+        pts = Xw + rng.normal(0, 0.10, (L, 3))
+    # poses/points enter the reference as float32 cv::Mat (Converter.cc:37-47)
+    pose_t = pose_t.astype(np.float32).astype(np.float64)
+    pts = pts.astype(np.float32).astype(np.float64)
+    pose_fixed = np.zeros(P, np.uint8); pose_fixed[0] = 1      # mnId == 1 (Optimizer.cc:94); index 0 here
+    return {
+        "pose_q": np.ascontiguousarray(pose_q), "pose_t": np.ascontiguousarray(pose_t), "pose_fixed": pose_fixed,
+        "pose_cam": np.tile(np.array(KITTI_CAM, np.float64), (P, 1)), "point_xyz": np.ascontiguousarray(pts),
+        "point_fixed": np.zeros(L, np.uint8), "edge_pose": edge_pose, "edge_point": edge_point,
+        "edge_obs": np.ascontiguousarray(obs), "edge_inv_sigma2": np.ascontiguousarray(inv_sigma2),
+    }
+
+
+def ba_shard(prob, rank, world):
+    """Landmark sharding of SURVEY.md §8e: landmark l goes to rank l % world with its edges; poses are replicated."""
+    keep_pts = np.nonzero(np.arange(len(prob["point_xyz"])) % world == rank)[0]
+    remap = np.full(len(prob["point_xyz"]), -1, np.int64)
+    remap[keep_pts] = np.arange(len(keep_pts))
+    ke = remap[prob["edge_point"]] >= 0
+    out = dict(prob)
+    out["point_xyz"] = np.ascontiguousarray(prob["point_xyz"][keep_pts])
+    out["point_fixed"] = np.ascontiguousarray(prob["point_fixed"][keep_pts])
+    out["edge_pose"] = np.ascontiguousarray(prob["edge_pose"][ke])
+    out["edge_point"] = np.ascontiguousarray(remap[prob["edge_point"][ke]].astype(np.int32))
+    out["edge_obs"] = np.ascontiguousarray(prob["edge_obs"][ke])
+    out["edge_inv_sigma2"] = np.ascontiguousarray(prob["edge_inv_sigma2"][ke])
+    out["pose_q"] = prob["pose_q"].copy(); out["pose_t"] = prob["pose_t"].copy()
+    out["_point_ids"] = keep_pts
+    return out

@@ -195,6 +195,57 @@ CORB_API int corb_bow_score_batch(corb_voc* v, const uint32_t* q_words, const do
                                   const uint32_t* const* c_words, const double* const* c_vals, const int32_t* c_n,
                                   double* scores);
 
+/* ------------------------------------------------------------------------------------------------ global bundle adjustment */
+
+/* Optimizer::BundleAdjustment flattened by the shim [Optimizer.cc:54-270]: the pointer graph of KeyFrames, MapPoints
+ * and observations becomes dense-index SoA arrays (the sparse vertex ids mnId / mnId+maxKFid+1 are only local indices).
+ *   pose_q/pose_t   world->camera pose of each keyframe: unit quaternion (x,y,z,w) and translation, fp64
+ *                   (Converter::toSE3Quat of the float32 4x4, Converter.cc:37-47); updated in place
+ *   pose_fixed      mnId == 1 || getFixed()  (Optimizer.cc:94)
+ *   pose_cam        fx, fy, cx, cy, bf of the keyframe (:164-167, :186-190)
+ *   point_xyz       MapPoint world positions (:113), updated in place; point_fixed = getFixed() (:120)
+ *   edge_*          one entry per observation: keyframe index, point index, (u, v, u_right) with u_right < 0 for a
+ *                   monocular observation (mvuRight < 0, :140), information = invSigma2 of the keypoint octave
+ * A (pose, point) pair may appear at most once (MapPoint::GetObservations is a map). Points without edges are ignored. */
+typedef struct {
+    int32_t n_poses, n_points, n_edges;
+    double* pose_q;
+    double* pose_t;
+    const uint8_t* pose_fixed;
+    const double* pose_cam;
+    double* point_xyz;
+    const uint8_t* point_fixed;
+    const int32_t* edge_pose;
+    const int32_t* edge_point;
+    const double* edge_obs;
+    const double* edge_inv_sigma2;
+} corb_ba_problem;
+
+typedef struct {
+    int32_t iterations;       /* LM iterations executed (what g2o's optimize() returns) */
+    int32_t n_trials;         /* LM trials = linear solves */
+    int32_t stopped;          /* 1 if *stop ended the solve */
+    int32_t solver_failures;  /* trials whose reduced system was not positive definite */
+    double chi2_initial, chi2_final, lambda_initial, lambda_final;
+    uint8_t trial_accepted[256]; /* accept/reject of the first 256 trials */
+    double trial_chi2[256];
+    double ms_total, ms_solve;   /* wall time of the whole call / device time inside the reduced-camera solves */
+    int64_t reduced_blocks;      /* 6x6 blocks in the envelope of the reduced camera system */
+} corb_ba_result;
+
+/* All-reduce hook for landmark-sharded BA: `buf` is a DEVICE pointer to n doubles, reduced in place over
+ * all ranks with op 0 = sum, 1 = min, 2 = max, ordered on CUDA stream `stream` (a cudaStream_t). The C++ server passes
+ * a function that calls ncclAllReduce on its communicator; the Python host layer passes torch.distributed.all_reduce. */
+typedef int (*corb_allreduce_fn)(void* user, double* d_buf, size_t n, int op, void* stream);
+
+/* Optimizer::BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust) [Optimizer.h:42-46] = g2o
+ * BlockSolver_6_3 + Levenberg-Marquardt [block_solver.hpp:354-604, optimization_algorithm_levenberg.cpp:61-189] on the
+ * GPU. `stop` (nullable) is polled before every iteration and LM trial like g2o's forceStopFlag. robust != 0 adds the
+ * Huber kernels of Optimizer.cc:101-102,155-160,179-184. With allreduce != NULL the problem holds this rank's landmark
+ * shard (all poses, a subset of points and their edges) and every rank ends with identical poses. */
+CORB_API int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile uint8_t* stop, int robust, int device,
+                           corb_ba_result* result, corb_allreduce_fn allreduce, void* allreduce_user);
+
 #ifdef __cplusplus
 }
 #endif

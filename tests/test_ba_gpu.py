@@ -1,0 +1,96 @@
+"""GPU parity of the global bundle adjustment against the CPU oracle.
+
+Tolerance (north_star): RMS reprojection error of the GPU and oracle solutions differs by < 1e-5 px, and the LM
+accept/reject sequence is identical. Poses/points themselves are compared with a looser absolute tolerance because the
+gauge is only fixed by one keyframe."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import _ba_bind as B
+from corb_slam_b200 import Optimizer
+from corb_slam_b200.synth import ba_problem
+
+pytestmark = pytest.mark.gpu
+
+RMS_TOL = 1e-5
+
+
+def _check(prob, iters=10, robust=False, rms_tol=RMS_TOL):
+    oracle.lib()
+    o_out, o_info = B.solve(prob, iters, robust=robust)
+    g_out, g_info = Optimizer.BundleAdjustment(prob, iters, bRobust=robust)
+    assert g_info["trial_accepted"] == o_info["trial_accepted"]
+    assert g_info["iterations"] == o_info["iterations"] and g_info["n_trials"] == o_info["n_trials"]
+    assert g_info["lambda_initial"] == pytest.approx(o_info["lambda_initial"], rel=1e-9)
+    assert g_info["chi2_initial"] == pytest.approx(o_info["chi2_initial"], rel=1e-10)
+    assert g_info["chi2_final"] == pytest.approx(o_info["chi2_final"], rel=1e-6)
+    _, o_rms = B.chi2(o_out)
+    _, g_rms = B.chi2(g_out)
+    assert abs(o_rms - g_rms) < rms_tol, (o_rms, g_rms)
+    assert np.abs(g_out["point_xyz"] - o_out["point_xyz"]).max() < 1e-4
+    assert np.abs(g_out["pose_t"] - o_out["pose_t"]).max() < 1e-4
+    # the input arrays must not have been modified
+    assert g_out["pose_q"] is not prob["pose_q"]
+    return o_info, g_info, g_rms
+
+
+@pytest.mark.parametrize("P,L", [(20, 2000), (200, 20000)])
+def test_ba_matches_oracle(P, L):
+    prob = ba_problem(P, L, seed=7, n_fusion=20)
+    o_info, g_info, rms = _check(prob)
+    assert o_info["chi2_final"] < 0.02 * o_info["chi2_initial"] and rms < 1.2
+
+
+def test_ba_robust_huber():
+    prob = ba_problem(30, 3000, seed=3, n_fusion=10)
+    rng = np.random.default_rng(0)
+    bad = rng.choice(len(prob["edge_pose"]), 150, replace=False)  # gross outliers
+    prob["edge_obs"][bad, 0] += rng.normal(0, 40, len(bad))
+    _check(prob, iters=8, robust=True)
+
+
+def test_ba_fixed_vertices_and_mono_only():
+    prob = ba_problem(25, 1500, seed=5, n_fusion=5, stereo_fraction=0.0)
+    prob["pose_fixed"][:3] = 1                   # several anchors (client-side GBA fixes foreign keyframes, Cache.cc:482)
+    prob["point_fixed"][::7] = 1                 # and foreign map points (Cache.cc:534)
+    o_info, g_info, _ = _check(prob, iters=6)
+    out, _ = Optimizer.BundleAdjustment(prob, 6, bRobust=False)
+    np.testing.assert_array_equal(out["pose_t"][:3], prob["pose_t"][:3])
+    np.testing.assert_array_equal(out["point_xyz"][::7], prob["point_xyz"][::7])
+
+
+def test_ba_free_gauge_and_rejected_steps():
+    # no fixed keyframe at all (server map without client 1): only the LM damping regularises
+    prob = ba_problem(15, 800, seed=9, n_fusion=0)
+    prob["pose_fixed"][:] = 0
+    _check(prob, iters=5, rms_tol=1e-4)
+    # a badly perturbed start provokes rejected trials; the accept/reject sequence must still agree
+    prob = ba_problem(15, 800, seed=11, n_fusion=0)
+    rng = np.random.default_rng(1)
+    prob["point_xyz"] += rng.normal(0, 1.5, prob["point_xyz"].shape)
+    prob["pose_t"][1:] += rng.normal(0, 0.8, prob["pose_t"][1:].shape)
+    o_info, g_info, _ = _check(prob, iters=10, rms_tol=1e-3)
+
+
+def test_ba_stop_flag_and_degenerate_inputs():
+    prob = ba_problem(20, 1000, seed=2)
+    stop = np.ones(1, np.uint8)
+    out, info = Optimizer.BundleAdjustment(prob, 10, pbStopFlag=stop, bRobust=False)
+    assert info["iterations"] == 0 and info["stopped"] == 1
+    np.testing.assert_array_equal(out["point_xyz"], prob["point_xyz"])
+    # zero iterations / points without edges / an empty problem
+    out, info = Optimizer.BundleAdjustment(prob, 0, bRobust=False)
+    assert info["iterations"] == 0
+    lonely = dict(prob)
+    lonely["point_xyz"] = np.vstack([prob["point_xyz"], [[1.0, 2.0, 30.0]]])
+    lonely["point_fixed"] = np.append(prob["point_fixed"], 0).astype(np.uint8)
+    o_out, o_info = B.solve(lonely, 4)
+    g_out, g_info = Optimizer.BundleAdjustment(lonely, 4, bRobust=False)
+    assert g_info["trial_accepted"] == o_info["trial_accepted"]
+    np.testing.assert_array_equal(g_out["point_xyz"][-1], [1.0, 2.0, 30.0])
+    with pytest.raises(Exception):
+        bad = dict(prob)
+        bad["edge_pose"] = prob["edge_pose"].copy()
+        bad["edge_pose"][0] = 10 ** 6
+        Optimizer.BundleAdjustment(bad, 1, bRobust=False)
