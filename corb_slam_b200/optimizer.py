@@ -45,11 +45,12 @@ def torch_allreduce(group=None):
 class Optimizer:
     @staticmethod
     def BundleAdjustment(problem, nIterations=5, pbStopFlag=None, nLoopKF=0, bRobust=True, device=0, allreduce=None):
-        """problem: dict with the arrays of corb_ba_problem (see corb_slam_b200.synth.ba_problem). pose_q / pose_t /
-        point_xyz are updated in place (they must be C-contiguous float64 arrays to be updated in place; otherwise the
-        returned dict holds the updated copies). pbStopFlag: optional np.uint8 array of one element polled by the solver.
+        """problem: dict with the arrays of corb_ba_problem (see corb_slam_b200.synth.ba_problem). The returned dict
+        holds updated copies of pose_q / pose_t / point_xyz (the reference writes mTcwGBA / mPosGBA, Optimizer.cc:219-263). pbStopFlag: optional np.uint8 array of one element polled by the solver.
         Returns (problem_out, info)."""
         keep = {k: np.ascontiguousarray(problem[k], _DT[k]) for k in _DT}
+        for k in ("pose_q", "pose_t", "point_xyz"):  # outputs are returned as copies, inputs stay untouched
+            keep[k] = keep[k].copy()
         p = BaProblem()
         p.n_poses, p.n_points, p.n_edges = len(keep["pose_fixed"]), len(keep["point_fixed"]), len(keep["edge_pose"])
         for k in _DT:

@@ -47,6 +47,8 @@ _DT = {"pose_q": np.float64, "pose_t": np.float64, "pose_fixed": np.uint8, "pose
 def make_problem(prob):
     """dict of arrays (corb_slam_b200.synth.ba_problem layout) -> (ctypes struct, keep-alive dict of contiguous arrays)."""
     keep = {k: np.ascontiguousarray(prob[k], _DT[k]) for k in _DT}
+    for k in ("pose_q", "pose_t", "point_xyz"):  # outputs: never write into the caller's arrays
+        keep[k] = keep[k].copy()
     p = Problem()
     p.n_poses, p.n_points, p.n_edges = len(keep["pose_fixed"]), len(keep["point_fixed"]), len(keep["edge_pose"])
     for k in _DT:
