@@ -106,6 +106,30 @@ def cpu_extract_fps(n_frames, clients=1):
     return clients * n_frames / dt, dt
 
 
+BA_P, BA_L, BA_ITERS = 2000, 200000, 10  # SURVEY.md §8d / BASELINE.json config #5 synthetic global-BA problem
+
+
+def ba_algorithmic_bytes(n_edges, n_points, n_poses, nnz_blocks):
+    """bytes one LM iteration must move (edges, landmarks, poses, reduced-system blocks)."""
+    return 552 * n_edges + 216 * n_points + 440 * n_poses + 288 * nnz_blocks
+
+
+def cpu_ba(n_poses, n_points):
+    """Oracle port of Optimizer::BundleAdjustment (single thread like g2o, Thirdparty/g2o/config.h:4)."""
+    import oracle
+    from oracle import _ba_bind as B
+    from corb_slam_b200.synth import ba_problem
+    oracle.lib()
+    prob = ba_problem(n_poses, n_points, seed=7)
+    t0 = time.perf_counter()
+    out, info = B.solve(prob, BA_ITERS, robust=False)
+    dt = time.perf_counter() - t0
+    return {"value": 1e3 * dt / (n_points / 1e4), "unit": "ms/10k landmarks", "cores": 1, "kind": "port",
+            "sample": "P=%d keyframes, L=%d landmarks, E=%d observations, %d LM iterations, %.1f s"
+                      % (n_poses, n_points, len(prob["edge_pose"]), info["iterations"], dt),
+            "iterations": info["iterations"], "chi2_final": info["chi2_final"], "rms_px": B.chi2(out)[1]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,6 +159,8 @@ def run_reference(args):
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_ba:
+        line["ba"] = dict(cpu_ba(BA_P, BA_L), metric="global_ba_ms_per_10k_landmarks", higher_is_better=False, impl="reference")
     print(json.dumps(line))
 
 
@@ -222,10 +248,34 @@ def run_ours(args):
     e2e_pyr_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_pyr_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---- global BA (second half of the BASELINE.json metric): landmark-sharded over the ranks, reduced camera system
+    #      all-reduced over NCCL from inside corb_ba_solve when more than one GPU is attached
+    ba_info, ba_ms, ba_rms, ba_edges = None, 0.0, None, 0
+    if not args.no_ba:
+        from corb_slam_b200 import Optimizer, torch_allreduce
+        from corb_slam_b200.synth import ba_problem, ba_shard
+        prob = ba_problem(BA_P, BA_L, seed=7)
+        ba_edges = len(prob["edge_pose"])
+        mine = ba_shard(prob, rank, world) if world > 1 else prob
+        cb = torch_allreduce() if world > 1 else None
+        Optimizer.BundleAdjustment(ba_shard(ba_problem(50, 2000, seed=1), rank, world) if world > 1 else ba_problem(50, 2000, seed=1),
+                                   2, bRobust=False, device=local, allreduce=cb)  # warm-up (context, NCCL channels)
+        barrier()
+        t0 = time.perf_counter()
+        ba_out, ba_info = Optimizer.BundleAdjustment(mine, BA_ITERS, bRobust=False, device=local, allreduce=cb)
+        torch.cuda.synchronize()
+        ba_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if rank == 0 and world == 1:
+            import oracle
+            from oracle import _ba_bind as B
+            oracle.lib()
+            ba_rms = B.chi2(ba_out)[1]  # checker only: RMS reprojection error of the GPU solution
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_pyr_s * 1e3, ba_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_pyr_ms = [float(x) for x in t.tolist()]
+    dev_ms, e2e_ms, e2e_pyr_ms, ba_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
         # per-kernel times of one image (eager replay with events) for the roofline of the dominant kernel
@@ -268,6 +318,26 @@ def run_ours(args):
                                        % (args.sample_frames, cpu_dt), "host_cores_available": os.cpu_count()},
             "keypoints_per_frame": kp_per_frame,
         }
+        if ba_info is not None:
+            ba_bytes = ba_algorithmic_bytes(ba_edges, BA_L, BA_P, ba_info["reduced_blocks"]) * ba_info["iterations"]
+            ach = ba_bytes / (ba_ms * 1e-3) / 1e9
+            line["ba"] = {
+                "metric": "global_ba_ms_per_10k_landmarks", "value": ba_ms / (BA_L / 1e4), "unit": "ms/10k landmarks",
+                "higher_is_better": False, "n_gpus": world, "scaling": "strong", "dtype": "f64",
+                "config": {"workload": "synthetic street BA: P=%d keyframes, L=%d landmarks, E=%d observations (80%% stereo), "
+                                       "%d LM iterations, bRobust=false, seed 7" % (BA_P, BA_L, ba_edges, BA_ITERS),
+                           "sharding": "landmarks l %% N per rank, poses replicated, all-reduce(sum, fp64) of the reduced "
+                                       "camera system per LM trial" if world > 1 else "single GPU, no collective"},
+                "ms_total": ba_ms, "ms_in_library": ba_info["ms_total"], "ms_reduced_camera_solves": ba_info["ms_solve"],
+                "iterations": ba_info["iterations"], "trials": ba_info["n_trials"], "trial_accepted": ba_info["trial_accepted"],
+                "chi2_initial": ba_info["chi2_initial"], "chi2_final": ba_info["chi2_final"], "rms_px": ba_rms,
+                "reduced_blocks": ba_info["reduced_blocks"],
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                             "algorithmic_bytes_per_iteration": ba_bytes // max(1, ba_info["iterations"]),
+                             "note": "whole-call wall time incl. host structure build and H2D/D2H; the single-CTA "
+                                     "block-skyline solve is latency bound"},
+                "cpu_baseline": cpu_ba(BA_P, BA_L) if not args.no_cpu_ba else None,
+            }
         print(json.dumps(line))
     exl.close(); exr.close()
     if world > 1:
@@ -281,6 +351,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sample-frames", type=int, default=200, help="stereo frames of the bounded CPU baseline sample")
+    ap.add_argument("--no-ba", action="store_true", help="skip the global-BA half of the metric")
+    ap.add_argument("--no-cpu-ba", action="store_true", help="skip the CPU BA baseline (about 10 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,241 @@
+"""CPU suite: pins the oracle's OpenCV-primitive models against golden vectors produced by the real cv2 4.13.0
+(tests/golden/opencv_primitives.npz, made by tools/gen_golden.py), checks the reference's source constants and the
+composed extractor's invariants, and the matching / BoW / BA restatements by algebra."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import _ba_bind as B
+from oracle import _match_bind as M
+from corb_slam_b200.synth import ba_problem, ba_shard, stereo_frame
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    oracle.lib()
+    return np.load(os.path.join(GOLD, "opencv_primitives.npz"))
+
+
+# ------------------------------------------------------------------------------------------------ OpenCV primitives
+def test_resize_linear_matches_cv2_golden(gold):
+    for name, sizes in (("scene", [(267, 167), (222, 139), (185, 116)]), ("noise", [(109, 81), (91, 67), (40, 23)])):
+        cur = gold["img_" + name]
+        for i, (w, h) in enumerate(sizes):
+            got = oracle.resize_linear(cur, w, h)
+            np.testing.assert_array_equal(got, gold["resize_%s_%d" % (name, i)])
+            cur = got
+
+
+def test_gaussian7_matches_cv2_golden(gold):
+    for name in ("scene", "noise", "tiny"):
+        np.testing.assert_array_equal(oracle.gaussian7(gold["img_" + name]), gold["blur_" + name])
+
+
+def test_fast_matches_cv2_golden(gold):
+    for name in ("scene", "noise", "cell"):
+        for th in (20, 7):
+            got = oracle.fast_detect(gold["img_" + name], th)
+            np.testing.assert_array_equal(got, gold["fast_%s_%d" % (name, th)])  # order, position and response
+            # the score map alone reproduces the detector: corner at th <=> score >= th, strict 8-neighbour maximum
+            sc = oracle.fast_score(gold["img_" + name]).astype(np.int32)
+            m = np.where(sc >= th, sc, 0)
+            keep = []
+            for y, x in zip(*np.nonzero(m)):
+                nb = m[y - 1:y + 2, x - 1:x + 2].copy()
+                nb[1, 1] = -1
+                if (m[y, x] > nb).all():
+                    keep.append((x, y, m[y, x]))
+            np.testing.assert_array_equal(np.array(keep, np.int32).reshape(-1, 3), got)
+
+
+def test_fast_atan2_matches_cv2_golden(gold):
+    got = np.array([oracle.fast_atan2(y, x) for y, x in zip(gold["atan2_y"], gold["atan2_x"])], np.float32)
+    np.testing.assert_array_equal(got.view(np.uint32), gold["atan2_deg"].view(np.uint32))
+
+
+def test_cv_round_half_to_even():
+    assert [oracle.cv_round(v) for v in (0.5, 1.5, 2.5, -0.5, -1.5, 2.4999, 2.5001)] == [0, 2, 2, 0, -2, 2, 3]
+
+
+def test_live_cv2_if_available():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (75, 113), dtype=np.uint8)
+    np.testing.assert_array_equal(oracle.resize_linear(img, 94, 62), cv2.resize(img, (94, 62), interpolation=cv2.INTER_LINEAR))
+    np.testing.assert_array_equal(oracle.gaussian7(img), cv2.GaussianBlur(img, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101))
+
+
+# ------------------------------------------------------------------------------------------------ extractor
+def test_constructor_tables_match_survey_appendix_a():
+    ex = oracle.OrbExtractor(2000, 1.2, 8, 20, 7)
+    assert list(ex.quota) == [434, 362, 302, 251, 209, 175, 145, 122] and ex.quota.sum() == 2000
+    assert list(ex.umax) == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]  # ORBextractor.cc:452-469
+    assert np.float32(ex.scale[6]) == np.float32(2.9859846) and np.float32(ex.scale[7]) == np.float32(3.5831816)
+    table = {(1242, 375): [(1242, 375), (1035, 312), (862, 260), (719, 217), (599, 181), (499, 151), (416, 126), (347, 105)],
+             (1241, 376): [(1241, 376), (1034, 313), (862, 261), (718, 218), (598, 181), (499, 151), (416, 126), (346, 105)],
+             (1226, 370): [(1226, 370), (1022, 308), (851, 257), (709, 214), (591, 178), (493, 149), (411, 124), (342, 103)]}
+    for (w, h), levels in table.items():
+        assert [ex.level_size(l, w, h) for l in range(8)] == levels
+    assert sum(a * b for a, b in table[(1242, 375)]) == 1441432
+    assert ex.capacity(1242, 375) == 2000 + 3 * 8
+    assert ex.capacity(40, 40) < 0  # smaller than the 30 px FAST grid: the reference cannot process it either
+
+
+def test_extractor_invariants_and_regression():
+    left, right = stereo_frame(1234, w=640, h=240)
+    ex = oracle.OrbExtractor(500, 1.2, 4, 20, 7)
+    kps, desc = ex(left)
+    ref = np.load(os.path.join(GOLD, "oracle_extract_640x240.npz"))
+    assert kps.tobytes() == ref["kps"].tobytes()
+    np.testing.assert_array_equal(desc, ref["desc"])
+    kps2, desc2 = ex(left)
+    assert kps2.tobytes() == kps.tobytes()  # deterministic, no state carried between frames
+    for l in range(4):
+        n, q = ex.level_count(l), ex.quota[l]
+        assert q <= n <= q + 2 or n == len(ex.candidates(l))  # DistributeOctTree overshoots by at most 2
+        lw, lh = ex.level_size(l, 640, 240)
+        k = kps[kps["octave"] == l]
+        x = k["x"] / ex.scale[l] if l else k["x"]
+        y = k["y"] / ex.scale[l] if l else k["y"]
+        assert (np.rint(x) >= 19).all() and (np.rint(x) < lw - 19).all() and (np.rint(y) >= 19).all() and (np.rint(y) < lh - 19).all()
+        assert (k["size"] == np.float32(int(31 * ex.scale[l]))).all()
+    assert (kps["class_id"] == -1).all() and (kps["angle"] >= 0).all() and (kps["angle"] < 360).all()
+    # stage taps agree with the primitives
+    np.testing.assert_array_equal(ex.pyramid(1), oracle.resize_linear(left, *ex.level_size(1, 640, 240)))
+    np.testing.assert_array_equal(ex.blurred(1), oracle.gaussian7(ex.pyramid(1)))
+    k0 = kps[0]
+    assert oracle.ic_angle(ex.pyramid(0), int(k0["x"]), int(k0["y"]), ex.umax) == k0["angle"]
+    np.testing.assert_array_equal(oracle.brief(ex.blurred(0), int(k0["x"]), int(k0["y"]), k0["angle"]), desc[0])
+
+
+def test_flat_and_empty_images():
+    ex = oracle.OrbExtractor(1000, 1.2, 8, 20, 7)
+    kps, desc = ex(np.full((375, 1242), 9, np.uint8))
+    assert len(kps) == 0
+    with pytest.raises(ValueError):
+        ex(np.zeros((40, 40), np.uint8))
+
+
+# ------------------------------------------------------------------------------------------------ matching / BoW
+def test_hamming_is_popcount():
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (50, 32), dtype=np.uint8)
+    for x, y in zip(a, b):
+        assert M.hamming256(x, y) == int(np.unpackbits(x ^ y).sum())
+
+
+def test_bow_transform_and_score_properties():
+    voc = M.Vocabulary.from_arrays(*M.random_vocabulary(10, 3, 0))
+    rng = np.random.default_rng(2)
+    d = rng.integers(0, 256, (800, 32), dtype=np.uint8)
+    words, vals, fn, fo, fi = voc.transform(d, 2)
+    assert (np.diff(words.astype(np.int64)) > 0).all() and vals.sum() == pytest.approx(1.0, abs=1e-12)
+    assert (np.diff(fn.astype(np.int64)) > 0).all() and fo[-1] == len(fi) and len(set(fi.tolist())) == len(fi)
+    w, wt, nid = voc.transform_features(d, 2)
+    assert len(fi) == int((wt > 0).sum())  # stopped words (weight 0) are dropped (TemplatedVocabulary.h:1157)
+    assert voc.score((words, vals), (words, vals)) == pytest.approx(1.0, abs=1e-12)
+    other = voc.transform(rng.integers(0, 256, (800, 32), dtype=np.uint8), 2)
+    s = voc.score((words, vals), other[:2])
+    assert 0.0 <= s < 1.0 and s == voc.score(other[:2], (words, vals))
+
+
+def test_search_by_bow_semantics():
+    voc = M.Vocabulary.from_arrays(*M.random_vocabulary(10, 3, 0))
+    rng = np.random.default_rng(3)
+    d = rng.integers(0, 256, (600, 32), dtype=np.uint8)
+    b = voc.transform(d, 2)
+    ang = rng.uniform(0, 360, 600).astype(np.float32)
+    A = M.Side(d, b[2], b[3], b[4], angles=ang)
+    for variant in (0, 1, 2):
+        m, n = M.search_by_bow(variant, A, A, 0.75, True)
+        used = np.nonzero(b[1] >= 0)[0]
+        assert n == int((m >= 0).sum()) and (m[m >= 0] == np.nonzero(m >= 0)[0]).all()  # self-match is the identity
+    # ties: identical descriptors make best == second best, so the ratio test rejects (App. D.3)
+    dd = np.tile(d[:1], (30, 1))
+    bb = voc.transform(dd, 2)
+    T = M.Side(dd, bb[2], bb[3], bb[4])
+    assert M.search_by_bow(0, T, T, 0.9, False)[1] == 0
+    # dead MapPoints on side A are skipped; variant 2 also honours side B
+    valid = np.zeros(600, np.uint8)
+    A0 = M.Side(d, b[2], b[3], b[4], valid=valid, angles=ang)
+    assert M.search_by_bow(0, A0, A, 0.75, True)[1] == 0 and M.search_by_bow(2, A, A0, 0.75, True)[1] == 0
+
+
+# ------------------------------------------------------------------------------------------------ bundle adjustment
+def test_ba_jacobians_against_central_differences():
+    oracle.lib()
+    prob = ba_problem(10, 300, seed=1)
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, len(prob["edge_pose"]), 12):
+        pi, li = prob["edge_pose"][i], prob["edge_point"][i]
+        q, t, cam, X = prob["pose_q"][pi], prob["pose_t"][pi], prob["pose_cam"][pi], prob["point_xyz"][li]
+        for obs, h, tol in ((np.array([*prob["edge_obs"][i][:2], -1.0]), 1e-6, 1e-5),       # monocular edge
+                            (np.array([*prob["edge_obs"][i][:2], 300.0]), 1e-3, 5e-3)):     # stereo: invz is float32
+            e, A, J = B.edge(q, t, cam, X, obs)
+            An, Jn = np.zeros_like(A), np.zeros_like(J)
+            for c in range(3):
+                d = np.zeros(3); d[c] = h
+                An[:, c] = (B.edge(q, t, cam, X + d, obs)[0] - B.edge(q, t, cam, X - d, obs)[0]) / (2 * h)
+            for c in range(6):
+                d = np.zeros(6); d[c] = h
+                qp, tp = B.pose_oplus(q, t, d)
+                qm, tm = B.pose_oplus(q, t, -d)
+                Jn[:, c] = (B.edge(qp, tp, cam, X, obs)[0] - B.edge(qm, tm, cam, X, obs)[0]) / (2 * h)
+            assert np.abs(A - An).max() < tol * max(1.0, np.abs(A).max())
+            assert np.abs(J - Jn).max() < tol * max(1.0, np.abs(J).max())
+
+
+def test_ba_converges_monotonically_and_respects_lm_constants():
+    prob = ba_problem(20, 2000, seed=7, n_fusion=10)
+    out, info = B.solve(prob, 10)
+    chi = [info["chi2_initial"]] + [c for c, a in zip(info["trial_chi2"], info["trial_accepted"]) if a]
+    assert all(b < a for a, b in zip(chi, chi[1:]))            # chi2 strictly decreases over accepted steps
+    assert info["chi2_final"] == chi[-1] and info["iterations"] == 10
+    assert B.chi2(out)[1] < 1.1 and B.chi2(prob)[1] > 5.0      # RMS reprojection error in pixels
+    np.testing.assert_array_equal(out["pose_t"][0], prob["pose_t"][0])  # the fixed keyframe does not move
+    assert prob["pose_t"] is not out["pose_t"]
+    # lambda0 = 1e-5 * max diag(H) (optimization_algorithm_levenberg.cpp:47,166-180)
+    assert 1e2 < info["lambda_initial"] < 1e5
+    # stop flag polled before the first iteration
+    out2, info2 = B.solve(prob, 10, stop=np.ones(1, np.uint8))
+    assert info2["iterations"] == 0 and info2["stopped"] == 1
+
+
+def test_ba_landmark_sharding_sums_to_the_same_system():
+    """Two shards whose partial reduced systems are summed through the all-reduce hook equal the unsharded solve."""
+    prob = ba_problem(15, 900, seed=4, n_fusion=6)
+    full, info = B.solve(prob, 6)
+    shards = [ba_shard(prob, r, 2) for r in range(2)]
+    # emulate the collective in-process: run rank 0 and rank 1 in lock step with threads
+    import threading
+    bar = threading.Barrier(2)
+    slots = [None, None]
+    results = [None, None]
+
+    def make_cb(rank):
+        def cb(arr, op):
+            slots[rank] = arr.copy()
+            bar.wait()
+            a, b = slots
+            res = a + b if op == 0 else (np.minimum(a, b) if op == 1 else np.maximum(a, b))
+            bar.wait()
+            arr[:] = res
+        return cb
+
+    def run(rank):
+        results[rank] = B.solve(shards[rank], 6, allreduce=make_cb(rank))
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for r in range(2):
+        out, inf = results[r]
+        assert inf["trial_accepted"] == info["trial_accepted"]
+        np.testing.assert_allclose(out["pose_t"], full["pose_t"], atol=1e-8)
+        np.testing.assert_allclose(out["point_xyz"], full["point_xyz"][shards[r]["_point_ids"]], atol=1e-8)
+    np.testing.assert_array_equal(results[0][0]["pose_q"], results[1][0]["pose_q"])  # ranks end with identical poses
