@@ -398,77 +398,175 @@ __global__ void __launch_bounds__(256) k_ba_add_lambda(BaDev d, double lambda) {
 
 // ---- K12: block-skyline Cholesky + forward/backward substitution, one CTA. Row j holds block columns first[j]..j;
 //      col_rows[coloff[k]..coloff[k+1]) lists the rows j > k whose envelope contains column k (ascending).
+//
+//      Right-looking with one-column look-ahead, two barriers per column:
+//        B: every active row solves its block against L_kk (L_jk = A_jk L_kk^-T) and stages it in shared memory;
+//           one thread finishes y_k = L_kk^-1 b_k (the forward substitution rides along with the factorisation)
+//        C: warp 0 updates and factors the next diagonal block while the other warps apply the trailing update
+//           A_ji -= L_jk L_ik^T over all active pairs from shared memory (4 pairs in flight per warp to cover the
+//           L2 round trip of the read-modify-write) and b_j -= L_jk y_k
 constexpr int kSolveThreads = 1024;
-__global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d) {
-    __shared__ double Lkk[36];
-    __shared__ double xk[6];
+constexpr int kSolveWarps = kSolveThreads / 32;
+
+__device__ __forceinline__ bool chol6(double* a) {  // in place, lower; upper part zeroed
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        double s = a[c * 6 + c];
+#pragma unroll
+        for (int p = 0; p < c; p++) s -= a[c * 6 + p] * a[c * 6 + p];
+        if (!(s > 0.0)) { ok = false; s = 1.0; }
+        const double dd = sqrt(s);
+        a[c * 6 + c] = dd;
+        const double inv = 1.0 / dd;
+#pragma unroll
+        for (int r = c + 1; r < 6; r++) {
+            double v = a[r * 6 + c];
+#pragma unroll
+            for (int p = 0; p < c; p++) v -= a[r * 6 + p] * a[c * 6 + p];
+            a[r * 6 + c] = v * inv;
+        }
+#pragma unroll
+        for (int r = 0; r < c; r++) a[r * 6 + c] = 0.0;
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_cap) {
+    extern __shared__ double Lact[];  // [lact_cap][36] staged L_jk of the active rows of the current column
+    __shared__ double Lkk[2][36];
+    __shared__ double yk[6];
     __shared__ int s_fail;
-    const int tid = threadIdx.x, n = d.Pf;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = d.Pf;
     if (tid == 0) s_fail = 0;
     for (int i = tid; i < n * 6; i += kSolveThreads) d.xp[i] = d.bs[i];
+    if (tid == 0 && n > 0) {
+        double a[36];
+        double* D = d.S + (size_t)(d.rowoff[0] - d.first[0]) * 36;
+#pragma unroll
+        for (int i = 0; i < 36; i++) a[i] = D[i];
+        if (!chol6(a)) s_fail = 1;
+#pragma unroll
+        for (int i = 0; i < 36; i++) { D[i] = a[i]; Lkk[0][i] = a[i]; }
+    }
     __syncthreads();
     for (int k = 0; k < n; k++) {
-        double* D = d.S + (size_t)(d.rowoff[k] + k - d.first[k]) * 36;
-        if (tid == 0) {
-            double a[36];
-#pragma unroll
-            for (int i = 0; i < 36; i++) a[i] = D[i];
-            bool ok = true;
-#pragma unroll
-            for (int c = 0; c < 6; c++) {
-                double s = a[c * 6 + c];
-#pragma unroll
-                for (int p = 0; p < c; p++) s -= a[c * 6 + p] * a[c * 6 + p];
-                if (!(s > 0.0)) { ok = false; s = 1.0; }
-                const double dd = sqrt(s);
-                a[c * 6 + c] = dd;
-                const double inv = 1.0 / dd;
-#pragma unroll
-                for (int r = c + 1; r < 6; r++) {
-                    double v = a[r * 6 + c];
-#pragma unroll
-                    for (int p = 0; p < c; p++) v -= a[r * 6 + p] * a[c * 6 + p];
-                    a[r * 6 + c] = v * inv;
-                }
-#pragma unroll
-                for (int r = 0; r < c; r++) a[r * 6 + c] = 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < 36; i++) { D[i] = a[i]; Lkk[i] = a[i]; }
-            if (!ok) s_fail = 1;
-        }
-        __syncthreads();
         if (s_fail) break;
+        const double* Lk = Lkk[k & 1];
         const int cb = d.coloff[k], nact = d.coloff[k + 1] - cb;
         const int* rows = d.col_rows + cb;
-        for (int it = tid; it < nact * 6; it += kSolveThreads) {  // L_jk = A_jk L_kk^-T, one block row per thread
-            const int j = rows[it / 6], r = it % 6;
+        const bool staged = nact <= lact_cap;
+        // ---- phase B
+        for (int it = tid; it < nact * 6; it += kSolveThreads) {
+            const int a = it / 6, r = it - a * 6;
+            const int j = rows[a];
             double* B = d.S + (size_t)(d.rowoff[j] + k - d.first[j]) * 36 + r * 6;
             double v[6];
 #pragma unroll
             for (int c = 0; c < 6; c++) {
                 double s = B[c];
 #pragma unroll
-                for (int p = 0; p < c; p++) s -= v[p] * Lkk[c * 6 + p];
-                v[c] = s / Lkk[c * 6 + c];
+                for (int p = 0; p < c; p++) s -= v[p] * Lk[c * 6 + p];
+                v[c] = s / Lk[c * 6 + c];
             }
 #pragma unroll
             for (int c = 0; c < 6; c++) B[c] = v[c];
+            if (staged) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) Lact[a * 36 + r * 6 + c] = v[c];
+            }
+        }
+        if (tid == kSolveThreads - 1) {  // y_k = L_kk^-1 b_k
+            double v[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                double s = d.xp[k * 6 + r];
+#pragma unroll
+                for (int p = 0; p < r; p++) s -= Lk[r * 6 + p] * v[p];
+                v[r] = s / Lk[r * 6 + r];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) { d.xp[k * 6 + r] = v[r]; yk[r] = v[r]; }
         }
         __syncthreads();
-        const int items = nact * nact * 36;  // A_ji -= L_jk L_ik^T for active j >= i
-        for (int it = tid; it < items; it += kSolveThreads) {
-            const int pr = it / 36, rc = it - pr * 36;
-            const int a = pr / nact, b = pr - a * nact;
-            if (b > a) continue;
-            const int j = rows[a], i = rows[b];
-            const int r = rc / 6, c = rc - r * 6;
-            const double* Lj = d.S + (size_t)(d.rowoff[j] + k - d.first[j]) * 36 + r * 6;
-            const double* Li = d.S + (size_t)(d.rowoff[i] + k - d.first[i]) * 36 + c * 6;
-            double s = 0;
+        // ---- phase C
+        const bool next_active = nact > 0 && rows[0] == k + 1;  // rows ascend, so k+1 can only be the first entry
+        if (warp == 0) {
+            if (lane == 0 && k + 1 < n) {
+                double a[36];
+                double* D = d.S + (size_t)(d.rowoff[k + 1] + (k + 1) - d.first[k + 1]) * 36;
 #pragma unroll
-            for (int p = 0; p < 6; p++) s += Lj[p] * Li[p];
-            d.S[(size_t)(d.rowoff[j] + i - d.first[j]) * 36 + rc] -= s;
+                for (int i = 0; i < 36; i++) a[i] = D[i];
+                if (next_active) {
+                    const double* L0 = staged ? Lact : d.S + (size_t)(d.rowoff[k + 1] + k - d.first[k + 1]) * 36;
+#pragma unroll
+                    for (int r = 0; r < 6; r++)
+#pragma unroll
+                        for (int c = 0; c < 6; c++) {
+                            double s = 0;
+#pragma unroll
+                            for (int p = 0; p < 6; p++) s += L0[r * 6 + p] * L0[c * 6 + p];
+                            a[r * 6 + c] -= s;
+                        }
+                }
+                if (!chol6(a)) s_fail = 1;
+#pragma unroll
+                for (int i = 0; i < 36; i++) { D[i] = a[i]; Lkk[(k + 1) & 1][i] = a[i]; }
+            }
+        } else if (warp == 1) {  // b_j -= L_jk y_k
+            for (int it = lane; it < nact * 6; it += 32) {
+                const int a = it / 6, r = it - a * 6;
+                const int j = rows[a];
+                const double* Lr = staged ? Lact + a * 36 + r * 6 : d.S + (size_t)(d.rowoff[j] + k - d.first[j]) * 36 + r * 6;
+                double s = 0;
+#pragma unroll
+                for (int c = 0; c < 6; c++) s += Lr[c] * yk[c];
+                d.xp[j * 6 + r] -= s;
+            }
+        } else {
+            // pairs (a >= b) of active rows, linear index p = a (a + 1) / 2 + b; pair 0 = (0, 0) is warp 0's when next_active
+            const int npairs = nact * (nact + 1) / 2;
+            const int p_begin = next_active ? 1 : 0;
+            const int r0 = lane / 6, c0 = lane - r0 * 6, c1 = 2 + lane;  // entries `lane` and `32 + lane` (lane < 4)
+            constexpr int U = 4;
+            for (int base = p_begin + (warp - 2) * U; base < npairs; base += (kSolveWarps - 2) * U) {
+                int pa[U], pb[U], toff[U];
+                double t0[U], t1[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int p = base + u;
+                    toff[u] = -1;
+                    if (p < npairs) {
+                        int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+                        while (a * (a + 1) / 2 > p) a--;
+                        while ((a + 1) * (a + 2) / 2 <= p) a++;
+                        const int b = p - a * (a + 1) / 2;
+                        const int j = rows[a];
+                        pa[u] = a;
+                        pb[u] = b;
+                        toff[u] = (d.rowoff[j] + rows[b] - d.first[j]) * 36;
+                        t0[u] = d.S[(size_t)toff[u] + lane];
+                        t1[u] = lane < 4 ? d.S[(size_t)toff[u] + 32 + lane] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (toff[u] >= 0) {
+                        const int ja = rows[pa[u]], jb = rows[pb[u]];
+                        const double* La = staged ? Lact + pa[u] * 36 : d.S + (size_t)(d.rowoff[ja] + k - d.first[ja]) * 36;
+                        const double* Lb = staged ? Lact + pb[u] * 36 : d.S + (size_t)(d.rowoff[jb] + k - d.first[jb]) * 36;
+                        double s0 = 0, s1 = 0;
+#pragma unroll
+                        for (int q = 0; q < 6; q++) s0 += La[r0 * 6 + q] * Lb[c0 * 6 + q];
+                        d.S[(size_t)toff[u] + lane] = t0[u] - s0;
+                        if (lane < 4) {
+#pragma unroll
+                            for (int q = 0; q < 6; q++) s1 += La[30 + q] * Lb[c1 * 6 + q];
+                            d.S[(size_t)toff[u] + 32 + lane] = t1[u] - s1;
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -478,34 +576,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d) {
         return;
     }
     if (tid == 0) d.scalars[4] = 0.0;
-    // forward: L y = b (column oriented)
-    for (int k = 0; k < n; k++) {
-        const double* D = d.S + (size_t)(d.rowoff[k] + k - d.first[k]) * 36;
-        if (tid == 0) {
-            double v[6];
-#pragma unroll
-            for (int r = 0; r < 6; r++) {
-                double s = d.xp[k * 6 + r];
-#pragma unroll
-                for (int p = 0; p < r; p++) s -= D[r * 6 + p] * v[p];
-                v[r] = s / D[r * 6 + r];
-            }
-#pragma unroll
-            for (int r = 0; r < 6; r++) { d.xp[k * 6 + r] = v[r]; xk[r] = v[r]; }
-        }
-        __syncthreads();
-        const int cb = d.coloff[k], nact = d.coloff[k + 1] - cb;
-        for (int it = tid; it < nact * 6; it += kSolveThreads) {
-            const int j = d.col_rows[cb + it / 6], r = it % 6;
-            const double* Lr = d.S + (size_t)(d.rowoff[j] + k - d.first[j]) * 36 + r * 6;
-            double s = 0;
-#pragma unroll
-            for (int c = 0; c < 6; c++) s += Lr[c] * xk[c];
-            d.xp[j * 6 + r] -= s;
-        }
-        __syncthreads();
-    }
-    // backward: L^T x = y (row oriented)
+    // ---- backward: L^T x = y (row oriented); xp already holds y from the fused forward pass
     for (int j = n - 1; j >= 0; j--) {
         const int fj = d.first[j];
         const double* rowp = d.S + (size_t)d.rowoff[j] * 36;
@@ -520,7 +591,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d) {
                 v[r] = s / D[r * 6 + r];
             }
 #pragma unroll
-            for (int r = 0; r < 6; r++) { d.xp[j * 6 + r] = v[r]; xk[r] = v[r]; }
+            for (int r = 0; r < 6; r++) { d.xp[j * 6 + r] = v[r]; yk[r] = v[r]; }
         }
         __syncthreads();
         for (int it = tid; it < (j - fj) * 6; it += kSolveThreads) {
@@ -528,7 +599,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d) {
             const double* Lb = rowp + (size_t)(i - fj) * 36;
             double s = 0;
 #pragma unroll
-            for (int r = 0; r < 6; r++) s += Lb[r * 6 + c] * xk[r];
+            for (int r = 0; r < 6; r++) s += Lb[r * 6 + c] * yk[r];
             d.xp[i * 6 + c] -= s;
         }
         __syncthreads();
@@ -644,6 +715,7 @@ struct BaHost {
     std::vector<void*> allocs;
     BaDev d;
     size_t s_doubles = 0;  // S blocks * 36
+    int lact_cap = 0;      // active rows of one column that fit the solve kernel's shared memory
     corb_allreduce_fn ar = nullptr;
     void* ar_user = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -734,7 +806,7 @@ struct BaHost {
         if (rc != CORB_OK) return rc;
         if (d.Pf > 0) k_ba_add_lambda<<<(d.Pf * 6 + 255) / 256, 256, 0, stream>>>(d, lambda);
         cudaEventRecord(ev0, stream);
-        k_ba_solve<<<1, kSolveThreads, 0, stream>>>(d);
+        k_ba_solve<<<1, kSolveThreads, (size_t)lact_cap * 36 * sizeof(double), stream>>>(d, lact_cap);
         cudaEventRecord(ev1, stream);
         if (d.L > 0) k_ba_backsub<<<(d.L + 255) / 256, 256, 0, stream>>>(d);
         const int nbu = std::max(1, (std::max(d.P, std::min(d.L, 1 << 20)) + 255) / 256);
@@ -819,29 +891,63 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         std::vector<int> cur(pose_off.begin(), pose_off.end() - 1);
         for (int k = 0; k < E; k++) pose_edges[cur[e_pose[k]]++] = k;
     }
-    // envelope: first[j] = smallest free pose sharing a free landmark with j
-    std::vector<double> firstd(std::max(Pf, 1));
-    for (int j = 0; j < Pf; j++) firstd[j] = j;
-    for (int l = 0; l < L; l++) {
-        if (lfree[l] < 0) continue;
-        int mn = Pf;
-        for (int k = lm_off[l]; k < lm_off[l + 1]; k++) {
-            const int pj = pfree[e_pose[k]];
-            if (pj >= 0) mn = std::min(mn, pj);
-        }
-        for (int k = lm_off[l]; k < lm_off[l + 1]; k++) {
-            const int pj = pfree[e_pose[k]];
-            if (pj >= 0) firstd[pj] = std::min(firstd[pj], (double)mn);
-        }
-    }
+    // ---- ordering + envelope. nbr_min/nbr_max[j] = smallest / largest free pose sharing a free landmark with j.
+    //      Long-range couplings (loop closures, map-fusion links) would stretch the envelope of every row they touch
+    //      back to the far keyframe; instead the smaller of the two vertex covers of the long links is ordered last
+    //      ("bordered band"): the remaining keyframes keep a narrow band and only the few border rows are long.
     int rc;
-    if (allreduce && Pf > 0) {  // all ranks must agree on the envelope
-        double* d_first;
-        if ((rc = H.alloc(&d_first, Pf)) != CORB_OK) return rc;
-        CORB_CUDA(cudaMemcpyAsync(d_first, firstd.data(), Pf * sizeof(double), cudaMemcpyHostToDevice, H.stream));
-        if ((rc = H.reduce(d_first, Pf, 1)) != CORB_OK) return rc;
-        CORB_CUDA(cudaMemcpyAsync(firstd.data(), d_first, Pf * sizeof(double), cudaMemcpyDeviceToHost, H.stream));
-        CORB_CUDA(cudaStreamSynchronize(H.stream));
+    double* d_tmp = nullptr;
+    if (allreduce && Pf > 0 && (rc = H.alloc(&d_tmp, 2 * (size_t)Pf)) != CORB_OK) return rc;
+    auto neighbour_range = [&](const std::vector<int>& idx, std::vector<double>& mn, std::vector<double>& mx) -> int {
+        mn.assign(std::max(Pf, 1), 0.0);
+        mx.assign(std::max(Pf, 1), 0.0);
+        for (int j = 0; j < Pf; j++) mn[j] = mx[j] = j;
+        for (int l = 0; l < L; l++) {
+            if (lfree[l] < 0) continue;
+            int lo = Pf, hi = -1;
+            for (int k = lm_off[l]; k < lm_off[l + 1]; k++) {
+                const int pj = idx[e_pose[k]];
+                if (pj >= 0) { lo = std::min(lo, pj); hi = std::max(hi, pj); }
+            }
+            for (int k = lm_off[l]; k < lm_off[l + 1]; k++) {
+                const int pj = idx[e_pose[k]];
+                if (pj >= 0) { mn[pj] = std::min(mn[pj], (double)lo); mx[pj] = std::max(mx[pj], (double)hi); }
+            }
+        }
+        if (allreduce && Pf > 0) {  // all ranks must agree on the structure of the reduced system
+            CORB_CUDA(cudaMemcpyAsync(d_tmp, mn.data(), Pf * sizeof(double), cudaMemcpyHostToDevice, H.stream));
+            CORB_CUDA(cudaMemcpyAsync(d_tmp + Pf, mx.data(), Pf * sizeof(double), cudaMemcpyHostToDevice, H.stream));
+            int r2 = H.reduce(d_tmp, Pf, 1);
+            if (r2 != CORB_OK) return r2;
+            r2 = H.reduce(d_tmp + Pf, Pf, 2);
+            if (r2 != CORB_OK) return r2;
+            CORB_CUDA(cudaMemcpyAsync(mn.data(), d_tmp, Pf * sizeof(double), cudaMemcpyDeviceToHost, H.stream));
+            CORB_CUDA(cudaMemcpyAsync(mx.data(), d_tmp + Pf, Pf * sizeof(double), cudaMemcpyDeviceToHost, H.stream));
+            CORB_CUDA(cudaStreamSynchronize(H.stream));
+        }
+        return CORB_OK;
+    };
+    std::vector<double> firstd, lastd;
+    if ((rc = neighbour_range(pfree, firstd, lastd)) != CORB_OK) return rc;
+    {
+        const int T = 64;  // links spanning more than T keyframes count as long-range
+        std::vector<int> up, down;
+        for (int j = 0; j < Pf; j++) {
+            if (lastd[j] - j > T) up.push_back(j);
+            if (j - firstd[j] > T) down.push_back(j);
+        }
+        const std::vector<int>& border = up.size() <= down.size() ? up : down;
+        if (!border.empty() && (int)border.size() < Pf) {
+            std::vector<uint8_t> is_border(Pf, 0);
+            for (int j : border) is_border[j] = 1;
+            std::vector<int> newidx(Pf);
+            int nxt = 0;
+            for (int j = 0; j < Pf; j++) if (!is_border[j]) newidx[j] = nxt++;
+            for (int j = 0; j < Pf; j++) if (is_border[j]) newidx[j] = nxt++;
+            for (int i = 0; i < P; i++) if (pfree[i] >= 0) pfree[i] = newidx[pfree[i]];
+            if ((rc = neighbour_range(pfree, firstd, lastd)) != CORB_OK) return rc;
+            res->border_poses = (int)border.size();
+        }
     }
     std::vector<int> first(Pf), rowoff(Pf + 1, 0), coloff(Pf + 1, 0);
     for (int j = 0; j < Pf; j++) {
@@ -860,6 +966,13 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             for (int k = first[j]; k < j; k++) col_rows[cur[k]++] = j;  // ascending j within a column
     }
     res->reduced_blocks = nblocks;
+    {
+        int max_nact = 0;
+        for (int k = 0; k < Pf; k++) max_nact = std::max(max_nact, coloff[k + 1] - coloff[k]);
+        H.lact_cap = std::max(1, std::min(max_nact, 700));
+        CORB_CUDA(cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, H.lact_cap * 36 * (int)sizeof(double)));
+        res->max_active_rows = max_nact;
+    }
     H.s_doubles = (size_t)nblocks * 36;
     // ---- device buffers
 #define UP(field, vec) if ((rc = H.upload(&d.field, vec)) != CORB_OK) return rc

@@ -231,6 +231,8 @@ typedef struct {
     double trial_chi2[256];
     double ms_total, ms_solve;   /* wall time of the whole call / device time inside the reduced-camera solves */
     int64_t reduced_blocks;      /* 6x6 blocks in the envelope of the reduced camera system */
+    int32_t border_poses;        /* keyframes ordered last because they carry long-range (loop/fusion) links */
+    int32_t max_active_rows;     /* widest front of the block-skyline factorisation */
 } corb_ba_result;
 
 /* All-reduce hook for landmark-sharded BA: `buf` is a DEVICE pointer to n doubles, reduced in place over

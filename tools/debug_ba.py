@@ -12,5 +12,5 @@ for k in ("iterations", "n_trials", "chi2_initial", "chi2_final", "lambda_initia
     print(k, o[k], g[k])
 print("oracle chi2", o["trial_chi2"])
 print("gpu    chi2", g["trial_chi2"])
-print("ms", g["ms_total"], g["ms_solve"], g["reduced_blocks"])
+print("ms", g["ms_total"], g["ms_solve"], g["reduced_blocks"], g["border_poses"], g["max_active_rows"])
 print("dX", np.abs(g_out["point_xyz"] - o_out["point_xyz"]).max(), "dt", np.abs(g_out["pose_t"] - o_out["pose_t"]).max())
