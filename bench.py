@@ -186,6 +186,7 @@ def run_ours(args):
 
     exl = ORBextractor(*ORB_PARAMS, device=local)
     exr = ORBextractor(*ORB_PARAMS, device=local)
+    exl.copy_outputs = exr.copy_outputs = False
     frames = [stereo_frame(frame_seed(i + 100 * rank)) for i in range(N_POOL)]
     pinned = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()) for l, r in frames]
     dev = [(a.cuda(), b.cuda()) for a, b in pinned]

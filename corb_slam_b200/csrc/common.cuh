@@ -73,4 +73,43 @@ __device__ __forceinline__ int block_excl_scan(int* data, int n, int* warp_tmp) 
     return total;
 }
 
+
+// Same for 64-bit values (two packed 32-bit counters scanned at once). `warp_tmp` must hold 33 long longs.
+__device__ __forceinline__ long long block_excl_scan64(long long* data, int n, long long* warp_tmp) {
+    const int nt = blockDim.x, t = threadIdx.x;
+    const int chunk = (n + nt - 1) / nt;
+    const int b = t * chunk, e = min(b + chunk, n);
+    long long sum = 0;
+    for (int i = b; i < e; i++) sum += data[i];
+    const int lane = t & 31, wid = t >> 5;
+    long long v = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_tmp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = (nt + 31) >> 5;
+        long long w = lane < nw ? warp_tmp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        warp_tmp[lane] = w;
+    }
+    __syncthreads();
+    long long run = v - sum + (wid ? warp_tmp[wid - 1] : 0);
+    const long long total = warp_tmp[((nt + 31) >> 5) - 1];
+    for (int i = b; i < e; i++) {
+        long long x = data[i];
+        data[i] = run;
+        run += x;
+    }
+    __syncthreads();
+    return total;
+}
+
 }  // namespace corb

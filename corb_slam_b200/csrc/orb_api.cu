@@ -56,6 +56,9 @@ struct corb_orb {
     corb_keypoint* h_kps = nullptr; // kp_cap
     uint8_t* h_desc = nullptr;      // kp_cap * 32
     int* h_scalars = nullptr;       // [0] count, [1] status
+    uint8_t* h_out = nullptr;       // pinned mirror of the device output blob (h_kps / h_desc / h_scalars point into it)
+    uint8_t* d_out = nullptr;
+    size_t out_bytes = 0;
     bool pending = false, pending_pyr = false, pending_empty = false;
 };
 
@@ -66,9 +69,8 @@ static void free_plan(corb_orb* h) {
     h->dev_allocs.clear();
     if (h->h_img) cudaFreeHost(h->h_img), h->h_img = nullptr;
     if (h->h_pyr) cudaFreeHost(h->h_pyr), h->h_pyr = nullptr;
-    if (h->h_kps) cudaFreeHost(h->h_kps), h->h_kps = nullptr;
-    if (h->h_desc) cudaFreeHost(h->h_desc), h->h_desc = nullptr;
-    if (h->h_scalars) cudaFreeHost(h->h_scalars), h->h_scalars = nullptr;
+    if (h->h_out) cudaFreeHost(h->h_out), h->h_out = nullptr;
+    h->h_kps = nullptr; h->h_desc = nullptr; h->h_scalars = nullptr;
     h->plan_w = h->plan_h = 0;
 }
 
@@ -205,10 +207,15 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     A(b.lvl_kp, g.kp_cap);
     A(b.level_count, kMaxLevels);
     A(b.level_cand, kMaxLevels);
-    A(b.kps, g.kp_cap);
-    A(b.desc, (size_t)g.kp_cap * 32);
-    A(b.count, 1);
-    A(b.status, 1);
+    // [keypoints | descriptors | count, status] in one allocation so one D2H copy returns everything
+    h->out_bytes = align_up_sz(sizeof(corb_keypoint) * (size_t)g.kp_cap, 16) + (size_t)g.kp_cap * 32 + 16;
+    uint8_t* out_blob;
+    A(out_blob, h->out_bytes);
+    b.kps = reinterpret_cast<corb_keypoint*>(out_blob);
+    b.desc = out_blob + align_up_sz(sizeof(corb_keypoint) * (size_t)g.kp_cap, 16);
+    b.count = reinterpret_cast<int*>(b.desc + (size_t)g.kp_cap * 32);
+    b.status = b.count + 1;
+    h->d_out = out_blob;
 #undef A
     b.xofs = d_xofs; b.alpha = d_alpha; b.yofs = d_yofs; b.beta = d_beta;
     CORB_CUDA(cudaMemcpy(d_xofs, xofs.data(), xofs.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -224,9 +231,10 @@ static int make_plan(corb_orb* h, int w, int hgt) {
 
     CORB_CUDA(cudaMallocHost(&h->h_img, (size_t)w * hgt));
     CORB_CUDA(cudaMallocHost(&h->h_pyr, h->pyr_bytes));
-    CORB_CUDA(cudaMallocHost(&h->h_kps, sizeof(corb_keypoint) * g.kp_cap));
-    CORB_CUDA(cudaMallocHost(&h->h_desc, (size_t)g.kp_cap * 32));
-    CORB_CUDA(cudaMallocHost(&h->h_scalars, 4 * sizeof(int)));
+    CORB_CUDA(cudaMallocHost(&h->h_out, h->out_bytes));
+    h->h_kps = reinterpret_cast<corb_keypoint*>(h->h_out);
+    h->h_desc = h->h_out + (b.desc - h->d_out);
+    h->h_scalars = reinterpret_cast<int*>(h->h_out + (reinterpret_cast<uint8_t*>(b.count) - h->d_out));
 
     // quadtree: keep a level's keys in shared memory when they fit (typical: 2-3 k keys), else global scratch
     int max_cand_level = 0;
@@ -242,24 +250,37 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     return record_graph(h);
 }
 
-// One CUDA graph per plan: resize chain -> { FAST cells -> quadtree | Gaussian blur } -> orientation + BRIEF.
-// The blur only depends on the pyramid, so it runs on a forked branch beside the FAST/quadtree critical path.
+// One CUDA graph per plan. Levels are independent once they exist, so the graph is a set of per-level pipelines
+//   level 0:            FAST_0 -> quadtree_0
+//   level l: resize_l -> FAST_l -> quadtree_l          (resize_l also feeds resize_{l+1})
+// joined by orientation + BRIEF; the Gaussian blur (needed only by BRIEF) runs behind the resize chain. The longest
+// pipeline (level 0: 36 % of the cells, the largest quadtree) therefore starts at t = 0 instead of after the chain.
 static int record_graph(corb_orb* h) {
     const OrbGeom& g = h->geom;
     const OrbBuffers& b = h->buf;
+    const int L = g.n_levels;
+    std::vector<cudaStream_t> ls(L, nullptr);
+    std::vector<cudaEvent_t> ev(2 * L + 1, nullptr);
+    for (auto& s : ls) CORB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : ev) CORB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CORB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    for (int l = 1; l < g.n_levels; l++) launch_resize(g, b, l, h->stream);
-    cudaEventRecord(h->ev_fork, h->stream);
-    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-    launch_blur(g, b, h->stream2);
-    cudaEventRecord(h->ev_join, h->stream2);
-    launch_fast_cells(g, b, h->stream);
-    launch_octtree(g, b, h->key_smem_cap, h->oct_smem, h->stream);
-    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+    for (int l = 0; l < L; l++) {
+        if (l > 0) launch_resize(g, b, l, h->stream);
+        cudaEventRecord(ev[l], h->stream);           // level l exists
+        cudaStreamWaitEvent(ls[l], ev[l], 0);
+        launch_fast_cells(g, b, l, ls[l]);
+        launch_octtree(g, b, l, h->key_smem_cap, h->oct_smem, ls[l]);
+        cudaEventRecord(ev[L + l], ls[l]);           // level l distributed
+    }
+    launch_blur(g, b, h->stream);
+    for (int l = 0; l < L; l++) cudaStreamWaitEvent(h->stream, ev[L + l], 0);
     launch_orient_desc(g, b, h->stream);
-    CORB_CUDA(cudaStreamEndCapture(h->stream, &h->graph));
+    cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
+    for (auto& s : ls) cudaStreamDestroy(s);
+    for (auto& x : ev) cudaEventDestroy(x);
+    CORB_CUDA(e);
     CORB_CUDA(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
-    h->kernel_launches = (g.n_levels - 1) + 4;
+    h->kernel_launches = (L - 1) + 2 * L + 2;
     return CORB_OK;
 }
 
@@ -394,15 +415,19 @@ int corb_orb_extract_submit(corb_orb* h, const uint8_t* img, int w, int hgt, int
     int rc = make_plan(h, w, hgt);
     if (rc != CORB_OK) return rc;
     const OrbGeom& g = h->geom;
-    if (stride == w) memcpy(h->h_img, img, (size_t)w * hgt);
-    else for (int y = 0; y < hgt; y++) memcpy(h->h_img + (size_t)y * w, img + (size_t)y * stride, w);
-    CORB_CUDA(cudaMemcpy2DAsync(h->buf.pyr, g.lv[0].pitch, h->h_img, w, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, img) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    if (pinned) {  // page-locked caller memory: DMA straight from it (it must stay valid until _wait, like any async copy)
+        CORB_CUDA(cudaMemcpy2DAsync(h->buf.pyr, g.lv[0].pitch, img, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        if (stride == w) memcpy(h->h_img, img, (size_t)w * hgt);
+        else for (int y = 0; y < hgt; y++) memcpy(h->h_img + (size_t)y * w, img + (size_t)y * stride, w);
+        CORB_CUDA(cudaMemcpy2DAsync(h->buf.pyr, g.lv[0].pitch, h->h_img, w, w, hgt, cudaMemcpyHostToDevice, h->stream));
+    }
     rc = enqueue_core(h);
     if (rc != CORB_OK) return rc;
-    CORB_CUDA(cudaMemcpyAsync(h->h_kps, h->buf.kps, sizeof(corb_keypoint) * g.kp_cap, cudaMemcpyDeviceToHost, h->stream));
-    CORB_CUDA(cudaMemcpyAsync(h->h_desc, h->buf.desc, (size_t)g.kp_cap * 32, cudaMemcpyDeviceToHost, h->stream));
-    CORB_CUDA(cudaMemcpyAsync(&h->h_scalars[0], h->buf.count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CORB_CUDA(cudaMemcpyAsync(&h->h_scalars[1], h->buf.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CORB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (want_pyramid)
         CORB_CUDA(cudaMemcpyAsync(h->h_pyr, h->buf.pyr, h->pyr_bytes, cudaMemcpyDeviceToHost, h->stream));
     h->pending = true;
@@ -501,9 +526,9 @@ int corb_orb_profile(corb_orb* h, int reps, float* ms, int cap, int* n) {
         }
         launch_blur(g, h->buf, h->stream);
         CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
-        launch_fast_cells(g, h->buf, h->stream);
+        launch_fast_cells(g, h->buf, -1, h->stream);
         CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
-        launch_octtree(g, h->buf, h->key_smem_cap, h->oct_smem, h->stream);
+        launch_octtree(g, h->buf, -1, h->key_smem_cap, h->oct_smem, h->stream);
         CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
         launch_orient_desc(g, h->buf, h->stream);
         CORB_CUDA(cudaEventRecord(ev[k++], h->stream));

@@ -57,7 +57,8 @@ void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_
 }
 
 // ------------------------------------------------------------------------------------------------ K2 FAST per cell
-constexpr int kRoiPitch = 68;  // bytes per ROI row in shared memory (>= kCellRoiMax, multiple of 4)
+constexpr int kRoiPitch = 72;  // bytes per ROI row in shared memory (>= kCellRoiMax + 3 bytes of alignment slack, multiple of 4)
+constexpr int kRoiPitchRaw = kRoiPitch;
 constexpr int kScDim = 62;     // valid area (<= 60) + 1 px zero border each side
 constexpr int kScPitch = 64;
 
@@ -72,14 +73,20 @@ __device__ __forceinline__ bool run9(uint32_t m) {
 
 // FAST-9/16 response (max over the 16 nine-arcs of the arc minimum of |ring - centre|, minus 1) if the pixel is a
 // corner at threshold `th`, else 0.  == cv::FAST's cornerScore for every pixel cv::FAST(th) reports.
+// Any nine-arc of the 16-ring covers at least two of the four compass pixels (0, 4, 8, 12), so most pixels are rejected
+// after four loads and compares.
 __device__ __forceinline__ int fast_score_dev(const uint8_t* c, int th) {
     constexpr int P = kRoiPitch;
     const int v = c[0];
     int r[16];
-    r[0] = c[3 * P];      r[1] = c[3 * P + 1];   r[2] = c[2 * P + 2];   r[3] = c[P + 3];
-    r[4] = c[3];          r[5] = c[-P + 3];      r[6] = c[-2 * P + 2];  r[7] = c[-3 * P + 1];
-    r[8] = c[-3 * P];     r[9] = c[-3 * P - 1];  r[10] = c[-2 * P - 2]; r[11] = c[-P - 3];
-    r[12] = c[-3];        r[13] = c[P - 3];      r[14] = c[2 * P - 2];  r[15] = c[3 * P - 1];
+    r[0] = c[3 * P]; r[4] = c[3]; r[8] = c[-3 * P]; r[12] = c[-3];
+    const int hi0 = v + th, lo0 = v - th;
+    if ((r[0] > hi0) + (r[4] > hi0) + (r[8] > hi0) + (r[12] > hi0) < 2 && (r[0] < lo0) + (r[4] < lo0) + (r[8] < lo0) + (r[12] < lo0) < 2)
+        return 0;
+    r[1] = c[3 * P + 1];   r[2] = c[2 * P + 2];   r[3] = c[P + 3];
+    r[5] = c[-P + 3];      r[6] = c[-2 * P + 2];  r[7] = c[-3 * P + 1];
+    r[9] = c[-3 * P - 1];  r[10] = c[-2 * P - 2]; r[11] = c[-P - 3];
+    r[13] = c[P - 3];      r[14] = c[2 * P - 2];  r[15] = c[3 * P - 1];
     const int hi = v + th, lo = v - th;
     uint32_t mb = 0, md = 0;
 #pragma unroll
@@ -139,12 +146,13 @@ __device__ __forceinline__ int block_scan_values(int v, int* warp_tmp, int* tota
 // ROI. The iniTh -> minTh fallback is decided per cell on the post-NMS count.
 __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const uint8_t* __restrict__ pyr, int* __restrict__ cell_count,
                                                     uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_r,
-                                                    int* __restrict__ status) {
-    __shared__ __align__(16) uint8_t roi[kCellRoiMax * kRoiPitch];
+                                                    int* __restrict__ status, int cell_begin) {
+    __shared__ __align__(16) uint8_t roi_raw[kCellRoiMax * kRoiPitchRaw + 8];
+    const uint8_t* roi;
     __shared__ __align__(16) uint8_t sc[kScDim * kScPitch];
     __shared__ int warp_tmp[33];
     const int tid = threadIdx.x;
-    const int cell = blockIdx.x;
+    const int cell = blockIdx.x + cell_begin;
     int l = 0;
     while (l + 1 < g.n_levels && cell >= g.lv[l + 1].cell_base) l++;
     const LevelGeom L = g.lv[l];
@@ -158,10 +166,15 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const uint8_t* __
         if (tid == 0) cell_count[cell] = 0;
         return;
     }
-    const uint8_t* src = pyr + L.img_off + (size_t)iniY * L.pitch + iniX;
-    for (int i = tid; i < rw * rh; i += 256) {
-        const int y = i / rw, x = i - y * rw;
-        roi[y * kRoiPitch + x] = src[(size_t)y * L.pitch + x];
+    {   // stage the ROI: 4-byte words from the 4-aligned column at or left of iniX (the pitch is a multiple of 128)
+        const int ax = iniX & ~3, shift = iniX - ax;           // shift in 0..3; roi row holds [ax, ax + 4 * nw)
+        const int nw = (rw + shift + 3) >> 2;                  // <= 18 words (rw <= 66), fits kRoiPitch + 4
+        const uint8_t* srow = pyr + L.img_off + (size_t)iniY * L.pitch + ax;
+        for (int i = tid; i < nw * rh; i += 256) {
+            const int y = i / nw, xw = i - y * nw;
+            reinterpret_cast<uint32_t*>(roi_raw + y * kRoiPitchRaw)[xw] = *reinterpret_cast<const uint32_t*>(srow + (size_t)y * L.pitch + 4 * xw);
+        }
+        roi = roi_raw + shift;
     }
     for (int i = tid; i < kScDim * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
     __syncthreads();
@@ -210,8 +223,11 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const uint8_t* __
     if (tid == 0) cell_count[cell] = total;
 }
 
-void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
-    k_fast_cells<<<g.n_cells, 256, 0, s>>>(g, b.pyr, b.cell_count, b.cand_xy, b.cand_r, b.status);
+// level < 0: all levels in one launch; else only the cells of that level (lets a level start as soon as it is resized)
+void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s) {
+    const int begin = level < 0 ? 0 : g.lv[level].cell_base;
+    const int n = level < 0 ? g.n_cells : g.lv[level].n_cols * g.lv[level].n_rows;
+    k_fast_cells<<<n, 256, 0, s>>>(g, b.pyr, b.cell_count, b.cand_xy, b.cand_r, b.status, begin);
 }
 
 // ------------------------------------------------------------------------------------------------ K5 Gaussian 7x7
@@ -282,9 +298,9 @@ void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
 constexpr int kOctThreads = 512;
 
 struct OctLayout {
-    int cntA, cntB, bndA, bndB, cc, procpos, scan, crank, krank, fresh, candf, warp_tmp, sh, keys_xy, keys_node, keys_r, total;
+    int cntA, cntB, bndA, bndB, cc, procpos, scan, crank, krank, fresh, candf, warp_tmp, sh, scan64, warp_tmp64, cell_off, keys_xy, keys_node, keys_r, total;
 };
-__host__ __device__ inline OctLayout oct_layout(int NC, int key_cap) {
+__host__ __device__ inline OctLayout oct_layout(int NC, int key_cap, int n_cell) {
     OctLayout o;
     int p = 0;
     o.cntA = p; p += 4 * NC;
@@ -301,6 +317,10 @@ __host__ __device__ inline OctLayout oct_layout(int NC, int key_cap) {
     o.warp_tmp = p; p += 4 * 36;
     o.sh = p; p += 4 * 8;
     p = (p + 15) & ~15;
+    o.scan64 = p; p += 8 * NC;
+    o.warp_tmp64 = p; p += 8 * 36;
+    o.cell_off = p; p += 4 * (n_cell + 1);
+    p = (p + 15) & ~15;
     o.keys_xy = p; p += 4 * key_cap;
     o.keys_node = p; p += 2 * ((key_cap + 1) & ~1);
     o.keys_r = p; p += (key_cap + 3) & ~3;
@@ -309,7 +329,7 @@ __host__ __device__ inline OctLayout oct_layout(int NC, int key_cap) {
 }
 
 int octtree_smem_bytes(const OrbGeom& g, int level, int key_smem_cap) {
-    return oct_layout(g.lv[level].node_cap, key_smem_cap).total;
+    return oct_layout(g.lv[level].node_cap, key_smem_cap, g.lv[level].n_cols * g.lv[level].n_rows).total;
 }
 
 __device__ __forceinline__ int quadrant_of(uint32_t xy, short4 b) {
@@ -329,13 +349,14 @@ __device__ __forceinline__ short4 child_bounds(short4 b, int q) {
     return c;
 }
 
-__global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b, int key_smem_cap) {
+__global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b, int key_smem_cap, int level_begin) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int l = blockIdx.x;
+    const int l = blockIdx.x + level_begin;
     const LevelGeom L = g.lv[l];
     const int NC = L.node_cap, N = L.quota;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const OctLayout lay = oct_layout(NC, key_smem_cap);
+    const int n_cell = L.n_cols * L.n_rows;
+    const OctLayout lay = oct_layout(NC, key_smem_cap, n_cell);
     int* cnt_cur = reinterpret_cast<int*>(smem + lay.cntA);
     int* cnt_nxt = reinterpret_cast<int*>(smem + lay.cntB);
     short4* bnd_cur = reinterpret_cast<short4*>(smem + lay.bndA);
@@ -350,13 +371,17 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
     uint8_t* candf = smem + lay.candf;
     int* warp_tmp = reinterpret_cast<int*>(smem + lay.warp_tmp);
     volatile int* sh = reinterpret_cast<int*>(smem + lay.sh);
+    long long* scan64 = reinterpret_cast<long long*>(smem + lay.scan64);
+    long long* warp_tmp64 = reinterpret_cast<long long*>(smem + lay.warp_tmp64);
 
-    // ---- gather the level's candidates in the order vToDistributeKeys is built: cell row, cell column, raster
-    const int n_cell = L.n_cols * L.n_rows;
-    int* cell_off = b.cell_off + L.cell_base;
+    // ---- gather the level's candidates in the order vToDistributeKeys is built: cell row, cell column, raster.
+    //      Cell offsets are scanned in shared memory; every key then finds its cell by binary search, so all global
+    //      loads of the gather are independent (a per-cell loop would serialise ~30 dependent L2 round trips per warp).
+    int* cell_off = reinterpret_cast<int*>(smem + lay.cell_off);
     for (int i = tid; i < n_cell; i += nt) cell_off[i] = b.cell_count[L.cell_base + i];
     __syncthreads();
     const int M = block_excl_scan(cell_off, n_cell, warp_tmp);
+    if (tid == 0) cell_off[n_cell] = M;
     uint32_t* kxy;
     uint16_t* knode;
     uint8_t* kr;
@@ -369,16 +394,16 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
         knode = b.key_node + L.cand_base;
         kr = b.key_r + L.cand_base;
     }
-    {
-        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-        for (int c = wid; c < n_cell; c += nw) {
-            const int n = b.cell_count[L.cell_base + c], off = cell_off[c];
-            const int src = L.cand_base + c * L.slot;
-            for (int e = lane; e < n; e += 32) {
-                kxy[off + e] = b.cand_xy[src + e];
-                kr[off + e] = b.cand_r[src + e];
-            }
+    __syncthreads();
+    for (int k = tid; k < M; k += nt) {
+        int lo = 0, hi = n_cell;  // last cell with cell_off[c] <= k
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cell_off[mid] <= k) lo = mid; else hi = mid;
         }
+        const int src = L.cand_base + lo * L.slot + (k - cell_off[lo]);
+        kxy[k] = b.cand_xy[src];
+        kr[k] = b.cand_r[src];
     }
     if (tid == 0) b.level_cand[l] = M;
     // ---- initial nodes (:542-589)
@@ -417,7 +442,88 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
             break;
         }
         const int prev = s;
-        // ---- processing order
+        if (!final_phase) {
+            // ---- full pass (:613-655): every node holding more than one key splits, in list order, no early stop.
+            //      One packed scan gives both the creation index of each parent's children and the rank of kept nodes.
+            for (int i = tid; i < 4 * s; i += nt) cc[i] = 0;
+            if (tid == 0) sh[2] = 0;
+            __syncthreads();
+            for (int k = tid; k < M; k += nt) {
+                const int nd = knode[k];
+                if (cnt_cur[nd] > 1) atomicAdd(&cc[nd * 4 + quadrant_of(kxy[k], bnd_cur[nd])], 1);
+            }
+            __syncthreads();
+            for (int i = tid; i < s; i += nt) {
+                const int* c4 = cc + i * 4;
+                const bool ex = cnt_cur[i] > 1;
+                const int nch = ex ? (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0) : 0;
+                scan64[i] = ((long long)nch << 32) | (ex ? 0 : 1);
+            }
+            __syncthreads();
+            const long long tot = block_excl_scan64(scan64, s, warp_tmp64);
+            const int T = (int)(tot >> 32), K = (int)(tot & 0xffffffffLL);
+            if (T + K > NC) {
+                if (tid == 0) atomicExch(b.status, 103);
+                s = 0;
+                break;
+            }
+            int n_expand = 0;
+            for (int i = tid; i < s; i += nt) {
+                const long long sc = scan64[i];
+                if (cnt_cur[i] > 1) {
+                    const short4 pb = bnd_cur[i];
+                    int idx = (int)(sc >> 32);
+                    crank[i] = idx;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int c = cc[i * 4 + q];
+                        if (c > 0) {
+                            const int np = T - 1 - idx;
+                            cnt_nxt[np] = c;
+                            bnd_nxt[np] = child_bounds(pb, q);
+                            fresh_nxt[np] = 1;
+                            n_expand += c > 1;
+                            idx++;
+                        }
+                    }
+                } else {
+                    const int np = T + (int)(sc & 0xffffffffLL);
+                    cnt_nxt[np] = cnt_cur[i];
+                    bnd_nxt[np] = bnd_cur[i];
+                    fresh_nxt[np] = 0;
+                    krank[i] = np;
+                }
+            }
+            if (n_expand) atomicAdd((int*)&sh[2], n_expand);
+            __syncthreads();
+            for (int k = tid; k < M; k += nt) {
+                const int nd = knode[k];
+                int np;
+                if (cnt_cur[nd] > 1) {
+                    const int q = quadrant_of(kxy[k], bnd_cur[nd]);
+                    const int* c4 = cc + nd * 4;
+                    int rank = 0;
+                    if (q > 0) rank += c4[0] > 0;
+                    if (q > 1) rank += c4[1] > 0;
+                    if (q > 2) rank += c4[2] > 0;
+                    np = T - 1 - (crank[nd] + rank);
+                } else {
+                    np = krank[nd];
+                }
+                knode[k] = (uint16_t)np;
+            }
+            __syncthreads();
+            const int n_to_expand = sh[2];
+            { int* t = cnt_cur; cnt_cur = cnt_nxt; cnt_nxt = t; }
+            { short4* t = bnd_cur; bnd_cur = bnd_nxt; bnd_nxt = t; }
+            { uint8_t* t = fresh_cur; fresh_cur = fresh_nxt; fresh_nxt = t; }
+            s = T + K;
+            __syncthreads();
+            if (s >= N || s == prev) finish = true;
+            else if (s + 3 * n_to_expand > N) final_phase = true;
+            continue;
+        }
+        // ---- near-quota phase (:660-733): generic step with a sorted processing order and an early stop
         int m;
         if (!final_phase) {
             for (int i = tid; i < s; i += nt) {
@@ -569,8 +675,9 @@ cudaError_t prepare_octtree(const OrbGeom& g, int key_smem_cap, int* smem_bytes_
     return cudaFuncSetAttribute(k_octtree, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int key_smem_cap, int smem_bytes, cudaStream_t s) {
-    k_octtree<<<g.n_levels, kOctThreads, smem_bytes, s>>>(g, b, key_smem_cap);
+void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int level, int key_smem_cap, int smem_bytes, cudaStream_t s) {
+    if (level < 0) k_octtree<<<g.n_levels, kOctThreads, smem_bytes, s>>>(g, b, key_smem_cap, 0);
+    else k_octtree<<<1, kOctThreads, octtree_smem_bytes(g, level, key_smem_cap), s>>>(g, b, key_smem_cap, level);
 }
 
 // ------------------------------------------------------------------------------------------------ K4 + K6
@@ -599,8 +706,10 @@ __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
 // One warp per kept keypoint: IC_Angle on the un-blurred level (ORBextractor.cc:77-104), then the 256 steered BRIEF
 // tests on the blurred level (:107-146), then the epilogue of operator() (:1092-1101, :837-847).
 __global__ void __launch_bounds__(256) k_orient_desc(OrbGeom g, OrbBuffers b) {
-    __shared__ int8_t pat[1024];
-    for (int i = threadIdx.x; i < 256; i += 256) reinterpret_cast<int*>(pat)[i] = reinterpret_cast<const int*>(d_pattern)[i];
+    // pattern transposed to [point-in-byte 0..15][lane 0..31] so the 32 lanes of a warp read 64 contiguous bytes
+    __shared__ char2 pat[16 * 32];
+    for (int i = threadIdx.x; i < 512; i += 256)
+        pat[(i & 15) * 32 + (i >> 4)] = make_char2(d_pattern[2 * i], d_pattern[2 * i + 1]);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int wslot = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -644,16 +753,18 @@ __global__ void __launch_bounds__(256) k_orient_desc(OrbGeom g, OrbBuffers b) {
     // ---- descriptor: lane = output byte; contract: cos/sin in double, rounded to float
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float rad = __fmul_rn(angle, factorPI);
-    const float ca = (float)cos((double)rad), sa = (float)sin((double)rad);
+    double sd, cd;
+    sincos((double)rad, &sd, &cd);
+    const float ca = (float)cd, sa = (float)sd;
     const uint8_t* cb = b.blur + L.img_off + (size_t)Y * L.pitch + X;
-    const int8_t* pp = pat + lane * 32;
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int t[2];
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            const float px = (float)pp[(2 * k + j) * 2], py = (float)pp[(2 * k + j) * 2 + 1];
+            const char2 pt = pat[(2 * k + j) * 32 + lane];
+            const float px = (float)pt.x, py = (float)pt.y;
             const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, sa), __fmul_rn(py, ca)));
             const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, ca), __fmul_rn(py, sa)));
             t[j] = cb[iy * L.pitch + ix];

@@ -33,10 +33,10 @@ struct OrbBuffers {
 int octtree_smem_bytes(const OrbGeom& g, int level, int key_smem_cap);
 
 void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s);
-void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s);
+void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s);
 void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s);
 cudaError_t prepare_octtree(const OrbGeom& g, int key_smem_cap, int* smem_bytes_out);
-void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int key_smem_cap, int smem_bytes, cudaStream_t s);
+void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int level, int key_smem_cap, int smem_bytes, cudaStream_t s);
 void launch_orient_desc(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s);
 
 }  // namespace corb

@@ -32,6 +32,8 @@ class ORBextractor:
                                     p(self._inv_sigma2, _lib.f32p), p(self.mnFeaturesPerLevel, _lib.i32p),
                                     p(self.umax, _lib.i32p)))
         self.mvImagePyramid = []
+        self._out_shape = None
+        self.copy_outputs = True  # False: return views into reused buffers (valid until the next call)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -90,9 +92,11 @@ class ORBextractor:
             self.mvImagePyramid = []
             return np.zeros(0, KP_DTYPE), None  # descriptors.release() (:1064-1065)
         h, w = self._shape
-        cap = self.capacity(w, h)
-        kps = np.empty(cap, KP_DTYPE)
-        desc = np.empty((cap, 32), np.uint8)
+        if self._out_shape != (h, w):  # output buffers are reused between calls of the same size
+            cap = self.capacity(w, h)
+            self._out = (np.empty(cap, KP_DTYPE), np.empty((cap, 32), np.uint8))
+            self._out_shape = (h, w)
+        kps, desc = self._out
         n = C.c_int32()
         pyr_ptrs = None
         if self._want_pyr:
@@ -103,8 +107,10 @@ class ORBextractor:
             self.mvImagePyramid = pyr
         self._keep = None
         if n.value == 0:
-            return kps[:0], None
-        return kps[:n.value], desc[:n.value]
+            return kps[:0].copy(), None
+        if self.copy_outputs:
+            return kps[:n.value].copy(), desc[:n.value].copy()
+        return kps[:n.value], desc[:n.value]  # views into buffers that the next call overwrites
 
     def __call__(self, image, mask=None, want_pyramid=False):
         """Returns (keypoints, descriptors): a structured array with cv::KeyPoint's fields and an (N,32) uint8 array
