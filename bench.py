@@ -167,7 +167,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from corb_slam_b200 import ORBextractor
+    from corb_slam_b200 import ORBextractor, extract_stereo, extract_stereo_device
     from corb_slam_b200.synth import stereo_frame, frame_seed
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,6 +190,7 @@ def run_ours(args):
     frames = [stereo_frame(frame_seed(i + 100 * rank)) for i in range(N_POOL)]
     pinned = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()) for l, r in frames]
     dev = [(a.cuda(), b.cuda()) for a, b in pinned]
+    npin = [(a.numpy(), b.numpy()) for a, b in pinned]  # numpy views of the page-locked frames
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     sl = torch.cuda.ExternalStream(exl.stream())
     sr = torch.cuda.ExternalStream(exr.stream())
@@ -199,8 +200,7 @@ def run_ours(args):
         if ev0 is not None:
             ev0.record(sl)
             sr.wait_event(ev0)
-        exl.extract_device(l.data_ptr(), W, H, W)
-        exr.extract_device(r.data_ptr(), W, H, W)
+        extract_stereo_device(exl, exr, l.data_ptr(), r.data_ptr(), W, H, W)
         if ev1 is not None:
             evr = torch.cuda.Event()
             evr.record(sr)
@@ -209,11 +209,7 @@ def run_ours(args):
 
     def step_host(i, pyr=False):
         l, r = pinned[i % N_POOL]
-        exl.submit(l.numpy(), pyr)
-        exr.submit(r.numpy(), pyr)
-        kl = exl.wait()
-        kr = exr.wait()
-        return kl, kr
+        return extract_stereo(exl, exr, npin[i % N_POOL][0], npin[i % N_POOL][1], want_pyramid=pyr)
 
     # ---- warm-up
     for i in range(max(args.warmup, 3)):
@@ -303,7 +299,7 @@ def run_ours(args):
                        "timing": "CUDA events per step on the extractor streams, sum over steps, max over ranks"},
             "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "note": "corb_orb_extract_submit/_wait on two handles, host numpy in, host keypoints+descriptors out"},
+                    "note": "corb_orb_extract_pair on two handles: page-locked host images in, host keypoints+descriptors out"},
             "e2e_with_pyramid": {"value": world * args.steps / (e2e_pyr_ms * 1e-3), "unit": "frames/s",
                                  "d2h_bytes_per_step": d2h + 2 * 1441432, "ms_per_step": e2e_pyr_ms / args.steps,
                                  "note": "also copies mvImagePyramid to the host (needed while ComputeStereoMatches is on the CPU)"},

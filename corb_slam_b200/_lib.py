@@ -87,6 +87,9 @@ def lib():
         L.corb_orb_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, i32p, C.POINTER(vp)]
         L.corb_orb_extract_submit.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.corb_orb_extract_wait.argtypes = [vp, vp, vp, i32p, C.POINTER(vp)]
+        L.corb_orb_extract_pair.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, i32p, vp, vp, i32p, C.POINTER(vp),
+                                            C.POINTER(vp)]
+        L.corb_orb_extract_pair_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
         L.corb_orb_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
         L.corb_orb_sync.argtypes = [vp]
         L.corb_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
@@ -94,6 +97,7 @@ def lib():
         L.corb_orb_stream.argtypes = [vp]
         L.corb_orb_stream.restype = vp
         L.corb_orb_launches_per_extract.argtypes = [vp]
+        L.corb_orb_uses_tma.argtypes = [vp]
         L.corb_orb_profile.argtypes = [vp, C.c_int, f32p, C.c_int, i32p]
         L.corb_orb_kernel_name.argtypes = [vp, C.c_int]
         L.corb_orb_kernel_name.restype = C.c_char_p

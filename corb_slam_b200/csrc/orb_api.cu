@@ -2,6 +2,7 @@
 // Replaces ORBextractor (corbslam_client/include/ORBextractor.h:45-112, src/ORBextractor.cc:410-470,1043-1132).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -40,14 +41,17 @@ struct corb_orb {
     int plan_w = 0, plan_h = 0;
     OrbGeom geom;
     OrbBuffers buf;
+    TmaMaps tma;
     size_t pyr_bytes = 0;
     int cand_total = 0;
     int key_smem_cap = 0, oct_smem = 0;
     std::vector<void*> dev_allocs;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
+    // two instantiations of the per-frame graph: results stay in HBM (dev) / results copied to pinned host memory (host)
+    cudaGraph_t graph[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    cudaGraphNode_t import_node[2] = {nullptr, nullptr};
     int kernel_launches = 0;
 
     // pinned host staging
@@ -63,8 +67,10 @@ struct corb_orb {
 };
 
 static void free_plan(corb_orb* h) {
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec), h->graph_exec = nullptr;
-    if (h->graph) cudaGraphDestroy(h->graph), h->graph = nullptr;
+    for (int v = 0; v < 2; v++) {
+        if (h->graph_exec[v]) cudaGraphExecDestroy(h->graph_exec[v]), h->graph_exec[v] = nullptr;
+        if (h->graph[v]) cudaGraphDestroy(h->graph[v]), h->graph[v] = nullptr;
+    }
     for (void* p : h->dev_allocs) cudaFree(p);
     h->dev_allocs.clear();
     if (h->h_img) cudaFreeHost(h->h_img), h->h_img = nullptr;
@@ -229,6 +235,9 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     CORB_CUDA(cudaMemset(b.level_count, 0, kMaxLevels * sizeof(int)));
     CORB_CUDA(cudaMemset(b.level_cand, 0, kMaxLevels * sizeof(int)));
 
+    memset(&h->tma, 0, sizeof(h->tma));
+    b.tma_maps = &h->tma;
+    b.use_tma = !getenv("CORB_NO_TMA") && encode_tma_maps(g, b.pyr, &h->tma) ? 1 : 0;
     CORB_CUDA(cudaMallocHost(&h->h_img, (size_t)w * hgt));
     CORB_CUDA(cudaMallocHost(&h->h_pyr, h->pyr_bytes));
     CORB_CUDA(cudaMallocHost(&h->h_out, h->out_bytes));
@@ -255,7 +264,7 @@ static int make_plan(corb_orb* h, int w, int hgt) {
 //   level l: resize_l -> FAST_l -> quadtree_l          (resize_l also feeds resize_{l+1})
 // joined by orientation + BRIEF; the Gaussian blur (needed only by BRIEF) runs behind the resize chain. The longest
 // pipeline (level 0: 36 % of the cells, the largest quadtree) therefore starts at t = 0 instead of after the chain.
-static int record_graph(corb_orb* h) {
+static int record_graph_variant(corb_orb* h, int variant) {
     const OrbGeom& g = h->geom;
     const OrbBuffers& b = h->buf;
     const int L = g.n_levels;
@@ -264,6 +273,7 @@ static int record_graph(corb_orb* h) {
     for (auto& s : ls) CORB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto& e : ev) CORB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CORB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    launch_import(g, b, h->h_img, g.lv[0].w, h->stream);  // placeholder source, patched before every launch
     for (int l = 0; l < L; l++) {
         if (l > 0) launch_resize(g, b, l, h->stream);
         cudaEventRecord(ev[l], h->stream);           // level l exists
@@ -275,12 +285,53 @@ static int record_graph(corb_orb* h) {
     launch_blur(g, b, h->stream);
     for (int l = 0; l < L; l++) cudaStreamWaitEvent(h->stream, ev[L + l], 0);
     launch_orient_desc(g, b, h->stream);
-    cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
+    if (variant == 1) cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph[variant]);
     for (auto& s : ls) cudaStreamDestroy(s);
     for (auto& x : ev) cudaEventDestroy(x);
     CORB_CUDA(e);
-    CORB_CUDA(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
-    h->kernel_launches = (L - 1) + 2 * L + 2;
+    // find the import kernel node so its source pointer can be patched per launch
+    size_t n_nodes = 0;
+    CORB_CUDA(cudaGraphGetNodes(h->graph[variant], nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    CORB_CUDA(cudaGraphGetNodes(h->graph[variant], nodes.data(), &n_nodes));
+    h->import_node[variant] = nullptr;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType t;
+        CORB_CUDA(cudaGraphNodeGetType(nd, &t));
+        if (t != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        CORB_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
+        if (kp.func == import_kernel_ptr()) h->import_node[variant] = nd;
+    }
+    CORB_CHECK(h->import_node[variant], CORB_ERR_CUDA, "import node not found in the captured graph");
+    CORB_CUDA(cudaGraphInstantiate(&h->graph_exec[variant], h->graph[variant], 0));
+    return CORB_OK;
+}
+
+static int record_graph(corb_orb* h) {
+    for (int v = 0; v < 2; v++) {
+        int rc = record_graph_variant(h, v);
+        if (rc != CORB_OK) return rc;
+    }
+    h->kernel_launches = 1 + (h->geom.n_levels - 1) + 2 * h->geom.n_levels + 2;
+    return CORB_OK;
+}
+
+// Launches the per-frame graph on (src, stride): src is device memory or page-locked host memory (UVA).
+static int launch_frame(corb_orb* h, int variant, const uint8_t* src, int stride) {
+    const LevelGeom& L0 = h->geom.lv[0];
+    uint8_t* dst = h->buf.pyr + L0.img_off;
+    int pitch = L0.pitch, w = L0.w, hh = L0.h;
+    void* args[6] = {(void*)&src, (void*)&stride, (void*)&dst, (void*)&pitch, (void*)&w, (void*)&hh};
+    cudaKernelNodeParams kp = {};
+    kp.func = const_cast<void*>(import_kernel_ptr());
+    kp.gridDim = dim3((L0.w + 1023) / 1024, L0.h);
+    kp.blockDim = dim3(256);
+    kp.sharedMemBytes = 0;
+    kp.kernelParams = args;
+    CORB_CUDA(cudaGraphExecKernelNodeSetParams(h->graph_exec[variant], h->import_node[variant], &kp));
+    CORB_CUDA(cudaGraphLaunch(h->graph_exec[variant], h->stream));
     return CORB_OK;
 }
 
@@ -396,11 +447,6 @@ int corb_orb_capacity(const corb_orb* h, int w, int hgt) {
     return capacity_for(h, w, hgt);
 }
 
-static int enqueue_core(corb_orb* h) {
-    CORB_CUDA(cudaGraphLaunch(h->graph_exec, h->stream));
-    return CORB_OK;
-}
-
 int corb_orb_extract_submit(corb_orb* h, const uint8_t* img, int w, int hgt, int stride, int want_pyramid) {
     CORB_CHECK(h, CORB_ERR_INVALID, "handle is NULL");
     CORB_CHECK(!h->pending, CORB_ERR_INVALID, "a submitted extraction has not been waited for");
@@ -414,20 +460,19 @@ int corb_orb_extract_submit(corb_orb* h, const uint8_t* img, int w, int hgt, int
     CORB_CUDA(cudaSetDevice(h->device));
     int rc = make_plan(h, w, hgt);
     if (rc != CORB_OK) return rc;
-    const OrbGeom& g = h->geom;
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, img) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     if (!pinned) cudaGetLastError();
-    if (pinned) {  // page-locked caller memory: DMA straight from it (it must stay valid until _wait, like any async copy)
-        CORB_CUDA(cudaMemcpy2DAsync(h->buf.pyr, g.lv[0].pitch, img, stride, w, hgt, cudaMemcpyHostToDevice, h->stream));
-    } else {
+    const uint8_t* src = img;
+    int src_stride = stride;
+    if (!pinned) {  // pageable caller memory: stage it; page-locked memory is read in place (keep it valid until _wait)
         if (stride == w) memcpy(h->h_img, img, (size_t)w * hgt);
         else for (int y = 0; y < hgt; y++) memcpy(h->h_img + (size_t)y * w, img + (size_t)y * stride, w);
-        CORB_CUDA(cudaMemcpy2DAsync(h->buf.pyr, g.lv[0].pitch, h->h_img, w, w, hgt, cudaMemcpyHostToDevice, h->stream));
+        src = h->h_img;
+        src_stride = w;
     }
-    rc = enqueue_core(h);
+    rc = launch_frame(h, 1, src, src_stride);  // import (PCIe read) -> kernels -> D2H of the result blob, one launch
     if (rc != CORB_OK) return rc;
-    CORB_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
     if (want_pyramid)
         CORB_CUDA(cudaMemcpyAsync(h->h_pyr, h->buf.pyr, h->pyr_bytes, cudaMemcpyDeviceToHost, h->stream));
     h->pending = true;
@@ -470,14 +515,36 @@ int corb_orb_extract(corb_orb* h, const uint8_t* img, int w, int hgt, int stride
     return corb_orb_extract_wait(h, kps, desc, n, pyr_out);
 }
 
+// Left and right image of one stereo frame from one thread (the reference starts two threads, Frame.cc:78-81): both
+// graphs are launched back to back, then both results are collected.
+int corb_orb_extract_pair(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride,
+                          corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r, uint8_t* desc_r, int* n_r,
+                          uint8_t* const* pyr_l, uint8_t* const* pyr_r) {
+    CORB_CHECK(hl && hr && hl != hr, CORB_ERR_INVALID, "two distinct handles are required");
+    int rc = corb_orb_extract_submit(hl, img_l, w, hgt, stride, pyr_l != nullptr);
+    if (rc != CORB_OK) return rc;
+    rc = corb_orb_extract_submit(hr, img_r, w, hgt, stride, pyr_r != nullptr);
+    const int rc_l = corb_orb_extract_wait(hl, kps_l, desc_l, n_l, pyr_l);
+    if (rc != CORB_OK) return rc;
+    rc = corb_orb_extract_wait(hr, kps_r, desc_r, n_r, pyr_r);
+    return rc_l != CORB_OK ? rc_l : rc;
+}
+
+int corb_orb_extract_pair_device(corb_orb* hl, corb_orb* hr, const uint8_t* d_img_l, const uint8_t* d_img_r, int w, int hgt,
+                                 int stride) {
+    CORB_CHECK(hl && hr && hl != hr, CORB_ERR_INVALID, "two distinct handles are required");
+    int rc = corb_orb_extract_device(hl, d_img_l, w, hgt, stride);
+    if (rc != CORB_OK) return rc;
+    return corb_orb_extract_device(hr, d_img_r, w, hgt, stride);
+}
+
 int corb_orb_extract_device(corb_orb* h, const uint8_t* d_img, int w, int hgt, int stride) {
     CORB_CHECK(h && d_img && w >= 1 && hgt >= 1 && stride >= w, CORB_ERR_INVALID, "bad argument");
     CORB_CHECK(!h->pending, CORB_ERR_INVALID, "a submitted extraction has not been waited for");
     CORB_CUDA(cudaSetDevice(h->device));
     int rc = make_plan(h, w, hgt);
     if (rc != CORB_OK) return rc;
-    CORB_CUDA(cudaMemcpy2DAsync(h->buf.pyr, h->geom.lv[0].pitch, d_img, stride, w, hgt, cudaMemcpyDeviceToDevice, h->stream));
-    return enqueue_core(h);
+    return launch_frame(h, 0, d_img, stride);
 }
 
 int corb_orb_sync(corb_orb* h) {
@@ -559,6 +626,7 @@ const char* corb_orb_kernel_name(const corb_orb* h, int i) {
 
 void* corb_orb_stream(const corb_orb* h) { return h ? (void*)h->stream : nullptr; }
 int corb_orb_launches_per_extract(const corb_orb* h) { return h ? h->kernel_launches : 0; }
+int corb_orb_uses_tma(const corb_orb* h) { return h && h->plan_w ? h->buf.use_tma : 0; }
 
 int corb_orb_tap(corb_orb* h, int what, int level, void* out, size_t out_bytes, int* n) {
     CORB_CHECK(h && h->plan_w && level >= 0 && level < h->nlevels, CORB_ERR_INVALID, "bad argument or no plan");

@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "orb_kernels.cuh"
 
+#include <cuda.h>
+
 namespace corb {
 
 __device__ __align__(16) const int8_t d_pattern[1024] = {
@@ -15,6 +17,35 @@ __device__ __align__(16) const int8_t d_pattern[1024] = {
 };
 // umax of ORBextractor.cc:452-469 for HALF_PATCH_SIZE = 15 (the host recomputes it and checks equality)
 __device__ const int d_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// ------------------------------------------------------------------------------------------------ K0 import
+// Copies the caller's image (device memory, or page-locked host memory read over PCIe through its UVA mapping) into
+// level 0 of the pitched pyramid. First node of the per-frame graph, so one cudaGraphLaunch is the only driver call
+// an extraction needs; its (src, stride) arguments are patched per launch with cudaGraphExecKernelNodeSetParams.
+__global__ void __launch_bounds__(256) k_import(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ dst, int pitch,
+                                                int w, int h) {
+    const int y = blockIdx.y;
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x0 >= w) return;
+    const uint8_t* s = src + (size_t)y * stride + x0;
+    uint32_t v;
+    if ((((uintptr_t)src | (uintptr_t)stride) & 3) == 0 && x0 + 3 < w) {
+        v = *reinterpret_cast<const uint32_t*>(s);
+    } else {
+        v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (x0 + k < w) v |= (uint32_t)s[k] << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + x0) = v;  // pitch % 128 == 0 and pitch >= w rounded up to 4
+}
+
+void launch_import(const OrbGeom& g, const OrbBuffers& b, const uint8_t* src, int stride, cudaStream_t s) {
+    const LevelGeom& L0 = g.lv[0];
+    dim3 grid((L0.w + 1023) / 1024, L0.h);
+    k_import<<<grid, 256, 0, s>>>(src, stride, b.pyr + L0.img_off, L0.pitch, L0.w, L0.h);
+}
+const void* import_kernel_ptr() { return (const void*)k_import; }
 
 // ------------------------------------------------------------------------------------------------ K1 resize
 // cv::resize INTER_LINEAR u8 (ORBextractor.cc:1120). Coefficient tables are built on the host exactly as OpenCV
@@ -57,8 +88,35 @@ void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_
 }
 
 // ------------------------------------------------------------------------------------------------ K2 FAST per cell
-constexpr int kRoiPitch = 72;  // bytes per ROI row in shared memory (>= kCellRoiMax + 3 bytes of alignment slack, multiple of 4)
+constexpr int kRoiPitch = 80;  // bytes per ROI row in shared memory: the TMA box width (multiple of 16, >= kCellRoiMax + 3)
 constexpr int kRoiPitchRaw = kRoiPitch;
+constexpr int kRoiTmaBytes = kRoiPitch * kCellRoiMax;  // one 80 x 66 box per cell
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives, sm_90+/sm_100a PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
 constexpr int kScDim = 62;     // valid area (<= 60) + 1 px zero border each side
 constexpr int kScPitch = 64;
 
@@ -144,13 +202,16 @@ __device__ __forceinline__ int block_scan_values(int v, int* warp_tmp, int* tota
 // The cell's ROI (wCell+6 x hCell+6) is staged in shared memory; FAST ignores a 3 px rim, so the valid areas of
 // neighbouring cells tile the level disjointly and NMS sees zeros outside its own cell, exactly like cv::FAST on the
 // ROI. The iniTh -> minTh fallback is decided per cell on the post-NMS count.
-__global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const uint8_t* __restrict__ pyr, int* __restrict__ cell_count,
+__global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_constant__ TmaMaps tm, int use_tma,
+                                                    const uint8_t* __restrict__ pyr, int* __restrict__ cell_count,
                                                     uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_r,
                                                     int* __restrict__ status, int cell_begin) {
-    __shared__ __align__(16) uint8_t roi_raw[kCellRoiMax * kRoiPitchRaw + 8];
+    __shared__ __align__(128) uint8_t roi_raw[kCellRoiMax * kRoiPitchRaw + 16];
+    __shared__ __align__(8) uint64_t tma_bar;
     const uint8_t* roi;
     __shared__ __align__(16) uint8_t sc[kScDim * kScPitch];
-    __shared__ int warp_tmp[33];
+    __shared__ uint32_t row_ini[128], row_min[128];  // two ballot words per valid row (<= 60 rows)
+    __shared__ int row_off[65];
     const int tid = threadIdx.x;
     const int cell = blockIdx.x + cell_begin;
     int l = 0;
@@ -166,68 +227,136 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const uint8_t* __
         if (tid == 0) cell_count[cell] = 0;
         return;
     }
-    {   // stage the ROI: 4-byte words from the 4-aligned column at or left of iniX (the pitch is a multiple of 128)
-        const int ax = iniX & ~3, shift = iniX - ax;           // shift in 0..3; roi row holds [ax, ax + 4 * nw)
-        const int nw = (rw + shift + 3) >> 2;                  // <= 18 words (rw <= 66), fits kRoiPitch + 4
-        const uint8_t* srow = pyr + L.img_off + (size_t)iniY * L.pitch + ax;
-        for (int i = tid; i < nw * rh; i += 256) {
-            const int y = i / nw, xw = i - y * nw;
-            reinterpret_cast<uint32_t*>(roi_raw + y * kRoiPitchRaw)[xw] = *reinterpret_cast<const uint32_t*>(srow + (size_t)y * L.pitch + 4 * xw);
+    if (use_tma) {
+        // stage the ROI with one TMA box load (80 x 66 bytes at (iniX, iniY) of this level's tensor map; out-of-image
+        // bytes are zero filled and never read): a single thread issues it, everybody waits on the mbarrier
+        if (tid == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&tma_bar, kRoiTmaBytes);
+            tma_load_2d(roi_raw, &tm.m[l], iniX, iniY, &tma_bar);
         }
+        roi = roi_raw;
+    } else {
+        // fallback: 4-byte words from the 4-aligned column at or left of iniX (the pitch is a multiple of 128)
+        const int ax = iniX & ~3, shift = iniX - ax;           // shift in 0..3; roi row holds [ax, ax + 4 * nw)
+        const int nw = (rw + shift + 3) >> 2;                  // <= 18 words (rw <= 66)
+        const uint8_t* srow = pyr + L.img_off + (size_t)iniY * L.pitch + ax;
+        const int xw = tid & 31;
+        if (xw < nw)
+            for (int y = tid >> 5; y < rh; y += 8)
+                reinterpret_cast<uint32_t*>(roi_raw + y * kRoiPitchRaw)[xw] = *reinterpret_cast<const uint32_t*>(srow + (size_t)y * L.pitch + 4 * xw);
         roi = roi_raw + shift;
     }
     for (int i = tid; i < kScDim * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+    if (use_tma) mbar_wait(&tma_bar, 0);
     __syncthreads();
+    // warp w owns rows w, w + 8, ...; lane = column (two halves: x = lane, lane + 32) -> no integer divisions, and the
+    // raster order needed for the output falls out of ballots (x order) and a scan over rows (y order)
+    const int lane = tid & 31, warp = tid >> 5;
     const int th_lo = min(g.ini_th, g.min_th);
-    const int npx = vw * vh;
-    for (int p = tid; p < npx; p += 256) {
-        const int y = p / vw, x = p - y * vw;
-        const int s = fast_score_dev(roi + (y + 3) * kRoiPitch + (x + 3), th_lo);
-        sc[(y + 1) * kScPitch + (x + 1)] = (uint8_t)s;
-    }
-    __syncthreads();
-    // strict 8-neighbour maxima of the (masked) score tile, this thread's contiguous raster chunk (<= 15 px)
-    const int chunk = (npx + 255) / 256;
-    const int p0 = tid * chunk, p1 = min(p0 + chunk, npx);
-    uint32_t m_ini = 0, m_min = 0;
-    for (int p = p0; p < p1; p++) {
-        const int y = p / vw, x = p - y * vw;
-        const uint8_t* q = sc + (y + 1) * kScPitch + (x + 1);
-        const int s = q[0];
-        if (s == 0) continue;
-        const bool mx = s > q[-kScPitch - 1] && s > q[-kScPitch] && s > q[-kScPitch + 1] && s > q[-1] && s > q[1] &&
-                        s > q[kScPitch - 1] && s > q[kScPitch] && s > q[kScPitch + 1];
-        if (mx) {
-            if (s >= g.ini_th) m_ini |= 1u << (p - p0);
-            if (s >= g.min_th) m_min |= 1u << (p - p0);
+    for (int y = warp; y < vh; y += 8) {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int x = lane + 32 * half;
+            if (x < vw) sc[(y + 1) * kScPitch + (x + 1)] = (uint8_t)fast_score_dev(roi + (y + 3) * kRoiPitch + (x + 3), th_lo);
         }
     }
-    const int any_ini = __syncthreads_or(m_ini != 0);
-    const uint32_t m = any_ini ? m_ini : m_min;
-    int total;
-    int pos = block_scan_values(__popc(m), warp_tmp, &total);
+    __syncthreads();
+    // strict 8-neighbour maxima of the (masked) score tile; per row two ballot words for each threshold
+    bool any_ini_local = false;
+    for (int y = warp; y < vh; y += 8) {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int x = lane + 32 * half;
+            bool f_ini = false, f_min = false;
+            if (x < vw) {
+                const uint8_t* q = sc + (y + 1) * kScPitch + (x + 1);
+                const int s = q[0];
+                if (s != 0 && s > q[-kScPitch - 1] && s > q[-kScPitch] && s > q[-kScPitch + 1] && s > q[-1] && s > q[1] &&
+                    s > q[kScPitch - 1] && s > q[kScPitch] && s > q[kScPitch + 1]) {
+                    f_ini = s >= g.ini_th;
+                    f_min = s >= g.min_th;
+                }
+            }
+            const uint32_t b_ini = __ballot_sync(0xffffffffu, f_ini), b_min = __ballot_sync(0xffffffffu, f_min);
+            if (lane == 0) { row_ini[y * 2 + half] = b_ini; row_min[y * 2 + half] = b_min; }
+            any_ini_local |= b_ini != 0;
+        }
+    }
+    const int any_ini = __syncthreads_or(any_ini_local);
+    const uint32_t* rowm = any_ini ? row_ini : row_min;
+    if (warp == 0) {  // exclusive scan of the per-row counts (vh <= 60 rows: two per lane)
+        const int y0 = 2 * lane, y1 = 2 * lane + 1;
+        const int c0 = y0 < vh ? __popc(rowm[y0 * 2]) + __popc(rowm[y0 * 2 + 1]) : 0;
+        const int c1 = y1 < vh ? __popc(rowm[y1 * 2]) + __popc(rowm[y1 * 2 + 1]) : 0;
+        int inc = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (y0 < vh) row_off[y0] = inc - c0 - c1;
+        if (y1 < vh) row_off[y1] = inc - c1;
+        if (lane == 31) row_off[64] = inc;
+    }
+    __syncthreads();
+    const int total = row_off[64];
     if (total > L.slot) {  // impossible for strict 8-neighbour maxima; never truncate silently
         if (tid == 0) { atomicExch(status, 101); cell_count[cell] = 0; }
         return;
     }
     const int base = L.cand_base + c * L.slot;
-    for (int p = p0; p < p1; p++) {
-        if (m >> (p - p0) & 1u) {
-            const int y = p / vw, x = p - y * vw;
-            // coordinates relative to (minBorderX, minBorderY): FAST's ROI coordinate + j*wCell (:822-823)
-            cand_xy[base + pos] = (uint32_t)(x + 3 + cj * L.w_cell) | (uint32_t)(y + 3 + ci * L.h_cell) << 16;
-            cand_r[base + pos] = sc[(y + 1) * kScPitch + (x + 1)];
-            pos++;
+    for (int y = warp; y < vh; y += 8) {
+        const uint32_t m0 = rowm[y * 2], m1 = rowm[y * 2 + 1];
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t m = half ? m1 : m0;
+            if (m >> lane & 1u) {
+                const int x = lane + 32 * half;
+                const int pos = row_off[y] + (half ? __popc(m0) : 0) + __popc(m & lt);
+                // coordinates relative to (minBorderX, minBorderY): FAST's ROI coordinate + j*wCell (:822-823)
+                cand_xy[base + pos] = (uint32_t)(x + 3 + cj * L.w_cell) | (uint32_t)(y + 3 + ci * L.h_cell) << 16;
+                cand_r[base + pos] = sc[(y + 1) * kScPitch + (x + 1)];
+            }
         }
     }
     if (tid == 0) cell_count[cell] = total;
+}
+
+// cuTensorMapEncodeTiled is a driver-API symbol; it is resolved at run time through the runtime so that the library
+// does not link libcuda (and still loads on a machine without a driver, where every compute call fails loudly).
+bool encode_tma_maps(const OrbGeom& g, uint8_t* pyr, TmaMaps* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (int l = 0; l < g.n_levels; l++) {
+        const LevelGeom& L = g.lv[l];
+        const cuuint64_t dims[2] = {(cuuint64_t)L.w, (cuuint64_t)L.h};
+        const cuuint64_t strides[1] = {(cuuint64_t)L.pitch};
+        const cuuint32_t box[2] = {(cuuint32_t)kRoiPitch, (cuuint32_t)kCellRoiMax};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = ((EncodeFn)fn)(&out->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, pyr + L.img_off, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    return true;
 }
 
 // level < 0: all levels in one launch; else only the cells of that level (lets a level start as soon as it is resized)
 void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s) {
     const int begin = level < 0 ? 0 : g.lv[level].cell_base;
     const int n = level < 0 ? g.n_cells : g.lv[level].n_cols * g.lv[level].n_rows;
-    k_fast_cells<<<n, 256, 0, s>>>(g, b.pyr, b.cell_count, b.cand_xy, b.cand_r, b.status, begin);
+    k_fast_cells<<<n, 256, 0, s>>>(g, *b.tma_maps, b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_r, b.status, begin);
 }
 
 // ------------------------------------------------------------------------------------------------ K5 Gaussian 7x7
@@ -332,6 +461,14 @@ int octtree_smem_bytes(const OrbGeom& g, int level, int key_smem_cap) {
     return oct_layout(g.lv[level].node_cap, key_smem_cap, g.lv[level].n_cols * g.lv[level].n_rows).total;
 }
 
+// Warp-aggregated shared-memory counter increment: lanes that hit the same counter elect one leader, so the early
+// quadtree passes (thousands of keys on a handful of counters) do not serialise on the shared-memory atomic unit.
+__device__ __forceinline__ void count_add(int* counters, int idx) {
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, idx);
+    if (idx >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counters[idx], __popc(peers));
+}
+
 __device__ __forceinline__ int quadrant_of(uint32_t xy, short4 b) {
     const int x = xy & 0xffff, y = xy >> 16;
     const int xm = b.x + ((b.z - b.x + 1) >> 1);  // UL.x + ceil((UR.x-UL.x)/2)   (:483)
@@ -412,7 +549,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
     for (int k = tid; k < M; k += nt) {
         const int ni = (int)__fdiv_rn((float)(kxy[k] & 0xffff), L.h_x);
         knode[k] = (uint16_t)ni;
-        atomicAdd(&cc[ni], 1);
+        count_add(cc, ni);
     }
     __syncthreads();
     for (int i = tid; i < L.n_ini; i += nt) scan[i] = cc[i] > 0;
@@ -450,7 +587,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
             __syncthreads();
             for (int k = tid; k < M; k += nt) {
                 const int nd = knode[k];
-                if (cnt_cur[nd] > 1) atomicAdd(&cc[nd * 4 + quadrant_of(kxy[k], bnd_cur[nd])], 1);
+                count_add(cc, cnt_cur[nd] > 1 ? nd * 4 + quadrant_of(kxy[k], bnd_cur[nd]) : -1);
             }
             __syncthreads();
             for (int i = tid; i < s; i += nt) {
@@ -546,15 +683,19 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
             for (int i = tid; i < s; i += nt)
                 if (candf[i]) krank[scan[i]] = i;  // candidates in position order (temporary)
             __syncthreads();
+            for (int i = tid; i < m; i += nt) crank[i] = cnt_cur[krank[i]];  // candidate counts, contiguous (temporary)
+            __syncthreads();
             for (int i = tid; i < m; i += nt) {
-                const int ci = cnt_cur[krank[i]];
+                const int ci = crank[i];
                 int rank = 0;
+#pragma unroll 8
                 for (int j = 0; j < m; j++) {
-                    const int cj = cnt_cur[krank[j]];
+                    const int cj = crank[j];
                     rank += (cj > ci) || (cj == ci && j < i);
                 }
                 procpos[rank] = krank[i];
             }
+            __syncthreads();
         }
         for (int i = tid; i < 4 * s; i += nt) cc[i] = 0;
         for (int i = tid; i < s; i += nt) crank[i] = -1;
@@ -563,7 +704,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
         // ---- keys per (node, quadrant)
         for (int k = tid; k < M; k += nt) {
             const int nd = knode[k];
-            if (candf[nd]) atomicAdd(&cc[nd * 4 + quadrant_of(kxy[k], bnd_cur[nd])], 1);
+            count_add(cc, candf[nd] ? nd * 4 + quadrant_of(kxy[k], bnd_cur[nd]) : -1);
         }
         __syncthreads();
         for (int r = tid; r < m; r += nt) {

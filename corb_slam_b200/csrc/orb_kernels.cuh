@@ -1,11 +1,17 @@
 // Launch wrappers of the ORB front-end kernels (definitions in orb_kernels.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "orb_geom.h"
 
 namespace corb {
+
+// one tensor map per pyramid level (u8, {w, h}, row pitch), box = 80 x 66 bytes: the FAST cell ROI
+struct TmaMaps {
+    CUtensorMap m[kMaxLevels];
+};
 
 struct OrbBuffers {
     uint8_t* pyr;        // un-blurred pyramid, all levels, pitched
@@ -28,10 +34,17 @@ struct OrbBuffers {
     uint8_t* desc;       // [kp_cap * 32]
     int* count;          // [1]
     int* status;         // [1] device-side error flag (0 ok)
+    const TmaMaps* tma_maps;  // host pointer (passed by value as a __grid_constant__ kernel parameter)
+    int use_tma;
 };
+
+// encodes the per-level tensor maps; returns false when the driver entry point is unavailable
+bool encode_tma_maps(const OrbGeom& g, uint8_t* pyr, TmaMaps* out);
 
 int octtree_smem_bytes(const OrbGeom& g, int level, int key_smem_cap);
 
+void launch_import(const OrbGeom& g, const OrbBuffers& b, const uint8_t* src, int stride, cudaStream_t s);
+const void* import_kernel_ptr();
 void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s);
 void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s);
 void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s);

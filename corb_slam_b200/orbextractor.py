@@ -128,6 +128,9 @@ class ORBextractor:
     def stream(self):
         return lib().corb_orb_stream(self._h)
 
+    def uses_tma(self):
+        return bool(lib().corb_orb_uses_tma(self._h))
+
     def launches_per_extract(self):
         return lib().corb_orb_launches_per_extract(self._h)
 
@@ -167,3 +170,44 @@ class ORBextractor:
         if getattr(self, "_shape", None) is None:
             raise RuntimeError("no extraction has run")
         return self._shape
+
+
+def extract_stereo(ex_left, ex_right, left, right, want_pyramid=False):
+    """Left/right extraction of one stereo frame from one thread (Frame::Frame's two ExtractORB threads, Frame.cc:78-81):
+    -> ((kps_l, desc_l), (kps_r, desc_r))."""
+    if left.shape != right.shape or left.dtype != np.uint8 or right.dtype != np.uint8 or left.ndim != 2:
+        raise TypeError("left/right must be 2-D uint8 arrays of the same shape")
+    if left.strides != right.strides or left.strides[1] != 1:
+        left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
+    h, w = left.shape
+    outs = []
+    for ex in (ex_left, ex_right):
+        if ex._out_shape != (h, w):
+            cap = ex.capacity(w, h)
+            ex._out = (np.empty(cap, KP_DTYPE), np.empty((cap, 32), np.uint8))
+            ex._out_shape = (h, w)
+        ex._shape = (h, w)
+        outs.append(ex._out)
+    nl, nr = C.c_int32(), C.c_int32()
+    pl = pr = None
+    if want_pyramid:
+        pyrs = [[np.empty(ex.level_size(l, w, h)[::-1], np.uint8) for l in range(ex.nlevels)] for ex in (ex_left, ex_right)]
+        pl = (C.c_void_p * ex_left.nlevels)(*[a.ctypes.data for a in pyrs[0]])
+        pr = (C.c_void_p * ex_right.nlevels)(*[a.ctypes.data for a in pyrs[1]])
+        ex_left.mvImagePyramid, ex_right.mvImagePyramid = pyrs
+    check(lib().corb_orb_extract_pair(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0],
+                                      outs[0][0].ctypes.data, outs[0][1].ctypes.data, C.byref(nl), outs[1][0].ctypes.data,
+                                      outs[1][1].ctypes.data, C.byref(nr), pl, pr))
+    res = []
+    for (k, d), n, ex in zip(outs, (nl.value, nr.value), (ex_left, ex_right)):
+        if n == 0:
+            res.append((k[:0].copy(), None))
+        elif ex.copy_outputs:
+            res.append((k[:n].copy(), d[:n].copy()))
+        else:
+            res.append((k[:n], d[:n]))
+    return tuple(res)
+
+
+def extract_stereo_device(ex_left, ex_right, d_left, d_right, w, h, stride):
+    check(lib().corb_orb_extract_pair_device(ex_left._h, ex_right._h, int(d_left), int(d_right), w, h, stride))

@@ -83,6 +83,14 @@ CORB_API int corb_orb_extract(corb_orb* h, const uint8_t* img, int w, int hgt, i
 CORB_API int corb_orb_extract_submit(corb_orb* h, const uint8_t* img, int w, int hgt, int stride, int want_pyramid);
 CORB_API int corb_orb_extract_wait(corb_orb* h, corb_keypoint* kps, uint8_t* desc, int* n, uint8_t* const* pyr_out);
 
+/* Both images of a stereo frame from ONE thread: the two per-frame graphs are launched back to back and both results
+ * collected - what Frame::Frame does with two std::threads (Frame.cc:78-81). Arguments as corb_orb_extract, per side. */
+CORB_API int corb_orb_extract_pair(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt,
+                                   int stride, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r,
+                                   uint8_t* desc_r, int* n_r, uint8_t* const* pyr_l, uint8_t* const* pyr_r);
+CORB_API int corb_orb_extract_pair_device(corb_orb* hl, corb_orb* hr, const uint8_t* d_img_l, const uint8_t* d_img_r, int w,
+                                          int hgt, int stride);
+
 /* Device-resident form: `d_img` is already in HBM (pitch `stride`), results stay in HBM for on-GPU consumers
  * (matcher, stereo). Enqueued on the handle's stream; corb_orb_sync() waits for it. */
 CORB_API int corb_orb_extract_device(corb_orb* h, const uint8_t* d_img, int w, int hgt, int stride);
@@ -97,6 +105,9 @@ CORB_API int corb_orb_device_level(const corb_orb* h, int level, int blurred, co
 CORB_API void* corb_orb_stream(const corb_orb* h);
 /* number of kernel launches one extraction enqueues (graph nodes that are kernels) */
 CORB_API int corb_orb_launches_per_extract(const corb_orb* h);
+/* 1 if the FAST kernel stages its tiles with TMA (cp.async.bulk.tensor) for the current plan; 0 if the driver entry point
+ * was unavailable or CORB_NO_TMA is set in the environment (plain vector loads then; same results) */
+CORB_API int corb_orb_uses_tma(const corb_orb* h);
 
 /* Per-kernel device time (ms, averaged over `reps` eager replays with CUDA events between launches) of one extraction
  * of the image currently resident; *n kernels in launch order, named by corb_orb_kernel_name(). For roofline reports. */

@@ -102,3 +102,43 @@ def test_strided_input_and_two_handles_concurrently():
         assert got[0].tobytes() == exp[0].tobytes()
         np.testing.assert_array_equal(got[1], exp[1])
     exl.close(); exr.close()
+
+
+def test_stereo_pair_call_and_device_resident_path():
+    import torch
+    from corb_slam_b200 import extract_stereo, extract_stereo_device
+    left, right = stereo_frame(1250)
+    ora = oracle.OrbExtractor(*PARAMS)
+    okl, okr = ora(left), ora(right)
+    exl, exr = ORBextractor(*PARAMS), ORBextractor(*PARAMS)
+    # pageable numpy input and page-locked input (read in place over PCIe by the import kernel) must agree
+    pl, pr = torch.from_numpy(left).pin_memory(), torch.from_numpy(right).pin_memory()
+    for a, b in ((left, right), (pl.numpy(), pr.numpy())):
+        (kl, dl), (kr, dr) = extract_stereo(exl, exr, a, b, want_pyramid=True)
+        assert kl.tobytes() == okl[0].tobytes() and kr.tobytes() == okr[0].tobytes()
+        np.testing.assert_array_equal(dl, okl[1]); np.testing.assert_array_equal(dr, okr[1])
+        np.testing.assert_array_equal(exr.mvImagePyramid[3], ora.pyramid(3))
+    # device-resident: pitched device image in, results stay in HBM
+    dl_, dr_ = torch.zeros((375, 1280), dtype=torch.uint8, device="cuda"), torch.zeros((375, 1280), dtype=torch.uint8, device="cuda")
+    dl_[:, :1242] = torch.from_numpy(left).cuda(); dr_[:, :1242] = torch.from_numpy(right).cuda()
+    extract_stereo_device(exl, exr, dl_.data_ptr(), dr_.data_ptr(), 1242, 375, 1280)
+    exl.sync(); exr.sync()
+    kp_ptr, desc_ptr, cnt_ptr = exr.device_results()
+    assert exr.tap_level_count(0) == ora.level_count(0)
+    np.testing.assert_array_equal(exr.tap_image(2), ora.pyramid(2))
+    exl.close(); exr.close()
+
+
+def test_tma_and_fallback_staging_agree(monkeypatch):
+    left, _ = stereo_frame(1260)
+    ex = ORBextractor(*PARAMS)
+    k1, d1 = ex(left)
+    assert ex.uses_tma(), "cuTensorMapEncodeTiled must be available on the B200 box"
+    ex.close()
+    monkeypatch.setenv("CORB_NO_TMA", "1")
+    ex2 = ORBextractor(*PARAMS)
+    k2, d2 = ex2(left)
+    assert not ex2.uses_tma()
+    assert k1.tobytes() == k2.tobytes()
+    np.testing.assert_array_equal(d1, d2)
+    ex2.close()
