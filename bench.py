@@ -281,8 +281,9 @@ def run_ours(args):
         prof = exl.profile(reps=20)
         agg = {}
         for name, ms in prof:
-            agg[name] = agg.get(name, 0.0) + ms
-        top = max(prof, key=lambda kv: kv[1])
+            base = name.split("[")[0]
+            agg[base] = agg.get(base, 0.0) + ms
+        top = max(prof, key=lambda kv: kv[1])  # the single longest launch (per-level launches run concurrently in the graph)
         pk, pk_kind = peaks()
         achieved = ALGO_BYTES_PER_IMAGE / (top[1] * 1e-3) / 1e9
         fps = world * args.steps / (dev_ms * 1e-3)
@@ -309,7 +310,8 @@ def run_ours(args):
                          "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_IMAGE, "kernel_ms": top[1],
                          "whole_frame_frac": 2 * ALGO_BYTES_PER_IMAGE * fps / world / 1e9 / pk["hbm_gbs"],
-                         "per_kernel_ms": {k: round(v, 5) for k, v in agg.items()}},
+                         "per_kernel_ms_sum_over_levels": {k: round(v, 5) for k, v in agg.items()},
+                         "per_launch_ms": {k: round(v, 5) for k, v in prof}},
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 2, "kind": "port",
                              "sample": "%d stereo frames, oracle port, L/R on two threads (Frame.cc:78-81), %.1f s"
                                        % (args.sample_frames, cpu_dt), "host_cores_available": os.cpu_count()},

@@ -572,14 +572,16 @@ int corb_orb_device_level(const corb_orb* h, int level, int blurred, const uint8
     return CORB_OK;
 }
 
-// Eager (non-graph) replay of the kernels of one extraction on the image currently in level 0, with a CUDA event
-// between consecutive launches: per-kernel device time for the roofline report. Order: resize 1..L-1, blur,
-// fast_cells, quadtree, orient_desc.
+// Eager (non-graph) replay of the launches of one extraction on the image currently in level 0, with a CUDA event
+// between consecutive launches: per-launch device time for the roofline report. Order: resize 1..L-1, blur,
+// fast_cells per level, quadtree per level, orient_desc (the graph runs the per-level launches concurrently).
+static int profile_launch_count(const corb_orb* h) { return (h->nlevels - 1) + 1 + 2 * h->nlevels + 1; }
+
 int corb_orb_profile(corb_orb* h, int reps, float* ms, int cap, int* n) {
     CORB_CHECK(h && h->plan_w && ms && n && reps >= 1, CORB_ERR_INVALID, "bad argument or no plan");
     const OrbGeom& g = h->geom;
-    const int nk = (g.n_levels - 1) + 4;
-    CORB_CHECK(cap >= nk, CORB_ERR_INVALID, "need room for %d kernels", nk);
+    const int nk = profile_launch_count(h);
+    CORB_CHECK(cap >= nk, CORB_ERR_INVALID, "need room for %d launches", nk);
     CORB_CUDA(cudaSetDevice(h->device));
     std::vector<cudaEvent_t> ev(nk + 1);
     for (auto& e : ev) CORB_CUDA(cudaEventCreate(&e));
@@ -593,10 +595,14 @@ int corb_orb_profile(corb_orb* h, int reps, float* ms, int cap, int* n) {
         }
         launch_blur(g, h->buf, h->stream);
         CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
-        launch_fast_cells(g, h->buf, -1, h->stream);
-        CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
-        launch_octtree(g, h->buf, -1, h->key_smem_cap, h->oct_smem, h->stream);
-        CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        for (int l = 0; l < g.n_levels; l++) {
+            launch_fast_cells(g, h->buf, l, h->stream);
+            CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        }
+        for (int l = 0; l < g.n_levels; l++) {
+            launch_octtree(g, h->buf, l, h->key_smem_cap, h->oct_smem, h->stream);
+            CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
+        }
         launch_orient_desc(g, h->buf, h->stream);
         CORB_CUDA(cudaEventRecord(ev[k++], h->stream));
         CORB_CUDA(cudaStreamSynchronize(h->stream));
@@ -613,15 +619,17 @@ int corb_orb_profile(corb_orb* h, int reps, float* ms, int cap, int* n) {
 
 const char* corb_orb_kernel_name(const corb_orb* h, int i) {
     if (!h) return "";
-    const int nr = h->nlevels - 1;
-    if (i < nr) return "k_resize";
-    switch (i - nr) {
-        case 0: return "k_blur";
-        case 1: return "k_fast_cells";
-        case 2: return "k_octtree";
-        case 3: return "k_orient_desc";
-    }
-    return "";
+    static thread_local char name[32];
+    const int nr = h->nlevels - 1, L = h->nlevels;
+    if (i < nr) { snprintf(name, sizeof(name), "k_resize[%d]", i + 1); return name; }
+    i -= nr;
+    if (i == 0) return "k_blur";
+    i -= 1;
+    if (i < L) { snprintf(name, sizeof(name), "k_fast_cells[%d]", i); return name; }
+    i -= L;
+    if (i < L) { snprintf(name, sizeof(name), "k_octtree[%d]", i); return name; }
+    i -= L;
+    return i == 0 ? "k_orient_desc" : "";
 }
 
 void* corb_orb_stream(const corb_orb* h) { return h ? (void*)h->stream : nullptr; }

@@ -88,9 +88,11 @@ void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_
 }
 
 // ------------------------------------------------------------------------------------------------ K2 FAST per cell
-constexpr int kRoiPitch = 80;  // bytes per ROI row in shared memory: the TMA box width (multiple of 16, >= kCellRoiMax + 3)
+constexpr int kRoiPitch = 96;  // bytes per ROI row in shared memory = TMA box width: multiple of 16 and >= kCellRoiMax + 15,
+                               // because the innermost TMA coordinate must be 16-byte aligned (measured: any other x traps
+                               // with 'illegal instruction' on sm_100a), so the box starts at iniX & ~15
 constexpr int kRoiPitchRaw = kRoiPitch;
-constexpr int kRoiTmaBytes = kRoiPitch * kCellRoiMax;  // one 80 x 66 box per cell
+constexpr int kRoiTmaBytes = kRoiPitch * kCellRoiMax;  // one 96 x 66 box per cell
 
 // ---- TMA (cp.async.bulk.tensor) + mbarrier primitives, sm_90+/sm_100a PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -202,7 +204,7 @@ __device__ __forceinline__ int block_scan_values(int v, int* warp_tmp, int* tota
 // The cell's ROI (wCell+6 x hCell+6) is staged in shared memory; FAST ignores a 3 px rim, so the valid areas of
 // neighbouring cells tile the level disjointly and NMS sees zeros outside its own cell, exactly like cv::FAST on the
 // ROI. The iniTh -> minTh fallback is decided per cell on the post-NMS count.
-__global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_constant__ TmaMaps tm, int use_tma,
+__global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_constant__ CUtensorMap tmap, int use_tma,
                                                     const uint8_t* __restrict__ pyr, int* __restrict__ cell_count,
                                                     uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_r,
                                                     int* __restrict__ status, int cell_begin) {
@@ -228,19 +230,19 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_cons
         return;
     }
     if (use_tma) {
-        // stage the ROI with one TMA box load (80 x 66 bytes at (iniX, iniY) of this level's tensor map; out-of-image
+        // stage the ROI with one TMA box load (96 x 66 bytes at (iniX & ~15, iniY) of this level's tensor map; out-of-image
         // bytes are zero filled and never read): a single thread issues it, everybody waits on the mbarrier
         if (tid == 0) mbar_init(&tma_bar, 1);
         __syncthreads();
         if (tid == 0) {
             mbar_expect_tx(&tma_bar, kRoiTmaBytes);
-            tma_load_2d(roi_raw, &tm.m[l], iniX, iniY, &tma_bar);
+            tma_load_2d(roi_raw, &tmap, iniX & ~15, iniY, &tma_bar);
         }
-        roi = roi_raw;
+        roi = roi_raw + (iniX & 15);
     } else {
         // fallback: 4-byte words from the 4-aligned column at or left of iniX (the pitch is a multiple of 128)
         const int ax = iniX & ~3, shift = iniX - ax;           // shift in 0..3; roi row holds [ax, ax + 4 * nw)
-        const int nw = (rw + shift + 3) >> 2;                  // <= 18 words (rw <= 66)
+        const int nw = (rw + shift + 3) >> 2;                  // <= 18 words (rw <= 66), within the 96-byte row
         const uint8_t* srow = pyr + L.img_off + (size_t)iniY * L.pitch + ax;
         const int xw = tid & 31;
         if (xw < nw)
@@ -352,11 +354,15 @@ bool encode_tma_maps(const OrbGeom& g, uint8_t* pyr, TmaMaps* out) {
     return true;
 }
 
-// level < 0: all levels in one launch; else only the cells of that level (lets a level start as soon as it is resized)
+// level < 0: every level (one launch each); else only that level (lets a level start as soon as it is resized)
 void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s) {
-    const int begin = level < 0 ? 0 : g.lv[level].cell_base;
-    const int n = level < 0 ? g.n_cells : g.lv[level].n_cols * g.lv[level].n_rows;
-    k_fast_cells<<<n, 256, 0, s>>>(g, *b.tma_maps, b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_r, b.status, begin);
+    // one launch per level: the level's tensor map travels as a __grid_constant__ parameter (the form TMA expects)
+    const int l0 = level < 0 ? 0 : level, l1 = level < 0 ? g.n_levels : level + 1;
+    for (int l = l0; l < l1; l++) {
+        const int n = g.lv[l].n_cols * g.lv[l].n_rows;
+        k_fast_cells<<<n, 256, 0, s>>>(g, b.tma_maps->m[l], b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_r, b.status,
+                                       g.lv[l].cell_base);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K5 Gaussian 7x7
