@@ -79,8 +79,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_extract_fps(n_frames, clients=1):
-    """Oracle port of the reference path: `clients` concurrent clients, each running left/right on two threads."""
+def cpu_extract_fps(n_frames, clients=1, stereo=False):
+    """Oracle port of the reference path: `clients` concurrent clients, each running left/right on two threads
+    (Frame.cc:78-81); with stereo=True also Frame::ComputeStereoMatches (Frame.cc:90) on the calling thread."""
     import oracle
     from corb_slam_b200.synth import stereo_frame, frame_seed
     frames = [stereo_frame(frame_seed(i)) for i in range(min(n_frames, N_POOL))]
@@ -91,10 +92,14 @@ def cpu_extract_fps(n_frames, clients=1):
     def client(exl, exr):
         for i in range(n_frames):
             l, r = frames[i % len(frames)]
-            t = threading.Thread(target=exr, args=(r,))
+            res = {}
+            t = threading.Thread(target=lambda: res.__setitem__("r", exr(r)))
             t.start()
-            exl(l)
+            kl, dl = exl(l)
             t.join()
+            if stereo:
+                kr, dr = res["r"]
+                oracle.stereo_matches(exl, exr, kl, dl, kr, dr, 386.1448, 386.1448 / 718.856)
 
     ths = [threading.Thread(target=client, args=e) for e in exs]
     t0 = time.perf_counter()
@@ -167,7 +172,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from corb_slam_b200 import ORBextractor, extract_stereo, extract_stereo_device
+    from corb_slam_b200 import ORBextractor, extract_stereo, extract_stereo_device, frame_stereo
     from corb_slam_b200.synth import stereo_frame, frame_seed
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,6 +248,13 @@ def run_ours(args):
     for i in range(args.steps):
         step_host(i, pyr=True)
     e2e_pyr_s = time.perf_counter() - t0
+    barrier()
+    t0 = time.perf_counter()
+    n_stereo = 0
+    for i in range(args.steps):  # the stereo Frame constructor: ExtractORB x2 + ComputeStereoMatches, pyramids stay in HBM
+        fr = frame_stereo(exl, exr, npin[i % N_POOL][0], npin[i % N_POOL][1], 386.1448, 386.1448 / 718.856)
+        n_stereo += int((fr[2] >= 0).sum())
+    e2e_frame_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
 
     # ---- global BA (second half of the BASELINE.json metric): landmark-sharded over the ranks, reduced camera system
@@ -269,10 +281,10 @@ def run_ours(args):
             oracle.lib()
             ba_rms = B.chi2(ba_out)[1]  # checker only: RMS reprojection error of the GPU solution
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_pyr_s * 1e3, ba_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_pyr_s * 1e3, ba_ms, e2e_frame_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_pyr_ms, ba_ms = [float(x) for x in t.tolist()]
+    dev_ms, e2e_ms, e2e_pyr_ms, ba_ms, e2e_frame_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
         # per-kernel times of one image (eager replay with events) for the roofline of the dominant kernel
@@ -291,6 +303,7 @@ def run_ours(args):
         h2d = 2 * W * H
         d2h = int(kp_per_frame * 60) + 16
         cpu_fps, cpu_dt = cpu_extract_fps(args.sample_frames, clients=1)
+        cpu_fps_frame, _ = cpu_extract_fps(max(8, args.sample_frames // 4), clients=1, stereo=True)
         line = {
             "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -304,7 +317,13 @@ def run_ours(args):
             "e2e_with_pyramid": {"value": world * args.steps / (e2e_pyr_ms * 1e-3), "unit": "frames/s",
                                  "d2h_bytes_per_step": d2h + 2 * 1441432, "ms_per_step": e2e_pyr_ms / args.steps,
                                  "note": "also copies mvImagePyramid to the host (needed while ComputeStereoMatches is on the CPU)"},
+            "e2e_stereo_frame": {"value": world * args.steps / (e2e_frame_ms * 1e-3), "unit": "frames/s",
+                                 "ms_per_step": e2e_frame_ms / args.steps, "stereo_matches_per_frame": n_stereo / max(1, args.steps),
+                                 "d2h_bytes_per_step": d2h + 8 * int(kp_per_frame / 2),
+                                 "note": "corb_frame_stereo: ExtractORB left+right and Frame::ComputeStereoMatches on the GPU; "
+                                         "the pyramids never leave HBM"},
             "gpu_launches": 2 * exl.launches_per_extract() * args.steps,
+            "tma": exl.uses_tma(),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
@@ -314,7 +333,8 @@ def run_ours(args):
                          "per_launch_ms": {k: round(v, 5) for k, v in prof}},
             "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 2, "kind": "port",
                              "sample": "%d stereo frames, oracle port, L/R on two threads (Frame.cc:78-81), %.1f s"
-                                       % (args.sample_frames, cpu_dt), "host_cores_available": os.cpu_count()},
+                                       % (args.sample_frames, cpu_dt), "host_cores_available": os.cpu_count(),
+                             "stereo_frame_value": cpu_fps_frame},
             "keypoints_per_frame": kp_per_frame,
         }
         if ba_info is not None:

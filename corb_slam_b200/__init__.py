@@ -4,7 +4,8 @@ Only what the path needs: csrc/ (CUDA kernels + the C ABI of libcorb_b200.so) an
 reference classes that own the path (ORBextractor, ORBmatcher, ORBVocabulary, Optimizer).
 """
 from ._lib import CorbError, KP_DTYPE, LIB_PATH  # noqa: F401
-from .orbextractor import ORBextractor, extract_stereo, extract_stereo_device  # noqa: F401
+from .orbextractor import (ORBextractor, compute_stereo_matches, extract_stereo, extract_stereo_device,  # noqa: F401
+                           frame_stereo)
 from .orbmatcher import ORBmatcher, BowFeatures  # noqa: F401
 from .orbvocabulary import ORBVocabulary  # noqa: F401
 from .optimizer import Optimizer, torch_allreduce  # noqa: F401

@@ -64,6 +64,12 @@ struct corb_orb {
     uint8_t* d_out = nullptr;
     size_t out_bytes = 0;
     bool pending = false, pending_pyr = false, pending_empty = false;
+
+    // stereo matching outputs (allocated on first use; this handle is the LEFT one)
+    float* d_stereo = nullptr;   // [u_right kp_cap | depth kp_cap | best_dist kp_cap (int)]
+    float* h_stereo = nullptr;   // pinned [u_right | depth]
+    cudaEvent_t ev_peer = nullptr;
+    int stereo_cap = 0;
 };
 
 static void free_plan(corb_orb* h) {
@@ -77,6 +83,9 @@ static void free_plan(corb_orb* h) {
     if (h->h_pyr) cudaFreeHost(h->h_pyr), h->h_pyr = nullptr;
     if (h->h_out) cudaFreeHost(h->h_out), h->h_out = nullptr;
     h->h_kps = nullptr; h->h_desc = nullptr; h->h_scalars = nullptr;
+    if (h->h_stereo) cudaFreeHost(h->h_stereo), h->h_stereo = nullptr;
+    h->d_stereo = nullptr;  // owned by dev_allocs
+    h->stereo_cap = 0;
     h->plan_w = h->plan_h = 0;
 }
 
@@ -412,6 +421,7 @@ void corb_orb_destroy(corb_orb* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_plan(h);
+    if (h->ev_peer) cudaEventDestroy(h->ev_peer);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -536,6 +546,75 @@ int corb_orb_extract_pair_device(corb_orb* hl, corb_orb* hr, const uint8_t* d_im
     int rc = corb_orb_extract_device(hl, d_img_l, w, hgt, stride);
     if (rc != CORB_OK) return rc;
     return corb_orb_extract_device(hr, d_img_r, w, hgt, stride);
+}
+
+// ---- Frame::ComputeStereoMatches (Frame.cc:470-644) on the resident results of the last extraction of `left`/`right`
+static int enqueue_stereo(corb_orb* left, corb_orb* right, float mbf, float mb) {
+    CORB_CHECK(left && right && left != right, CORB_ERR_INVALID, "two distinct handles are required");
+    CORB_CHECK(left->plan_w && left->plan_w == right->plan_w && left->plan_h == right->plan_h && left->nlevels == right->nlevels &&
+                   left->device == right->device && left->scale_factor_f == right->scale_factor_f,
+               CORB_ERR_INVALID, "left and right extractor must share device, image size and pyramid parameters");
+    CORB_CHECK(mb > 0.f && mbf > 0.f, CORB_ERR_INVALID, "mbf and mb must be positive");
+    CORB_CUDA(cudaSetDevice(left->device));
+    const OrbGeom& g = left->geom;
+    if (left->stereo_cap != g.kp_cap) {
+        int rc = dev_alloc(left, &left->d_stereo, 3 * (size_t)g.kp_cap);
+        if (rc != CORB_OK) return rc;
+        if (left->h_stereo) cudaFreeHost(left->h_stereo), left->h_stereo = nullptr;
+        CORB_CUDA(cudaMallocHost(&left->h_stereo, 2 * (size_t)g.kp_cap * sizeof(float)));
+        left->stereo_cap = g.kp_cap;
+    }
+    if (!left->ev_peer) CORB_CUDA(cudaEventCreateWithFlags(&left->ev_peer, cudaEventDisableTiming));
+    StereoArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kl = left->buf.kps; a.kr = right->buf.kps;
+    a.dl = reinterpret_cast<const uint4*>(left->buf.desc); a.dr = reinterpret_cast<const uint4*>(right->buf.desc);
+    a.nl = left->buf.count; a.nr = right->buf.count;
+    a.pyr_l = left->buf.pyr; a.pyr_r = right->buf.pyr;
+    for (int l = 0; l < left->nlevels; l++) { a.scale[l] = left->scale[l]; a.inv_scale[l] = left->inv_scale[l]; }
+    a.mbf = mbf; a.mb = mb;
+    a.u_right = left->d_stereo; a.depth = left->d_stereo + g.kp_cap;
+    a.best_dist = reinterpret_cast<int*>(left->d_stereo + 2 * (size_t)g.kp_cap);
+    a.n_rows = g.lv[0].h;
+    CORB_CUDA(cudaEventRecord(left->ev_peer, right->stream));   // the right extraction must have finished
+    CORB_CUDA(cudaStreamWaitEvent(left->stream, left->ev_peer, 0));
+    launch_stereo(g, a, left->stream);
+    CORB_CUDA(cudaGetLastError());
+    CORB_CUDA(cudaMemcpyAsync(left->h_stereo, left->d_stereo, 2 * (size_t)g.kp_cap * sizeof(float), cudaMemcpyDeviceToHost, left->stream));
+    return CORB_OK;
+}
+
+int corb_stereo_match(corb_orb* left, corb_orb* right, float mbf, float mb, int n_left, float* u_right, float* depth) {
+    CORB_CHECK(u_right && depth && n_left >= 0, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(left && !left->pending && right && !right->pending, CORB_ERR_INVALID, "wait for the submitted extractions first");
+    int rc = enqueue_stereo(left, right, mbf, mb);
+    if (rc != CORB_OK) return rc;
+    CORB_CUDA(cudaStreamSynchronize(left->stream));
+    CORB_CHECK(n_left <= left->geom.kp_cap, CORB_ERR_INVALID, "n_left exceeds the keypoint capacity");
+    memcpy(u_right, left->h_stereo, n_left * sizeof(float));
+    memcpy(depth, left->h_stereo + left->geom.kp_cap, n_left * sizeof(float));
+    return CORB_OK;
+}
+
+int corb_frame_stereo(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride, float mbf,
+                      float mb, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r, uint8_t* desc_r, int* n_r,
+                      float* u_right, float* depth) {
+    CORB_CHECK(hl && hr && hl != hr && n_l && u_right && depth, CORB_ERR_INVALID, "bad argument");
+    int rc = corb_orb_extract_submit(hl, img_l, w, hgt, stride, 0);
+    if (rc != CORB_OK) return rc;
+    rc = corb_orb_extract_submit(hr, img_r, w, hgt, stride, 0);
+    int rc_s = CORB_OK;
+    if (rc == CORB_OK && !hl->pending_empty && !hr->pending_empty) rc_s = enqueue_stereo(hl, hr, mbf, mb);
+    const int rc_l = corb_orb_extract_wait(hl, kps_l, desc_l, n_l, nullptr);   // also completes the stereo kernels (same stream)
+    if (rc != CORB_OK) return rc;
+    rc = corb_orb_extract_wait(hr, kps_r, desc_r, n_r, nullptr);
+    if (rc_l != CORB_OK) return rc_l;
+    if (rc != CORB_OK) return rc;
+    if (rc_s != CORB_OK) return rc_s;
+    if (hl->pending_empty || hr->pending_empty || *n_l == 0) return CORB_OK;
+    memcpy(u_right, hl->h_stereo, *n_l * sizeof(float));
+    memcpy(depth, hl->h_stereo + hl->geom.kp_cap, *n_l * sizeof(float));
+    return CORB_OK;
 }
 
 int corb_orb_extract_device(corb_orb* h, const uint8_t* d_img, int w, int hgt, int stride) {

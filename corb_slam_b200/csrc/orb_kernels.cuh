@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/corb_b200.h"
 #include "orb_geom.h"
 
 namespace corb {
@@ -51,5 +52,20 @@ void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s);
 cudaError_t prepare_octtree(const OrbGeom& g, int key_smem_cap, int* smem_bytes_out);
 void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int level, int key_smem_cap, int smem_bytes, cudaStream_t s);
 void launch_orient_desc(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s);
+
+// Frame::ComputeStereoMatches on the device-resident results of two extractor handles (stereo.cu)
+struct StereoArgs {
+    const corb_keypoint *kl, *kr;
+    const uint4 *dl, *dr;
+    const int *nl, *nr;          // device counts of the two extractions
+    const uint8_t *pyr_l, *pyr_r;
+    float scale[kMaxLevels], inv_scale[kMaxLevels];
+    float mbf, mb;
+    float *u_right, *depth;      // [kp_cap]
+    int* best_dist;              // [kp_cap] SAD of the accepted match, -1 if none
+    int n_rows;
+};
+
+void launch_stereo(const OrbGeom& g, const StereoArgs& a, cudaStream_t s);
 
 }  // namespace corb

@@ -1,0 +1,165 @@
+// Frame::ComputeStereoMatches (corbslam_client/src/Frame.cc:470-644) on the device-resident results of the left and
+// right extractor handles: row-band Hamming search, 11x11 SAD refinement over +-5 px on the keypoint's pyramid level,
+// parabola fit, median-based outlier rejection. With this on the GPU the pyramids never cross PCIe;
+// only mvuRight / mvDepth (2 x N floats) go back to the host. Bit-exact against oracle_stereo_matches.
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "orb_kernels.cuh"
+
+namespace corb {
+
+constexpr int kThHigh = 100, kThLowS = 50;
+
+// one warp per left keypoint
+__global__ void __launch_bounds__(256) k_stereo_match(OrbGeom g, StereoArgs a) {
+    const int iL = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nl = *a.nl, nr = *a.nr;
+    if (iL >= g.kp_cap) return;
+    if (iL >= nl) {
+        if (lane == 0) { a.u_right[iL] = -1.0f; a.depth[iL] = -1.0f; a.best_dist[iL] = -1; }
+        return;
+    }
+    const corb_keypoint kpL = a.kl[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    const float minZ = a.mb, minD = 0.0f, maxD = __fdiv_rn(a.mbf, minZ);
+    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+    float out_u = -1.0f, out_d = -1.0f;
+    int out_sad = -1;
+    int bestDist = kThHigh, bestIdx = INT_MAX;
+    if (!(maxU < 0) && row >= 0 && row < a.n_rows) {
+        const uint4 l0 = a.dl[2 * iL], l1 = a.dl[2 * iL + 1];
+        for (int iR = lane; iR < nr; iR += 32) {
+            const corb_keypoint kpR = a.kr[iR];
+            const float r = __fmul_rn(2.0f, a.scale[kpR.octave]);
+            const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
+            if (row < minr || row > maxr) continue;                       // vRowIndices[(int)vL] membership (:487-497)
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            if (!(kpR.x >= minU && kpR.x <= maxU)) continue;
+            const uint4 r0 = a.dr[2 * iR], r1 = a.dr[2 * iR + 1];
+            const int d = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) + __popc(l1.x ^ r1.x) +
+                          __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
+            if (d < bestDist) { bestDist = d; bestIdx = iR; }             // ascending iR per lane: first minimum wins
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int od = __shfl_xor_sync(0xffffffffu, bestDist, o), oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
+            if (od < bestDist || (od == bestDist && oi < bestIdx)) { bestDist = od; bestIdx = oi; }
+        }
+        if (bestDist < (kThHigh + kThLowS) / 2) {
+            // ---- sub-pixel refinement on level kpL.octave of both pyramids (:551-626)
+            const float uR0 = a.kr[bestIdx].x;
+            const float sf = a.inv_scale[levelL];
+            const float scaleduL = roundf(__fmul_rn(uL, sf)), scaledvL = roundf(__fmul_rn(vL, sf));
+            const float scaleduR0 = roundf(__fmul_rn(uR0, sf));
+            const LevelGeom L = g.lv[levelL];
+            const float iniu = scaleduR0, endu = __fadd_rn(scaleduR0, 11.0f);   // scaleduR0 + L - w, scaleduR0 + L + w + 1
+            if (!(iniu < 0 || endu >= (float)L.w)) {
+                const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+                const uint8_t* pl = a.pyr_l + L.img_off + (size_t)cv * L.pitch + cu;
+                const uint8_t* pr = a.pyr_r + L.img_off + (size_t)cv * L.pitch + cr;
+                const int cL = pl[0];
+                int av[4], off[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int p = lane + 32 * t;
+                    const int dy = p / 11 - 5, dx = p - (p / 11) * 11 - 5;
+                    off[t] = p < 121 ? dy * L.pitch + dx : INT_MIN;
+                    av[t] = p < 121 ? (int)pl[off[t]] - cL : 0;
+                }
+                int sadBest = INT_MAX, bestinc = 0;
+                float d_prev = 0.f, d_best = 0.f, d_next = 0.f, d_last = 0.f;
+                bool want_next = false;
+#pragma unroll 1
+                for (int inc = -5; inc <= 5; inc++) {
+                    const int cR = pr[inc];
+                    int acc = 0;
+#pragma unroll
+                    for (int t = 0; t < 4; t++)
+                        if (off[t] != INT_MIN) acc += abs(av[t] - ((int)pr[off[t] + inc] - cR));
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    const float dist = (float)acc;   // exact: the SAD of integer-valued floats stays below 2^24
+                    if (want_next) { d_next = dist; want_next = false; }
+                    if (dist < (float)sadBest) {
+                        sadBest = (int)dist; bestinc = inc;
+                        d_prev = d_last; d_best = dist; want_next = true;
+                    }
+                    d_last = dist;
+                }
+                if (bestinc != -5 && bestinc != 5) {
+                    const float deltaR = __fdiv_rn(__fsub_rn(d_prev, d_next),
+                                                   __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d_prev, d_next), __fmul_rn(2.0f, d_best))));
+                    if (!(deltaR < -1 || deltaR > 1)) {
+                        float bestuR = __fmul_rn(a.scale[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= minD && disparity < maxD) {
+                            if (disparity <= 0) {
+                                disparity = (float)0.01;
+                                bestuR = (float)((double)uL - 0.01);
+                            }
+                            out_d = __fdiv_rn(a.mbf, disparity);
+                            out_u = bestuR;
+                            out_sad = sadBest;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { a.u_right[iL] = out_u; a.depth[iL] = out_d; a.best_dist[iL] = out_sad; }
+}
+
+// median of the accepted SADs (element size/2 of the sorted list) and rejection of matches >= 1.5 * 1.4 * median (:630-643)
+__global__ void __launch_bounds__(1024) k_stereo_outliers(OrbGeom g, StereoArgs a) {
+    __shared__ int s_count, s_median;
+    __shared__ int sm[32];
+    const int tid = threadIdx.x;
+    const int nl = *a.nl;
+    int cnt = 0;
+    for (int i = tid; i < nl; i += 1024) cnt += a.best_dist[i] >= 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0) sm[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int c = 0;
+        for (int w = 0; w < 32; w++) c += sm[w];
+        s_count = c;
+        s_median = -1;
+    }
+    __syncthreads();
+    const int n = s_count;
+    if (n == 0) return;
+    const int k = n / 2;
+    for (int i = tid; i < nl; i += 1024) {
+        const int di = a.best_dist[i];
+        if (di < 0) continue;
+        int less = 0, eq = 0;
+        for (int j = 0; j < nl; j++) {
+            const int dj = a.best_dist[j];
+            less += dj >= 0 && dj < di;
+            eq += dj == di;
+        }
+        if (less <= k && k < less + eq) s_median = di;   // all writers store the same value
+    }
+    __syncthreads();
+    const float median = (float)s_median;
+    const float thDist = __fmul_rn(1.5f * 1.4f, median);
+    for (int i = tid; i < nl; i += 1024) {
+        const int di = a.best_dist[i];
+        if (di >= 0 && !((float)di < thDist)) { a.u_right[i] = -1.0f; a.depth[i] = -1.0f; }
+    }
+}
+
+void launch_stereo(const OrbGeom& g, const StereoArgs& a, cudaStream_t s) {
+    k_stereo_match<<<(g.kp_cap * 32 + 255) / 256, 256, 0, s>>>(g, a);
+    k_stereo_outliers<<<1, 1024, 0, s>>>(g, a);
+}
+
+}  // namespace corb

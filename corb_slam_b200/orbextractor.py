@@ -211,3 +211,39 @@ def extract_stereo(ex_left, ex_right, left, right, want_pyramid=False):
 
 def extract_stereo_device(ex_left, ex_right, d_left, d_right, w, h, stride):
     check(lib().corb_orb_extract_pair_device(ex_left._h, ex_right._h, int(d_left), int(d_right), w, h, stride))
+
+
+def compute_stereo_matches(ex_left, ex_right, n_left, mbf, mb):
+    """Frame::ComputeStereoMatches (Frame.cc:470-644) on the last extraction of the two handles -> (mvuRight, mvDepth)."""
+    ur = np.empty(max(n_left, 1), np.float32)
+    dp = np.empty(max(n_left, 1), np.float32)
+    check(lib().corb_stereo_match(ex_left._h, ex_right._h, float(mbf), float(mb), int(n_left), ur.ctypes.data, dp.ctypes.data))
+    return ur[:n_left], dp[:n_left]
+
+
+def frame_stereo(ex_left, ex_right, left, right, mbf, mb):
+    """ExtractORB left + right and ComputeStereoMatches in one call (the stereo Frame constructor, Frame.cc:61-117):
+    -> ((kps_l, desc_l), (kps_r, desc_r), mvuRight, mvDepth)."""
+    if left.shape != right.shape or left.dtype != np.uint8 or right.dtype != np.uint8 or left.ndim != 2:
+        raise TypeError("left/right must be 2-D uint8 arrays of the same shape")
+    if left.strides != right.strides or left.strides[1] != 1:
+        left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
+    h, w = left.shape
+    outs = []
+    for ex in (ex_left, ex_right):
+        if ex._out_shape != (h, w):
+            cap = ex.capacity(w, h)
+            ex._out = (np.empty(cap, KP_DTYPE), np.empty((cap, 32), np.uint8))
+            ex._out_shape = (h, w)
+        ex._shape = (h, w)
+        outs.append(ex._out)
+    if getattr(ex_left, "_stereo_out", None) is None or len(ex_left._stereo_out[0]) != len(outs[0][0]):
+        ex_left._stereo_out = (np.empty(len(outs[0][0]), np.float32), np.empty(len(outs[0][0]), np.float32))
+    ur, dp = ex_left._stereo_out
+    nl, nr = C.c_int32(), C.c_int32()
+    check(lib().corb_frame_stereo(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0], float(mbf),
+                                  float(mb), outs[0][0].ctypes.data, outs[0][1].ctypes.data, C.byref(nl), outs[1][0].ctypes.data,
+                                  outs[1][1].ctypes.data, C.byref(nr), ur.ctypes.data, dp.ctypes.data))
+    cp = (lambda a: a.copy()) if ex_left.copy_outputs else (lambda a: a)
+    return ((cp(outs[0][0][:nl.value]), cp(outs[0][1][:nl.value])), (cp(outs[1][0][:nr.value]), cp(outs[1][1][:nr.value])),
+            cp(ur[:nl.value]), cp(dp[:nl.value]))

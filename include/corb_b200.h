@@ -91,6 +91,17 @@ CORB_API int corb_orb_extract_pair(corb_orb* hl, corb_orb* hr, const uint8_t* im
 CORB_API int corb_orb_extract_pair_device(corb_orb* hl, corb_orb* hr, const uint8_t* d_img_l, const uint8_t* d_img_r, int w,
                                           int hgt, int stride);
 
+/* Frame::ComputeStereoMatches [Frame.cc:470-644] on the results of the last extraction of `left` and `right`, which are
+ * still resident in HBM (keypoints, descriptors and both un-blurred pyramids): u_right[i] = mvuRight[i], depth[i] =
+ * mvDepth[i] for the n_left left keypoints, -1 where there is no match. mbf, mb as in Frame (mbf = baseline * fx, mb = mbf/fx).
+ * Both handles must have completed an extraction of the same image size on the same device. */
+CORB_API int corb_stereo_match(corb_orb* left, corb_orb* right, float mbf, float mb, int n_left, float* u_right, float* depth);
+/* The heavy part of the stereo Frame constructor [Frame.cc:61-117] in one call: ExtractORB left and right, then
+ * ComputeStereoMatches, with nothing but the results crossing PCIe (the pyramids stay on the device). */
+CORB_API int corb_frame_stereo(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride,
+                               float mbf, float mb, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r,
+                               uint8_t* desc_r, int* n_r, float* u_right, float* depth);
+
 /* Device-resident form: `d_img` is already in HBM (pitch `stride`), results stay in HBM for on-GPU consumers
  * (matcher, stereo). Enqueued on the handle's stream; corb_orb_sync() waits for it. */
 CORB_API int corb_orb_extract_device(corb_orb* h, const uint8_t* d_img, int w, int hgt, int stride);

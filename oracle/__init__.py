@@ -60,6 +60,8 @@ def lib():
         L.oracle_orb_blurred.argtypes = [C.c_void_p, C.c_int, _i32p, _i32p]
         L.oracle_orb_candidates.argtypes = [C.c_void_p, C.c_int, C.POINTER(_i32p)]
         L.oracle_orb_level_count.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _u8p, C.c_int, C.c_void_p, _u8p, C.c_int, C.c_float,
+                                            C.c_float, _f32p, _f32p]
         L.oracle_resize_linear_u8.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_int]
         L.oracle_gaussian7_u8.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         L.oracle_fast_score.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
@@ -208,3 +210,14 @@ class OrbExtractor:
 
     def level_count(self, level):
         return lib().oracle_orb_level_count(self._h, level)
+
+
+def stereo_matches(ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, mbf, mb):
+    """Frame::ComputeStereoMatches (Frame.cc:470-644) -> (mvuRight, mvDepth, n_kept); needs both extractors' last pyramids."""
+    kl = np.ascontiguousarray(kps_l); kr = np.ascontiguousarray(kps_r)
+    dl = np.ascontiguousarray(desc_l, np.uint8); dr = np.ascontiguousarray(desc_r, np.uint8)
+    ur = np.empty(len(kl), np.float32); dp = np.empty(len(kl), np.float32)
+    n = lib().oracle_stereo_matches(ex_left._h, ex_right._h, kl.ctypes.data_as(C.c_void_p), _p(dl, _u8p), len(kl),
+                                    kr.ctypes.data_as(C.c_void_p), _p(dr, _u8p), len(kr), float(mbf), float(mb), _p(ur, _f32p),
+                                    _p(dp, _f32p))
+    return ur, dp, n

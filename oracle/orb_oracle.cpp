@@ -521,6 +521,103 @@ int oracle_orb_candidates(const oracle_orb* o, int level, const int32_t** xyr) {
 }
 int oracle_orb_level_count(const oracle_orb* o, int level) { return o->level_count[level]; }
 
+/* Frame::ComputeStereoMatches (corbslam_client/src/Frame.cc:470-644) on the results of the last extraction of the
+ * left and right oracle extractors (keypoints/descriptors passed in, un-blurred pyramids taken from the handles).
+ * u_right / depth: n_left floats, -1 where no match. */
+int oracle_stereo_matches(const oracle_orb* L, const oracle_orb* R, const oracle_keypoint* kl, const uint8_t* dl, int nl,
+                          const oracle_keypoint* kr, const uint8_t* dr, int nr, float mbf, float mb, float* u_right, float* depth) {
+    const int TH_HIGH = 100, TH_LOW = 50;
+    for (int i = 0; i < nl; i++) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const int nRows = L->pyr[0].h;
+    std::vector<std::vector<size_t>> rows(nRows);
+    for (int iR = 0; iR < nr; iR++) {
+        const float kpY = kr[iR].y;
+        const float r = 2.0f * R->scale[kr[iR].octave];
+        const int maxr = (int)std::ceil(kpY + r), minr = (int)std::floor(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++)
+            if (yi >= 0 && yi < nRows) rows[yi].push_back(iR); /* the reference indexes unchecked (always in range for ORB keypoints) */
+    }
+    const float minZ = mb, minD = 0, maxD = mbf / minZ;
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < nl; iL++) {
+        const int levelL = kl[iL].octave;
+        const float vL = kl[iL].y, uL = kl[iL].x;
+        const int row = (int)vL;
+        if (row < 0 || row >= nRows) continue;
+        const std::vector<size_t>& cand = rows[row];
+        if (cand.empty()) continue;
+        const float minU = uL - maxD, maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        size_t bestIdxR = 0;
+        for (size_t iC = 0; iC < cand.size(); iC++) {
+            const size_t iR = cand[iC];
+            if (kr[iR].octave < levelL - 1 || kr[iR].octave > levelL + 1) continue;
+            const float uR = kr[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                const int32_t* pa = (const int32_t*)(dl + (size_t)iL * 32);
+                const int32_t* pb = (const int32_t*)(dr + iR * 32);
+                int dist = 0;
+                for (int k = 0; k < 8; k++) dist += __builtin_popcount((unsigned)(pa[k] ^ pb[k]));
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = kr[bestIdxR].x;
+            const float scaleFactor = L->inv_scale[levelL];
+            const float scaleduL = std::round(uL * scaleFactor), scaledvL = std::round(vL * scaleFactor);
+            const float scaleduR0 = std::round(uR0 * scaleFactor);
+            const int w = 5, Ls = 5;
+            const Image& imL = L->pyr[levelL];
+            const Image& imR = R->pyr[levelL];
+            const int cu = (int)scaleduL, cv = (int)scaledvL, cr = (int)scaleduR0;
+            int best = 2147483647, bestincR = 0;
+            float vDists[11];
+            const float iniu = scaleduR0 + Ls - w, endu = scaleduR0 + Ls + w + 1;
+            if (iniu < 0 || endu >= imR.w) continue;
+            const float cL = imL.px[(size_t)cv * imL.w + cu];
+            for (int incR = -Ls; incR <= Ls; incR++) {
+                const float cR = imR.px[(size_t)cv * imR.w + cr + incR];
+                double acc = 0; /* cv::norm(NORM_L1) of CV_32F accumulates in double */
+                for (int dy = -w; dy <= w; dy++)
+                    for (int dx = -w; dx <= w; dx++) {
+                        const float a = (float)imL.px[(size_t)(cv + dy) * imL.w + cu + dx] - cL;
+                        const float b = (float)imR.px[(size_t)(cv + dy) * imR.w + cr + incR + dx] - cR;
+                        acc += std::fabs(a - b);
+                    }
+                const float dist = (float)acc;
+                if (dist < best) { best = (int)dist; bestincR = incR; }
+                vDists[Ls + incR] = dist;
+            }
+            if (bestincR == -Ls || bestincR == Ls) continue;
+            const float dist1 = vDists[Ls + bestincR - 1], dist2 = vDists[Ls + bestincR], dist3 = vDists[Ls + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = L->scale[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                depth[iL] = mbf / disparity;
+                u_right[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(best, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return 0; /* the reference reads vDistIdx[0] of an empty vector here (undefined) */
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    int kept = (int)vDistIdx.size();
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+        if (vDistIdx[i].first < thDist) break;
+        u_right[vDistIdx[i].second] = -1;
+        depth[vDistIdx[i].second] = -1;
+        kept--;
+    }
+    return kept;
+}
+
 void oracle_resize_linear_u8(const uint8_t* s, int sw, int sh, int ss, uint8_t* d, int dw, int dh, int ds) {
     resize_linear_u8(s, sw, sh, ss, d, dw, dh, ds);
 }

@@ -51,6 +51,10 @@ const uint8_t* oracle_orb_blurred(const oracle_orb*, int level, int* w, int* h);
 int oracle_orb_candidates(const oracle_orb*, int level, const int32_t** xyr);
 int oracle_orb_level_count(const oracle_orb*, int level);
 
+/* Frame::ComputeStereoMatches (Frame.cc:470-644) on the last extraction of the two handles; returns #matches kept */
+int oracle_stereo_matches(const oracle_orb* L, const oracle_orb* R, const oracle_keypoint* kl, const uint8_t* dl, int nl,
+                          const oracle_keypoint* kr, const uint8_t* dr, int nr, float mbf, float mb, float* u_right, float* depth);
+
 /* primitives, exposed for pinning against cv2 */
 void oracle_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
 void oracle_gaussian7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);

@@ -142,3 +142,43 @@ def test_tma_and_fallback_staging_agree(monkeypatch):
     assert k1.tobytes() == k2.tobytes()
     np.testing.assert_array_equal(d1, d2)
     ex2.close()
+
+
+KITTI_BF, KITTI_FX = 386.1448, 718.856
+
+
+@pytest.mark.parametrize("seed,disparity", [(1234, 8), (1270, 23), (1271, 1), (1272, 0)])
+def test_compute_stereo_matches_bit_exact(seed, disparity):
+    from corb_slam_b200 import compute_stereo_matches, extract_stereo, frame_stereo
+    left, right = stereo_frame(seed, disparity=disparity)
+    mbf, mb = KITTI_BF, KITTI_BF / KITTI_FX
+    ol, orr = oracle.OrbExtractor(*PARAMS), oracle.OrbExtractor(*PARAMS)
+    (okl, odl), (okr, odr) = ol(left), orr(right)
+    our, odp, kept = oracle.stereo_matches(ol, orr, okl, odl, okr, odr, mbf, mb)
+    exl, exr = ORBextractor(*PARAMS), ORBextractor(*PARAMS)
+    (kl, dl), (kr, dr) = extract_stereo(exl, exr, left, right)
+    ur, dp = compute_stereo_matches(exl, exr, len(kl), mbf, mb)
+    np.testing.assert_array_equal(ur.view(np.uint32), our.view(np.uint32))
+    np.testing.assert_array_equal(dp.view(np.uint32), odp.view(np.uint32))
+    assert int((ur >= 0).sum()) == kept and (kept > 800 or disparity == 0)
+    # the one-call form (stereo Frame constructor) gives the same
+    (kl2, dl2), (kr2, dr2), ur2, dp2 = frame_stereo(exl, exr, left, right, mbf, mb)
+    assert kl2.tobytes() == okl.tobytes() and kr2.tobytes() == okr.tobytes()
+    np.testing.assert_array_equal(ur2.view(np.uint32), our.view(np.uint32))
+    np.testing.assert_array_equal(dp2.view(np.uint32), odp.view(np.uint32))
+    exl.close(); exr.close()
+
+
+def test_stereo_matches_unrelated_images():
+    from corb_slam_b200 import frame_stereo
+    left, _ = stereo_frame(1280)
+    _, right = stereo_frame(1281)
+    mbf, mb = KITTI_BF, KITTI_BF / KITTI_FX
+    ol, orr = oracle.OrbExtractor(*PARAMS), oracle.OrbExtractor(*PARAMS)
+    (okl, odl), (okr, odr) = ol(left), orr(right)
+    our, odp, kept = oracle.stereo_matches(ol, orr, okl, odl, okr, odr, mbf, mb)
+    exl, exr = ORBextractor(*PARAMS), ORBextractor(*PARAMS)
+    _, _, ur, dp = frame_stereo(exl, exr, left, right, mbf, mb)
+    np.testing.assert_array_equal(ur.view(np.uint32), our.view(np.uint32))
+    np.testing.assert_array_equal(dp.view(np.uint32), odp.view(np.uint32))
+    exl.close(); exr.close()
