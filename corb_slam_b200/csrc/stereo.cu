@@ -18,12 +18,9 @@ __global__ void __launch_bounds__(256) k_stereo_match(OrbGeom g, StereoArgs a) {
     const int iL = (blockIdx.x * 256 + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int nl = *a.nl, nr = *a.nr;
-    if (iL >= g.kp_cap) return;
-    if (iL >= nl) {
-        if (lane == 0) { a.u_right[iL] = -1.0f; a.depth[iL] = -1.0f; a.best_dist[iL] = -1; }
-        return;
-    }
-    const corb_keypoint kpL = a.kl[iL];
+    corb_keypoint kpL;
+    kpL.x = kpL.y = 0.f; kpL.octave = 0;
+    if (iL < nl) kpL = a.kl[iL];
     const int levelL = kpL.octave;
     const float vL = kpL.y, uL = kpL.x;
     const int row = (int)vL;
@@ -32,20 +29,42 @@ __global__ void __launch_bounds__(256) k_stereo_match(OrbGeom g, StereoArgs a) {
     float out_u = -1.0f, out_d = -1.0f;
     int out_sad = -1;
     int bestDist = kThHigh, bestIdx = INT_MAX;
-    if (!(maxU < 0) && row >= 0 && row < a.n_rows) {
-        const uint4 l0 = a.dl[2 * iL], l1 = a.dl[2 * iL + 1];
-        for (int iR = lane; iR < nr; iR += 32) {
-            const corb_keypoint kpR = a.kr[iR];
+    // The 8 left keypoints of this block scan the right keypoints in tiles of 256 staged in shared memory as
+    // (min row, max row, octave, x): the row-table membership test of the reference (:487-497) becomes two compares.
+    __shared__ int4 tile[256];
+    const bool searching = iL < nl && !(maxU < 0) && row >= 0 && row < a.n_rows;
+    uint4 l0 = make_uint4(0, 0, 0, 0), l1 = l0;
+    if (searching) { l0 = a.dl[2 * iL]; l1 = a.dl[2 * iL + 1]; }
+    for (int base = 0; base < nr; base += 256) {
+        __syncthreads();
+        const int jr = base + threadIdx.x;
+        if (jr < nr) {
+            const corb_keypoint kpR = a.kr[jr];
             const float r = __fmul_rn(2.0f, a.scale[kpR.octave]);
-            const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
-            if (row < minr || row > maxr) continue;                       // vRowIndices[(int)vL] membership (:487-497)
-            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
-            if (!(kpR.x >= minU && kpR.x <= maxU)) continue;
+            tile[threadIdx.x] = make_int4((int)floorf(__fsub_rn(kpR.y, r)), (int)ceilf(__fadd_rn(kpR.y, r)), kpR.octave,
+                                          __float_as_int(kpR.x));
+        }
+        __syncthreads();
+        if (!searching) continue;
+        const int cnt = min(256, nr - base);
+        for (int j = lane; j < cnt; j += 32) {
+            const int4 t = tile[j];
+            if (row < t.x || row > t.y) continue;                          // vRowIndices[(int)vL] membership (:487-497)
+            if (t.z < levelL - 1 || t.z > levelL + 1) continue;
+            const float uR = __int_as_float(t.w);
+            if (!(uR >= minU && uR <= maxU)) continue;
+            const int iR = base + j;
             const uint4 r0 = a.dr[2 * iR], r1 = a.dr[2 * iR + 1];
             const int d = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) + __popc(l1.x ^ r1.x) +
                           __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
-            if (d < bestDist) { bestDist = d; bestIdx = iR; }             // ascending iR per lane: first minimum wins
+            if (d < bestDist) { bestDist = d; bestIdx = iR; }              // ascending iR per lane: first minimum wins
         }
+    }
+    if (iL >= nl) {
+        if (lane == 0 && iL < g.kp_cap) { a.u_right[iL] = -1.0f; a.depth[iL] = -1.0f; a.best_dist[iL] = -1; }
+        return;
+    }
+    if (searching) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             const int od = __shfl_xor_sync(0xffffffffu, bestDist, o), oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
@@ -115,41 +134,47 @@ __global__ void __launch_bounds__(256) k_stereo_match(OrbGeom g, StereoArgs a) {
     if (lane == 0) { a.u_right[iL] = out_u; a.depth[iL] = out_d; a.best_dist[iL] = out_sad; }
 }
 
-// median of the accepted SADs (element size/2 of the sorted list) and rejection of matches >= 1.5 * 1.4 * median (:630-643)
+// median of the accepted SADs (element size/2 of the sorted list) and rejection of matches >= 1.5 * 1.4 * median (:630-643).
+// The SAD of an 11x11 u8 patch is < 2^16, so the k-th smallest value is found by a two-pass radix select on shared-
+// memory histograms (high byte, then low byte) instead of sorting.
 __global__ void __launch_bounds__(1024) k_stereo_outliers(OrbGeom g, StereoArgs a) {
-    __shared__ int s_count, s_median;
-    __shared__ int sm[32];
+    __shared__ int hist[256];
+    __shared__ int s_sel[3];  // [0] selected bin, [1] remaining rank, [2] count
     const int tid = threadIdx.x;
     const int nl = *a.nl;
-    int cnt = 0;
-    for (int i = tid; i < nl; i += 1024) cnt += a.best_dist[i] >= 0;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((tid & 31) == 0) sm[tid >> 5] = cnt;
-    __syncthreads();
-    if (tid == 0) {
-        int c = 0;
-        for (int w = 0; w < 32; w++) c += sm[w];
-        s_count = c;
-        s_median = -1;
-    }
-    __syncthreads();
-    const int n = s_count;
-    if (n == 0) return;
-    const int k = n / 2;
-    for (int i = tid; i < nl; i += 1024) {
-        const int di = a.best_dist[i];
-        if (di < 0) continue;
-        int less = 0, eq = 0;
-        for (int j = 0; j < nl; j++) {
-            const int dj = a.best_dist[j];
-            less += dj >= 0 && dj < di;
-            eq += dj == di;
+    int hi_bin = 0, k = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < nl; i += 1024) {
+            const int d = a.best_dist[i];
+            if (d < 0) continue;
+            if (pass == 0) atomicAdd(&hist[(d >> 8) & 255], 1);
+            else if (((d >> 8) & 255) == hi_bin) atomicAdd(&hist[d & 255], 1);
         }
-        if (less <= k && k < less + eq) s_median = di;   // all writers store the same value
+        __syncthreads();
+        if (tid == 0) {
+            if (pass == 0) {
+                int n = 0;
+                for (int b = 0; b < 256; b++) n += hist[b];
+                s_sel[2] = n;
+                k = n / 2;
+            }
+            int cum = 0, sel = 255;
+            for (int b = 0; b < 256; b++) {
+                if (k < cum + hist[b]) { sel = b; break; }
+                cum += hist[b];
+            }
+            s_sel[0] = sel;
+            s_sel[1] = k - cum;
+        }
+        __syncthreads();
+        if (s_sel[2] == 0) return;  // no match at all (the reference would read an empty vector here)
+        if (pass == 0) hi_bin = s_sel[0];
+        k = s_sel[1];
+        __syncthreads();
     }
-    __syncthreads();
-    const float median = (float)s_median;
+    const float median = (float)((hi_bin << 8) | s_sel[0]);
     const float thDist = __fmul_rn(1.5f * 1.4f, median);
     for (int i = tid; i < nl; i += 1024) {
         const int di = a.best_dist[i];
