@@ -135,6 +135,94 @@ def cpu_ba(n_poses, n_points):
             "iterations": info["iterations"], "chi2_final": info["chi2_final"], "rms_px": B.chi2(out)[1]}
 
 
+def matcher_workload(seed=3, n_feat=2000, n_cand=32):
+    """Synthetic matching/BoW workload: a k=10, L=5 vocabulary (111 110 nodes), one query frame of
+    2000 descriptors and `n_cand` candidate keyframes that are noisy re-observations of it."""
+    import oracle
+    from oracle import _match_bind as M
+    oracle.lib()
+    spec = M.random_vocabulary(10, 5, seed)
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (n_feat, 32), dtype=np.uint8)
+    cands = []
+    for c in range(n_cand):
+        d = base[rng.permutation(n_feat)].copy()
+        flips = rng.integers(0, 256, (n_feat, 6))
+        for j in range(6):
+            d[np.arange(n_feat), flips[:, j] >> 3] ^= (1 << (flips[:, j] & 7)).astype(np.uint8)
+        cands.append(d)
+    return spec, base, cands
+
+
+def bench_matcher(device, with_cpu=True):
+    """Calls/s and Hamming pairs/s of SearchByBoW (batched over candidates), descriptors/s of the vocabulary descent,
+    scores/s of the L1 BoW score; each beside the oracle port on one host thread."""
+    import oracle
+    from oracle import _match_bind as M
+    from corb_slam_b200 import BowFeatures, ORBmatcher, ORBVocabulary
+    spec, base, cands = matcher_workload()
+    gvoc = ORBVocabulary.from_arrays(*spec, device=device)
+    ovoc = M.Vocabulary.from_arrays(*spec)
+    levelsup = 3  # L - 3 = level 2 nodes -> 100 groups, like ORBvoc (L = 6, levelsup = 4)
+    n = len(base)
+    rng = np.random.default_rng(0)
+    ang = rng.uniform(0, 360, n).astype(np.float32)
+    valid = (rng.random(n) < 0.7).astype(np.uint8)
+    out = {}
+    # ---- transform (voc->transform, Frame.cc:404)
+    gvoc.transform(base, levelsup)
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        qb = gvoc.transform(base, levelsup)
+    dt = (time.perf_counter() - t0) / reps
+    out["transform"] = {"descriptors_per_s": n / dt, "ms_per_call": dt * 1e3}
+    cb = [gvoc.transform(c, levelsup) for c in cands]
+    # ---- SearchByBoW, batched over candidates (MapFusion.cpp:691 / Tracking.cc:1405)
+    m = ORBmatcher(0.75, True, device=device)
+    A = [BowFeatures(c, b[2], b[3], b[4], valid=valid, angles=ang) for c, b in zip(cands, cb)]
+    B = [BowFeatures(base, qb[2], qb[3], qb[4], angles=ang) for _ in cands]
+    pairs = 0
+    for a_, b_ in zip(cb, [qb] * len(cb)):  # Hamming evaluations = sum over common nodes of nA * nB
+        na = dict(zip(a_[2].tolist(), np.diff(a_[3]).tolist())); nb = dict(zip(b_[2].tolist(), np.diff(b_[3]).tolist()))
+        pairs += sum(na[k] * nb[k] for k in na if k in nb)
+    res = m.SearchByBoWBatch(0, A, B)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = m.SearchByBoWBatch(0, A, B)
+    dt = (time.perf_counter() - t0) / reps
+    out["search_by_bow"] = {"calls_per_s": len(A) / dt, "hamming_pairs_per_s": pairs / dt, "ms_per_batch": dt * 1e3,
+                            "batch": len(A), "matches_per_call": float(np.mean([r[1] for r in res]))}
+    # ---- L1 score, one query against all candidates (KeyFrameDatabase.cc:238)
+    cvecs = [(b[0], b[1]) for b in cb] * 8
+    gvoc.score_batch((qb[0], qb[1]), cvecs)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sc = gvoc.score_batch((qb[0], qb[1]), cvecs)
+    dt = (time.perf_counter() - t0) / reps
+    out["l1_score"] = {"scores_per_s": len(cvecs) / dt, "ms_per_batch": dt * 1e3, "batch": len(cvecs)}
+    if with_cpu:
+        t0 = time.perf_counter(); oq = ovoc.transform(base, levelsup); dt = time.perf_counter() - t0
+        out["transform"]["cpu_descriptors_per_s"] = n / dt
+        oA = [M.Side(c, b[2], b[3], b[4], valid=valid, angles=ang) for c, b in zip(cands, cb)]
+        oB = M.Side(base, qb[2], qb[3], qb[4], angles=ang)
+        t0 = time.perf_counter()
+        for a_ in oA:
+            M.search_by_bow(0, a_, oB, 0.75, True)
+        dt = time.perf_counter() - t0
+        out["search_by_bow"]["cpu_calls_per_s"] = len(oA) / dt
+        out["search_by_bow"]["cpu_hamming_pairs_per_s"] = pairs / dt
+        t0 = time.perf_counter()
+        for c in cvecs:
+            M.bow_score_l1(qb[0], qb[1], c[0], c[1])
+        dt = time.perf_counter() - t0
+        out["l1_score"]["cpu_scores_per_s"] = len(cvecs) / dt
+        out["cpu"] = "oracle port, 1 thread (includes the ctypes call overhead of one call per candidate)"
+    out["workload"] = "k=10 L=5 synthetic vocabulary, 2000 descriptors per frame, 32 candidate keyframes, level-2 node groups"
+    m.close(); gvoc.close()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -337,6 +425,8 @@ def run_ours(args):
                              "stereo_frame_value": cpu_fps_frame},
             "keypoints_per_frame": kp_per_frame,
         }
+        if not args.no_matcher:
+            line["matcher"] = bench_matcher(local)
         if ba_info is not None:
             ba_bytes = ba_algorithmic_bytes(ba_edges, BA_L, BA_P, ba_info["reduced_blocks"]) * ba_info["iterations"]
             ach = ba_bytes / (ba_ms * 1e-3) / 1e9
@@ -372,6 +462,7 @@ def main():
     ap.add_argument("--sample-frames", type=int, default=200, help="stereo frames of the bounded CPU baseline sample")
     ap.add_argument("--no-ba", action="store_true", help="skip the global-BA half of the metric")
     ap.add_argument("--no-cpu-ba", action="store_true", help="skip the CPU BA baseline (about 10 s)")
+    ap.add_argument("--no-matcher", action="store_true", help="skip the SearchByBoW / vocabulary / score section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -432,25 +432,59 @@ __device__ __forceinline__ bool chol6(double* a) {  // in place, lower; upper pa
     return ok;
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_cap) {
+// Warp-cooperative update + Cholesky of one 6x6 diagonal block: lane t < 21 owns entry (r, c), r >= c, of the lower
+// triangle in a register; columns are finalised with shuffles (no local-memory arrays on the sequential critical path).
+// D <- chol(D - L0 L0^T) (L0 == nullptr: no update), result also written to Lout (full 6x6, upper part zero).
+__device__ __forceinline__ bool warp_chol6(double* D, const double* L0, double* Lout, int lane) {
+    int r = 0, c = 0;
+    if (lane < 21) {
+        r = lane >= 15 ? 5 : lane >= 10 ? 4 : lane >= 6 ? 3 : lane >= 3 ? 2 : lane >= 1 ? 1 : 0;
+        c = lane - r * (r + 1) / 2;
+    }
+    double a = lane < 21 ? D[r * 6 + c] : 0.0;
+    if (L0 && lane < 21) {
+        double s = 0;
+#pragma unroll
+        for (int p = 0; p < 6; p++) s += L0[r * 6 + p] * L0[c * 6 + p];
+        a -= s;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        double akk = __shfl_sync(0xffffffffu, a, k * (k + 1) / 2 + k);
+        if (!(akk > 0.0)) { ok = false; akk = 1.0; }
+        const double dk = sqrt(akk), inv = 1.0 / dk;
+        if (lane < 21 && c == k) a = (r == k) ? dk : a * inv;
+        const double lrk = __shfl_sync(0xffffffffu, a, r * (r + 1) / 2 + min(k, r));
+        const double lck = __shfl_sync(0xffffffffu, a, c * (c + 1) / 2 + min(k, c));
+        if (lane < 21 && c > k) a -= lrk * lck;
+    }
+    if (lane < 21) {
+        D[r * 6 + c] = a;
+        Lout[r * 6 + c] = a;
+        if (r != c) { D[c * 6 + r] = 0.0; Lout[c * 6 + r] = 0.0; }
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_cap, int k_begin, int k_end, int n_band, int flags) {
+    // flags: 1 = first launch (load b, clear the failure flag), 2 = defer border x border updates to k_ba_border_syrk,
+    //        4 = run the backward substitution after the last column
     extern __shared__ double Lact[];  // [lact_cap][36] staged L_jk of the active rows of the current column
     __shared__ double Lkk[2][36];
     __shared__ double yk[6];
     __shared__ int s_fail;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = d.Pf;
-    if (tid == 0) s_fail = 0;
-    for (int i = tid; i < n * 6; i += kSolveThreads) d.xp[i] = d.bs[i];
-    if (tid == 0 && n > 0) {
-        double a[36];
-        double* D = d.S + (size_t)(d.rowoff[0] - d.first[0]) * 36;
-#pragma unroll
-        for (int i = 0; i < 36; i++) a[i] = D[i];
-        if (!chol6(a)) s_fail = 1;
-#pragma unroll
-        for (int i = 0; i < 36; i++) { D[i] = a[i]; Lkk[0][i] = a[i]; }
+    if (tid == 0) s_fail = (flags & 1) ? 0 : (d.scalars[4] != 0.0);
+    if (flags & 1)
+        for (int i = tid; i < n * 6; i += kSolveThreads) d.xp[i] = d.bs[i];
+    __syncthreads();
+    if (warp == 0 && k_begin < k_end && !s_fail) {
+        double* D = d.S + (size_t)(d.rowoff[k_begin] + k_begin - d.first[k_begin]) * 36;
+        if (!warp_chol6(D, nullptr, Lkk[k_begin & 1], lane) && lane == 0) s_fail = 1;
     }
     __syncthreads();
-    for (int k = 0; k < n; k++) {
+    for (int k = k_begin; k < k_end; k++) {
         if (s_fail) break;
         const double* Lk = Lkk[k & 1];
         const int cb = d.coloff[k], nact = d.coloff[k + 1] - cb;
@@ -492,26 +526,10 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
         // ---- phase C
         const bool next_active = nact > 0 && rows[0] == k + 1;  // rows ascend, so k+1 can only be the first entry
         if (warp == 0) {
-            if (lane == 0 && k + 1 < n) {
-                double a[36];
+            if (k + 1 < k_end) {
                 double* D = d.S + (size_t)(d.rowoff[k + 1] + (k + 1) - d.first[k + 1]) * 36;
-#pragma unroll
-                for (int i = 0; i < 36; i++) a[i] = D[i];
-                if (next_active) {
-                    const double* L0 = staged ? Lact : d.S + (size_t)(d.rowoff[k + 1] + k - d.first[k + 1]) * 36;
-#pragma unroll
-                    for (int r = 0; r < 6; r++)
-#pragma unroll
-                        for (int c = 0; c < 6; c++) {
-                            double s = 0;
-#pragma unroll
-                            for (int p = 0; p < 6; p++) s += L0[r * 6 + p] * L0[c * 6 + p];
-                            a[r * 6 + c] -= s;
-                        }
-                }
-                if (!chol6(a)) s_fail = 1;
-#pragma unroll
-                for (int i = 0; i < 36; i++) { D[i] = a[i]; Lkk[(k + 1) & 1][i] = a[i]; }
+                const double* L0 = !next_active ? nullptr : staged ? Lact : d.S + (size_t)(d.rowoff[k + 1] + k - d.first[k + 1]) * 36;
+                if (!warp_chol6(D, L0, Lkk[(k + 1) & 1], lane) && lane == 0) s_fail = 1;
             }
         } else if (warp == 1) {  // b_j -= L_jk y_k
             for (int it = lane; it < nact * 6; it += 32) {
@@ -527,6 +545,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
             // pairs (a >= b) of active rows, linear index p = a (a + 1) / 2 + b; pair 0 = (0, 0) is warp 0's when next_active
             const int npairs = nact * (nact + 1) / 2;
             const int p_begin = next_active ? 1 : 0;
+            const bool defer = (flags & 2) != 0;  // pairs of two border rows are applied later by k_ba_border_syrk
             const int r0 = lane / 6, c0 = lane - r0 * 6, c1 = 2 + lane;  // entries `lane` and `32 + lane` (lane < 4)
             constexpr int U = 4;
             for (int base = p_begin + (warp - 2) * U; base < npairs; base += (kSolveWarps - 2) * U) {
@@ -542,6 +561,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
                         while ((a + 1) * (a + 2) / 2 <= p) a++;
                         const int b = p - a * (a + 1) / 2;
                         const int j = rows[a];
+                        if (defer && rows[b] >= n_band) continue;  // rows ascend: b is the smaller row of the pair
                         pa[u] = a;
                         pb[u] = b;
                         toff[u] = (d.rowoff[j] + rows[b] - d.first[j]) * 36;
@@ -576,6 +596,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
         return;
     }
     if (tid == 0) d.scalars[4] = 0.0;
+    if (!(flags & 4)) return;
     // ---- backward: L^T x = y (row oriented); xp already holds y from the fused forward pass
     for (int j = n - 1; j >= 0; j--) {
         const int fj = d.first[j];
@@ -604,6 +625,39 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
         }
         __syncthreads();
     }
+}
+
+// ---- K12b: deferred update of the border block (keyframes with long-range links, ordered last):
+//      S(j, i) -= sum_k L_jk L_ik^T over the band columns k shared by the envelopes of border rows j >= i.
+//      One warp per (j, i) pair; lane = entry of the 6x6 block; fixed k order => deterministic.
+__global__ void __launch_bounds__(256) k_ba_border_syrk(BaDev d, int n_band) {
+    const int nbord = d.Pf - n_band;
+    const int p = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (p >= nbord * (nbord + 1) / 2) return;
+    const int lane = threadIdx.x & 31;
+    int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+    while (a * (a + 1) / 2 > p) a--;
+    while ((a + 1) * (a + 2) / 2 <= p) a++;
+    const int b = p - a * (a + 1) / 2;
+    const int j = n_band + a, i = n_band + b;
+    const int k0 = max(d.first[j], d.first[i]);
+    const double* Lj = d.S + (size_t)(d.rowoff[j] - d.first[j]) * 36;
+    const double* Li = d.S + (size_t)(d.rowoff[i] - d.first[i]) * 36;
+    const int r0 = lane / 6, c0 = lane - r0 * 6, c1 = 2 + lane;
+    double s0 = 0, s1 = 0;
+    for (int k = k0; k < n_band; k++) {
+        const double* A = Lj + (size_t)k * 36;
+        const double* B = Li + (size_t)k * 36;
+#pragma unroll
+        for (int q = 0; q < 6; q++) s0 += A[r0 * 6 + q] * B[c0 * 6 + q];
+        if (lane < 4) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) s1 += A[30 + q] * B[c1 * 6 + q];
+        }
+    }
+    double* T = d.S + (size_t)(d.rowoff[j] + i - d.first[j]) * 36;
+    T[lane] -= s0;
+    if (lane < 4) T[32 + lane] -= s1;
 }
 
 // ---- K13a: xl = Dinv (bl - Hpl^T xp) per landmark
@@ -716,6 +770,7 @@ struct BaHost {
     BaDev d;
     size_t s_doubles = 0;  // S blocks * 36
     int lact_cap = 0;      // active rows of one column that fit the solve kernel's shared memory
+    int n_band = 0;        // free keyframes before the border block (== Pf when there is no border)
     corb_allreduce_fn ar = nullptr;
     void* ar_user = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -806,7 +861,18 @@ struct BaHost {
         if (rc != CORB_OK) return rc;
         if (d.Pf > 0) k_ba_add_lambda<<<(d.Pf * 6 + 255) / 256, 256, 0, stream>>>(d, lambda);
         cudaEventRecord(ev0, stream);
-        k_ba_solve<<<1, kSolveThreads, (size_t)lact_cap * 36 * sizeof(double), stream>>>(d, lact_cap);
+        {   // band columns (border x border updates deferred) -> border SYRK on the whole GPU -> border columns + backward
+            const size_t sm = (size_t)lact_cap * 36 * sizeof(double);
+            const int nbord = d.Pf - n_band;
+            if (nbord > 0) {
+                k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, 0, n_band, n_band, 1 | 2);
+                const int npairs = nbord * (nbord + 1) / 2;
+                k_ba_border_syrk<<<(npairs * 32 + 255) / 256, 256, 0, stream>>>(d, n_band);
+                k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, n_band, d.Pf, n_band, 4);
+            } else {
+                k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, 0, d.Pf, n_band, 1 | 4);
+            }
+        }
         cudaEventRecord(ev1, stream);
         if (d.L > 0) k_ba_backsub<<<(d.L + 255) / 256, 256, 0, stream>>>(d);
         const int nbu = std::max(1, (std::max(d.P, std::min(d.L, 1 << 20)) + 255) / 256);
@@ -929,6 +995,7 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     };
     std::vector<double> firstd, lastd;
     if ((rc = neighbour_range(pfree, firstd, lastd)) != CORB_OK) return rc;
+    H.n_band = Pf;
     {
         const int T = 64;  // links spanning more than T keyframes count as long-range
         std::vector<int> up, down;
@@ -947,6 +1014,7 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             for (int i = 0; i < P; i++) if (pfree[i] >= 0) pfree[i] = newidx[pfree[i]];
             if ((rc = neighbour_range(pfree, firstd, lastd)) != CORB_OK) return rc;
             res->border_poses = (int)border.size();
+            H.n_band = Pf - (int)border.size();
         }
     }
     std::vector<int> first(Pf), rowoff(Pf + 1, 0), coloff(Pf + 1, 0);
