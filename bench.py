@@ -343,6 +343,33 @@ def run_ours(args):
         fr = frame_stereo(exl, exr, npin[i % N_POOL][0], npin[i % N_POOL][1], 386.1448, 386.1448 / 718.856)
         n_stereo += int((fr[2] >= 0).sum())
     e2e_frame_s = time.perf_counter() - t0
+    # ---- several clients sharing one GPU (capacity, not the headline): C threads, each with its own handle pair,
+    #      each running the same host-buffer e2e call; ctypes releases the GIL inside the C ABI
+    multi = None
+    if args.clients_per_gpu > 1:
+        C_ = args.clients_per_gpu
+        pairs = [(ORBextractor(*ORB_PARAMS, device=local), ORBextractor(*ORB_PARAMS, device=local)) for _ in range(C_)]
+        for a_, b_ in pairs:
+            a_.copy_outputs = b_.copy_outputs = False
+            extract_stereo(a_, b_, npin[0][0], npin[0][1])
+        start = threading.Barrier(C_ + 1)
+
+        def client(idx):
+            a_, b_ = pairs[idx]
+            start.wait()
+            for i in range(args.steps):
+                extract_stereo(a_, b_, npin[(i + idx) % N_POOL][0], npin[(i + idx) % N_POOL][1])
+
+        ths = [threading.Thread(target=client, args=(c,)) for c in range(C_)]
+        [t_.start() for t_ in ths]
+        start.wait()
+        t0 = time.perf_counter()
+        [t_.join() for t_ in ths]
+        dt = time.perf_counter() - t0
+        multi = {"clients_per_gpu": C_, "value": C_ * args.steps / dt, "unit": "frames/s",
+                 "note": "aggregate e2e frames/s of %d independent clients (threads) sharing this GPU; not the headline" % C_}
+        for a_, b_ in pairs:
+            a_.close(); b_.close()
     clocks = sampler.stop() if sampler else None
 
     # ---- global BA (second half of the BASELINE.json metric): landmark-sharded over the ranks, reduced camera system
@@ -410,6 +437,7 @@ def run_ours(args):
                                  "d2h_bytes_per_step": d2h + 8 * int(kp_per_frame / 2),
                                  "note": "corb_frame_stereo: ExtractORB left+right and Frame::ComputeStereoMatches on the GPU; "
                                          "the pyramids never leave HBM"},
+            "multi_client": multi,
             "gpu_launches": 2 * exl.launches_per_extract() * args.steps,
             "tma": exl.uses_tma(),
             "clocks": clocks,
@@ -462,6 +490,7 @@ def main():
     ap.add_argument("--sample-frames", type=int, default=200, help="stereo frames of the bounded CPU baseline sample")
     ap.add_argument("--no-ba", action="store_true", help="skip the global-BA half of the metric")
     ap.add_argument("--no-cpu-ba", action="store_true", help="skip the CPU BA baseline (about 10 s)")
+    ap.add_argument("--clients-per-gpu", type=int, default=4, help="extra capacity measurement with this many clients on one GPU (1 = skip)")
     ap.add_argument("--no-matcher", action="store_true", help="skip the SearchByBoW / vocabulary / score section")
     args = ap.parse_args()
     if args.impl == "reference":
