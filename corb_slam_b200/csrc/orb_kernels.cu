@@ -430,7 +430,10 @@ void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
 // (count, address) and splits from the back until the list reaches N; nodes created in one step have addresses
 // in creation order (canonical tie-break), i.e. reverse list position, so its processing order is
 // (count descending, position ascending) and the early stop is the first prefix whose size reaches N.
-constexpr int kOctThreads = 512;
+#ifndef CORB_OCT_THREADS
+#define CORB_OCT_THREADS 512
+#endif
+constexpr int kOctThreads = CORB_OCT_THREADS;
 
 struct OctLayout {
     int cntA, cntB, bndA, bndB, cc, procpos, scan, crank, krank, fresh, candf, warp_tmp, sh, scan64, warp_tmp64, cell_off, keys_xy, keys_node, keys_r, total;
