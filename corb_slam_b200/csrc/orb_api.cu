@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -64,6 +65,20 @@ struct corb_orb {
     uint8_t* d_out = nullptr;
     size_t out_bytes = 0;
     bool pending = false, pending_pyr = false, pending_empty = false;
+    bool own_dirty = false;  // work enqueued on the handle's own stream has not been synchronised yet
+
+    // one graph for a stereo pair (this handle = left): [right frame || left frame] (-> stereo matching) (-> D2H)
+    //   variant 0: results stay in HBM, 1: + D2H of both result blobs, 2: + ComputeStereoMatches + D2H of everything
+    corb_orb* pair_peer = nullptr;
+    long long uid = 0, pair_peer_uid = -1;  // handles are identified by a process-unique id, not by address
+    int pair_peer_serial = -1, pair_self_serial = -1;
+    float pair_mbf = 0.f, pair_mb = 0.f;
+    cudaGraph_t pair_graph[3] = {nullptr, nullptr, nullptr};
+    cudaGraphExec_t pair_exec[3] = {nullptr, nullptr, nullptr};
+    cudaGraphNode_t pair_imp_l[3] = {nullptr, nullptr, nullptr}, pair_imp_r[3] = {nullptr, nullptr, nullptr};
+    int plan_serial = 0;          // bumped whenever the plan (device buffers) is rebuilt
+    cudaEvent_t ev_busy = nullptr; // recorded on the stream that last ran work touching this handle's buffers
+    cudaStream_t busy_stream = nullptr;
 
     // stereo matching outputs (allocated on first use; this handle is the LEFT one)
     float* d_stereo = nullptr;   // [u_right kp_cap | depth kp_cap | best_dist kp_cap (int)]
@@ -73,6 +88,12 @@ struct corb_orb {
 };
 
 static void free_plan(corb_orb* h) {
+    for (int v = 0; v < 3; v++) {
+        if (h->pair_exec[v]) cudaGraphExecDestroy(h->pair_exec[v]), h->pair_exec[v] = nullptr;
+        if (h->pair_graph[v]) cudaGraphDestroy(h->pair_graph[v]), h->pair_graph[v] = nullptr;
+    }
+    h->pair_peer = nullptr;
+    h->plan_serial++;
     for (int v = 0; v < 2; v++) {
         if (h->graph_exec[v]) cudaGraphExecDestroy(h->graph_exec[v]), h->graph_exec[v] = nullptr;
         if (h->graph[v]) cudaGraphDestroy(h->graph[v]), h->graph[v] = nullptr;
@@ -134,11 +155,16 @@ static int dev_alloc(corb_orb* h, T** p, size_t n) {
 }
 
 static int record_graph(corb_orb* h);
+static int settle(corb_orb* h);
 
 static int make_plan(corb_orb* h, int w, int hgt) {
     if (h->plan_w == w && h->plan_h == hgt) return CORB_OK;
     CORB_CUDA(cudaSetDevice(h->device));
-    if (h->stream) CORB_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->stream) {
+        int rc0 = settle(h);  // a peer's pair graph may still be using this handle's buffers
+        if (rc0 != CORB_OK) return rc0;
+        CORB_CUDA(cudaStreamSynchronize(h->stream));
+    }
     free_plan(h);
     OrbGeom& g = h->geom;
     memset(&g, 0, sizeof(g));
@@ -273,47 +299,72 @@ static int make_plan(corb_orb* h, int w, int hgt) {
 //   level l: resize_l -> FAST_l -> quadtree_l          (resize_l also feeds resize_{l+1})
 // joined by orientation + BRIEF; the Gaussian blur (needed only by BRIEF) runs behind the resize chain. The longest
 // pipeline (level 0: 36 % of the cells, the largest quadtree) therefore starts at t = 0 instead of after the chain.
-static int record_graph_variant(corb_orb* h, int variant) {
+// Enqueues the work of one frame of handle `h` into the capture that is active on `stream`. `ls`/`ev` are scratch
+// streams/events (n_levels and 2*n_levels of them) that only shape the captured dependency graph.
+static void capture_frame(corb_orb* h, cudaStream_t stream, bool d2h, std::vector<cudaStream_t>& ls, std::vector<cudaEvent_t>& ev) {
     const OrbGeom& g = h->geom;
     const OrbBuffers& b = h->buf;
     const int L = g.n_levels;
-    std::vector<cudaStream_t> ls(L, nullptr);
-    std::vector<cudaEvent_t> ev(2 * L + 1, nullptr);
-    for (auto& s : ls) CORB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    for (auto& e : ev) CORB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CORB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    launch_import(g, b, h->h_img, g.lv[0].w, h->stream);  // placeholder source, patched before every launch
+    launch_import(g, b, h->h_img, g.lv[0].w, stream);  // placeholder source, patched before every launch
     for (int l = 0; l < L; l++) {
-        if (l > 0) launch_resize(g, b, l, h->stream);
-        cudaEventRecord(ev[l], h->stream);           // level l exists
+        if (l > 0) launch_resize(g, b, l, stream);
+        cudaEventRecord(ev[l], stream);               // level l exists
         cudaStreamWaitEvent(ls[l], ev[l], 0);
         launch_fast_cells(g, b, l, ls[l]);
         launch_octtree(g, b, l, h->key_smem_cap, h->oct_smem, ls[l]);
-        cudaEventRecord(ev[L + l], ls[l]);           // level l distributed
+        cudaEventRecord(ev[L + l], ls[l]);            // level l distributed
     }
-    launch_blur(g, b, h->stream);
-    for (int l = 0; l < L; l++) cudaStreamWaitEvent(h->stream, ev[L + l], 0);
-    launch_orient_desc(g, b, h->stream);
-    if (variant == 1) cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, h->stream);
-    cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph[variant]);
-    for (auto& s : ls) cudaStreamDestroy(s);
-    for (auto& x : ev) cudaEventDestroy(x);
-    CORB_CUDA(e);
-    // find the import kernel node so its source pointer can be patched per launch
+    launch_blur(g, b, stream);
+    for (int l = 0; l < L; l++) cudaStreamWaitEvent(stream, ev[L + l], 0);
+    launch_orient_desc(g, b, stream);
+    if (d2h) cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, stream);
+}
+
+struct CaptureScratch {
+    std::vector<cudaStream_t> ls;
+    std::vector<cudaEvent_t> ev;
+    int init(int n_streams, int n_events) {
+        ls.assign(n_streams, nullptr);
+        ev.assign(n_events, nullptr);
+        for (auto& s : ls) CORB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (auto& e : ev) CORB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return CORB_OK;
+    }
+    ~CaptureScratch() {
+        for (auto& s : ls) if (s) cudaStreamDestroy(s);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+    }
+};
+
+// finds the k_import node(s) of a captured graph; `dst` selects the one writing to that level-0 buffer
+static int find_import_node(cudaGraph_t graph, const uint8_t* dst, cudaGraphNode_t* out) {
     size_t n_nodes = 0;
-    CORB_CUDA(cudaGraphGetNodes(h->graph[variant], nullptr, &n_nodes));
+    CORB_CUDA(cudaGraphGetNodes(graph, nullptr, &n_nodes));
     std::vector<cudaGraphNode_t> nodes(n_nodes);
-    CORB_CUDA(cudaGraphGetNodes(h->graph[variant], nodes.data(), &n_nodes));
-    h->import_node[variant] = nullptr;
+    CORB_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
+    *out = nullptr;
     for (cudaGraphNode_t nd : nodes) {
         cudaGraphNodeType t;
         CORB_CUDA(cudaGraphNodeGetType(nd, &t));
         if (t != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         CORB_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
-        if (kp.func == import_kernel_ptr()) h->import_node[variant] = nd;
+        if (kp.func == import_kernel_ptr() && *reinterpret_cast<uint8_t* const*>(kp.kernelParams[2]) == dst) *out = nd;
     }
-    CORB_CHECK(h->import_node[variant], CORB_ERR_CUDA, "import node not found in the captured graph");
+    CORB_CHECK(*out, CORB_ERR_CUDA, "import node not found in the captured graph");
+    return CORB_OK;
+}
+
+static int record_graph_variant(corb_orb* h, int variant) {
+    const int L = h->geom.n_levels;
+    CaptureScratch sc;
+    int rc = sc.init(L, 2 * L);
+    if (rc != CORB_OK) return rc;
+    CORB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    capture_frame(h, h->stream, variant == 1, sc.ls, sc.ev);
+    CORB_CUDA(cudaStreamEndCapture(h->stream, &h->graph[variant]));
+    rc = find_import_node(h->graph[variant], h->buf.pyr + h->geom.lv[0].img_off, &h->import_node[variant]);
+    if (rc != CORB_OK) return rc;
     CORB_CUDA(cudaGraphInstantiate(&h->graph_exec[variant], h->graph[variant], 0));
     return CORB_OK;
 }
@@ -327,8 +378,7 @@ static int record_graph(corb_orb* h) {
     return CORB_OK;
 }
 
-// Launches the per-frame graph on (src, stride): src is device memory or page-locked host memory (UVA).
-static int launch_frame(corb_orb* h, int variant, const uint8_t* src, int stride) {
+static int patch_import(cudaGraphExec_t exec, cudaGraphNode_t node, corb_orb* h, const uint8_t* src, int stride) {
     const LevelGeom& L0 = h->geom.lv[0];
     uint8_t* dst = h->buf.pyr + L0.img_off;
     int pitch = L0.pitch, w = L0.w, hh = L0.h;
@@ -339,9 +389,159 @@ static int launch_frame(corb_orb* h, int variant, const uint8_t* src, int stride
     kp.blockDim = dim3(256);
     kp.sharedMemBytes = 0;
     kp.kernelParams = args;
-    CORB_CUDA(cudaGraphExecKernelNodeSetParams(h->graph_exec[variant], h->import_node[variant], &kp));
-    CORB_CUDA(cudaGraphLaunch(h->graph_exec[variant], h->stream));
+    CORB_CUDA(cudaGraphExecKernelNodeSetParams(exec, node, &kp));
     return CORB_OK;
+}
+
+// Work that touched this handle's buffers may have been enqueued on a peer's stream (pair graphs run on the left
+// handle's stream): order this handle's own stream behind it before using the buffers again.
+static int settle(corb_orb* h) {
+    if (h->busy_stream && h->busy_stream != h->stream) {
+        CORB_CUDA(cudaEventRecord(h->ev_busy, h->busy_stream));
+        CORB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_busy, 0));
+    }
+    h->busy_stream = nullptr;
+    return CORB_OK;
+}
+
+// Launches the per-frame graph on (src, stride): src is device memory or page-locked host memory (UVA).
+static int launch_frame(corb_orb* h, int variant, const uint8_t* src, int stride) {
+    int rc = settle(h);
+    if (rc != CORB_OK) return rc;
+    rc = patch_import(h->graph_exec[variant], h->import_node[variant], h, src, stride);
+    if (rc != CORB_OK) return rc;
+    CORB_CUDA(cudaGraphLaunch(h->graph_exec[variant], h->stream));
+    h->own_dirty = true;
+    return CORB_OK;
+}
+
+static void fill_stereo_args(corb_orb* left, corb_orb* right, float mbf, float mb, StereoArgs* a) {
+    const OrbGeom& g = left->geom;
+    memset(a, 0, sizeof(*a));
+    a->kl = left->buf.kps; a->kr = right->buf.kps;
+    a->dl = reinterpret_cast<const uint4*>(left->buf.desc); a->dr = reinterpret_cast<const uint4*>(right->buf.desc);
+    a->nl = left->buf.count; a->nr = right->buf.count;
+    a->pyr_l = left->buf.pyr; a->pyr_r = right->buf.pyr;
+    for (int l = 0; l < left->nlevels; l++) { a->scale[l] = left->scale[l]; a->inv_scale[l] = left->inv_scale[l]; }
+    a->mbf = mbf; a->mb = mb;
+    a->u_right = left->d_stereo; a->depth = left->d_stereo + g.kp_cap;
+    a->best_dist = reinterpret_cast<int*>(left->d_stereo + 2 * (size_t)g.kp_cap);
+    a->n_rows = g.lv[0].h;
+}
+
+static int ensure_stereo_buffers(corb_orb* left) {
+    const OrbGeom& g = left->geom;
+    if (left->stereo_cap != g.kp_cap) {
+        int rc = dev_alloc(left, &left->d_stereo, 3 * (size_t)g.kp_cap);
+        if (rc != CORB_OK) return rc;
+        if (left->h_stereo) cudaFreeHost(left->h_stereo), left->h_stereo = nullptr;
+        CORB_CUDA(cudaMallocHost(&left->h_stereo, 2 * (size_t)g.kp_cap * sizeof(float)));
+        left->stereo_cap = g.kp_cap;
+    }
+    return CORB_OK;
+}
+
+static int check_pair(corb_orb* left, corb_orb* right) {
+    CORB_CHECK(left && right && left != right, CORB_ERR_INVALID, "two distinct handles are required");
+    CORB_CHECK(left->plan_w && left->plan_w == right->plan_w && left->plan_h == right->plan_h && left->nlevels == right->nlevels &&
+                   left->device == right->device && left->scale_factor_f == right->scale_factor_f,
+               CORB_ERR_INVALID, "left and right extractor must share device, image size and pyramid parameters");
+    return CORB_OK;
+}
+
+// One graph for both images of a stereo frame, on the left handle's stream (see corb_orb::pair_graph).
+static int ensure_pair_graph(corb_orb* hl, corb_orb* hr, int variant, float mbf, float mb) {
+    int rc = check_pair(hl, hr);
+    if (rc != CORB_OK) return rc;
+    if (hl->pair_peer != hr || hl->pair_peer_uid != hr->uid || hl->pair_peer_serial != hr->plan_serial ||
+        hl->pair_self_serial != hl->plan_serial) {
+        for (int v = 0; v < 3; v++) {
+            if (hl->pair_exec[v]) cudaGraphExecDestroy(hl->pair_exec[v]), hl->pair_exec[v] = nullptr;
+            if (hl->pair_graph[v]) cudaGraphDestroy(hl->pair_graph[v]), hl->pair_graph[v] = nullptr;
+        }
+        hl->pair_peer = hr;
+        hl->pair_peer_uid = hr->uid;
+        hl->pair_peer_serial = hr->plan_serial;
+        hl->pair_self_serial = hl->plan_serial;
+    }
+    if (variant == 2 && hl->pair_exec[2] && (hl->pair_mbf != mbf || hl->pair_mb != mb)) {
+        cudaGraphExecDestroy(hl->pair_exec[2]); hl->pair_exec[2] = nullptr;
+        cudaGraphDestroy(hl->pair_graph[2]); hl->pair_graph[2] = nullptr;
+    }
+    if (hl->pair_exec[variant]) return CORB_OK;
+    const int L = hl->geom.n_levels;
+    if (variant == 2 && (rc = ensure_stereo_buffers(hl)) != CORB_OK) return rc;
+    CaptureScratch sl, sr, sb;
+    if ((rc = sl.init(L, 2 * L)) != CORB_OK || (rc = sr.init(L, 2 * L)) != CORB_OK || (rc = sb.init(1, 2)) != CORB_OK) return rc;
+    CORB_CUDA(cudaStreamBeginCapture(hl->stream, cudaStreamCaptureModeThreadLocal));
+    cudaEventRecord(sb.ev[0], hl->stream);
+    cudaStreamWaitEvent(sb.ls[0], sb.ev[0], 0);
+    capture_frame(hr, sb.ls[0], variant >= 1, sr.ls, sr.ev);
+    capture_frame(hl, hl->stream, variant >= 1, sl.ls, sl.ev);
+    cudaEventRecord(sb.ev[1], sb.ls[0]);
+    cudaStreamWaitEvent(hl->stream, sb.ev[1], 0);
+    if (variant == 2) {
+        StereoArgs a;
+        fill_stereo_args(hl, hr, mbf, mb, &a);
+        launch_stereo(hl->geom, a, hl->stream);
+        cudaMemcpyAsync(hl->h_stereo, hl->d_stereo, 2 * (size_t)hl->geom.kp_cap * sizeof(float), cudaMemcpyDeviceToHost, hl->stream);
+        hl->pair_mbf = mbf;
+        hl->pair_mb = mb;
+    }
+    CORB_CUDA(cudaStreamEndCapture(hl->stream, &hl->pair_graph[variant]));
+    if ((rc = find_import_node(hl->pair_graph[variant], hl->buf.pyr + hl->geom.lv[0].img_off, &hl->pair_imp_l[variant])) != CORB_OK) return rc;
+    if ((rc = find_import_node(hl->pair_graph[variant], hr->buf.pyr + hr->geom.lv[0].img_off, &hl->pair_imp_r[variant])) != CORB_OK) return rc;
+    CORB_CUDA(cudaGraphInstantiate(&hl->pair_exec[variant], hl->pair_graph[variant], 0));
+    return CORB_OK;
+}
+
+// stages a host image for the import kernel: page-locked caller memory is read in place, pageable memory is copied
+static void stage_input(corb_orb* h, const uint8_t* img, int w, int hgt, int stride, const uint8_t** src, int* src_stride) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, img) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    *src = img;
+    *src_stride = stride;
+    if (!pinned) {
+        if (stride == w) memcpy(h->h_img, img, (size_t)w * hgt);
+        else for (int y = 0; y < hgt; y++) memcpy(h->h_img + (size_t)y * w, img + (size_t)y * stride, w);
+        *src = h->h_img;
+        *src_stride = w;
+    }
+}
+
+static int launch_pair(corb_orb* hl, corb_orb* hr, int variant, const uint8_t* src_l, int stride_l, const uint8_t* src_r, int stride_r) {
+    int rc = settle(hl);
+    if (rc != CORB_OK) return rc;
+    if (hr->own_dirty) {  // earlier stand-alone work on the right handle's own stream must finish first
+        CORB_CUDA(cudaEventRecord(hr->ev_busy, hr->stream));
+        CORB_CUDA(cudaStreamWaitEvent(hl->stream, hr->ev_busy, 0));
+        hr->own_dirty = false;
+    }
+    if ((rc = patch_import(hl->pair_exec[variant], hl->pair_imp_l[variant], hl, src_l, stride_l)) != CORB_OK) return rc;
+    if ((rc = patch_import(hl->pair_exec[variant], hl->pair_imp_r[variant], hr, src_r, stride_r)) != CORB_OK) return rc;
+    CORB_CUDA(cudaGraphLaunch(hl->pair_exec[variant], hl->stream));
+    hl->own_dirty = true;
+    hr->busy_stream = hl->stream;
+    return CORB_OK;
+}
+
+static int collect(corb_orb* h, corb_keypoint* kps, uint8_t* desc, int* n) {
+    CORB_CHECK(h->h_scalars[1] == 0, CORB_ERR_CAPACITY, "device-side consistency check %d failed", h->h_scalars[1]);
+    const int cnt = h->h_scalars[0];
+    CORB_CHECK(cnt >= 0 && cnt <= h->geom.kp_cap, CORB_ERR_CAPACITY, "keypoint count %d out of range", cnt);
+    if (n) *n = cnt;
+    if (kps) memcpy(kps, h->h_kps, sizeof(corb_keypoint) * cnt);
+    if (desc) memcpy(desc, h->h_desc, (size_t)cnt * 32);
+    return CORB_OK;
+}
+
+static void copy_pyramid(corb_orb* h, uint8_t* const* pyr_out) {
+    for (int l = 0; l < h->nlevels; l++) {
+        if (!pyr_out[l]) continue;
+        const LevelGeom& L = h->geom.lv[l];
+        for (int y = 0; y < L.h; y++) memcpy(pyr_out[l] + (size_t)y * L.w, h->h_pyr + L.img_off + (size_t)y * L.pitch, L.w);
+    }
 }
 
 extern "C" {
@@ -368,6 +568,10 @@ int corb_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
     CORB_CUDA(cudaGetDeviceCount(&ndev));
     CORB_CHECK(device >= 0 && device < ndev, CORB_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
     corb_orb* h = new corb_orb;
+    {
+        static std::atomic<long long> next_uid{1};
+        h->uid = next_uid.fetch_add(1);
+    }
     h->nfeatures = nfeatures; h->nlevels = nlevels; h->ini_th = ini_th; h->min_th = min_th; h->device = device;
     h->scale_factor_f = scale_factor;
     h->scale_factor = scale_factor;
@@ -407,6 +611,7 @@ int corb_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_busy, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         set_error("CUDA setup on device %d failed: %s", device, cudaGetErrorString(e));
         corb_orb_destroy(h);
@@ -419,9 +624,13 @@ int corb_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
 void corb_orb_destroy(corb_orb* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) {
+        settle(h);
+        cudaStreamSynchronize(h->stream);
+    }
     free_plan(h);
     if (h->ev_peer) cudaEventDestroy(h->ev_peer);
+    if (h->ev_busy) cudaEventDestroy(h->ev_busy);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -470,17 +679,10 @@ int corb_orb_extract_submit(corb_orb* h, const uint8_t* img, int w, int hgt, int
     CORB_CUDA(cudaSetDevice(h->device));
     int rc = make_plan(h, w, hgt);
     if (rc != CORB_OK) return rc;
-    cudaPointerAttributes attr;
-    const bool pinned = cudaPointerGetAttributes(&attr, img) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    if (!pinned) cudaGetLastError();
-    const uint8_t* src = img;
-    int src_stride = stride;
-    if (!pinned) {  // pageable caller memory: stage it; page-locked memory is read in place (keep it valid until _wait)
-        if (stride == w) memcpy(h->h_img, img, (size_t)w * hgt);
-        else for (int y = 0; y < hgt; y++) memcpy(h->h_img + (size_t)y * w, img + (size_t)y * stride, w);
-        src = h->h_img;
-        src_stride = w;
-    }
+
+    const uint8_t* src;
+    int src_stride;
+    stage_input(h, img, w, hgt, stride, &src, &src_stride);
     rc = launch_frame(h, 1, src, src_stride);  // import (PCIe read) -> kernels -> D2H of the result blob, one launch
     if (rc != CORB_OK) return rc;
     if (want_pyramid)
@@ -501,19 +703,12 @@ int corb_orb_extract_wait(corb_orb* h, corb_keypoint* kps, uint8_t* desc, int* n
     }
     CORB_CUDA(cudaSetDevice(h->device));
     CORB_CUDA(cudaStreamSynchronize(h->stream));
-    CORB_CHECK(h->h_scalars[1] == 0, CORB_ERR_CAPACITY, "device-side consistency check %d failed", h->h_scalars[1]);
-    const int cnt = h->h_scalars[0];
-    CORB_CHECK(cnt >= 0 && cnt <= h->geom.kp_cap, CORB_ERR_CAPACITY, "keypoint count %d out of range", cnt);
-    *n = cnt;
-    if (kps) memcpy(kps, h->h_kps, sizeof(corb_keypoint) * cnt);
-    if (desc) memcpy(desc, h->h_desc, (size_t)cnt * 32);
+    h->own_dirty = false;
+    int rc = collect(h, kps, desc, n);
+    if (rc != CORB_OK) return rc;
     if (pyr_out) {
         CORB_CHECK(h->pending_pyr, CORB_ERR_INVALID, "pyramid requested at wait but not at submit");
-        for (int l = 0; l < h->nlevels; l++) {
-            if (!pyr_out[l]) continue;
-            const LevelGeom& L = h->geom.lv[l];
-            for (int y = 0; y < L.h; y++) memcpy(pyr_out[l] + (size_t)y * L.w, h->h_pyr + L.img_off + (size_t)y * L.pitch, L.w);
-        }
+        copy_pyramid(h, pyr_out);
     }
     return CORB_OK;
 }
@@ -526,70 +721,80 @@ int corb_orb_extract(corb_orb* h, const uint8_t* img, int w, int hgt, int stride
 }
 
 // Left and right image of one stereo frame from one thread (the reference starts two threads, Frame.cc:78-81): both
-// graphs are launched back to back, then both results are collected.
+// frames are one CUDA graph on the left handle's stream (two parallel branches), i.e. one driver launch per stereo frame.
+static int pair_prepare(corb_orb* hl, corb_orb* hr, int w, int hgt) {
+    CORB_CHECK(hl && hr && hl != hr, CORB_ERR_INVALID, "two distinct handles are required");
+    CORB_CHECK(!hl->pending && !hr->pending, CORB_ERR_INVALID, "a submitted extraction has not been waited for");
+    CORB_CHECK(hl->device == hr->device, CORB_ERR_INVALID, "left and right handle must live on the same device");
+    CORB_CUDA(cudaSetDevice(hl->device));
+    int rc = make_plan(hl, w, hgt);
+    if (rc != CORB_OK) return rc;
+    return make_plan(hr, w, hgt);
+}
+
 int corb_orb_extract_pair(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride,
                           corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r, uint8_t* desc_r, int* n_r,
                           uint8_t* const* pyr_l, uint8_t* const* pyr_r) {
-    CORB_CHECK(hl && hr && hl != hr, CORB_ERR_INVALID, "two distinct handles are required");
-    int rc = corb_orb_extract_submit(hl, img_l, w, hgt, stride, pyr_l != nullptr);
+    CORB_CHECK(hl && hr && n_l && n_r, CORB_ERR_INVALID, "bad argument");
+    if (!img_l || !img_r || w < 1 || hgt < 1) {  // empty image(s): fall back to the per-handle path (silent return, :1046)
+        int rc = corb_orb_extract(hl, img_l, w, hgt, stride, kps_l, desc_l, n_l, pyr_l);
+        if (rc != CORB_OK) return rc;
+        return corb_orb_extract(hr, img_r, w, hgt, stride, kps_r, desc_r, n_r, pyr_r);
+    }
+    CORB_CHECK(stride >= w, CORB_ERR_INVALID, "stride %d < width %d", stride, w);
+    int rc = pair_prepare(hl, hr, w, hgt);
     if (rc != CORB_OK) return rc;
-    rc = corb_orb_extract_submit(hr, img_r, w, hgt, stride, pyr_r != nullptr);
-    const int rc_l = corb_orb_extract_wait(hl, kps_l, desc_l, n_l, pyr_l);
-    if (rc != CORB_OK) return rc;
-    rc = corb_orb_extract_wait(hr, kps_r, desc_r, n_r, pyr_r);
-    return rc_l != CORB_OK ? rc_l : rc;
+    if ((rc = ensure_pair_graph(hl, hr, 1, 0.f, 0.f)) != CORB_OK) return rc;
+    const uint8_t *sl, *sr;
+    int stl, str_;
+    stage_input(hl, img_l, w, hgt, stride, &sl, &stl);
+    stage_input(hr, img_r, w, hgt, stride, &sr, &str_);
+    if ((rc = launch_pair(hl, hr, 1, sl, stl, sr, str_)) != CORB_OK) return rc;
+    if (pyr_l) CORB_CUDA(cudaMemcpyAsync(hl->h_pyr, hl->buf.pyr, hl->pyr_bytes, cudaMemcpyDeviceToHost, hl->stream));
+    if (pyr_r) CORB_CUDA(cudaMemcpyAsync(hr->h_pyr, hr->buf.pyr, hr->pyr_bytes, cudaMemcpyDeviceToHost, hl->stream));
+    CORB_CUDA(cudaStreamSynchronize(hl->stream));
+    hl->own_dirty = false;
+    hr->busy_stream = nullptr;
+    if ((rc = collect(hl, kps_l, desc_l, n_l)) != CORB_OK) return rc;
+    if ((rc = collect(hr, kps_r, desc_r, n_r)) != CORB_OK) return rc;
+    if (pyr_l) copy_pyramid(hl, pyr_l);
+    if (pyr_r) copy_pyramid(hr, pyr_r);
+    return CORB_OK;
 }
 
 int corb_orb_extract_pair_device(corb_orb* hl, corb_orb* hr, const uint8_t* d_img_l, const uint8_t* d_img_r, int w, int hgt,
                                  int stride) {
-    CORB_CHECK(hl && hr && hl != hr, CORB_ERR_INVALID, "two distinct handles are required");
-    int rc = corb_orb_extract_device(hl, d_img_l, w, hgt, stride);
+    CORB_CHECK(d_img_l && d_img_r && w >= 1 && hgt >= 1 && stride >= w, CORB_ERR_INVALID, "bad argument");
+    int rc = pair_prepare(hl, hr, w, hgt);
     if (rc != CORB_OK) return rc;
-    return corb_orb_extract_device(hr, d_img_r, w, hgt, stride);
+    if ((rc = ensure_pair_graph(hl, hr, 0, 0.f, 0.f)) != CORB_OK) return rc;
+    return launch_pair(hl, hr, 0, d_img_l, stride, d_img_r, stride);
 }
 
 // ---- Frame::ComputeStereoMatches (Frame.cc:470-644) on the resident results of the last extraction of `left`/`right`
-static int enqueue_stereo(corb_orb* left, corb_orb* right, float mbf, float mb) {
-    CORB_CHECK(left && right && left != right, CORB_ERR_INVALID, "two distinct handles are required");
-    CORB_CHECK(left->plan_w && left->plan_w == right->plan_w && left->plan_h == right->plan_h && left->nlevels == right->nlevels &&
-                   left->device == right->device && left->scale_factor_f == right->scale_factor_f,
-               CORB_ERR_INVALID, "left and right extractor must share device, image size and pyramid parameters");
-    CORB_CHECK(mb > 0.f && mbf > 0.f, CORB_ERR_INVALID, "mbf and mb must be positive");
-    CORB_CUDA(cudaSetDevice(left->device));
-    const OrbGeom& g = left->geom;
-    if (left->stereo_cap != g.kp_cap) {
-        int rc = dev_alloc(left, &left->d_stereo, 3 * (size_t)g.kp_cap);
-        if (rc != CORB_OK) return rc;
-        if (left->h_stereo) cudaFreeHost(left->h_stereo), left->h_stereo = nullptr;
-        CORB_CUDA(cudaMallocHost(&left->h_stereo, 2 * (size_t)g.kp_cap * sizeof(float)));
-        left->stereo_cap = g.kp_cap;
-    }
-    if (!left->ev_peer) CORB_CUDA(cudaEventCreateWithFlags(&left->ev_peer, cudaEventDisableTiming));
-    StereoArgs a;
-    memset(&a, 0, sizeof(a));
-    a.kl = left->buf.kps; a.kr = right->buf.kps;
-    a.dl = reinterpret_cast<const uint4*>(left->buf.desc); a.dr = reinterpret_cast<const uint4*>(right->buf.desc);
-    a.nl = left->buf.count; a.nr = right->buf.count;
-    a.pyr_l = left->buf.pyr; a.pyr_r = right->buf.pyr;
-    for (int l = 0; l < left->nlevels; l++) { a.scale[l] = left->scale[l]; a.inv_scale[l] = left->inv_scale[l]; }
-    a.mbf = mbf; a.mb = mb;
-    a.u_right = left->d_stereo; a.depth = left->d_stereo + g.kp_cap;
-    a.best_dist = reinterpret_cast<int*>(left->d_stereo + 2 * (size_t)g.kp_cap);
-    a.n_rows = g.lv[0].h;
-    CORB_CUDA(cudaEventRecord(left->ev_peer, right->stream));   // the right extraction must have finished
-    CORB_CUDA(cudaStreamWaitEvent(left->stream, left->ev_peer, 0));
-    launch_stereo(g, a, left->stream);
-    CORB_CUDA(cudaGetLastError());
-    CORB_CUDA(cudaMemcpyAsync(left->h_stereo, left->d_stereo, 2 * (size_t)g.kp_cap * sizeof(float), cudaMemcpyDeviceToHost, left->stream));
-    return CORB_OK;
-}
-
 int corb_stereo_match(corb_orb* left, corb_orb* right, float mbf, float mb, int n_left, float* u_right, float* depth) {
     CORB_CHECK(u_right && depth && n_left >= 0, CORB_ERR_INVALID, "bad argument");
     CORB_CHECK(left && !left->pending && right && !right->pending, CORB_ERR_INVALID, "wait for the submitted extractions first");
-    int rc = enqueue_stereo(left, right, mbf, mb);
+    CORB_CHECK(mb > 0.f && mbf > 0.f, CORB_ERR_INVALID, "mbf and mb must be positive");
+    int rc = check_pair(left, right);
     if (rc != CORB_OK) return rc;
+    CORB_CUDA(cudaSetDevice(left->device));
+    if ((rc = ensure_stereo_buffers(left)) != CORB_OK) return rc;
+    if ((rc = settle(left)) != CORB_OK) return rc;
+    // the right extraction must have finished: order the left stream behind whatever stream produced it
+    cudaStream_t rs = right->busy_stream ? right->busy_stream : right->stream;
+    if (rs != left->stream) {
+        CORB_CUDA(cudaEventRecord(right->ev_busy, rs));
+        CORB_CUDA(cudaStreamWaitEvent(left->stream, right->ev_busy, 0));
+    }
+    StereoArgs a;
+    fill_stereo_args(left, right, mbf, mb, &a);
+    launch_stereo(left->geom, a, left->stream);
+    CORB_CUDA(cudaGetLastError());
+    CORB_CUDA(cudaMemcpyAsync(left->h_stereo, left->d_stereo, 2 * (size_t)left->geom.kp_cap * sizeof(float), cudaMemcpyDeviceToHost,
+                              left->stream));
     CORB_CUDA(cudaStreamSynchronize(left->stream));
+    left->own_dirty = false;
     CORB_CHECK(n_left <= left->geom.kp_cap, CORB_ERR_INVALID, "n_left exceeds the keypoint capacity");
     memcpy(u_right, left->h_stereo, n_left * sizeof(float));
     memcpy(depth, left->h_stereo + left->geom.kp_cap, n_left * sizeof(float));
@@ -599,19 +804,26 @@ int corb_stereo_match(corb_orb* left, corb_orb* right, float mbf, float mb, int 
 int corb_frame_stereo(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride, float mbf,
                       float mb, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r, uint8_t* desc_r, int* n_r,
                       float* u_right, float* depth) {
-    CORB_CHECK(hl && hr && hl != hr && n_l && u_right && depth, CORB_ERR_INVALID, "bad argument");
-    int rc = corb_orb_extract_submit(hl, img_l, w, hgt, stride, 0);
+    CORB_CHECK(hl && hr && hl != hr && n_l && n_r && u_right && depth, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(mb > 0.f && mbf > 0.f, CORB_ERR_INVALID, "mbf and mb must be positive");
+    if (!img_l || !img_r || w < 1 || hgt < 1) {
+        *n_l = *n_r = 0;
+        return CORB_OK;
+    }
+    CORB_CHECK(stride >= w, CORB_ERR_INVALID, "stride %d < width %d", stride, w);
+    int rc = pair_prepare(hl, hr, w, hgt);
     if (rc != CORB_OK) return rc;
-    rc = corb_orb_extract_submit(hr, img_r, w, hgt, stride, 0);
-    int rc_s = CORB_OK;
-    if (rc == CORB_OK && !hl->pending_empty && !hr->pending_empty) rc_s = enqueue_stereo(hl, hr, mbf, mb);
-    const int rc_l = corb_orb_extract_wait(hl, kps_l, desc_l, n_l, nullptr);   // also completes the stereo kernels (same stream)
-    if (rc != CORB_OK) return rc;
-    rc = corb_orb_extract_wait(hr, kps_r, desc_r, n_r, nullptr);
-    if (rc_l != CORB_OK) return rc_l;
-    if (rc != CORB_OK) return rc;
-    if (rc_s != CORB_OK) return rc_s;
-    if (hl->pending_empty || hr->pending_empty || *n_l == 0) return CORB_OK;
+    if ((rc = ensure_pair_graph(hl, hr, 2, mbf, mb)) != CORB_OK) return rc;  // extraction x2 + stereo matching + D2H, one launch
+    const uint8_t *sl, *sr;
+    int stl, str_;
+    stage_input(hl, img_l, w, hgt, stride, &sl, &stl);
+    stage_input(hr, img_r, w, hgt, stride, &sr, &str_);
+    if ((rc = launch_pair(hl, hr, 2, sl, stl, sr, str_)) != CORB_OK) return rc;
+    CORB_CUDA(cudaStreamSynchronize(hl->stream));
+    hl->own_dirty = false;
+    hr->busy_stream = nullptr;
+    if ((rc = collect(hl, kps_l, desc_l, n_l)) != CORB_OK) return rc;
+    if ((rc = collect(hr, kps_r, desc_r, n_r)) != CORB_OK) return rc;
     memcpy(u_right, hl->h_stereo, *n_l * sizeof(float));
     memcpy(depth, hl->h_stereo + hl->geom.kp_cap, *n_l * sizeof(float));
     return CORB_OK;
@@ -629,7 +841,10 @@ int corb_orb_extract_device(corb_orb* h, const uint8_t* d_img, int w, int hgt, i
 int corb_orb_sync(corb_orb* h) {
     CORB_CHECK(h, CORB_ERR_INVALID, "handle is NULL");
     CORB_CUDA(cudaSetDevice(h->device));
+    int rc = settle(h);
+    if (rc != CORB_OK) return rc;
     CORB_CUDA(cudaStreamSynchronize(h->stream));
+    h->own_dirty = false;
     return CORB_OK;
 }
 
@@ -662,6 +877,10 @@ int corb_orb_profile(corb_orb* h, int reps, float* ms, int cap, int* n) {
     const int nk = profile_launch_count(h);
     CORB_CHECK(cap >= nk, CORB_ERR_INVALID, "need room for %d launches", nk);
     CORB_CUDA(cudaSetDevice(h->device));
+    {
+        int rc = settle(h);
+        if (rc != CORB_OK) return rc;
+    }
     std::vector<cudaEvent_t> ev(nk + 1);
     for (auto& e : ev) CORB_CUDA(cudaEventCreate(&e));
     for (int i = 0; i < nk; i++) ms[i] = 0.f;
@@ -718,6 +937,10 @@ int corb_orb_uses_tma(const corb_orb* h) { return h && h->plan_w ? h->buf.use_tm
 int corb_orb_tap(corb_orb* h, int what, int level, void* out, size_t out_bytes, int* n) {
     CORB_CHECK(h && h->plan_w && level >= 0 && level < h->nlevels, CORB_ERR_INVALID, "bad argument or no plan");
     CORB_CUDA(cudaSetDevice(h->device));
+    {
+        int rc = settle(h);
+        if (rc != CORB_OK) return rc;
+    }
     CORB_CUDA(cudaStreamSynchronize(h->stream));
     const LevelGeom& L = h->geom.lv[level];
     if (what == CORB_TAP_PYRAMID || what == CORB_TAP_BLURRED) {
