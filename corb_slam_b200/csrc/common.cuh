@@ -74,6 +74,58 @@ __device__ __forceinline__ int block_excl_scan(int* data, int n, int* warp_tmp) 
 }
 
 
+// Vectorised variant for the latency-critical single-CTA kernels: int4 accesses (conflict-free), the per-thread values
+// stay in registers, warp totals are combined by every warp itself (__reduce_add_sync), so there are two barriers and
+// no serial chunk loops. `data` must be 16-byte aligned with room for n rounded up to a multiple of 4 (pad entries are
+// read as zero and overwritten); n <= 16 * blockDim.x, else the generic scan above is used. `warp_tmp`: 33 ints.
+__device__ __forceinline__ int block_excl_scan4(int* data, int n, int* warp_tmp) {
+    const int nt = blockDim.x, t = threadIdx.x;
+    const int n4 = (n + 3) >> 2;
+    if (n4 > 4 * nt) return block_excl_scan(data, n, warp_tmp);
+    const int per = (n4 + nt - 1) / nt;  // 1..4 consecutive int4 per thread
+    const int b = t * per;
+    int4 v[4];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v[i] = make_int4(0, 0, 0, 0);
+        if (i < per && b + i < n4) {
+            v[i] = reinterpret_cast<const int4*>(data)[b + i];
+            const int e0 = 4 * (b + i);
+            if (e0 + 1 >= n) v[i].y = 0;
+            if (e0 + 2 >= n) v[i].z = 0;
+            if (e0 + 3 >= n) v[i].w = 0;
+            sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    }
+    const int lane = t & 31, wid = t >> 5, nw = (nt + 31) >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_tmp[wid] = inc;
+    __syncthreads();
+    const int wt = lane < nw ? warp_tmp[lane] : 0;
+    const int total = __reduce_add_sync(0xffffffffu, wt);
+    const int base = __reduce_add_sync(0xffffffffu, lane < wid ? wt : 0);
+    int run = base + inc - sum;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (i < per && b + i < n4) {
+            int4 o4;
+            o4.x = run; run += v[i].x;
+            o4.y = run; run += v[i].y;
+            o4.z = run; run += v[i].z;
+            o4.w = run; run += v[i].w;
+            reinterpret_cast<int4*>(data)[b + i] = o4;
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
 // Same for 64-bit values (two packed 32-bit counters scanned at once). `warp_tmp` must hold 33 long longs.
 __device__ __forceinline__ long long block_excl_scan64(long long* data, int n, long long* warp_tmp) {
     const int nt = blockDim.x, t = threadIdx.x;

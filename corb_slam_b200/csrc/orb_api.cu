@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <vector>
 
@@ -46,6 +47,7 @@ struct corb_orb {
     size_t pyr_bytes = 0;
     int cand_total = 0;
     int key_smem_cap = 0, oct_smem = 0;
+    bool level_graph = false;  // CORB_LEVEL_GRAPH=1: the older per-level pipeline graph (resize chain, per-level FAST/quadtree)
     std::vector<void*> dev_allocs;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -113,6 +115,7 @@ static void free_plan(corb_orb* h) {
 // Geometry of one level; returns false if the reference itself cannot process this size (empty FAST grid, nIni = 0).
 static bool level_geometry(const corb_orb* h, int l, int w, int hgt, LevelGeom* L) {
     memset(L, 0, sizeof(*L));
+    L->level = l;
     L->w = cv_round_f((float)w * h->inv_scale[l]);  // ORBextractor.cc:1111-1112
     L->h = cv_round_f((float)hgt * h->inv_scale[l]);
     L->max_bx = L->w - kEdge + 3;
@@ -240,14 +243,12 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     A(d_beta, beta.size());
     A(b.cell_count, g.n_cells);
     A(b.cand_xy, h->cand_total);
-    A(b.cand_r, h->cand_total);
-    A(b.cell_off, g.n_cells);
-    A(b.key_xy, h->cand_total);
-    A(b.key_r, h->cand_total);
+    A(b.cand_ro, h->cand_total);
     A(b.key_node, h->cand_total);
     A(b.lvl_kp, g.kp_cap);
     A(b.level_count, kMaxLevels);
     A(b.level_cand, kMaxLevels);
+    A(b.level_cand_out, kMaxLevels);
     // [keypoints | descriptors | count, status] in one allocation so one D2H copy returns everything
     h->out_bytes = align_up_sz(sizeof(corb_keypoint) * (size_t)g.kp_cap, 16) + (size_t)g.kp_cap * 32 + 16;
     uint8_t* out_blob;
@@ -258,6 +259,7 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     b.status = b.count + 1;
     h->d_out = out_blob;
 #undef A
+#define A2(ptr, n) if ((rc = dev_alloc(h, &(ptr), (n))) != CORB_OK) return rc
     b.xofs = d_xofs; b.alpha = d_alpha; b.yofs = d_yofs; b.beta = d_beta;
     CORB_CUDA(cudaMemcpy(d_xofs, xofs.data(), xofs.size() * sizeof(int), cudaMemcpyHostToDevice));
     CORB_CUDA(cudaMemcpy(d_alpha, alpha.data(), alpha.size() * sizeof(short2), cudaMemcpyHostToDevice));
@@ -269,10 +271,39 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     CORB_CUDA(cudaMemset(b.count, 0, sizeof(int)));
     CORB_CUDA(cudaMemset(b.level_count, 0, kMaxLevels * sizeof(int)));
     CORB_CUDA(cudaMemset(b.level_cand, 0, kMaxLevels * sizeof(int)));
+    CORB_CUDA(cudaMemset(b.level_cand_out, 0, kMaxLevels * sizeof(int)));
+    {   // quadtree path tables (k_octtree's closed-form path)
+        std::vector<uint16_t> lut;
+        for (int l = 0; l < h->nlevels; l++) {
+            g.lv[l].lut_off = (int)lut.size();
+            lut.resize(lut.size() + oct_lut_entries_host(g.lv[l]) + 2);
+            build_oct_lut(g.lv[l], lut.data() + g.lv[l].lut_off);
+        }
+        uint16_t* d_lut;
+        A2(d_lut, lut.size());
+        CORB_CUDA(cudaMemcpy(d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        b.oct_lut = d_lut;
+    }
 
     memset(&h->tma, 0, sizeof(h->tma));
     b.tma_maps = &h->tma;
     b.use_tma = !getenv("CORB_NO_TMA") && encode_tma_maps(g, b.pyr, &h->tma) ? 1 : 0;
+    b.oct_fast = getenv("CORB_OCT_GENERIC") ? 0 : 1;
+    {
+        CUtensorMap* d_maps;
+        A2(d_maps, kMaxLevels);
+        CORB_CUDA(cudaMemcpy(d_maps, h->tma.m, sizeof(h->tma.m), cudaMemcpyHostToDevice));
+        b.tma_dev = d_maps;
+        std::vector<int> ptab;
+        build_pyr_plan(g, xofs.data(), yofs.data(), &b.pyr_plan, &ptab);
+        int* d_ptab;
+        A2(d_ptab, ptab.size());
+        CORB_CUDA(cudaMemcpy(d_ptab, ptab.data(), ptab.size() * sizeof(int), cudaMemcpyHostToDevice));
+        b.pyr_plan.tab = d_ptab;
+        cudaError_t pe = prepare_pyramid(b.pyr_plan);
+        CORB_CHECK(pe == cudaSuccess, CORB_ERR_CUDA, "pyramid kernel shared memory: %s", cudaGetErrorString(pe));
+    }
+    h->level_graph = getenv("CORB_LEVEL_GRAPH") != nullptr;
     CORB_CUDA(cudaMallocHost(&h->h_img, (size_t)w * hgt));
     CORB_CUDA(cudaMallocHost(&h->h_pyr, h->pyr_bytes));
     CORB_CUDA(cudaMallocHost(&h->h_out, h->out_bytes));
@@ -283,7 +314,7 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     // quadtree: keep a level's keys in shared memory when they fit (typical: 2-3 k keys), else global scratch
     int max_cand_level = 0;
     for (int l = 0; l < h->nlevels; l++) max_cand_level = std::max(max_cand_level, g.lv[l].n_cols * g.lv[l].n_rows * g.lv[l].slot);
-    h->key_smem_cap = std::min(max_cand_level, 12288);
+    h->key_smem_cap = std::min(max_cand_level, 8192);
     cudaError_t e = prepare_octtree(g, h->key_smem_cap, &h->oct_smem);
     if (e != cudaSuccess || h->oct_smem > 200 * 1024) {
         set_error("quadtree kernel needs %d B of shared memory (nfeatures too large?): %s", h->oct_smem, cudaGetErrorString(e));
@@ -301,23 +332,50 @@ static int make_plan(corb_orb* h, int w, int hgt) {
 // pipeline (level 0: 36 % of the cells, the largest quadtree) therefore starts at t = 0 instead of after the chain.
 // Enqueues the work of one frame of handle `h` into the capture that is active on `stream`. `ls`/`ev` are scratch
 // streams/events (n_levels and 2*n_levels of them) that only shape the captured dependency graph.
-static void capture_frame(corb_orb* h, cudaStream_t stream, bool d2h, std::vector<cudaStream_t>& ls, std::vector<cudaEvent_t>& ev) {
+// With `peer` (the right handle of a stereo pair, same geometry) every launch processes both images (grid z = 2).
+static void capture_frame(corb_orb* h, cudaStream_t stream, bool d2h, std::vector<cudaStream_t>& ls, std::vector<cudaEvent_t>& ev,
+                          corb_orb* peer = nullptr) {
     const OrbGeom& g = h->geom;
     const OrbBuffers& b = h->buf;
+    const OrbBuffers* b1 = peer ? &peer->buf : nullptr;
     const int L = g.n_levels;
-    launch_import(g, b, h->h_img, g.lv[0].w, stream);  // placeholder source, patched before every launch
+    // placeholder sources, patched before every launch
+    launch_import(g, b, h->h_img, g.lv[0].w, stream, b1, peer ? peer->h_img : nullptr, g.lv[0].w);
+    if (!h->level_graph) {
+        // import -> pyramid (all levels, one launch) -> FAST (all cells of all levels) -> quadtree (one CTA per level)
+        //                                 \-> blur ----------------------------------------------------/-> orient + BRIEF
+        launch_pyramid(g, b, stream, b1);
+        launch_fast_all(g, b, stream, b1);
+        // the blur (1 524 CTAs) would queue in front of FAST's CTAs if it started with them; behind FAST it fills the
+        // machine while the quadtree occupies 8 SMs
+        cudaEventRecord(ev[0], stream);
+        cudaStreamWaitEvent(ls[0], ev[0], 0);
+        launch_blur(g, b, ls[0], b1);
+        cudaEventRecord(ev[1], ls[0]);
+        launch_octtree(g, b, -1, h->key_smem_cap, h->oct_smem, stream, b1);
+        cudaStreamWaitEvent(stream, ev[1], 0);
+        launch_orient_desc(g, b, stream, b1);
+        if (d2h) {
+            cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, stream);
+            if (peer) cudaMemcpyAsync(peer->h_out, peer->d_out, peer->out_bytes, cudaMemcpyDeviceToHost, stream);
+        }
+        return;
+    }
     for (int l = 0; l < L; l++) {
-        if (l > 0) launch_resize(g, b, l, stream);
+        if (l > 0) launch_resize(g, b, l, stream, b1);
         cudaEventRecord(ev[l], stream);               // level l exists
         cudaStreamWaitEvent(ls[l], ev[l], 0);
-        launch_fast_cells(g, b, l, ls[l]);
-        launch_octtree(g, b, l, h->key_smem_cap, h->oct_smem, ls[l]);
+        launch_fast_cells(g, b, l, ls[l], b1);
+        launch_octtree(g, b, l, h->key_smem_cap, h->oct_smem, ls[l], b1);
         cudaEventRecord(ev[L + l], ls[l]);            // level l distributed
     }
-    launch_blur(g, b, stream);
+    launch_blur(g, b, stream, b1);
     for (int l = 0; l < L; l++) cudaStreamWaitEvent(stream, ev[L + l], 0);
-    launch_orient_desc(g, b, stream);
-    if (d2h) cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, stream);
+    launch_orient_desc(g, b, stream, b1);
+    if (d2h) {
+        cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, stream);
+        if (peer) cudaMemcpyAsync(peer->h_out, peer->d_out, peer->out_bytes, cudaMemcpyDeviceToHost, stream);
+    }
 }
 
 struct CaptureScratch {
@@ -374,18 +432,21 @@ static int record_graph(corb_orb* h) {
         int rc = record_graph_variant(h, v);
         if (rc != CORB_OK) return rc;
     }
-    h->kernel_launches = 1 + (h->geom.n_levels - 1) + 2 * h->geom.n_levels + 2;
+    h->kernel_launches = h->level_graph ? 1 + (h->geom.n_levels - 1) + 2 * h->geom.n_levels + 2 : 6;
     return CORB_OK;
 }
 
-static int patch_import(cudaGraphExec_t exec, cudaGraphNode_t node, corb_orb* h, const uint8_t* src, int stride) {
+static int patch_import(cudaGraphExec_t exec, cudaGraphNode_t node, corb_orb* h, const uint8_t* src, int stride,
+                        corb_orb* peer = nullptr, const uint8_t* src1 = nullptr, int stride1 = 0) {
     const LevelGeom& L0 = h->geom.lv[0];
     uint8_t* dst = h->buf.pyr + L0.img_off;
+    uint8_t* dst1 = peer ? peer->buf.pyr + L0.img_off : nullptr;
     int pitch = L0.pitch, w = L0.w, hh = L0.h;
-    void* args[6] = {(void*)&src, (void*)&stride, (void*)&dst, (void*)&pitch, (void*)&w, (void*)&hh};
+    void* args[9] = {(void*)&src, (void*)&stride, (void*)&dst, (void*)&pitch, (void*)&w, (void*)&hh, (void*)&src1, (void*)&stride1,
+                     (void*)&dst1};
     cudaKernelNodeParams kp = {};
     kp.func = const_cast<void*>(import_kernel_ptr());
-    kp.gridDim = dim3((L0.w + 1023) / 1024, L0.h);
+    kp.gridDim = dim3((L0.w + 1023) / 1024, L0.h, peer ? 2 : 1);
     kp.blockDim = dim3(256);
     kp.sharedMemBytes = 0;
     kp.kernelParams = args;
@@ -444,8 +505,9 @@ static int ensure_stereo_buffers(corb_orb* left) {
 static int check_pair(corb_orb* left, corb_orb* right) {
     CORB_CHECK(left && right && left != right, CORB_ERR_INVALID, "two distinct handles are required");
     CORB_CHECK(left->plan_w && left->plan_w == right->plan_w && left->plan_h == right->plan_h && left->nlevels == right->nlevels &&
-                   left->device == right->device && left->scale_factor_f == right->scale_factor_f,
-               CORB_ERR_INVALID, "left and right extractor must share device, image size and pyramid parameters");
+                   left->device == right->device && left->scale_factor_f == right->scale_factor_f &&
+                   left->nfeatures == right->nfeatures && left->ini_th == right->ini_th && left->min_th == right->min_th,
+               CORB_ERR_INVALID, "left and right extractor must share device, image size and ORB parameters (Tracking.cc:118-121)");
     return CORB_OK;
 }
 
@@ -471,15 +533,10 @@ static int ensure_pair_graph(corb_orb* hl, corb_orb* hr, int variant, float mbf,
     if (hl->pair_exec[variant]) return CORB_OK;
     const int L = hl->geom.n_levels;
     if (variant == 2 && (rc = ensure_stereo_buffers(hl)) != CORB_OK) return rc;
-    CaptureScratch sl, sr, sb;
-    if ((rc = sl.init(L, 2 * L)) != CORB_OK || (rc = sr.init(L, 2 * L)) != CORB_OK || (rc = sb.init(1, 2)) != CORB_OK) return rc;
+    CaptureScratch sl;
+    if ((rc = sl.init(L, 2 * L)) != CORB_OK) return rc;
     CORB_CUDA(cudaStreamBeginCapture(hl->stream, cudaStreamCaptureModeThreadLocal));
-    cudaEventRecord(sb.ev[0], hl->stream);
-    cudaStreamWaitEvent(sb.ls[0], sb.ev[0], 0);
-    capture_frame(hr, sb.ls[0], variant >= 1, sr.ls, sr.ev);
-    capture_frame(hl, hl->stream, variant >= 1, sl.ls, sl.ev);
-    cudaEventRecord(sb.ev[1], sb.ls[0]);
-    cudaStreamWaitEvent(hl->stream, sb.ev[1], 0);
+    capture_frame(hl, hl->stream, variant >= 1, sl.ls, sl.ev, hr);  // both images in every launch (grid z = 2)
     if (variant == 2) {
         StereoArgs a;
         fill_stereo_args(hl, hr, mbf, mb, &a);
@@ -490,7 +547,6 @@ static int ensure_pair_graph(corb_orb* hl, corb_orb* hr, int variant, float mbf,
     }
     CORB_CUDA(cudaStreamEndCapture(hl->stream, &hl->pair_graph[variant]));
     if ((rc = find_import_node(hl->pair_graph[variant], hl->buf.pyr + hl->geom.lv[0].img_off, &hl->pair_imp_l[variant])) != CORB_OK) return rc;
-    if ((rc = find_import_node(hl->pair_graph[variant], hr->buf.pyr + hr->geom.lv[0].img_off, &hl->pair_imp_r[variant])) != CORB_OK) return rc;
     CORB_CUDA(cudaGraphInstantiate(&hl->pair_exec[variant], hl->pair_graph[variant], 0));
     return CORB_OK;
 }
@@ -518,8 +574,7 @@ static int launch_pair(corb_orb* hl, corb_orb* hr, int variant, const uint8_t* s
         CORB_CUDA(cudaStreamWaitEvent(hl->stream, hr->ev_busy, 0));
         hr->own_dirty = false;
     }
-    if ((rc = patch_import(hl->pair_exec[variant], hl->pair_imp_l[variant], hl, src_l, stride_l)) != CORB_OK) return rc;
-    if ((rc = patch_import(hl->pair_exec[variant], hl->pair_imp_r[variant], hr, src_r, stride_r)) != CORB_OK) return rc;
+    if ((rc = patch_import(hl->pair_exec[variant], hl->pair_imp_l[variant], hl, src_l, stride_l, hr, src_r, stride_r)) != CORB_OK) return rc;
     CORB_CUDA(cudaGraphLaunch(hl->pair_exec[variant], hl->stream));
     hl->own_dirty = true;
     hr->busy_stream = hl->stream;
@@ -957,26 +1012,27 @@ int corb_orb_tap(corb_orb* h, int what, int level, void* out, size_t out_bytes, 
     }
     if (what == CORB_TAP_CANDIDATES) {
         CORB_CHECK(n, CORB_ERR_INVALID, "n is NULL");
-        const int n_cell = L.n_cols * L.n_rows;
-        std::vector<int> cc(n_cell);
-        CORB_CUDA(cudaMemcpy(cc.data(), h->buf.cell_count + L.cell_base, n_cell * sizeof(int), cudaMemcpyDeviceToHost));
-        std::vector<uint32_t> xy((size_t)n_cell * L.slot);
-        std::vector<uint8_t> r((size_t)n_cell * L.slot);
-        CORB_CUDA(cudaMemcpy(xy.data(), h->buf.cand_xy + L.cand_base, xy.size() * 4, cudaMemcpyDeviceToHost));
-        CORB_CUDA(cudaMemcpy(r.data(), h->buf.cand_r + L.cand_base, r.size(), cudaMemcpyDeviceToHost));
+        // the level's list holds the corners in arrival order; the order key restores the reference order
         int total = 0;
-        for (int c = 0; c < n_cell; c++) total += cc[c];
+        CORB_CUDA(cudaMemcpy(&total, h->buf.level_cand_out + level, sizeof(int), cudaMemcpyDeviceToHost));
+        CORB_CHECK(total >= 0 && total <= L.n_cols * L.n_rows * L.slot, CORB_ERR_CAPACITY, "candidate count %d out of range", total);
         *n = total;
         if (!out) return CORB_OK;
         CORB_CHECK(out_bytes >= (size_t)total * 12, CORB_ERR_INVALID, "output buffer too small for %d candidates", total);
+        std::vector<uint32_t> xy(total), ro(total);
+        if (total) {
+            CORB_CUDA(cudaMemcpy(xy.data(), h->buf.cand_xy + L.cand_base, (size_t)total * 4, cudaMemcpyDeviceToHost));
+            CORB_CUDA(cudaMemcpy(ro.data(), h->buf.cand_ro + L.cand_base, (size_t)total * 4, cudaMemcpyDeviceToHost));
+        }
+        std::vector<int> idx(total);
+        for (int i = 0; i < total; i++) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](int a_, int b_) { return (ro[a_] & 0xffffffu) > (ro[b_] & 0xffffffu); });
         int32_t* o = (int32_t*)out;
-        for (int c = 0; c < n_cell; c++)
-            for (int e = 0; e < cc[c]; e++) {
-                const uint32_t v = xy[(size_t)c * L.slot + e];
-                *o++ = v & 0xffff;
-                *o++ = v >> 16;
-                *o++ = r[(size_t)c * L.slot + e];
-            }
+        for (int i : idx) {
+            *o++ = xy[i] & 0xffff;
+            *o++ = xy[i] >> 16;
+            *o++ = ro[i] >> 24;
+        }
         return CORB_OK;
     }
     set_error("unknown tap %d", what);

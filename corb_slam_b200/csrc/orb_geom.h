@@ -12,6 +12,7 @@ constexpr int kPatch = 31;       // PATCH_SIZE      (:72)
 constexpr int kCellRoiMax = 66;  // wCell + 6 < 60 + 6 (W = 30 => wCell = ceil(width / floor(width/30)) < 60)
 
 struct LevelGeom {
+    int level;               // index of this level
     int w, h, pitch;         // level size, bytes per row (multiple of 128)
     int img_off;             // byte offset of the level inside the pyramid / blurred buffers
     int max_bx, max_by;      // maxBorderX/Y = w-16, h-16
@@ -23,6 +24,7 @@ struct LevelGeom {
     int n_ini;               // initial quadtree nodes
     float h_x;               // (float)width / n_ini
     int node_cap;            // max(quota + 3, 4 * n_ini)
+    int lut_off;             // quadtree path tables of this level inside OrbBuffers::oct_lut: xs[w - 32] then ys[h - 32]
     int kp_base;             // first per-level keypoint slot (= sum of node_cap of lower levels)
     int xtab_off, ytab_off;  // offsets into the resize tables (level >= 1)
     int blur_tile_base;      // first tile of this level in the blur launch

@@ -12,6 +12,54 @@
 
 namespace corb {
 
+// Debug build only (make EXTRA=-DCORB_TIMELINE): every block stamps %globaltimer on entry/exit into a per-kernel
+// (min start, max end) table, so tools/timeline.py can draw the concurrency of the per-frame graph without nsys.
+#ifdef CORB_TIMELINE
+__device__ unsigned long long g_tl[2][64];
+struct TlScope {
+    int id;
+    __device__ __forceinline__ static unsigned long long now() {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        return t;
+    }
+    __device__ __forceinline__ TlScope(int i) : id(i) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) atomicMin(&g_tl[0][id], now());
+    }
+    __device__ __forceinline__ ~TlScope() {
+        if (threadIdx.x == 0 && threadIdx.y == 0) atomicMax(&g_tl[1][id], now());
+    }
+};
+#define TL_SCOPE(id) TlScope tl_scope_(id)
+}  // namespace corb
+extern "C" __attribute__((visibility("default"))) int corb_debug_timeline(unsigned long long* out128, int reset) {
+    if (out128 && cudaMemcpyFromSymbol(out128, corb::g_tl, sizeof(corb::g_tl)) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long init[2][64];
+        for (int i = 0; i < 64; i++) { init[0][i] = ~0ull; init[1][i] = 0; }
+        if (cudaMemcpyToSymbol(corb::g_tl, init, sizeof(init)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+namespace corb {
+#else
+#define TL_SCOPE(id) do { } while (0)
+#endif
+
+#ifdef CORB_OCT_TRACE
+#define TR_DECL long long tr_[16]; int trn_ = 0
+#define TR() do { if (threadIdx.x == 0 && threadIdx.y == 0 && trn_ < 16) tr_[trn_++] = clock64(); } while (0)
+#define TR_PRINT(name, cond) do { if (threadIdx.x == 0 && threadIdx.y == 0 && blockIdx.z == 0 && (cond)) { \
+        for (int i_ = trn_; i_ < 16; i_++) tr_[i_] = tr_[trn_ - 1]; \
+        printf("%s blk %d n=%d: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld total %lld\n", name, (int)blockIdx.x, trn_, \
+               tr_[1] - tr_[0], tr_[2] - tr_[1], tr_[3] - tr_[2], tr_[4] - tr_[3], tr_[5] - tr_[4], tr_[6] - tr_[5], tr_[7] - tr_[6], \
+               tr_[8] - tr_[7], tr_[9] - tr_[8], tr_[10] - tr_[9], tr_[11] - tr_[10], tr_[12] - tr_[11], tr_[trn_ - 1] - tr_[0]); } } while (0)
+#else
+#define TR_DECL do { } while (0)
+#define TR() do { } while (0)
+#define TR_PRINT(name, cond) do { } while (0)
+#endif
+
 __device__ __align__(16) const int8_t d_pattern[1024] = {
 #include "../../include/corb_brief_pattern.inc"
 };
@@ -23,7 +71,10 @@ __device__ const int d_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 1
 // level 0 of the pitched pyramid. First node of the per-frame graph, so one cudaGraphLaunch is the only driver call
 // an extraction needs; its (src, stride) arguments are patched per launch with cudaGraphExecKernelNodeSetParams.
 __global__ void __launch_bounds__(256) k_import(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ dst, int pitch,
-                                                int w, int h) {
+                                                int w, int h, const uint8_t* __restrict__ src1, int stride1,
+                                                uint8_t* __restrict__ dst1) {
+    TL_SCOPE(0);
+    if (blockIdx.z) { src = src1; stride = stride1; dst = dst1; }  // second image of a stereo pair
     const int y = blockIdx.y;
     const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
     if (x0 >= w) return;
@@ -40,10 +91,12 @@ __global__ void __launch_bounds__(256) k_import(const uint8_t* __restrict__ src,
     *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + x0) = v;  // pitch % 128 == 0 and pitch >= w rounded up to 4
 }
 
-void launch_import(const OrbGeom& g, const OrbBuffers& b, const uint8_t* src, int stride, cudaStream_t s) {
+void launch_import(const OrbGeom& g, const OrbBuffers& b, const uint8_t* src, int stride, cudaStream_t s, const OrbBuffers* b1,
+                   const uint8_t* src1, int stride1) {
     const LevelGeom& L0 = g.lv[0];
-    dim3 grid((L0.w + 1023) / 1024, L0.h);
-    k_import<<<grid, 256, 0, s>>>(src, stride, b.pyr + L0.img_off, L0.pitch, L0.w, L0.h);
+    dim3 grid((L0.w + 1023) / 1024, L0.h, b1 ? 2 : 1);
+    k_import<<<grid, 256, 0, s>>>(src, stride, b.pyr + L0.img_off, L0.pitch, L0.w, L0.h, src1, stride1,
+                                  b1 ? b1->pyr + L0.img_off : nullptr);
 }
 const void* import_kernel_ptr() { return (const void*)k_import; }
 
@@ -53,7 +106,10 @@ const void* import_kernel_ptr() { return (const void*)k_import; }
 __global__ void __launch_bounds__(256) k_resize(LevelGeom src, LevelGeom dst, const uint8_t* __restrict__ pyr_src,
                                                 uint8_t* __restrict__ pyr_dst, const int* __restrict__ xofs,
                                                 const short2* __restrict__ alpha, const int* __restrict__ yofs,
-                                                const short2* __restrict__ beta) {
+                                                const short2* __restrict__ beta, const uint8_t* __restrict__ pyr_src1,
+                                                uint8_t* __restrict__ pyr_dst1) {
+    TL_SCOPE(dst.level);
+    if (blockIdx.z) { pyr_src = pyr_src1; pyr_dst = pyr_dst1; }
     const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int dy = blockIdx.y * 8 + threadIdx.y;
     if (dy >= dst.h || dx0 >= dst.w) return;
@@ -79,12 +135,189 @@ __global__ void __launch_bounds__(256) k_resize(LevelGeom src, LevelGeom dst, co
     *reinterpret_cast<uint32_t*>(pyr_dst + (size_t)dy * dst.pitch + dx0) = packed;  // pitch % 128 == 0, dx0 % 4 == 0
 }
 
-void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s) {
+void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s, const OrbBuffers* b1) {
     const LevelGeom& src = g.lv[level - 1];
     const LevelGeom& dst = g.lv[level];
-    dim3 block(32, 8), grid((dst.w + 127) / 128, (dst.h + 7) / 8);
+    dim3 block(32, 8), grid((dst.w + 127) / 128, (dst.h + 7) / 8, b1 ? 2 : 1);
     k_resize<<<grid, block, 0, s>>>(src, dst, b.pyr + src.img_off, b.pyr + dst.img_off, b.xofs + dst.xtab_off,
-                                    b.alpha + dst.xtab_off, b.yofs + dst.ytab_off, b.beta + dst.ytab_off);
+                                    b.alpha + dst.xtab_off, b.yofs + dst.ytab_off, b.beta + dst.ytab_off,
+                                    b1 ? b1->pyr + src.img_off : nullptr, b1 ? b1->pyr + dst.img_off : nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ K1' fused pyramid
+// ComputePyramid (ORBextractor.cc:1107-1132) in ONE launch. Level l is a resize of level l-1, so a chain of per-level
+// launches is serial (7 dependent kernels, ~30 us of launch + drain latency for 1 MB of pixels). Here a CTA takes one
+// tile of level 0, and produces the pixels it owns on EVERY level, level after level in shared memory: the resize
+// arithmetic is the one of k_resize (bit-exact), pixels in the halo between tiles are computed redundantly.
+constexpr int kPyrTW = 64, kPyrTH = 32;
+
+void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, PyrPlan* plan, std::vector<int>* tab) {
+    const int L = g.n_levels;
+    PyrPlan& p = *plan;
+    p.tw = kPyrTW; p.th = kPyrTH;
+    p.ntx = (g.lv[0].w + p.tw - 1) / p.tw;
+    p.nty = (g.lv[0].h + p.th - 1) / p.th;
+    tab->clear();
+    int max_w[kMaxLevels] = {0}, max_h[kMaxLevels] = {0};
+    for (int axis = 0; axis < 2; axis++) {
+        const int nt = axis == 0 ? p.ntx : p.nty, tile = axis == 0 ? p.tw : p.th;
+        auto size_of = [&](int l) { return axis == 0 ? g.lv[l].w : g.lv[l].h; };
+        auto ofs = [&](int l, int d) {  // left/top source pixel of level-l pixel d in level l-1 (clamped like k_resize)
+            const int v = axis == 0 ? xofs[g.lv[l].xtab_off + d] : yofs[g.lv[l].ytab_off + d];
+            return std::min(std::max(v, 0), size_of(l - 1) - 1);
+        };
+        // f[l][d]: where the chain of left/top sources of level-l pixel d ends in level 0
+        std::vector<std::vector<int>> f(L), own(L), n0(L), n1(L);
+        for (int l = 0; l < L; l++) {
+            f[l].resize(size_of(l));
+            for (int d = 0; d < size_of(l); d++) f[l][d] = l == 0 ? d : f[l - 1][ofs(l, d)];
+            own[l].assign(nt + 1, size_of(l));
+            for (int t = nt - 1; t >= 0; t--) {
+                int d = own[l][t + 1];
+                while (d > 0 && f[l][d - 1] >= t * tile) d--;
+                own[l][t] = d;
+            }
+            own[l][0] = 0;
+            n0[l].assign(nt, 1);
+            n1[l].assign(nt, 0);
+        }
+        for (int t = 0; t < nt; t++) {
+            for (int l = L - 1; l >= 0; l--) {
+                int a = own[l][t], b2 = own[l][t + 1] - 1;  // owned, inclusive (empty if a > b2)
+                if (l + 1 < L && n0[l + 1][t] <= n1[l + 1][t]) {
+                    const int sa = ofs(l + 1, n0[l + 1][t]), sb = std::min(ofs(l + 1, n1[l + 1][t]) + 1, size_of(l) - 1);
+                    if (a > b2) { a = sa; b2 = sb; }
+                    else { a = std::min(a, sa); b2 = std::max(b2, sb); }
+                }
+                n0[l][t] = a; n1[l][t] = b2;
+                if (a <= b2) {
+                    int& m = axis == 0 ? max_w[l] : max_h[l];
+                    m = std::max(m, b2 - a + 1);
+                }
+            }
+        }
+        for (int l = 0; l < L; l++) {
+            (axis == 0 ? p.xoff[l] : p.yoff[l]) = (int)tab->size();
+            tab->insert(tab->end(), own[l].begin(), own[l].end());
+            tab->insert(tab->end(), n0[l].begin(), n0[l].end());
+            tab->insert(tab->end(), n1[l].begin(), n1[l].end());
+        }
+    }
+    int buf = 0, tabs = 0;
+    for (int l = 0; l < L; l++) {
+        buf = std::max(buf, ((max_w[l] + 3 + 3) & ~3) * max_h[l]);  // level 0 is stored from a 4-aligned column
+        if (l > 0) tabs += 2 * (max_w[l] + max_h[l]);
+    }
+    p.buf_bytes = (buf + 15) & ~15;
+    p.tab_smem_ints = tabs;
+}
+
+__global__ void __launch_bounds__(256) k_pyramid(OrbGeom g, PyrPlan p, uint8_t* __restrict__ pyr, const int* __restrict__ xofs,
+                                                 const short2* __restrict__ alpha, const int* __restrict__ yofs,
+                                                 const short2* __restrict__ beta, uint8_t* __restrict__ pyr1) {
+    extern __shared__ __align__(16) uint8_t psm[];
+    if (blockIdx.z) pyr = pyr1;
+    TL_SCOPE(1);
+    TR_DECL; TR();
+    uint8_t* cur = psm;
+    uint8_t* nxt = psm + p.buf_bytes;
+    int* stab = reinterpret_cast<int*>(psm + 2 * p.buf_bytes);
+    __shared__ int rng[kMaxLevels][8];  // per level: x own0, own1, need0, need1, y own0, own1, need0, need1
+    __shared__ int toff[kMaxLevels];    // start of level l's staged table slice in stab
+    const int tid = threadIdx.x, tx = blockIdx.x, ty = blockIdx.y;
+    const int L = g.n_levels;
+    if (tid < L * 8) {
+        const int l = tid >> 3, k = tid & 7, axis = k >> 2, kk = k & 3;
+        const int nt = axis ? p.nty : p.ntx, t = axis ? ty : tx;
+        const int* sec = p.tab + (axis ? p.yoff[l] : p.xoff[l]);
+        rng[l][k] = kk == 0 ? sec[t] : kk == 1 ? sec[t + 1] : kk == 2 ? sec[nt + 1 + t] : sec[2 * nt + 1 + t];
+    }
+    __syncthreads();
+    TR();
+    // level 0 (4-byte words of the needed region of the 128-byte pitched level-0 image) and the slices of the resize
+    // tables this tile needs on every level are fetched in the same phase: one round of global latency for both
+    const LevelGeom L0 = g.lv[0];
+    int pw;  // pitch of `cur`
+    int px0 = rng[0][2] & ~3, py0 = rng[0][6];  // origin of `cur` in level coordinates
+    {
+        const int nh = rng[0][7] - py0 + 1;
+        const int nwords = ((rng[0][3] - px0) >> 2) + 1;
+        pw = nwords * 4;
+        const uint8_t* s0 = pyr + L0.img_off + (size_t)py0 * L0.pitch + px0;
+        const int lanes = tid & 31, rows = tid >> 5;
+        for (int yy = rows; yy < nh; yy += 8)
+            for (int xx = lanes; xx < nwords; xx += 32)
+                reinterpret_cast<uint32_t*>(cur)[yy * nwords + xx] = *reinterpret_cast<const uint32_t*>(s0 + (size_t)yy * L0.pitch + 4 * xx);
+    }
+    {
+        int o = 0;
+        for (int l = 1; l < L; l++) {
+            const LevelGeom& D = g.lv[l];
+            const int x0 = rng[l][2], nw = rng[l][3] - x0 + 1, y0 = rng[l][6], nh = rng[l][7] - y0 + 1;
+            if (nw <= 0 || nh <= 0) break;
+            if (tid == 0) toff[l] = o;
+            int* t = stab + o;
+            for (int i = tid; i < nw + nh; i += 256) {
+                if (i < nw) {
+                    t[i] = xofs[D.xtab_off + x0 + i];
+                    t[nw + i] = *reinterpret_cast<const int*>(&alpha[D.xtab_off + x0 + i]);
+                } else {
+                    const int j = i - nw;
+                    t[2 * nw + j] = yofs[D.ytab_off + y0 + j];
+                    t[2 * nw + nh + j] = *reinterpret_cast<const int*>(&beta[D.ytab_off + y0 + j]);
+                }
+            }
+            o += 2 * (nw + nh);
+        }
+    }
+    __syncthreads();
+    TR();
+    for (int l = 1; l < L; l++) {
+        const LevelGeom D = g.lv[l];
+        const int x0 = rng[l][2], nw = rng[l][3] - x0 + 1, y0 = rng[l][6], nh = rng[l][7] - y0 + 1;
+        if (nw <= 0 || nh <= 0) break;  // deeper levels need nothing either
+        const int ox0 = rng[l][0], ox1 = rng[l][1], oy0 = rng[l][4], oy1 = rng[l][5];
+        const int sw = g.lv[l - 1].w, sh = g.lv[l - 1].h;
+        const int* t = stab + toff[l];
+        uint8_t* dst = pyr + D.img_off;
+        for (int yy = tid >> 5; yy < nh; yy += 8)
+        for (int xx = tid & 31; xx < nw; xx += 32) {
+            const int i = yy * nw + xx;
+            const int sx = t[xx];
+            const int sx1 = min(sx + 1, sw - 1);
+            const int aw = t[nw + xx];
+            const int a0 = (short)(aw & 0xffff), a1 = aw >> 16;
+            const int sy = t[2 * nw + yy];
+            const int sy0 = min(max(sy, 0), sh - 1), sy1 = min(max(sy + 1, 0), sh - 1);
+            const int bw = t[2 * nw + nh + yy];
+            const int b0 = (short)(bw & 0xffff), b1 = bw >> 16;
+            const uint8_t* r0p = cur + (sy0 - py0) * pw - px0;
+            const uint8_t* r1p = cur + (sy1 - py0) * pw - px0;
+            const int r0 = (int)r0p[sx] * a0 + (int)r0p[sx1] * a1;
+            const int r1 = (int)r1p[sx] * a0 + (int)r1p[sx1] * a1;
+            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            nxt[i] = (uint8_t)v;
+            const int dx = x0 + xx, dy = y0 + yy;
+            if (dx >= ox0 && dx < ox1 && dy >= oy0 && dy < oy1) dst[(size_t)dy * D.pitch + dx] = (uint8_t)v;
+        }
+        __syncthreads();
+        TR();
+        { uint8_t* tmp = cur; cur = nxt; nxt = tmp; }
+        pw = nw; px0 = x0; py0 = y0;
+    }
+    TR_PRINT("pyr", blockIdx.x == 3 && blockIdx.y == 3);
+}
+
+cudaError_t prepare_pyramid(const PyrPlan& p) {
+    const int smem = 2 * p.buf_bytes + 4 * p.tab_smem_ints + 16;
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(k_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+void launch_pyramid(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1) {
+    const PyrPlan& p = b.pyr_plan;
+    const int smem = 2 * p.buf_bytes + 4 * p.tab_smem_ints + 16;
+    k_pyramid<<<dim3(p.ntx, p.nty, b1 ? 2 : 1), 256, smem, s>>>(g, p, b.pyr, b.xofs, b.alpha, b.yofs, b.beta, b1 ? b1->pyr : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ K2 FAST per cell
@@ -206,20 +439,34 @@ __device__ __forceinline__ int block_scan_values(int v, int* warp_tmp, int* tota
 // ROI. The iniTh -> minTh fallback is decided per cell on the post-NMS count.
 __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_constant__ CUtensorMap tmap, int use_tma,
                                                     const uint8_t* __restrict__ pyr, int* __restrict__ cell_count,
-                                                    uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_r,
-                                                    int* __restrict__ status, int cell_begin) {
+                                                    uint32_t* __restrict__ cand_xy, uint32_t* __restrict__ cand_ro,
+                                                    int* __restrict__ level_cand, int* __restrict__ status, int cell_begin,
+                                                    const CUtensorMap* __restrict__ tmap_dev, FastImage2 im1,
+                                                    const __grid_constant__ CUtensorMap tmap1) {
     __shared__ __align__(128) uint8_t roi_raw[kCellRoiMax * kRoiPitchRaw + 16];
     __shared__ __align__(8) uint64_t tma_bar;
     const uint8_t* roi;
+    TR_DECL; TR();
     __shared__ __align__(16) uint8_t sc[kScDim * kScPitch];
-    __shared__ uint32_t row_ini[128], row_min[128];  // two ballot words per valid row (<= 60 rows)
-    __shared__ int row_off[65];
+    __shared__ uint32_t row_ini[128];  // two ballot words per valid row (<= 60 rows)
+    __shared__ uint16_t surv[60 * 60];  // pixels that pass the compass pre-test (y << 6 | x)
+    __shared__ int n_surv;
+    __shared__ int row_off[66];
     const int tid = threadIdx.x;
     const int cell = blockIdx.x + cell_begin;
     int l = 0;
     while (l + 1 < g.n_levels && cell >= g.lv[l + 1].cell_base) l++;
+    TL_SCOPE(16 + l);
+    const CUtensorMap* tm = &tmap;
+    if (blockIdx.z) {  // second image of a stereo pair
+        pyr = im1.pyr; cell_count = im1.cell_count; cand_xy = im1.cand_xy; cand_ro = im1.cand_ro; level_cand = im1.level_cand;
+        status = im1.status;
+        tmap_dev = im1.tmap_dev;
+        tm = &tmap1;
+    }
     const LevelGeom L = g.lv[l];
     const int c = cell - L.cell_base;
+    TR();
     const int ci = c / L.n_cols, cj = c - ci * L.n_cols;
     const int iniX = kBorder + cj * L.w_cell, iniY = kBorder + ci * L.h_cell;
     const int maxX = min(iniX + L.w_cell + 6, L.max_bx), maxY = min(iniY + L.h_cell + 6, L.max_by);
@@ -236,7 +483,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_cons
         __syncthreads();
         if (tid == 0) {
             mbar_expect_tx(&tma_bar, kRoiTmaBytes);
-            tma_load_2d(roi_raw, &tmap, iniX & ~15, iniY, &tma_bar);
+            tma_load_2d(roi_raw, tmap_dev ? tmap_dev + l : tm, iniX & ~15, iniY, &tma_bar);
         }
         roi = roi_raw + (iniX & 15);
     } else {
@@ -250,44 +497,74 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_cons
                 reinterpret_cast<uint32_t*>(roi_raw + y * kRoiPitchRaw)[xw] = *reinterpret_cast<const uint32_t*>(srow + (size_t)y * L.pitch + 4 * xw);
         roi = roi_raw + shift;
     }
-    for (int i = tid; i < kScDim * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
     if (use_tma) mbar_wait(&tma_bar, 0);
-    __syncthreads();
+    TR();
     // warp w owns rows w, w + 8, ...; lane = column (two halves: x = lane, lane + 32) -> no integer divisions, and the
-    // raster order needed for the output falls out of ballots (x order) and a scan over rows (y order)
+    // raster order needed for the output falls out of ballots (x order) and a scan over rows (y order).
+    // The FAST response is expensive (16 ring loads, a min/max network) but most pixels fail the four-compass-point
+    // pre-test, and a warp pays for the full evaluation as soon as one lane needs it. So: pass 1 runs the pre-test
+    // on every pixel and compacts the survivors into a shared list, pass 2 evaluates the list densely.
+    // cv::FAST(iniTh) first; only a cell without any corner is redone at minTh (:809-815) - a corner at iniTh
+    // beats every neighbour that is not a corner at iniTh, so the iniTh score map alone decides the iniTh result.
     const int lane = tid & 31, warp = tid >> 5;
-    const int th_lo = min(g.ini_th, g.min_th);
-    for (int y = warp; y < vh; y += 8) {
+    int th = g.ini_th;
+    const uint32_t* rowm = row_ini;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        for (int i = tid; i < kScDim * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
+        if (tid == 0) n_surv = 0;
+        __syncthreads();
+        for (int y = warp; y < vh; y += 8) {
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int x = lane + 32 * half;
-            if (x < vw) sc[(y + 1) * kScPitch + (x + 1)] = (uint8_t)fast_score_dev(roi + (y + 3) * kRoiPitch + (x + 3), th_lo);
-        }
-    }
-    __syncthreads();
-    // strict 8-neighbour maxima of the (masked) score tile; per row two ballot words for each threshold
-    bool any_ini_local = false;
-    for (int y = warp; y < vh; y += 8) {
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int x = lane + 32 * half;
-            bool f_ini = false, f_min = false;
-            if (x < vw) {
-                const uint8_t* q = sc + (y + 1) * kScPitch + (x + 1);
-                const int s = q[0];
-                if (s != 0 && s > q[-kScPitch - 1] && s > q[-kScPitch] && s > q[-kScPitch + 1] && s > q[-1] && s > q[1] &&
-                    s > q[kScPitch - 1] && s > q[kScPitch] && s > q[kScPitch + 1]) {
-                    f_ini = s >= g.ini_th;
-                    f_min = s >= g.min_th;
+            for (int half = 0; half < 2; half++) {
+                const int x = lane + 32 * half;
+                bool pass = false;
+                if (x < vw) {
+                    const uint8_t* c = roi + (y + 3) * kRoiPitch + (x + 3);
+                    const int v = c[0], r0 = c[3 * kRoiPitch], r4 = c[3], r8 = c[-3 * kRoiPitch], r12 = c[-3];
+                    const int hi = v + th, lo = v - th;
+                    pass = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi) >= 2 || (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo) >= 2;
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&n_surv, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (pass) surv[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(y << 6 | x);
                 }
             }
-            const uint32_t b_ini = __ballot_sync(0xffffffffu, f_ini), b_min = __ballot_sync(0xffffffffu, f_min);
-            if (lane == 0) { row_ini[y * 2 + half] = b_ini; row_min[y * 2 + half] = b_min; }
-            any_ini_local |= b_ini != 0;
         }
+        __syncthreads();
+        TR();
+        const int ns = n_surv;
+        for (int i = tid; i < ns; i += 256) {
+            const int y = surv[i] >> 6, x = surv[i] & 63;
+            sc[(y + 1) * kScPitch + (x + 1)] = (uint8_t)fast_score_dev(roi + (y + 3) * kRoiPitch + (x + 3), th);
+        }
+        __syncthreads();
+        TR();
+        // strict 8-neighbour maxima of the score tile (non-corners are 0); per row two ballot words
+        bool any_local = false;
+        for (int y = warp; y < vh; y += 8) {
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int x = lane + 32 * half;
+                bool f = false;
+                if (x < vw) {
+                    const uint8_t* q = sc + (y + 1) * kScPitch + (x + 1);
+                    const int s = q[0];
+                    f = s != 0 && s > q[-kScPitch - 1] && s > q[-kScPitch] && s > q[-kScPitch + 1] && s > q[-1] && s > q[1] &&
+                        s > q[kScPitch - 1] && s > q[kScPitch] && s > q[kScPitch + 1];
+                }
+                const uint32_t bm = __ballot_sync(0xffffffffu, f);
+                if (lane == 0) row_ini[y * 2 + half] = bm;
+                any_local |= bm != 0;
+            }
+        }
+        const int any = __syncthreads_or(any_local);
+        TR();
+        if (any || g.min_th >= g.ini_th) break;
+        th = g.min_th;
     }
-    const int any_ini = __syncthreads_or(any_ini_local);
-    const uint32_t* rowm = any_ini ? row_ini : row_min;
     if (warp == 0) {  // exclusive scan of the per-row counts (vh <= 60 rows: two per lane)
         const int y0 = 2 * lane, y1 = 2 * lane + 1;
         const int c0 = y0 < vh ? __popc(rowm[y0 * 2]) + __popc(rowm[y0 * 2 + 1]) : 0;
@@ -300,15 +577,21 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_cons
         }
         if (y0 < vh) row_off[y0] = inc - c0 - c1;
         if (y1 < vh) row_off[y1] = inc - c1;
-        if (lane == 31) row_off[64] = inc;
+        if (lane == 31) {
+            row_off[64] = inc;
+            // reserve this cell's stretch of the level's candidate list (a strict 8-neighbour maximum has no
+            // 8-neighbour that is one too, so a cell holds at most `slot` corners and the list cannot overflow)
+            row_off[65] = inc > 0 && inc <= L.slot ? atomicAdd(&level_cand[l], inc) : 0;
+        }
     }
     __syncthreads();
     const int total = row_off[64];
-    if (total > L.slot) {  // impossible for strict 8-neighbour maxima; never truncate silently
+    if (total > L.slot) {  // impossible; never truncate silently
         if (tid == 0) { atomicExch(status, 101); cell_count[cell] = 0; }
         return;
     }
-    const int base = L.cand_base + c * L.slot;
+    const int base = L.cand_base + row_off[65];
+    const uint32_t order0 = 0xffffffu - (uint32_t)(c * L.slot);
     for (int y = warp; y < vh; y += 8) {
         const uint32_t m0 = rowm[y * 2], m1 = rowm[y * 2 + 1];
         const uint32_t lt = (1u << lane) - 1u;
@@ -320,11 +603,13 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_cons
                 const int pos = row_off[y] + (half ? __popc(m0) : 0) + __popc(m & lt);
                 // coordinates relative to (minBorderX, minBorderY): FAST's ROI coordinate + j*wCell (:822-823)
                 cand_xy[base + pos] = (uint32_t)(x + 3 + cj * L.w_cell) | (uint32_t)(y + 3 + ci * L.h_cell) << 16;
-                cand_r[base + pos] = sc[(y + 1) * kScPitch + (x + 1)];
+                cand_ro[base + pos] = (uint32_t)sc[(y + 1) * kScPitch + (x + 1)] << 24 | (order0 - (uint32_t)pos);
             }
         }
     }
     if (tid == 0) cell_count[cell] = total;
+    TR();
+    TR_PRINT("fast", cell == 100 || cell == 900 || cell == 1200);
 }
 
 // cuTensorMapEncodeTiled is a driver-API symbol; it is resolved at run time through the runtime so that the library
@@ -355,14 +640,32 @@ bool encode_tma_maps(const OrbGeom& g, uint8_t* pyr, TmaMaps* out) {
 }
 
 // level < 0: every level (one launch each); else only that level (lets a level start as soon as it is resized)
-void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s) {
+static FastImage2 fast_image2(const OrbBuffers* b1, bool dev_maps) {
+    FastImage2 im = {};
+    if (b1) {
+        im.pyr = b1->pyr; im.cell_count = b1->cell_count; im.cand_xy = b1->cand_xy; im.cand_ro = b1->cand_ro;
+        im.level_cand = b1->level_cand; im.status = b1->status;
+        im.tmap_dev = dev_maps ? b1->tma_dev : nullptr;
+    }
+    return im;
+}
+
+void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s, const OrbBuffers* b1) {
     // one launch per level: the level's tensor map travels as a __grid_constant__ parameter (the form TMA expects)
     const int l0 = level < 0 ? 0 : level, l1 = level < 0 ? g.n_levels : level + 1;
     for (int l = l0; l < l1; l++) {
         const int n = g.lv[l].n_cols * g.lv[l].n_rows;
-        k_fast_cells<<<n, 256, 0, s>>>(g, b.tma_maps->m[l], b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_r, b.status,
-                                       g.lv[l].cell_base);
+        k_fast_cells<<<dim3(n, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b.tma_maps->m[l], b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_ro,
+                                                            b.level_cand, b.status, g.lv[l].cell_base, nullptr, fast_image2(b1, false),
+                                                            (b1 ? b1 : &b)->tma_maps->m[l]);
     }
+}
+
+// every cell of every level in one launch; the per-level tensor maps are read from their device copy
+void launch_fast_all(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1) {
+    k_fast_cells<<<dim3(g.n_cells, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b.tma_maps->m[0], b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_ro,
+                                                                b.level_cand, b.status, 0, b.tma_dev, fast_image2(b1, true),
+                                                                b.tma_maps->m[0]);
 }
 
 // ------------------------------------------------------------------------------------------------ K5 Gaussian 7x7
@@ -376,9 +679,12 @@ __device__ __forceinline__ int reflect101(int p, int n) {
     return p;
 }
 
-__global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+__global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+                                              const uint8_t* __restrict__ pyr1, uint8_t* __restrict__ blur1) {
+    if (blockIdx.z) { pyr = pyr1; blur = blur1; }
     __shared__ uint8_t in[kBlurTH + 6][kBlurTW + 8];
     __shared__ uint16_t hb[kBlurTH + 6][kBlurTW];
+    TL_SCOPE(48);
     const int tid = threadIdx.x;
     int l = 0;
     while (l + 1 < g.n_levels && (int)blockIdx.x >= g.lv[l + 1].blur_tile_base) l++;
@@ -415,8 +721,8 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
     }
 }
 
-void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
-    k_blur<<<g.blur_tiles, 256, 0, s>>>(g, b.pyr, b.blur);
+void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1) {
+    k_blur<<<dim3(g.blur_tiles, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b.pyr, b.blur, b1 ? b1->pyr : nullptr, b1 ? b1->blur : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 quadtree
@@ -436,38 +742,98 @@ void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
 constexpr int kOctThreads = CORB_OCT_THREADS;
 
 struct OctLayout {
-    int cntA, cntB, bndA, bndB, cc, procpos, scan, crank, krank, fresh, candf, warp_tmp, sh, scan64, warp_tmp64, cell_off, keys_xy, keys_node, keys_r, total;
+    int cntA, cntB, bndA, bndB, cc, procpos, scan, crank, krank, fresh, candf, warp_tmp, sh, scan64, warp_tmp64, keys_xy, keys_node, keys_ro, total;
+    int fast;  // closed-form path tabulated (n_ini small enough), with the arrays below
+    int f_hist, f_code, f_owner, f_flag, f_stat, f_lut;
 };
-__host__ __device__ inline OctLayout oct_layout(int NC, int key_cap, int n_cell) {
+// Closed-form path (see k_octtree): quadtree depths 0..kOctDh are tabulated from one histogram of the keys' depth-kOctDh
+// cells; the cell index of depth d is root * 4^d + sum q_i * 4^(d-i).
+constexpr int kOctDh = 5;
+constexpr int kOctFastMaxIni = 8;
+constexpr int kOctSmemLimit = 200 * 1024;
+__host__ __device__ inline int oct_depth_off(int n_ini, int d) { return n_ini * (((1 << (2 * d)) - 1) / 3); }
+__host__ __device__ inline OctLayout oct_layout(int NC, int key_cap, int n_lut, int n_ini) {
     OctLayout o;
     int p = 0;
-    o.cntA = p; p += 4 * NC;
-    o.cntB = p; p += 4 * NC;
-    o.bndA = p; p += 8 * NC;
-    o.bndB = p; p += 8 * NC;
-    o.cc = p; p += 16 * NC;
-    o.procpos = p; p += 4 * NC;
-    o.scan = p; p += 4 * NC;
-    o.crank = p; p += 4 * NC;
-    o.krank = p; p += 4 * NC;
-    o.fresh = p; p += 2 * ((NC + 3) & ~3);  // fresh A and B
-    o.candf = p; p += (NC + 3) & ~3;
-    o.warp_tmp = p; p += 4 * 36;
-    o.sh = p; p += 4 * 8;
-    p = (p + 15) & ~15;
-    o.scan64 = p; p += 8 * NC;
-    o.warp_tmp64 = p; p += 8 * 36;
-    o.cell_off = p; p += 4 * (n_cell + 1);
-    p = (p + 15) & ~15;
-    o.keys_xy = p; p += 4 * key_cap;
-    o.keys_node = p; p += 2 * ((key_cap + 1) & ~1);
-    o.keys_r = p; p += (key_cap + 3) & ~3;
-    o.total = (p + 15) & ~15;
+    // every array starts on a 16-byte boundary and is padded to a multiple of 16 bytes (vectorised scans read whole int4)
+#define OCT_ALLOC(field, bytes) do { o.field = p; p += ((bytes) + 15) & ~15; } while (0)
+    OCT_ALLOC(cntA, 4 * NC);
+    OCT_ALLOC(cntB, 4 * NC);
+    OCT_ALLOC(bndA, 8 * NC);
+    OCT_ALLOC(bndB, 8 * NC);
+    OCT_ALLOC(cc, 16 * NC);
+    OCT_ALLOC(procpos, 4 * NC);
+    OCT_ALLOC(scan, 4 * NC);
+    OCT_ALLOC(crank, 4 * NC);
+    OCT_ALLOC(krank, 4 * NC);
+    OCT_ALLOC(fresh, 2 * ((NC + 3) & ~3));  // fresh A and B
+    OCT_ALLOC(candf, NC);
+    OCT_ALLOC(warp_tmp, 4 * 36);
+    OCT_ALLOC(sh, 4 * 8);
+    OCT_ALLOC(scan64, 8 * NC);
+    OCT_ALLOC(warp_tmp64, 8 * 36);
+    OCT_ALLOC(keys_xy, 4 * key_cap);
+    OCT_ALLOC(keys_node, 2 * key_cap);
+    OCT_ALLOC(keys_ro, 4 * key_cap);
+    o.f_hist = o.f_code = o.f_owner = o.f_flag = o.f_stat = o.f_lut = 0;
+    const int HC = n_ini << (2 * kOctDh), TC = oct_depth_off(n_ini, kOctDh + 1);
+    {   // the closed-form tables are optional: keep them only while the whole layout stays inside kOctSmemLimit
+        const int extra = 4 * (HC + 4) + 4 * (TC + 4) + 64 + 2 * key_cap + 2 * HC + 2 * (n_lut + 2) + 6 * 16;
+        o.fast = n_ini <= kOctFastMaxIni && p + extra <= kOctSmemLimit;
+    }
+    if (o.fast) {
+        OCT_ALLOC(f_hist, 4 * (HC + 4));
+        OCT_ALLOC(f_flag, 4 * (TC + 4));
+        OCT_ALLOC(f_stat, 4 * 16);
+        OCT_ALLOC(f_code, 2 * key_cap);
+        OCT_ALLOC(f_owner, 2 * HC);
+        OCT_ALLOC(f_lut, 2 * (n_lut + 2));
+    }
+#undef OCT_ALLOC
+    o.total = p;
     return o;
 }
 
+// entries of a level's path tables: xs over the window width (even-padded), ys over the window height
+__host__ __device__ inline int oct_lut_entries(const LevelGeom& L) {
+    return ((L.max_bx - kBorder + 1) & ~1) + ((L.max_by - kBorder + 1) & ~1);
+}
+
+// Host: xs[x] = root << 2Dh | x-bits of the path on the even bit positions, ys[y] = y-bits on the odd positions, so the
+// depth-Dh cell of a key is xs[x] | ys[y]. Same float and integer arithmetic as DistributeOctTree / DivideNode
+// (ORBextractor.cc:481-489, 543-559): root = (int)(x / hX), halves = ceil(extent / 2).
+void build_oct_lut(const LevelGeom& L, uint16_t* out) {
+    const int W = L.max_bx - kBorder, H = L.max_by - kBorder, Wp = (W + 1) & ~1;
+    for (int x = 0; x < W; x++) {
+        const int ni = (int)((float)x / L.h_x);
+        int x0 = (int)(L.h_x * (float)ni), x1 = (int)(L.h_x * (float)(ni + 1));
+        int code = 0;
+        for (int d = 0; d < kOctDh; d++) {
+            const int xm = x0 + ((x1 - x0 + 1) >> 1);
+            const int bit = x < xm ? 0 : 1;
+            if (bit) x0 = xm; else x1 = xm;
+            code = code * 4 + bit;
+        }
+        out[x] = (uint16_t)(ni << (2 * kOctDh) | code);
+    }
+    for (int x = W; x < Wp; x++) out[x] = 0;
+    for (int y = 0; y < H; y++) {
+        int y0 = 0, y1 = H, code = 0;
+        for (int d = 0; d < kOctDh; d++) {
+            const int ym = y0 + ((y1 - y0 + 1) >> 1);
+            const int bit = y < ym ? 0 : 1;
+            if (bit) y0 = ym; else y1 = ym;
+            code = code * 4 + 2 * bit;
+        }
+        out[Wp + y] = (uint16_t)code;
+    }
+    if (H & 1) out[Wp + H] = 0;
+}
+
+int oct_lut_entries_host(const LevelGeom& L) { return oct_lut_entries(L); }
+
 int octtree_smem_bytes(const OrbGeom& g, int level, int key_smem_cap) {
-    return oct_layout(g.lv[level].node_cap, key_smem_cap, g.lv[level].n_cols * g.lv[level].n_rows).total;
+    return oct_layout(g.lv[level].node_cap, key_smem_cap, oct_lut_entries(g.lv[level]), g.lv[level].n_ini).total;
 }
 
 // Warp-aggregated shared-memory counter increment: lanes that hit the same counter elect one leader, so the early
@@ -495,14 +861,25 @@ __device__ __forceinline__ short4 child_bounds(short4 b, int q) {
     return c;
 }
 
-__global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b, int key_smem_cap, int level_begin) {
+#ifdef CORB_OCT_TRACE
+#define OCT_T(i) do { if (threadIdx.x == 0) oct_tr[i] = clock64(); } while (0)
+#else
+#define OCT_T(i) do { } while (0)
+#endif
+__global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b0, int key_smem_cap, int level_begin, OrbBuffers b1) {
+    const OrbBuffers b = blockIdx.z ? b1 : b0;
     extern __shared__ __align__(16) uint8_t smem[];
+#ifdef CORB_OCT_TRACE
+    long long oct_tr[24];
+    for (int i = 0; i < 24; i++) oct_tr[i] = 0;
+#endif
+    TL_SCOPE(32 + blockIdx.x + level_begin);
+    OCT_T(0);
     const int l = blockIdx.x + level_begin;
     const LevelGeom L = g.lv[l];
     const int NC = L.node_cap, N = L.quota;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int n_cell = L.n_cols * L.n_rows;
-    const OctLayout lay = oct_layout(NC, key_smem_cap, n_cell);
+    const OctLayout lay = oct_layout(NC, key_smem_cap, oct_lut_entries(L), L.n_ini);
     int* cnt_cur = reinterpret_cast<int*>(smem + lay.cntA);
     int* cnt_nxt = reinterpret_cast<int*>(smem + lay.cntB);
     short4* bnd_cur = reinterpret_cast<short4*>(smem + lay.bndA);
@@ -520,38 +897,307 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
     long long* scan64 = reinterpret_cast<long long*>(smem + lay.scan64);
     long long* warp_tmp64 = reinterpret_cast<long long*>(smem + lay.warp_tmp64);
 
-    // ---- gather the level's candidates in the order vToDistributeKeys is built: cell row, cell column, raster.
-    //      Cell offsets are scanned in shared memory; every key then finds its cell by binary search, so all global
-    //      loads of the gather are independent (a per-cell loop would serialise ~30 dependent L2 round trips per warp).
-    int* cell_off = reinterpret_cast<int*>(smem + lay.cell_off);
-    for (int i = tid; i < n_cell; i += nt) cell_off[i] = b.cell_count[L.cell_base + i];
-    __syncthreads();
-    const int M = block_excl_scan(cell_off, n_cell, warp_tmp);
-    if (tid == 0) cell_off[n_cell] = M;
-    uint32_t* kxy;
-    uint16_t* knode;
-    uint8_t* kr;
-    if (M <= key_smem_cap) {
-        kxy = reinterpret_cast<uint32_t*>(smem + lay.keys_xy);
-        knode = reinterpret_cast<uint16_t*>(smem + lay.keys_node);
-        kr = smem + lay.keys_r;
-    } else {
-        kxy = b.key_xy + L.cand_base;
-        knode = b.key_node + L.cand_base;
-        kr = b.key_r + L.cand_base;
-    }
-    __syncthreads();
-    for (int k = tid; k < M; k += nt) {
-        int lo = 0, hi = n_cell;  // last cell with cell_off[c] <= k
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (cell_off[mid] <= k) lo = mid; else hi = mid;
+    // ---- the level's candidates: FAST appended them to the level's list (any order; the reference order travels as
+    //      the order key in the low 24 bits of kro). The first batches are fetched before the count is known, so the
+    //      count, the records and the path tables all arrive in one round of global latency.
+    const int lut_n = oct_lut_entries(L);
+    const bool fast_try = lay.fast && b.oct_fast;
+    uint32_t* kxy = reinterpret_cast<uint32_t*>(smem + lay.keys_xy);
+    uint16_t* knode = reinterpret_cast<uint16_t*>(smem + lay.keys_node);
+    uint32_t* kro = reinterpret_cast<uint32_t*>(smem + lay.keys_ro);
+    const uint32_t* gxy = b.cand_xy + L.cand_base;
+    const uint32_t* gro = b.cand_ro + L.cand_base;
+    const int cap_level = L.n_cols * L.n_rows * L.slot;
+    int M;
+    {
+        uint32_t vx[4], vr[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = min(tid + u * nt, cap_level - 1);
+            vx[u] = gxy[k];
+            vr[u] = gro[k];
         }
-        const int src = L.cand_base + lo * L.slot + (k - cell_off[lo]);
-        kxy[k] = b.cand_xy[src];
-        kr[k] = b.cand_r[src];
+        if (fast_try) {
+            const uint32_t* glut = reinterpret_cast<const uint32_t*>(b.oct_lut + L.lut_off);
+            uint32_t* slut = reinterpret_cast<uint32_t*>(smem + lay.f_lut);
+            for (int i = tid; i < lut_n / 2; i += nt) slut[i] = glut[i];
+        }
+        M = b.level_cand[l];
+        if (M <= key_smem_cap) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (tid + u * nt < M) { kxy[tid + u * nt] = vx[u]; kro[tid + u * nt] = vr[u]; }
+            for (int k = tid + 4 * nt; k < M; k += nt) { kxy[k] = gxy[k]; kro[k] = gro[k]; }
+        } else {  // too many for shared memory: the generic passes read the records in place
+            kxy = const_cast<uint32_t*>(gxy);
+            kro = const_cast<uint32_t*>(gro);
+            knode = b.key_node + L.cand_base;
+        }
     }
-    if (tid == 0) b.level_cand[l] = M;
+    __syncthreads();
+    if (tid == 0) {
+        b.level_cand[l] = 0;  // every thread has read it: ready for the next frame
+        b.level_cand_out[l] = M;
+    }
+    OCT_T(2);
+    // ---- closed-form path. The split geometry depends only on the root rectangle, so a key's path (root, q1, q2, ...)
+    //      is a pure function of its coordinates and every node count is a range sum over one histogram of the keys'
+    //      depth-kOctDh cells (exclusive scan P: count(d, c) = P[(c+1) << 2(Dh-d)] - P[c << 2(Dh-d)]). Full passes
+    //      (:613-655) split every node with more than one key, hence after pass d the list holds one node per
+    //      non-empty depth-d cell: s_d = #non-empty cells, nToExpand_d = #cells with more than one key, and the pass at
+    //      which the loop stops or enters the near-quota phase follows from those two numbers per depth. The list after
+    //      pass d is R_d ++ singles(R_{d-1}) ++ ... ++ singles(R_0), R_d = depth-d children of split nodes; push_front
+    //      in creation order reverses the order each pass, which makes R_d sorted by the cell index with every other
+    //      digit complemented (tau below). The near-quota rounds then run on nodes only (child counts are range sums),
+    //      and keys find their final node through a dense (depth, cell) -> position map. Anything that needs a depth
+    //      beyond kOctDh (sparse levels, tight clusters) falls through to the generic pass-by-pass code below.
+    bool done = false;
+    int s = 0;
+    if (lay.fast && b.oct_fast && M > 0 && M <= key_smem_cap) {
+        int* hist = reinterpret_cast<int*>(smem + lay.f_hist);
+        int* fflag = reinterpret_cast<int*>(smem + lay.f_flag);
+        int* fstat = reinterpret_cast<int*>(smem + lay.f_stat);
+        uint16_t* kcode = reinterpret_cast<uint16_t*>(smem + lay.f_code);
+        uint16_t* owner = reinterpret_cast<uint16_t*>(smem + lay.f_owner);
+        int* fc_cur = reinterpret_cast<int*>(bnd_cur);  // node = depth << 24 | cell
+        int* fc_nxt = reinterpret_cast<int*>(bnd_nxt);
+        const int nini = L.n_ini;
+        const int HC = nini << (2 * kOctDh);
+        for (int i = tid; i < (HC + 4) / 4; i += nt) reinterpret_cast<int4*>(hist)[i] = make_int4(0, 0, 0, 0);
+        if (tid < 16) fstat[tid] = 0;
+        __syncthreads();
+        {
+            const uint16_t* xs = reinterpret_cast<const uint16_t*>(smem + lay.f_lut);
+            const uint16_t* ys = xs + ((L.max_bx - kBorder + 1) & ~1);
+            for (int k = tid; k < M; k += nt) {
+                const uint32_t xy = kxy[k];
+                const int code = xs[xy & 0xffff] | ys[xy >> 16];
+                kcode[k] = (uint16_t)code;
+                atomicAdd(&hist[code], 1);
+            }
+        }
+        __syncthreads();
+    OCT_T(3);
+        block_excl_scan4(hist, HC, warp_tmp);
+        if (tid == 0) hist[HC] = M;
+        __syncthreads();
+    OCT_T(4);
+        auto hcount = [&](int d, int c) {
+            const int sh2 = 2 * (kOctDh - d);
+            return hist[(c + 1) << sh2] - hist[c << sh2];
+        };
+        // per depth: non-empty cells (low half) and cells holding more than one key (high half); depths 0..Dh-1 first,
+        // the deepest tabulated depth only when the stop depth was not found among them
+        auto depth_stats = [&](int d) {
+            const int ncell = nini << (2 * d);
+            int acc = 0;
+            for (int c = tid; c < ncell; c += nt) {
+                const int n = hcount(d, c);
+                acc += (n > 0) + ((n > 1) << 16);
+            }
+            acc = __reduce_add_sync(0xffffffffu, acc);
+            if ((tid & 31) == 0 && acc) {
+                atomicAdd(&fstat[d], acc & 0xffff);
+                atomicAdd(&fstat[8 + d], acc >> 16);
+            }
+        };
+#pragma unroll
+        for (int d = 0; d < kOctDh; d++) depth_stats(d);
+        __syncthreads();
+        int dstar = -1;
+        bool final_phase = false;
+        auto find_stop = [&](int dmax) {
+            int sp = fstat[0];
+            for (int d = 1; d <= dmax; d++) {
+                const int sd = fstat[d];
+                if (sd >= N || sd == sp) { dstar = d; return; }
+                if (sd + 3 * fstat[8 + d] > N) { dstar = d; final_phase = true; return; }
+                sp = sd;
+            }
+        };
+        find_stop(kOctDh - 1);
+        if (dstar < 0) {
+            depth_stats(kOctDh);
+            __syncthreads();
+            find_stop(kOctDh);
+        }
+    OCT_T(5);
+        if (dstar > 0 && fstat[dstar] <= NC) {
+            // membership flags over the concatenated segments [depth dstar | singles of depth dstar-1 | ... | depth 0]
+            const int etot = oct_depth_off(nini, dstar + 1);
+            auto entry = [&](int e, int* d_out, int* c_out, int* n_out) -> bool {
+                int d = dstar, base = 0;
+                while (e >= base + (nini << (2 * d))) { base += nini << (2 * d); d--; }
+                const int i = e - base;
+                const int lowmask = (1 << (2 * d)) - 1;
+                int r = i >> (2 * d);
+                if (d & 1) r = nini - 1 - r;
+                const int c = (r << (2 * d)) | ((i & lowmask) ^ (0x33333333 & lowmask));  // tau_d (an involution)
+                const int n = hcount(d, c);
+                const bool par = d == 0 || hcount(d - 1, c >> 2) > 1;
+                *d_out = d; *c_out = c; *n_out = n;
+                return par && (d == dstar ? n > 0 : n == 1);
+            };
+            for (int e = tid; e < etot; e += nt) {
+                int d, c, n;
+                fflag[e] = entry(e, &d, &c, &n) ? 1 : 0;
+            }
+            __syncthreads();
+            s = block_excl_scan4(fflag, etot, warp_tmp);
+    OCT_T(6);
+            if (tid == 0) fflag[etot] = s;
+            __syncthreads();
+            for (int e = tid; e < etot; e += nt) {
+                const int pos = fflag[e];
+                if (fflag[e + 1] != pos) {
+                    int d, c, n;
+                    entry(e, &d, &c, &n);
+                    fc_cur[pos] = d << 24 | c;
+                    cnt_cur[pos] = n;
+                    fresh_cur[pos] = d == dstar;
+                }
+            }
+            __syncthreads();
+    OCT_T(7);
+            bool bail = false;
+            int dmax = dstar;  // deepest node depth in the list
+            while (final_phase) {  // near-quota rounds (:660-733) on nodes only
+                const int prev = s;
+                for (int i = tid; i < s; i += nt) {
+                    const int f = fresh_cur[i] && cnt_cur[i] > 1;
+                    scan[i] = f;
+                    candf[i] = (uint8_t)f;
+                }
+                if (tid == 0) sh[3] = 0;
+                __syncthreads();
+                const int m = block_excl_scan4(scan, s, warp_tmp);
+    OCT_T(8);
+                for (int i = tid; i < s; i += nt) {
+                    if (candf[i]) {
+                        krank[scan[i]] = i;  // candidates in position order
+                        const int fc = fc_cur[i], d = fc >> 24, c = fc & 0xffffff;
+                        if (d + 1 > kOctDh) {
+                            sh[3] = 1;
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) cc[i * 4 + q] = hcount(d + 1, c * 4 + q);
+                        }
+                    }
+                    crank[i] = -1;
+                }
+                __syncthreads();
+                if (sh[3]) { bail = true; break; }
+    OCT_T(9);
+                for (int i = tid; i < m; i += nt) scan[i] = cnt_cur[krank[i]];  // candidate counts, contiguous
+                if (tid == 0) { sh[0] = m; sh[1] = 0; }
+                __syncthreads();
+                // processing order: count descending, position ascending. Four lanes share one candidate.
+                for (int i0 = 0; i0 < m; i0 += nt / 4) {
+                    const int i = i0 + (tid >> 2), sub = tid & 3;
+                    int rank = 0;
+                    if (i < m) {
+                        const int ci = scan[i];
+                        for (int j = sub; j < m; j += 4) {
+                            const int cj = scan[j];
+                            rank += (cj > ci) || (cj == ci && j < i);
+                        }
+                    }
+                    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+                    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+                    if (i < m && sub == 0) procpos[rank] = krank[i];
+                }
+                __syncthreads();
+    OCT_T(10);
+                for (int r = tid; r < m; r += nt) {
+                    const int* c4 = cc + procpos[r] * 4;
+                    scan[r] = (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0) - 1;
+                }
+                __syncthreads();
+                block_excl_scan4(scan, m, warp_tmp);
+                for (int r = tid; r < m; r += nt) {  // first prefix whose list size reaches N (:728-729)
+                    const int* c4 = cc + procpos[r] * 4;
+                    const int inc = scan[r] + (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0) - 1;
+                    if (s + inc >= N && s + scan[r] < N) sh[0] = r + 1;
+                }
+                __syncthreads();
+                const int mproc = sh[0];
+    OCT_T(11);
+                for (int r = tid; r < mproc; r += nt) {
+                    const int nd = procpos[r];
+                    crank[nd] = scan[r] + r;
+                    if (r == mproc - 1) {
+                        const int* c4 = cc + nd * 4;
+                        sh[1] = scan[r] + r + (c4[0] > 0) + (c4[1] > 0) + (c4[2] > 0) + (c4[3] > 0);
+                    }
+                }
+                __syncthreads();
+                const int T = sh[1];
+                for (int i = tid; i < s; i += nt) scan[i] = crank[i] < 0;
+                __syncthreads();
+                const int K = block_excl_scan4(scan, s, warp_tmp);
+                if (T + K > NC) { bail = true; break; }  // cannot happen (list size <= max(N + 3, 4 nIni))
+    OCT_T(12);
+                for (int i = tid; i < s; i += nt) {
+                    if (crank[i] >= 0) {
+                        const int fc = fc_cur[i], d = fc >> 24, c = fc & 0xffffff;
+                        int idx = crank[i];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int n = cc[i * 4 + q];
+                            if (n > 0) {
+                                const int np = T - 1 - idx;
+                                cnt_nxt[np] = n;
+                                fc_nxt[np] = (d + 1) << 24 | (c * 4 + q);
+                                fresh_nxt[np] = 1;
+                                idx++;
+                            }
+                        }
+                    } else {
+                        const int np = T + scan[i];
+                        cnt_nxt[np] = cnt_cur[i];
+                        fc_nxt[np] = fc_cur[i];
+                        fresh_nxt[np] = 0;
+                    }
+                }
+                __syncthreads();
+                { int* t = cnt_cur; cnt_cur = cnt_nxt; cnt_nxt = t; }
+                { int* t = fc_cur; fc_cur = fc_nxt; fc_nxt = t; }
+                { uint8_t* t = fresh_cur; fresh_cur = fresh_nxt; fresh_nxt = t; }
+                s = T + K;
+                dmax++;
+    OCT_T(13);
+                if (s >= N || s == prev) break;
+            }
+            if (!bail) {
+                // every final node writes its list position over the depth-Dh cells it covers (aligned runs of
+                // 4^(Dh - depth) entries), so a key finds its node with one lookup
+                for (int i = tid; i < s; i += nt) {
+                    const int fc = fc_cur[i], d = fc >> 24, c = fc & 0xffffff;
+                    const int run = 1 << (2 * (kOctDh - d));
+                    uint16_t* o = owner + (size_t)c * run;
+                    if (run >= 8) {
+                        const uint32_t w = (uint32_t)i | (uint32_t)i << 16;
+                        const uint4 v = make_uint4(w, w, w, w);
+                        for (int j = 0; j < run; j += 8) *reinterpret_cast<uint4*>(o + j) = v;
+                    } else {
+                        for (int j = 0; j < run; j++) o[j] = (uint16_t)i;
+                    }
+                }
+                __syncthreads();
+                for (int k = tid; k < M; k += nt) knode[k] = owner[kcode[k]];
+                done = true;
+    OCT_T(14);
+            }
+            // restore the canonical buffer roles for the generic path / epilogue (pointers only; contents are rebuilt)
+            cnt_cur = reinterpret_cast<int*>(smem + lay.cntA);
+            cnt_nxt = reinterpret_cast<int*>(smem + lay.cntB);
+            fresh_cur = smem + lay.fresh;
+            fresh_nxt = fresh_cur + ((NC + 3) & ~3);
+        }
+        __syncthreads();
+    }
+    if (!done) {
+    OCT_T(15);
     // ---- initial nodes (:542-589)
     for (int i = tid; i < 4 * NC; i += nt) cc[i] = 0;
     __syncthreads();
@@ -563,7 +1209,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
     __syncthreads();
     for (int i = tid; i < L.n_ini; i += nt) scan[i] = cc[i] > 0;
     __syncthreads();
-    int s = block_excl_scan(scan, L.n_ini, warp_tmp);
+    s = block_excl_scan(scan, L.n_ini, warp_tmp);
     for (int i = tid; i < L.n_ini; i += nt) {
         if (cc[i] > 0) {
             const int p = scan[i];
@@ -804,18 +1450,33 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
         if (s >= N || s == prev) finish = true;
         else if (!final_phase && s + 3 * n_to_expand > N) final_phase = true;
     }
+    }
     // ---- keep the max-response key of every node, first in candidate order on ties (:738-757)
     uint32_t* best = reinterpret_cast<uint32_t*>(cc);
+    OCT_T(16);
     for (int i = tid; i < s; i += nt) best[i] = 0;
     __syncthreads();
-    for (int k = tid; k < M; k += nt) atomicMax(&best[knode[k]], (uint32_t)kr[k] << 24 | (0xffffffu - (uint32_t)k));
+    // kro = response << 24 | (0xffffff - order key): the maximum is the largest response, earliest candidate on ties
+    for (int k = tid; k < M; k += nt) atomicMax(&best[knode[k]], kro[k]);
     __syncthreads();
-    for (int i = tid; i < s; i += nt) {
-        const int k = (int)(0xffffffu - (best[i] & 0xffffffu));
-        const uint32_t xy = kxy[k];
-        b.lvl_kp[L.kp_base + i] = make_uint2(((xy & 0xffff) + kBorder) | ((xy >> 16) + kBorder) << 16, kr[k]);
+    for (int k = tid; k < M; k += nt) {  // order keys are unique, so exactly one key per node matches
+        const int nd = knode[k];
+        const uint32_t v = kro[k];
+        if (best[nd] == v) {
+            const uint32_t xy = kxy[k];
+            b.lvl_kp[L.kp_base + nd] = make_uint2(((xy & 0xffff) + kBorder) | ((xy >> 16) + kBorder) << 16, v >> 24);
+        }
     }
     if (tid == 0) b.level_count[l] = s;
+#ifdef CORB_OCT_TRACE
+    OCT_T(17);
+    if (threadIdx.x == 0 && blockIdx.x + level_begin == 0 && blockIdx.z == 0) {
+        printf("oct L0 M=%d s=%d done=%d :", M, s, (int)done);
+        long long last = oct_tr[0];
+        for (int i = 1; i < 18; i++) if (oct_tr[i]) { printf(" t%d+%lld", i, oct_tr[i] - last); last = oct_tr[i]; }
+        printf(" total %lld\n", oct_tr[17] - oct_tr[0]);
+    }
+#endif
 }
 
 cudaError_t prepare_octtree(const OrbGeom& g, int key_smem_cap, int* smem_bytes_out) {
@@ -825,9 +1486,11 @@ cudaError_t prepare_octtree(const OrbGeom& g, int key_smem_cap, int* smem_bytes_
     return cudaFuncSetAttribute(k_octtree, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int level, int key_smem_cap, int smem_bytes, cudaStream_t s) {
-    if (level < 0) k_octtree<<<g.n_levels, kOctThreads, smem_bytes, s>>>(g, b, key_smem_cap, 0);
-    else k_octtree<<<1, kOctThreads, octtree_smem_bytes(g, level, key_smem_cap), s>>>(g, b, key_smem_cap, level);
+void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int level, int key_smem_cap, int smem_bytes, cudaStream_t s,
+                    const OrbBuffers* b1) {
+    const int nz = b1 ? 2 : 1;
+    if (level < 0) k_octtree<<<dim3(g.n_levels, 1, nz), kOctThreads, smem_bytes, s>>>(g, b, key_smem_cap, 0, b1 ? *b1 : b);
+    else k_octtree<<<dim3(1, 1, nz), kOctThreads, octtree_smem_bytes(g, level, key_smem_cap), s>>>(g, b, key_smem_cap, level, b1 ? *b1 : b);
 }
 
 // ------------------------------------------------------------------------------------------------ K4 + K6
@@ -855,9 +1518,11 @@ __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
 
 // One warp per kept keypoint: IC_Angle on the un-blurred level (ORBextractor.cc:77-104), then the 256 steered BRIEF
 // tests on the blurred level (:107-146), then the epilogue of operator() (:1092-1101, :837-847).
-__global__ void __launch_bounds__(256) k_orient_desc(OrbGeom g, OrbBuffers b) {
+__global__ void __launch_bounds__(256) k_orient_desc(OrbGeom g, OrbBuffers b0, OrbBuffers b1) {
+    const OrbBuffers b = blockIdx.z ? b1 : b0;
     // pattern transposed to [point-in-byte 0..15][lane 0..31] so the 32 lanes of a warp read 64 contiguous bytes
     __shared__ char2 pat[16 * 32];
+    TL_SCOPE(49);
     for (int i = threadIdx.x; i < 512; i += 256)
         pat[(i & 15) * 32 + (i >> 4)] = make_char2(d_pattern[2 * i], d_pattern[2 * i + 1]);
     __syncthreads();
@@ -940,8 +1605,8 @@ __global__ void __launch_bounds__(256) k_orient_desc(OrbGeom g, OrbBuffers b) {
     }
 }
 
-void launch_orient_desc(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s) {
-    k_orient_desc<<<(g.kp_cap + 7) / 8, 256, 0, s>>>(g, b);
+void launch_orient_desc(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1) {
+    k_orient_desc<<<dim3((g.kp_cap + 7) / 8, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b, b1 ? *b1 : b);
 }
 
 }  // namespace corb

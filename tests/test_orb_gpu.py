@@ -182,3 +182,38 @@ def test_stereo_matches_unrelated_images():
     np.testing.assert_array_equal(ur.view(np.uint32), our.view(np.uint32))
     np.testing.assert_array_equal(dp.view(np.uint32), odp.view(np.uint32))
     exl.close(); exr.close()
+
+
+def test_quadtree_closed_form_equals_pass_by_pass(monkeypatch):
+    """k_octtree's closed-form path (histogram of depth-5 cells) and its generic pass-by-pass code give the same
+    keypoints in the same order; both equal the oracle (DistributeOctTree, ORBextractor.cc:539-763)."""
+    for seed, size, params in [(21, (1242, 375), PARAMS), (22, (640, 480), (1000, 1.2, 8, 20, 7)),
+                               (23, (1242, 375), (5000, 1.2, 8, 20, 7)), (24, (400, 300), (150, 1.3, 5, 20, 7))]:
+        img, _ = stereo_frame(seed, w=size[0], h=size[1])
+        monkeypatch.delenv("CORB_OCT_GENERIC", raising=False)
+        fast = ORBextractor(*params)
+        kf, df = fast(img)
+        monkeypatch.setenv("CORB_OCT_GENERIC", "1")
+        gen = ORBextractor(*params)
+        kg, dg = gen(img)
+        monkeypatch.delenv("CORB_OCT_GENERIC", raising=False)
+        okp, odesc = oracle.OrbExtractor(*params)(img)
+        assert kf.tobytes() == kg.tobytes() == okp.tobytes()
+        np.testing.assert_array_equal(df, dg)
+        np.testing.assert_array_equal(df, odesc)
+        fast.close(); gen.close()
+
+
+def test_sparse_and_clustered_keys_fall_back_to_generic_quadtree():
+    """Few corners (fewer than the quota) and tight clusters need quadtree depths beyond the tabulated ones."""
+    img = np.full((375, 1242), 60, np.uint8)
+    rng = np.random.default_rng(5)
+    for _ in range(150):  # isolated bright squares -> a few hundred corners, far fewer than 2000
+        x, y = int(rng.integers(30, 1200)), int(rng.integers(30, 340))
+        img[y:y + 5, x:x + 5] = 200
+    _compare(img)
+    img2 = np.full((375, 1242), 60, np.uint8)
+    for _ in range(400):  # everything inside one 120 x 90 window
+        x, y = int(rng.integers(600, 720)), int(rng.integers(150, 240))
+        img2[y:y + 3, x:x + 3] = int(rng.integers(120, 255))
+    _compare(img2)
