@@ -438,7 +438,7 @@ def run_ours(args):
                                  "note": "corb_frame_stereo: ExtractORB left+right and Frame::ComputeStereoMatches on the GPU; "
                                          "the pyramids never leave HBM"},
             "multi_client": multi,
-            "gpu_launches": 2 * exl.launches_per_extract() * args.steps,
+            "gpu_launches": exl.launches_per_extract() * args.steps,  # one set of launches per stereo pair (grid z = 2)
             "tma": exl.uses_tma(),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -47,7 +47,9 @@ struct corb_orb {
     size_t pyr_bytes = 0;
     int cand_total = 0;
     int key_smem_cap = 0, oct_smem = 0;
-    bool level_graph = false;  // CORB_LEVEL_GRAPH=1: the older per-level pipeline graph (resize chain, per-level FAST/quadtree)
+    bool h2d_node = false;  // CORB_H2D_NODE=1: host images enter through a copy-engine memcpy node instead of k_import's
+                            // loads from mapped host memory (measured equal on B200 + PCIe 5; kept for other hosts)
+    int graph_mode = 0;  // 0: fused pyramid + per-level FAST/quadtree branches, 1: four fused launches, 2: resize chain + branches
     std::vector<void*> dev_allocs;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -59,6 +61,7 @@ struct corb_orb {
 
     // pinned host staging
     uint8_t* h_img = nullptr;       // plan_w * plan_h
+    uint8_t* d_stage = nullptr;     // plan_w * plan_h, tightly packed landing buffer of the H2D node (owned by dev_allocs)
     uint8_t* h_pyr = nullptr;       // pyr_bytes
     corb_keypoint* h_kps = nullptr; // kp_cap
     uint8_t* h_desc = nullptr;      // kp_cap * 32
@@ -241,6 +244,7 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     A(d_alpha, alpha.size());
     A(d_yofs, yofs.size());
     A(d_beta, beta.size());
+    A(h->d_stage, (size_t)w * hgt);
     A(b.cell_count, g.n_cells);
     A(b.cand_xy, h->cand_total);
     A(b.cand_ro, h->cand_total);
@@ -303,7 +307,11 @@ static int make_plan(corb_orb* h, int w, int hgt) {
         cudaError_t pe = prepare_pyramid(b.pyr_plan);
         CORB_CHECK(pe == cudaSuccess, CORB_ERR_CUDA, "pyramid kernel shared memory: %s", cudaGetErrorString(pe));
     }
-    h->level_graph = getenv("CORB_LEVEL_GRAPH") != nullptr;
+    h->h2d_node = getenv("CORB_H2D_NODE") != nullptr;
+    {   // CORB_GRAPH=fused|hybrid selects the alternative per-frame graph shapes (kept for A/B measurements)
+        const char* gm = getenv("CORB_GRAPH");
+        h->graph_mode = gm && !strcmp(gm, "fused") ? 1 : gm && !strcmp(gm, "hybrid") ? 0 : 2;
+    }
     CORB_CUDA(cudaMallocHost(&h->h_img, (size_t)w * hgt));
     CORB_CUDA(cudaMallocHost(&h->h_pyr, h->pyr_bytes));
     CORB_CUDA(cudaMallocHost(&h->h_out, h->out_bytes));
@@ -314,7 +322,7 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     // quadtree: keep a level's keys in shared memory when they fit (typical: 2-3 k keys), else global scratch
     int max_cand_level = 0;
     for (int l = 0; l < h->nlevels; l++) max_cand_level = std::max(max_cand_level, g.lv[l].n_cols * g.lv[l].n_rows * g.lv[l].slot);
-    h->key_smem_cap = std::min(max_cand_level, 8192);
+    h->key_smem_cap = std::min(max_cand_level, 4096);
     cudaError_t e = prepare_octtree(g, h->key_smem_cap, &h->oct_smem);
     if (e != cudaSuccess || h->oct_smem > 200 * 1024) {
         set_error("quadtree kernel needs %d B of shared memory (nfeatures too large?): %s", h->oct_smem, cudaGetErrorString(e));
@@ -339,9 +347,46 @@ static void capture_frame(corb_orb* h, cudaStream_t stream, bool d2h, std::vecto
     const OrbBuffers& b = h->buf;
     const OrbBuffers* b1 = peer ? &peer->buf : nullptr;
     const int L = g.n_levels;
-    // placeholder sources, patched before every launch
-    launch_import(g, b, h->h_img, g.lv[0].w, stream, b1, peer ? peer->h_img : nullptr, g.lv[0].w);
-    if (!h->level_graph) {
+    // placeholder sources, patched before every launch. Host images (the variants that also copy the results back)
+    // come in through the copy engine: a 2D memcpy node per image, which sustains more of the PCIe bandwidth than SM
+    // loads from mapped host memory; device images go through k_import.
+    if (d2h && h->h2d_node) {
+        // (only 1-D memcpy nodes can be re-pointed in an instantiated graph, so the image lands tightly packed in a
+        // staging buffer and k_import re-pitches it from there)
+        const LevelGeom& L0 = g.lv[0];
+        const size_t bytes = (size_t)L0.w * L0.h;
+        cudaMemcpyAsync(h->d_stage, h->h_img, bytes, cudaMemcpyHostToDevice, stream);
+        if (peer) cudaMemcpyAsync(peer->d_stage, peer->h_img, bytes, cudaMemcpyHostToDevice, stream);
+        launch_import(g, b, h->d_stage, L0.w, stream, b1, peer ? peer->d_stage : nullptr, L0.w);
+    } else {
+        launch_import(g, b, h->h_img, g.lv[0].w, stream, b1, peer ? peer->h_img : nullptr, g.lv[0].w);
+    }
+    if (h->graph_mode == 0) {
+        // import -> pyramid (all levels, one launch) -> per level: FAST_l -> quadtree_l -> join -> orient + BRIEF
+        //                                           \-> blur (queued behind the FAST launches) ------/
+        launch_pyramid(g, b, stream, b1);
+        cudaEventRecord(ev[0], stream);
+        for (int l = 0; l < L; l++) {
+            cudaStream_t sl = l == 0 ? stream : ls[l];
+            if (l > 0) cudaStreamWaitEvent(sl, ev[0], 0);
+            launch_fast_cells(g, b, l, sl, b1);
+            if (l == 0) cudaEventRecord(ev[2], sl);
+            launch_octtree(g, b, l, h->key_smem_cap, h->oct_smem, sl, b1);
+            if (l > 0) cudaEventRecord(ev[L + l], sl);
+        }
+        cudaStreamWaitEvent(ls[L], ev[2], 0);  // the blur (low priority) starts once FAST on level 0 is through
+        launch_blur(g, b, ls[L], b1);
+        cudaEventRecord(ev[1], ls[L]);
+        cudaStreamWaitEvent(stream, ev[1], 0);
+        for (int l = 1; l < L; l++) cudaStreamWaitEvent(stream, ev[L + l], 0);
+        launch_orient_desc(g, b, stream, b1);
+        if (d2h) {
+            cudaMemcpyAsync(h->h_out, h->d_out, h->out_bytes, cudaMemcpyDeviceToHost, stream);
+            if (peer) cudaMemcpyAsync(peer->h_out, peer->d_out, peer->out_bytes, cudaMemcpyDeviceToHost, stream);
+        }
+        return;
+    }
+    if (h->graph_mode == 1) {
         // import -> pyramid (all levels, one launch) -> FAST (all cells of all levels) -> quadtree (one CTA per level)
         //                                 \-> blur ----------------------------------------------------/-> orient + BRIEF
         launch_pyramid(g, b, stream, b1);
@@ -384,7 +429,15 @@ struct CaptureScratch {
     int init(int n_streams, int n_events) {
         ls.assign(n_streams, nullptr);
         ev.assign(n_events, nullptr);
-        for (auto& s : ls) CORB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        // kernel nodes inherit the priority of the stream they were captured on: the branches of the coarse levels
+        // (index 0 = level 0) get the highest priority, so their CTAs are not queued behind later, cheaper launches
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least urgent (0), hi = most urgent (negative)
+        ls.push_back(nullptr);  // one extra, least urgent stream (the blur branch)
+        for (size_t i = 0; i < ls.size(); i++) {
+            const int prio = i + 1 == ls.size() ? lo : std::min(lo, hi + (int)i / 2);
+            CORB_CUDA(cudaStreamCreateWithPriority(&ls[i], cudaStreamNonBlocking, prio));
+        }
         for (auto& e : ev) CORB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         return CORB_OK;
     }
@@ -413,15 +466,18 @@ static int find_import_node(cudaGraph_t graph, const uint8_t* dst, cudaGraphNode
     return CORB_OK;
 }
 
+static int find_h2d_node(cudaGraph_t graph, const uint8_t* dst, cudaGraphNode_t* out);
+
 static int record_graph_variant(corb_orb* h, int variant) {
     const int L = h->geom.n_levels;
     CaptureScratch sc;
-    int rc = sc.init(L, 2 * L);
+    int rc = sc.init(L, 2 * L + 3);
     if (rc != CORB_OK) return rc;
     CORB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     capture_frame(h, h->stream, variant == 1, sc.ls, sc.ev);
     CORB_CUDA(cudaStreamEndCapture(h->stream, &h->graph[variant]));
-    rc = find_import_node(h->graph[variant], h->buf.pyr + h->geom.lv[0].img_off, &h->import_node[variant]);
+    rc = variant == 1 && h->h2d_node ? find_h2d_node(h->graph[variant], h->d_stage, &h->import_node[variant])
+                      : find_import_node(h->graph[variant], h->buf.pyr + h->geom.lv[0].img_off, &h->import_node[variant]);
     if (rc != CORB_OK) return rc;
     CORB_CUDA(cudaGraphInstantiate(&h->graph_exec[variant], h->graph[variant], 0));
     return CORB_OK;
@@ -432,12 +488,46 @@ static int record_graph(corb_orb* h) {
         int rc = record_graph_variant(h, v);
         if (rc != CORB_OK) return rc;
     }
-    h->kernel_launches = h->level_graph ? 1 + (h->geom.n_levels - 1) + 2 * h->geom.n_levels + 2 : 6;
+    h->kernel_launches = h->graph_mode == 2 ? 1 + (h->geom.n_levels - 1) + 2 * h->geom.n_levels + 2
+                       : h->graph_mode == 1 ? 6 : 2 + 2 * h->geom.n_levels + 2;
+    return CORB_OK;
+}
+
+// finds the H2D memcpy node that fills `dst` (a handle's staging buffer)
+static int find_h2d_node(cudaGraph_t graph, const uint8_t* dst, cudaGraphNode_t* out) {
+    size_t n_nodes = 0;
+    CORB_CUDA(cudaGraphGetNodes(graph, nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    CORB_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
+    *out = nullptr;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType t;
+        CORB_CUDA(cudaGraphNodeGetType(nd, &t));
+        if (t != cudaGraphNodeTypeMemcpy) continue;
+        cudaMemcpy3DParms mp;
+        CORB_CUDA(cudaGraphMemcpyNodeGetParams(nd, &mp));
+        if (mp.dstPtr.ptr == (void*)dst) *out = nd;
+    }
+    CORB_CHECK(*out, CORB_ERR_CUDA, "H2D node not found in the captured graph");
+    return CORB_OK;
+}
+
+static int patch_memcpy_import(cudaGraphExec_t exec, cudaGraphNode_t node, corb_orb* h, const uint8_t* src, int stride) {
+    const LevelGeom& L0 = h->geom.lv[0];
+    CORB_CHECK(stride == L0.w, CORB_ERR_INVALID, "host images are staged contiguously before the H2D node");
+    CORB_CUDA(cudaGraphExecMemcpyNodeSetParams1D(exec, node, h->d_stage, src, (size_t)L0.w * L0.h, cudaMemcpyHostToDevice));
     return CORB_OK;
 }
 
 static int patch_import(cudaGraphExec_t exec, cudaGraphNode_t node, corb_orb* h, const uint8_t* src, int stride,
-                        corb_orb* peer = nullptr, const uint8_t* src1 = nullptr, int stride1 = 0) {
+                        corb_orb* peer = nullptr, const uint8_t* src1 = nullptr, int stride1 = 0, cudaGraphNode_t node1 = nullptr) {
+    cudaGraphNodeType nt;
+    CORB_CUDA(cudaGraphNodeGetType(node, &nt));
+    if (nt == cudaGraphNodeTypeMemcpy) {
+        int rc = patch_memcpy_import(exec, node, h, src, stride);
+        if (rc == CORB_OK && peer) rc = patch_memcpy_import(exec, node1, peer, src1, stride1);
+        return rc;
+    }
     const LevelGeom& L0 = h->geom.lv[0];
     uint8_t* dst = h->buf.pyr + L0.img_off;
     uint8_t* dst1 = peer ? peer->buf.pyr + L0.img_off : nullptr;
@@ -534,7 +624,7 @@ static int ensure_pair_graph(corb_orb* hl, corb_orb* hr, int variant, float mbf,
     const int L = hl->geom.n_levels;
     if (variant == 2 && (rc = ensure_stereo_buffers(hl)) != CORB_OK) return rc;
     CaptureScratch sl;
-    if ((rc = sl.init(L, 2 * L)) != CORB_OK) return rc;
+    if ((rc = sl.init(L, 2 * L + 3)) != CORB_OK) return rc;
     CORB_CUDA(cudaStreamBeginCapture(hl->stream, cudaStreamCaptureModeThreadLocal));
     capture_frame(hl, hl->stream, variant >= 1, sl.ls, sl.ev, hr);  // both images in every launch (grid z = 2)
     if (variant == 2) {
@@ -546,7 +636,12 @@ static int ensure_pair_graph(corb_orb* hl, corb_orb* hr, int variant, float mbf,
         hl->pair_mb = mb;
     }
     CORB_CUDA(cudaStreamEndCapture(hl->stream, &hl->pair_graph[variant]));
-    if ((rc = find_import_node(hl->pair_graph[variant], hl->buf.pyr + hl->geom.lv[0].img_off, &hl->pair_imp_l[variant])) != CORB_OK) return rc;
+    if (variant >= 1 && hl->h2d_node) {
+        if ((rc = find_h2d_node(hl->pair_graph[variant], hl->d_stage, &hl->pair_imp_l[variant])) != CORB_OK) return rc;
+        if ((rc = find_h2d_node(hl->pair_graph[variant], hr->d_stage, &hl->pair_imp_r[variant])) != CORB_OK) return rc;
+    } else if ((rc = find_import_node(hl->pair_graph[variant], hl->buf.pyr + hl->geom.lv[0].img_off, &hl->pair_imp_l[variant])) != CORB_OK) {
+        return rc;
+    }
     CORB_CUDA(cudaGraphInstantiate(&hl->pair_exec[variant], hl->pair_graph[variant], 0));
     return CORB_OK;
 }
@@ -558,7 +653,7 @@ static void stage_input(corb_orb* h, const uint8_t* img, int w, int hgt, int str
     if (!pinned) cudaGetLastError();
     *src = img;
     *src_stride = stride;
-    if (!pinned) {
+    if (!pinned || (h->h2d_node && stride != w)) {  // the H2D node copies w * hgt contiguous bytes
         if (stride == w) memcpy(h->h_img, img, (size_t)w * hgt);
         else for (int y = 0; y < hgt; y++) memcpy(h->h_img + (size_t)y * w, img + (size_t)y * stride, w);
         *src = h->h_img;
@@ -574,7 +669,8 @@ static int launch_pair(corb_orb* hl, corb_orb* hr, int variant, const uint8_t* s
         CORB_CUDA(cudaStreamWaitEvent(hl->stream, hr->ev_busy, 0));
         hr->own_dirty = false;
     }
-    if ((rc = patch_import(hl->pair_exec[variant], hl->pair_imp_l[variant], hl, src_l, stride_l, hr, src_r, stride_r)) != CORB_OK) return rc;
+    if ((rc = patch_import(hl->pair_exec[variant], hl->pair_imp_l[variant], hl, src_l, stride_l, hr, src_r, stride_r,
+                           hl->pair_imp_r[variant])) != CORB_OK) return rc;
     CORB_CUDA(cudaGraphLaunch(hl->pair_exec[variant], hl->stream));
     hl->own_dirty = true;
     hr->busy_stream = hl->stream;
@@ -662,7 +758,11 @@ int corb_orb_create(int nfeatures, float scale_factor, int nlevels, int ini_th, 
         }
     }
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    {
+        int lo = 0, hi = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, hi);  // level-0 branch runs here
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeom g, PyrPlan p, uint8_t* 
     uint8_t* nxt = psm + p.buf_bytes;
     int* stab = reinterpret_cast<int*>(psm + 2 * p.buf_bytes);
     __shared__ int rng[kMaxLevels][8];  // per level: x own0, own1, need0, need1, y own0, own1, need0, need1
-    __shared__ int toff[kMaxLevels];    // start of level l's staged table slice in stab
+    __shared__ int lvi[kMaxLevels][6];  // per level: w, h, pitch, img_off, xtab_off, ytab_off (read once from the parameters)
     const int tid = threadIdx.x, tx = blockIdx.x, ty = blockIdx.y;
     const int L = g.n_levels;
     if (tid < L * 8) {
@@ -231,74 +231,101 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeom g, PyrPlan p, uint8_t* 
         const int nt = axis ? p.nty : p.ntx, t = axis ? ty : tx;
         const int* sec = p.tab + (axis ? p.yoff[l] : p.xoff[l]);
         rng[l][k] = kk == 0 ? sec[t] : kk == 1 ? sec[t + 1] : kk == 2 ? sec[nt + 1 + t] : sec[2 * nt + 1 + t];
+    } else if (tid >= 128 && tid < 128 + L * 6) {
+        const int l = (tid - 128) / 6, k = (tid - 128) - 6 * l;
+        const LevelGeom& G = g.lv[l];
+        lvi[l][k] = k == 0 ? G.w : k == 1 ? G.h : k == 2 ? G.pitch : k == 3 ? G.img_off : k == 4 ? G.xtab_off : G.ytab_off;
     }
     __syncthreads();
     TR();
     // level 0 (4-byte words of the needed region of the 128-byte pitched level-0 image) and the slices of the resize
     // tables this tile needs on every level are fetched in the same phase: one round of global latency for both
-    const LevelGeom L0 = g.lv[0];
     int pw;  // pitch of `cur`
     int px0 = rng[0][2] & ~3, py0 = rng[0][6];  // origin of `cur` in level coordinates
     {
         const int nh = rng[0][7] - py0 + 1;
         const int nwords = ((rng[0][3] - px0) >> 2) + 1;
         pw = nwords * 4;
-        const uint8_t* s0 = pyr + L0.img_off + (size_t)py0 * L0.pitch + px0;
+        const int pitch0 = lvi[0][2];
+        const uint8_t* s0 = pyr + lvi[0][3] + (size_t)py0 * pitch0 + px0;
         const int lanes = tid & 31, rows = tid >> 5;
         for (int yy = rows; yy < nh; yy += 8)
             for (int xx = lanes; xx < nwords; xx += 32)
-                reinterpret_cast<uint32_t*>(cur)[yy * nwords + xx] = *reinterpret_cast<const uint32_t*>(s0 + (size_t)yy * L0.pitch + 4 * xx);
+                reinterpret_cast<uint32_t*>(cur)[yy * nwords + xx] = *reinterpret_cast<const uint32_t*>(s0 + (size_t)yy * pitch0 + 4 * xx);
     }
-    {
+    // start of level l's staged table slice in stab
+    auto slice_off = [&](int l) {
         int o = 0;
-        for (int l = 1; l < L; l++) {
-            const LevelGeom& D = g.lv[l];
+        for (int k = 1; k < l; k++) o += 2 * (max(rng[k][3] - rng[k][2] + 1, 0) + max(rng[k][7] - rng[k][6] + 1, 0));
+        return o;
+    };
+    {
+        // warp w stages level w + 1 (and w + 9 ...): the levels' loads are in flight together
+        for (int l = 1 + (tid >> 5); l < L; l += 8) {
             const int x0 = rng[l][2], nw = rng[l][3] - x0 + 1, y0 = rng[l][6], nh = rng[l][7] - y0 + 1;
-            if (nw <= 0 || nh <= 0) break;
-            if (tid == 0) toff[l] = o;
-            int* t = stab + o;
-            for (int i = tid; i < nw + nh; i += 256) {
+            if (nw <= 0 || nh <= 0) continue;
+            int* t = stab + slice_off(l);
+            const int xo = lvi[l][4] + x0, yo = lvi[l][5] + y0;
+            for (int i = tid & 31; i < nw + nh; i += 32) {
                 if (i < nw) {
-                    t[i] = xofs[D.xtab_off + x0 + i];
-                    t[nw + i] = *reinterpret_cast<const int*>(&alpha[D.xtab_off + x0 + i]);
+                    t[i] = xofs[xo + i];
+                    t[nw + i] = *reinterpret_cast<const int*>(&alpha[xo + i]);
                 } else {
                     const int j = i - nw;
-                    t[2 * nw + j] = yofs[D.ytab_off + y0 + j];
-                    t[2 * nw + nh + j] = *reinterpret_cast<const int*>(&beta[D.ytab_off + y0 + j]);
+                    t[2 * nw + j] = yofs[yo + j];
+                    t[2 * nw + nh + j] = *reinterpret_cast<const int*>(&beta[yo + j]);
                 }
             }
-            o += 2 * (nw + nh);
         }
     }
     __syncthreads();
     TR();
+    int toff = 0;
+#pragma unroll 1
     for (int l = 1; l < L; l++) {
-        const LevelGeom D = g.lv[l];
         const int x0 = rng[l][2], nw = rng[l][3] - x0 + 1, y0 = rng[l][6], nh = rng[l][7] - y0 + 1;
         if (nw <= 0 || nh <= 0) break;  // deeper levels need nothing either
         const int ox0 = rng[l][0], ox1 = rng[l][1], oy0 = rng[l][4], oy1 = rng[l][5];
-        const int sw = g.lv[l - 1].w, sh = g.lv[l - 1].h;
-        const int* t = stab + toff[l];
-        uint8_t* dst = pyr + D.img_off;
-        for (int yy = tid >> 5; yy < nh; yy += 8)
-        for (int xx = tid & 31; xx < nw; xx += 32) {
-            const int i = yy * nw + xx;
+        const int sw = lvi[l - 1][0], sh = lvi[l - 1][1];
+        const int dpitch = lvi[l][2];
+        const int* t = stab + toff;
+        toff += 2 * (nw + nh);
+        uint8_t* dst = pyr + lvi[l][3];
+        // thread = (column, row group); four rows per batch so that their shared-memory loads overlap
+        const int nwp = (nw + 31) & ~31;
+        const int xx = tid % nwp, yg = tid / nwp, ystep = 256 / nwp;
+        if (xx < nw && yg < ystep) {
             const int sx = t[xx];
             const int sx1 = min(sx + 1, sw - 1);
             const int aw = t[nw + xx];
             const int a0 = (short)(aw & 0xffff), a1 = aw >> 16;
-            const int sy = t[2 * nw + yy];
-            const int sy0 = min(max(sy, 0), sh - 1), sy1 = min(max(sy + 1, 0), sh - 1);
-            const int bw = t[2 * nw + nh + yy];
-            const int b0 = (short)(bw & 0xffff), b1 = bw >> 16;
-            const uint8_t* r0p = cur + (sy0 - py0) * pw - px0;
-            const uint8_t* r1p = cur + (sy1 - py0) * pw - px0;
-            const int r0 = (int)r0p[sx] * a0 + (int)r0p[sx1] * a1;
-            const int r1 = (int)r1p[sx] * a0 + (int)r1p[sx1] * a1;
-            const int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-            nxt[i] = (uint8_t)v;
-            const int dx = x0 + xx, dy = y0 + yy;
-            if (dx >= ox0 && dx < ox1 && dy >= oy0 && dy < oy1) dst[(size_t)dy * D.pitch + dx] = (uint8_t)v;
+            const int dx = x0 + xx;
+            const bool own_x = dx >= ox0 && dx < ox1;
+            for (int yb = yg; yb < nh; yb += 4 * ystep) {
+                int v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int yy = min(yb + u * ystep, nh - 1);
+                    const int sy = t[2 * nw + yy];
+                    const int sy0 = min(max(sy, 0), sh - 1), sy1 = min(max(sy + 1, 0), sh - 1);
+                    const int bw = t[2 * nw + nh + yy];
+                    const int b0 = (short)(bw & 0xffff), b1 = bw >> 16;
+                    const uint8_t* r0p = cur + (sy0 - py0) * pw - px0;
+                    const uint8_t* r1p = cur + (sy1 - py0) * pw - px0;
+                    const int r0 = (int)r0p[sx] * a0 + (int)r0p[sx1] * a1;
+                    const int r1 = (int)r1p[sx] * a0 + (int)r1p[sx1] * a1;
+                    v[u] = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int yy = yb + u * ystep;
+                    if (yy < nh) {
+                        nxt[yy * nw + xx] = (uint8_t)v[u];
+                        const int dy = y0 + yy;
+                        if (own_x && dy >= oy0 && dy < oy1) dst[(size_t)dy * dpitch + dx] = (uint8_t)v[u];
+                    }
+                }
+            }
         }
         __syncthreads();
         TR();
@@ -512,6 +539,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_cons
     for (int attempt = 0; attempt < 2; attempt++) {
         for (int i = tid; i < kScDim * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(sc)[i] = 0;
         if (tid == 0) n_surv = 0;
+        if (tid < 128) row_ini[tid] = 0;
         __syncthreads();
         for (int y = warp; y < vh; y += 8) {
 #pragma unroll
@@ -542,22 +570,17 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_cons
         }
         __syncthreads();
         TR();
-        // strict 8-neighbour maxima of the score tile (non-corners are 0); per row two ballot words
+        // strict 8-neighbour maxima of the score tile (non-corners are 0). Only pixels of the survivor list can have a
+        // non-zero score, so only those are tested; their bits go into two mask words per row.
         bool any_local = false;
-        for (int y = warp; y < vh; y += 8) {
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const int x = lane + 32 * half;
-                bool f = false;
-                if (x < vw) {
-                    const uint8_t* q = sc + (y + 1) * kScPitch + (x + 1);
-                    const int s = q[0];
-                    f = s != 0 && s > q[-kScPitch - 1] && s > q[-kScPitch] && s > q[-kScPitch + 1] && s > q[-1] && s > q[1] &&
-                        s > q[kScPitch - 1] && s > q[kScPitch] && s > q[kScPitch + 1];
-                }
-                const uint32_t bm = __ballot_sync(0xffffffffu, f);
-                if (lane == 0) row_ini[y * 2 + half] = bm;
-                any_local |= bm != 0;
+        for (int i = tid; i < ns; i += 256) {
+            const int y = surv[i] >> 6, x = surv[i] & 63;
+            const uint8_t* q = sc + (y + 1) * kScPitch + (x + 1);
+            const int s = q[0];
+            if (s != 0 && s > q[-kScPitch - 1] && s > q[-kScPitch] && s > q[-kScPitch + 1] && s > q[-1] && s > q[1] &&
+                s > q[kScPitch - 1] && s > q[kScPitch] && s > q[kScPitch + 1]) {
+                atomicOr(&row_ini[y * 2 + (x >> 5)], 1u << (x & 31));
+                any_local = true;
             }
         }
         const int any = __syncthreads_or(any_local);
@@ -751,6 +774,8 @@ struct OctLayout {
 constexpr int kOctDh = 5;
 constexpr int kOctFastMaxIni = 8;
 constexpr int kOctSmemLimit = 200 * 1024;
+// f_flag doubles as the bins of the counting sort of the near-quota rounds: (warps + 1) x 256 ints
+__host__ __device__ inline int kOctFlagInts(int TC) { return TC + 4 > (CORB_OCT_THREADS / 32 + 1) * 256 ? TC + 4 : (CORB_OCT_THREADS / 32 + 1) * 256; }
 __host__ __device__ inline int oct_depth_off(int n_ini, int d) { return n_ini * (((1 << (2 * d)) - 1) / 3); }
 __host__ __device__ inline OctLayout oct_layout(int NC, int key_cap, int n_lut, int n_ini) {
     OctLayout o;
@@ -778,16 +803,16 @@ __host__ __device__ inline OctLayout oct_layout(int NC, int key_cap, int n_lut, 
     o.f_hist = o.f_code = o.f_owner = o.f_flag = o.f_stat = o.f_lut = 0;
     const int HC = n_ini << (2 * kOctDh), TC = oct_depth_off(n_ini, kOctDh + 1);
     {   // the closed-form tables are optional: keep them only while the whole layout stays inside kOctSmemLimit
-        const int extra = 4 * (HC + 4) + 4 * (TC + 4) + 64 + 2 * key_cap + 2 * HC + 2 * (n_lut + 2) + 6 * 16;
+        const int extra = 4 * (HC + 4) + 4 * kOctFlagInts(TC) + 64 + 2 * (n_lut + 2) + 4 * 16;
         o.fast = n_ini <= kOctFastMaxIni && p + extra <= kOctSmemLimit;
     }
     if (o.fast) {
         OCT_ALLOC(f_hist, 4 * (HC + 4));
-        OCT_ALLOC(f_flag, 4 * (TC + 4));
+        OCT_ALLOC(f_flag, 4 * kOctFlagInts(TC));
         OCT_ALLOC(f_stat, 4 * 16);
-        OCT_ALLOC(f_code, 2 * key_cap);
-        OCT_ALLOC(f_owner, 2 * HC);
         OCT_ALLOC(f_lut, 2 * (n_lut + 2));
+        o.f_code = o.keys_node;  // a key's depth-Dh cell is replaced in place by the list position of its node
+        o.f_owner = o.f_flag;    // the cell -> node map is built after the last use of the flag / bin array (2 HC <= its size)
     }
 #undef OCT_ALLOC
     o.total = p;
@@ -1091,20 +1116,44 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
                 for (int i = tid; i < m; i += nt) scan[i] = cnt_cur[krank[i]];  // candidate counts, contiguous
                 if (tid == 0) { sh[0] = m; sh[1] = 0; }
                 __syncthreads();
-                // processing order: count descending, position ascending. Four lanes share one candidate.
-                for (int i0 = 0; i0 < m; i0 += nt / 4) {
-                    const int i = i0 + (tid >> 2), sub = tid & 3;
-                    int rank = 0;
-                    if (i < m) {
+                // processing order: count descending, position ascending = a stable counting sort on the count.
+                // Per-warp bins (match_any gives the rank among equal counts inside a warp), a prefix over the warps
+                // per bin, and a scan over the bins from the largest count down. Counts >= 256 or more than one
+                // candidate per thread (never seen on images) take the quadratic ranking instead.
+                const int cmax = __syncthreads_or(tid < m && scan[tid] >= 256);
+                if (!cmax && m <= nt) {
+                    int* wh = fflag;              // [nw][256] per-warp bin counts -> exclusive prefix over warps
+                    int* tot = fflag + (nt >> 5) * 256;  // [256] reversed bin totals -> exclusive scan
+                    const int nwarp = nt >> 5, wid = tid >> 5, lane = tid & 31;
+                    for (int i = tid; i < (nwarp + 1) * 64; i += nt) reinterpret_cast<int4*>(wh)[i] = make_int4(0, 0, 0, 0);
+                    __syncthreads();
+                    const int ci = tid < m ? scan[tid] : -1;
+                    const unsigned peers = __match_any_sync(0xffffffffu, ci);
+                    const int in_warp = __popc(peers & ((1u << lane) - 1u));
+                    if (ci >= 0 && in_warp == 0) wh[wid * 256 + ci] = __popc(peers);
+                    __syncthreads();
+                    if (tid < 256) {
+                        int acc = 0;
+                        for (int w = 0; w < nwarp; w++) {
+                            const int t = wh[w * 256 + tid];
+                            wh[w * 256 + tid] = acc;
+                            acc += t;
+                        }
+                        tot[255 - tid] = acc;
+                    }
+                    __syncthreads();
+                    block_excl_scan4(tot, 256, warp_tmp);
+                    if (ci >= 0) procpos[tot[255 - ci] + wh[wid * 256 + ci] + in_warp] = krank[tid];
+                } else {
+                    for (int i = tid; i < m; i += nt) {
                         const int ci = scan[i];
-                        for (int j = sub; j < m; j += 4) {
+                        int rank = 0;
+                        for (int j = 0; j < m; j++) {
                             const int cj = scan[j];
                             rank += (cj > ci) || (cj == ci && j < i);
                         }
+                        procpos[rank] = krank[i];
                     }
-                    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-                    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-                    if (i < m && sub == 0) procpos[rank] = krank[i];
                 }
                 __syncthreads();
     OCT_T(10);

@@ -40,7 +40,11 @@ class ORBextractor:
             lib().corb_orb_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals are already gone, the process frees the device memory
+            pass
 
     # ---- getters (ORBextractor.h:63-85)
     def GetLevels(self):
