@@ -43,7 +43,8 @@ class BaResult(C.Structure):
                 ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_initial", C.c_double),
                 ("lambda_final", C.c_double), ("trial_accepted", C.c_uint8 * 256), ("trial_chi2", C.c_double * 256),
                 ("ms_total", C.c_double), ("ms_solve", C.c_double), ("reduced_blocks", C.c_int64),
-                ("border_poses", C.c_int32), ("max_active_rows", C.c_int32)]
+                ("border_poses", C.c_int32), ("max_active_rows", C.c_int32), ("ms_setup", C.c_double),
+                ("band_chunks", C.c_int32), ("separator_poses", C.c_int32)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, vp, vp, C.c_size_t, C.c_int, vp)

@@ -18,7 +18,12 @@
 #include <algorithm>
 #include <chrono>
 #include <numeric>
+#include <mutex>
+#include <thread>
 #include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -135,7 +140,11 @@ struct BaDev {
     const int *pose_off, *pose_edges;  // CSR by pose: positions into the landmark-sorted edge arrays
     double *Hpp, *bp, *Hll, *bl, *W, *Dinv, *db;
     const int *first, *rowoff, *coloff, *col_rows;
+    const int *coloff_b, *col_rows_b;
+    const int *chunk_start;        // [n_chunks + 1] band columns of each independent chunk
+    double *bpart;                 // [n_border][n_chunks][6] per-chunk parts of the border rows' forward substitution  // same lists without the border rows in the band columns (bordered solve)
     double *S, *bs;                // reduced system: [S | bs] contiguous
+    double *invd;                  // [Pf * 6] reciprocals of the diagonal of the Cholesky factor (triangular solves multiply)
     double *xp, *xl;
     double *partial, *scalars;     // reduction scratch; scalars[0] chi2, [1] scale part, [2] xx, [3] max diag, [4] fail flag
     int robust;
@@ -405,7 +414,10 @@ __global__ void __launch_bounds__(256) k_ba_add_lambda(BaDev d, double lambda) {
 //        C: warp 0 updates and factors the next diagonal block while the other warps apply the trailing update
 //           A_ji -= L_jk L_ik^T over all active pairs from shared memory (4 pairs in flight per warp to cover the
 //           L2 round trip of the read-modify-write) and b_j -= L_jk y_k
-constexpr int kSolveThreads = 1024;
+#ifndef CORB_BA_THREADS
+#define CORB_BA_THREADS 1024
+#endif
+constexpr int kSolveThreads = CORB_BA_THREADS;
 constexpr int kSolveWarps = kSolveThreads / 32;
 
 __device__ __forceinline__ bool chol6(double* a) {  // in place, lower; upper part zeroed
@@ -435,13 +447,19 @@ __device__ __forceinline__ bool chol6(double* a) {  // in place, lower; upper pa
 // Warp-cooperative update + Cholesky of one 6x6 diagonal block: lane t < 21 owns entry (r, c), r >= c, of the lower
 // triangle in a register; columns are finalised with shuffles (no local-memory arrays on the sequential critical path).
 // D <- chol(D - L0 L0^T) (L0 == nullptr: no update), result also written to Lout (full 6x6, upper part zero).
-__device__ __forceinline__ bool warp_chol6(double* D, const double* L0, double* Lout, int lane) {
+// `a_pre` (optional) = this lane's entry of D, loaded earlier to take the L2 round trip off the sequential path.
+// The reciprocals 1 / L_kk go to inv_out[6] (and inv_glob): every triangular solve against this block multiplies by
+// them instead of dividing (fp64 division is a ~250-cycle software sequence on the critical path of each column).
+// 1 / sqrt(a) is rsqrt(a) (1 ulp) and L_kk = a * rsqrt(a): two roundings instead of sqrt's one, far below the 1e-5 px
+// tolerance of the BA parity tests.
+__device__ __forceinline__ bool warp_chol6(double* D, const double* L0, double* Lout, int lane, double* inv_out, double* inv_glob,
+                                           bool have_pre = false, double a_pre = 0.0) {
     int r = 0, c = 0;
     if (lane < 21) {
         r = lane >= 15 ? 5 : lane >= 10 ? 4 : lane >= 6 ? 3 : lane >= 3 ? 2 : lane >= 1 ? 1 : 0;
         c = lane - r * (r + 1) / 2;
     }
-    double a = lane < 21 ? D[r * 6 + c] : 0.0;
+    double a = have_pre ? a_pre : (lane < 21 ? D[r * 6 + c] : 0.0);
     if (L0 && lane < 21) {
         double s = 0;
 #pragma unroll
@@ -453,7 +471,8 @@ __device__ __forceinline__ bool warp_chol6(double* D, const double* L0, double* 
     for (int k = 0; k < 6; k++) {
         double akk = __shfl_sync(0xffffffffu, a, k * (k + 1) / 2 + k);
         if (!(akk > 0.0)) { ok = false; akk = 1.0; }
-        const double dk = sqrt(akk), inv = 1.0 / dk;
+        const double inv = rsqrt(akk), dk = akk * inv;
+        if (lane == 0) { inv_out[k] = inv; inv_glob[k] = inv; }
         if (lane < 21 && c == k) a = (r == k) ? dk : a * inv;
         const double lrk = __shfl_sync(0xffffffffu, a, r * (r + 1) / 2 + min(k, r));
         const double lck = __shfl_sync(0xffffffffu, a, c * (c + 1) / 2 + min(k, c));
@@ -467,41 +486,84 @@ __device__ __forceinline__ bool warp_chol6(double* D, const double* L0, double* 
     return ok;
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_cap, int k_begin, int k_end, int n_band, int flags) {
+__global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_cap, int k_begin, int k_end, int n_band, int flags,
+                                                             int stage_nnz) {
     // flags: 1 = first launch (load b, clear the failure flag), 2 = defer border x border updates to k_ba_border_syrk,
-    //        4 = run the backward substitution after the last column
+    //        4 = run the backward substitution after the last column, 8 = band columns see band rows only (the border rows
+    //        are swept by k_ba_border_rows), 16 = backward over the border rows only (j >= n_band), 32 = no factorisation,
+    //        backward over the band rows only (j < n_band)
     extern __shared__ double Lact[];  // [lact_cap][36] staged L_jk of the active rows of the current column
     __shared__ double Lkk[2][36];
+    __shared__ double Lki[2][6];  // reciprocals of the diagonal of L_kk
     __shared__ double yk[6];
     __shared__ int s_fail;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = d.Pf;
+    // The envelope index arrays sit on the address path of every block access (column list -> row -> row offset ->
+    // block): read from global memory that is three dependent L2 round trips per column before the first operand
+    // arrives. When they fit (stage_nnz >= 0) they are copied behind Lact once.
+    const int* firstp = d.first;
+    const int* rowoffp = d.rowoff;
+    const int* coloffp = (flags & 8) ? d.coloff_b : d.coloff;
+    const int* colrowsp = (flags & 8) ? d.col_rows_b : d.col_rows;
+    if (stage_nnz >= 0) {
+        int* sidx = reinterpret_cast<int*>(Lact + (size_t)lact_cap * 36);
+        int* sfirst = sidx, *srowoff = sidx + n, *scoloff = sidx + 2 * n, *scolrows = sidx + 3 * n + 1;
+        for (int i = tid; i < n; i += kSolveThreads) { sfirst[i] = firstp[i]; srowoff[i] = rowoffp[i]; }
+        for (int i = tid; i <= n; i += kSolveThreads) scoloff[i] = coloffp[i];
+        for (int i = tid; i < stage_nnz; i += kSolveThreads) scolrows[i] = colrowsp[i];
+        firstp = sfirst; rowoffp = srowoff; coloffp = scoloff; colrowsp = scolrows;
+    }
+    if (flags & 64) {  // one CTA per independent band chunk
+        k_begin = d.chunk_start[blockIdx.x];
+        k_end = d.chunk_start[blockIdx.x + 1];
+    }
     if (tid == 0) s_fail = (flags & 1) ? 0 : (d.scalars[4] != 0.0);
-    if (flags & 1)
-        for (int i = tid; i < n * 6; i += kSolveThreads) d.xp[i] = d.bs[i];
-    __syncthreads();
-    if (warp == 0 && k_begin < k_end && !s_fail) {
-        double* D = d.S + (size_t)(d.rowoff[k_begin] + k_begin - d.first[k_begin]) * 36;
-        if (!warp_chol6(D, nullptr, Lkk[k_begin & 1], lane) && lane == 0) s_fail = 1;
+    if (flags & 1) {
+        if (flags & 64) {
+            for (int i = k_begin * 6 + tid; i < k_end * 6; i += kSolveThreads) d.xp[i] = d.bs[i];
+            if (blockIdx.x == 0)
+                for (int i = n_band * 6 + tid; i < n * 6; i += kSolveThreads) d.xp[i] = d.bs[i];
+        } else {
+            for (int i = tid; i < n * 6; i += kSolveThreads) d.xp[i] = d.bs[i];
+        }
     }
     __syncthreads();
-    for (int k = k_begin; k < k_end; k++) {
+    if (warp == 0 && k_begin < k_end && !s_fail && !(flags & 32)) {
+        double* D = d.S + (size_t)(rowoffp[k_begin] + k_begin - firstp[k_begin]) * 36;
+        if (!warp_chol6(D, nullptr, Lkk[k_begin & 1], lane, Lki[k_begin & 1], d.invd + (size_t)k_begin * 6) && lane == 0) s_fail = 1;
+    }
+    __syncthreads();
+#ifdef CORB_BA_TRACE
+    long long trB = 0, trC = 0, trT = clock64(), nact_sum = 0, trBw = 0, trChol = 0;
+#endif
+    for (int k = k_begin; k < ((flags & 32) ? k_begin : k_end); k++) {
         if (s_fail) break;
+#ifdef CORB_BA_TRACE
+        const long long trs = clock64();
+#endif
         const double* Lk = Lkk[k & 1];
-        const int cb = d.coloff[k], nact = d.coloff[k + 1] - cb;
-        const int* rows = d.col_rows + cb;
+        const double* Li = Lki[k & 1];
+        const int cb = coloffp[k], nact = coloffp[k + 1] - cb;
+        const int* rows = colrowsp + cb;
         const bool staged = nact <= lact_cap;
-        // ---- phase B
+        // ---- phase B (warp 0 has no rows here when there are other warps: it fetches its entry of the next diagonal block)
+        double dpre = 0.0;
+        if (warp == 0 && k + 1 < k_end && lane < 21) {
+            const int rr = lane >= 15 ? 5 : lane >= 10 ? 4 : lane >= 6 ? 3 : lane >= 3 ? 2 : lane >= 1 ? 1 : 0;
+            const int cc = lane - rr * (rr + 1) / 2;
+            dpre = d.S[(size_t)(rowoffp[k + 1] + (k + 1) - firstp[k + 1]) * 36 + rr * 6 + cc];
+        }
         for (int it = tid; it < nact * 6; it += kSolveThreads) {
             const int a = it / 6, r = it - a * 6;
             const int j = rows[a];
-            double* B = d.S + (size_t)(d.rowoff[j] + k - d.first[j]) * 36 + r * 6;
+            double* B = d.S + (size_t)(rowoffp[j] + k - firstp[j]) * 36 + r * 6;
             double v[6];
 #pragma unroll
             for (int c = 0; c < 6; c++) {
                 double s = B[c];
 #pragma unroll
                 for (int p = 0; p < c; p++) s -= v[p] * Lk[c * 6 + p];
-                v[c] = s / Lk[c * 6 + c];
+                v[c] = s * Li[c];
             }
 #pragma unroll
             for (int c = 0; c < 6; c++) B[c] = v[c];
@@ -517,25 +579,36 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
                 double s = d.xp[k * 6 + r];
 #pragma unroll
                 for (int p = 0; p < r; p++) s -= Lk[r * 6 + p] * v[p];
-                v[r] = s / Lk[r * 6 + r];
+                v[r] = s * Li[r];
             }
 #pragma unroll
             for (int r = 0; r < 6; r++) { d.xp[k * 6 + r] = v[r]; yk[r] = v[r]; }
         }
+#ifdef CORB_BA_TRACE
+        const long long trb1 = clock64();
+#endif
         __syncthreads();
+#ifdef CORB_BA_TRACE
+        const long long trm = clock64();
+        trB += trb1 - trs; trBw += trm - trb1; nact_sum += nact;
+#endif
         // ---- phase C
         const bool next_active = nact > 0 && rows[0] == k + 1;  // rows ascend, so k+1 can only be the first entry
         if (warp == 0) {
             if (k + 1 < k_end) {
-                double* D = d.S + (size_t)(d.rowoff[k + 1] + (k + 1) - d.first[k + 1]) * 36;
-                const double* L0 = !next_active ? nullptr : staged ? Lact : d.S + (size_t)(d.rowoff[k + 1] + k - d.first[k + 1]) * 36;
-                if (!warp_chol6(D, L0, Lkk[(k + 1) & 1], lane) && lane == 0) s_fail = 1;
+                double* D = d.S + (size_t)(rowoffp[k + 1] + (k + 1) - firstp[k + 1]) * 36;
+                const double* L0 = !next_active ? nullptr : staged ? Lact : d.S + (size_t)(rowoffp[k + 1] + k - firstp[k + 1]) * 36;
+                if (!warp_chol6(D, L0, Lkk[(k + 1) & 1], lane, Lki[(k + 1) & 1], d.invd + (size_t)(k + 1) * 6, true, dpre) && lane == 0)
+                    s_fail = 1;
             }
+#ifdef CORB_BA_TRACE
+            trChol += clock64() - trm;
+#endif
         } else if (warp == 1) {  // b_j -= L_jk y_k
             for (int it = lane; it < nact * 6; it += 32) {
                 const int a = it / 6, r = it - a * 6;
                 const int j = rows[a];
-                const double* Lr = staged ? Lact + a * 36 + r * 6 : d.S + (size_t)(d.rowoff[j] + k - d.first[j]) * 36 + r * 6;
+                const double* Lr = staged ? Lact + a * 36 + r * 6 : d.S + (size_t)(rowoffp[j] + k - firstp[j]) * 36 + r * 6;
                 double s = 0;
 #pragma unroll
                 for (int c = 0; c < 6; c++) s += Lr[c] * yk[c];
@@ -564,7 +637,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
                         if (defer && rows[b] >= n_band) continue;  // rows ascend: b is the smaller row of the pair
                         pa[u] = a;
                         pb[u] = b;
-                        toff[u] = (d.rowoff[j] + rows[b] - d.first[j]) * 36;
+                        toff[u] = (rowoffp[j] + rows[b] - firstp[j]) * 36;
                         t0[u] = d.S[(size_t)toff[u] + lane];
                         t1[u] = lane < 4 ? d.S[(size_t)toff[u] + 32 + lane] : 0.0;
                     }
@@ -573,8 +646,8 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
                 for (int u = 0; u < U; u++) {
                     if (toff[u] >= 0) {
                         const int ja = rows[pa[u]], jb = rows[pb[u]];
-                        const double* La = staged ? Lact + pa[u] * 36 : d.S + (size_t)(d.rowoff[ja] + k - d.first[ja]) * 36;
-                        const double* Lb = staged ? Lact + pb[u] * 36 : d.S + (size_t)(d.rowoff[jb] + k - d.first[jb]) * 36;
+                        const double* La = staged ? Lact + pa[u] * 36 : d.S + (size_t)(rowoffp[ja] + k - firstp[ja]) * 36;
+                        const double* Lb = staged ? Lact + pb[u] * 36 : d.S + (size_t)(rowoffp[jb] + k - firstp[jb]) * 36;
                         double s0 = 0, s1 = 0;
 #pragma unroll
                         for (int q = 0; q < 6; q++) s0 += La[r0 * 6 + q] * Lb[c0 * 6 + q];
@@ -589,18 +662,28 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
             }
         }
         __syncthreads();
+#ifdef CORB_BA_TRACE
+        trC += clock64() - trm;
+#endif
     }
+#ifdef CORB_BA_TRACE
+    if (tid == 0 && k_end > k_begin)
+        printf("k_ba_solve cols %d..%d: phase B work %lld + barrier wait %lld cyc/col, phase C %lld (chol %lld) cyc/col, mean nact %.1f, total %lld cyc\n", k_begin, k_end,
+               trB / (k_end - k_begin), trBw / (k_end - k_begin), trC / (k_end - k_begin), trChol / (k_end - k_begin), (double)nact_sum / (k_end - k_begin), clock64() - trT);
+    const long long trb0 = clock64();
+#endif
     if (s_fail) {
         for (int i = tid; i < n * 6; i += kSolveThreads) d.xp[i] = 0.0;
         if (tid == 0) d.scalars[4] = 1.0;
         return;
     }
-    if (tid == 0) d.scalars[4] = 0.0;
+    if (tid == 0 && !(flags & 64)) d.scalars[4] = 0.0;  // (chunk CTAs only ever raise the flag; the host clears it)
     if (!(flags & 4)) return;
     // ---- backward: L^T x = y (row oriented); xp already holds y from the fused forward pass
-    for (int j = n - 1; j >= 0; j--) {
-        const int fj = d.first[j];
-        const double* rowp = d.S + (size_t)d.rowoff[j] * 36;
+    const int j_hi = (flags & 32) ? n_band - 1 : n - 1, j_lo = (flags & 16) ? n_band : 0;
+    for (int j = j_hi; j >= j_lo; j--) {
+        const int fj = firstp[j];
+        const double* rowp = d.S + (size_t)rowoffp[j] * 36;
         const double* D = rowp + (size_t)(j - fj) * 36;
         if (tid == 0) {
             double v[6];
@@ -609,7 +692,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
                 double s = d.xp[j * 6 + r];
 #pragma unroll
                 for (int p = r + 1; p < 6; p++) s -= D[p * 6 + r] * v[p];
-                v[r] = s / D[r * 6 + r];
+                v[r] = s * d.invd[j * 6 + r];
             }
 #pragma unroll
             for (int r = 0; r < 6; r++) { d.xp[j * 6 + r] = v[r]; yk[r] = v[r]; }
@@ -625,6 +708,265 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
         }
         __syncthreads();
     }
+#ifdef CORB_BA_TRACE
+    if (tid == 0) printf("k_ba_solve backward over %d rows: %lld cyc\n", n, clock64() - trb0);
+#endif
+}
+
+// ---- K12c: the border rows (keyframes with long-range links, ordered last) against the finished band factor.
+//      L_jk = (A_jk - sum_{c<k} L_jc L_kc^T) L_kk^-T only needs row j itself and the band rows, so every border row is
+//      swept left to right on its own: one small CTA per border row, all rows concurrently, instead of riding along as
+//      active rows of every band column in the one-CTA sweep (they were 80 % of its active rows). Per entry the
+//      updates are subtracted in ascending column order with the same 6-term sums as the right-looking sweep, and the
+//      right-hand side follows the same way (b_j -= L_jk y_k), so the result is bit-identical to it.
+//      Operands of column k + 1 (A_j,k+1, the L_k+1,c blocks, L_k+1,k+1, y_k+1) do not depend on the running row and
+//      are fetched while column k is computed.
+__global__ void __launch_bounds__(64) k_ba_border_rows(BaDev d, int n_band, int wmax, int stage) {
+    // wmax = longest band envelope (blocks left of the diagonal); dynamic shared memory: ring[wmax + 1] | Lkc[2][wmax]
+    extern __shared__ double bsm[];
+    const int kBorderRing = wmax + 1;
+    double (*ring)[36] = reinterpret_cast<double (*)[36]>(bsm);  // L_jc of the last columns, slot c % kBorderRing
+    double (*Lkc0)[36] = reinterpret_cast<double (*)[36]>(bsm + (size_t)kBorderRing * 36);  // band blocks L_kc, c = lo..k-1,
+    double (*Lkc1)[36] = Lkc0 + wmax;                                                       // of the column computed / fetched
+    __shared__ double Lkk[2][36];
+    __shared__ double yk[2][6];
+    __shared__ double Lki[2][6];
+    __shared__ double T[36];
+    const int j = n_band + blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nq = gridDim.y, q = blockIdx.y;  // this CTA sweeps the columns of band chunk q only (chunks are decoupled)
+#ifdef CORB_BA_TRACE
+    const long long tr0 = clock64();
+#endif
+    if (d.scalars[4] != 0.0) return;  // the band factorisation failed
+    // first / rowoff of the band rows sit on the address path of every fetch: staged in shared memory when they fit
+    const int* firstp = d.first;
+    const int* rowoffp = d.rowoff;
+    if (stage) {
+        int* sidx = reinterpret_cast<int*>(Lkc1 + wmax);
+        for (int i = tid; i < n_band; i += 64) { sidx[i] = d.first[i]; sidx[n_band + i] = d.rowoff[i]; }
+        firstp = sidx;
+        rowoffp = sidx + n_band;
+        __syncthreads();
+    }
+    const int fj = d.first[j];
+    double* rowp = d.S + (size_t)d.rowoff[j] * 36;  // block of column k at rowp + (k - fj) * 36
+    const int r = tid / 6, c0 = tid - r * 6;
+    // Operands of a column are fetched into registers while the previous column is computed and committed to the
+    // shared buffers afterwards (a shared-memory store right behind its load would stall the in-order thread for the
+    // whole L2 round trip). Up to kPre band blocks travel in registers; longer envelopes commit directly.
+    constexpr int kPre = 6;
+    double pa = 0, pkk = 0, py = 0, pl[kPre];
+    auto fetch_issue = [&](int k, int buf) {
+        const int fk = firstp[k];
+        const int lo = max(fj, fk);
+        const double* bandrow = d.S + (size_t)rowoffp[k] * 36;
+        if (tid < 36) {
+            pa = rowp[(size_t)(k - fj) * 36 + tid];
+            pkk = bandrow[(size_t)(k - fk) * 36 + tid];
+#pragma unroll
+            for (int i = 0; i < kPre; i++) pl[i] = lo + i < k ? bandrow[(size_t)(lo + i - fk) * 36 + tid] : 0.0;
+            double (*Lb)[36] = buf ? Lkc1 : Lkc0;
+            for (int c = lo + kPre; c < k; c++) Lb[c - lo][tid] = bandrow[(size_t)(c - fk) * 36 + tid];
+        } else if (tid < 42) {
+            py = d.xp[k * 6 + tid - 36];
+        } else if (tid < 48) {
+            py = d.invd[k * 6 + tid - 42];
+        }
+    };
+    auto fetch_commit = [&](int k, int buf) {
+        const int lo = max(fj, firstp[k]);
+        if (tid < 36) {
+            double (*Lb)[36] = buf ? Lkc1 : Lkc0;
+#pragma unroll
+            for (int i = 0; i < kPre; i++)
+                if (lo + i < k) Lb[i][tid] = pl[i];
+            Lkk[buf][tid] = pkk;
+        } else if (tid < 42) {
+            yk[buf][tid - 36] = py;
+        } else if (tid < 48) {
+            Lki[buf][tid - 42] = py;
+        }
+    };
+    double a_cur = 0;
+    double bj = 0.0;  // this chunk's part of sum_k L_jk y_k (k_ba_border_rhs subtracts the parts in chunk order)
+    const int k_lo = max(fj, d.chunk_start[q]), k_hi = min(d.chunk_start[q + 1], n_band);
+    if (k_lo < k_hi) {
+        fetch_issue(k_lo, 0);
+        fetch_commit(k_lo, 0);
+        a_cur = pa;
+    }
+    __syncthreads();
+    for (int k = k_lo; k < k_hi; k++) {
+        const int buf = (k - k_lo) & 1;
+        if (k + 1 < k_hi) fetch_issue(k + 1, buf ^ 1);
+        const int lo = max(fj, firstp[k]);
+        if (tid < 36) {
+            double t = a_cur;
+            for (int c = lo; c < k; c++) {
+                const double* La = ring[c % kBorderRing];
+                const double* Lb = (buf ? Lkc1 : Lkc0)[c - lo];
+                double s0 = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) s0 += La[r * 6 + q] * Lb[c0 * 6 + q];
+                t = t - s0;
+            }
+            T[tid] = t;
+        }
+        __syncthreads();
+        if (tid < 6) {  // row `tid` of L_jk = T L_kk^-T, then b_j[tid] -= L_jk[tid, :] y_k
+            const double* Lk = Lkk[buf];
+            double v[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double s = T[tid * 6 + c];
+#pragma unroll
+                for (int p = 0; p < c; p++) s -= v[p] * Lk[c * 6 + p];
+                v[c] = s * Lki[buf][c];
+            }
+            double* out = rowp + (size_t)(k - fj) * 36 + tid * 6;
+            double* rg = ring[k % kBorderRing] + tid * 6;
+            double s = 0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                out[c] = v[c];
+                rg[c] = v[c];
+                s += v[c] * yk[buf][c];
+            }
+            bj += s;
+        }
+        if (k + 1 < k_hi) {
+            fetch_commit(k + 1, buf ^ 1);
+            a_cur = pa;
+        }
+        __syncthreads();
+    }
+    if (tid < 6) d.bpart[((size_t)blockIdx.x * nq + q) * 6 + tid] = bj;
+#ifdef CORB_BA_TRACE
+    if (tid == 0 && blockIdx.x == 0 && q == 0) printf("k_ba_border_rows row %d chunk 0: %d columns, %lld cyc\n", j, k_hi - k_lo, clock64() - tr0);
+#endif
+}
+
+// b_j -= sum over the chunks (in chunk order) of their parts of sum_k L_jk y_k
+__global__ void __launch_bounds__(256) k_ba_border_rhs(BaDev d, int n_band, int nq) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= (d.Pf - n_band) * 6 || d.scalars[4] != 0.0) return;
+    const int b = i / 6, r = i - b * 6;
+    double x = d.xp[(size_t)n_band * 6 + i];
+    for (int q = 0; q < nq; q++) x -= d.bpart[((size_t)b * nq + q) * 6 + r];
+    d.xp[(size_t)n_band * 6 + i] = x;
+}
+
+// ---- K12d: backward substitution over the band rows, one warp per independent chunk. Row j only touches the <= wmax rows of its envelope,
+//      so the running right-hand sides live in a shared ring and the blocks of row j - 1 are fetched while row j is
+//      solved; same operation order as the row loop at the end of k_ba_solve (bit-identical), without its two block
+//      barriers and global read-modify-writes per row.
+__global__ void __launch_bounds__(32) k_ba_band_backward(BaDev d, int n_band, int wmax, int stage) {
+    extern __shared__ double bsm[];
+    const int R = wmax + 1;
+    double* xs = bsm;                       // [R][6] ring, slot j % R: xp of rows j - wmax .. j
+    double* blk0 = bsm + (size_t)R * 6;     // [R][36] blocks of the row being solved: envelope blocks then the diagonal
+    double* blk1 = blk0 + (size_t)R * 36;   // ... of the next row (being fetched)
+    __shared__ double v[6];
+    __shared__ double inv2[2][6];  // reciprocal diagonal of the row being solved / fetched
+    const int lane = threadIdx.x;
+#ifdef CORB_BA_TRACE
+    const long long tr0 = clock64();
+#endif
+    if (d.scalars[4] != 0.0 || n_band <= 0) return;
+    const int* firstp = d.first;
+    const int* rowoffp = d.rowoff;
+    if (stage) {
+        int* sidx = reinterpret_cast<int*>(blk1 + (size_t)R * 36);
+        for (int i = lane; i < n_band; i += 32) { sidx[i] = d.first[i]; sidx[n_band + i] = d.rowoff[i]; }
+        firstp = sidx;
+        rowoffp = sidx + n_band;
+        __syncwarp();
+    }
+    constexpr int kPre = 8;  // doubles per lane that travel in registers (covers wmax <= 6)
+    double pre[kPre], px = 0, pinv = 0;
+    auto row_blocks = [&](int j) { return j - firstp[j] + 1; };
+    auto issue = [&](int j, double* dst) {  // row j's blocks first[j]..j (contiguous in S) -> registers / dst
+        const double* src = d.S + (size_t)rowoffp[j] * 36;
+        const int n = row_blocks(j) * 36;
+#pragma unroll
+        for (int i = 0; i < kPre; i++) pre[i] = lane + 32 * i < n ? src[lane + 32 * i] : 0.0;
+        if (lane >= 26) pinv = d.invd[j * 6 + lane - 26];
+        for (int i = lane + 32 * kPre; i < n; i += 32) dst[i] = src[i];
+    };
+    auto commit = [&](int j, double* dst) {
+        const int n = row_blocks(j) * 36;
+#pragma unroll
+        for (int i = 0; i < kPre; i++)
+            if (lane + 32 * i < n) dst[lane + 32 * i] = pre[i];
+        if (lane >= 26) inv2[dst == blk0 ? 0 : 1][lane - 26] = pinv;
+    };
+    const int j_lo = d.chunk_start[blockIdx.x], j_hi = d.chunk_start[blockIdx.x + 1] - 1;
+    if (j_hi < j_lo) return;
+    // rows j_hi .. j_hi - R + 1 into the ring
+    for (int i = lane; i < R * 6; i += 32) {
+        const int j = j_hi - i / 6;
+        if (j >= 0) xs[(j % R) * 6 + i % 6] = d.xp[j * 6 + i % 6];
+    }
+    issue(j_hi, blk0);
+    commit(j_hi, blk0);
+    __syncwarp();
+#ifdef CORB_BA_TRACE
+    long long tr_solve = 0, tr_upd = 0, tr_commit = 0, tr_issue = 0;
+#endif
+    for (int j = j_hi; j >= j_lo; j--) {
+#ifdef CORB_BA_TRACE
+        const long long tz = clock64();
+#endif
+        double* cur = ((j_hi - j) & 1) ? blk1 : blk0;
+        double* nxt = ((j_hi - j) & 1) ? blk0 : blk1;
+        const int fj = firstp[j], nb = j - fj;
+        if (j > j_lo) issue(j - 1, nxt);
+        const int jin = j - R;  // row entering the ring once row j is done (its slot)
+        if (jin >= 0 && lane < 6) px = d.xp[jin * 6 + lane];
+        const double* D = cur + (size_t)nb * 36;
+#ifdef CORB_BA_TRACE
+        const long long ta = clock64();
+#endif
+        if (lane == 0) {
+            double w[6];
+#pragma unroll
+            for (int r = 5; r >= 0; r--) {
+                double s = xs[(j % R) * 6 + r];
+#pragma unroll
+                for (int p = r + 1; p < 6; p++) s -= D[p * 6 + r] * w[p];
+                w[r] = s * inv2[cur == blk0 ? 0 : 1][r];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) { d.xp[j * 6 + r] = w[r]; v[r] = w[r]; }
+        }
+        __syncwarp();
+#ifdef CORB_BA_TRACE
+        const long long tb = clock64();
+#endif
+        for (int it = lane; it < nb * 6; it += 32) {
+            const int i = fj + it / 6, c = it % 6;
+            const double* Lb = cur + (size_t)(i - fj) * 36;
+            double s = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) s += Lb[r * 6 + c] * v[r];
+            xs[(i % R) * 6 + c] -= s;
+        }
+        __syncwarp();
+#ifdef CORB_BA_TRACE
+        const long long tc = clock64();
+#endif
+        if (j > j_lo) commit(j - 1, nxt);
+        if (jin >= 0 && lane < 6) xs[(j % R) * 6 + lane] = px;
+        __syncwarp();
+#ifdef CORB_BA_TRACE
+        tr_solve += tb - ta; tr_upd += tc - tb; tr_commit += clock64() - tc; tr_issue += ta - tz;
+#endif
+    }
+#ifdef CORB_BA_TRACE
+    if (lane == 0 && blockIdx.x == 0) printf("k_ba_band_backward %d rows: %lld cyc; per row issue %lld solve %lld update %lld commit %lld\n", n_band, clock64() - tr0,
+                          tr_issue / n_band, tr_solve / n_band, tr_upd / n_band, tr_commit / n_band);
+#endif
 }
 
 // ---- K12b: deferred update of the border block (keyframes with long-range links, ordered last):
@@ -763,13 +1105,56 @@ using namespace corb;
 
 namespace {
 
+// Device memory of a BA call comes from a per-device arena that outlives the call: a global BA allocates ~40 buffers
+// (some > 100 MB) and cudaMalloc / cudaFree cost tens of milliseconds in total, which is comparable to the whole
+// optimisation on a B200. The arena grows by slabs and is reused by the next call on the same device; a concurrent call
+// on the same device (arena busy) falls back to plain cudaMalloc.
+__global__ void __launch_bounds__(256) k_ba_iota_hist(const int* __restrict__ e_pose, int n, int* __restrict__ iota, int* __restrict__ cnt) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < n) {
+        iota[k] = k;
+        atomicAdd(&cnt[e_pose[k]], 1);
+    }
+}
+
+struct BaArena {
+    std::mutex mu;
+    bool busy = false;
+    std::vector<std::pair<char*, size_t>> slabs;
+    size_t cur = 0, off = 0;
+    void* take(size_t bytes) {  // caller holds `busy`
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (;;) {
+            if (cur < slabs.size() && off + bytes <= slabs[cur].second) {
+                void* q = slabs[cur].first + off;
+                off += bytes;
+                return q;
+            }
+            if (cur + 1 < slabs.size()) { cur++; off = 0; continue; }
+            const size_t sz = std::max(bytes, (size_t)256 << 20);
+            void* q = nullptr;
+            if (cudaMalloc(&q, sz) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            slabs.emplace_back((char*)q, sz);
+            cur = slabs.size() - 1;
+            off = 0;
+        }
+    }
+};
+static BaArena g_arena[16];
+
 struct BaHost {
     int device;
+    BaArena* arena = nullptr;  // non-null while this call owns its device's arena
     cudaStream_t stream = nullptr;
     std::vector<void*> allocs;
     BaDev d;
     size_t s_doubles = 0;  // S blocks * 36
     int lact_cap = 0;      // active rows of one column that fit the solve kernel's shared memory
+    int band_wmax = 1;
+    int stage_nnz_b = -1;  // entries of the band column lists when the index arrays fit the solve kernel's shared memory
+    size_t stage_bytes_b = 0;
+    size_t band_idx_bytes = 0;
+    int n_chunks = 1;           // independent band chunks (columns chunk_start[q] .. chunk_start[q + 1])  // first[] / rowoff[] of the band rows staged by the border-row and band-backward kernels     // longest band envelope (blocks left of the diagonal)
     int n_band = 0;        // free keyframes before the border block (== Pf when there is no border)
     corb_allreduce_fn ar = nullptr;
     void* ar_user = nullptr;
@@ -778,7 +1163,12 @@ struct BaHost {
     double* h_scalars = nullptr;  // pinned [8]
 
     ~BaHost() {
+        if (stream) cudaStreamSynchronize(stream);
         for (void* p : allocs) cudaFree(p);
+        if (arena) {
+            std::lock_guard<std::mutex> lk(arena->mu);
+            arena->busy = false;
+        }
         if (h_scalars) cudaFreeHost(h_scalars);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -786,10 +1176,48 @@ struct BaHost {
     }
     template <typename T>
     int alloc(T** p, size_t n) {
-        void* q = nullptr;
-        CORB_CUDA(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T) + 256));
-        allocs.push_back(q);
+        const size_t bytes = std::max<size_t>(n, 1) * sizeof(T) + 256;
+        void* q = arena ? arena->take(bytes) : nullptr;
+        if (!q) {
+            CORB_CUDA(cudaMalloc(&q, bytes));
+            allocs.push_back(q);
+        }
         *p = (T*)q;
+        return CORB_OK;
+    }
+    template <typename T>
+    int upload_raw(const T** p, const T* src, size_t n) {
+        T* q;
+        int rc = alloc(&q, n);
+        if (rc != CORB_OK) return rc;
+        if (n) CORB_CUDA(cudaMemcpyAsync(q, src, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+        *p = q;
+        return CORB_OK;
+    }
+    // pose_off / pose_edges: positions of every keyframe's edges inside the landmark-ordered edge arrays, ascending
+    // (a stable sort of the edge index by keyframe; the fixed order keeps k_ba_build_pose's sums deterministic)
+    int build_pose_csr() {
+        int *keys_out, *vals_in, *vals_out, *off;
+        int rc;
+        if ((rc = alloc(&keys_out, (size_t)d.E)) != CORB_OK || (rc = alloc(&vals_in, (size_t)d.E)) != CORB_OK ||
+            (rc = alloc(&vals_out, (size_t)d.E)) != CORB_OK || (rc = alloc(&off, (size_t)d.P + 1)) != CORB_OK)
+            return rc;
+        CORB_CUDA(cudaMemsetAsync(off, 0, ((size_t)d.P + 1) * sizeof(int), stream));
+        if (d.E > 0) {
+            k_ba_iota_hist<<<(d.E + 255) / 256, 256, 0, stream>>>(d.e_pose, d.E, vals_in, off + 1);
+            int bits = 1;
+            while ((1 << bits) < d.P) bits++;
+            size_t tmp_bytes = 0;
+            CORB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d.e_pose, keys_out, vals_in, vals_out, d.E, 0, bits, stream));
+            size_t scan_bytes = 0;
+            CORB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, off + 1, off + 1, d.P, stream));
+            char* tmp;
+            if ((rc = alloc(&tmp, std::max(tmp_bytes, scan_bytes))) != CORB_OK) return rc;
+            CORB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d.e_pose, keys_out, vals_in, vals_out, d.E, 0, bits, stream));
+            CORB_CUDA(cub::DeviceScan::InclusiveSum(tmp, scan_bytes, off + 1, off + 1, d.P, stream));
+        }
+        d.pose_off = off;
+        d.pose_edges = vals_out;
         return CORB_OK;
     }
     template <typename T>
@@ -865,12 +1293,20 @@ struct BaHost {
             const size_t sm = (size_t)lact_cap * 36 * sizeof(double);
             const int nbord = d.Pf - n_band;
             if (nbord > 0) {
-                k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, 0, n_band, n_band, 1 | 2);
+                // band rows alone -> every border row against the band factor, concurrently -> border x border SYRK ->
+                // dense border block + backward over the border rows -> backward over the band rows
+                CORB_CUDA(cudaMemsetAsync(d.scalars + 4, 0, sizeof(double), stream));
+                k_ba_solve<<<n_chunks, kSolveThreads, sm + stage_bytes_b, stream>>>(d, lact_cap, 0, n_band, n_band, 1 | 8 | 64, stage_nnz_b);
+                k_ba_border_rows<<<dim3(nbord, n_chunks), 64, (size_t)(3 * band_wmax + 1) * 36 * sizeof(double) + band_idx_bytes, stream>>>(
+                    d, n_band, band_wmax, band_idx_bytes > 0);
+                k_ba_border_rhs<<<(nbord * 6 + 255) / 256, 256, 0, stream>>>(d, n_band, n_chunks);
                 const int npairs = nbord * (nbord + 1) / 2;
                 k_ba_border_syrk<<<(npairs * 32 + 255) / 256, 256, 0, stream>>>(d, n_band);
-                k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, n_band, d.Pf, n_band, 4);
+                k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, n_band, d.Pf, n_band, 4 | 16, -1);
+                k_ba_band_backward<<<n_chunks, 32, (size_t)(band_wmax + 1) * (6 + 72) * sizeof(double) + band_idx_bytes, stream>>>(
+                    d, n_band, band_wmax, band_idx_bytes > 0);
             } else {
-                k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, 0, d.Pf, n_band, 1 | 4);
+                k_ba_solve<<<1, kSolveThreads, sm + stage_bytes_b, stream>>>(d, lact_cap, 0, d.Pf, n_band, 1 | 4 | 8, stage_nnz_b);
             }
         }
         cudaEventRecord(ev1, stream);
@@ -898,6 +1334,16 @@ struct BaHost {
 
 }  // namespace
 
+// splits [0, n) over a few host threads (the structure build is memory bound: more than 8 threads do not help)
+template <typename F>
+static void host_parallel_for(int n, F fn) {
+    const int nt = std::max(1, std::min(8, std::min((int)std::thread::hardware_concurrency(), n / 65536)));
+    if (nt <= 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([=]() { fn((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); });
+    for (auto& t : th) t.join();
+}
+
 extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile uint8_t* stop, int robust, int device,
                              corb_ba_result* res, corb_allreduce_fn allreduce, void* allreduce_user) {
     const auto t_start = std::chrono::steady_clock::now();
@@ -915,8 +1361,25 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     CORB_CUDA(cudaGetDeviceCount(&ndev));
     CORB_CHECK(device >= 0 && device < ndev, CORB_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
     CORB_CUDA(cudaSetDevice(device));
+#ifdef CORB_BA_TRACE
+    auto lap = [&](const char* what) {
+        printf("  setup %-28s at %.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
+#else
+    auto lap = [&](const char*) {};
+#endif
+    lap("validated edges");
     BaHost H;
     H.device = device;
+    if (device < 16 && !getenv("CORB_BA_NO_ARENA")) {
+        std::lock_guard<std::mutex> lk(g_arena[device].mu);
+        if (!g_arena[device].busy) {
+            g_arena[device].busy = true;
+            g_arena[device].cur = 0;
+            g_arena[device].off = 0;
+            H.arena = &g_arena[device];
+        }
+    }
     H.ar = allreduce;
     H.ar_user = allreduce_user;
     CORB_CUDA(cudaStreamCreateWithFlags(&H.stream, cudaStreamNonBlocking));
@@ -928,35 +1391,46 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     d.P = P; d.L = L; d.E = E; d.robust = robust != 0;
     d.delta2d = (double)(float)sqrt(5.99);   // thHuber2D / thHuber3D are floats in the reference (Optimizer.cc:101-102)
     d.delta3d = (double)(float)sqrt(7.815);
+    lap("cuda context / stream / events");
     // ---- host-side structure (the analogue of g2o's buildStructure, block_solver.hpp:143-295)
     std::vector<int> pfree(P), lfree(L);
     int Pf = 0, Lf = 0;
     for (int i = 0; i < P; i++) pfree[i] = p->pose_fixed[i] ? -1 : Pf++;
     for (int i = 0; i < L; i++) lfree[i] = p->point_fixed[i] ? -1 : Lf++;
     d.Pf = Pf;
-    std::vector<int> lm_off(L + 1, 0), perm(E);
+    std::vector<int> lm_off(L + 1, 0);
     for (int e = 0; e < E; e++) lm_off[p->edge_point[e] + 1]++;
     for (int i = 0; i < L; i++) lm_off[i + 1] += lm_off[i];
-    {
+    // Edges grouped by landmark (the order Optimizer::BundleAdjustment creates them in, Optimizer.cc:131-196: for every
+    // map point, its observations) are used in place; anything else is stably sorted by landmark first.
+    bool grouped = true;
+    for (int e = 1; e < E && grouped; e++) grouped = p->edge_point[e - 1] <= p->edge_point[e];
+    std::vector<int> perm, e_pose_v, e_point_v;
+    std::vector<double> e_obs_v, e_info_v;
+    if (!grouped) {
+        perm.resize(E);
         std::vector<int> cur(lm_off.begin(), lm_off.end() - 1);
         for (int e = 0; e < E; e++) perm[cur[p->edge_point[e]]++] = e;
+        e_pose_v.resize(E); e_point_v.resize(E); e_obs_v.resize((size_t)E * 3); e_info_v.resize(E);
     }
-    std::vector<int> e_pose(E), e_point(E);
-    std::vector<double> e_obs((size_t)E * 3), e_info(E);
-    for (int k = 0; k < E; k++) {
-        const int e = perm[k];
-        e_pose[k] = p->edge_pose[e]; e_point[k] = p->edge_point[e];
-        e_obs[3 * (size_t)k] = p->edge_obs[3 * (size_t)e]; e_obs[3 * (size_t)k + 1] = p->edge_obs[3 * (size_t)e + 1];
-        e_obs[3 * (size_t)k + 2] = p->edge_obs[3 * (size_t)e + 2];
-        e_info[k] = p->edge_inv_sigma2[e];
-    }
-    std::vector<int> pose_off(P + 1, 0), pose_edges(E);
-    for (int k = 0; k < E; k++) pose_off[e_pose[k] + 1]++;
-    for (int i = 0; i < P; i++) pose_off[i + 1] += pose_off[i];
-    {
-        std::vector<int> cur(pose_off.begin(), pose_off.end() - 1);
-        for (int k = 0; k < E; k++) pose_edges[cur[e_pose[k]]++] = k;
-    }
+    std::vector<int>& e_pose = e_pose_v;
+    std::vector<int>& e_point = e_point_v;
+    std::vector<double>& e_obs = e_obs_v;
+    std::vector<double>& e_info = e_info_v;
+    if (!grouped) host_parallel_for(E, [&](int k0, int k1) {
+        for (int k = k0; k < k1; k++) {
+            const int e = perm[k];
+            e_pose[k] = p->edge_pose[e]; e_point[k] = p->edge_point[e];
+            e_obs[3 * (size_t)k] = p->edge_obs[3 * (size_t)e]; e_obs[3 * (size_t)k + 1] = p->edge_obs[3 * (size_t)e + 1];
+            e_obs[3 * (size_t)k + 2] = p->edge_obs[3 * (size_t)e + 2];
+            e_info[k] = p->edge_inv_sigma2[e];
+        }
+    });
+    const int* ep = grouped ? p->edge_pose : e_pose.data();      // edge arrays in landmark order
+    const int* ept = grouped ? p->edge_point : e_point.data();
+    const double* eobs = grouped ? p->edge_obs : e_obs.data();
+    const double* einfo = grouped ? p->edge_inv_sigma2 : e_info.data();
+    lap("edges grouped by landmark");
     // ---- ordering + envelope. nbr_min/nbr_max[j] = smallest / largest free pose sharing a free landmark with j.
     //      Long-range couplings (loop closures, map-fusion links) would stretch the envelope of every row they touch
     //      back to the far keyframe; instead the smaller of the two vertex covers of the long links is ordered last
@@ -968,18 +1442,24 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         mn.assign(std::max(Pf, 1), 0.0);
         mx.assign(std::max(Pf, 1), 0.0);
         for (int j = 0; j < Pf; j++) mn[j] = mx[j] = j;
-        for (int l = 0; l < L; l++) {
-            if (lfree[l] < 0) continue;
-            int lo = Pf, hi = -1;
-            for (int k = lm_off[l]; k < lm_off[l + 1]; k++) {
-                const int pj = idx[e_pose[k]];
-                if (pj >= 0) { lo = std::min(lo, pj); hi = std::max(hi, pj); }
+        std::mutex merge;
+        host_parallel_for(L, [&](int l0, int l1) {
+            std::vector<double> tmn(mn), tmx(mx);  // min / max commute: per-thread copies, merged at the end
+            for (int l = l0; l < l1; l++) {
+                if (lfree[l] < 0) continue;
+                int lo = Pf, hi = -1;
+                for (int k = lm_off[l]; k < lm_off[l + 1]; k++) {
+                    const int pj = idx[ep[k]];
+                    if (pj >= 0) { lo = std::min(lo, pj); hi = std::max(hi, pj); }
+                }
+                for (int k = lm_off[l]; k < lm_off[l + 1]; k++) {
+                    const int pj = idx[ep[k]];
+                    if (pj >= 0) { tmn[pj] = std::min(tmn[pj], (double)lo); tmx[pj] = std::max(tmx[pj], (double)hi); }
+                }
             }
-            for (int k = lm_off[l]; k < lm_off[l + 1]; k++) {
-                const int pj = idx[e_pose[k]];
-                if (pj >= 0) { mn[pj] = std::min(mn[pj], (double)lo); mx[pj] = std::max(mx[pj], (double)hi); }
-            }
-        }
+            std::lock_guard<std::mutex> lk(merge);
+            for (int j = 0; j < Pf; j++) { mn[j] = std::min(mn[j], tmn[j]); mx[j] = std::max(mx[j], tmx[j]); }
+        });
         if (allreduce && Pf > 0) {  // all ranks must agree on the structure of the reduced system
             CORB_CUDA(cudaMemcpyAsync(d_tmp, mn.data(), Pf * sizeof(double), cudaMemcpyHostToDevice, H.stream));
             CORB_CUDA(cudaMemcpyAsync(d_tmp + Pf, mx.data(), Pf * sizeof(double), cudaMemcpyHostToDevice, H.stream));
@@ -1017,6 +1497,50 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             H.n_band = Pf - (int)border.size();
         }
     }
+    // ---- chunks. The band factorisation is a serial sweep (each block column waits for the previous one). Taking
+    //      wmax consecutive keyframes out of the band every n/Q columns ("separators", wmax = band half width) leaves Q
+    //      chunks that share no landmark, i.e. Q independent band factorisations, one CTA each. The separators join
+    //      the border rows: ordered last (before the long-range rows), swept against the chunks by k_ba_border_rows -
+    //      per (row, chunk), also concurrently - and factored in the small dense border block.
+    std::vector<int> chunk_start(2, 0);
+    chunk_start[1] = H.n_band;
+    {
+        int wmax = 0;
+        for (int j = 0; j < H.n_band; j++) wmax = std::max(wmax, j - (int)firstd[j]);
+        const char* qenv = getenv("CORB_BA_CHUNKS");
+        int Q = qenv ? atoi(qenv) : 8;  // measured on B200 (P = 2000): 4 -> 4.4, 6 -> 3.9, 8 -> 4.1, 12 -> 5.3, 16 -> 7.5 ms per solve
+        Q = std::min(Q, H.n_band / 64);
+        if (wmax >= 1 && wmax <= 8 && Q >= 2 && H.n_band - (Q - 1) * wmax >= Q) {
+            const int nb0 = H.n_band, nbord0 = Pf - nb0;
+            std::vector<uint8_t> is_sep(nb0, 0);
+            for (int q = 1; q < Q; q++) {
+                const int pq = (int)((long long)q * nb0 / Q);
+                for (int j = pq - wmax; j < pq; j++) is_sep[j] = 1;
+            }
+            std::vector<int> newidx(Pf);
+            int nxt = 0;
+            chunk_start.assign(1, 0);
+            for (int j = 0; j < nb0; j++) {
+                if (is_sep[j]) {
+                    if (j + 1 == nb0 || !is_sep[j + 1]) chunk_start.push_back(nxt);  // a chunk ends in front of each separator
+                    continue;
+                }
+                newidx[j] = nxt++;
+            }
+            chunk_start.push_back(nxt);
+            const int nb1 = nxt;
+            for (int j = 0; j < nb0; j++) if (is_sep[j]) newidx[j] = nxt++;
+            for (int j = nb0; j < Pf; j++) newidx[j] = nxt++;
+            for (int i = 0; i < P; i++) if (pfree[i] >= 0) pfree[i] = newidx[pfree[i]];
+            if ((rc = neighbour_range(pfree, firstd, lastd)) != CORB_OK) return rc;
+            H.n_band = nb1;
+            res->separator_poses = nb0 - nb1;
+            res->border_poses = nbord0 + res->separator_poses;
+        }
+    }
+    H.n_chunks = (int)chunk_start.size() - 1;
+    res->band_chunks = H.n_chunks;
+    lap("ordering (border, chunks)");
     std::vector<int> first(Pf), rowoff(Pf + 1, 0), coloff(Pf + 1, 0);
     for (int j = 0; j < Pf; j++) {
         first[j] = (int)firstd[j];
@@ -1033,20 +1557,53 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         for (int j = 0; j < Pf; j++)
             for (int k = first[j]; k < j; k++) col_rows[cur[k]++] = j;  // ascending j within a column
     }
+    {
+        int wmax = 1;
+        for (int j = 0; j < H.n_band; j++) wmax = std::max(wmax, j - first[j]);
+        H.band_wmax = wmax;
+        const size_t idx = (size_t)2 * H.n_band * sizeof(int);
+        H.band_idx_bytes = (3 * wmax + 1) * 36 * sizeof(double) + idx <= 180 * 1024 ? idx : 0;
+        CORB_CUDA(cudaFuncSetAttribute(k_ba_border_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (3 * wmax + 1) * 36 * (int)sizeof(double) + (int)H.band_idx_bytes));
+        CORB_CUDA(cudaFuncSetAttribute(k_ba_band_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (wmax + 1) * (6 + 72) * (int)sizeof(double) + (int)H.band_idx_bytes));
+    }
+    // the same lists without the border rows in the band columns: the band sweep of the bordered solve
+    std::vector<int> coloff_b(Pf + 1, 0), col_rows_b(col_rows.size());
+    {
+        int w = 0;
+        for (int k = 0; k < Pf; k++) {
+            coloff_b[k] = w;
+            for (int e = coloff[k]; e < coloff[k + 1]; e++)
+                if (k >= H.n_band || col_rows[e] < H.n_band) col_rows_b[w++] = col_rows[e];
+        }
+        if (Pf) coloff_b[Pf] = w;
+    }
     res->reduced_blocks = nblocks;
     {
         int max_nact = 0;
         for (int k = 0; k < Pf; k++) max_nact = std::max(max_nact, coloff[k + 1] - coloff[k]);
         H.lact_cap = std::max(1, std::min(max_nact, 700));
-        CORB_CUDA(cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, H.lact_cap * 36 * (int)sizeof(double)));
+        const size_t lact_bytes = (size_t)H.lact_cap * 36 * sizeof(double);
+        const size_t idx_bytes = ((size_t)3 * Pf + 1 + (Pf ? coloff_b[Pf] : 0)) * sizeof(int);
+        if (lact_bytes + idx_bytes <= 200 * 1024) {
+            H.stage_nnz_b = Pf ? coloff_b[Pf] : 0;
+            H.stage_bytes_b = idx_bytes;
+        }
+        CORB_CUDA(cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lact_bytes + H.stage_bytes_b)));
         res->max_active_rows = max_nact;
     }
     H.s_doubles = (size_t)nblocks * 36;
+    lap("envelope lists");
     // ---- device buffers
 #define UP(field, vec) if ((rc = H.upload(&d.field, vec)) != CORB_OK) return rc
-    UP(pfree, pfree); UP(lfree, lfree); UP(e_pose, e_pose); UP(e_point, e_point); UP(e_obs, e_obs); UP(e_info, e_info);
-    UP(lm_off, lm_off); UP(pose_off, pose_off); UP(pose_edges, pose_edges); UP(first, first); UP(rowoff, rowoff);
-    UP(coloff, coloff); UP(col_rows, col_rows);
+    UP(pfree, pfree); UP(lfree, lfree);
+    if ((rc = H.upload_raw(&d.e_pose, ep, (size_t)E)) != CORB_OK || (rc = H.upload_raw(&d.e_point, ept, (size_t)E)) != CORB_OK ||
+        (rc = H.upload_raw(&d.e_obs, eobs, (size_t)E * 3)) != CORB_OK || (rc = H.upload_raw(&d.e_info, einfo, (size_t)E)) != CORB_OK)
+        return rc;
+    if ((rc = H.build_pose_csr()) != CORB_OK) return rc;  // CSR by keyframe, built on the device from the uploaded e_pose
+    UP(lm_off, lm_off); UP(first, first); UP(rowoff, rowoff);
+    UP(coloff, coloff); UP(col_rows, col_rows); UP(coloff_b, coloff_b); UP(col_rows_b, col_rows_b); UP(chunk_start, chunk_start);
 #undef UP
     {
         std::vector<double> cam(p->pose_cam, p->pose_cam + (size_t)P * 5);
@@ -1057,7 +1614,8 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     AL(Hpp, (size_t)Pf * 36); AL(bp, (size_t)Pf * 6); AL(Hll, (size_t)L * 9); AL(bl, (size_t)L * 3); AL(W, (size_t)E * 18);
     AL(Dinv, (size_t)L * 9); AL(db, (size_t)L * 3);
     AL(S, H.s_doubles + (size_t)Pf * 6);
-    AL(xp, (size_t)Pf * 6); AL(xl, (size_t)L * 3);
+    AL(xp, (size_t)Pf * 6); AL(xl, (size_t)L * 3); AL(invd, (size_t)Pf * 6 + 6);
+    AL(bpart, (size_t)std::max(1, Pf - H.n_band) * H.n_chunks * 6);
     const size_t npart = (size_t)std::max(std::max((E + 255) / 256, (L * 3 + 255) / 256), 2048) * 2 + 16;
     AL(partial, npart); AL(scalars, 8);
 #undef AL
@@ -1067,6 +1625,8 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     CORB_CUDA(cudaMemcpyAsync(d.X, p->point_xyz, (size_t)L * 3 * sizeof(double), cudaMemcpyHostToDevice, H.stream));
     CORB_CUDA(cudaMemsetAsync(d.scalars, 0, 8 * sizeof(double), H.stream));
 
+    lap("uploads + allocations");
+    res->ms_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     // ---- Levenberg-Marquardt (optimization_algorithm_levenberg.cpp:61-164, sparse_optimizer.cpp:354-419)
     auto terminate = [&]() { return stop && *stop; };
     double lambda = -1, ni = 2;

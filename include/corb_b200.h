@@ -255,6 +255,9 @@ typedef struct {
     int64_t reduced_blocks;      /* 6x6 blocks in the envelope of the reduced camera system */
     int32_t border_poses;        /* keyframes ordered last because they carry long-range (loop/fusion) links */
     int32_t max_active_rows;     /* widest front of the block-skyline factorisation */
+    double ms_setup;             /* host structure build + uploads before the first LM iteration */
+    int32_t band_chunks;         /* independent chunks the band was cut into (separator keyframes join the border) */
+    int32_t separator_poses;     /* keyframes ordered last only to decouple the chunks */
 } corb_ba_result;
 
 /* All-reduce hook for landmark-sharded BA: `buf` is a DEVICE pointer to n doubles, reduced in place over

@@ -94,3 +94,35 @@ def test_ba_stop_flag_and_degenerate_inputs():
         bad["edge_pose"] = prob["edge_pose"].copy()
         bad["edge_pose"][0] = 10 ** 6
         Optimizer.BundleAdjustment(bad, 1, bRobust=False)
+
+
+def test_ba_edge_order_does_not_matter():
+    """Edges grouped by landmark are used in place (the order Optimizer.cc:131-196 creates them in); any other order is
+    stably sorted by landmark first. Both routes must give the same optimisation."""
+    prob = ba_problem(40, 4000, seed=13, n_fusion=8)
+    out_a, info_a = Optimizer.BundleAdjustment(prob, 6, bRobust=False)
+    rng = np.random.default_rng(4)
+    perm = rng.permutation(len(prob["edge_pose"]))
+    shuf = dict(prob)
+    for k in ("edge_pose", "edge_point", "edge_obs", "edge_inv_sigma2"):
+        shuf[k] = np.ascontiguousarray(prob[k][perm])
+    out_b, info_b = Optimizer.BundleAdjustment(shuf, 6, bRobust=False)
+    assert info_a["trial_accepted"] == info_b["trial_accepted"]
+    assert info_b["chi2_final"] == pytest.approx(info_a["chi2_final"], rel=1e-9)
+    np.testing.assert_allclose(out_b["pose_t"], out_a["pose_t"], atol=1e-8)
+    np.testing.assert_allclose(out_b["point_xyz"], out_a["point_xyz"], atol=1e-8)
+
+
+def test_ba_chunked_band_equals_single_sweep(monkeypatch):
+    """Long trajectories are cut into independent band chunks (separator keyframes join the border block); the result
+    must agree with the single sweep (CORB_BA_CHUNKS=1) and with the oracle."""
+    prob = ba_problem(600, 20000, seed=17, n_fusion=12)
+    monkeypatch.setenv("CORB_BA_CHUNKS", "1")
+    out_1, info_1 = Optimizer.BundleAdjustment(prob, 5, bRobust=False)
+    monkeypatch.delenv("CORB_BA_CHUNKS")
+    out_q, info_q = Optimizer.BundleAdjustment(prob, 5, bRobust=False)
+    assert info_1["band_chunks"] == 1 and info_q["band_chunks"] > 1 and info_q["separator_poses"] > 0
+    assert info_q["trial_accepted"] == info_1["trial_accepted"]
+    assert info_q["chi2_final"] == pytest.approx(info_1["chi2_final"], rel=1e-9)
+    np.testing.assert_allclose(out_q["pose_t"], out_1["pose_t"], atol=1e-7)
+    _check(prob, iters=5)
