@@ -218,6 +218,42 @@ def bench_matcher(device, with_cpu=True):
         dt = time.perf_counter() - t0
         out["l1_score"]["cpu_scores_per_s"] = len(cvecs) / dt
         out["cpu"] = "oracle port, 1 thread (includes the ctypes call overhead of one call per candidate)"
+    # ---- SearchByProjection (TrackWithMotionModel / SearchLocalPoints: every tracked frame)
+    from corb_slam_b200 import FrameView
+    from corb_slam_b200.synth import projection_scene
+    sc = projection_scene(1)
+    c = sc["cur"]
+    fv = FrameView(c["x"], c["y"], c["octave"], c["angle"], c["desc"], c["u_right"], sc["scales"], sc["bounds"], sc["K"], sc["mbf"],
+                   sc["Tcw"], taken=sc["taken"])
+    pm = ORBmatcher(0.8, True, device=device)
+    last_args = (fv, sc["last_valid"], sc["Xw"], sc["mp_desc"], sc["last"]["octave"], sc["last"]["angle"], sc["Tlw"], 15.0)
+    map_args = (fv, sc["in_view"], sc["proj"], sc["level"], sc["view_cos"], sc["mp_desc"])
+    pm.SearchByProjectionLastFrame(*last_args, last_blocks=sc["last_blocks"]); pm.SearchByProjectionMapPoints(*map_args)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        _, n_last = pm.SearchByProjectionLastFrame(*last_args, last_blocks=sc["last_blocks"])
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        _, n_map = pm.SearchByProjectionMapPoints(*map_args)
+    t2 = time.perf_counter()
+    out["search_by_projection"] = {"last_frame_calls_per_s": reps / (t1 - t0), "map_points_calls_per_s": reps / (t2 - t1),
+                                   "last_frame_ms": 1e3 * (t1 - t0) / reps, "map_points_ms": 1e3 * (t2 - t1) / reps,
+                                   "queries": int(len(sc["last_valid"])), "frame_features": int(fv.n), "matches": [int(n_last), int(n_map)],
+                                   "note": "host arrays in, host match array out (H2D + two kernels + D2H per call)"}
+    if with_cpu:
+        from oracle import _proj_bind as PB
+        cs = fv.c_struct()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            PB.search_by_projection_last(cs, fv.n, sc["last_valid"], sc["last_blocks"], sc["Xw"], sc["mp_desc"], sc["last"]["octave"],
+                                         sc["last"]["angle"], sc["Tlw"], 15.0, False, True)
+        t1 = time.perf_counter()
+        for _ in range(reps):
+            PB.search_by_projection_map(cs, fv.n, sc["in_view"], None, sc["proj"], sc["level"], sc["view_cos"], sc["mp_desc"], 1.0, 0.8)
+        t2 = time.perf_counter()
+        out["search_by_projection"]["cpu_last_frame_calls_per_s"] = reps / (t1 - t0)
+        out["search_by_projection"]["cpu_map_points_calls_per_s"] = reps / (t2 - t1)
+    pm.close()
     out["workload"] = "k=10 L=5 synthetic vocabulary, 2000 descriptors per frame, 32 candidate keyframes, level-2 node groups"
     m.close(); gvoc.close()
     return out

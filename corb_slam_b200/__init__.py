@@ -8,4 +8,5 @@ from .orbextractor import (ORBextractor, compute_stereo_matches, extract_stereo,
                            frame_stereo)
 from .orbmatcher import ORBmatcher, BowFeatures  # noqa: F401
 from .orbvocabulary import ORBVocabulary  # noqa: F401
+from .frame import FrameView  # noqa: F401
 from .optimizer import Optimizer, torch_allreduce  # noqa: F401

@@ -118,6 +118,8 @@ def lib():
                                            C.POINTER(vp), i32p]
         L.corb_bow_match_batch_device.argtypes = [vp, C.c_int, C.c_int, C.POINTER(BowSide), C.POINTER(BowSide), C.c_float,
                                                   C.c_int, C.POINTER(vp), vp]
+        L.corb_search_by_projection_last.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, i32p]
+        L.corb_search_by_projection_map.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, i32p]
         L.corb_voc_load_text.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
         L.corb_voc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
         L.corb_voc_destroy.argtypes = [vp]

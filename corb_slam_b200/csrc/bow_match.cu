@@ -284,7 +284,20 @@ struct corb_matcher {
     cudaStream_t stream = nullptr;
     Arena arena;
     Arena dev_calls;  // for the device-resident batch form (call table + scratch)
+    Arena proj;       // projection matchers (proj_match.cu)
 };
+
+namespace corb {
+int matcher_device(const corb_matcher* m) { return m->device; }
+cudaStream_t matcher_stream(const corb_matcher* m) { return m->stream; }
+int matcher_proj_reserve(corb_matcher* m, size_t bytes, uint8_t** d, uint8_t** h) {
+    int rc = m->proj.reserve(bytes);
+    if (rc != CORB_OK) return rc;
+    *d = m->proj.d;
+    *h = m->proj.h;
+    return CORB_OK;
+}
+}  // namespace corb
 
 struct corb_voc {
     int device;
@@ -322,6 +335,7 @@ void corb_matcher_destroy(corb_matcher* m) {
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
     m->arena.release();
     m->dev_calls.release();
+    m->proj.release();
     delete m;
 }
 

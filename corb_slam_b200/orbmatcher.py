@@ -57,7 +57,49 @@ class ORBmatcher:
             lib().corb_matcher_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+    # ---- SearchByProjection (ORBmatcher.h:51,55; ORBmatcher.cc:44-131, 1470-1614)
+    def SearchByProjectionLastFrame(self, cur, last_valid, last_xyz, last_mp_desc, last_octave, last_angle, Tlw, th, bMono=False,
+                                    last_blocks=None):
+        """SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono). `cur` is a frame.FrameView; the
+        LastFrame members are passed flattened (see include/corb_b200.h). Returns (match[cur.n] -> last index or -1, nmatches)."""
+        u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+        valid, blocks = u8(last_valid), u8(last_blocks)
+        xyz = np.ascontiguousarray(last_xyz, np.float32)
+        desc = np.ascontiguousarray(last_mp_desc, np.uint8)
+        octv = np.ascontiguousarray(last_octave, np.int32)
+        ang = np.ascontiguousarray(last_angle, np.float32)
+        T = np.ascontiguousarray(np.asarray(Tlw, np.float32).reshape(-1)[:12])
+        match = np.empty(cur.n, np.int32)
+        nm = C.c_int32()
+        cs = cur.c_struct()
+        check(lib().corb_search_by_projection_last(self._h, C.byref(cs), len(valid), valid.ctypes.data,
+                                                   blocks.ctypes.data if blocks is not None else None, xyz.ctypes.data,
+                                                   desc.ctypes.data, octv.ctypes.data, ang.ctypes.data, T.ctypes.data, float(th),
+                                                   int(bool(bMono)), int(self.mbCheckOrientation), match.ctypes.data, C.byref(nm)))
+        return match, nm.value
+
+    def SearchByProjectionMapPoints(self, F, in_view, proj, level, view_cos, mp_desc, th=1.0, blocks=None):
+        """SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, th): proj[:, 0:3] = mTrackProjX, mTrackProjY,
+        mTrackProjXR; level = mnTrackScaleLevel; view_cos = mTrackViewCos. Returns (match[F.n] -> map point index or -1, n)."""
+        u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+        iv, bl = u8(in_view), u8(blocks)
+        pr = np.ascontiguousarray(proj, np.float32)
+        lv = np.ascontiguousarray(level, np.int32)
+        vc = np.ascontiguousarray(view_cos, np.float32)
+        desc = np.ascontiguousarray(mp_desc, np.uint8)
+        match = np.empty(F.n, np.int32)
+        nm = C.c_int32()
+        cs = F.c_struct()
+        check(lib().corb_search_by_projection_map(self._h, C.byref(cs), len(iv), iv.ctypes.data, bl.ctypes.data if bl is not None else None,
+                                                  pr.ctypes.data, lv.ctypes.data, vc.ctypes.data, desc.ctypes.data, float(th),
+                                                  float(self.mfNNratio), match.ctypes.data, C.byref(nm)))
+        return match, nm.value
 
     @staticmethod
     def DescriptorDistance(a, b):

@@ -143,3 +143,68 @@ def ba_shard(prob, rank, world):
     out["pose_q"] = prob["pose_q"].copy(); out["pose_t"] = prob["pose_t"].copy()
     out["_point_ids"] = keep_pts
     return out
+
+
+# --------------------------------------------------------------------------------------------- projection matching scene
+def projection_scene(seed=0, n_points=2500, w=1242, h=375, n_levels=8, scale_factor=1.2, motion=0.6, desc_noise=18,
+                     clutter=600, temporal_fraction=0.15):
+    """Two consecutive stereo frames of a synthetic scene for ORBmatcher::SearchByProjection: random 3-D points in front
+    of a KITTI-like camera, a last frame (identity pose) and a current frame moved `motion` metres forward with a small
+    rotation. Every point yields a last-frame feature with a MapPoint; the current frame holds noisy re-detections of
+    most points plus `clutter` unrelated features. Returns a dict of numpy arrays (all float32 / int32 / uint8)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, bf = KITTI_CAM
+    scales = np.float32(scale_factor) ** np.arange(n_levels, dtype=np.float32)
+    # world points (last camera frame = world)
+    z = rng.uniform(4.0, 60.0, n_points)
+    x = (rng.uniform(0, w, n_points) - cx) / fx * z
+    y = (rng.uniform(0, h, n_points) - cy) / fy * z
+    Xw = np.stack([x, y, z], 1).astype(np.float32)
+    Tlw = np.eye(4, dtype=np.float32)[:3]
+    yaw = 0.01
+    R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    Tcw = np.concatenate([R, np.array([[0.02], [0.01], [-motion]])], 1).astype(np.float32)
+
+    def project(T, X):
+        Xc = X @ T[:, :3].T.astype(np.float64) + T[:, 3].astype(np.float64)
+        return fx * Xc[:, 0] / Xc[:, 2] + cx, fy * Xc[:, 1] / Xc[:, 2] + cy, Xc[:, 2]
+
+    desc = rng.integers(0, 256, (n_points, 32), dtype=np.uint8)
+
+    def noisy(d, nbits):
+        d = d.copy()
+        flips = rng.integers(0, 256, (len(d), nbits))
+        for j in range(nbits):
+            d[np.arange(len(d)), flips[:, j] >> 3] ^= (1 << (flips[:, j] & 7)).astype(np.uint8)
+        return d
+
+    octave = np.clip(np.floor(np.log(np.maximum(60.0 / z, 1.0)) / np.log(scale_factor)), 0, n_levels - 1).astype(np.int32)
+    ul, vl, zl = project(Tlw, Xw)
+    last = {"x": ul.astype(np.float32), "y": vl.astype(np.float32), "octave": octave,
+            "angle": rng.uniform(0, 360, n_points).astype(np.float32)}
+    last_valid = (rng.random(n_points) < 0.9).astype(np.uint8)             # pMP && !outlier
+    last_blocks = (rng.random(n_points) >= temporal_fraction).astype(np.uint8)  # Observations() > 0 (temporal points: 0)
+    # current frame: re-detections (80 %) + clutter, shuffled
+    uc, vc, zc = project(Tcw, Xw)
+    seen = (rng.random(n_points) < 0.8) & (uc > 0) & (uc < w) & (vc > 0) & (vc < h) & (zc > 0.5)
+    ids = np.nonzero(seen)[0]
+    cx_ = np.concatenate([uc[ids] + rng.normal(0, 1.5, len(ids)), rng.uniform(0, w, clutter)])
+    cy_ = np.concatenate([vc[ids] + rng.normal(0, 1.5, len(ids)), rng.uniform(0, h, clutter)])
+    coct = np.concatenate([np.clip(octave[ids] + rng.integers(-1, 2, len(ids)), 0, n_levels - 1), rng.integers(0, n_levels, clutter)])
+    cang = np.concatenate([last["angle"][ids] + rng.normal(0, 4, len(ids)), rng.uniform(0, 360, clutter)]) % 360.0
+    cdesc = np.concatenate([noisy(desc[ids], desc_noise), rng.integers(0, 256, (clutter, 32), dtype=np.uint8)])
+    depth = np.concatenate([zc[ids], rng.uniform(4, 60, clutter)])
+    cur_ur = np.where(rng.random(len(cx_)) < 0.8, cx_ - bf / depth + rng.normal(0, 0.5, len(cx_)), -1.0)
+    perm = rng.permutation(len(cx_))
+    cur = {"x": cx_[perm].astype(np.float32), "y": cy_[perm].astype(np.float32), "octave": coct[perm].astype(np.int32),
+           "angle": cang[perm].astype(np.float32), "desc": np.ascontiguousarray(cdesc[perm]),
+           "u_right": cur_ur[perm].astype(np.float32)}
+    taken = (rng.random(len(cx_)) < 0.03).astype(np.uint8)
+    # local-map variant: Frame::isInFrustum outputs for the same points (ProjX/Y/XR, predicted level, viewing cosine)
+    proj = np.stack([uc, vc, uc - bf / np.maximum(zc, 0.1)], 1).astype(np.float32)
+    in_view = (seen | (rng.random(n_points) < 0.05)).astype(np.uint8) & (zc > 0.5)
+    level = np.clip(octave + rng.integers(0, 2, n_points), 0, n_levels - 1).astype(np.int32)
+    view_cos = rng.uniform(0.99, 1.0, n_points).astype(np.float32)
+    return {"scales": scales, "bounds": (0.0, 0.0, float(w), float(h)), "K": (fx, fy, cx, cy), "mbf": bf, "Tcw": Tcw, "Tlw": Tlw,
+            "cur": cur, "taken": taken, "last": last, "last_valid": last_valid, "last_blocks": last_blocks, "Xw": Xw,
+            "mp_desc": desc, "proj": proj, "in_view": in_view.astype(np.uint8), "level": level, "view_cos": view_cos}

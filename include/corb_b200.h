@@ -146,6 +146,53 @@ CORB_API void corb_matcher_destroy(corb_matcher* m);
 CORB_API int corb_hamming_pairs(corb_matcher* m, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* pairs,
                                 int n, int32_t* out);
 
+/* ---- ORBmatcher::SearchByProjection -------------------------------------------------------
+ * Flattened view of the reference's Frame for the projection matchers (Frame.h:60-200), filled by the shim:
+ *   x, y, octave, angle   mvKeysUn[i].pt / .octave / .angle
+ *   desc                  mDescriptors (n x 32 bytes);  u_right  mvuRight
+ *   taken[i]              mvpMapPoints[i] holds a MapPoint with Observations() > 0: the feature is skipped
+ *                         (ORBmatcher.cc:81-84, 1554-1557); NULL = none
+ *   grid_off / grid_idx   Frame::mGrid[64][48] (Frame.cc:229-245) as CSR, cell = ix * 48 + iy, indices in push_back order
+ *   min/max, grid_*_inv   mnMinX.. / mfGridElementWidthInv.. ;  scale_factors  mvScaleFactors
+ *   fx..mb, Tcw           intrinsics, stereo baseline terms, rows 0..2 of mTcw (row-major 3x4) */
+typedef struct {
+    int32_t n;
+    const float* x;
+    const float* y;
+    const int32_t* octave;
+    const float* angle;
+    const uint8_t* desc;
+    const float* u_right;
+    const uint8_t* taken;
+    const int32_t* grid_off;
+    const int32_t* grid_idx;
+    float min_x, min_y, max_x, max_y, grid_w_inv, grid_h_inv;
+    const float* scale_factors;
+    int32_t n_levels;
+    float fx, fy, cx, cy, mbf, mb;
+    float Tcw[12];
+} corb_frame_view;
+
+/* int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+ * [ORBmatcher.h:55, ORBmatcher.cc:1470-1614]; called by Tracking::TrackWithMotionModel (Tracking.cc:872-882).
+ * Per last-frame feature i: last_valid = mvpMapPoints[i] && !mvbOutlier[i]; last_blocks = pMP->Observations() > 0
+ * (NULL = all; temporal stereo points have none); last_xyz = pMP->GetWorldPos(); last_mp_desc = pMP->GetDescriptor();
+ * last_octave = mvKeys[i].octave; last_angle = mvKeysUn[i].angle; Tlw = LastFrame.mTcw rows 0..2.
+ * match[i2] (size cur->n) = index i of the last-frame feature whose MapPoint current feature i2 received, else -1. */
+CORB_API int corb_search_by_projection_last(corb_matcher* m, const corb_frame_view* cur, int32_t n_last, const uint8_t* last_valid,
+                                            const uint8_t* last_blocks, const float* last_xyz, const uint8_t* last_mp_desc,
+                                            const int32_t* last_octave, const float* last_angle, const float* Tlw, float th,
+                                            int mono, int check_orientation, int32_t* match, int32_t* nmatches);
+
+/* int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th)
+ * [ORBmatcher.h:51, ORBmatcher.cc:44-131]; called by Tracking::SearchLocalPoints (Tracking.cc:1199-1212).
+ * Per map point: in_view = mbTrackInView && !isBad(); blocks = Observations() > 0 (NULL = all);
+ * proj = (mTrackProjX, mTrackProjY, mTrackProjXR); level = mnTrackScaleLevel; view_cos = mTrackViewCos.
+ * match[idx] (size F->n) = index of the map point assigned to frame feature idx, else -1. */
+CORB_API int corb_search_by_projection_map(corb_matcher* m, const corb_frame_view* F, int32_t n_mp, const uint8_t* in_view,
+                                           const uint8_t* blocks, const float* proj, const int32_t* level, const float* view_cos,
+                                           const uint8_t* mp_desc, float th, float nnratio, int32_t* match, int32_t* nmatches);
+
 /* One side of a SearchByBoW call, flattened by the shim:
  *   desc/n            mDescriptors (n x 32 bytes)
  *   fv_*              DBoW2::FeatureVector as CSR: fv_nodes[fv_n] ascending node ids, fv_off[fv_n+1], fv_idx[] feature

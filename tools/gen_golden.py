@@ -44,6 +44,21 @@ def main():
     xs = np.concatenate([rng.integers(-40000, 40000, 500), [0, 7, 0, 0, 1, -1, -3]]).astype(np.float32)
     out["atan2_y"], out["atan2_x"] = ys, xs
     out["atan2_deg"] = np.array([cv2.fastAtan2(float(y), float(x)) for y, x in zip(ys, xs)], np.float32)
+    # cv::Mat products of the projection matchers (ORBmatcher.cc:1483,1488,1504) = cv::gemm on CV_32F:
+    # Rcw*x+tcw, -Rcw.t()*t, with poses / points of realistic magnitude
+    n = 400
+    ang = rng.uniform(-0.3, 0.3, (n, 3))
+    Rs = np.empty((n, 3, 3), np.float32)
+    for i, (a, b, c) in enumerate(ang):
+        Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+        Rs[i] = (Rz @ Ry @ Rx).astype(np.float32)
+    ts = rng.uniform(-50, 50, (n, 3, 1)).astype(np.float32)
+    xs3 = rng.uniform(-80, 80, (n, 3, 1)).astype(np.float32)
+    out["gemm_R"], out["gemm_t"], out["gemm_x"] = Rs, ts, xs3
+    out["gemm_Rx_plus_t"] = np.stack([cv2.gemm(Rs[i], xs3[i], 1.0, ts[i], 1.0) for i in range(n)])
+    out["gemm_minus_Rt_t"] = np.stack([cv2.gemm(Rs[i], ts[i], -1.0, None, 0.0, flags=cv2.GEMM_1_T) for i in range(n)])
     path = os.path.join(ROOT, "tests", "golden", "opencv_primitives.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", {k: v.shape for k, v in out.items() if k.startswith("fast")})
