@@ -79,6 +79,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel_label):
+    """DRAM bytes per launch of `kernel_label` ("k_octtree[3]") from the committed ncu --set full capture of one stereo
+    frame (profiles/r01b_stereo_frame_ncu_full.csv; every launch there covers both images of the pair, so the figure is
+    halved to match the per-image algorithmic bytes). None when the capture is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01b_stereo_frame_ncu_full.csv")
+    if not os.path.exists(path):
+        return None
+    base = kernel_label.split("[")[0]
+    idx = int(kernel_label.split("[")[1].rstrip("]")) if "[" in kernel_label else 0
+    if base == "k_resize":
+        idx -= 1  # levels 1..7
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    rd = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum")]
+    wr = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum")]
+    if not rd or not wr:
+        return None
+
+    def to_bytes(v, h):
+        unit = h[h.index("[") + 1:h.index("]")] if "[" in h else "byte"
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    hits = [r for r in rows[1:] if r and r[0].startswith(base)]
+    if idx >= len(hits):
+        return None
+    r = hits[idx]
+    return 0.5 * (to_bytes(r[rd[0]], hdr[rd[0]]) + to_bytes(r[wr[0]], hdr[wr[0]]))
+
+
 def cpu_extract_fps(n_frames, clients=1, stereo=False):
     """Oracle port of the reference path: `clients` concurrent clients, each running left/right on two threads
     (Frame.cc:78-81); with stereo=True also Frame::ComputeStereoMatches (Frame.cc:90) on the calling thread."""
@@ -478,7 +507,8 @@ def run_ours(args):
             "tma": exl.uses_tma(),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                         "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic(top[0]), "peak_source": pk_kind,
+                         "traffic_source": "profiles/r01b_stereo_frame_ncu_full.csv (ncu --set full, dram read + write of that launch / 2 images)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_IMAGE, "kernel_ms": top[1],
                          "whole_frame_frac": 2 * ALGO_BYTES_PER_IMAGE * fps / world / 1e9 / pk["hbm_gbs"],
                          "per_kernel_ms_sum_over_levels": {k: round(v, 5) for k, v in agg.items()},

@@ -414,7 +414,12 @@ static void capture_frame(corb_orb* h, cudaStream_t stream, bool d2h, std::vecto
         launch_octtree(g, b, l, h->key_smem_cap, h->oct_smem, ls[l], b1);
         cudaEventRecord(ev[L + l], ls[l]);            // level l distributed
     }
-    launch_blur(g, b, stream, b1);
+    // the blur is needed only by BRIEF at the very end: least urgent stream, behind the last resize
+    cudaEventRecord(ev[2 * L], stream);
+    cudaStreamWaitEvent(ls[L], ev[2 * L], 0);
+    launch_blur(g, b, ls[L], b1);
+    cudaEventRecord(ev[2 * L + 1], ls[L]);
+    cudaStreamWaitEvent(stream, ev[2 * L + 1], 0);
     for (int l = 0; l < L; l++) cudaStreamWaitEvent(stream, ev[L + l], 0);
     launch_orient_desc(g, b, stream, b1);
     if (d2h) {
@@ -435,7 +440,11 @@ struct CaptureScratch {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least urgent (0), hi = most urgent (negative)
         ls.push_back(nullptr);  // one extra, least urgent stream (the blur branch)
         for (size_t i = 0; i < ls.size(); i++) {
-            const int prio = i + 1 == ls.size() ? lo : std::min(lo, hi + (int)i / 2);
+            // CORB_PRIO (A/B switch): 0 = no priorities, 1 = level branches from the most urgent level down,
+            // 2 (default) = the serial resize chain (main stream, most urgent) above every level branch
+            const char* pe = getenv("CORB_PRIO");
+            const int mode = pe ? atoi(pe) : 2;
+            const int prio = mode == 0 ? lo : i + 1 == ls.size() ? lo : std::min(lo, hi + (mode == 2 ? 1 : 0) + (int)i / 2);
             CORB_CUDA(cudaStreamCreateWithPriority(&ls[i], cudaStreamNonBlocking, prio));
         }
         for (auto& e : ev) CORB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
