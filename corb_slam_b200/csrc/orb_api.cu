@@ -49,6 +49,7 @@ struct corb_orb {
     int key_smem_cap = 0, oct_smem = 0;
     bool h2d_node = false;  // CORB_H2D_NODE=1: host images enter through a copy-engine memcpy node instead of k_import's
                             // loads from mapped host memory (measured equal on B200 + PCIe 5; kept for other hosts)
+    int tail_base = 0;      // chain graph: levels tail_base + 1 .. are produced by one k_pyramid launch (0 = resize launches only)
     int graph_mode = 0;  // 0: fused pyramid + per-level FAST/quadtree branches, 1: four fused launches, 2: resize chain + branches
     std::vector<void*> dev_allocs;
     cudaStream_t stream = nullptr, stream2 = nullptr;
@@ -300,13 +301,27 @@ static int make_plan(corb_orb* h, int w, int hgt) {
         CORB_CUDA(cudaMemcpy(d_maps, h->tma.m, sizeof(h->tma.m), cudaMemcpyHostToDevice));
         b.tma_dev = d_maps;
         std::vector<int> ptab;
-        build_pyr_plan(g, xofs.data(), yofs.data(), &b.pyr_plan, &ptab);
+        build_pyr_plan(g, xofs.data(), yofs.data(), 0, &b.pyr_plan, &ptab);
         int* d_ptab;
         A2(d_ptab, ptab.size());
         CORB_CUDA(cudaMemcpy(d_ptab, ptab.data(), ptab.size() * sizeof(int), cudaMemcpyHostToDevice));
         b.pyr_plan.tab = d_ptab;
         cudaError_t pe = prepare_pyramid(b.pyr_plan);
         CORB_CHECK(pe == cudaSuccess, CORB_ERR_CUDA, "pyramid kernel shared memory: %s", cudaGetErrorString(pe));
+        // the short end of the resize chain (small levels: a launch each costs more than the pixels) in one launch
+        const char* te = getenv("CORB_PYR_TAIL");
+        h->tail_base = te ? atoi(te) : 0;  // measured: every tail variant loses to the plain chain (131.7 vs 134-147 us)
+        if (h->tail_base < 1 || h->tail_base >= h->nlevels - 1) h->tail_base = 0;  // 0 = plain chain
+        if (h->tail_base) {
+            std::vector<int> ttab;
+            build_pyr_plan(g, xofs.data(), yofs.data(), h->tail_base, &b.pyr_tail, &ttab);
+            int* d_ttab;
+            A2(d_ttab, ttab.size());
+            CORB_CUDA(cudaMemcpy(d_ttab, ttab.data(), ttab.size() * sizeof(int), cudaMemcpyHostToDevice));
+            b.pyr_tail.tab = d_ttab;
+            pe = prepare_pyramid(b.pyr_tail);
+            CORB_CHECK(pe == cudaSuccess, CORB_ERR_CUDA, "pyramid kernel shared memory: %s", cudaGetErrorString(pe));
+        }
     }
     h->h2d_node = getenv("CORB_H2D_NODE") != nullptr;
     {   // CORB_GRAPH=fused|hybrid selects the alternative per-frame graph shapes (kept for A/B measurements)
@@ -360,7 +375,8 @@ static void capture_frame(corb_orb* h, cudaStream_t stream, bool d2h, std::vecto
         if (peer) cudaMemcpyAsync(peer->d_stage, peer->h_img, bytes, cudaMemcpyHostToDevice, stream);
         launch_import(g, b, h->d_stage, L0.w, stream, b1, peer ? peer->d_stage : nullptr, L0.w);
     } else {
-        launch_import(g, b, h->h_img, g.lv[0].w, stream, b1, peer ? peer->h_img : nullptr, g.lv[0].w);
+        // host variants read mapped page-locked memory: the flat 128-bit kernel; device images: the row kernel
+        launch_import(g, b, h->h_img, g.lv[0].w, stream, b1, peer ? peer->h_img : nullptr, g.lv[0].w, d2h);
     }
     if (ev_after_import) cudaEventRecord(ev_after_import, stream);
     if (h->graph_mode == 0) {
@@ -409,7 +425,8 @@ static void capture_frame(corb_orb* h, cudaStream_t stream, bool d2h, std::vecto
         return;
     }
     for (int l = 0; l < L; l++) {
-        if (l > 0) launch_resize(g, b, l, stream, b1);
+        if (l > 0 && (h->tail_base == 0 || l <= h->tail_base)) launch_resize(g, b, l, stream, b1);
+        else if (l > 0 && l == h->tail_base + 1) launch_pyramid(g, b, stream, b1, true);  // levels l .. L - 1 at once
         cudaEventRecord(ev[l], stream);               // level l exists
         cudaStreamWaitEvent(ls[l], ev[l], 0);
         launch_fast_cells(g, b, l, ls[l], b1);
@@ -471,7 +488,9 @@ static int find_import_node(cudaGraph_t graph, const uint8_t* dst, cudaGraphNode
         if (t != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         CORB_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
-        if (kp.func == import_kernel_ptr() && *reinterpret_cast<uint8_t* const*>(kp.kernelParams[2]) == dst) *out = nd;
+        if ((kp.func == import_kernel_ptr(false) || kp.func == import_kernel_ptr(true)) &&
+            *reinterpret_cast<uint8_t* const*>(kp.kernelParams[2]) == dst)
+            *out = nd;
     }
     CORB_CHECK(*out, CORB_ERR_CUDA, "import node not found in the captured graph");
     return CORB_OK;
@@ -501,6 +520,7 @@ static int record_graph(corb_orb* h) {
     }
     h->kernel_launches = h->graph_mode == 2 ? 1 + (h->geom.n_levels - 1) + 2 * h->geom.n_levels + 2
                        : h->graph_mode == 1 ? 6 : 2 + 2 * h->geom.n_levels + 2;
+    if (h->graph_mode == 2 && h->tail_base) h->kernel_launches -= h->geom.n_levels - 1 - h->tail_base - 1;
     return CORB_OK;
 }
 
@@ -545,10 +565,12 @@ static int patch_import(cudaGraphExec_t exec, cudaGraphNode_t node, corb_orb* h,
     int pitch = L0.pitch, w = L0.w, hh = L0.h;
     void* args[9] = {(void*)&src, (void*)&stride, (void*)&dst, (void*)&pitch, (void*)&w, (void*)&hh, (void*)&src1, (void*)&stride1,
                      (void*)&dst1};
+    cudaKernelNodeParams cur;
+    CORB_CUDA(cudaGraphKernelNodeGetParams(node, &cur));  // which of the two import kernels this node runs
+    const bool host_src = cur.func == import_kernel_ptr(true);
     cudaKernelNodeParams kp = {};
-    kp.func = const_cast<void*>(import_kernel_ptr());
-    kp.gridDim = dim3((L0.w + 1023) / 1024, L0.h, peer ? 2 : 1);
-    kp.blockDim = dim3(256);
+    kp.func = cur.func;
+    import_launch_dims(L0.w, L0.h, peer ? 2 : 1, host_src, &kp.gridDim, &kp.blockDim);
     kp.sharedMemBytes = 0;
     kp.kernelParams = args;
     CORB_CUDA(cudaGraphExecKernelNodeSetParams(exec, node, &kp));

@@ -70,9 +70,10 @@ __device__ const int d_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 1
 // Copies the caller's image (device memory, or page-locked host memory read over PCIe through its UVA mapping) into
 // level 0 of the pitched pyramid. First node of the per-frame graph, so one cudaGraphLaunch is the only driver call
 // an extraction needs; its (src, stride) arguments are patched per launch with cudaGraphExecKernelNodeSetParams.
-__global__ void __launch_bounds__(256) k_import(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ dst, int pitch,
-                                                int w, int h, const uint8_t* __restrict__ src1, int stride1,
-                                                uint8_t* __restrict__ dst1) {
+// Row-wise variant for device-resident sources (4 bytes per thread, word stores into the pitched level).
+__global__ void __launch_bounds__(256) k_import_rows(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ dst, int pitch,
+                                                     int w, int h, const uint8_t* __restrict__ src1, int stride1,
+                                                     uint8_t* __restrict__ dst1) {
     TL_SCOPE(0);
     if (blockIdx.z) { src = src1; stride = stride1; dst = dst1; }  // second image of a stereo pair
     const int y = blockIdx.y;
@@ -91,14 +92,59 @@ __global__ void __launch_bounds__(256) k_import(const uint8_t* __restrict__ src,
     *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + x0) = v;  // pitch % 128 == 0 and pitch >= w rounded up to 4
 }
 
-void launch_import(const OrbGeom& g, const OrbBuffers& b, const uint8_t* src, int stride, cudaStream_t s, const OrbBuffers* b1,
-                   const uint8_t* src1, int stride1) {
-    const LevelGeom& L0 = g.lv[0];
-    dim3 grid((L0.w + 1023) / 1024, L0.h, b1 ? 2 : 1);
-    k_import<<<grid, 256, 0, s>>>(src, stride, b.pyr + L0.img_off, L0.pitch, L0.w, L0.h, src1, stride1,
-                                  b1 ? b1->pyr + L0.img_off : nullptr);
+// Flat variant for host sources (mapped page-locked memory read over PCIe).
+__global__ void __launch_bounds__(256) k_import(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ dst, int pitch,
+                                                int w, int h, const uint8_t* __restrict__ src1, int stride1,
+                                                uint8_t* __restrict__ dst1) {
+    TL_SCOPE(0);
+    if (blockIdx.z) { src = src1; stride = stride1; dst = dst1; }  // second image of a stereo pair
+    // The image is walked as a flat run of w * h bytes, 16 per thread: a contiguous, 16-byte aligned source (the usual
+    // case: a cv::Mat or a pinned staging buffer) is read with one 128-bit load per thread, i.e. 512-byte requests per
+    // warp on the PCIe link when the source is mapped host memory. (Image rows themselves are rarely aligned: 1242 % 4 = 2.)
+    const long long n = (long long)w * h;
+    const long long off = ((long long)blockIdx.x * 256 + threadIdx.x) * 16;
+    if (off >= n) return;
+    int row = (int)(off / w), col = (int)(off - (long long)row * w);
+    uint32_t v[4];
+    if (stride == w && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && off + 16 <= n) {
+        const uint4 q = *reinterpret_cast<const uint4*>(src + off);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+        int r = row, c = col;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (off + k < n) v[k >> 2] |= (uint32_t)src[(size_t)r * stride + c] << (8 * (k & 3));
+            if (++c >= w) { c = 0; r++; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (off + k < n) dst[(size_t)row * pitch + col] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
+        if (++col >= w) { col = 0; row++; }
+    }
 }
-const void* import_kernel_ptr() { return (const void*)k_import; }
+
+static dim3 import_grid(int w, int h, int n_img, bool host_src) {
+    return host_src ? dim3((unsigned)(((long long)w * h + 16 * 256 - 1) / (16 * 256)), 1, n_img) : dim3((w + 1023) / 1024, h, n_img);
+}
+
+void launch_import(const OrbGeom& g, const OrbBuffers& b, const uint8_t* src, int stride, cudaStream_t s, const OrbBuffers* b1,
+                   const uint8_t* src1, int stride1, bool host_src) {
+    const LevelGeom& L0 = g.lv[0];
+    const dim3 grid = import_grid(L0.w, L0.h, b1 ? 2 : 1, host_src);
+    if (host_src)
+        k_import<<<grid, 256, 0, s>>>(src, stride, b.pyr + L0.img_off, L0.pitch, L0.w, L0.h, src1, stride1, b1 ? b1->pyr + L0.img_off : nullptr);
+    else
+        k_import_rows<<<grid, 256, 0, s>>>(src, stride, b.pyr + L0.img_off, L0.pitch, L0.w, L0.h, src1, stride1,
+                                           b1 ? b1->pyr + L0.img_off : nullptr);
+}
+void import_launch_dims(int w, int h, int n_img, bool host_src, dim3* grid, dim3* block) {
+    *grid = import_grid(w, h, n_img, host_src);
+    *block = dim3(256);
+}
+const void* import_kernel_ptr(bool host_src) { return host_src ? (const void*)k_import : (const void*)k_import_rows; }
 
 // ------------------------------------------------------------------------------------------------ K1 resize
 // cv::resize INTER_LINEAR u8 (ORBextractor.cc:1120). Coefficient tables are built on the host exactly as OpenCV
@@ -151,12 +197,13 @@ void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_
 // arithmetic is the one of k_resize (bit-exact), pixels in the halo between tiles are computed redundantly.
 constexpr int kPyrTW = 64, kPyrTH = 32;
 
-void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, PyrPlan* plan, std::vector<int>* tab) {
+void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, int base, PyrPlan* plan, std::vector<int>* tab) {
     const int L = g.n_levels;
     PyrPlan& p = *plan;
+    p.base = base;  // the level that is read; levels base + 1 .. L - 1 are produced
     p.tw = kPyrTW; p.th = kPyrTH;
-    p.ntx = (g.lv[0].w + p.tw - 1) / p.tw;
-    p.nty = (g.lv[0].h + p.th - 1) / p.th;
+    p.ntx = (g.lv[base].w + p.tw - 1) / p.tw;
+    p.nty = (g.lv[base].h + p.th - 1) / p.th;
     tab->clear();
     int max_w[kMaxLevels] = {0}, max_h[kMaxLevels] = {0};
     for (int axis = 0; axis < 2; axis++) {
@@ -168,9 +215,9 @@ void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, PyrPlan*
         };
         // f[l][d]: where the chain of left/top sources of level-l pixel d ends in level 0
         std::vector<std::vector<int>> f(L), own(L), n0(L), n1(L);
-        for (int l = 0; l < L; l++) {
+        for (int l = base; l < L; l++) {
             f[l].resize(size_of(l));
-            for (int d = 0; d < size_of(l); d++) f[l][d] = l == 0 ? d : f[l - 1][ofs(l, d)];
+            for (int d = 0; d < size_of(l); d++) f[l][d] = l == base ? d : f[l - 1][ofs(l, d)];
             own[l].assign(nt + 1, size_of(l));
             for (int t = nt - 1; t >= 0; t--) {
                 int d = own[l][t + 1];
@@ -182,7 +229,7 @@ void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, PyrPlan*
             n1[l].assign(nt, 0);
         }
         for (int t = 0; t < nt; t++) {
-            for (int l = L - 1; l >= 0; l--) {
+            for (int l = L - 1; l >= base; l--) {
                 int a = own[l][t], b2 = own[l][t + 1] - 1;  // owned, inclusive (empty if a > b2)
                 if (l + 1 < L && n0[l + 1][t] <= n1[l + 1][t]) {
                     const int sa = ofs(l + 1, n0[l + 1][t]), sb = std::min(ofs(l + 1, n1[l + 1][t]) + 1, size_of(l) - 1);
@@ -196,7 +243,7 @@ void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, PyrPlan*
                 }
             }
         }
-        for (int l = 0; l < L; l++) {
+        for (int l = base; l < L; l++) {
             (axis == 0 ? p.xoff[l] : p.yoff[l]) = (int)tab->size();
             tab->insert(tab->end(), own[l].begin(), own[l].end());
             tab->insert(tab->end(), n0[l].begin(), n0[l].end());
@@ -204,9 +251,9 @@ void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, PyrPlan*
         }
     }
     int buf = 0, tabs = 0;
-    for (int l = 0; l < L; l++) {
-        buf = std::max(buf, ((max_w[l] + 3 + 3) & ~3) * max_h[l]);  // level 0 is stored from a 4-aligned column
-        if (l > 0) tabs += 2 * (max_w[l] + max_h[l]);
+    for (int l = base; l < L; l++) {
+        buf = std::max(buf, ((max_w[l] + 3 + 3) & ~3) * max_h[l]);  // the base level is stored from a 4-aligned column
+        if (l > base) tabs += 2 * (max_w[l] + max_h[l]);
     }
     p.buf_bytes = (buf + 15) & ~15;
     p.tab_smem_ints = tabs;
@@ -225,8 +272,8 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeom g, PyrPlan p, uint8_t* 
     __shared__ int rng[kMaxLevels][8];  // per level: x own0, own1, need0, need1, y own0, own1, need0, need1
     __shared__ int lvi[kMaxLevels][6];  // per level: w, h, pitch, img_off, xtab_off, ytab_off (read once from the parameters)
     const int tid = threadIdx.x, tx = blockIdx.x, ty = blockIdx.y;
-    const int L = g.n_levels;
-    if (tid < L * 8) {
+    const int L = g.n_levels, B = p.base;
+    if (tid < L * 8 && (tid >> 3) >= B) {
         const int l = tid >> 3, k = tid & 7, axis = k >> 2, kk = k & 3;
         const int nt = axis ? p.nty : p.ntx, t = axis ? ty : tx;
         const int* sec = p.tab + (axis ? p.yoff[l] : p.xoff[l]);
@@ -241,13 +288,13 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeom g, PyrPlan p, uint8_t* 
     // level 0 (4-byte words of the needed region of the 128-byte pitched level-0 image) and the slices of the resize
     // tables this tile needs on every level are fetched in the same phase: one round of global latency for both
     int pw;  // pitch of `cur`
-    int px0 = rng[0][2] & ~3, py0 = rng[0][6];  // origin of `cur` in level coordinates
+    int px0 = rng[B][2] & ~3, py0 = rng[B][6];  // origin of `cur` in level coordinates
     {
-        const int nh = rng[0][7] - py0 + 1;
-        const int nwords = ((rng[0][3] - px0) >> 2) + 1;
+        const int nh = rng[B][7] - py0 + 1;
+        const int nwords = ((rng[B][3] - px0) >> 2) + 1;
         pw = nwords * 4;
-        const int pitch0 = lvi[0][2];
-        const uint8_t* s0 = pyr + lvi[0][3] + (size_t)py0 * pitch0 + px0;
+        const int pitch0 = lvi[B][2];
+        const uint8_t* s0 = pyr + lvi[B][3] + (size_t)py0 * pitch0 + px0;
         const int lanes = tid & 31, rows = tid >> 5;
         for (int yy = rows; yy < nh; yy += 8)
             for (int xx = lanes; xx < nwords; xx += 32)
@@ -256,12 +303,12 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeom g, PyrPlan p, uint8_t* 
     // start of level l's staged table slice in stab
     auto slice_off = [&](int l) {
         int o = 0;
-        for (int k = 1; k < l; k++) o += 2 * (max(rng[k][3] - rng[k][2] + 1, 0) + max(rng[k][7] - rng[k][6] + 1, 0));
+        for (int k = B + 1; k < l; k++) o += 2 * (max(rng[k][3] - rng[k][2] + 1, 0) + max(rng[k][7] - rng[k][6] + 1, 0));
         return o;
     };
     {
         // warp w stages level w + 1 (and w + 9 ...): the levels' loads are in flight together
-        for (int l = 1 + (tid >> 5); l < L; l += 8) {
+        for (int l = B + 1 + (tid >> 5); l < L; l += 8) {
             const int x0 = rng[l][2], nw = rng[l][3] - x0 + 1, y0 = rng[l][6], nh = rng[l][7] - y0 + 1;
             if (nw <= 0 || nh <= 0) continue;
             int* t = stab + slice_off(l);
@@ -282,7 +329,7 @@ __global__ void __launch_bounds__(256) k_pyramid(OrbGeom g, PyrPlan p, uint8_t* 
     TR();
     int toff = 0;
 #pragma unroll 1
-    for (int l = 1; l < L; l++) {
+    for (int l = B + 1; l < L; l++) {
         const int x0 = rng[l][2], nw = rng[l][3] - x0 + 1, y0 = rng[l][6], nh = rng[l][7] - y0 + 1;
         if (nw <= 0 || nh <= 0) break;  // deeper levels need nothing either
         const int ox0 = rng[l][0], ox1 = rng[l][1], oy0 = rng[l][4], oy1 = rng[l][5];
@@ -341,8 +388,8 @@ cudaError_t prepare_pyramid(const PyrPlan& p) {
     return cudaFuncSetAttribute(k_pyramid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
-void launch_pyramid(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1) {
-    const PyrPlan& p = b.pyr_plan;
+void launch_pyramid(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1, bool tail) {
+    const PyrPlan& p = tail ? b.pyr_tail : b.pyr_plan;
     const int smem = 2 * p.buf_bytes + 4 * p.tab_smem_ints + 16;
     k_pyramid<<<dim3(p.ntx, p.nty, b1 ? 2 : 1), 256, smem, s>>>(g, p, b.pyr, b.xofs, b.alpha, b.yofs, b.beta, b1 ? b1->pyr : nullptr);
 }

@@ -32,6 +32,7 @@ struct FastImage2 {
 // ends up in level 0, a monotone map, so the owned ranges partition the level) and the inclusive range it must
 // compute (owned pixels plus everything deeper levels of the same tile read).
 struct PyrPlan {
+    int base;                                 // source level (0 for the whole pyramid)
     int tw, th, ntx, nty;
     int buf_bytes;                            // one shared-memory level buffer
     int tab_smem_ints;                        // staged resize-table slices (all levels)
@@ -66,7 +67,8 @@ struct OrbBuffers {
     int use_tma;
     int oct_fast;        // 1: k_octtree may take its closed-form path (CORB_OCT_GENERIC=1 forces the pass-by-pass code)
     const CUtensorMap* tma_dev;  // device copy of the per-level tensor maps (all-level FAST launch)
-    PyrPlan pyr_plan;
+    PyrPlan pyr_plan;    // whole pyramid from level 0 (CORB_GRAPH=hybrid|fused)
+    PyrPlan pyr_tail;    // levels pyr_tail.base + 1 .. from level pyr_tail.base: the short end of the resize chain in one launch
 };
 
 // encodes the per-level tensor maps; returns false when the driver entry point is unavailable
@@ -79,13 +81,14 @@ void build_oct_lut(const LevelGeom& L, uint16_t* out);
 // Every launch takes an optional second image (`b1`, the other handle of a stereo pair with the same geometry): the
 // grid gets z = 2 and block z works on b1, so a stereo frame costs one set of launches instead of two.
 void launch_import(const OrbGeom& g, const OrbBuffers& b, const uint8_t* src, int stride, cudaStream_t s,
-                   const OrbBuffers* b1 = nullptr, const uint8_t* src1 = nullptr, int stride1 = 0);
-const void* import_kernel_ptr();
+                   const OrbBuffers* b1 = nullptr, const uint8_t* src1 = nullptr, int stride1 = 0, bool host_src = false);
+const void* import_kernel_ptr(bool host_src);
+void import_launch_dims(int w, int h, int n_img, bool host_src, dim3* grid, dim3* block);
 void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s, const OrbBuffers* b1 = nullptr);
 // host side of PyrPlan: fills everything but `tab` (returned in tab_host for the caller to upload)
-void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, PyrPlan* plan, std::vector<int>* tab_host);
+void build_pyr_plan(const OrbGeom& g, const int* xofs, const int* yofs, int base, PyrPlan* plan, std::vector<int>* tab_host);
 cudaError_t prepare_pyramid(const PyrPlan& p);
-void launch_pyramid(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1 = nullptr);
+void launch_pyramid(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1 = nullptr, bool tail = false);
 void launch_fast_all(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1 = nullptr);
 void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s, const OrbBuffers* b1 = nullptr);
 void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1 = nullptr);
