@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 struct corb_matcher;
 
@@ -204,16 +205,23 @@ __device__ inline void three_maxima_counts(const int* cnt, int L, int& ind1, int
 
 constexpr int kResolveChunk = 1024, kHeads = 4;
 
-__global__ void __launch_bounds__(256) k_proj_resolve(ProjFrame F, ProjQueries Q, ProjWork W) {
-    extern __shared__ uint8_t s_taken[];  // [F.n] then heads
+__global__ void __launch_bounds__(256) k_proj_resolve(ProjFrame F, ProjQueries Q, ProjWork W, int stage_angle) {
+    // Everything the serial walk touches sits in shared memory: a global load on its path would cost one L2 round trip
+    // (~700 cycles) per query, ten times the walk itself.
+    extern __shared__ uint8_t s_dyn[];  // [F.n] taken flags, then (stage_angle) [F.n] frame angles
+    uint8_t* s_taken = s_dyn;
+    const float* s_angle = stage_angle ? reinterpret_cast<const float*>(s_dyn + ((F.n + 15) & ~15)) : F.angle;
     __shared__ uint2 heads[kResolveChunk][kHeads];
     __shared__ int hn[kResolveChunk];
+    __shared__ float s_aux[kResolveChunk];
+    __shared__ uint8_t s_blocks[kResolveChunk];
     __shared__ int bins[kHistoLength];
     __shared__ int s_nm, s_nev, s_keep[3];
     const int tid = threadIdx.x;
     for (int i = tid; i < F.n; i += 256) {
         s_taken[i] = F.taken ? F.taken[i] : 0;
         W.match[i] = -1;
+        if (stage_angle) reinterpret_cast<float*>(s_dyn + ((F.n + 15) & ~15))[i] = F.angle[i];
     }
     if (tid < kHistoLength) bins[tid] = 0;
     if (tid == 0) { s_nm = 0; s_nev = 0; }
@@ -224,53 +232,89 @@ __global__ void __launch_bounds__(256) k_proj_resolve(ProjFrame F, ProjQueries Q
         for (int i = tid; i < cn * kHeads; i += 256) {
             const int ql = i / kHeads, h = i - ql * kHeads;
             const int nc = W.ncand[c0 + ql];
-            if (h == 0) hn[ql] = nc;
+            if (h == 0) {
+                hn[ql] = nc;
+                s_aux[ql] = Q.aux[c0 + ql];
+                s_blocks[ql] = Q.blocks ? Q.blocks[c0 + ql] : 1;
+            }
             if (h < nc) heads[ql][h] = W.cand[(size_t)(c0 + ql) * W.K + h];
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid < 32) {
+            // One warp walks the chunk 32 queries at a time. Every lane proposes the first (and, for the ratio test, the
+            // second) entry of its sorted list that is not taken yet; a lane is final when no earlier lane of the batch
+            // takes one of the features it looked at, so the longest conflict-free prefix commits at once and the rest
+            // proposes again. The lowest pending lane never conflicts, and conflicts are rare (a few per batch), so this
+            // is the reference's query order at ~1/20 of the cost of a one-thread walk.
+            const int lane = tid;
             int nm = s_nm, nev = s_nev;
-            for (int ql = 0; ql < cn; ql++) {
-                const int nc = hn[ql];
-                if (nc == 0) continue;
-                const int q = c0 + ql;
+            for (int base = 0; base < cn; base += 32) {
+                const int ql = base + lane, q = c0 + ql;
+                const int nc = ql < cn ? hn[ql] : 0;
                 const uint2* full = W.cand + (size_t)q * W.K;
-                // first and second not-yet-taken entries of the sorted list = best and second best of the reference's scan
-                int found = 0;
-                uint2 e1 = make_uint2(0, 0), e2 = make_uint2(0, 0);
-                for (int h = 0; h < nc && found < 2; h++) {
-                    const uint2 e = h < kHeads ? heads[ql][h] : full[h];
-                    if (s_taken[e.y & 0xffffff]) continue;
-                    if (found == 0) e1 = e; else e2 = e;
-                    found++;
-                    if (Q.variant == 0) break;  // the last-frame variant has no ratio test
-                }
-                if (found == 0) continue;
-                const int bestDist = (int)(e1.x >> 20), bestIdx = (int)(e1.y & 0xffffff);
-                if (bestDist > kThHigh) continue;
-                if (Q.variant == 1) {
-                    const int bestLevel = (int)(e1.y >> 24);
-                    const int bestDist2 = found > 1 ? (int)(e2.x >> 20) : 256, bestLevel2 = found > 1 ? (int)(e2.y >> 24) : -1;
-                    if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(Q.nnratio, (float)bestDist2)) continue;  // :117-120
-                }
-                W.match[bestIdx] = q;
-                if (!Q.blocks || Q.blocks[q]) s_taken[bestIdx] = 1;
-                nm++;
-                if (Q.variant == 0 && Q.check_ori) {
-                    float rot = __fsub_rn(Q.aux[q], F.angle[bestIdx]);  // :1585-1593
-                    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-                    int bin = (int)roundf(__fmul_rn(rot, factor));
-                    if (bin == kHistoLength) bin = 0;
-                    if (bin >= 0 && bin < kHistoLength) {
-                        bins[bin]++;
-                        W.ev_idx[nev] = bestIdx;
-                        W.ev_bin[nev] = bin;
-                        nev++;
+                unsigned pending = __ballot_sync(0xffffffffu, nc > 0);
+                int hpos = 0;
+                while (pending) {
+                    const bool mine = pending >> lane & 1u;
+                    int found = 0, f1 = -1, f2 = -1;
+                    uint2 e1 = make_uint2(0, 0), e2 = make_uint2(0, 0);
+                    if (mine) {
+                        for (int h = hpos; h < nc && found < (Q.variant == 1 ? 2 : 1); h++) {
+                            const uint2 e = h < kHeads ? heads[ql][h] : full[h];
+                            if (s_taken[e.y & 0xffffff]) continue;
+                            if (found == 0) { e1 = e; hpos = h; } else e2 = e;
+                            found++;
+                        }
+                        if (found > 0) f1 = (int)(e1.y & 0xffffff);
+                        if (found > 1) f2 = (int)(e2.y & 0xffffff);
                     }
+                    bool acc = false;
+                    if (found > 0) {
+                        const int bestDist = (int)(e1.x >> 20);
+                        acc = bestDist <= kThHigh;
+                        if (acc && Q.variant == 1) {
+                            const int bestLevel = (int)(e1.y >> 24);
+                            const int bestDist2 = found > 1 ? (int)(e2.x >> 20) : 256, bestLevel2 = found > 1 ? (int)(e2.y >> 24) : -1;
+                            if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(Q.nnratio, (float)bestDist2)) acc = false;  // :117-120
+                        }
+                    }
+                    const unsigned accmask = __ballot_sync(0xffffffffu, mine && acc);
+                    bool conflicted = false;
+                    for (unsigned mm = accmask; mm; mm &= mm - 1) {  // every accepting lane against the later lanes' first / second entries
+                        const int j = __ffs(mm) - 1;
+                        const int pj = __shfl_sync(0xffffffffu, f1, j);
+                        if (j < lane && (pj == f1 || pj == f2)) conflicted = true;
+                    }
+                    const unsigned confmask = __ballot_sync(0xffffffffu, mine && conflicted);
+                    const int first_conf = confmask ? __ffs(confmask) - 1 : 32;
+                    const bool commit = mine && lane < first_conf;
+                    bool ev = false;
+                    int bin = 0;
+                    if (commit && acc) {
+                        W.match[f1] = q;
+                        if (s_blocks[ql]) s_taken[f1] = 1;
+                        if (Q.variant == 0 && Q.check_ori) {
+                            float rot = __fsub_rn(s_aux[ql], s_angle[f1]);  // :1585-1593
+                            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                            bin = (int)roundf(__fmul_rn(rot, factor));
+                            if (bin == kHistoLength) bin = 0;
+                            ev = bin >= 0 && bin < kHistoLength;
+                        }
+                    }
+                    const unsigned cm = __ballot_sync(0xffffffffu, commit && acc), em = __ballot_sync(0xffffffffu, ev);
+                    if (ev) {
+                        const int pos = nev + __popc(em & ((1u << lane) - 1u));
+                        atomicAdd(&bins[bin], 1);
+                        W.ev_idx[pos] = f1;
+                        W.ev_bin[pos] = bin;
+                    }
+                    nm += __popc(cm);
+                    nev += __popc(em);
+                    pending &= first_conf >= 32 ? 0u : ~((1u << first_conf) - 1u);
+                    __syncwarp();
                 }
             }
-            s_nm = nm;
-            s_nev = nev;
+            if (lane == 0) { s_nm = nm; s_nev = nev; }
         }
     }
     __syncthreads();
@@ -328,6 +372,9 @@ static int run_projection(corb_matcher* m, const corb_frame_view* f, int variant
         backward = -tlc[2] > f->mb && !mono;
     }
     for (int K = 128;; K = 1024) {
+#ifdef CORB_PROJ_TRACE
+        const auto tp0 = std::chrono::steady_clock::now();
+#endif
         // ---- pack everything into one pinned block -> one H2D copy
         size_t off = 0;
         auto take = [&](size_t bytes) { const size_t o = off; off = align_up_sz(off + bytes, 16); return o; };
@@ -353,6 +400,13 @@ static int run_projection(corb_matcher* m, const corb_frame_view* f, int variant
         if (blocks) memcpy(h + oQb, blocks, nq); else memset(h + oQb, 1, nq);
         memcpy(h + oQx, xyz, 12 * (size_t)nq); memcpy(h + oQd, qdesc, 32 * (size_t)nq); memcpy(h + oQl, level, 4 * (size_t)nq);
         memcpy(h + oQa, aux, 4 * (size_t)nq);
+#ifdef CORB_PROJ_TRACE
+        static cudaEvent_t e0, e1, e2, e3;
+        static bool evi = false;
+        if (!evi) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3); evi = true; }
+        const auto tp1 = std::chrono::steady_clock::now();
+        cudaEventRecord(e0, st);
+#endif
         CORB_CUDA(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
         CORB_CUDA(cudaMemsetAsync(d + oMisc, 0, 16, st));
         ProjFrame F;
@@ -373,13 +427,36 @@ static int run_projection(corb_matcher* m, const corb_frame_view* f, int variant
         W.match = (int*)(d + oOut); W.nmatches = (int*)(d + oMisc); W.overflow = W.nmatches + 1; W.K = K;
         const size_t sm1 = (size_t)8 * K * sizeof(uint2);
         if (sm1 > 48 * 1024) CORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+#ifdef CORB_PROJ_TRACE
+        cudaEventRecord(e1, st);
+#endif
         k_proj_candidates<<<(nq + 7) / 8, 256, sm1, st>>>(F, Q, W);
-        CORB_CHECK(n <= 160 * 1024, CORB_ERR_UNSUPPORTED, "frame with %d features", n);
-        if (n > 8 * 1024) CORB_CUDA(cudaFuncSetAttribute(k_proj_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, n + 16));
-        k_proj_resolve<<<1, 256, (size_t)n + 16, st>>>(F, Q, W);
+#ifdef CORB_PROJ_TRACE
+        cudaEventRecord(e2, st);
+#endif
+        CORB_CHECK(n <= 128 * 1024, CORB_ERR_UNSUPPORTED, "frame with %d features", n);
+        const int stage_angle = n <= 24 * 1024;
+        const size_t sm2 = (size_t)((n + 15) & ~15) + (stage_angle ? 4 * (size_t)n : 0) + 16;
+        CORB_CUDA(cudaFuncSetAttribute(k_proj_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm2, 1024)));
+        k_proj_resolve<<<1, 256, sm2, st>>>(F, Q, W, stage_angle);
         CORB_CUDA(cudaGetLastError());
+#ifdef CORB_PROJ_TRACE
+        cudaEventRecord(e3, st);
+#endif
         CORB_CUDA(cudaMemcpyAsync(h + oOut, d + oOut, 4 * (size_t)n + 16, cudaMemcpyDeviceToHost, st));
         CORB_CUDA(cudaStreamSynchronize(st));
+#ifdef CORB_PROJ_TRACE
+        {
+            float a = 0, b2 = 0, c2 = 0;
+            cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b2, e1, e2); cudaEventElapsedTime(&c2, e2, e3);
+            const auto tp2 = std::chrono::steady_clock::now();
+            static int cnt = 0;
+            if (++cnt % 50 == 0)
+                printf("proj trace: pack %.1f us | h2d %.1f us candidates %.1f us resolve %.1f us | launch..sync %.1f us\n",
+                       std::chrono::duration<double, std::micro>(tp1 - tp0).count(), a * 1e3, b2 * 1e3, c2 * 1e3,
+                       std::chrono::duration<double, std::micro>(tp2 - tp1).count());
+        }
+#endif
         const int* misc = (const int*)(h + oMisc);
         if (misc[1] > K) {  // a candidate list did not fit: once more with room for 1024 per query
             CORB_CHECK(K < 1024 && misc[1] <= 1024, CORB_ERR_CAPACITY, "%d candidates in one search window", misc[1]);
