@@ -96,6 +96,7 @@ def lib():
         L.corb_orb_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
         L.corb_orb_sync.argtypes = [vp]
         L.corb_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.corb_orb_host_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i32p]
         L.corb_orb_device_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), i32p, i32p, i32p]
         L.corb_orb_stream.argtypes = [vp]
         L.corb_orb_stream.restype = vp

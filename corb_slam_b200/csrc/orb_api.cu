@@ -92,6 +92,8 @@ struct corb_orb {
     float* h_stereo = nullptr;   // pinned [u_right | depth]
     cudaEvent_t ev_peer = nullptr;
     int stereo_cap = 0;
+    int* d_bands = nullptr;      // right-keypoint row bands for the stereo matcher (owned by dev_allocs)
+    int stereo_bands = 0;
 };
 
 static void free_plan(corb_orb* h) {
@@ -611,6 +613,11 @@ static void fill_stereo_args(corb_orb* left, corb_orb* right, float mbf, float m
     a->u_right = left->d_stereo; a->depth = left->d_stereo + g.kp_cap;
     a->best_dist = reinterpret_cast<int*>(left->d_stereo + 2 * (size_t)g.kp_cap);
     a->n_rows = g.lv[0].h;
+    a->n_bands = left->stereo_bands;
+    a->band_cap = g.kp_cap;
+    a->band_cnt = left->d_bands;
+    a->band_list = left->d_bands + align_up(left->stereo_bands, 64);
+    a->rinfo = reinterpret_cast<int4*>(left->d_bands + align_up(left->stereo_bands, 64) + align_up_sz((size_t)left->stereo_bands * g.kp_cap, 4));
 }
 
 static int ensure_stereo_buffers(corb_orb* left) {
@@ -621,6 +628,12 @@ static int ensure_stereo_buffers(corb_orb* left) {
         if (left->h_stereo) cudaFreeHost(left->h_stereo), left->h_stereo = nullptr;
         CORB_CUDA(cudaMallocHost(&left->h_stereo, 2 * (size_t)g.kp_cap * sizeof(float)));
         left->stereo_cap = g.kp_cap;
+        // 8-row bands of right keypoints: counters | lists [bands][kp_cap] | per-keypoint records (int4)
+        left->stereo_bands = (g.lv[0].h + 7) / 8 + 1;
+        const size_t ints = (size_t)align_up(left->stereo_bands, 64) + align_up_sz((size_t)left->stereo_bands * g.kp_cap, 4) + 4 * (size_t)g.kp_cap + 16;
+        rc = dev_alloc(left, &left->d_bands, ints);
+        if (rc != CORB_OK) return rc;
+        CORB_CUDA(cudaMemset(left->d_bands, 0, (size_t)align_up(left->stereo_bands, 64) * sizeof(int)));
     }
     return CORB_OK;
 }
@@ -1063,6 +1076,17 @@ int corb_orb_device_results(const corb_orb* h, const corb_keypoint** d_kps, cons
     if (d_kps) *d_kps = h->buf.kps;
     if (d_desc) *d_desc = h->buf.desc;
     if (d_count) *d_count = h->buf.count;
+    return CORB_OK;
+}
+
+int corb_orb_host_results(const corb_orb* h, const corb_keypoint** kps, const uint8_t** desc, int* n) {
+    CORB_CHECK(h && h->plan_w && h->h_scalars, CORB_ERR_INVALID, "no extraction has run on this handle");
+    CORB_CHECK(h->h_scalars[1] == 0, CORB_ERR_CAPACITY, "device-side consistency check %d failed", h->h_scalars[1]);
+    const int cnt = h->h_scalars[0];
+    CORB_CHECK(cnt >= 0 && cnt <= h->geom.kp_cap, CORB_ERR_CAPACITY, "keypoint count %d out of range", cnt);
+    if (kps) *kps = h->h_kps;
+    if (desc) *desc = h->h_desc;
+    if (n) *n = cnt;
     return CORB_OK;
 }
 

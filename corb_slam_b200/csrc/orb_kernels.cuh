@@ -108,6 +108,12 @@ struct StereoArgs {
     float *u_right, *depth;      // [kp_cap]
     int* best_dist;              // [kp_cap] SAD of the accepted match, -1 if none
     int n_rows;
+    // right keypoints bucketed by 8-row bands (a keypoint sits in every band its row range touches): the coarse form of
+    // the reference's vRowIndices (Frame.cc:487-497); the exact row test is applied per candidate
+    int4* rinfo;                 // [kp_cap] (min row, max row, octave, x bits) per right keypoint
+    int* band_cnt;               // [n_bands] entries per band; zeroed by k_stereo_outliers for the next frame
+    int* band_list;              // [n_bands][band_cap] right keypoint indices
+    int n_bands, band_cap;
 };
 
 void launch_stereo(const OrbGeom& g, const StereoArgs& a, cudaStream_t s);

@@ -13,6 +13,23 @@ namespace corb {
 
 constexpr int kThHigh = 100, kThLowS = 50;
 
+constexpr int kBandShift = 3;  // 8 image rows per band
+
+// one thread per right keypoint: row range / octave / x record + membership in the bands its rows touch
+__global__ void __launch_bounds__(256) k_stereo_bands(OrbGeom g, StereoArgs a) {
+    const int jr = blockIdx.x * 256 + threadIdx.x;
+    if (jr >= *a.nr) return;
+    const corb_keypoint kpR = a.kr[jr];
+    const float r = __fmul_rn(2.0f, a.scale[kpR.octave]);
+    const int lo = (int)floorf(__fsub_rn(kpR.y, r)), hi = (int)ceilf(__fadd_rn(kpR.y, r));
+    a.rinfo[jr] = make_int4(lo, hi, kpR.octave, __float_as_int(kpR.x));
+    const int b0 = max(lo, 0) >> kBandShift, b1 = min(min(hi, a.n_rows - 1) >> kBandShift, a.n_bands - 1);
+    for (int b = b0; b <= b1; b++) {
+        const int pos = atomicAdd(&a.band_cnt[b], 1);
+        if (pos < a.band_cap) a.band_list[(size_t)b * a.band_cap + pos] = jr;
+    }
+}
+
 // one warp per left keypoint
 __global__ void __launch_bounds__(256) k_stereo_match(OrbGeom g, StereoArgs a) {
     const int iL = (blockIdx.x * 256 + threadIdx.x) >> 5;
@@ -29,37 +46,31 @@ __global__ void __launch_bounds__(256) k_stereo_match(OrbGeom g, StereoArgs a) {
     float out_u = -1.0f, out_d = -1.0f;
     int out_sad = -1;
     int bestDist = kThHigh, bestIdx = INT_MAX;
-    // The 8 left keypoints of this block scan the right keypoints in tiles of 256 staged in shared memory as
-    // (min row, max row, octave, x): the row-table membership test of the reference (:487-497) becomes two compares.
-    __shared__ int4 tile[256];
+    // The left keypoint looks only at the right keypoints of its 8-row band (a twentieth of them on a 375-row image);
+    // the exact row-table membership of the reference (:487-497) is two compares on the keypoint's record. The reference
+    // scans candidates in ascending right index and keeps the first minimum: here the order inside a band is arbitrary,
+    // so ties go to the lower index explicitly.
     const bool searching = iL < nl && !(maxU < 0) && row >= 0 && row < a.n_rows;
     uint4 l0 = make_uint4(0, 0, 0, 0), l1 = l0;
-    if (searching) { l0 = a.dl[2 * iL]; l1 = a.dl[2 * iL + 1]; }
-    for (int base = 0; base < nr; base += 256) {
-        __syncthreads();
-        const int jr = base + threadIdx.x;
-        if (jr < nr) {
-            const corb_keypoint kpR = a.kr[jr];
-            const float r = __fmul_rn(2.0f, a.scale[kpR.octave]);
-            tile[threadIdx.x] = make_int4((int)floorf(__fsub_rn(kpR.y, r)), (int)ceilf(__fadd_rn(kpR.y, r)), kpR.octave,
-                                          __float_as_int(kpR.x));
-        }
-        __syncthreads();
-        if (!searching) continue;
-        const int cnt = min(256, nr - base);
+    if (searching) {
+        l0 = a.dl[2 * iL]; l1 = a.dl[2 * iL + 1];
+        const int band = min(row >> kBandShift, a.n_bands - 1);
+        const int cnt = min(a.band_cnt[band], a.band_cap);
+        const int* list = a.band_list + (size_t)band * a.band_cap;
         for (int j = lane; j < cnt; j += 32) {
-            const int4 t = tile[j];
+            const int iR = list[j];
+            const int4 t = a.rinfo[iR];
             if (row < t.x || row > t.y) continue;                          // vRowIndices[(int)vL] membership (:487-497)
             if (t.z < levelL - 1 || t.z > levelL + 1) continue;
             const float uR = __int_as_float(t.w);
             if (!(uR >= minU && uR <= maxU)) continue;
-            const int iR = base + j;
             const uint4 r0 = a.dr[2 * iR], r1 = a.dr[2 * iR + 1];
             const int d = __popc(l0.x ^ r0.x) + __popc(l0.y ^ r0.y) + __popc(l0.z ^ r0.z) + __popc(l0.w ^ r0.w) + __popc(l1.x ^ r1.x) +
                           __popc(l1.y ^ r1.y) + __popc(l1.z ^ r1.z) + __popc(l1.w ^ r1.w);
-            if (d < bestDist) { bestDist = d; bestIdx = iR; }              // ascending iR per lane: first minimum wins
+            if (d < bestDist || (d == bestDist && iR < bestIdx)) { bestDist = d; bestIdx = iR; }
         }
     }
+    (void)nr;
     if (iL >= nl) {
         if (lane == 0 && iL < g.kp_cap) { a.u_right[iL] = -1.0f; a.depth[iL] = -1.0f; a.best_dist[iL] = -1; }
         return;
@@ -142,6 +153,7 @@ __global__ void __launch_bounds__(1024) k_stereo_outliers(OrbGeom g, StereoArgs 
     __shared__ int s_sel[3];  // [0] selected bin, [1] remaining rank, [2] count
     const int tid = threadIdx.x;
     const int nl = *a.nl;
+    for (int i = tid; i < a.n_bands; i += 1024) a.band_cnt[i] = 0;  // k_stereo_match is done with the bands: ready for the next frame
     int hi_bin = 0, k = 0;
     for (int pass = 0; pass < 2; pass++) {
         if (tid < 256) hist[tid] = 0;
@@ -183,6 +195,7 @@ __global__ void __launch_bounds__(1024) k_stereo_outliers(OrbGeom g, StereoArgs 
 }
 
 void launch_stereo(const OrbGeom& g, const StereoArgs& a, cudaStream_t s) {
+    k_stereo_bands<<<(g.kp_cap + 255) / 256, 256, 0, s>>>(g, a);
     k_stereo_match<<<(g.kp_cap * 32 + 255) / 256, 256, 0, s>>>(g, a);
     k_stereo_outliers<<<1, 1024, 0, s>>>(g, a);
 }

@@ -46,6 +46,17 @@ class ORBextractor:
         except Exception:  # interpreter shutdown: module globals are already gone, the process frees the device memory
             pass
 
+    def host_results(self):
+        """(keypoints, descriptors) of the last completed extraction as views of the handle's page-locked result buffer
+        (corb_orb_host_results); valid until the next extraction on this handle."""
+        kp, dp, n = C.c_void_p(), C.c_void_p(), C.c_int32()
+        check(lib().corb_orb_host_results(self._h, C.byref(kp), C.byref(dp), C.byref(n)))
+        if n.value == 0:
+            return np.empty(0, KP_DTYPE), None
+        k = np.frombuffer((C.c_uint8 * (n.value * KP_DTYPE.itemsize)).from_address(kp.value), KP_DTYPE)
+        d = np.frombuffer((C.c_uint8 * (n.value * 32)).from_address(dp.value), np.uint8).reshape(n.value, 32)
+        return k, d
+
     # ---- getters (ORBextractor.h:63-85)
     def GetLevels(self):
         return self.nlevels
@@ -194,6 +205,11 @@ def extract_stereo(ex_left, ex_right, left, right, want_pyramid=False):
         outs.append(ex._out)
     nl, nr = C.c_int32(), C.c_int32()
     pl = pr = None
+    if not want_pyramid and not ex_left.copy_outputs and not ex_right.copy_outputs:
+        # zero-copy: the results are read in place from the handles' page-locked result buffers
+        check(lib().corb_orb_extract_pair(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0],
+                                          None, None, C.byref(nl), None, None, C.byref(nr), None, None))
+        return tuple(ex.host_results() for ex in (ex_left, ex_right))
     if want_pyramid:
         pyrs = [[np.empty(ex.level_size(l, w, h)[::-1], np.uint8) for l in range(ex.nlevels)] for ex in (ex_left, ex_right)]
         pl = (C.c_void_p * ex_left.nlevels)(*[a.ctypes.data for a in pyrs[0]])

@@ -109,6 +109,11 @@ CORB_API int corb_orb_sync(corb_orb* h);
 /* device pointers of the last extraction: keypoints [capacity], descriptors [capacity*32], count [1] */
 CORB_API int corb_orb_device_results(const corb_orb* h, const corb_keypoint** d_kps, const uint8_t** d_desc,
                                      const int** d_count);
+/* Zero-copy form of the host results: the extraction calls accept NULL for `kps` / `desc`; the results of the last
+ * completed extraction on `h` can then be read in place from the handle's page-locked result buffer (where the D2H node
+ * of the frame graph put them). Valid until the next extraction on the handle. The shim builds std::vector<cv::KeyPoint>
+ * straight from these (one pass over the data instead of two). */
+CORB_API int corb_orb_host_results(const corb_orb* h, const corb_keypoint** kps, const uint8_t** desc, int* n);
 /* device pointer + pitch of pyramid level l (un-blurred if blurred == 0) of the last extraction */
 CORB_API int corb_orb_device_level(const corb_orb* h, int level, int blurred, const uint8_t** d_ptr, int* pitch, int* lw,
                                    int* lh);

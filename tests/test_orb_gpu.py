@@ -217,3 +217,21 @@ def test_sparse_and_clustered_keys_fall_back_to_generic_quadtree():
         x, y = int(rng.integers(600, 720)), int(rng.integers(150, 240))
         img2[y:y + 3, x:x + 3] = int(rng.integers(120, 255))
     _compare(img2)
+
+
+def test_zero_copy_host_results_equal_copied_results():
+    """corb_orb_host_results: NULL output pointers + views of the page-locked result buffer give the same keypoints and
+    descriptors as the copying form (and as the oracle)."""
+    from corb_slam_b200 import extract_stereo
+    left, right = stereo_frame(31)
+    a, b = ORBextractor(*PARAMS), ORBextractor(*PARAMS)
+    (kl, dl), (kr, dr) = extract_stereo(a, b, left, right)
+    a.copy_outputs = b.copy_outputs = False
+    (vl, wl), (vr, wr) = extract_stereo(a, b, left, right)
+    assert vl.tobytes() == kl.tobytes() and vr.tobytes() == kr.tobytes()
+    np.testing.assert_array_equal(wl, dl)
+    np.testing.assert_array_equal(wr, dr)
+    okp, odesc = oracle.OrbExtractor(*PARAMS)(right)
+    assert vr.tobytes() == okp.tobytes()
+    np.testing.assert_array_equal(wr, odesc)
+    a.close(); b.close()
