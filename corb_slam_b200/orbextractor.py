@@ -261,6 +261,10 @@ def frame_stereo(ex_left, ex_right, left, right, mbf, mb):
         ex_left._stereo_out = (np.empty(len(outs[0][0]), np.float32), np.empty(len(outs[0][0]), np.float32))
     ur, dp = ex_left._stereo_out
     nl, nr = C.c_int32(), C.c_int32()
+    if not ex_left.copy_outputs and not ex_right.copy_outputs:  # zero-copy keypoints / descriptors (corb_orb_host_results)
+        check(lib().corb_frame_stereo(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0], float(mbf),
+                                      float(mb), None, None, C.byref(nl), None, None, C.byref(nr), ur.ctypes.data, dp.ctypes.data))
+        return ex_left.host_results(), ex_right.host_results(), ur[:nl.value], dp[:nl.value]
     check(lib().corb_frame_stereo(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0], float(mbf),
                                   float(mb), outs[0][0].ctypes.data, outs[0][1].ctypes.data, C.byref(nl), outs[1][0].ctypes.data,
                                   outs[1][1].ctypes.data, C.byref(nr), ur.ctypes.data, dp.ctypes.data))
