@@ -142,6 +142,7 @@ struct BaDev {
     const int *first, *rowoff, *coloff, *col_rows;
     const int *coloff_b, *col_rows_b;
     const int *chunk_start;        // [n_chunks + 1] band columns of each independent chunk
+    double *syrk_part;             // [border pairs][n_chunks][36] per-chunk parts of the border x border update
     double *bpart;                 // [n_border][n_chunks][6] per-chunk parts of the border rows' forward substitution  // same lists without the border rows in the band columns (bordered solve)
     double *S, *bs;                // reduced system: [S | bs] contiguous
     double *invd;                  // [Pf * 6] reciprocals of the diagonal of the Cholesky factor (triangular solves multiply)
@@ -352,18 +353,24 @@ __global__ void __launch_bounds__(256) k_ba_dinv(BaDev d, double lambda) {
 // ---- K11b: one warp per keyframe = one block row of the reduced system:
 //      S(j, j') = Hpp(j) [j'=j] - sum_l W_jl Dinv_l W_j'l^T  for j' <= j,   bs(j) = bp(j) - sum_l W_jl Dinv_l bl
 //      lane = entry (r,c) of the 6x6 block (lanes 0..3 also own entries 32..35); the warp walks its edges in order.
+//      The kAccBlocks blocks next to the diagonal (all of a band row's envelope) are accumulated in shared memory and
+//      written once: a read-modify-write on global memory per term made every term of a row wait one L2 round trip
+//      for the previous one. Blocks further left (long-range rows) still accumulate in global memory, which the host
+//      has zeroed (cudaMemsetAsync over S). The order of the terms per entry is unchanged (edge order).
+constexpr int kAccBlocks = 8;
 __global__ void __launch_bounds__(256) k_ba_schur_rows(BaDev d) {
+    __shared__ double acc[8][kAccBlocks][36];
     const int pi = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (pi >= d.P) return;
     const int j = d.pfree[pi];
     if (j < 0) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int fj = d.first[j];
     double* row = d.S + (size_t)d.rowoff[j] * 36;
-    const int nrow = (j - fj + 1) * 36;
-    for (int i = lane; i < nrow; i += 32) row[i] = 0.0;
+    const int jacc = max(fj, j - kAccBlocks + 1);  // blocks jacc..j live in acc[w][j2 - jacc]
+    for (int i = lane; i < kAccBlocks * 36; i += 32) (&acc[w][0][0])[i] = 0.0;
     __syncwarp();
-    double* diag = row + (size_t)(j - fj) * 36;
+    double* diag = acc[w][j - jacc];
     diag[lane] = d.Hpp[(size_t)j * 36 + lane];
     if (lane < 4) diag[32 + lane] = d.Hpp[(size_t)j * 36 + 32 + lane];
     __syncwarp();
@@ -390,11 +397,13 @@ __global__ void __launch_bounds__(256) k_ba_schur_rows(BaDev d) {
             const int j2 = d.pfree[d.e_pose[e2]];
             if (j2 < 0 || j2 > j) continue;
             const double* W2 = d.W + (size_t)e2 * 18;
-            double* blk = row + (size_t)(j2 - fj) * 36;
+            double* blk = j2 >= jacc ? acc[w][j2 - jacc] : row + (size_t)(j2 - fj) * 36;
             blk[lane] -= bd0[0] * W2[c0 * 3] + bd0[1] * W2[c0 * 3 + 1] + bd0[2] * W2[c0 * 3 + 2];
             if (lane < 4) blk[32 + lane] -= bd1[0] * W2[c1 * 3] + bd1[1] * W2[c1 * 3 + 1] + bd1[2] * W2[c1 * 3 + 2];
         }
     }
+    __syncwarp();
+    for (int i = lane; i < (j - jacc + 1) * 36; i += 32) row[(size_t)(jacc - fj) * 36 + i] = (&acc[w][0][0])[i];
     if (lane < 6) d.bs[(size_t)j * 6 + lane] = d.bp[(size_t)j * 6 + lane] - coeff;
 }
 
@@ -713,6 +722,114 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
 #endif
 }
 
+// ---- K12e: the dense border block (border columns n_band .. n-1), left-looking, one CTA.
+//      The right-looking sweep applied every column's trailing update as read-modify-writes on the whole remaining
+//      block: with ~50 active rows that is 1 400 blocks per column through one SM's L2 port, and each pass waits for
+//      the previous one (2 ms per solve). Left-looking, block (a, k) is formed when column k is reached:
+//      T_ak = A_ak - sum_{c < k} L_ac L_kc^T reads only finished blocks (contiguous in each row's storage), one warp per
+//      block, no read-modify-write; warp 0 forms the diagonal block first and factors it while the other warps form the
+//      rest of the column. Per entry the terms are subtracted in ascending column order with the same 6-term sums, so
+//      the factor is bit-identical to the right-looking one. The band-column terms of these blocks were applied by
+//      k_ba_border_syrk; the forward substitution (y_k) rides along.
+__global__ void __launch_bounds__(1024) k_ba_border_dense(BaDev d, int n_band) {
+    extern __shared__ double dsm[];  // T[max items][36] | ys[nbord][6]
+    __shared__ double Lkk[36], Lki[6], bk[6];
+    __shared__ int s_fail;
+    const int n = d.Pf, nbord = n - n_band;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* T = dsm;
+    double* ys = dsm + (size_t)(nbord + 1) * 36;
+    if (tid == 0) s_fail = d.scalars[4] != 0.0;
+    __syncthreads();
+    const int r0 = lane / 6, c0 = lane - r0 * 6, c1 = 2 + lane;  // entries `lane` and `32 + lane` (lane < 4)
+    for (int k = n_band; k < n && !s_fail; k++) {
+        const int cb = d.coloff[k], nact = d.coloff[k + 1] - cb;
+        const int* rows = d.col_rows + cb;
+        const int fk = d.first[k];
+        const double* rowk = d.S + (size_t)(d.rowoff[k] - fk) * 36;  // block (k, c) at rowk + c * 36
+        // ---- form the column: item 0 = diagonal, item i = (rows[i - 1], k)
+        for (int it = warp; it <= nact; it += 32) {
+            const int a = it == 0 ? k : rows[it - 1];
+            const int fa = d.first[a];
+            const double* rowa = d.S + (size_t)(d.rowoff[a] - fa) * 36;
+            double t0 = rowa[(size_t)k * 36 + lane];
+            double t1 = lane < 4 ? rowa[(size_t)k * 36 + 32 + lane] : 0.0;
+            const int clo = max(n_band, max(fa, fk));
+            for (int c = clo; c < k; c++) {
+                const double* La = rowa + (size_t)c * 36;
+                const double* Lb = rowk + (size_t)c * 36;
+                double s0 = 0, s1 = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) s0 += La[r0 * 6 + q] * Lb[c0 * 6 + q];
+                t0 = t0 - s0;
+                if (lane < 4) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) s1 += La[30 + q] * Lb[c1 * 6 + q];
+                    t1 = t1 - s1;
+                }
+            }
+            T[it * 36 + lane] = t0;
+            if (lane < 4) T[it * 36 + 32 + lane] = t1;
+            if (it == 0) {  // warp 0: factor the diagonal block right away
+                __syncwarp();
+                double* D = const_cast<double*>(rowk) + (size_t)k * 36;
+                if (!warp_chol6(T, nullptr, Lkk, lane, Lki, d.invd + (size_t)k * 6) && lane == 0) s_fail = 1;
+                if (lane < 21) {  // warp_chol6 left L_kk in T[0..35] and Lkk; the factor's home is the skyline
+                    const int rr = lane >= 15 ? 5 : lane >= 10 ? 4 : lane >= 6 ? 3 : lane >= 3 ? 2 : lane >= 1 ? 1 : 0;
+                    const int cc = lane - rr * (rr + 1) / 2;
+                    D[rr * 6 + cc] = Lkk[rr * 6 + cc];
+                    if (rr != cc) D[cc * 6 + rr] = 0.0;
+                }
+            }
+        }
+        if (warp == 31 && lane < 6) {  // b_k -= sum_c L_kc y_c over the earlier border columns (ascending c)
+            double b = d.xp[k * 6 + lane];
+            for (int c = max(n_band, fk); c < k; c++) {
+                const double* Lr = rowk + (size_t)c * 36 + lane * 6;
+                const double* yc = ys + (size_t)(c - n_band) * 6;
+                double s2 = 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) s2 += Lr[q] * yc[q];
+                b -= s2;
+            }
+            bk[lane] = b;
+        }
+        __syncthreads();
+        if (s_fail) break;
+        // ---- L_ak = T_ak L_kk^-T, one thread per row of a block; y_k = L_kk^-1 b_k
+        for (int it = tid; it < nact * 6; it += 1024) {
+            const int i = it / 6, r = it - i * 6;
+            const int a = rows[i];
+            const double* Tr = T + (size_t)(i + 1) * 36 + r * 6;
+            double* out = d.S + (size_t)(d.rowoff[a] + k - d.first[a]) * 36 + r * 6;
+            double v[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double s2 = Tr[c];
+#pragma unroll
+                for (int p = 0; p < c; p++) s2 -= v[p] * Lkk[c * 6 + p];
+                v[c] = s2 * Lki[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 6; c++) out[c] = v[c];
+        }
+        if (tid == 1023) {
+            double v[6];
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                double s2 = bk[r];
+#pragma unroll
+                for (int p = 0; p < r; p++) s2 -= Lkk[r * 6 + p] * v[p];
+                v[r] = s2 * Lki[r];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) { d.xp[k * 6 + r] = v[r]; ys[(size_t)(k - n_band) * 6 + r] = v[r]; }
+        }
+        __syncthreads();
+    }
+    if (s_fail && tid == 0) d.scalars[4] = 1.0;
+}
+
 // ---- K12c: the border rows (keyframes with long-range links, ordered last) against the finished band factor.
 //      L_jk = (A_jk - sum_{c<k} L_jc L_kc^T) L_kk^-T only needs row j itself and the band rows, so every border row is
 //      swept left to right on its own: one small CTA per border row, all rows concurrently, instead of riding along as
@@ -972,7 +1089,40 @@ __global__ void __launch_bounds__(32) k_ba_band_backward(BaDev d, int n_band, in
 // ---- K12b: deferred update of the border block (keyframes with long-range links, ordered last):
 //      S(j, i) -= sum_k L_jk L_ik^T over the band columns k shared by the envelopes of border rows j >= i.
 //      One warp per (j, i) pair; lane = entry of the 6x6 block; fixed k order => deterministic.
-__global__ void __launch_bounds__(256) k_ba_border_syrk(BaDev d, int n_band) {
+//      The band columns are independent chunks, so a pair's sum is cut at the chunk boundaries: one warp per
+//      (pair, chunk) writes a partial block (nq > 1), and k_ba_border_syrk_apply subtracts the partials in chunk order.
+__global__ void __launch_bounds__(256) k_ba_border_syrk(BaDev d, int n_band, int nq) {
+    const int nbord = d.Pf - n_band;
+    const int wi = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int p = wi / nq, q = wi - p * nq;
+    if (p >= nbord * (nbord + 1) / 2) return;
+    const int lane = threadIdx.x & 31;
+    int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+    while (a * (a + 1) / 2 > p) a--;
+    while ((a + 1) * (a + 2) / 2 <= p) a++;
+    const int b = p - a * (a + 1) / 2;
+    const int j = n_band + a, i = n_band + b;
+    const int k0 = max(max(d.first[j], d.first[i]), d.chunk_start[q]), k1 = min(n_band, d.chunk_start[q + 1]);
+    const double* Lj = d.S + (size_t)(d.rowoff[j] - d.first[j]) * 36;
+    const double* Li = d.S + (size_t)(d.rowoff[i] - d.first[i]) * 36;
+    const int r0 = lane / 6, c0 = lane - r0 * 6, c1 = 2 + lane;
+    double s0 = 0, s1 = 0;
+    for (int k = k0; k < k1; k++) {
+        const double* A = Lj + (size_t)k * 36;
+        const double* B = Li + (size_t)k * 36;
+#pragma unroll
+        for (int q2 = 0; q2 < 6; q2++) s0 += A[r0 * 6 + q2] * B[c0 * 6 + q2];
+        if (lane < 4) {
+#pragma unroll
+            for (int q2 = 0; q2 < 6; q2++) s1 += A[30 + q2] * B[c1 * 6 + q2];
+        }
+    }
+    double* out = d.syrk_part + ((size_t)p * nq + q) * 36;
+    out[lane] = s0;
+    if (lane < 4) out[32 + lane] = s1;
+}
+
+__global__ void __launch_bounds__(256) k_ba_border_syrk_apply(BaDev d, int n_band, int nq) {
     const int nbord = d.Pf - n_band;
     const int p = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (p >= nbord * (nbord + 1) / 2) return;
@@ -982,22 +1132,13 @@ __global__ void __launch_bounds__(256) k_ba_border_syrk(BaDev d, int n_band) {
     while ((a + 1) * (a + 2) / 2 <= p) a++;
     const int b = p - a * (a + 1) / 2;
     const int j = n_band + a, i = n_band + b;
-    const int k0 = max(d.first[j], d.first[i]);
-    const double* Lj = d.S + (size_t)(d.rowoff[j] - d.first[j]) * 36;
-    const double* Li = d.S + (size_t)(d.rowoff[i] - d.first[i]) * 36;
-    const int r0 = lane / 6, c0 = lane - r0 * 6, c1 = 2 + lane;
-    double s0 = 0, s1 = 0;
-    for (int k = k0; k < n_band; k++) {
-        const double* A = Lj + (size_t)k * 36;
-        const double* B = Li + (size_t)k * 36;
-#pragma unroll
-        for (int q = 0; q < 6; q++) s0 += A[r0 * 6 + q] * B[c0 * 6 + q];
-        if (lane < 4) {
-#pragma unroll
-            for (int q = 0; q < 6; q++) s1 += A[30 + q] * B[c1 * 6 + q];
-        }
-    }
     double* T = d.S + (size_t)(d.rowoff[j] + i - d.first[j]) * 36;
+    double s0 = 0, s1 = 0;
+    for (int q = 0; q < nq; q++) {
+        const double* part = d.syrk_part + ((size_t)p * nq + q) * 36;
+        s0 += part[lane];
+        if (lane < 4) s1 += part[32 + lane];
+    }
     T[lane] -= s0;
     if (lane < 4) T[32 + lane] -= s1;
 }
@@ -1154,6 +1295,7 @@ struct BaHost {
     int stage_nnz_b = -1;  // entries of the band column lists when the index arrays fit the solve kernel's shared memory
     size_t stage_bytes_b = 0;
     size_t band_idx_bytes = 0;
+    bool border_dense_ok = false;  // the left-looking border kernel's shared staging fits
     int n_chunks = 1;           // independent band chunks (columns chunk_start[q] .. chunk_start[q + 1])  // first[] / rowoff[] of the band rows staged by the border-row and band-backward kernels     // longest band envelope (blocks left of the diagonal)
     int n_band = 0;        // free keyframes before the border block (== Pf when there is no border)
     corb_allreduce_fn ar = nullptr;
@@ -1284,7 +1426,10 @@ struct BaHost {
     // setLambda + BlockSolver::solve + update + computeScale; leaves the tentative estimate in q/t/X
     int trial(double lambda, bool* ok, double* scale) {
         if (d.L > 0) k_ba_dinv<<<(d.L + 255) / 256, 256, 0, stream>>>(d, lambda);
-        if (d.P > 0) k_ba_schur_rows<<<(d.P * 32 + 255) / 256, 256, 0, stream>>>(d);
+        if (d.P > 0) {
+            CORB_CUDA(cudaMemsetAsync(d.S, 0, s_doubles * sizeof(double), stream));  // rows are accumulated into, not zeroed, by the kernel
+            k_ba_schur_rows<<<(d.P * 32 + 255) / 256, 256, 0, stream>>>(d);
+        }
         int rc = reduce(d.S, s_doubles + (size_t)d.Pf * 6, 0);
         if (rc != CORB_OK) return rc;
         if (d.Pf > 0) k_ba_add_lambda<<<(d.Pf * 6 + 255) / 256, 256, 0, stream>>>(d, lambda);
@@ -1301,8 +1446,14 @@ struct BaHost {
                     d, n_band, band_wmax, band_idx_bytes > 0);
                 k_ba_border_rhs<<<(nbord * 6 + 255) / 256, 256, 0, stream>>>(d, n_band, n_chunks);
                 const int npairs = nbord * (nbord + 1) / 2;
-                k_ba_border_syrk<<<(npairs * 32 + 255) / 256, 256, 0, stream>>>(d, n_band);
-                k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, n_band, d.Pf, n_band, 4 | 16, -1);
+                k_ba_border_syrk<<<(int)(((size_t)npairs * n_chunks * 32 + 255) / 256), 256, 0, stream>>>(d, n_band, n_chunks);
+                k_ba_border_syrk_apply<<<(npairs * 32 + 255) / 256, 256, 0, stream>>>(d, n_band, n_chunks);
+                if (getenv("CORB_BA_BORDER_RL") || !border_dense_ok) {  // A/B switch / border too large for the staging buffer
+                    k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, n_band, d.Pf, n_band, 4 | 16, -1);
+                } else {
+                    k_ba_border_dense<<<1, 1024, ((size_t)(nbord + 1) * 36 + (size_t)nbord * 6) * sizeof(double), stream>>>(d, n_band);
+                    k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, d.Pf, d.Pf, n_band, 4 | 16, -1);  // backward over the border rows
+                }
                 k_ba_band_backward<<<n_chunks, 32, (size_t)(band_wmax + 1) * (6 + 72) * sizeof(double) + band_idx_bytes, stream>>>(
                     d, n_band, band_wmax, band_idx_bytes > 0);
             } else {
@@ -1567,6 +1718,11 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
                                        (3 * wmax + 1) * 36 * (int)sizeof(double) + (int)H.band_idx_bytes));
         CORB_CUDA(cudaFuncSetAttribute(k_ba_band_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (wmax + 1) * (6 + 72) * (int)sizeof(double) + (int)H.band_idx_bytes));
+        const size_t nbord = (size_t)(Pf - H.n_band);
+        const size_t dense_bytes = ((nbord + 1) * 36 + nbord * 6) * sizeof(double);
+        H.border_dense_ok = nbord > 0 && dense_bytes <= 200 * 1024;
+        if (H.border_dense_ok)
+            CORB_CUDA(cudaFuncSetAttribute(k_ba_border_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dense_bytes, 1024)));
     }
     // the same lists without the border rows in the band columns: the band sweep of the bordered solve
     std::vector<int> coloff_b(Pf + 1, 0), col_rows_b(col_rows.size());
@@ -1616,6 +1772,10 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     AL(S, H.s_doubles + (size_t)Pf * 6);
     AL(xp, (size_t)Pf * 6); AL(xl, (size_t)L * 3); AL(invd, (size_t)Pf * 6 + 6);
     AL(bpart, (size_t)std::max(1, Pf - H.n_band) * H.n_chunks * 6);
+    {
+        const size_t nb = (size_t)(Pf - H.n_band);
+        AL(syrk_part, std::max<size_t>(1, nb * (nb + 1) / 2 * H.n_chunks * 36));
+    }
     const size_t npart = (size_t)std::max(std::max((E + 255) / 256, (L * 3 + 255) / 256), 2048) * 2 + 16;
     AL(partial, npart); AL(scalars, 8);
 #undef AL
