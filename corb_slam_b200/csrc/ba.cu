@@ -353,31 +353,24 @@ __global__ void __launch_bounds__(256) k_ba_dinv(BaDev d, double lambda) {
 // ---- K11b: one warp per keyframe = one block row of the reduced system:
 //      S(j, j') = Hpp(j) [j'=j] - sum_l W_jl Dinv_l W_j'l^T  for j' <= j,   bs(j) = bp(j) - sum_l W_jl Dinv_l bl
 //      lane = entry (r,c) of the 6x6 block (lanes 0..3 also own entries 32..35); the warp walks its edges in order.
-//      The kAccBlocks blocks next to the diagonal (all of a band row's envelope) are accumulated in shared memory and
-//      written once: a read-modify-write on global memory per term made every term of a row wait one L2 round trip
-//      for the previous one. Blocks further left (long-range rows) still accumulate in global memory, which the host
-//      has zeroed (cudaMemsetAsync over S). The order of the terms per entry is unchanged (edge order).
-constexpr int kAccBlocks = 8;
-__global__ void __launch_bounds__(256) k_ba_schur_rows(BaDev d) {
-    __shared__ double acc[8][kAccBlocks][36];
-    const int pi = (blockIdx.x * 256 + threadIdx.x) >> 5;
-    if (pi >= d.P) return;
-    const int j = d.pfree[pi];
-    if (j < 0) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int fj = d.first[j];
-    double* row = d.S + (size_t)d.rowoff[j] * 36;
-    const int jacc = max(fj, j - kAccBlocks + 1);  // blocks jacc..j live in acc[w][j2 - jacc]
-    for (int i = lane; i < kAccBlocks * 36; i += 32) (&acc[w][0][0])[i] = 0.0;
-    __syncwarp();
-    double* diag = acc[w][j - jacc];
-    diag[lane] = d.Hpp[(size_t)j * 36 + lane];
-    if (lane < 4) diag[32 + lane] = d.Hpp[(size_t)j * 36 + 32 + lane];
-    __syncwarp();
+//      One CTA (8 warps) per keyframe. A row touches few distinct blocks (its own keyframe and the co-observers of its
+//      landmarks) but each of them hundreds of times, and every edge costs a chain of dependent index loads
+//      (edge -> landmark -> Dinv, the landmark's edges -> their poses -> W): one warp per row left that latency exposed
+//      for ~500 edges in a row (2 ms per launch, set by the slowest row). Now warp w takes the edges k = w, w + 8, ...,
+//      accumulates into a private block cache in shared memory (tag = block column), and the caches are merged in warp
+//      order - a fixed order per entry, so the sums are deterministic. A row with more distinct blocks than slots
+//      (dense covisibility) is redone by warp 0 alone, overflow blocks accumulating in global memory (the previous
+//      algorithm); the host has zeroed S (cudaMemsetAsync).
+constexpr int kAccSlots = 16, kBaseSlots = 32;
+
+// the edges pose_off[pi] + w0, + step, ... of keyframe pi into the cache (acc, tags) of the calling warp; blocks that do not
+// fit go to `row` in global memory when allowed (single-warp use only), else *overflow is raised and the term is dropped
+__device__ __forceinline__ void schur_accumulate(const BaDev& d, int pi, int j, int w0, int step, double (*acc)[36], int* tags, int& nslots,
+                                                 double& coeff, double* row, int fj, bool global_ok, int* overflow) {
+    const int lane = threadIdx.x & 31;
     const int r0 = lane / 6, c0 = lane - r0 * 6;  // entry `lane`
     const int c1 = 2 + lane;                      // entry 32 + lane = (5, 2 + lane) for lane < 4
-    double coeff = 0.0;
-    for (int k = d.pose_off[pi]; k < d.pose_off[pi + 1]; k++) {
+    for (int k = d.pose_off[pi] + w0; k < d.pose_off[pi + 1]; k += step) {
         const int e = d.pose_edges[k];
         const int l = d.e_point[e];
         if (d.lfree[l] < 0) continue;
@@ -397,13 +390,115 @@ __global__ void __launch_bounds__(256) k_ba_schur_rows(BaDev d) {
             const int j2 = d.pfree[d.e_pose[e2]];
             if (j2 < 0 || j2 > j) continue;
             const double* W2 = d.W + (size_t)e2 * 18;
-            double* blk = j2 >= jacc ? acc[w][j2 - jacc] : row + (size_t)(j2 - fj) * 36;
+            int slot = -1;  // warp-uniform lookup (j2 is the same for every lane)
+            const int tg = lane < kAccSlots ? tags[lane] : -2;
+            const unsigned hit = __ballot_sync(0xffffffffu, tg == j2);
+            if (hit) {
+                slot = __ffs(hit) - 1;
+            } else if (nslots < kAccSlots) {
+                slot = nslots++;
+                if (lane == 0) tags[slot] = j2;
+                __syncwarp();
+            }
+            double* blk;
+            if (slot >= 0) blk = acc[slot];
+            else if (global_ok) blk = row + (size_t)(j2 - fj) * 36;
+            else { if (lane == 0) *overflow = 1; continue; }
             blk[lane] -= bd0[0] * W2[c0 * 3] + bd0[1] * W2[c0 * 3 + 1] + bd0[2] * W2[c0 * 3 + 2];
             if (lane < 4) blk[32 + lane] -= bd1[0] * W2[c1 * 3] + bd1[1] * W2[c1 * 3 + 1] + bd1[2] * W2[c1 * 3 + 2];
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_ba_schur_rows(BaDev d) {
+    __shared__ double acc[8][kAccSlots][36];
+    __shared__ int tags[8][kAccSlots];
+    __shared__ int nsl[8];
+    __shared__ double coeffs[8][6];
+    __shared__ double base[kBaseSlots][36];
+    __shared__ int btag[kBaseSlots];
+    __shared__ int nbase, s_over;
+    const int pi = blockIdx.x;
+    const int j = d.pfree[pi];
+    if (j < 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int fj = d.first[j];
+    double* row = d.S + (size_t)d.rowoff[j] * 36;
+    for (int i = tid; i < 8 * kAccSlots * 36; i += 256) (&acc[0][0][0])[i] = 0.0;
+    for (int i = tid; i < kBaseSlots * 36; i += 256) (&base[0][0])[i] = 0.0;
+    if (tid < 8 * kAccSlots) (&tags[0][0])[tid] = -1;
+    if (tid == 0) { s_over = 0; nbase = 0; }
+    __syncthreads();
+    {
+        int nslots = 0;
+        double coeff = 0.0;
+        schur_accumulate(d, pi, j, w, 8, acc[w], tags[w], nslots, coeff, row, fj, false, &s_over);
+        if (lane == 0) nsl[w] = nslots;
+        if (lane < 6) coeffs[w][lane] = coeff;
+    }
+    __syncthreads();
+    if (!s_over) {
+        // merge the caches in warp order: a tag occurs once per warp table, so inside a round every base slot has one writer
+        for (int ww = 0; ww < 8; ww++) {
+            const int nb0 = nbase;
+            for (int sl = w; sl < nsl[ww]; sl += 8) {
+                const int tg = tags[ww][sl];
+                int bi = -1;
+                if (lane == 0) {
+                    for (int i = 0; i < nb0; i++) if (btag[i] == tg) { bi = i; break; }
+                    if (bi < 0) {
+                        bi = atomicAdd(&nbase, 1);
+                        if (bi < kBaseSlots) btag[bi] = tg; else s_over = 1;
+                    }
+                }
+                bi = __shfl_sync(0xffffffffu, bi, 0);
+                if (bi >= kBaseSlots) continue;
+                base[bi][lane] += acc[ww][sl][lane];
+                if (lane < 4) base[bi][32 + lane] += acc[ww][sl][32 + lane];
+            }
+            __syncthreads();
+        }
+    }
+    if (!s_over) {
+        const int nb = nbase;
+        bool have_diag = false;
+        for (int bi = w; bi < nb; bi += 8) {  // every block of the row is written exactly once
+            const int j2 = btag[bi];
+            double* blk = row + (size_t)(j2 - fj) * 36;
+            const double h0 = j2 == j ? d.Hpp[(size_t)j * 36 + lane] : 0.0;
+            blk[lane] = h0 + base[bi][lane];
+            if (lane < 4) blk[32 + lane] = (j2 == j ? d.Hpp[(size_t)j * 36 + 32 + lane] : 0.0) + base[bi][32 + lane];
+        }
+        for (int bi = 0; bi < nb; bi++) have_diag |= btag[bi] == j;
+        if (!have_diag && w == 0) {  // a keyframe without any free landmark: the diagonal is Hpp alone
+            double* blk = row + (size_t)(j - fj) * 36;
+            blk[lane] = d.Hpp[(size_t)j * 36 + lane];
+            if (lane < 4) blk[32 + lane] = d.Hpp[(size_t)j * 36 + 32 + lane];
+        }
+        if (tid < 6) {
+            double c = 0.0;
+            for (int ww = 0; ww < 8; ww++) c += coeffs[ww][tid];
+            d.bs[(size_t)j * 6 + tid] = d.bp[(size_t)j * 6 + tid] - c;
+        }
+        return;
+    }
+    // ---- dense covisibility: warp 0 alone, diagonal in slot 0 starting from Hpp, overflow blocks in global memory
+    if (w != 0) return;
+    for (int i = lane; i < kAccSlots * 36; i += 32) (&acc[0][0][0])[i] = 0.0;
+    if (lane < kAccSlots) tags[0][lane] = lane == 0 ? j : -1;
     __syncwarp();
-    for (int i = lane; i < (j - jacc + 1) * 36; i += 32) row[(size_t)(jacc - fj) * 36 + i] = (&acc[w][0][0])[i];
+    acc[0][0][lane] = d.Hpp[(size_t)j * 36 + lane];
+    if (lane < 4) acc[0][0][32 + lane] = d.Hpp[(size_t)j * 36 + 32 + lane];
+    __syncwarp();
+    int nslots = 1;
+    double coeff = 0.0;
+    schur_accumulate(d, pi, j, 0, 1, acc[0], tags[0], nslots, coeff, row, fj, true, &s_over);
+    __syncwarp();
+    for (int sl = 0; sl < nslots; sl++) {
+        double* blk = row + (size_t)(tags[0][sl] - fj) * 36;
+        blk[lane] = acc[0][sl][lane];
+        if (lane < 4) blk[32 + lane] = acc[0][sl][32 + lane];
+    }
     if (lane < 6) d.bs[(size_t)j * 6 + lane] = d.bp[(size_t)j * 6 + lane] - coeff;
 }
 
@@ -731,14 +826,17 @@ __global__ void __launch_bounds__(kSolveThreads) k_ba_solve(BaDev d, int lact_ca
 //      rest of the column. Per entry the terms are subtracted in ascending column order with the same 6-term sums, so
 //      the factor is bit-identical to the right-looking one. The band-column terms of these blocks were applied by
 //      k_ba_border_syrk; the forward substitution (y_k) rides along.
+constexpr int kDenseU = 8;  // blocks of a row fetched per batch
 __global__ void __launch_bounds__(1024) k_ba_border_dense(BaDev d, int n_band) {
-    extern __shared__ double dsm[];  // T[max items][36] | ys[nbord][6]
+    extern __shared__ double dsm[];  // T[nbord + 1][36] | ys[nbord][6] | Lrow[nbord][36] | stage[32 warps][kDenseU][36]
     __shared__ double Lkk[36], Lki[6], bk[6];
     __shared__ int s_fail;
     const int n = d.Pf, nbord = n - n_band;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* T = dsm;
     double* ys = dsm + (size_t)(nbord + 1) * 36;
+    double* Lrow = ys + (size_t)nbord * 6;                                   // row k's finished blocks L_kc, c = ck0 .. k-1
+    double* stage = Lrow + (size_t)nbord * 36 + (size_t)warp * kDenseU * 36;  // this warp's batch of L_ac blocks
     if (tid == 0) s_fail = d.scalars[4] != 0.0;
     __syncthreads();
     const int r0 = lane / 6, c0 = lane - r0 * 6, c1 = 2 + lane;  // entries `lane` and `32 + lane` (lane < 4)
@@ -747,6 +845,9 @@ __global__ void __launch_bounds__(1024) k_ba_border_dense(BaDev d, int n_band) {
         const int* rows = d.col_rows + cb;
         const int fk = d.first[k];
         const double* rowk = d.S + (size_t)(d.rowoff[k] - fk) * 36;  // block (k, c) at rowk + c * 36
+        const int ck0 = max(n_band, fk);
+        for (int i = tid; i < (k - ck0) * 36; i += 1024) Lrow[i] = rowk[(size_t)ck0 * 36 + i];  // shared by every block of the column
+        __syncthreads();
         // ---- form the column: item 0 = diagonal, item i = (rows[i - 1], k)
         for (int it = warp; it <= nact; it += 32) {
             const int a = it == 0 ? k : rows[it - 1];
@@ -755,18 +856,31 @@ __global__ void __launch_bounds__(1024) k_ba_border_dense(BaDev d, int n_band) {
             double t0 = rowa[(size_t)k * 36 + lane];
             double t1 = lane < 4 ? rowa[(size_t)k * 36 + 32 + lane] : 0.0;
             const int clo = max(n_band, max(fa, fk));
-            for (int c = clo; c < k; c++) {
-                const double* La = rowa + (size_t)c * 36;
-                const double* Lb = rowk + (size_t)c * 36;
-                double s0 = 0, s1 = 0;
+            for (int cb0 = clo; cb0 < k; cb0 += kDenseU) {
+                // row a's blocks are contiguous: fetch a batch with all loads in flight, then use it from shared memory
+                const int nb = min(kDenseU, k - cb0);
+                double v[(kDenseU * 36 + 31) / 32];
 #pragma unroll
-                for (int q = 0; q < 6; q++) s0 += La[r0 * 6 + q] * Lb[c0 * 6 + q];
-                t0 = t0 - s0;
-                if (lane < 4) {
+                for (int u = 0; u < (kDenseU * 36 + 31) / 32; u++)
+                    v[u] = lane + 32 * u < nb * 36 ? rowa[(size_t)cb0 * 36 + lane + 32 * u] : 0.0;
 #pragma unroll
-                    for (int q = 0; q < 6; q++) s1 += La[30 + q] * Lb[c1 * 6 + q];
-                    t1 = t1 - s1;
+                for (int u = 0; u < (kDenseU * 36 + 31) / 32; u++)
+                    if (lane + 32 * u < nb * 36) stage[lane + 32 * u] = v[u];
+                __syncwarp();
+                for (int c = cb0; c < cb0 + nb; c++) {
+                    const double* La = stage + (size_t)(c - cb0) * 36;
+                    const double* Lb = Lrow + (size_t)(c - ck0) * 36;
+                    double s0 = 0, s1 = 0;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) s0 += La[r0 * 6 + q] * Lb[c0 * 6 + q];
+                    t0 = t0 - s0;
+                    if (lane < 4) {
+#pragma unroll
+                        for (int q = 0; q < 6; q++) s1 += La[30 + q] * Lb[c1 * 6 + q];
+                        t1 = t1 - s1;
+                    }
                 }
+                __syncwarp();
             }
             T[it * 36 + lane] = t0;
             if (lane < 4) T[it * 36 + 32 + lane] = t1;
@@ -1295,6 +1409,7 @@ struct BaHost {
     int stage_nnz_b = -1;  // entries of the band column lists when the index arrays fit the solve kernel's shared memory
     size_t stage_bytes_b = 0;
     size_t band_idx_bytes = 0;
+    size_t border_dense_bytes = 0;
     bool border_dense_ok = false;  // the left-looking border kernel's shared staging fits
     int n_chunks = 1;           // independent band chunks (columns chunk_start[q] .. chunk_start[q + 1])  // first[] / rowoff[] of the band rows staged by the border-row and band-backward kernels     // longest band envelope (blocks left of the diagonal)
     int n_band = 0;        // free keyframes before the border block (== Pf when there is no border)
@@ -1428,7 +1543,7 @@ struct BaHost {
         if (d.L > 0) k_ba_dinv<<<(d.L + 255) / 256, 256, 0, stream>>>(d, lambda);
         if (d.P > 0) {
             CORB_CUDA(cudaMemsetAsync(d.S, 0, s_doubles * sizeof(double), stream));  // rows are accumulated into, not zeroed, by the kernel
-            k_ba_schur_rows<<<(d.P * 32 + 255) / 256, 256, 0, stream>>>(d);
+            k_ba_schur_rows<<<d.P, 256, 0, stream>>>(d);  // one CTA per keyframe
         }
         int rc = reduce(d.S, s_doubles + (size_t)d.Pf * 6, 0);
         if (rc != CORB_OK) return rc;
@@ -1451,7 +1566,7 @@ struct BaHost {
                 if (getenv("CORB_BA_BORDER_RL") || !border_dense_ok) {  // A/B switch / border too large for the staging buffer
                     k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, n_band, d.Pf, n_band, 4 | 16, -1);
                 } else {
-                    k_ba_border_dense<<<1, 1024, ((size_t)(nbord + 1) * 36 + (size_t)nbord * 6) * sizeof(double), stream>>>(d, n_band);
+                    k_ba_border_dense<<<1, 1024, border_dense_bytes, stream>>>(d, n_band);
                     k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, d.Pf, d.Pf, n_band, 4 | 16, -1);  // backward over the border rows
                 }
                 k_ba_band_backward<<<n_chunks, 32, (size_t)(band_wmax + 1) * (6 + 72) * sizeof(double) + band_idx_bytes, stream>>>(
@@ -1719,7 +1834,8 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         CORB_CUDA(cudaFuncSetAttribute(k_ba_band_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (wmax + 1) * (6 + 72) * (int)sizeof(double) + (int)H.band_idx_bytes));
         const size_t nbord = (size_t)(Pf - H.n_band);
-        const size_t dense_bytes = ((nbord + 1) * 36 + nbord * 6) * sizeof(double);
+        const size_t dense_bytes = ((nbord + 1) * 36 + nbord * 6 + nbord * 36 + (size_t)32 * kDenseU * 36) * sizeof(double);
+        H.border_dense_bytes = dense_bytes;
         H.border_dense_ok = nbord > 0 && dense_bytes <= 200 * 1024;
         if (H.border_dense_ok)
             CORB_CUDA(cudaFuncSetAttribute(k_ba_border_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dense_bytes, 1024)));

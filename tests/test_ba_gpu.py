@@ -126,3 +126,14 @@ def test_ba_chunked_band_equals_single_sweep(monkeypatch):
     assert info_q["chi2_final"] == pytest.approx(info_1["chi2_final"], rel=1e-9)
     np.testing.assert_allclose(out_q["pose_t"], out_1["pose_t"], atol=1e-7)
     _check(prob, iters=5)
+
+
+def test_ba_dense_covisibility():
+    """Landmarks seen by 40 consecutive keyframes: a reduced-system row then has more distinct blocks than the per-warp
+    and per-row caches of k_ba_schur_rows hold (single-warp fallback with global accumulation), and the band is too wide
+    to be cut into chunks."""
+    prob = ba_problem(70, 2500, seed=21, obs_per_point=40, n_fusion=6)
+    o_info, g_info, _ = _check(prob, iters=5)
+    assert g_info["band_chunks"] == 1
+    prob = ba_problem(60, 3000, seed=22, obs_per_point=20, n_fusion=0)   # fits the merged cache (<= 32 blocks), not one warp's
+    _check(prob, iters=5)
