@@ -66,6 +66,33 @@ __device__ __align__(16) const int8_t d_pattern[1024] = {
 // umax of ORBextractor.cc:452-469 for HALF_PATCH_SIZE = 15 (the host recomputes it and checks equality)
 __device__ const int d_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
+// Programmatic dependent launch: a kernel launched with this attribute may be scheduled while its predecessor in the
+// stream is still draining; it blocks in pdl_wait() (griddepcontrol.wait) until the predecessor has completed and its
+// writes are visible. Along the serial chains of small kernels (resize_1 .. resize_7, FAST_l -> quadtree_l) this takes
+// the ~1.3 us launch gap per edge off the critical path. CORB_PDL=0 launches everything the plain way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the dependent launch be scheduled once every CTA of this grid has got here (it still waits in pdl_wait() for this
+// grid to finish); without it the dependent is only released when the last CTA exits.
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static bool pdl_enabled() {
+    static const bool on = !(getenv("CORB_PDL") && atoi(getenv("CORB_PDL")) == 0);
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static void launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------ K0 import
 // Copies the caller's image (device memory, or page-locked host memory read over PCIe through its UVA mapping) into
 // level 0 of the pitched pyramid. First node of the per-frame graph, so one cudaGraphLaunch is the only driver call
@@ -75,6 +102,7 @@ __global__ void __launch_bounds__(256) k_import_rows(const uint8_t* __restrict__
                                                      int w, int h, const uint8_t* __restrict__ src1, int stride1,
                                                      uint8_t* __restrict__ dst1) {
     TL_SCOPE(0);
+    pdl_release();
     if (blockIdx.z) { src = src1; stride = stride1; dst = dst1; }  // second image of a stereo pair
     const int y = blockIdx.y;
     const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
@@ -97,6 +125,8 @@ __global__ void __launch_bounds__(256) k_import(const uint8_t* __restrict__ src,
                                                 int w, int h, const uint8_t* __restrict__ src1, int stride1,
                                                 uint8_t* __restrict__ dst1) {
     TL_SCOPE(0);
+    // (no pdl_release here: this kernel lasts as long as the PCIe read, and dependents parked on the SMs for that long
+    //  take slots from the other image's pipeline - measured 122 -> 127 us per frame)
     if (blockIdx.z) { src = src1; stride = stride1; dst = dst1; }  // second image of a stereo pair
     // The image is walked as a flat run of w * h bytes, 16 per thread: a contiguous, 16-byte aligned source (the usual
     // case: a cv::Mat or a pinned staging buffer) is read with one 128-bit load per thread, i.e. 512-byte requests per
@@ -156,6 +186,8 @@ __global__ void __launch_bounds__(256) k_resize(LevelGeom src, LevelGeom dst, co
                                                 uint8_t* __restrict__ pyr_dst1) {
     TL_SCOPE(dst.level);
     if (blockIdx.z) { pyr_src = pyr_src1; pyr_dst = pyr_dst1; }
+    pdl_release();
+    pdl_wait();  // level l - 1 comes from the previous launch of the chain
     const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int dy = blockIdx.y * 8 + threadIdx.y;
     if (dy >= dst.h || dx0 >= dst.w) return;
@@ -185,9 +217,9 @@ void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_
     const LevelGeom& src = g.lv[level - 1];
     const LevelGeom& dst = g.lv[level];
     dim3 block(32, 8), grid((dst.w + 127) / 128, (dst.h + 7) / 8, b1 ? 2 : 1);
-    k_resize<<<grid, block, 0, s>>>(src, dst, b.pyr + src.img_off, b.pyr + dst.img_off, b.xofs + dst.xtab_off,
-                                    b.alpha + dst.xtab_off, b.yofs + dst.ytab_off, b.beta + dst.ytab_off,
-                                    b1 ? b1->pyr + src.img_off : nullptr, b1 ? b1->pyr + dst.img_off : nullptr);
+    launch_chain(k_resize, grid, block, 0, s, src, dst, (const uint8_t*)(b.pyr + src.img_off), b.pyr + dst.img_off, b.xofs + dst.xtab_off,
+                 b.alpha + dst.xtab_off, b.yofs + dst.ytab_off, b.beta + dst.ytab_off,
+                 (const uint8_t*)(b1 ? b1->pyr + src.img_off : nullptr), b1 ? b1->pyr + dst.img_off : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ K1' fused pyramid
@@ -531,6 +563,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_cons
     int l = 0;
     while (l + 1 < g.n_levels && cell >= g.lv[l + 1].cell_base) l++;
     TL_SCOPE(16 + l);
+    pdl_release();  // the quadtree launch behind this one may be scheduled; it waits for this grid in pdl_wait()
     const CUtensorMap* tm = &tmap;
     if (blockIdx.z) {  // second image of a stereo pair
         pyr = im1.pyr; cell_count = im1.cell_count; cand_xy = im1.cand_xy; cand_ro = im1.cand_ro; level_cand = im1.level_cand;
@@ -947,6 +980,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
 #endif
     TL_SCOPE(32 + blockIdx.x + level_begin);
     OCT_T(0);
+    pdl_wait();  // the candidates come from the FAST launch right before this one in the stream
     const int l = blockIdx.x + level_begin;
     const LevelGeom L = g.lv[l];
     const int NC = L.node_cap, N = L.quota;
@@ -1585,8 +1619,9 @@ cudaError_t prepare_octtree(const OrbGeom& g, int key_smem_cap, int* smem_bytes_
 void launch_octtree(const OrbGeom& g, const OrbBuffers& b, int level, int key_smem_cap, int smem_bytes, cudaStream_t s,
                     const OrbBuffers* b1) {
     const int nz = b1 ? 2 : 1;
-    if (level < 0) k_octtree<<<dim3(g.n_levels, 1, nz), kOctThreads, smem_bytes, s>>>(g, b, key_smem_cap, 0, b1 ? *b1 : b);
-    else k_octtree<<<dim3(1, 1, nz), kOctThreads, octtree_smem_bytes(g, level, key_smem_cap), s>>>(g, b, key_smem_cap, level, b1 ? *b1 : b);
+    if (level < 0) launch_chain(k_octtree, dim3(g.n_levels, 1, nz), dim3(kOctThreads), (size_t)smem_bytes, s, g, b, key_smem_cap, 0, b1 ? *b1 : b);
+    else launch_chain(k_octtree, dim3(1, 1, nz), dim3(kOctThreads), (size_t)octtree_smem_bytes(g, level, key_smem_cap), s, g, b, key_smem_cap,
+                      level, b1 ? *b1 : b);
 }
 
 // ------------------------------------------------------------------------------------------------ K4 + K6
