@@ -33,6 +33,7 @@ class ORBextractor:
                                     p(self.umax, _lib.i32p)))
         self.mvImagePyramid = []
         self._out_shape = None
+        self._shape_v = None
         self.copy_outputs = True  # False: return views into reused buffers (valid until the next call)
 
     def close(self):
@@ -45,6 +46,30 @@ class ORBextractor:
             self.close()
         except Exception:  # interpreter shutdown: module globals are already gone, the process frees the device memory
             pass
+
+    @property
+    def _shape(self):
+        return self._shape_v
+
+    @_shape.setter
+    def _shape(self, v):
+        if v != self._shape_v:  # a different image size rebuilds the plan: the page-locked result buffer moves
+            self._hv_shape = None
+        self._shape_v = v
+
+    def _host_view(self, n, shape):
+        """Slices of numpy views over the whole page-locked result buffer; the views are built once per plan (the buffer
+        moves only when the image size changes), so a call costs two slices instead of a C call and two new arrays."""
+        if n == 0:
+            return np.empty(0, KP_DTYPE), None
+        if getattr(self, "_hv_shape", None) != shape:
+            kp, dp, cnt = C.c_void_p(), C.c_void_p(), C.c_int32()
+            check(lib().corb_orb_host_results(self._h, C.byref(kp), C.byref(dp), C.byref(cnt)))
+            cap = self.capacity(shape[1], shape[0])
+            self._hv = (np.frombuffer((C.c_uint8 * (cap * KP_DTYPE.itemsize)).from_address(kp.value), KP_DTYPE),
+                        np.frombuffer((C.c_uint8 * (cap * 32)).from_address(dp.value), np.uint8).reshape(cap, 32))
+            self._hv_shape = shape
+        return self._hv[0][:n], self._hv[1][:n]
 
     def host_results(self):
         """(keypoints, descriptors) of the last completed extraction as views of the handle's page-locked result buffer
@@ -135,6 +160,7 @@ class ORBextractor:
 
     # ---- device-resident path (inputs already in HBM)
     def extract_device(self, d_ptr, w, h, stride):
+        self._hv_shape = None  # (may rebuild the plan for another size)
         check(lib().corb_orb_extract_device(self._h, int(d_ptr), w, h, stride))
 
     def sync(self):
@@ -209,7 +235,7 @@ def extract_stereo(ex_left, ex_right, left, right, want_pyramid=False):
         # zero-copy: the results are read in place from the handles' page-locked result buffers
         check(lib().corb_orb_extract_pair(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0],
                                           None, None, C.byref(nl), None, None, C.byref(nr), None, None))
-        return tuple(ex.host_results() for ex in (ex_left, ex_right))
+        return ex_left._host_view(nl.value, (h, w)), ex_right._host_view(nr.value, (h, w))
     if want_pyramid:
         pyrs = [[np.empty(ex.level_size(l, w, h)[::-1], np.uint8) for l in range(ex.nlevels)] for ex in (ex_left, ex_right)]
         pl = (C.c_void_p * ex_left.nlevels)(*[a.ctypes.data for a in pyrs[0]])
@@ -230,6 +256,8 @@ def extract_stereo(ex_left, ex_right, left, right, want_pyramid=False):
 
 
 def extract_stereo_device(ex_left, ex_right, d_left, d_right, w, h, stride):
+    if (h, w) != ex_left._shape_v or (h, w) != ex_right._shape_v:
+        ex_left._hv_shape = ex_right._hv_shape = None  # another size rebuilds the plans
     check(lib().corb_orb_extract_pair_device(ex_left._h, ex_right._h, int(d_left), int(d_right), w, h, stride))
 
 
@@ -264,7 +292,7 @@ def frame_stereo(ex_left, ex_right, left, right, mbf, mb):
     if not ex_left.copy_outputs and not ex_right.copy_outputs:  # zero-copy keypoints / descriptors (corb_orb_host_results)
         check(lib().corb_frame_stereo(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0], float(mbf),
                                       float(mb), None, None, C.byref(nl), None, None, C.byref(nr), ur.ctypes.data, dp.ctypes.data))
-        return ex_left.host_results(), ex_right.host_results(), ur[:nl.value], dp[:nl.value]
+        return ex_left._host_view(nl.value, (h, w)), ex_right._host_view(nr.value, (h, w)), ur[:nl.value], dp[:nl.value]
     check(lib().corb_frame_stereo(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0], float(mbf),
                                   float(mb), outs[0][0].ctypes.data, outs[0][1].ctypes.data, C.byref(nl), outs[1][0].ctypes.data,
                                   outs[1][1].ctypes.data, C.byref(nr), ur.ctypes.data, dp.ctypes.data))

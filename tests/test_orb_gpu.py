@@ -235,3 +235,17 @@ def test_zero_copy_host_results_equal_copied_results():
     assert vr.tobytes() == okp.tobytes()
     np.testing.assert_array_equal(wr, odesc)
     a.close(); b.close()
+
+
+def test_zero_copy_views_survive_a_size_change():
+    """The cached views of the page-locked result buffer are rebuilt when the image size (and with it the plan) changes."""
+    from corb_slam_b200 import extract_stereo
+    a, b = ORBextractor(*PARAMS), ORBextractor(*PARAMS)
+    a.copy_outputs = b.copy_outputs = False
+    for seed, size in [(41, (1242, 375)), (42, (640, 480)), (43, (1242, 375))]:
+        left, right = stereo_frame(seed, w=size[0], h=size[1])
+        (vl, wl), (vr, wr) = extract_stereo(a, b, left, right)
+        okp, odesc = oracle.OrbExtractor(*PARAMS)(left)
+        assert vl.tobytes() == okp.tobytes()
+        np.testing.assert_array_equal(wl, odesc)
+    a.close(); b.close()
