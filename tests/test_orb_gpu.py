@@ -249,3 +249,36 @@ def test_zero_copy_views_survive_a_size_change():
         assert vl.tobytes() == okp.tobytes()
         np.testing.assert_array_equal(wl, odesc)
     a.close(); b.close()
+
+
+def test_repeated_and_concurrent_extraction_is_deterministic():
+    """Size-independent properties at the bench size: the same frame gives the same bytes on every call (the FAST
+    candidate lists are filled in arrival order, the quadtree must not depend on it), on both handles of a pair, and
+    from several client threads sharing the GPU (per-handle streams, counters and graphs)."""
+    import threading
+    from corb_slam_b200 import extract_stereo
+    left, right = stereo_frame(51)
+    ref = ORBextractor(*PARAMS)
+    k0, d0 = ref(left)
+    k1, d1 = ref(right)
+    for _ in range(10):
+        k, d = ref(left)
+        assert k.tobytes() == k0.tobytes() and d.tobytes() == d0.tobytes()
+    errors = []
+
+    def client(idx):
+        try:
+            a, b = ORBextractor(*PARAMS), ORBextractor(*PARAMS)
+            for i in range(15):
+                (kl, dl), (kr, dr) = extract_stereo(a, b, left, right) if (i + idx) % 2 else extract_stereo(b, a, left, right)
+                assert kl.tobytes() == k0.tobytes() and dl.tobytes() == d0.tobytes()
+                assert kr.tobytes() == k1.tobytes() and dr.tobytes() == d1.tobytes()
+            a.close(); b.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ths = [threading.Thread(target=client, args=(i,)) for i in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errors, errors
+    ref.close()
