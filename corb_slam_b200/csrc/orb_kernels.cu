@@ -543,7 +543,7 @@ __device__ __forceinline__ int block_scan_values(int v, int* warp_tmp, int* tota
 // The cell's ROI (wCell+6 x hCell+6) is staged in shared memory; FAST ignores a 3 px rim, so the valid areas of
 // neighbouring cells tile the level disjointly and NMS sees zeros outside its own cell, exactly like cv::FAST on the
 // ROI. The iniTh -> minTh fallback is decided per cell on the post-NMS count.
-__global__ void __launch_bounds__(256) k_fast_cells(OrbGeom g, const __grid_constant__ CUtensorMap tmap, int use_tma,
+__global__ void __launch_bounds__(256, 6) k_fast_cells(OrbGeom g, const __grid_constant__ CUtensorMap tmap, int use_tma,
                                                     const uint8_t* __restrict__ pyr, int* __restrict__ cell_count,
                                                     uint32_t* __restrict__ cand_xy, uint32_t* __restrict__ cand_ro,
                                                     int* __restrict__ level_cand, int* __restrict__ status, int cell_begin,
