@@ -129,6 +129,7 @@ def lib():
         L.corb_voc_transform_features.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
         L.corb_voc_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, i32p, vp, vp, vp, i32p]
         L.corb_bow_score_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), vp, vp]
+        L.corb_ba_release_cache.argtypes = [C.c_int]
         L.corb_ba_solve.argtypes = [C.POINTER(BaProblem), C.c_int, vp, C.c_int, C.c_int, C.POINTER(BaResult), vp, vp]
         _lib = L
     return _lib

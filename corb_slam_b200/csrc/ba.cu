@@ -1375,6 +1375,13 @@ __global__ void __launch_bounds__(256) k_ba_iota_hist(const int* __restrict__ e_
 struct BaArena {
     std::mutex mu;
     bool busy = false;
+    bool release_when_idle = false;
+    void free_slabs() {  // caller holds mu and the arena is idle
+        for (auto& s : slabs) cudaFree(s.first);
+        slabs.clear();
+        cur = off = 0;
+        release_when_idle = false;
+    }
     std::vector<std::pair<char*, size_t>> slabs;
     size_t cur = 0, off = 0;
     void* take(size_t bytes) {  // caller holds `busy`
@@ -1425,6 +1432,7 @@ struct BaHost {
         if (arena) {
             std::lock_guard<std::mutex> lk(arena->mu);
             arena->busy = false;
+            if (arena->release_when_idle) arena->free_slabs();
         }
         if (h_scalars) cudaFreeHost(h_scalars);
         if (ev0) cudaEventDestroy(ev0);
@@ -1608,6 +1616,20 @@ static void host_parallel_for(int n, F fn) {
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) th.emplace_back([=]() { fn((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); });
     for (auto& t : th) t.join();
+}
+
+extern "C" int corb_ba_release_cache(int device) {
+    CORB_CHECK(device >= 0 && device < 16, CORB_ERR_INVALID, "device %d out of range", device);
+    std::lock_guard<std::mutex> lk(g_arena[device].mu);
+    if (g_arena[device].busy) {
+        g_arena[device].release_when_idle = true;
+        return CORB_OK;
+    }
+    if (!g_arena[device].slabs.empty()) {
+        CORB_CUDA(cudaSetDevice(device));
+        g_arena[device].free_slabs();
+    }
+    return CORB_OK;
 }
 
 extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile uint8_t* stop, int robust, int device,

@@ -1445,43 +1445,31 @@ __global__ void __launch_bounds__(kOctThreads) k_octtree(OrbGeom g, OrbBuffers b
             else if (s + 3 * n_to_expand > N) final_phase = true;
             continue;
         }
-        // ---- near-quota phase (:660-733): generic step with a sorted processing order and an early stop
+        // ---- near-quota phase (:660-733): a step with a sorted processing order and an early stop (full passes `continue` above)
         int m;
-        if (!final_phase) {
-            for (int i = tid; i < s; i += nt) {
-                const int f = cnt_cur[i] > 1;
-                scan[i] = f;
-                candf[i] = (uint8_t)f;
-            }
-            __syncthreads();
-            m = block_excl_scan(scan, s, warp_tmp);
-            for (int i = tid; i < s; i += nt)
-                if (candf[i]) procpos[scan[i]] = i;
-        } else {
-            for (int i = tid; i < s; i += nt) {
-                const int f = fresh_cur[i] && cnt_cur[i] > 1;
-                scan[i] = f;
-                candf[i] = (uint8_t)f;
-            }
-            __syncthreads();
-            m = block_excl_scan(scan, s, warp_tmp);
-            for (int i = tid; i < s; i += nt)
-                if (candf[i]) krank[scan[i]] = i;  // candidates in position order (temporary)
-            __syncthreads();
-            for (int i = tid; i < m; i += nt) crank[i] = cnt_cur[krank[i]];  // candidate counts, contiguous (temporary)
-            __syncthreads();
-            for (int i = tid; i < m; i += nt) {
-                const int ci = crank[i];
-                int rank = 0;
-#pragma unroll 8
-                for (int j = 0; j < m; j++) {
-                    const int cj = crank[j];
-                    rank += (cj > ci) || (cj == ci && j < i);
-                }
-                procpos[rank] = krank[i];
-            }
-            __syncthreads();
+        for (int i = tid; i < s; i += nt) {
+            const int f = fresh_cur[i] && cnt_cur[i] > 1;
+            scan[i] = f;
+            candf[i] = (uint8_t)f;
         }
+        __syncthreads();
+        m = block_excl_scan(scan, s, warp_tmp);
+        for (int i = tid; i < s; i += nt)
+            if (candf[i]) krank[scan[i]] = i;  // candidates in position order (temporary)
+        __syncthreads();
+        for (int i = tid; i < m; i += nt) crank[i] = cnt_cur[krank[i]];  // candidate counts, contiguous (temporary)
+        __syncthreads();
+        for (int i = tid; i < m; i += nt) {
+            const int ci = crank[i];
+            int rank = 0;
+#pragma unroll 8
+            for (int j = 0; j < m; j++) {
+                const int cj = crank[j];
+                rank += (cj > ci) || (cj == ci && j < i);
+            }
+            procpos[rank] = krank[i];
+        }
+        __syncthreads();
         for (int i = tid; i < 4 * s; i += nt) cc[i] = 0;
         for (int i = tid; i < s; i += nt) crank[i] = -1;
         if (tid == 0) { sh[0] = m; sh[1] = 0; sh[2] = 0; }

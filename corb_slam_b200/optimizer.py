@@ -42,6 +42,11 @@ def torch_allreduce(group=None):
     return ALLREDUCE_FN(_cb)
 
 
+def release_cache(device=0):
+    """Returns the device memory corb_ba_solve keeps between calls (corb_ba_release_cache)."""
+    check(lib().corb_ba_release_cache(int(device)))
+
+
 class Optimizer:
     @staticmethod
     def BundleAdjustment(problem, nIterations=5, pbStopFlag=None, nLoopKF=0, bRobust=True, device=0, allreduce=None):

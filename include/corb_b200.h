@@ -312,6 +312,11 @@ typedef struct {
     int32_t separator_poses;     /* keyframes ordered last only to decouple the chunks */
 } corb_ba_result;
 
+/* corb_ba_solve keeps its device buffers in a per-device arena between calls (a global BA allocates ~40 buffers; the
+ * cudaMalloc / cudaFree pairs cost as much as the optimisation). This returns the arena of `device` to the driver;
+ * a call that is running on the device keeps its memory and the arena is released when it ends. */
+CORB_API int corb_ba_release_cache(int device);
+
 /* All-reduce hook for landmark-sharded BA: `buf` is a DEVICE pointer to n doubles, reduced in place over
  * all ranks with op 0 = sum, 1 = min, 2 = max, ordered on CUDA stream `stream` (a cudaStream_t). The C++ server passes
  * a function that calls ncclAllReduce on its communicator; the Python host layer passes torch.distributed.all_reduce. */

@@ -137,3 +137,15 @@ def test_ba_dense_covisibility():
     assert g_info["band_chunks"] == 1
     prob = ba_problem(60, 3000, seed=22, obs_per_point=20, n_fusion=0)   # fits the merged cache (<= 32 blocks), not one warp's
     _check(prob, iters=5)
+
+
+def test_ba_arena_release_and_reuse():
+    """corb_ba_release_cache returns the per-device arena; the next call rebuilds it and gives the same result."""
+    from corb_slam_b200.optimizer import release_cache
+    prob = ba_problem(30, 3000, seed=4, n_fusion=4)
+    a, ia = Optimizer.BundleAdjustment(prob, 4, bRobust=False)
+    release_cache(0)
+    release_cache(0)
+    b, ib = Optimizer.BundleAdjustment(prob, 4, bRobust=False)
+    assert ia["chi2_final"] == ib["chi2_final"]
+    np.testing.assert_array_equal(a["pose_t"], b["pose_t"])
