@@ -1376,11 +1376,19 @@ struct BaArena {
     std::mutex mu;
     bool busy = false;
     bool release_when_idle = false;
+    // the call's stream, timing events and pinned scalar mailbox live with the arena too (~2 ms of driver calls per BA otherwise)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double* h_scalars = nullptr;
     void free_slabs() {  // caller holds mu and the arena is idle
         for (auto& s : slabs) cudaFree(s.first);
         slabs.clear();
         cur = off = 0;
         release_when_idle = false;
+        if (h_scalars) cudaFreeHost(h_scalars), h_scalars = nullptr;
+        if (ev0) cudaEventDestroy(ev0), ev0 = nullptr;
+        if (ev1) cudaEventDestroy(ev1), ev1 = nullptr;
+        if (stream) cudaStreamDestroy(stream), stream = nullptr;
     }
     std::vector<std::pair<char*, size_t>> slabs;
     size_t cur = 0, off = 0;
@@ -1407,6 +1415,7 @@ static BaArena g_arena[16];
 struct BaHost {
     int device;
     BaArena* arena = nullptr;  // non-null while this call owns its device's arena
+    bool arena_owns_handles = false;
     cudaStream_t stream = nullptr;
     std::vector<void*> allocs;
     BaDev d;
@@ -1434,10 +1443,12 @@ struct BaHost {
             arena->busy = false;
             if (arena->release_when_idle) arena->free_slabs();
         }
-        if (h_scalars) cudaFreeHost(h_scalars);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-        if (stream) cudaStreamDestroy(stream);
+        if (!arena_owns_handles) {
+            if (h_scalars) cudaFreeHost(h_scalars);
+            if (ev0) cudaEventDestroy(ev0);
+            if (ev1) cudaEventDestroy(ev1);
+            if (stream) cudaStreamDestroy(stream);
+        }
     }
     template <typename T>
     int alloc(T** p, size_t n) {
@@ -1670,10 +1681,20 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     }
     H.ar = allreduce;
     H.ar_user = allreduce_user;
-    CORB_CUDA(cudaStreamCreateWithFlags(&H.stream, cudaStreamNonBlocking));
-    CORB_CUDA(cudaEventCreate(&H.ev0));
-    CORB_CUDA(cudaEventCreate(&H.ev1));
-    CORB_CUDA(cudaMallocHost(&H.h_scalars, 8 * sizeof(double)));
+    if (H.arena) {
+        BaArena& A = *H.arena;
+        if (!A.stream) CORB_CUDA(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
+        if (!A.ev0) CORB_CUDA(cudaEventCreate(&A.ev0));
+        if (!A.ev1) CORB_CUDA(cudaEventCreate(&A.ev1));
+        if (!A.h_scalars) CORB_CUDA(cudaMallocHost(&A.h_scalars, 8 * sizeof(double)));
+        H.stream = A.stream; H.ev0 = A.ev0; H.ev1 = A.ev1; H.h_scalars = A.h_scalars;
+        H.arena_owns_handles = true;
+    } else {
+        CORB_CUDA(cudaStreamCreateWithFlags(&H.stream, cudaStreamNonBlocking));
+        CORB_CUDA(cudaEventCreate(&H.ev0));
+        CORB_CUDA(cudaEventCreate(&H.ev1));
+        CORB_CUDA(cudaMallocHost(&H.h_scalars, 8 * sizeof(double)));
+    }
     BaDev& d = H.d;
     memset(&d, 0, sizeof(d));
     d.P = P; d.L = L; d.E = E; d.robust = robust != 0;

@@ -692,14 +692,14 @@ static int ensure_pair_graph(corb_orb* hl, corb_orb* hr, int variant, float mbf,
     // give each image its own launches so that the left image's pipeline starts as soon as *its* bytes are in, while
     // the right image is still being read (measured: 145 -> 132 us per frame); device-resident images are processed
     // together in every launch (grid z = 2). CORB_PAIR_MERGED=1 forces the merged form everywhere (A/B switch).
-    const bool split = variant >= 1 && getenv("CORB_PAIR_MERGED") == nullptr && !hl->h2d_node;
+    const bool split = (variant >= 1 || getenv("CORB_PAIR_SPLIT_DEV") != nullptr) && getenv("CORB_PAIR_MERGED") == nullptr && !hl->h2d_node;
     hl->pair_split[variant] = split;
     if (split && ((rc = sr.init(L, 2 * L + 3)) != CORB_OK || (rc = sb.init(1, 2)) != CORB_OK)) return rc;
     CORB_CUDA(cudaStreamBeginCapture(hl->stream, cudaStreamCaptureModeThreadLocal));
     if (split) {
-        capture_frame(hl, hl->stream, true, sl.ls, sl.ev, nullptr, sb.ev[0]);
+        capture_frame(hl, hl->stream, variant >= 1, sl.ls, sl.ev, nullptr, sb.ev[0]);
         cudaStreamWaitEvent(sb.ls[0], sb.ev[0], 0);  // right import behind the left import
-        capture_frame(hr, sb.ls[0], true, sr.ls, sr.ev);
+        capture_frame(hr, sb.ls[0], variant >= 1, sr.ls, sr.ev);
         cudaEventRecord(sb.ev[1], sb.ls[0]);
         cudaStreamWaitEvent(hl->stream, sb.ev[1], 0);
     } else {
