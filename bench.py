@@ -283,8 +283,70 @@ def bench_matcher(device, with_cpu=True):
         out["search_by_projection"]["cpu_last_frame_calls_per_s"] = reps / (t1 - t0)
         out["search_by_projection"]["cpu_map_points_calls_per_s"] = reps / (t2 - t1)
     pm.close()
+    out["pnp_ransac"] = bench_pnp(device, with_cpu)
     out["workload"] = "k=10 L=5 synthetic vocabulary, 2000 descriptors per frame, 32 candidate keyframes, level-2 node groups"
     m.close(); gvoc.close()
+    return out
+
+
+def pnp_workload(n_cand=20, n=150):
+    """The relocalisation / map-fusion loop: n_cand candidate keyframes, each a PnPsolver over n matches (30 % of them wrong),
+    SetRansacParameters(0.99, 10, 300, 4, 0.5, 5.991) as Tracking.cc:1414 / MapFusion.cpp:701, explicit draws."""
+    import numpy as np
+    from corb_slam_b200.synth import pnp_problem
+    rng = np.random.default_rng(11)
+    cands = []
+    for c in range(n_cand):
+        p = pnp_problem(500 + c, n=n, outlier_fraction=0.3 if c % 4 else 0.97, pixel_noise=0.5)  # every fourth candidate is a false positive
+        draws = np.stack([rng.integers(0, n - k, 300) for k in range(4)], 1).astype(np.int32)
+        cands.append((p, draws))
+    return cands
+
+
+def bench_pnp(device, with_cpu=True, reps=20):
+    """EPnP-RANSAC batched over candidates: ms per batch through the C ABI (host arrays in and out)
+    beside the sequential oracle port on one host thread."""
+    import numpy as np
+    from corb_slam_b200 import PnPsolver
+    cands = pnp_workload()
+
+    def solvers():
+        out = []
+        for p, draws in cands:
+            n = len(p["p2d"])
+            s = PnPsolver(p["p2d"], np.zeros(n, np.int64), p["sigma2"][:1] * 0 + 1.0, p["K"], p["p3d"], np.ones(n, bool), device=device)
+            s.mvSigma2 = p["sigma2"]
+            s.SetRansacParameters(0.99, 10, 300, 4, 0.5, 5.991)
+            s.set_draws(draws)
+            out.append(s)
+        return out
+
+    PnPsolver.iterate_batch(solvers(), 5)
+    t = 0.0
+    hyp = 0
+    for _ in range(reps):
+        ss = solvers()
+        t0 = time.perf_counter()
+        res = PnPsolver.iterate_batch(ss, 5)
+        t += time.perf_counter() - t0
+        hyp = sum(s.mRansacMaxIts for s in ss)
+    out = {"candidates": len(cands), "matches_per_candidate": len(cands[0][0]["p2d"]), "hypotheses_per_batch": hyp,
+           "ms_per_batch": 1e3 * t / reps, "hypotheses_per_s": hyp * reps / t, "poses_found": sum(r[0] is not None for r in res),
+           "note": "one corb_pnp_iterate_batch call: every RANSAC hypothesis of every candidate is evaluated (H2D + 6 kernels + D2H)"}
+    if with_cpu:
+        from oracle import _pnp_bind as PB
+        t = 0.0
+        its = 0
+        for _ in range(3):
+            for (p, draws), s in zip(cands, solvers()):
+                o = PB.PnpSolver(p["p2d"], p["p3d"], s.mvMaxError, *[float(v) for v in p["K"]], s.mRansacMinInliers, s.mRansacMaxIts)
+                t0 = time.perf_counter()
+                o.iterate(5, draws)
+                t += time.perf_counter() - t0
+                its += o.iterations
+        out["cpu_ms_per_batch"] = 1e3 * t / 3
+        out["cpu_iterations_per_batch"] = its / 3
+        out["cpu"] = "oracle port, 1 thread, sequential with the reference's early exit (fewer hypotheses than the GPU evaluates)"
     return out
 
 

@@ -47,6 +47,19 @@ class BaResult(C.Structure):
                 ("band_chunks", C.c_int32), ("separator_poses", C.c_int32)]
 
 
+class PnpProblem(C.Structure):
+    """corb_pnp_problem (include/corb_b200.h)."""
+    _fields_ = [("n", C.c_int32), ("p2d", vp), ("p3d", vp), ("max_err", vp), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("min_inliers", C.c_int32), ("max_its", C.c_int32), ("iterations_done", C.c_int32),
+                ("n_iterations", C.c_int32), ("draws", vp)]
+
+
+class PnpResult(C.Structure):
+    """corb_pnp_result (include/corb_b200.h)."""
+    _fields_ = [("status", C.c_int32), ("no_more", C.c_int32), ("n_inliers", C.c_int32), ("iterations", C.c_int32),
+                ("Tcw", C.c_float * 16)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, vp, vp, C.c_size_t, C.c_int, vp)
 
 
@@ -129,6 +142,8 @@ def lib():
         L.corb_voc_transform_features.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
         L.corb_voc_transform.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, i32p, vp, vp, vp, i32p]
         L.corb_bow_score_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), vp, vp]
+        L.corb_pnp_ransac_params.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p]
+        L.corb_pnp_iterate_batch.argtypes = [vp, C.c_int, C.POINTER(PnpProblem), C.POINTER(PnpResult), C.POINTER(vp)]
         L.corb_ba_release_cache.argtypes = [C.c_int]
         L.corb_ba_solve.argtypes = [C.POINTER(BaProblem), C.c_int, vp, C.c_int, C.c_int, C.POINTER(BaResult), vp, vp]
         _lib = L

@@ -285,6 +285,7 @@ struct corb_matcher {
     Arena arena;
     Arena dev_calls;  // for the device-resident batch form (call table + scratch)
     Arena proj;       // projection matchers (proj_match.cu)
+    Arena pnp;        // EPnP-RANSAC batches (pnp.cu)
 };
 
 namespace corb {
@@ -295,6 +296,13 @@ int matcher_proj_reserve(corb_matcher* m, size_t bytes, uint8_t** d, uint8_t** h
     if (rc != CORB_OK) return rc;
     *d = m->proj.d;
     *h = m->proj.h;
+    return CORB_OK;
+}
+int matcher_pnp_reserve(corb_matcher* m, size_t bytes, uint8_t** d, uint8_t** h) {
+    int rc = m->pnp.reserve(bytes);
+    if (rc != CORB_OK) return rc;
+    *d = m->pnp.d;
+    *h = m->pnp.h;
     return CORB_OK;
 }
 }  // namespace corb
@@ -336,6 +344,7 @@ void corb_matcher_destroy(corb_matcher* m) {
     m->arena.release();
     m->dev_calls.release();
     m->proj.release();
+    m->pnp.release();
     delete m;
 }
 

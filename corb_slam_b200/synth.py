@@ -208,3 +208,29 @@ def projection_scene(seed=0, n_points=2500, w=1242, h=375, n_levels=8, scale_fac
     return {"scales": scales, "bounds": (0.0, 0.0, float(w), float(h)), "K": (fx, fy, cx, cy), "mbf": bf, "Tcw": Tcw, "Tlw": Tlw,
             "cur": cur, "taken": taken, "last": last, "last_valid": last_valid, "last_blocks": last_blocks, "Xw": Xw,
             "mp_desc": desc, "proj": proj, "in_view": in_view.astype(np.uint8), "level": level, "view_cos": view_cos}
+
+
+def pnp_problem(seed, n=120, outlier_fraction=0.4, pixel_noise=0.7, w=1242, h=375, n_levels=8, scale_factor=1.2):
+    """One relocalisation / map-fusion candidate for PnPsolver (PnPsolver.cc:66-111): `n` 2-D keypoints matched to
+    MapPoints, `outlier_fraction` of them wrong matches. Returns float32 p2d [n,2], p3d [n,3] (world), sigma2 [n]
+    (mvLevelSigma2 of the keypoint octave), the KITTI intrinsics (fx, fy, cx, cy) and the true Tcw (3x4, float64)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, _ = KITTI_CAM
+    yaw, pitch = rng.normal(0, 0.2), rng.normal(0, 0.03)
+    Ry = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+    Rx = np.array([[1, 0, 0], [0, np.cos(pitch), -np.sin(pitch)], [0, np.sin(pitch), np.cos(pitch)]])
+    R = Rx @ Ry
+    t = rng.normal(0, 1.0, 3) * np.array([1.0, 0.1, 1.0])
+    z = rng.uniform(4.0, 50.0, n)
+    u = rng.uniform(0, w, n)
+    v = rng.uniform(0, h, n)
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    Xw = (Xc - t) @ R  # Xc = R Xw + t
+    octave = rng.integers(0, n_levels, n)
+    sigma2 = (np.float32(scale_factor) ** octave.astype(np.float32)) ** 2
+    p2d = np.stack([u, v], 1) + rng.normal(0, pixel_noise, (n, 2)) * np.sqrt(sigma2)[:, None]
+    bad = rng.random(n) < outlier_fraction
+    p2d[bad] = np.stack([rng.uniform(0, w, bad.sum()), rng.uniform(0, h, bad.sum())], 1)
+    return {"p2d": p2d.astype(np.float32), "p3d": Xw.astype(np.float32), "sigma2": sigma2.astype(np.float32),
+            "K": (np.float32(fx), np.float32(fy), np.float32(cx), np.float32(cy)), "Tcw": np.concatenate([R, t[:, None]], 1),
+            "outlier": bad}

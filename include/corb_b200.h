@@ -5,6 +5,7 @@
  *   Hamming / BoW      corbslam_client/include/ORBmatcher.h:41-67,  src/ORBmatcher.cc:162-423,657-790,1792-1808
  *   DBoW2              corbslam_client/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1259,1338-1424,
  *                      ScoringObject.cpp:23-68, BowVector.cpp:34-84, FeatureVector.cpp:31-45
+ *   EPnP-RANSAC        corbslam_client/include/PnPsolver.h:64-78,   src/PnPsolver.cc:66-383,420-962
  *   global BA          corbslam_client/include/Optimizer.h:42-46, src/Optimizer.cc:54-270 and the g2o slice under it
  *
  * Plain pointers and sizes only. All functions return a corb_status (0 = ok); corb_last_error() gives the text of
@@ -268,6 +269,52 @@ CORB_API int corb_voc_transform(corb_voc* v, const uint8_t* desc, int n, int lev
 CORB_API int corb_bow_score_batch(corb_voc* v, const uint32_t* q_words, const double* q_vals, int nq, int ncand,
                                   const uint32_t* const* c_words, const double* const* c_vals, const int32_t* c_n,
                                   double* scores);
+
+/* ------------------------------------------------------------------------------------------------ EPnP-RANSAC (PnPsolver) */
+
+/* PnPsolver::SetRansacParameters(probability, minInliers, maxIterations, minSet, epsilon, th2) [PnPsolver.cc:163-198]:
+ * the adjusted mRansacMinInliers and mRansacMaxIts for N correspondences (host scalar logic, no device needed). */
+CORB_API int corb_pnp_ransac_params(int N, double probability, int min_inliers, int max_iterations, int min_set, float epsilon,
+                                    int* out_min_inliers, int* out_max_its);
+
+/* One PnPsolver object flattened by the shim [constructor PnPsolver.cc:66-151]: the matches with a live MapPoint
+ * (pMP && !pMP->isBad()), in mvKeyPointIndices order. The reference draws its minimal sets from the process-global
+ * rand() stream (DUtils::Random::RandomInt, Random.cpp:47-50), so its result is not a function of its arguments; here
+ * the draws are an argument: draws[4 * it + k] is the value RandomInt(0, vAvailableIndices.size() - 1) returns for pick k
+ * of RANSAC iteration `it` (0-based over the life of the solver object), i.e. 0 <= draws[4 * it + k] < n - k. The shim
+ * draws them with the same RandomInt calls, for iterations [0, it_end), it_end = max(max_its, iterations_done +
+ * n_iterations) - the loop condition of iterate() (:223). The call is stateless: iterations [0, iterations_done) are
+ * recomputed (the best-so-far state of the reference object is a function of them). */
+typedef struct {
+    int32_t n;               /* N = mvP2D.size() */
+    const float* p2d;        /* [n][2] mvP2D: undistorted keypoint positions */
+    const float* p3d;        /* [n][3] mvP3Dw: MapPoint world positions */
+    const float* max_err;    /* [n] mvMaxError = mvLevelSigma2[octave] * th2 (:194-197) */
+    float fx, fy, cx, cy;    /* :107-110 */
+    int32_t min_inliers;     /* adjusted mRansacMinInliers */
+    int32_t max_its;         /* adjusted mRansacMaxIts */
+    int32_t iterations_done; /* mnIterations before this call */
+    int32_t n_iterations;    /* the nIterations argument of iterate() */
+    const int32_t* draws;    /* [it_end][4] */
+} corb_pnp_problem;
+
+typedef struct {
+    int32_t status;     /* 0 = empty cv::Mat; 1 = refined pose (early return, :262-273); 2 = best pose when the iterations
+                           are exhausted (:279-291) */
+    int32_t no_more;    /* bNoMore */
+    int32_t n_inliers;  /* nInliers */
+    int32_t iterations; /* mnIterations after the call */
+    float Tcw[16];      /* row-major 4x4 CV_32F, valid when status != 0 */
+} corb_pnp_result;
+
+/* PnPsolver::iterate(nIterations, bNoMore, vbInliers, nInliers) [PnPsolver.cc:206-300] for a batch of solver objects -
+ * the relocalisation / map-fusion candidates of Tracking.cc:1432-1440 and MapFusion.cpp:720-728 - in one call: every
+ * RANSAC hypothesis of every candidate is one GPU thread (EPnP on 4 points), inlier counting one warp per hypothesis,
+ * Refine() one thread per best-so-far record; the sequential bookkeeping of the reference (best so far, the first
+ * iteration whose Refine() succeeds) is resolved afterwards from the per-hypothesis results. inliers[c] (nullable)
+ * receives n bytes: vbInliers over the flattened correspondences (the shim scatters them through mvKeyPointIndices). */
+CORB_API int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_problem* problems, corb_pnp_result* results,
+                                    uint8_t* const* inliers);
 
 /* ------------------------------------------------------------------------------------------------ global bundle adjustment */
 

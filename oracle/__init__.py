@@ -77,6 +77,9 @@ def lib():
         if hasattr(L, "oracle_search_by_projection_last"):
             from . import _proj_bind
             _proj_bind.bind(L)
+        if hasattr(L, "oracle_pnp_iterate"):
+            from . import _pnp_bind
+            _pnp_bind.bind(L)
         _lib = L
     return _lib
 
