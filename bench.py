@@ -305,40 +305,45 @@ def pnp_workload(n_cand=20, n=150):
 
 def bench_pnp(device, with_cpu=True, reps=20):
     """EPnP-RANSAC batched over candidates: ms per batch through the C ABI (host arrays in and out)
-    beside the sequential oracle port on one host thread."""
+    at a relocalisation-sized batch (20 candidates) and a map-fusion-sized one (200), beside the sequential oracle port on
+    one host thread."""
     import numpy as np
     from corb_slam_b200 import PnPsolver
-    cands = pnp_workload()
 
-    def solvers():
+    def solvers(cands):
         out = []
         for p, draws in cands:
             n = len(p["p2d"])
-            s = PnPsolver(p["p2d"], np.zeros(n, np.int64), p["sigma2"][:1] * 0 + 1.0, p["K"], p["p3d"], np.ones(n, bool), device=device)
+            s = PnPsolver(p["p2d"], np.zeros(n, np.int64), [1.0], p["K"], p["p3d"], np.ones(n, bool), device=device)
             s.mvSigma2 = p["sigma2"]
             s.SetRansacParameters(0.99, 10, 300, 4, 0.5, 5.991)
             s.set_draws(draws)
             out.append(s)
         return out
 
-    PnPsolver.iterate_batch(solvers(), 5)
-    t = 0.0
-    hyp = 0
-    for _ in range(reps):
-        ss = solvers()
-        t0 = time.perf_counter()
-        res = PnPsolver.iterate_batch(ss, 5)
-        t += time.perf_counter() - t0
+    def gpu(cands):
+        PnPsolver.iterate_batch(solvers(cands), 5)
+        t = 0.0
+        for _ in range(reps):
+            ss = solvers(cands)
+            t0 = time.perf_counter()
+            res = PnPsolver.iterate_batch(ss, 5)
+            t += time.perf_counter() - t0
         hyp = sum(s.mRansacMaxIts for s in ss)
-    out = {"candidates": len(cands), "matches_per_candidate": len(cands[0][0]["p2d"]), "hypotheses_per_batch": hyp,
-           "ms_per_batch": 1e3 * t / reps, "hypotheses_per_s": hyp * reps / t, "poses_found": sum(r[0] is not None for r in res),
-           "note": "one corb_pnp_iterate_batch call: every RANSAC hypothesis of every candidate is evaluated (H2D + 6 kernels + D2H)"}
+        return {"candidates": len(cands), "hypotheses_per_batch": hyp, "ms_per_batch": 1e3 * t / reps, "hypotheses_per_s": hyp * reps / t,
+                "poses_found": sum(r[0] is not None for r in res)}
+
+    cands = pnp_workload()
+    out = gpu(cands)
+    out["matches_per_candidate"] = len(cands[0][0]["p2d"])
+    out["note"] = "one corb_pnp_iterate_batch call: every RANSAC hypothesis of every candidate is evaluated (H2D + 6 kernels + D2H)"
+    out["large_batch"] = gpu(pnp_workload(n_cand=200))
     if with_cpu:
         from oracle import _pnp_bind as PB
         t = 0.0
         its = 0
         for _ in range(3):
-            for (p, draws), s in zip(cands, solvers()):
+            for (p, draws), s in zip(cands, solvers(cands)):
                 o = PB.PnpSolver(p["p2d"], p["p3d"], s.mvMaxError, *[float(v) for v in p["K"]], s.mRansacMinInliers, s.mRansacMaxIts)
                 t0 = time.perf_counter()
                 o.iterate(5, draws)

@@ -65,13 +65,15 @@ struct PnpDev {
 constexpr int kSolveThreads = 32;
 constexpr size_t kSolveSmem = (size_t)WS_DOUBLES * kSolveThreads * sizeof(double);
 
-// MODE 0: thread = RANSAC iteration (minimal set of 4 from the draws, :228-246). MODE 1: thread = best-so-far record
+// MODE 0: thread = RANSAC iteration (minimal set of 4 from the draws, :228-246). MODE 1: warp = best-so-far record
 // (EPnP over the record's inlier mask = Refine(), :302-324).
 template <int MODE>
 __global__ void __launch_bounds__(kSolveThreads) k_pnp_solve(PnpDev D) {
     extern __shared__ double smem[];
     const PnpProb P = D.probs[blockIdx.y];
-    const int item = blockIdx.x * kSolveThreads + threadIdx.x;
+    // MODE 1: the whole warp works on one record (ordered sums over the inliers split across lanes, everything else
+    // replicated per lane on the lane's own workspace)
+    const int item = MODE == 0 ? blockIdx.x * kSolveThreads + threadIdx.x : blockIdx.x;
     if (MODE == 0 ? item >= P.it_end : item >= D.n_rec[blockIdx.y]) return;
     PtSet s;
     s.p3d = D.p3d + 3 * (size_t)P.pt_off;
@@ -111,9 +113,11 @@ __global__ void __launch_bounds__(kSolveThreads) k_pnp_solve(PnpDev D) {
     Epnp e;
     e.fu = (double)P.fx; e.fv = (double)P.fy; e.uc = (double)P.cx; e.vc = (double)P.cy;
     double Rt[12];
-    e.compute_pose(s, Ws{smem + threadIdx.x, kSolveThreads}, Rt);
+    e.template compute_pose<MODE == 1>(s, Ws{smem + threadIdx.x, kSolveThreads}, Rt);
+    if (MODE == 0 || threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) out[i] = Rt[i];
+        for (int i = 0; i < 12; i++) out[i] = Rt[i];
+    }
 }
 
 // CheckInliers: one warp per pose (hypothesis or refined record), lane = correspondence, ballot = mask word.
@@ -343,7 +347,7 @@ int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_probl
     k_pnp_solve<0><<<gs, kSolveThreads, kSolveSmem, st>>>(D);
     k_pnp_check<0><<<gc, kCheckWarps * 32, 0, st>>>(D);
     k_pnp_records<<<C, 32, 0, st>>>(D);
-    k_pnp_solve<1><<<gs, kSolveThreads, kSolveSmem, st>>>(D);
+    k_pnp_solve<1><<<dim3(max_it, C), kSolveThreads, kSolveSmem, st>>>(D);  // blocks beyond a problem's record count exit
     k_pnp_check<1><<<gc, kCheckWarps * 32, 0, st>>>(D);
     k_pnp_finalize<<<C, 32, 0, st>>>(D);
     CORB_CUDA(cudaGetLastError());

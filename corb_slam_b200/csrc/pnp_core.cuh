@@ -79,9 +79,46 @@ CORB_HD inline void load_pw(const PtSet& s, int idx, double pw[3]) {  // add_cor
     pw[0] = (double)s.p3d[3 * idx]; pw[1] = (double)s.p3d[3 * idx + 1]; pw[2] = (double)s.p3d[3 * idx + 2];
 }
 
+// acc[a] += term_a(point) for every point of the set, in set order. WARP (device only, mask sets only, all 32 lanes of
+// the warp hold identical state and call together): lane l evaluates the addends of bit l of each mask word, then the
+// additions are performed in ascending bit order on every lane (shuffle broadcast), so each lane ends with the same
+// accumulators a single thread would have produced - same addends, same order, same bits.
+template <bool WARP, int NA, class F>
+CORB_HD inline void ordered_sum(const PtSet& s, double* acc, F&& term) {
+#ifdef __CUDA_ARCH__
+    if (WARP) {
+        const int lane = threadIdx.x & 31;
+        for (int w = 0; w < s.n_words; w++) {
+            const uint32_t bits = s.mask[w];
+            if (!bits) continue;
+            double t[NA];
+#pragma unroll
+            for (int a = 0; a < NA; a++) t[a] = 0;
+            if ((bits >> lane) & 1u) term(w * 32 + lane, t);
+            for (uint32_t b = bits; b; b &= b - 1) {
+                const int k = __ffs((int)b) - 1;
+#pragma unroll
+                for (int a = 0; a < NA; a++) acc[a] += __shfl_sync(0xffffffffu, t[a], k);
+            }
+        }
+        return;
+    }
+#endif
+    PtIter it;
+    int idx;
+    double t[NA];
+    for (it_begin(it); it_next(s, it, idx);) {
+        term(idx, t);
+        for (int a = 0; a < NA; a++) acc[a] += t[a];
+    }
+}
+
 // JacobiSVDImpl_<double>: At = A^T (n rows of length m, m >= n). On return row i of At = left singular vector i, W
 // descending, row i of Vt = right singular vector i (only when with_v).
-CORB_HD inline void jacobi_svd(Ws At, Ws W, Ws Vt, bool with_v, int m, int n) {
+// The sizes are template parameters so that the loops over a row unroll: a thread then has all loads of a row pair in
+// flight at once instead of one dependent load-multiply-add per trip (3x on the whole EPnP).
+template <int m, int n, bool with_v>
+CORB_HD inline void jacobi_svd(Ws At, Ws W, Ws Vt) {
     const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
     const int max_iter = m > 30 ? m : 30;
     for (int i = 0; i < n; i++) {
@@ -99,6 +136,7 @@ CORB_HD inline void jacobi_svd(Ws At, Ws W, Ws Vt, bool with_v, int m, int n) {
             for (int j = i + 1; j < n; j++) {
                 const Ws Ai = At.at(i * m), Aj = At.at(j * m);
                 double a = W[i], p = 0, b = W[j];
+#pragma unroll
                 for (int k = 0; k < m; k++) p += Ai[k] * Aj[k];
                 if (fabs(p) <= eps * sqrt(a * b)) continue;
                 p *= 2;
@@ -113,6 +151,7 @@ CORB_HD inline void jacobi_svd(Ws At, Ws W, Ws Vt, bool with_v, int m, int n) {
                     s = p / (gamma * c * 2);
                 }
                 a = b = 0;
+#pragma unroll
                 for (int k = 0; k < m; k++) {
                     const double x = Ai[k], y = Aj[k];
                     const double t0 = c * x + s * y;
@@ -124,6 +163,7 @@ CORB_HD inline void jacobi_svd(Ws At, Ws W, Ws Vt, bool with_v, int m, int n) {
                 changed = true;
                 if (with_v) {
                     const Ws Vi = Vt.at(i * n), Vj = Vt.at(j * n);
+#pragma unroll
                     for (int k = 0; k < n; k++) {
                         const double x = Vi[k], y = Vj[k];
                         const double t0 = c * x + s * y;
@@ -158,16 +198,18 @@ CORB_HD inline void jacobi_svd(Ws At, Ws W, Ws Vt, bool with_v, int m, int n) {
 }
 
 // SVD of a small row-major m x n matrix held in registers / local memory, through the S area of the workspace.
-CORB_HD inline void svd_small(const double* A, int m, int n, bool with_v, Ws ws) {
+template <int m, int n, bool with_v>
+CORB_HD inline void svd_small(const double* A, Ws ws) {
     const Ws At = ws.at(WS_S);
     for (int i = 0; i < n; i++)
         for (int k = 0; k < m; k++) At[i * m + k] = A[k * n + i];
-    jacobi_svd(At, ws.at(WS_SW), ws.at(WS_SV), with_v, m, n);
+    jacobi_svd<m, n, with_v>(At, ws.at(WS_SW), ws.at(WS_SV));
 }
 
 // cvSolve(CV_SVD), one right-hand side (SVBkSbImpl_): x = sum_i v_i ((u_i . b) (1 / w_i)) over w_i > 2 eps sum(w)
-CORB_HD inline void svd_solve(const double* A, int m, int n, const double* b, double* x, Ws ws) {
-    svd_small(A, m, n, true, ws);
+template <int m, int n>
+CORB_HD inline void svd_solve(const double* A, const double* b, double* x, Ws ws) {
+    svd_small<m, n, true>(A, ws);
     const Ws Ut = ws.at(WS_S), Vt = ws.at(WS_SV), W = ws.at(WS_SW);
     double threshold = 0;
     for (int i = 0; i < n; i++) { x[i] = 0; threshold += W[i]; }
@@ -185,7 +227,7 @@ CORB_HD inline void svd_solve(const double* A, int m, int n, const double* b, do
 
 // cvInvert(CV_SVD) of a 3 x 3 matrix
 CORB_HD inline void svd_invert3(const double* A, double* inv, Ws ws) {
-    svd_small(A, 3, 3, true, ws);
+    svd_small<3, 3, true>(A, ws);
     const Ws Ut = ws.at(WS_S), Vt = ws.at(WS_SV), W = ws.at(WS_SW);
     double threshold = 0;
     for (int i = 0; i < 3; i++) threshold += W[i];
@@ -223,25 +265,21 @@ struct Epnp {
         for (int j = 0; j < 3; j++) pc[j] = a[0] * ccs[0][j] + a[1] * ccs[1][j] + a[2] * ccs[2][j] + a[3] * ccs[3][j];
     }
 
+    template <bool WARP>
     CORB_HD void choose_control_points(const PtSet& s, Ws ws) {  // :420-455
         const int n = s.n;
-        PtIter it;
-        int idx;
-        double pw[3];
-        cws[0][0] = cws[0][1] = cws[0][2] = 0;
-        for (it_begin(it); it_next(s, it, idx);) {
-            load_pw(s, idx, pw);
-            for (int j = 0; j < 3; j++) cws[0][j] += pw[j];
-        }
-        for (int j = 0; j < 3; j++) cws[0][j] /= n;
-        double m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0;
-        for (it_begin(it); it_next(s, it, idx);) {
+        double c0[3] = {0, 0, 0};
+        ordered_sum<WARP, 3>(s, c0, [&](int idx, double* t) { load_pw(s, idx, t); });
+        for (int j = 0; j < 3; j++) cws[0][j] = c0[j] / n;
+        double m[6] = {0, 0, 0, 0, 0, 0};  // upper triangle of PW0^T PW0: 00 01 02 11 12 22
+        ordered_sum<WARP, 6>(s, m, [&](int idx, double* t) {
+            double pw[3];
             load_pw(s, idx, pw);
             const double d0 = pw[0] - cws[0][0], d1 = pw[1] - cws[0][1], d2 = pw[2] - cws[0][2];
-            m00 += d0 * d0; m01 += d0 * d1; m02 += d0 * d2; m11 += d1 * d1; m12 += d1 * d2; m22 += d2 * d2;
-        }
-        const double ptp[9] = {m00, m01, m02, m01, m11, m12, m02, m12, m22};
-        svd_small(ptp, 3, 3, false, ws);
+            t[0] = d0 * d0; t[1] = d0 * d1; t[2] = d0 * d2; t[3] = d1 * d1; t[4] = d1 * d2; t[5] = d2 * d2;
+        });
+        const double ptp[9] = {m[0], m[1], m[2], m[1], m[3], m[4], m[2], m[4], m[5]};
+        svd_small<3, 3, false>(ptp, ws);
         const Ws uct = ws.at(WS_S), dc = ws.at(WS_SW);
         for (int i = 1; i < 4; i++) {
             const double k = sqrt(dc[i - 1] / n);
@@ -256,21 +294,70 @@ struct Epnp {
         svd_invert3(cc, ci, ws);
     }
 
-    // M^T M accumulated row by row (fill_M :484-500 + cvMulTransposed), then its SVD: rows of ws[WS_A..] = Ut
+    // the two rows fill_M (:484-500) writes for one correspondence, column c: M1 = a[c/3] * {fu, 0, uc-u}[c%3],
+    // M2 = a[c/3] * {0, fv, vc-v}[c%3]
+    CORB_HD void m_rows(const PtSet& s, int idx, double* M1, double* M2) const {
+        double pw[3], a[4];
+        load_pw(s, idx, pw);
+        alphas_of(pw, a);
+        const double u = (double)s.p2d[2 * idx], v = (double)s.p2d[2 * idx + 1];
+        for (int i = 0; i < 4; i++) {
+            M1[3 * i] = a[i] * fu; M1[3 * i + 1] = 0.0; M1[3 * i + 2] = a[i] * (uc - u);
+            M2[3 * i] = 0.0; M2[3 * i + 1] = a[i] * fv; M2[3 * i + 2] = a[i] * (vc - v);
+        }
+    }
+
+    // M^T M accumulated row by row (cvMulTransposed: every element summed over the rows in order), then its SVD: rows
+    // of ws[WS_A..] = Ut. WARP: lane l owns the upper-triangle entries l, l+32, l+64 and adds every correspondence's two
+    // products to them in set order; the entries are then broadcast into every lane's copy of the workspace.
+    template <bool WARP>
     CORB_HD void mtm_svd(const PtSet& s, Ws ws) {
         const Ws A = ws.at(WS_A);
+#ifdef __CUDA_ARCH__
+        if (WARP) {
+            const int lane = threadIdx.x & 31;
+            int ei[3], ej[3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {  // entry e = lane + 32 q of the row-major upper triangle -> (i, j)
+                int e = lane + 32 * q, i = 0;
+                if (e >= 78) e = 77;
+                while (e >= 12 - i) { e -= 12 - i; i++; }
+                ei[q] = i; ej[q] = i + e;
+            }
+            double acc[3] = {0, 0, 0};
+            for (int w = 0; w < s.n_words; w++) {
+                for (uint32_t b = s.mask[w]; b; b &= b - 1) {
+                    double M1[12], M2[12];
+                    m_rows(s, w * 32 + __ffs((int)b) - 1, M1, M2);
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        double x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+#pragma unroll
+                        for (int c = 0; c < 12; c++) {  // register selects instead of dynamic indexing
+                            if (c == ei[q]) { x1 = M1[c]; x2 = M2[c]; }
+                            if (c == ej[q]) { y1 = M1[c]; y2 = M2[c]; }
+                        }
+                        acc[q] += x1 * y1;
+                        acc[q] += x2 * y2;
+                    }
+                }
+            }
+            for (int e = 0, i = 0, j = 0; e < 78; e++) {
+                const double v = __shfl_sync(0xffffffffu, e < 32 ? acc[0] : e < 64 ? acc[1] : acc[2], e & 31);
+                A[i * 12 + j] = v;
+                A[j * 12 + i] = v;
+                if (++j == 12) { i++; j = i; }
+            }
+            jacobi_svd<12, 12, false>(A, ws.at(WS_W), A);
+            return;
+        }
+#endif
         for (int i = 0; i < 144; i++) A[i] = 0;
         PtIter it;
         int idx;
-        double pw[3], a[4], M1[12], M2[12];
+        double M1[12], M2[12];
         for (it_begin(it); it_next(s, it, idx);) {
-            load_pw(s, idx, pw);
-            alphas_of(pw, a);
-            const double u = (double)s.p2d[2 * idx], v = (double)s.p2d[2 * idx + 1];
-            for (int i = 0; i < 4; i++) {
-                M1[3 * i] = a[i] * fu; M1[3 * i + 1] = 0.0; M1[3 * i + 2] = a[i] * (uc - u);
-                M2[3 * i] = 0.0; M2[3 * i + 1] = a[i] * fv; M2[3 * i + 2] = a[i] * (vc - v);
-            }
+            m_rows(s, idx, M1, M2);
             for (int i = 0; i < 12; i++)
                 for (int j = i; j < 12; j++) {
                     double acc = A[i * 12 + j];
@@ -281,7 +368,7 @@ struct Epnp {
         }
         for (int i = 0; i < 12; i++)
             for (int j = i + 1; j < 12; j++) A[j * 12 + i] = A[i * 12 + j];
-        jacobi_svd(A, ws.at(WS_W), A, false, 12, 12);
+        jacobi_svd<12, 12, false>(A, ws.at(WS_W), A);
     }
 
     CORB_HD void compute_L_6x10(Ws ws, double* L) const {  // :787-829
@@ -322,43 +409,48 @@ struct Epnp {
     }
 
     // compute_R_and_t :676-687 = compute_ccs, compute_pcs, solve_for_sign, estimate_R_and_t, reprojection_error
+    template <bool WARP>
     CORB_HD double compute_R_and_t(const PtSet& s, const double* betas, Ws ws, double R[3][3], double t[3]) {
         const int n = s.n;
         compute_ccs(betas, ws);
-        PtIter it;
-        int idx;
-        double pw[3], a[4], pc[3];
         // solve_for_sign (:660-674): the sign of the first point's depth; negating ccs negates every pc exactly
-        it_begin(it);
-        if (it_next(s, it, idx)) {
-            load_pw(s, idx, pw);
-            alphas_of(pw, a);
-            pc_of(a, pc);
-            if (pc[2] < 0.0)
-                for (int i = 0; i < 4; i++)
-                    for (int j = 0; j < 3; j++) ccs[i][j] = -ccs[i][j];
+        {
+            PtIter it;
+            int idx;
+            it_begin(it);
+            if (it_next(s, it, idx)) {
+                double pw[3], a[4], pc[3];
+                load_pw(s, idx, pw);
+                alphas_of(pw, a);
+                pc_of(a, pc);
+                if (pc[2] < 0.0)
+                    for (int i = 0; i < 4; i++)
+                        for (int j = 0; j < 3; j++) ccs[i][j] = -ccs[i][j];
+            }
         }
         // estimate_R_and_t :587-651
-        double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
-        for (it_begin(it); it_next(s, it, idx);) {
-            load_pw(s, idx, pw);
-            alphas_of(pw, a);
-            pc_of(a, pc);
-            for (int j = 0; j < 3; j++) { pc0[j] += pc[j]; pw0[j] += pw[j]; }
-        }
-        for (int j = 0; j < 3; j++) { pc0[j] /= n; pw0[j] /= n; }
+        double c6[6] = {0, 0, 0, 0, 0, 0};  // pc0 | pw0
+        ordered_sum<WARP, 6>(s, c6, [&](int idx, double* tt) {
+            double a[4];
+            load_pw(s, idx, tt + 3);
+            alphas_of(tt + 3, a);
+            pc_of(a, tt);
+        });
+        double pc0[3], pw0[3];
+        for (int j = 0; j < 3; j++) { pc0[j] = c6[j] / n; pw0[j] = c6[3 + j] / n; }
         double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (it_begin(it); it_next(s, it, idx);) {
+        ordered_sum<WARP, 9>(s, abt, [&](int idx, double* tt) {
+            double pw[3], a[4], pc[3];
             load_pw(s, idx, pw);
             alphas_of(pw, a);
             pc_of(a, pc);
             for (int j = 0; j < 3; j++) {
-                abt[3 * j] += (pc[j] - pc0[j]) * (pw[0] - pw0[0]);
-                abt[3 * j + 1] += (pc[j] - pc0[j]) * (pw[1] - pw0[1]);
-                abt[3 * j + 2] += (pc[j] - pc0[j]) * (pw[2] - pw0[2]);
+                tt[3 * j] = (pc[j] - pc0[j]) * (pw[0] - pw0[0]);
+                tt[3 * j + 1] = (pc[j] - pc0[j]) * (pw[1] - pw0[1]);
+                tt[3 * j + 2] = (pc[j] - pc0[j]) * (pw[2] - pw0[2]);
             }
-        }
-        svd_small(abt, 3, 3, true, ws);
+        });
+        svd_small<3, 3, true>(abt, ws);
         const Ws Ut = ws.at(WS_S), Vt = ws.at(WS_SV);
         for (int i = 0; i < 3; i++)
             for (int j = 0; j < 3; j++) R[i][j] = Ut[i] * Vt[j] + Ut[3 + i] * Vt[3 + j] + Ut[6 + i] * Vt[6 + j];
@@ -370,7 +462,8 @@ struct Epnp {
         t[2] = pc0[2] - dot3(R[2], pw0);
         // reprojection_error :568-585
         double sum2 = 0.0;
-        for (it_begin(it); it_next(s, it, idx);) {
+        ordered_sum<WARP, 1>(s, &sum2, [&](int idx, double* tt) {
+            double pw[3];
             load_pw(s, idx, pw);
             const double Xc = dot3(R[0], pw) + t[0];
             const double Yc = dot3(R[1], pw) + t[1];
@@ -378,16 +471,17 @@ struct Epnp {
             const double ue = uc + fu * Xc * inv_Zc;
             const double ve = vc + fv * Yc * inv_Zc;
             const double u = (double)s.p2d[2 * idx], v = (double)s.p2d[2 * idx + 1];
-            sum2 += sqrt((u - ue) * (u - ue) + (v - ve) * (v - ve));
-        }
+            tt[0] = sqrt((u - ue) * (u - ue) + (v - ve) * (v - ve));
+        });
         return sum2 / n;
     }
 
-    CORB_HD static void find_betas(int which, const double* L, const double* rho, double* betas, Ws ws) {  // :692-785
+    template <int which>
+    CORB_HD static void find_betas(const double* L, const double* rho, double* betas, Ws ws) {  // :692-785
         double l[30], b[5];
         if (which == 1) {
             for (int i = 0; i < 6; i++) { l[4 * i] = L[10 * i]; l[4 * i + 1] = L[10 * i + 1]; l[4 * i + 2] = L[10 * i + 3]; l[4 * i + 3] = L[10 * i + 6]; }
-            svd_solve(l, 6, 4, rho, b, ws);
+            svd_solve<6, 4>(l, rho, b, ws);
             if (b[0] < 0) {
                 betas[0] = sqrt(-b[0]); betas[1] = -b[1] / betas[0]; betas[2] = -b[2] / betas[0]; betas[3] = -b[3] / betas[0];
             } else {
@@ -395,10 +489,10 @@ struct Epnp {
             }
             return;
         }
-        const int nc = which == 2 ? 3 : 5;
+        constexpr int nc = which == 2 ? 3 : 5;
         for (int i = 0; i < 6; i++)
             for (int k = 0; k < nc; k++) l[nc * i + k] = L[10 * i + k];
-        svd_solve(l, 6, nc, rho, b, ws);
+        svd_solve<6, nc>(l, rho, b, ws);
         if (b[0] < 0) {
             betas[0] = sqrt(-b[0]);
             betas[1] = (b[2] < 0) ? sqrt(-b[2]) : 0.0;
@@ -475,30 +569,37 @@ struct Epnp {
         }
     }
 
+    // one of the three beta approximations of compute_pose (:545-557) and the selection N = 1; if (e2 < e1) N = 2;
+    // if (e3 < e[N]) N = 3 (:559-561): strict improvements only (NaN never wins)
+    template <bool WARP, int which>
+    CORB_HD void branch(const PtSet& s, Ws ws, const double* L, const double* rho, double& best_err, double* Rt) {
+        double betas[4], R[3][3], t[3];
+        find_betas<which>(L, rho, betas, ws);
+        gauss_newton(L, rho, betas);
+        const double err = compute_R_and_t<WARP>(s, betas, ws, R, t);
+        if (which == 1 || err < best_err) {
+            best_err = err;
+            for (int i = 0; i < 3; i++) {
+                for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[i][j];
+                Rt[9 + i] = t[i];
+            }
+        }
+    }
+
     // compute_pose :527-574. Rt = R (row-major 9) followed by t (3).
+    template <bool WARP = false>
     CORB_HD double compute_pose(const PtSet& s, Ws ws, double* Rt) {
-        choose_control_points(s, ws);
+        choose_control_points<WARP>(s, ws);
         compute_barycentric(ws);
-        mtm_svd(s, ws);
+        mtm_svd<WARP>(s, ws);
         double L[60], rho[6];
         compute_L_6x10(ws, L);
         rho[0] = dist2(cws[0], cws[1]); rho[1] = dist2(cws[0], cws[2]); rho[2] = dist2(cws[0], cws[3]);  // compute_rho :831-839
         rho[3] = dist2(cws[1], cws[2]); rho[4] = dist2(cws[1], cws[3]); rho[5] = dist2(cws[2], cws[3]);
         double best_err = 0;
-        for (int which = 1; which <= 3; which++) {
-            double betas[4], R[3][3], t[3];
-            find_betas(which, L, rho, betas, ws);
-            gauss_newton(L, rho, betas);
-            const double err = compute_R_and_t(s, betas, ws, R, t);
-            // N = 1; if (e2 < e1) N = 2; if (e3 < e[N]) N = 3  (:563-566): strict improvements only (NaN never wins)
-            if (which == 1 || err < best_err) {
-                best_err = err;
-                for (int i = 0; i < 3; i++) {
-                    for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[i][j];
-                    Rt[9 + i] = t[i];
-                }
-            }
-        }
+        branch<WARP, 1>(s, ws, L, rho, best_err, Rt);
+        branch<WARP, 2>(s, ws, L, rho, best_err, Rt);
+        branch<WARP, 3>(s, ws, L, rho, best_err, Rt);
         return best_err;
     }
 };
