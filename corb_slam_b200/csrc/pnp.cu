@@ -12,6 +12,7 @@
 //
 // Compiled with -fmad=false (csrc/Makefile): double arithmetic is then the same sequence of correctly rounded
 // operations as the oracle's, and the parity tests compare poses bit for bit.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -63,18 +64,23 @@ struct PnpDev {
 };
 
 constexpr int kSolveThreads = 32;
-constexpr size_t kSolveSmem = (size_t)WS_DOUBLES * kSolveThreads * sizeof(double);
+constexpr size_t kSolveSmem = (size_t)WS_DOUBLES * kSolveThreads * sizeof(double);  // one workspace per lane
+template <int TEAM>
+constexpr size_t solve_smem() { return kSolveSmem + (TEAM > 1 ? (kSolveThreads / TEAM) * COOP_DOUBLES * sizeof(double) : 0); }
 
-// MODE 0: thread = RANSAC iteration (minimal set of 4 from the draws, :228-246). MODE 1: warp = best-so-far record
-// (EPnP over the record's inlier mask = Refine(), :302-324).
-template <int MODE>
+// MODE 0: RANSAC iterations (minimal set of 4 from the draws, :228-246). MODE 1: best-so-far records (EPnP over the
+// record's inlier mask = Refine(), :302-324). TEAM = lanes per item: 1 = one thread per item (large batches: throughput),
+// 8 / 32 = a team per item (small batches: latency) - the team replicates the scalar work on per-lane workspaces, runs the
+// 12 x 12 Jacobi sweeps as a wavefront on a shared copy and, in MODE 1, splits the ordered sums over the inliers.
+template <int MODE, int TEAM>
 __global__ void __launch_bounds__(kSolveThreads) k_pnp_solve(PnpDev D) {
     extern __shared__ double smem[];
     const PnpProb P = D.probs[blockIdx.y];
-    // MODE 1: the whole warp works on one record (ordered sums over the inliers split across lanes, everything else
-    // replicated per lane on the lane's own workspace)
-    const int item = MODE == 0 ? blockIdx.x * kSolveThreads + threadIdx.x : blockIdx.x;
-    if (MODE == 0 ? item >= P.it_end : item >= D.n_rec[blockIdx.y]) return;
+    const int n_items = MODE == 0 ? P.it_end : D.n_rec[blockIdx.y];
+    int item = (blockIdx.x * kSolveThreads + threadIdx.x) / TEAM;
+    if (TEAM == 1 ? item >= n_items : (int)(blockIdx.x * kSolveThreads) / TEAM >= n_items) return;  // warp-uniform for teams
+    const bool valid = item < n_items;
+    if (!valid) item = n_items - 1;  // a team without an item repeats the last one (its lanes take part in the barriers)
     PtSet s;
     s.p3d = D.p3d + 3 * (size_t)P.pt_off;
     s.p2d = D.p2d + 2 * (size_t)P.pt_off;
@@ -112,9 +118,13 @@ __global__ void __launch_bounds__(kSolveThreads) k_pnp_solve(PnpDev D) {
     }
     Epnp e;
     e.fu = (double)P.fx; e.fv = (double)P.fy; e.uc = (double)P.cx; e.vc = (double)P.cy;
+    if (TEAM > 1) {
+        double* area = smem + (size_t)WS_DOUBLES * kSolveThreads + (size_t)(threadIdx.x / TEAM) * COOP_DOUBLES;
+        e.coop = Coop{area, area + 12 * COOP_ROW, (int*)(area + 12 * COOP_ROW + 12), (int)threadIdx.x % TEAM, TEAM};
+    }
     double Rt[12];
-    e.template compute_pose<MODE == 1>(s, Ws{smem + threadIdx.x, kSolveThreads}, Rt);
-    if (MODE == 0 || threadIdx.x == 0) {
+    e.template compute_pose<(MODE == 1 && TEAM == 32)>(s, Ws{smem + threadIdx.x, kSolveThreads}, Rt);
+    if (valid && threadIdx.x % TEAM == 0) {
 #pragma unroll
         for (int i = 0; i < 12; i++) out[i] = Rt[i];
     }
@@ -339,15 +349,23 @@ int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_probl
     static bool attr_set[64] = {};
     const int dev = matcher_device(m);
     if (dev < 64 && !attr_set[dev]) {
-        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem));
-        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveSmem));
+        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<1>()));
+        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<8>()));
+        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<32>()));
         attr_set[dev] = true;
     }
-    const dim3 gs((max_it + kSolveThreads - 1) / kSolveThreads, C), gc((max_it + kCheckWarps - 1) / kCheckWarps, C);
-    k_pnp_solve<0><<<gs, kSolveThreads, kSolveSmem, st>>>(D);
+    // Hypotheses: a team of 8 lanes each while the batch leaves the GPU mostly idle (the call is then bound by the latency
+    // of ONE hypothesis, which the team shortens); one thread each for large batches. CORB_PNP_TEAM=0/1 forces either.
+    const char* env = getenv("CORB_PNP_TEAM");
+    const bool team = env ? atoi(env) != 0 : n_hyp <= 8192;
+    const dim3 gc((max_it + kCheckWarps - 1) / kCheckWarps, C);
+    if (team)
+        k_pnp_solve<0, 8><<<dim3((max_it + 3) / 4, C), kSolveThreads, solve_smem<8>(), st>>>(D);
+    else
+        k_pnp_solve<0, 1><<<dim3((max_it + kSolveThreads - 1) / kSolveThreads, C), kSolveThreads, solve_smem<1>(), st>>>(D);
     k_pnp_check<0><<<gc, kCheckWarps * 32, 0, st>>>(D);
     k_pnp_records<<<C, 32, 0, st>>>(D);
-    k_pnp_solve<1><<<dim3(max_it, C), kSolveThreads, kSolveSmem, st>>>(D);  // blocks beyond a problem's record count exit
+    k_pnp_solve<1, 32><<<dim3(max_it, C), kSolveThreads, solve_smem<32>(), st>>>(D);  // blocks beyond a problem's record count exit
     k_pnp_check<1><<<gc, kCheckWarps * 32, 0, st>>>(D);
     k_pnp_finalize<<<C, 32, 0, st>>>(D);
     CORB_CUDA(cudaGetLastError());

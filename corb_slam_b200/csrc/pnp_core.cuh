@@ -86,7 +86,7 @@ CORB_HD inline void load_pw(const PtSet& s, int idx, double pw[3]) {  // add_cor
 template <bool WARP, int NA, class F>
 CORB_HD inline void ordered_sum(const PtSet& s, double* acc, F&& term) {
 #ifdef __CUDA_ARCH__
-    if (WARP) {
+    if (WARP && s.mask) {
         const int lane = threadIdx.x & 31;
         for (int w = 0; w < s.n_words; w++) {
             const uint32_t bits = s.mask[w];
@@ -197,6 +197,105 @@ CORB_HD inline void jacobi_svd(Ws At, Ws W, Ws Vt) {
     }
 }
 
+// Team-cooperative form of jacobi_svd<12, 12, false> (device only). The pair visits of a sweep, (0,1), (0,2), ... (10,11),
+// touch only rows i and j and W[i], W[j]; visits on disjoint rows do not interact at all, so any schedule that keeps the
+// lexicographic order between visits that SHARE a row produces the sequential result bit for bit. Visit (i, j) runs at
+// step i + j: two visits of one step have different i and different j (and i = j' would need j < i), so they are
+// disjoint, and for visits sharing a row the step order equals the lexicographic order. 21 steps of up to 6 concurrent
+// visits replace 66 sequential ones. S is the team's matrix in shared memory (row stride 13: the rows six lanes touch in
+// one step fall into different banks), SW its 12 squared norms / singular values, perm 12 ints. All lanes of the WARP
+// must call (full-mask barriers); `tl` is the lane's index inside its team of `team` lanes (8 or 32), teams converge
+// independently. On return rows 8..11 of S are the left singular vectors of the four smallest singular values (all
+// EPnP uses, compute_L_6x10 / compute_ccs), the other rows are left unnormalised.
+struct Coop {
+    double* S;   // nullptr: single-thread Jacobi
+    double* SW;
+    int* perm;
+    int tl, team;
+};
+constexpr int COOP_ROW = 13;
+constexpr int COOP_DOUBLES = 12 * COOP_ROW + 12 + 6;  // S | SW | perm (12 ints)
+
+#ifdef __CUDACC__
+__device__ inline void jacobi12_wavefront(const Coop& co) {
+    const double eps = DBL_EPSILON * 10;
+    double* S = co.S;
+    double* W = co.SW;
+    const int tl = co.tl;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned team_mask = co.team == 32 ? 0xffffffffu : (((1u << co.team) - 1u) << (lane & ~(unsigned)(co.team - 1)));
+    for (int r = tl; r < 12; r += co.team) {
+        double sd = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { const double t = S[r * COOP_ROW + k]; sd += t * t; }
+        W[r] = sd;
+    }
+    __syncwarp();
+    bool done = false;
+    for (int iter = 0; iter < 30; iter++) {  // max_iter = max(m, 30)
+        bool changed = false;
+        for (int t = 1; t <= 21; t++) {
+            const int i = (t > 11 ? t - 11 : 0) + tl, j = t - i;
+            if (!done && i < j) {
+                double* Ai = S + i * COOP_ROW;
+                double* Aj = S + j * COOP_ROW;
+                double a = W[i], p = 0, b = W[j];
+#pragma unroll
+                for (int k = 0; k < 12; k++) p += Ai[k] * Aj[k];
+                if (!(fabs(p) <= eps * sqrt(a * b))) {
+                    p *= 2;
+                    const double beta = a - b, gamma = sqrt(p * p + beta * beta);
+                    double c, sn;
+                    if (beta < 0) {
+                        const double delta = (gamma - beta) * 0.5;
+                        sn = sqrt(delta / gamma);
+                        c = p / (gamma * sn * 2);
+                    } else {
+                        c = sqrt((gamma + beta) / (gamma * 2));
+                        sn = p / (gamma * c * 2);
+                    }
+                    a = b = 0;
+#pragma unroll
+                    for (int k = 0; k < 12; k++) {
+                        const double x = Ai[k], y = Aj[k];
+                        const double t0 = c * x + sn * y;
+                        const double t1 = -sn * x + c * y;
+                        Ai[k] = t0; Aj[k] = t1;
+                        a += t0 * t0; b += t1 * t1;
+                    }
+                    W[i] = a; W[j] = b;
+                    changed = true;
+                }
+            }
+            __syncwarp();
+        }
+        if (!(__ballot_sync(0xffffffffu, changed) & team_mask)) done = true;  // if (!changed) break;
+        if (__all_sync(0xffffffffu, done)) break;
+    }
+    for (int r = tl; r < 12; r += co.team) {
+        double sd = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { const double t = S[r * COOP_ROW + k]; sd += t * t; }
+        W[r] = sqrt(sd);
+    }
+    __syncwarp();
+    if (tl == 0) {  // the descending selection sort (first maximum wins, swap), on a permutation instead of on the rows
+        int* perm = co.perm;
+        for (int i = 0; i < 12; i++) perm[i] = i;
+        for (int i = 0; i < 11; i++) {
+            int j = i;
+            for (int k = i + 1; k < 12; k++)
+                if (W[j] < W[k]) j = k;
+            if (i != j) {
+                const double tw = W[i]; W[i] = W[j]; W[j] = tw;
+                const int tp = perm[i]; perm[i] = perm[j]; perm[j] = tp;
+            }
+        }
+    }
+    __syncwarp();
+}
+#endif
+
 // SVD of a small row-major m x n matrix held in registers / local memory, through the S area of the workspace.
 template <int m, int n, bool with_v>
 CORB_HD inline void svd_small(const double* A, Ws ws) {
@@ -255,6 +354,31 @@ CORB_HD inline double dist2(const double* p1, const double* p2) {
 struct Epnp {
     double fu, fv, uc, vc;
     double cws[4][3], ccs[4][3], ci[9];
+    Coop coop = {nullptr, nullptr, nullptr, 0, 32};
+
+    // SVD of the symmetric 12 x 12 in ws[WS_A..]: afterwards rows 8..11 hold the left singular vectors EPnP uses. With a
+    // team (coop.S != nullptr; every lane of the team holds the same matrix in its own workspace) the sweeps run as a
+    // wavefront on the team's shared copy and each lane takes rows 8..11 back, scaled by 1 / w like JacobiSVDImpl_ does.
+    CORB_HD void svd12(Ws ws) {
+        const Ws A = ws.at(WS_A);
+#ifdef __CUDA_ARCH__
+        if (coop.S) {
+            for (int r = coop.tl; r < 12; r += coop.team)
+                for (int k = 0; k < 12; k++) coop.S[r * COOP_ROW + k] = A[r * 12 + k];
+            __syncwarp();
+            jacobi12_wavefront(coop);
+            for (int r = 8; r < 12; r++) {
+                const double sd = coop.SW[r];
+                const double sc = sd > DBL_MIN ? 1 / sd : 0.;
+                const double* row = coop.S + coop.perm[r] * COOP_ROW;
+                for (int k = 0; k < 12; k++) A[r * 12 + k] = row[k] * sc;
+            }
+            __syncwarp();
+            return;
+        }
+#endif
+        jacobi_svd<12, 12, false>(A, ws.at(WS_W), A);
+    }
 
     CORB_HD void alphas_of(const double pw[3], double a[4]) const {  // compute_barycentric_coordinates :471-481
         for (int j = 0; j < 3; j++)
@@ -314,7 +438,7 @@ struct Epnp {
     CORB_HD void mtm_svd(const PtSet& s, Ws ws) {
         const Ws A = ws.at(WS_A);
 #ifdef __CUDA_ARCH__
-        if (WARP) {
+        if (WARP && s.mask) {
             const int lane = threadIdx.x & 31;
             int ei[3], ej[3];
 #pragma unroll
@@ -348,7 +472,7 @@ struct Epnp {
                 A[j * 12 + i] = v;
                 if (++j == 12) { i++; j = i; }
             }
-            jacobi_svd<12, 12, false>(A, ws.at(WS_W), A);
+            svd12(ws);
             return;
         }
 #endif
@@ -368,7 +492,7 @@ struct Epnp {
         }
         for (int i = 0; i < 12; i++)
             for (int j = i + 1; j < 12; j++) A[j * 12 + i] = A[i * 12 + j];
-        jacobi_svd<12, 12, false>(A, ws.at(WS_W), A);
+        svd12(ws);
     }
 
     CORB_HD void compute_L_6x10(Ws ws, double* L) const {  // :787-829

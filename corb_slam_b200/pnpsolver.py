@@ -107,17 +107,28 @@ class PnPsolver:
         return Tcw, bool(r.no_more), vbInliers, int(r.n_inliers)
 
     @staticmethod
-    def iterate_batch(solvers, nIterations):
-        """iterate(nIterations, ...) of every solver, one GPU call. Returns a list of (Tcw | None, bNoMore, vbInliers, nInliers)."""
-        if not solvers:
-            return []
+    def pack_batch(solvers, nIterations):
+        """The C arguments of one corb_pnp_iterate_batch call (what the C++ shim's Fill() builds)."""
         n = len(solvers)
         probs = (PnpProblem * n)(*[s._problem(nIterations) for s in solvers])
         res = (PnpResult * n)()
         bufs = [np.zeros(max(s.N, 1), np.uint8) for s in solvers]
         ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
-        check(lib().corb_pnp_iterate_batch(_matcher(solvers[0].device), n, probs, res, ptrs))
-        return [s._unpack(res[i], bufs[i]) for i, s in enumerate(solvers)]
+        return n, probs, res, ptrs, bufs
+
+    @staticmethod
+    def call_batch(device, packed):
+        n, probs, res, ptrs, _ = packed
+        check(lib().corb_pnp_iterate_batch(_matcher(device), n, probs, res, ptrs))
+
+    @staticmethod
+    def iterate_batch(solvers, nIterations):
+        """iterate(nIterations, ...) of every solver, one GPU call. Returns a list of (Tcw | None, bNoMore, vbInliers, nInliers)."""
+        if not solvers:
+            return []
+        packed = PnPsolver.pack_batch(solvers, nIterations)
+        PnPsolver.call_batch(solvers[0].device, packed)
+        return [s._unpack(packed[2][i], packed[4][i]) for i, s in enumerate(solvers)]
 
     def iterate(self, nIterations):
         """cv::Mat iterate(int nIterations, bool &bNoMore, vector<bool> &vbInliers, int &nInliers) (:206-300)."""

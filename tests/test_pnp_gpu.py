@@ -38,7 +38,10 @@ def _same(res, ores, g, o, tag):
         assert Tcw.tobytes() == oT.tobytes(), (tag, np.abs(Tcw - oT).max())
 
 
-def test_batch_equals_sequential_oracle():
+@pytest.mark.parametrize("team", ["1", "0"])
+def test_batch_equals_sequential_oracle(monkeypatch, team):
+    """team=1: a team of 8 lanes per hypothesis (wavefront Jacobi); team=0: one thread per hypothesis. Same bits either way."""
+    monkeypatch.setenv("CORB_PNP_TEAM", team)
     oracle.lib()
     rng = np.random.default_rng(0)
     gs, os_, ds = [], [], []
