@@ -357,7 +357,7 @@ int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_probl
     // Hypotheses: a team of 8 lanes each while the batch leaves the GPU mostly idle (the call is then bound by the latency
     // of ONE hypothesis, which the team shortens); one thread each for large batches. CORB_PNP_TEAM=0/1 forces either.
     const char* env = getenv("CORB_PNP_TEAM");
-    const bool team = env ? atoi(env) != 0 : n_hyp <= 8192;
+    const bool team = env ? atoi(env) != 0 : n_hyp <= 2400;  // 4 teams per 55 KB block, 4 blocks per SM: one wave on 148 SMs
     const dim3 gc((max_it + kCheckWarps - 1) / kCheckWarps, C);
     if (team)
         k_pnp_solve<0, 8><<<dim3((max_it + 3) / 4, C), kSolveThreads, solve_smem<8>(), st>>>(D);
