@@ -58,6 +58,12 @@ def test_no_cpu_fallback_without_a_gpu():
     with pytest.raises(CorbError):
         Optimizer.BundleAdjustment(ba_problem(5, 50, seed=0), 1, bRobust=False)
     assert b"CUDA" in _lib.lib().corb_last_error() or b"cuda" in _lib.lib().corb_last_error()
+    from corb_slam_b200 import PnPsolver
+    from corb_slam_b200.synth import pnp_problem
+    p = pnp_problem(0, n=40)
+    s = PnPsolver(p["p2d"], np.zeros(40, int), [1.0], p["K"], p["p3d"], np.ones(40, bool))
+    with pytest.raises(CorbError):
+        s.iterate(5)
 
 
 def test_argument_validation_without_a_gpu():
