@@ -508,7 +508,7 @@ def run_ours(args):
 
     # ---- global BA (second half of the BASELINE.json metric): landmark-sharded over the ranks, reduced camera system
     #      all-reduced over NCCL from inside corb_ba_solve when more than one GPU is attached
-    ba_info, ba_ms, ba_rms, ba_edges = None, 0.0, None, 0
+    ba_info, ba_ms, ba_rms, ba_edges, ba_allreduce = None, 0.0, None, 0, None
     if not args.no_ba:
         from corb_slam_b200 import Optimizer, torch_allreduce
         from corb_slam_b200.synth import ba_problem, ba_shard
@@ -532,6 +532,23 @@ def run_ours(args):
             from oracle import _ba_bind as B
             oracle.lib()
             ba_rms = B.chi2(ba_out)[1]  # checker only: RMS reprojection error of the GPU solution
+        if world > 1:
+            # the one exchange step of the sharded BA on its own: all-reduce(sum, fp64) of [S | bschur] (36 doubles per block of
+            # the reduced camera system + 6 per pose), timed with CUDA events, against the NVLink roofline
+            n_red = 36 * int(ba_info["reduced_blocks"]) + 6 * BA_P
+            buf = torch.zeros(n_red, dtype=torch.float64, device="cuda")
+            for _ in range(3):
+                dist.all_reduce(buf)
+            torch.cuda.synchronize(); barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(20):
+                dist.all_reduce(buf)
+            ev1.record(); torch.cuda.synchronize()
+            ar_ms = ev0.elapsed_time(ev1) / 20
+            tt = torch.tensor([ar_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ba_allreduce = {"message_bytes": 8 * n_red, "ms": float(tt.item())}
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_pyr_s * 1e3, ba_ms, e2e_frame_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -613,6 +630,14 @@ def run_ours(args):
                                      "(chunked block-skyline Cholesky) is bound by the serial latency of a block column"},
                 "cpu_baseline": cpu_ba(BA_P, BA_L) if not args.no_cpu_ba else None,
             }
+            if ba_allreduce is not None:
+                S, ms = ba_allreduce["message_bytes"], ba_allreduce["ms"]
+                bus = 2.0 * (world - 1) / world * S / (ms * 1e-3) / 1e9  # bytes every GPU sends + receives per second
+                line["ba"]["allreduce"] = {
+                    "bound": "nvlink", "message_bytes": S, "ms": ms, "per_call_ms_total": ms * ba_info["n_trials"],
+                    "achieved": bus, "peak": 900.0, "unit": "GB/s", "frac": bus / 900.0,
+                    "note": "NCCL all-reduce(sum, fp64) of the reduced camera system [S | bschur], one per LM trial; bus bandwidth "
+                            "2(n-1)/n * S / t against 900 GB/s per direction (NVLink 5); a %.1f MB message is latency bound" % (S / 1e6)}
         print(json.dumps(line))
     exl.close(); exr.close()
     if world > 1:
