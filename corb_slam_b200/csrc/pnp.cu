@@ -63,22 +63,35 @@ struct PnpDev {
     uint8_t* res_inl;
 };
 
-constexpr int kSolveThreads = 32;
-constexpr size_t kSolveSmem = (size_t)WS_DOUBLES * kSolveThreads * sizeof(double);  // one workspace per lane
-template <int TEAM>
-constexpr size_t solve_smem() { return kSolveSmem + (TEAM > 1 ? (kSolveThreads / TEAM) * COOP_DOUBLES * sizeof(double) : 0); }
+constexpr int kSolveThreads = 32;  // lanes per warp of a solve block; a block has NB warps
+constexpr int kTeamWs = WS_DOUBLES + 1;  // workspace stride of a lead-only team (odd: the four leads of a warp hit different banks)
+
+// Shared memory of one warp of a solve block: its workspaces, then the shared Jacobi areas of its teams.
+template <int MODE, int TEAM>
+__host__ __device__ constexpr size_t warp_doubles() {
+    return (MODE == 0 && TEAM > 1 ? (size_t)(kSolveThreads / TEAM) * kTeamWs : (size_t)WS_DOUBLES * kSolveThreads) +
+           (TEAM > 1 ? (size_t)(kSolveThreads / TEAM) * COOP_DOUBLES : 0);
+}
+template <int MODE, int TEAM, int NB>
+constexpr size_t solve_smem() { return (NB * warp_doubles<MODE, TEAM>() + (NB > 1 ? (kSolveThreads / TEAM) * 3 * 13 : 0)) * sizeof(double); }
 
 // MODE 0: RANSAC iterations (minimal set of 4 from the draws, :228-246). MODE 1: best-so-far records (EPnP over the
-// record's inlier mask = Refine(), :302-324). TEAM = lanes per item: 1 = one thread per item (large batches: throughput),
-// 8 / 32 = a team per item (small batches: latency) - the team replicates the scalar work on per-lane workspaces, runs the
-// 12 x 12 Jacobi sweeps as a wavefront on a shared copy and, in MODE 1, splits the ordered sums over the inliers.
-template <int MODE, int TEAM>
-__global__ void __launch_bounds__(kSolveThreads) k_pnp_solve(PnpDev D) {
+// record's inlier mask = Refine(), :302-324).
+// TEAM = lanes per item. 1: one thread per item (large batches: throughput). 8 / 32: a team per item (small batches:
+// latency) that runs the 12 x 12 Jacobi sweeps as a wavefront on a shared copy; in MODE 0 the scalar phases run on the
+// team's lane 0 (one workspace per team), in MODE 1 every lane replicates them on its own workspace and the ordered sums
+// over the inliers are split across the lanes.
+// NB = warps per block. 3: warp w evaluates only beta approximation w + 1 of its items (everything before it is
+// repeated by the three warps side by side) and warp 0 applies compute_pose's selection rule to the three results.
+template <int MODE, int TEAM, int NB>
+__global__ void __launch_bounds__(kSolveThreads * NB) k_pnp_solve(PnpDev D) {
     extern __shared__ double smem[];
+    constexpr int kItems = kSolveThreads / TEAM;  // items per block
     const PnpProb P = D.probs[blockIdx.y];
     const int n_items = MODE == 0 ? P.it_end : D.n_rec[blockIdx.y];
-    int item = (blockIdx.x * kSolveThreads + threadIdx.x) / TEAM;
-    if (TEAM == 1 ? item >= n_items : (int)(blockIdx.x * kSolveThreads) / TEAM >= n_items) return;  // warp-uniform for teams
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int item = blockIdx.x * kItems + lane / TEAM;
+    if (TEAM == 1 ? item >= n_items : (int)blockIdx.x * kItems >= n_items) return;  // block-uniform for teams
     const bool valid = item < n_items;
     if (!valid) item = n_items - 1;  // a team without an item repeats the last one (its lanes take part in the barriers)
     PtSet s;
@@ -118,15 +131,38 @@ __global__ void __launch_bounds__(kSolveThreads) k_pnp_solve(PnpDev D) {
     }
     Epnp e;
     e.fu = (double)P.fx; e.fv = (double)P.fy; e.uc = (double)P.cx; e.vc = (double)P.cy;
+    constexpr size_t kWarpDoubles = warp_doubles<MODE, TEAM>();
+    double* wbase = smem + (size_t)warp * kWarpDoubles;
+    constexpr bool kLeadOnly = MODE == 0 && TEAM > 1;
+    Ws ws = kLeadOnly ? Ws{wbase + (size_t)(lane / TEAM) * kTeamWs, 1} : Ws{wbase + lane, kSolveThreads};
     if (TEAM > 1) {
-        double* area = smem + (size_t)WS_DOUBLES * kSolveThreads + (size_t)(threadIdx.x / TEAM) * COOP_DOUBLES;
-        e.coop = Coop{area, area + 12 * COOP_ROW, (int*)(area + 12 * COOP_ROW + 12), (int)threadIdx.x % TEAM, TEAM};
+        double* area = wbase + (kLeadOnly ? (size_t)kItems * kTeamWs : (size_t)WS_DOUBLES * kSolveThreads) + (size_t)(lane / TEAM) * COOP_DOUBLES;
+        e.coop = Coop{area, area + 12 * COOP_ROW, (int*)(area + 12 * COOP_ROW + 12), lane % TEAM, TEAM, kLeadOnly};
     }
     double Rt[12];
-    e.template compute_pose<(MODE == 1 && TEAM == 32)>(s, Ws{smem + threadIdx.x, kSolveThreads}, Rt);
-    if (valid && threadIdx.x % TEAM == 0) {
+    const double err = e.template compute_pose_part<(MODE == 1 && TEAM == 32)>(s, ws, NB == 3 ? warp + 1 : 0, Rt);
+    const bool lead = lane % TEAM == 0;
+    if (NB == 1) {
+        if (valid && lead) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) out[i] = Rt[i];
+            for (int i = 0; i < 12; i++) out[i] = Rt[i];
+        }
+        return;
+    }
+    // three warps, one beta approximation each: N = 1; if (e2 < e1) N = 2; if (e3 < e[N]) N = 3  (:559-561)
+    double* sel = smem + (size_t)NB * kWarpDoubles + (size_t)(lane / TEAM) * 3 * 13;
+    if (lead) {
+        sel[warp * 13] = err;
+#pragma unroll
+        for (int i = 0; i < 12; i++) sel[warp * 13 + 1 + i] = Rt[i];
+    }
+    __syncthreads();
+    if (warp == 0 && lead && valid) {
+        int N = 0;
+        if (sel[13] < sel[0]) N = 1;
+        if (sel[26] < sel[N * 13]) N = 2;
+#pragma unroll
+        for (int i = 0; i < 12; i++) out[i] = sel[N * 13 + 1 + i];
     }
 }
 
@@ -279,7 +315,7 @@ int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_probl
     // ---- the problems that reach the loop (N >= mRansacMinInliers, :215-219); the others only set bNoMore
     std::vector<int> live;
     size_t n_pts = 0, n_hyp = 0, n_mask = 0;
-    int max_it = 0;
+    int max_it = 0, max_rec = 0;  // records are strict maxima of counts in [min_inliers, n]: at most n - min_inliers + 1
     for (int c = 0; c < n_problems; c++) {
         const corb_pnp_problem& p = problems[c];
         CORB_CHECK(p.n >= 0 && p.n < (1 << 24) && p.min_inliers >= 4 && p.max_its >= 1 && p.iterations_done >= 0 && p.n_iterations >= 0,
@@ -304,6 +340,7 @@ int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_probl
         n_hyp += it_end;
         n_mask += (size_t)it_end * ((p.n + 31) / 32);
         max_it = std::max(max_it, it_end);
+        max_rec = std::max(max_rec, std::min(it_end, p.n - p.min_inliers + 1));
     }
     const int C = (int)live.size();
     if (C == 0) return CORB_OK;
@@ -349,24 +386,29 @@ int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_probl
     static bool attr_set[64] = {};
     const int dev = matcher_device(m);
     if (dev < 64 && !attr_set[dev]) {
-        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<1>()));
-        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<8>()));
-        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<32>()));
+        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<0, 1, 1>()));
+        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<0, 8, 3>()));
+        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<1, 32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<1, 32, 1>()));
+        CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<1, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<1, 32, 3>()));
         attr_set[dev] = true;
     }
-    // Hypotheses: a team of 8 lanes each while the batch leaves the GPU mostly idle (the call is then bound by the latency
-    // of ONE hypothesis, which the team shortens); one thread each for large batches. CORB_PNP_TEAM=0/1 forces either.
+    // Small batches leave the GPU mostly idle and the call is bound by the latency of ONE hypothesis: a team of 8 lanes per
+    // hypothesis and three warps per item (one beta approximation each) shorten it. Large batches keep one thread per
+    // hypothesis and one warp per record. CORB_PNP_TEAM=0/1 forces either.
     const char* env = getenv("CORB_PNP_TEAM");
-    const bool team = env ? atoi(env) != 0 : n_hyp <= 2400;  // 4 teams per 55 KB block, 4 blocks per SM: one wave on 148 SMs
+    const bool team = env ? atoi(env) != 0 : n_hyp <= 2400;
     const dim3 gc((max_it + kCheckWarps - 1) / kCheckWarps, C);
     if (team)
-        k_pnp_solve<0, 8><<<dim3((max_it + 3) / 4, C), kSolveThreads, solve_smem<8>(), st>>>(D);
+        k_pnp_solve<0, 8, 3><<<dim3((max_it + 3) / 4, C), 3 * kSolveThreads, solve_smem<0, 8, 3>(), st>>>(D);
     else
-        k_pnp_solve<0, 1><<<dim3((max_it + kSolveThreads - 1) / kSolveThreads, C), kSolveThreads, solve_smem<1>(), st>>>(D);
+        k_pnp_solve<0, 1, 1><<<dim3((max_it + kSolveThreads - 1) / kSolveThreads, C), kSolveThreads, solve_smem<0, 1, 1>(), st>>>(D);
     k_pnp_check<0><<<gc, kCheckWarps * 32, 0, st>>>(D);
     k_pnp_records<<<C, 32, 0, st>>>(D);
-    k_pnp_solve<1, 32><<<dim3(max_it, C), kSolveThreads, solve_smem<32>(), st>>>(D);  // blocks beyond a problem's record count exit
-    k_pnp_check<1><<<gc, kCheckWarps * 32, 0, st>>>(D);
+    if (team)  // blocks beyond a problem's record count exit
+        k_pnp_solve<1, 32, 3><<<dim3(max_rec, C), 3 * kSolveThreads, solve_smem<1, 32, 3>(), st>>>(D);
+    else
+        k_pnp_solve<1, 32, 1><<<dim3(max_rec, C), kSolveThreads, solve_smem<1, 32, 1>(), st>>>(D);
+    k_pnp_check<1><<<dim3((max_rec + kCheckWarps - 1) / kCheckWarps, C), kCheckWarps * 32, 0, st>>>(D);
     k_pnp_finalize<<<C, 32, 0, st>>>(D);
     CORB_CUDA(cudaGetLastError());
     CORB_CUDA(cudaMemcpyAsync(h + oRes, d + oRes, out_end - oRes, cudaMemcpyDeviceToHost, st));

@@ -212,6 +212,8 @@ struct Coop {
     double* SW;
     int* perm;
     int tl, team;
+    bool lead_only;  // the team shares ONE workspace and only its lane 0 runs the scalar phases (the others only take part in
+                     // the wavefront); false: every lane replicates the scalar phases on its own workspace
 };
 constexpr int COOP_ROW = 13;
 constexpr int COOP_DOUBLES = 12 * COOP_ROW + 12 + 6;  // S | SW | perm (12 ints)
@@ -354,7 +356,7 @@ CORB_HD inline double dist2(const double* p1, const double* p2) {
 struct Epnp {
     double fu, fv, uc, vc;
     double cws[4][3], ccs[4][3], ci[9];
-    Coop coop = {nullptr, nullptr, nullptr, 0, 32};
+    Coop coop = {nullptr, nullptr, nullptr, 0, 32, false};
 
     // SVD of the symmetric 12 x 12 in ws[WS_A..]: afterwards rows 8..11 hold the left singular vectors EPnP uses. With a
     // team (coop.S != nullptr; every lane of the team holds the same matrix in its own workspace) the sweeps run as a
@@ -367,12 +369,13 @@ struct Epnp {
                 for (int k = 0; k < 12; k++) coop.S[r * COOP_ROW + k] = A[r * 12 + k];
             __syncwarp();
             jacobi12_wavefront(coop);
-            for (int r = 8; r < 12; r++) {
-                const double sd = coop.SW[r];
-                const double sc = sd > DBL_MIN ? 1 / sd : 0.;
-                const double* row = coop.S + coop.perm[r] * COOP_ROW;
-                for (int k = 0; k < 12; k++) A[r * 12 + k] = row[k] * sc;
-            }
+            if (!coop.lead_only || coop.tl == 0)
+                for (int r = 8; r < 12; r++) {
+                    const double sd = coop.SW[r];
+                    const double sc = sd > DBL_MIN ? 1 / sd : 0.;
+                    const double* row = coop.S + coop.perm[r] * COOP_ROW;
+                    for (int k = 0; k < 12; k++) A[r * 12 + k] = row[k] * sc;
+                }
             __syncwarp();
             return;
         }
@@ -435,7 +438,7 @@ struct Epnp {
     // of ws[WS_A..] = Ut. WARP: lane l owns the upper-triangle entries l, l+32, l+64 and adds every correspondence's two
     // products to them in set order; the entries are then broadcast into every lane's copy of the workspace.
     template <bool WARP>
-    CORB_HD void mtm_svd(const PtSet& s, Ws ws) {
+    CORB_HD void mtm_build(const PtSet& s, Ws ws) {
         const Ws A = ws.at(WS_A);
 #ifdef __CUDA_ARCH__
         if (WARP && s.mask) {
@@ -472,7 +475,6 @@ struct Epnp {
                 A[j * 12 + i] = v;
                 if (++j == 12) { i++; j = i; }
             }
-            svd12(ws);
             return;
         }
 #endif
@@ -492,7 +494,6 @@ struct Epnp {
         }
         for (int i = 0; i < 12; i++)
             for (int j = i + 1; j < 12; j++) A[j * 12 + i] = A[i * 12 + j];
-        svd12(ws);
     }
 
     CORB_HD void compute_L_6x10(Ws ws, double* L) const {  // :787-829
@@ -693,37 +694,67 @@ struct Epnp {
         }
     }
 
-    // one of the three beta approximations of compute_pose (:545-557) and the selection N = 1; if (e2 < e1) N = 2;
-    // if (e3 < e[N]) N = 3 (:559-561): strict improvements only (NaN never wins)
+    // one of the three beta approximations of compute_pose (:545-557): betas, Gauss-Newton, R | t, reprojection error
     template <bool WARP, int which>
-    CORB_HD void branch(const PtSet& s, Ws ws, const double* L, const double* rho, double& best_err, double* Rt) {
+    CORB_HD double branch_raw(const PtSet& s, Ws ws, const double* L, const double* rho, double* Rt) {
         double betas[4], R[3][3], t[3];
         find_betas<which>(L, rho, betas, ws);
         gauss_newton(L, rho, betas);
         const double err = compute_R_and_t<WARP>(s, betas, ws, R, t);
+        for (int i = 0; i < 3; i++) {
+            for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[i][j];
+            Rt[9 + i] = t[i];
+        }
+        return err;
+    }
+    // ... and the selection N = 1; if (e2 < e1) N = 2; if (e3 < e[N]) N = 3 (:559-561): strict improvements only (NaN never wins)
+    template <bool WARP, int which>
+    CORB_HD void branch(const PtSet& s, Ws ws, const double* L, const double* rho, double& best_err, double* Rt) {
+        double cand[12];
+        const double err = branch_raw<WARP, which>(s, ws, L, rho, cand);
         if (which == 1 || err < best_err) {
             best_err = err;
-            for (int i = 0; i < 3; i++) {
-                for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[i][j];
-                Rt[9 + i] = t[i];
-            }
+            for (int i = 0; i < 12; i++) Rt[i] = cand[i];
         }
     }
 
     // compute_pose :527-574. Rt = R (row-major 9) followed by t (3).
     template <bool WARP = false>
-    CORB_HD double compute_pose(const PtSet& s, Ws ws, double* Rt) {
-        choose_control_points<WARP>(s, ws);
-        compute_barycentric(ws);
-        mtm_svd<WARP>(s, ws);
-        double L[60], rho[6];
-        compute_L_6x10(ws, L);
-        rho[0] = dist2(cws[0], cws[1]); rho[1] = dist2(cws[0], cws[2]); rho[2] = dist2(cws[0], cws[3]);  // compute_rho :831-839
-        rho[3] = dist2(cws[1], cws[2]); rho[4] = dist2(cws[1], cws[3]); rho[5] = dist2(cws[2], cws[3]);
+    CORB_HD double compute_pose(const PtSet& s, Ws ws, double* Rt) { return compute_pose_part<WARP>(s, ws, 0, Rt); }
+
+    // only_branch = 0: the whole compute_pose. 1..3 (warp-uniform): everything up to the SVD, then that beta approximation
+    // alone; the caller applies the selection rule to the three (error, pose) results. In a lead-only team the scalar
+    // phases run on the team's lane 0 and the other lanes only join the wavefront (their Rt and result are not written).
+    template <bool WARP>
+    CORB_HD double compute_pose_part(const PtSet& s, Ws ws, int only_branch, double* Rt) {
+        const bool lead = !coop.lead_only || coop.tl == 0;
+        if (lead) {
+            choose_control_points<WARP>(s, ws);
+            compute_barycentric(ws);
+            mtm_build<WARP>(s, ws);
+        }
+#ifdef __CUDA_ARCH__
+        if (coop.lead_only) __syncwarp();
+#endif
+        svd12(ws);
         double best_err = 0;
-        branch<WARP, 1>(s, ws, L, rho, best_err, Rt);
-        branch<WARP, 2>(s, ws, L, rho, best_err, Rt);
-        branch<WARP, 3>(s, ws, L, rho, best_err, Rt);
+        if (lead) {
+            double L[60], rho[6];
+            compute_L_6x10(ws, L);
+            rho[0] = dist2(cws[0], cws[1]); rho[1] = dist2(cws[0], cws[2]); rho[2] = dist2(cws[0], cws[3]);  // compute_rho :831-839
+            rho[3] = dist2(cws[1], cws[2]); rho[4] = dist2(cws[1], cws[3]); rho[5] = dist2(cws[2], cws[3]);
+            if (only_branch == 0) {
+                branch<WARP, 1>(s, ws, L, rho, best_err, Rt);
+                branch<WARP, 2>(s, ws, L, rho, best_err, Rt);
+                branch<WARP, 3>(s, ws, L, rho, best_err, Rt);
+            } else if (only_branch == 1) {
+                best_err = branch_raw<WARP, 1>(s, ws, L, rho, Rt);
+            } else if (only_branch == 2) {
+                best_err = branch_raw<WARP, 2>(s, ws, L, rho, Rt);
+            } else {
+                best_err = branch_raw<WARP, 3>(s, ws, L, rho, Rt);
+            }
+        }
         return best_err;
     }
 };
