@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -383,14 +384,14 @@ int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_probl
     D.rec_iter = (int*)(d + oRecIter); D.n_rec = (int*)(d + oNrec); D.slot_of_iter = (int*)(d + oSlot);
     D.ref_Rt = (double*)(d + oRefRt); D.ref_cnt = (int*)(d + oRefCnt); D.ref_mask = (uint32_t*)(d + oRefMask);
     D.res = (int*)(d + oRes); D.res_inl = d + oInl;
-    static bool attr_set[64] = {};
+    static std::atomic<bool> attr_set[64];  // per device; setting the attribute twice from two threads is harmless
     const int dev = matcher_device(m);
-    if (dev < 64 && !attr_set[dev]) {
+    if (dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
         CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<0, 1, 1>()));
         CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<0, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<0, 8, 3>()));
         CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<1, 32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<1, 32, 1>()));
         CORB_CUDA(cudaFuncSetAttribute(k_pnp_solve<1, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem<1, 32, 3>()));
-        attr_set[dev] = true;
+        if (dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
     // Small batches leave the GPU mostly idle and the call is bound by the latency of ONE hypothesis: a team of 8 lanes per
     // hypothesis and three warps per item (one beta approximation each) shorten it. Large batches keep one thread per
