@@ -1740,6 +1740,34 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     const double* eobs = grouped ? p->edge_obs : e_obs.data();
     const double* einfo = grouped ? p->edge_inv_sigma2 : e_info.data();
     lap("edges grouped by landmark");
+    // The edge arrays are the bulk of the upload (40 B per observation out of pageable memory: ~5 ms at E = 1 M, during which
+    // the enqueuing thread is blocked). A helper thread enqueues them now, while this thread derives the ordering and the
+    // envelope; it is joined before anything that reads them is enqueued. (With an all-reduce hook the ordering itself
+    // synchronises on the stream, so the copies stay where they were.)
+    cudaError_t up_err = cudaSuccess;  // (declared before the thread that writes it, so it outlives the join)
+    struct Joiner {
+        std::thread t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } uploader;
+    const bool early_upload = !allreduce && E > 0;
+    if (early_upload) {
+        int *q_pose, *q_point;
+        double *q_obs, *q_info;
+        int rc0;
+        if ((rc0 = H.alloc(&q_pose, (size_t)E)) != CORB_OK || (rc0 = H.alloc(&q_point, (size_t)E)) != CORB_OK ||
+            (rc0 = H.alloc(&q_obs, (size_t)E * 3)) != CORB_OK || (rc0 = H.alloc(&q_info, (size_t)E)) != CORB_OK)
+            return rc0;
+        d.e_pose = q_pose; d.e_point = q_point; d.e_obs = q_obs; d.e_info = q_info;
+        cudaStream_t st = H.stream;
+        uploader.t = std::thread([=, &up_err] {
+            cudaError_t e = cudaSetDevice(device);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(q_pose, ep, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(q_point, ept, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(q_obs, eobs, (size_t)E * 3 * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(q_info, einfo, (size_t)E * sizeof(double), cudaMemcpyHostToDevice, st);
+            up_err = e;
+        });
+    }
     // ---- ordering + envelope. nbr_min/nbr_max[j] = smallest / largest free pose sharing a free landmark with j.
     //      Long-range couplings (loop closures, map-fusion links) would stretch the envelope of every row they touch
     //      back to the far keyframe; instead the smaller of the two vertex covers of the long links is ordered last
@@ -1913,9 +1941,13 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     // ---- device buffers
 #define UP(field, vec) if ((rc = H.upload(&d.field, vec)) != CORB_OK) return rc
     UP(pfree, pfree); UP(lfree, lfree);
-    if ((rc = H.upload_raw(&d.e_pose, ep, (size_t)E)) != CORB_OK || (rc = H.upload_raw(&d.e_point, ept, (size_t)E)) != CORB_OK ||
-        (rc = H.upload_raw(&d.e_obs, eobs, (size_t)E * 3)) != CORB_OK || (rc = H.upload_raw(&d.e_info, einfo, (size_t)E)) != CORB_OK)
+    if (early_upload) {
+        uploader.t.join();
+        CORB_CHECK(up_err == cudaSuccess, CORB_ERR_CUDA, "uploading the edge arrays failed: %s", cudaGetErrorString(up_err));
+    } else if ((rc = H.upload_raw(&d.e_pose, ep, (size_t)E)) != CORB_OK || (rc = H.upload_raw(&d.e_point, ept, (size_t)E)) != CORB_OK ||
+               (rc = H.upload_raw(&d.e_obs, eobs, (size_t)E * 3)) != CORB_OK || (rc = H.upload_raw(&d.e_info, einfo, (size_t)E)) != CORB_OK) {
         return rc;
+    }
     if ((rc = H.build_pose_csr()) != CORB_OK) return rc;  // CSR by keyframe, built on the device from the uploaded e_pose
     UP(lm_off, lm_off); UP(first, first); UP(rowoff, rowoff);
     UP(coloff, coloff); UP(col_rows, col_rows); UP(coloff_b, coloff_b); UP(col_rows_b, col_rows_b); UP(chunk_start, chunk_start);
