@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <numeric>
 #include <mutex>
@@ -1380,12 +1381,20 @@ struct BaArena {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* h_scalars = nullptr;
+    // page-locked staging slots for the upload of the caller's (pageable) edge arrays: kStageSlots threads each copy
+    // chunks into their slot and enqueue the DMA from there - several times the rate of cudaMemcpy from pageable memory
+    static constexpr int kStageSlots = 4;
+    static constexpr size_t kStageBytes = (size_t)4 << 20;
+    uint8_t* h_stage = nullptr;
+    cudaEvent_t stage_ev[kStageSlots] = {};
     void free_slabs() {  // caller holds mu and the arena is idle
         for (auto& s : slabs) cudaFree(s.first);
         slabs.clear();
         cur = off = 0;
         release_when_idle = false;
         if (h_scalars) cudaFreeHost(h_scalars), h_scalars = nullptr;
+        if (h_stage) cudaFreeHost(h_stage), h_stage = nullptr;
+        for (auto& e : stage_ev) if (e) cudaEventDestroy(e), e = nullptr;
         if (ev0) cudaEventDestroy(ev0), ev0 = nullptr;
         if (ev1) cudaEventDestroy(ev1), ev1 = nullptr;
         if (stream) cudaStreamDestroy(stream), stream = nullptr;
@@ -1653,9 +1662,26 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     CORB_CHECK(P == 0 || (p->pose_q && p->pose_t && p->pose_fixed && p->pose_cam), CORB_ERR_INVALID, "pose arrays are NULL");
     CORB_CHECK(L == 0 || (p->point_xyz && p->point_fixed), CORB_ERR_INVALID, "point arrays are NULL");
     CORB_CHECK(E == 0 || (p->edge_pose && p->edge_point && p->edge_obs && p->edge_inv_sigma2), CORB_ERR_INVALID, "edge arrays are NULL");
-    for (int e = 0; e < E; e++)
-        CORB_CHECK(p->edge_pose[e] >= 0 && p->edge_pose[e] < P && p->edge_point[e] >= 0 && p->edge_point[e] < L, CORB_ERR_INVALID,
-                   "edge %d references pose %d / point %d out of range", e, p->edge_pose[e], p->edge_point[e]);
+    // one pass over the edges on a few threads: range check, and is the list grouped by landmark already (the order
+    // Optimizer::BundleAdjustment creates it in, Optimizer.cc:131-196)?
+    std::atomic<int> first_bad(E);
+    std::atomic<bool> grouped_a(true);
+    host_parallel_for(E, [&](int e0, int e1) {
+        int bad = E;
+        bool g = true;
+        for (int e = e0; e < e1; e++) {
+            const int a = p->edge_pose[e], b = p->edge_point[e];
+            if ((unsigned)a >= (unsigned)P || (unsigned)b >= (unsigned)L) { bad = std::min(bad, e); continue; }
+            if (e > 0 && p->edge_point[e - 1] > b) g = false;
+        }
+        if (!g) grouped_a.store(false);
+        int cur = first_bad.load();
+        while (bad < cur && !first_bad.compare_exchange_weak(cur, bad)) {}
+    });
+    {
+        const int e = first_bad.load();
+        CORB_CHECK(e >= E, CORB_ERR_INVALID, "edge %d references pose %d / point %d out of range", e, p->edge_pose[e], p->edge_point[e]);
+    }
     int ndev = 0;
     CORB_CUDA(cudaGetDeviceCount(&ndev));
     CORB_CHECK(device >= 0 && device < ndev, CORB_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
@@ -1687,6 +1713,10 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         if (!A.ev0) CORB_CUDA(cudaEventCreate(&A.ev0));
         if (!A.ev1) CORB_CUDA(cudaEventCreate(&A.ev1));
         if (!A.h_scalars) CORB_CUDA(cudaMallocHost(&A.h_scalars, 8 * sizeof(double)));
+        if (!A.h_stage && (size_t)E * 40 >= 4 * BaArena::kStageBytes) {
+            CORB_CUDA(cudaMallocHost(&A.h_stage, BaArena::kStageSlots * BaArena::kStageBytes));
+            for (auto& e : A.stage_ev) CORB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
         H.stream = A.stream; H.ev0 = A.ev0; H.ev1 = A.ev1; H.h_scalars = A.h_scalars;
         H.arena_owns_handles = true;
     } else {
@@ -1707,13 +1737,22 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     for (int i = 0; i < P; i++) pfree[i] = p->pose_fixed[i] ? -1 : Pf++;
     for (int i = 0; i < L; i++) lfree[i] = p->point_fixed[i] ? -1 : Lf++;
     d.Pf = Pf;
+    // Edges grouped by landmark (for every map point, its observations) are used in place; anything else is stably
+    // sorted by landmark first. lm_off[l] = first edge of landmark l.
+    const bool grouped = grouped_a.load();
     std::vector<int> lm_off(L + 1, 0);
-    for (int e = 0; e < E; e++) lm_off[p->edge_point[e] + 1]++;
-    for (int i = 0; i < L; i++) lm_off[i + 1] += lm_off[i];
-    // Edges grouped by landmark (the order Optimizer::BundleAdjustment creates them in, Optimizer.cc:131-196: for every
-    // map point, its observations) are used in place; anything else is stably sorted by landmark first.
-    bool grouped = true;
-    for (int e = 1; e < E && grouped; e++) grouped = p->edge_point[e - 1] <= p->edge_point[e];
+    if (grouped) {  // sorted keys: landmark l starts where the key first reaches l; every entry is written exactly once
+        host_parallel_for(E, [&](int e0, int e1) {
+            for (int e = e0; e < e1; e++) {
+                const int prev = e > 0 ? p->edge_point[e - 1] : -1, cur = p->edge_point[e];
+                for (int l = prev + 1; l <= cur; l++) lm_off[l] = e;
+            }
+        });
+        for (int l = (E > 0 ? p->edge_point[E - 1] : -1) + 1; l <= L; l++) lm_off[l] = E;
+    } else {
+        for (int e = 0; e < E; e++) lm_off[p->edge_point[e] + 1]++;
+        for (int i = 0; i < L; i++) lm_off[i + 1] += lm_off[i];
+    }
     std::vector<int> perm, e_pose_v, e_point_v;
     std::vector<double> e_obs_v, e_info_v;
     if (!grouped) {
@@ -1759,12 +1798,42 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             return rc0;
         d.e_pose = q_pose; d.e_point = q_point; d.e_obs = q_obs; d.e_info = q_info;
         cudaStream_t st = H.stream;
+        BaArena* stage = H.arena && H.arena->h_stage ? H.arena : nullptr;
         uploader.t = std::thread([=, &up_err] {
-            cudaError_t e = cudaSetDevice(device);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(q_pose, ep, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(q_point, ept, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(q_obs, eobs, (size_t)E * 3 * sizeof(double), cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(q_info, einfo, (size_t)E * sizeof(double), cudaMemcpyHostToDevice, st);
+            struct Job { char* dst; const char* src; size_t bytes; };
+            const Job jobs[4] = {{(char*)q_obs, (const char*)eobs, (size_t)E * 3 * sizeof(double)}, {(char*)q_info, (const char*)einfo, (size_t)E * sizeof(double)},
+                                 {(char*)q_pose, (const char*)ep, (size_t)E * sizeof(int)}, {(char*)q_point, (const char*)ept, (size_t)E * sizeof(int)}};
+            if (!stage) {
+                cudaError_t e = cudaSetDevice(device);
+                for (const Job& j : jobs)
+                    if (e == cudaSuccess) e = cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice, st);
+                up_err = e;
+                return;
+            }
+            std::vector<Job> chunks;
+            for (const Job& j : jobs)
+                for (size_t o = 0; o < j.bytes; o += BaArena::kStageBytes)
+                    chunks.push_back({j.dst + o, j.src + o, std::min(BaArena::kStageBytes, j.bytes - o)});
+            cudaError_t errs[BaArena::kStageSlots];
+            std::vector<std::thread> th;
+            for (int t = 0; t < BaArena::kStageSlots; t++)
+                th.emplace_back([&, t] {
+                    cudaError_t e = cudaSetDevice(device);
+                    uint8_t* slot = stage->h_stage + (size_t)t * BaArena::kStageBytes;
+                    bool used = false;
+                    for (size_t k = t; k < chunks.size() && e == cudaSuccess; k += BaArena::kStageSlots) {
+                        if (used) e = cudaEventSynchronize(stage->stage_ev[t]);  // the slot's previous DMA has read it
+                        if (e != cudaSuccess) break;
+                        memcpy(slot, chunks[k].src, chunks[k].bytes);
+                        e = cudaMemcpyAsync(chunks[k].dst, slot, chunks[k].bytes, cudaMemcpyHostToDevice, st);
+                        if (e == cudaSuccess) e = cudaEventRecord(stage->stage_ev[t], st);
+                        used = true;
+                    }
+                    errs[t] = e;
+                });
+            for (auto& x : th) x.join();
+            cudaError_t e = cudaSuccess;
+            for (cudaError_t x : errs) if (e == cudaSuccess) e = x;
             up_err = e;
         });
     }
