@@ -149,3 +149,34 @@ def test_ba_arena_release_and_reuse():
     b, ib = Optimizer.BundleAdjustment(prob, 4, bRobust=False)
     assert ia["chi2_final"] == ib["chi2_final"]
     np.testing.assert_array_equal(a["pose_t"], b["pose_t"])
+
+
+def test_ba_large_problem_staged_upload_equals_plain_upload(monkeypatch):
+    """Above ~420 k observations the edge arrays travel through page-locked staging slots on helper threads (part of the
+    per-device arena); without the arena they are plain copies. Same bits either way, and the chi2 the oracle reports for
+    the GPU solution equals the library's own."""
+    prob = ba_problem(500, 100000, seed=11, n_fusion=6)
+    assert len(prob["edge_pose"]) * 40 >= 16 << 20
+    a, ia = Optimizer.BundleAdjustment(prob, 3, bRobust=False)
+    monkeypatch.setenv("CORB_BA_NO_ARENA", "1")
+    b, ib = Optimizer.BundleAdjustment(prob, 3, bRobust=False)
+    monkeypatch.delenv("CORB_BA_NO_ARENA")
+    assert ia["chi2_final"] == ib["chi2_final"] and ia["trial_accepted"] == ib["trial_accepted"]
+    np.testing.assert_array_equal(a["pose_t"], b["pose_t"])
+    np.testing.assert_array_equal(a["point_xyz"], b["point_xyz"])
+    # shuffled edges (not grouped by landmark): the library sorts them, the staged path uploads the sorted copies
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(prob["edge_pose"]))
+    shuf = dict(prob)
+    for k in ("edge_pose", "edge_point", "edge_obs", "edge_inv_sigma2"):
+        shuf[k] = np.ascontiguousarray(prob[k][perm])
+    c, ic = Optimizer.BundleAdjustment(shuf, 3, bRobust=False)
+    assert ic["trial_accepted"] == ia["trial_accepted"] and ic["chi2_final"] == pytest.approx(ia["chi2_final"], rel=1e-9)
+    oracle.lib()
+    chi2, _ = B.chi2(a)
+    assert chi2 == pytest.approx(ia["chi2_final"], rel=1e-9)
+    with pytest.raises(Exception):  # an out-of-range edge anywhere in the list is reported, nothing is computed
+        bad = dict(prob)
+        bad["edge_pose"] = prob["edge_pose"].copy()
+        bad["edge_pose"][len(perm) // 2] = 500
+        Optimizer.BundleAdjustment(bad, 1, bRobust=False)
