@@ -71,7 +71,7 @@ constexpr int kTeamWs = WS_DOUBLES + 1;  // workspace stride of a lead-only team
 template <int MODE, int TEAM>
 __host__ __device__ constexpr size_t warp_doubles() {
     return (MODE == 0 && TEAM > 1 ? (size_t)(kSolveThreads / TEAM) * kTeamWs : (size_t)WS_DOUBLES * kSolveThreads) +
-           (TEAM > 1 ? (size_t)(kSolveThreads / TEAM) * COOP_DOUBLES : 0);
+           (TEAM > 1 ? (size_t)(kSolveThreads / TEAM) * COOP_DOUBLES : 0) + (MODE == 1 && TEAM == 32 ? (size_t)TBUF_DOUBLES : 0);
 }
 template <int MODE, int TEAM, int NB>
 constexpr size_t solve_smem() { return (NB * warp_doubles<MODE, TEAM>() + (NB > 1 ? (kSolveThreads / TEAM) * 3 * 13 : 0)) * sizeof(double); }
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(kSolveThreads * NB) k_pnp_solve(PnpDev D) {
     Ws ws = kLeadOnly ? Ws{wbase + (size_t)(lane / TEAM) * kTeamWs, 1} : Ws{wbase + lane, kSolveThreads};
     if (TEAM > 1) {
         double* area = wbase + (kLeadOnly ? (size_t)kItems * kTeamWs : (size_t)WS_DOUBLES * kSolveThreads) + (size_t)(lane / TEAM) * COOP_DOUBLES;
-        e.coop = Coop{area, area + 12 * COOP_ROW, (int*)(area + 12 * COOP_ROW + 12), lane % TEAM, TEAM, kLeadOnly};
+        e.coop = Coop{area, area + 12 * COOP_ROW, (int*)(area + 12 * COOP_ROW + 12), lane % TEAM, TEAM,
+                      MODE == 1 && TEAM == 32 ? area + COOP_DOUBLES : nullptr, kLeadOnly};
     }
     double Rt[12];
     const double err = e.template compute_pose_part<(MODE == 1 && TEAM == 32)>(s, ws, NB == 3 ? warp + 1 : 0, Rt);

@@ -83,9 +83,36 @@ CORB_HD inline void load_pw(const PtSet& s, int idx, double pw[3]) {  // add_cor
 // the warp hold identical state and call together): lane l evaluates the addends of bit l of each mask word, then the
 // additions are performed in ascending bit order on every lane (shuffle broadcast), so each lane ends with the same
 // accumulators a single thread would have produced - same addends, same order, same bits.
+constexpr int TBUF_ROW = 33;                 // transpose buffer: [accumulator][lane], padded so that column reads spread over the banks
+constexpr int TBUF_DOUBLES = 9 * TBUF_ROW;  // up to 9 accumulators per pass
+
 template <bool WARP, int NA, class F>
-CORB_HD inline void ordered_sum(const PtSet& s, double* acc, F&& term) {
+CORB_HD inline void ordered_sum(const PtSet& s, double* acc, F&& term, double* tbuf = nullptr) {
 #ifdef __CUDA_ARCH__
+    if (WARP && s.mask && tbuf) {
+        // addends of a mask word go through shared memory: lane a < NA then owns accumulator a and adds its column in
+        // ascending bit order (one load + one add per addend instead of a shuffle broadcast of every addend to every lane);
+        // the finished accumulators are broadcast once
+        const int lane = threadIdx.x & 31;
+        double own = lane < NA ? acc[lane < NA ? lane : 0] : 0.0;
+        for (int w = 0; w < s.n_words; w++) {
+            const uint32_t bits = s.mask[w];
+            if (!bits) continue;
+            if ((bits >> lane) & 1u) {
+                double t[NA];
+                term(w * 32 + lane, t);
+#pragma unroll
+                for (int a = 0; a < NA; a++) tbuf[a * TBUF_ROW + lane] = t[a];
+            }
+            __syncwarp();
+            if (lane < NA)
+                for (uint32_t b = bits; b; b &= b - 1) own += tbuf[lane * TBUF_ROW + __ffs((int)b) - 1];
+            __syncwarp();
+        }
+#pragma unroll
+        for (int a = 0; a < NA; a++) acc[a] = __shfl_sync(0xffffffffu, own, a);
+        return;
+    }
     if (WARP && s.mask) {
         const int lane = threadIdx.x & 31;
         for (int w = 0; w < s.n_words; w++) {
@@ -212,6 +239,7 @@ struct Coop {
     double* SW;
     int* perm;
     int tl, team;
+    double* tbuf;    // per-warp transpose buffer of the ordered sums (TBUF_DOUBLES), or nullptr
     bool lead_only;  // the team shares ONE workspace and only its lane 0 runs the scalar phases (the others only take part in
                      // the wavefront); false: every lane replicates the scalar phases on its own workspace
 };
@@ -356,7 +384,7 @@ CORB_HD inline double dist2(const double* p1, const double* p2) {
 struct Epnp {
     double fu, fv, uc, vc;
     double cws[4][3], ccs[4][3], ci[9];
-    Coop coop = {nullptr, nullptr, nullptr, 0, 32, false};
+    Coop coop = {nullptr, nullptr, nullptr, 0, 32, nullptr, false};
 
     // SVD of the symmetric 12 x 12 in ws[WS_A..]: afterwards rows 8..11 hold the left singular vectors EPnP uses. With a
     // team (coop.S != nullptr; every lane of the team holds the same matrix in its own workspace) the sweeps run as a
@@ -396,7 +424,7 @@ struct Epnp {
     CORB_HD void choose_control_points(const PtSet& s, Ws ws) {  // :420-455
         const int n = s.n;
         double c0[3] = {0, 0, 0};
-        ordered_sum<WARP, 3>(s, c0, [&](int idx, double* t) { load_pw(s, idx, t); });
+        ordered_sum<WARP, 3>(s, c0, [&](int idx, double* t) { load_pw(s, idx, t); }, coop.tbuf);
         for (int j = 0; j < 3; j++) cws[0][j] = c0[j] / n;
         double m[6] = {0, 0, 0, 0, 0, 0};  // upper triangle of PW0^T PW0: 00 01 02 11 12 22
         ordered_sum<WARP, 6>(s, m, [&](int idx, double* t) {
@@ -404,7 +432,7 @@ struct Epnp {
             load_pw(s, idx, pw);
             const double d0 = pw[0] - cws[0][0], d1 = pw[1] - cws[0][1], d2 = pw[2] - cws[0][2];
             t[0] = d0 * d0; t[1] = d0 * d1; t[2] = d0 * d2; t[3] = d1 * d1; t[4] = d1 * d2; t[5] = d2 * d2;
-        });
+        }, coop.tbuf);
         const double ptp[9] = {m[0], m[1], m[2], m[1], m[3], m[4], m[2], m[4], m[5]};
         svd_small<3, 3, false>(ptp, ws);
         const Ws uct = ws.at(WS_S), dc = ws.at(WS_SW);
@@ -560,7 +588,7 @@ struct Epnp {
             load_pw(s, idx, tt + 3);
             alphas_of(tt + 3, a);
             pc_of(a, tt);
-        });
+        }, coop.tbuf);
         double pc0[3], pw0[3];
         for (int j = 0; j < 3; j++) { pc0[j] = c6[j] / n; pw0[j] = c6[3 + j] / n; }
         double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -574,7 +602,7 @@ struct Epnp {
                 tt[3 * j + 1] = (pc[j] - pc0[j]) * (pw[1] - pw0[1]);
                 tt[3 * j + 2] = (pc[j] - pc0[j]) * (pw[2] - pw0[2]);
             }
-        });
+        }, coop.tbuf);
         svd_small<3, 3, true>(abt, ws);
         const Ws Ut = ws.at(WS_S), Vt = ws.at(WS_SV);
         for (int i = 0; i < 3; i++)
@@ -597,7 +625,7 @@ struct Epnp {
             const double ve = vc + fv * Yc * inv_Zc;
             const double u = (double)s.p2d[2 * idx], v = (double)s.p2d[2 * idx + 1];
             tt[0] = sqrt((u - ue) * (u - ue) + (v - ve) * (v - ve));
-        });
+        }, coop.tbuf);
         return sum2 / n;
     }
 
