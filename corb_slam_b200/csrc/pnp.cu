@@ -101,26 +101,9 @@ __global__ void __launch_bounds__(kSolveThreads * NB) k_pnp_solve(PnpDev D) {
     s.n_words = P.n_words;
     double* out;
     if (MODE == 0) {
-        // vAvailableIndices = mvAllIndices; idx = avail[randi]; avail[randi] = avail.back(); pop_back()  (:228-242):
-        // at most four positions of the identity list are ever modified
         const int4 dr = D.draws[P.hyp_off + item];
         const int r[4] = {dr.x, dr.y, dr.z, dr.w};
-        int mp[4], mv[4], sz = P.n;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int idx = r[k];
-            const int last = sz - 1;
-            int lastval = last;
-#pragma unroll
-            for (int j = 0; j < k; j++) {  // ascending j: the latest modification wins
-                if (mp[j] == r[k]) idx = mv[j];
-                if (mp[j] == last) lastval = mv[j];
-            }
-            s.list[k] = idx;
-            mp[k] = r[k];
-            mv[k] = lastval;
-            sz--;
-        }
+        resolve_draws(P.n, r, s.list);  // the vAvailableIndices bookkeeping of :228-242
         s.n = 4;
         s.mask = nullptr;
         out = D.hyp_Rt + 12 * (size_t)(P.hyp_off + item);

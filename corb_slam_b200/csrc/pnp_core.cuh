@@ -83,6 +83,33 @@ CORB_HD inline void load_pw(const PtSet& s, int idx, double pw[3]) {  // add_cor
 // the warp hold identical state and call together): lane l evaluates the addends of bit l of each mask word, then the
 // additions are performed in ascending bit order on every lane (shuffle broadcast), so each lane ends with the same
 // accumulators a single thread would have produced - same addends, same order, same bits.
+// The minimal set of one RANSAC iteration (PnPsolver.cc:228-242): vAvailableIndices = mvAllIndices (the identity list of
+// n entries); four times: idx = avail[randi]; avail[randi] = avail.back(); avail.pop_back(). At most four positions of the
+// identity list are ever modified, so the list is never materialised: (mp, mv) record the modified positions, the latest
+// modification of a position wins.
+CORB_HD inline void resolve_draws(int n, const int r[4], int list[4]) {
+    int mp[4], mv[4], sz = n;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) {
+        int idx = r[k];
+        const int last = sz - 1;
+        int lastval = last;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int j = 0; j < k; j++) {  // ascending j: the latest modification wins
+            if (mp[j] == r[k]) idx = mv[j];
+            if (mp[j] == last) lastval = mv[j];
+        }
+        list[k] = idx;
+        mp[k] = r[k];
+        mv[k] = lastval;
+        sz--;
+    }
+}
+
 constexpr int TBUF_ROW = 33;                 // transpose buffer: [accumulator][lane], padded so that column reads spread over the banks
 constexpr int TBUF_DOUBLES = 9 * TBUF_ROW;  // up to 9 accumulators per pass
 

@@ -30,6 +30,8 @@ double harness_epnp_pose(const float* p3d, const float* p2d, int n_pts, const in
     return e.compute_pose(s, ws, Rt);
 }
 
+void harness_resolve_draws(int n, const int* r, int* list) { resolve_draws(n, r, list); }
+
 int harness_count_inliers(const double* Rt, double fu, double fv, double uc, double vc, const float* p3d, const float* p2d,
                           const float* max_err, int n, uint8_t* inl) {
     int c = 0;

@@ -150,3 +150,60 @@ def test_device_epnp_compiled_for_the_host_is_bit_exact(harness):
                                       Rt.ctypes.data)
         R, t, eo = P.epnp_pose(p["p3d"][sel].astype(np.float64), p["p2d"][sel].astype(np.float64), fx, fy, cx, cy)
         assert Rt[:9].tobytes() == R.tobytes() and Rt[9:].tobytes() == t.tobytes() and e == eo, seed
+
+
+def test_draw_resolution_equals_the_list_bookkeeping(harness):
+    """resolve_draws (the kernel's replay of vAvailableIndices, PnPsolver.cc:228-242) against the literal list operations,
+    exhaustively for small n and on random draws for large n."""
+    def model(n, r):
+        avail = list(range(n))
+        out = []
+        for k in range(4):
+            out.append(avail[r[k]])
+            avail[r[k]] = avail[-1]
+            avail.pop()
+        return out
+
+    def dev(n, r):
+        rr = np.array(r, np.int32)
+        out = np.zeros(4, np.int32)
+        harness.harness_resolve_draws(n, rr.ctypes.data, out.ctypes.data)
+        return out.tolist()
+
+    harness.harness_resolve_draws.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    harness.harness_resolve_draws.restype = None
+    for n in (4, 5, 6, 7):
+        for a in range(n):
+            for b in range(n - 1):
+                for c in range(n - 2):
+                    for d in range(n - 3):
+                        assert dev(n, (a, b, c, d)) == model(n, (a, b, c, d)), (n, a, b, c, d)
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        n = int(rng.integers(4, 3000))
+        r = [int(rng.integers(0, n - k)) for k in range(4)]
+        got = dev(n, r)
+        assert got == model(n, r) and len(set(got)) == 4
+
+
+def test_wavefront_schedule_preserves_the_order_of_dependent_visits():
+    """jacobi12_wavefront runs visit (i, j) of a cyclic-by-rows sweep at step i + j. The claim behind its bit-exactness: visits
+    of one step touch disjoint rows, and two visits that share a row keep their lexicographic (= sequential) order."""
+    n = 12
+    visits = [(i, j) for i in range(n - 1) for j in range(i + 1, n)]
+    step = {v: v[0] + v[1] for v in visits}
+    by_step = {}
+    for v in visits:
+        by_step.setdefault(step[v], []).append(v)
+    assert sorted(by_step) == list(range(1, 2 * n - 2)) and max(len(b) for b in by_step.values()) == n // 2
+    for vs in by_step.values():
+        rows = [r for v in vs for r in v]
+        assert len(rows) == len(set(rows))
+        # the kernel's lane -> visit map: i = max(0, t - 11) + lane, j = t - i, active while i < j
+        t = vs[0][0] + vs[0][1]
+        lanes = [(max(0, t - (n - 1)) + l, t - (max(0, t - (n - 1)) + l)) for l in range(8)]
+        assert sorted(v for v in lanes if v[0] < v[1]) == sorted(vs)
+    for a in range(len(visits)):
+        for b in range(a + 1, len(visits)):
+            if set(visits[a]) & set(visits[b]):
+                assert step[visits[a]] < step[visits[b]], (visits[a], visits[b])
