@@ -309,10 +309,12 @@ typedef struct {
 
 /* PnPsolver::iterate(nIterations, bNoMore, vbInliers, nInliers) [PnPsolver.cc:206-300] for a batch of solver objects -
  * the relocalisation / map-fusion candidates of Tracking.cc:1432-1440 and MapFusion.cpp:720-728 - in one call: every
- * RANSAC hypothesis of every candidate is one GPU thread (EPnP on 4 points), inlier counting one warp per hypothesis,
- * Refine() one thread per best-so-far record; the sequential bookkeeping of the reference (best so far, the first
- * iteration whose Refine() succeeds) is resolved afterwards from the per-hypothesis results. inliers[c] (nullable)
- * receives n bytes: vbInliers over the flattened correspondences (the shim scatters them through mvKeyPointIndices). */
+ * RANSAC hypothesis of every candidate is evaluated at once (EPnP on 4 points: a team of 8 lanes per hypothesis in small
+ * batches, one thread in large ones), inlier counting is one warp per hypothesis, Refine() one warp per best-so-far record;
+ * the sequential bookkeeping of the reference (best so far, the first iteration whose Refine() succeeds) is resolved
+ * afterwards from the per-hypothesis results, so the outcome equals the sequential loop on the same draws. inliers[c]
+ * (nullable) receives n bytes: vbInliers over the flattened correspondences (the shim scatters them through
+ * mvKeyPointIndices). One handle must not be used from two threads at once. */
 CORB_API int corb_pnp_iterate_batch(corb_matcher* m, int n_problems, const corb_pnp_problem* problems, corb_pnp_result* results,
                                     uint8_t* const* inliers);
 
