@@ -668,5 +668,6 @@ double oracle_epnp_pose(int n, const double* pws, const double* us, double fu, d
 void oracle_svd(const double* A, int m, int n, double* Ut, double* W, double* Vt) { svd(A, m, n, Ut, W, Vt); }
 void oracle_svd_solve(const double* A, int m, int n, const double* b, double* x) { svd_solve(A, m, n, b, x); }
 void oracle_svd_invert3(const double* A, double* inv) { svd_invert3(A, inv); }
+void oracle_mul_transposed(const double* src, int rows, int cols, double* dst) { mul_transposed(src, rows, cols, dst); }
 
 } // extern "C"

@@ -1,0 +1,2 @@
+/* STUB OpenCV — TEST INFRASTRUCTURE ONLY (see opencv2/core/core.hpp). */
+#include "opencv2/opencv.hpp"

@@ -1,0 +1,5 @@
+/* STUB OpenCV — TEST INFRASTRUCTURE ONLY (see opencv2/core/core.hpp). */
+#include "opencv2/core/core.hpp"
+#include "opencv2/imgproc/imgproc.hpp"
+#include "opencv2/features2d/features2d.hpp"
+#include "opencv2/highgui/highgui.hpp"
