@@ -366,7 +366,11 @@ static int run_projection(corb_matcher* m, const corb_frame_view* f, int variant
         CORB_CHECK(Tlw, CORB_ERR_INVALID, "Tlw is NULL");
         float twc[3], tlc[3];
         const float tcw[3] = {f->Tcw[3], f->Tcw[7], f->Tcw[11]}, tlw[3] = {Tlw[3], Tlw[7], Tlw[11]};
-        gemm3(f->Tcw, true, -1.0, tcw, 0.0, nullptr, twc);  // twc = -Rcw.t()*tcw (:1483)
+        // twc = -Rcw.t()*tcw (:1483): cv::MatExpr's unary minus materialises the transpose first (matop.cpp: MatOp::subtract(Scalar,
+        // expr) assigns the T node to a Mat), so the product is an UNtransposed gemm on the stored transpose with alpha = -1,
+        // i.e. the small-matrix float path (checked against the reference's own expression in tests/test_ref_cpu.py).
+        const float Rt[12] = {f->Tcw[0], f->Tcw[4], f->Tcw[8], 0.f, f->Tcw[1], f->Tcw[5], f->Tcw[9], 0.f, f->Tcw[2], f->Tcw[6], f->Tcw[10], 0.f};
+        gemm3(Rt, false, -1.0, tcw, 0.0, nullptr, twc);
         gemm3(Tlw, false, 1.0, twc, 1.0, tlw, tlc);          // tlc = Rlw*twc+tlw (:1488)
         forward = tlc[2] > f->mb && !mono;
         backward = -tlc[2] > f->mb && !mono;

@@ -13,7 +13,8 @@
  * The reduced camera system is solved with a block-skyline Cholesky (the reference uses Eigen's SimplicialLDLT with AMD
  * ordering, linear_solver_eigen.h:94-124 — Eigen is not vendored): same direct solution up to fp64 round-off.
  *
- * PARITY STATUS: parity unpinned — the reference ships no BA fixtures. Pinned by algebra instead: analytic
+ * PARITY STATUS: parity unpinned (the only path left as a port: g2o and Optimizer.cc need Eigen3, which is not in the image,
+ * so they cannot be compiled into oracle/_ref) — the reference ships no BA fixtures. Pinned by algebra instead: analytic
  * Jacobians vs central differences, chi2 monotone over accepted steps, LM constants from the source (tests/test_ba_oracle.py).
  *
  * Landmarks may be sharded over ranks: every rank holds all poses and a subset of landmarks with their edges; the

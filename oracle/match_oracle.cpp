@@ -7,8 +7,9 @@
  *     :1218-1259 (descent), :1338-1424 (text loader); FORB.cpp:81-101; BowVector.cpp:34-84;
  *     FeatureVector.cpp:31-45; ScoringObject.cpp:23-68 (L1)
  *
- * PARITY STATUS: parity unpinned — the reference has no tests or golden vectors for this path.
- * Pinned by: source constants (TH_LOW 50, TH_HIGH 100, HISTO_LENGTH 30), the SWAR popcount identity checked against
+ * PARITY STATUS: PINNED against the reference's own ORBmatcher.cc and Thirdparty/DBoW2 compiled unmodified into
+ * oracle/_ref/libref.so, on the real ORBvoc.txt (k 10, L 6, 1 082 073 nodes): BowVector / FeatureVector / L1 score bits and
+ * the match arrays of the three SearchByBoW variants are equal (tests/test_ref_cpu.py). Also: source constants (TH_LOW 50, TH_HIGH 100, HISTO_LENGTH 30), the SWAR popcount identity checked against
  * __builtin_popcount, and the real vocabulary header (k 10, L 6, L1_NORM, TF_IDF) where the file is available.
  *
  * Two reference behaviours that depend on uninitialised memory are given canonical definitions:

@@ -6,10 +6,13 @@
  * INTER_LINEAR u8, GaussianBlur 7x7 sigma 2 u8, fastAtan2, cvRound), pinned to cv2 4.13.0
  * semantics by tests/test_oracle_primitives.py and the fixtures in tests/golden/.
  *
- * PARITY STATUS: the reference ships no golden vectors. The OpenCV
- * primitive models are pinned against cv2 4.13.0 run in the build container; the composition
- * (cell grid, quadtree, ordering) is pinned only by source reading => "parity unpinned" for the
- * composed extractor, pinned for the primitives.
+ * PARITY STATUS: PINNED. The reference ships no golden vectors; the OpenCV primitive
+ * models are pinned against cv2 4.13.0 (tests/golden/), and the composition (cell grid, quadtree, ordering,
+ * orientation, descriptors, stereo matching) is pinned byte for byte against the reference's own
+ * ORBextractor.cc / Frame.cc compiled unmodified into oracle/_ref/libref.so (oracle/refbuild,
+ * tests/test_ref_cpu.py). The one canonical choice: quadtree ties are split in creation order, where the
+ * reference compares heap addresses (ORBextractor.cc:591,627,684) - libref runs with a creation-ordered
+ * node allocator; with plain malloc ~1 % of a frame's keypoints change.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
  * use this code. The product (libcorb_b200.so) never links or calls it.

@@ -21,9 +21,11 @@
  * path can be compared bit for bit), and a singular value <= DBL_MIN leaves a zero left vector instead of OpenCV's
  * random completion.
  *
- * PARITY STATUS: parity unpinned for the composition - the reference has no tests or golden vectors, and
- * the RANSAC of the reference consumes the process-global rand() stream, so its outcome is not a function of its
- * arguments. What is pinned: (1) the SVD / solve / invert restatements against cv2.SVDecomp / cv2.solve / cv2.invert
+ * PARITY STATUS: PINNED against the reference's own PnPsolver.cc compiled unmodified into oracle/_ref/libref.so (cvSVD /
+ * cvSolve / cvInvert of the stub OpenCV are the restatements below): with the draws its rand() stream produces, status,
+ * bNoMore, inlier sets, iteration counts and the float32 Tcw are equal bit for bit over resumed calls
+ * (tests/test_ref_cpu.py). The RANSAC of the reference consumes the process-global rand() stream, so its outcome is not a
+ * function of its arguments; here the draws are. Also pinned: (1) the SVD / solve / invert restatements against cv2.SVDecomp / cv2.solve / cv2.invert
  * 4.13.0 (LAPACK-backed in this wheel, so to 1e-9, not bit for bit) and (2) compute_pose against cv2.solvePnP
  * (SOLVEPNP_EPNP) - OpenCV's own copy of the same EPnP code - on 6..200 points (tests/golden/pnp_cv2.npz,
  * tools/gen_golden_pnp.py). With a minimal set of 4 points M^T M has a 4-dimensional null space whose basis is decided

@@ -7,11 +7,12 @@
  *   corbslam_client/src/Frame.cc:331-384       Frame::GetFeaturesInArea (64 x 48 grid, Frame.h:38-39)
  *   corbslam_client/src/ORBmatcher.cc:1746-1808 ComputeThreeMaxima, DescriptorDistance
  *
- * PARITY STATUS: parity unpinned — the reference has no tests or golden vectors for this path.
- * Pinned by source constants (TH_HIGH 100, HISTO_LENGTH 30, FRAME_GRID 64 x 48, radii 2.5 / 4.0) and, for the one
+ * PARITY STATUS: PINNED against the reference's own ORBmatcher.cc / Frame.cc (GetFeaturesInArea on the real mGrid)
+ * compiled unmodified into oracle/_ref/libref.so: match arrays equal on every test scene (tests/test_ref_cpu.py).
+ * Also pinned by source constants (TH_HIGH 100, HISTO_LENGTH 30, FRAME_GRID 64 x 48, radii 2.5 / 4.0) and, for the one
  * piece of arithmetic delegated to OpenCV (cv::Mat products `Rcw*x3Dw+tcw`, `-Rcw.t()*tcw`, `Rlw*twc+tlw` =
  * cv::gemm on CV_32F: float dot product in the untransposed small-matrix case, double accumulation with a transposed
- * operand, alpha/beta applied in double), by golden vectors
+ * operand, alpha/beta applied in double; which gemm call a cv::MatExpr becomes follows matop.cpp), by golden vectors
  * generated with cv2.gemm 4.13.0 (tests/golden/opencv_primitives.npz, tools/gen_golden.py).
  * Built with -ffp-contract=off: `fx*xc*invzc+cx` is two float multiplications and one float addition.
  *
@@ -136,7 +137,11 @@ int oracle_search_by_projection_last(const oracle_frame_view* cur, int n_last, c
     if (cur->taken) memcpy(taken.data(), cur->taken, cur->n);
     float twc[3], tlc[3];
     const float tcw[3] = {cur->Tcw[3], cur->Tcw[7], cur->Tcw[11]}, tlw[3] = {Tlw[3], Tlw[7], Tlw[11]};
-    oracle_gemm3(cur->Tcw, 1, -1.0, tcw, 0.0, nullptr, twc);  /* twc = -Rcw.t()*tcw   (:1483) */
+    /* twc = -Rcw.t()*tcw (:1483). cv::MatExpr: unary minus on a transpose node materialises the transpose (matop.cpp,
+     * MatOp::subtract(Scalar, expr)), the product then is gemm(Rt, tcw, alpha = -1, flags = 0) = the small-matrix float path. */
+    const float Rt[12] = {cur->Tcw[0], cur->Tcw[4], cur->Tcw[8], 0.f, cur->Tcw[1], cur->Tcw[5], cur->Tcw[9], 0.f,
+                          cur->Tcw[2], cur->Tcw[6], cur->Tcw[10], 0.f};
+    oracle_gemm3(Rt, 0, -1.0, tcw, 0.0, nullptr, twc);
     oracle_gemm3(Tlw, 0, 1.0, twc, 1.0, tlw, tlc);             /* tlc = Rlw*twc+tlw    (:1488) */
     const bool bForward = tlc[2] > cur->mb && !mono, bBackward = -tlc[2] > cur->mb && !mono;
     std::vector<int> vIndices2;

@@ -6,7 +6,7 @@
  * malloc the freed list nodes are recycled LIFO and the order is arbitrary (and differs between the two extractor
  * threads of Frame.cc:78-81). To compare the unmodified source with anything, the environment has to be fixed: while
  * `monotone` is on (default), std::list<ExtractorNode> nodes - recognised by their size - come from a per-thread bump
- * pool, so that address order == creation order, which is the canonical tie-break of the oracle and of the CUDA path
+ * pool (only while a glue call that runs the extractor is in flight), so that address order == creation order, which is the canonical tie-break of the oracle and of the CUDA path
  * (DESIGN.md section 2). ref_set_monotone_nodes(0) restores plain malloc; tests/test_ref_cpu.py measures how many
  * keypoints that changes. Every other allocation is malloc / free. (-Bsymbolic binds libref's own calls to these.) */
 #include <sys/mman.h>
@@ -23,6 +23,7 @@ namespace {
 const size_t kNodeBytes = sizeof(std::_List_node<ORB_SLAM2::ExtractorNode>);
 const size_t kPoolBytes = (size_t)1 << 30; /* address space only (MAP_NORESERVE) */
 std::atomic<int> g_monotone(1);
+std::atomic<int> g_active(0); /* > 0 while a glue call that runs ORBextractor::operator() is in flight */
 struct Pool {
     char* base;
     size_t off, live;
@@ -53,7 +54,7 @@ inline bool pool_free(void* ptr) {
 } // namespace
 
 void* operator new(size_t n) {
-    if (n == kNodeBytes && g_monotone.load(std::memory_order_relaxed)) return pool_alloc();
+    if (n == kNodeBytes && g_active.load(std::memory_order_relaxed) > 0 && g_monotone.load(std::memory_order_relaxed)) return pool_alloc();
     void* p = std::malloc(n ? n : 1);
     if (!p) throw std::bad_alloc();
     return p;
@@ -69,3 +70,6 @@ void operator delete[](void* p) noexcept { std::free(p); }
 void operator delete[](void* p, size_t) noexcept { std::free(p); }
 
 extern "C" void ref_set_monotone_nodes(int on) { g_monotone.store(on ? 1 : 0); }
+/* The pool is only live inside extractor calls: a block of the node size allocated here but released inside libstdc++.so
+ * (which keeps its own operator delete when libref is dlopen()ed RTLD_LOCAL) must never come from the pool. */
+extern "C" void ref_alloc_scope(int delta) { g_active.fetch_add(delta); }
