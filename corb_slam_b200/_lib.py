@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcorb_b200.so")
+# CORB_LIB selects another BUILD of the same library (instrumented debug variants, csrc/Makefile); there is no other backend
+LIB_PATH = os.environ.get("CORB_LIB") or os.path.join(_HERE, "libcorb_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY, ERR_STOPPED, ERR_IO = range(7)
 

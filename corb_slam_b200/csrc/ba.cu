@@ -148,7 +148,7 @@ struct BaDev {
     double *S, *bs;                // reduced system: [S | bs] contiguous
     double *invd;                  // [Pf * 6] reciprocals of the diagonal of the Cholesky factor (triangular solves multiply)
     double *xp, *xl;
-    double *partial, *scalars;     // reduction scratch; scalars[0] chi2, [1] scale part, [2] xx, [3] max diag, [4] fail flag
+    double *partial, *scalars;     // reduction scratch; [1] scale part, [2] xx, [3] max diag, [4] fail flag, [6] chi2, [7] stop votes
     int robust;
     double delta2d, delta3d;
 };
@@ -1443,6 +1443,11 @@ struct BaHost {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double ms_solve = 0;
     double* h_scalars = nullptr;  // pinned [8]
+    // Sharded solve: every rank must take the same branch on the caller's stop flag (each chi2 / trial is a collective), so
+    // the flag is sampled where chi2 is reduced, summed over the ranks next to it, and only the reduced value is branched on.
+    const volatile uint8_t* stop_flag = nullptr;
+    bool agreed_stop = false;
+    bool stop_requested() const { return ar ? agreed_stop : (stop_flag && *stop_flag); }
 
     ~BaHost() {
         if (stream) cudaStreamSynchronize(stream);
@@ -1527,11 +1532,17 @@ struct BaHost {
     int chi2(double* out) {
         const int nb = (d.E + 255) / 256;
         if (nb > 0) k_ba_chi2<<<nb, 256, 0, stream>>>(d);
-        k_reduce_final<false><<<1, 256, 0, stream>>>(d.partial, nb, d.scalars);
-        int rc = reduce(d.scalars, 1, 0);
+        k_reduce_final<false><<<1, 256, 0, stream>>>(d.partial, nb, d.scalars + 6);
+        if (ar) {  // scalars[7] = this rank's vote; h_scalars[5] is never a read-back target, the stream is idle between calls
+            h_scalars[5] = (stop_flag && *stop_flag) ? 1.0 : 0.0;
+            CORB_CUDA(cudaMemcpyAsync(d.scalars + 7, h_scalars + 5, sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
+        int rc = reduce(d.scalars + 6, ar ? 2 : 1, 0);
         if (rc != CORB_OK) return rc;
-        rc = read_scalars(1);
-        *out = h_scalars[0];
+        CORB_CUDA(cudaMemcpyAsync(h_scalars + 6, d.scalars + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CORB_CUDA(cudaStreamSynchronize(stream));
+        *out = h_scalars[6];
+        if (ar) agreed_stop = h_scalars[7] != 0.0;
         return rc;
     }
     int build() {
@@ -1707,6 +1718,7 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     }
     H.ar = allreduce;
     H.ar_user = allreduce_user;
+    H.stop_flag = stop;
     if (H.arena) {
         BaArena& A = *H.arena;
         if (!A.stream) CORB_CUDA(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
@@ -1969,16 +1981,14 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         H.band_wmax = wmax;
         const size_t idx = (size_t)2 * H.n_band * sizeof(int);
         H.band_idx_bytes = (3 * wmax + 1) * 36 * sizeof(double) + idx <= 180 * 1024 ? idx : 0;
-        CORB_CUDA(cudaFuncSetAttribute(k_ba_border_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (3 * wmax + 1) * 36 * (int)sizeof(double) + (int)H.band_idx_bytes));
-        CORB_CUDA(cudaFuncSetAttribute(k_ba_band_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (wmax + 1) * (6 + 72) * (int)sizeof(double) + (int)H.band_idx_bytes));
+        CORB_SMEM_OPT_IN(k_ba_border_rows);
+        CORB_SMEM_OPT_IN(k_ba_band_backward);
         const size_t nbord = (size_t)(Pf - H.n_band);
         const size_t dense_bytes = ((nbord + 1) * 36 + nbord * 6 + nbord * 36 + (size_t)32 * kDenseU * 36) * sizeof(double);
         H.border_dense_bytes = dense_bytes;
         H.border_dense_ok = nbord > 0 && dense_bytes <= 200 * 1024;
         if (H.border_dense_ok)
-            CORB_CUDA(cudaFuncSetAttribute(k_ba_border_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(dense_bytes, 1024)));
+            CORB_SMEM_OPT_IN(k_ba_border_dense);
     }
     // the same lists without the border rows in the band columns: the band sweep of the bordered solve
     std::vector<int> coloff_b(Pf + 1, 0), col_rows_b(col_rows.size());
@@ -2002,7 +2012,7 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             H.stage_nnz_b = Pf ? coloff_b[Pf] : 0;
             H.stage_bytes_b = idx_bytes;
         }
-        CORB_CUDA(cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lact_bytes + H.stage_bytes_b)));
+        CORB_SMEM_OPT_IN(k_ba_solve);
         res->max_active_rows = max_nact;
     }
     H.s_doubles = (size_t)nblocks * 36;
@@ -2048,7 +2058,7 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     lap("uploads + allocations");
     res->ms_setup = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     // ---- Levenberg-Marquardt (optimization_algorithm_levenberg.cpp:61-164, sparse_optimizer.cpp:354-419)
-    auto terminate = [&]() { return stop && *stop; };
+    auto terminate = [&]() { return H.stop_requested(); };
     double lambda = -1, ni = 2;
     int nBad = 0, it = 0;
     bool ok = true;
@@ -2057,6 +2067,10 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         if ((rc = H.chi2(&currentChi)) != CORB_OK) return rc;
         const double iniChi = currentChi;
         if (it == 0) res->chi2_initial = currentChi;
+        if (H.ar && terminate()) {  // the ranks agreed on the flag in the reduction above (first poll of a sharded solve)
+            if (it == 0) res->chi2_final = currentChi;
+            break;
+        }
         if ((rc = H.build()) != CORB_OK) return rc;
         if (it == 0) {
             if ((rc = H.lambda_init(&lambda)) != CORB_OK) return rc;

@@ -1,5 +1,6 @@
 // Shared host/device helpers for libcorb_b200 (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -19,6 +20,25 @@ const char* get_error();
             corb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
             return CORB_ERR_CUDA;                                                                   \
         }                                                                                           \
+    } while (0)
+
+// The dynamic shared memory limit of a kernel is global per (function, device). It is raised ONCE per device to the opt-in
+// maximum (minus the kernel's static shared memory), never to a call's exact requirement: two concurrent calls with different
+// sizes could otherwise lower the limit between another call's set and its launch.
+#define CORB_SMEM_OPT_IN(kernel)                                                                                       \
+    do {                                                                                                               \
+        static std::atomic<unsigned long long> _done{0};                                                              \
+        int _dev = 0;                                                                                                  \
+        CORB_CUDA(cudaGetDevice(&_dev));                                                                               \
+        const unsigned long long _bit = 1ull << (_dev & 63);                                                           \
+        if (!(_done.load(std::memory_order_acquire) & _bit)) {                                                         \
+            int _max = 0;                                                                                              \
+            cudaFuncAttributes _fa;                                                                                    \
+            CORB_CUDA(cudaDeviceGetAttribute(&_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, _dev));                   \
+            CORB_CUDA(cudaFuncGetAttributes(&_fa, kernel));                                                            \
+            CORB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, _max - (int)_fa.sharedSizeBytes)); \
+            _done.fetch_or(_bit, std::memory_order_release);                                                           \
+        }                                                                                                              \
     } while (0)
 
 #define CORB_CHECK(cond, code, ...)         \

@@ -430,7 +430,7 @@ static int run_projection(corb_matcher* m, const corb_frame_view* f, int variant
         W.cand = (uint2*)(d + oCand); W.ncand = (int*)(d + oNc); W.ev_idx = (int*)(d + oEvI); W.ev_bin = (int*)(d + oEvB);
         W.match = (int*)(d + oOut); W.nmatches = (int*)(d + oMisc); W.overflow = W.nmatches + 1; W.K = K;
         const size_t sm1 = (size_t)8 * K * sizeof(uint2);
-        if (sm1 > 48 * 1024) CORB_CUDA(cudaFuncSetAttribute(k_proj_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+        if (sm1 > 48 * 1024) CORB_SMEM_OPT_IN(k_proj_candidates);
 #ifdef CORB_PROJ_TRACE
         cudaEventRecord(e1, st);
 #endif
@@ -441,7 +441,7 @@ static int run_projection(corb_matcher* m, const corb_frame_view* f, int variant
         CORB_CHECK(n <= 128 * 1024, CORB_ERR_UNSUPPORTED, "frame with %d features", n);
         const int stage_angle = n <= 24 * 1024;
         const size_t sm2 = (size_t)((n + 15) & ~15) + (stage_angle ? 4 * (size_t)n : 0) + 16;
-        CORB_CUDA(cudaFuncSetAttribute(k_proj_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm2, 1024)));
+        CORB_SMEM_OPT_IN(k_proj_resolve);
         k_proj_resolve<<<1, 256, sm2, st>>>(F, Q, W, stage_angle);
         CORB_CUDA(cudaGetLastError());
 #ifdef CORB_PROJ_TRACE

@@ -23,18 +23,23 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
 
 
-def torch_allreduce(group=None):
-    """All-reduce callback backed by torch.distributed (NCCL over NVLink on the GPU box)."""
+def torch_allreduce(group=None, device=None):
+    """All-reduce callback backed by torch.distributed (NCCL over NVLink on the GPU box). `device`: the CUDA device index
+    corb_ba_solve runs on (default: torch's current device at the time this is called)."""
     import torch
     import torch.distributed as dist
     ops = {0: dist.ReduceOp.SUM, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX}
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
 
     def _cb(user, d_buf, n, op, stream):
         try:
-            t = torch.as_tensor(_DevArray(d_buf, n), device="cuda")
-            s = torch.cuda.ExternalStream(stream)
-            with torch.cuda.stream(s):
-                dist.all_reduce(t, op=ops[op], group=group)
+            with torch.cuda.device(dev):
+                t = torch.as_tensor(_DevArray(d_buf, n), device=dev)
+                if t.data_ptr() != d_buf:  # a silent copy would leave the solver's own buffer unreduced
+                    raise RuntimeError("the all-reduce buffer was copied (device mismatch)")
+                s = torch.cuda.ExternalStream(stream, device=dev)
+                with torch.cuda.stream(s):
+                    dist.all_reduce(t, op=ops[op], group=group)
             return 0
         except Exception as e:  # never let an exception cross the C boundary
             print("corb all-reduce callback failed:", repr(e))

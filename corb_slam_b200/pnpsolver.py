@@ -5,8 +5,15 @@ MapFusion.cpp:720-728 iterate every candidate's solver in turn - here all candid
 
 The reference draws its minimal sets with DUtils::Random::RandomInt, i.e. from the process-global rand() stream
 (Random.cpp:47-50). The mirror does the same by default (glibc rand() through ctypes) and hands the draws to the
-library, which makes the GPU result a pure function of its arguments; pass `rand=` to supply another source."""
+library, which makes the GPU result a pure function of its arguments; pass `rand=` to supply another source.
+
+Deviation in how much of the rand() stream is consumed: the first iterate() of a solver draws 4 values for EVERY iteration
+up to max(mRansacMaxIts, done + nIterations), because the whole batch is evaluated at once; the reference draws 4 per
+iteration it actually executes and stops at the first successful Refine(). A single solver sees exactly the reference's
+draws (tests/test_ref_gpu.py); with several candidates in one process (Tracking.cc:1432, MapFusion.cpp:720) every solver
+after the first starts further down the stream than it would in the reference - still a valid RANSAC, not the same one."""
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -30,15 +37,21 @@ def random_int(lo, hi, rand=_glibc_rand):
     return int((float(rand()) / (float(RAND_MAX) + 1.0)) * d) + lo
 
 
-_matchers = {}
+_tls = threading.local()
 
 
 def _matcher(device):
-    h = _matchers.get(device)
+    """One corb_matcher handle per (thread, device): a handle owns a stream and the staging arena of corb_pnp_iterate_batch and
+    must not be used from two threads at once (include/corb_b200.h), while the reference runs PnPsolver::iterate concurrently
+    from Tracking::Relocalization and the server's MapFusion thread; ctypes releases the GIL during the call."""
+    handles = getattr(_tls, "handles", None)
+    if handles is None:
+        handles = _tls.handles = {}
+    h = handles.get(device)
     if h is None:
         h = C.c_void_p()
         check(lib().corb_matcher_create(int(device), C.byref(h)))
-        _matchers[device] = h
+        handles[device] = h
     return h
 
 

@@ -375,7 +375,9 @@ typedef int (*corb_allreduce_fn)(void* user, double* d_buf, size_t n, int op, vo
  * BlockSolver_6_3 + Levenberg-Marquardt [block_solver.hpp:354-604, optimization_algorithm_levenberg.cpp:61-189] on the
  * GPU. `stop` (nullable) is polled before every iteration and LM trial like g2o's forceStopFlag. robust != 0 adds the
  * Huber kernels of Optimizer.cc:101-102,155-160,179-184. With allreduce != NULL the problem holds this rank's landmark
- * shard (all poses, a subset of points and their edges) and every rank ends with identical poses. */
+ * shard (all poses, a subset of points and their edges) and every rank ends with identical poses; the stop decision is then
+ * collective: each rank's flag is sampled where chi2 is reduced and summed over the ranks next to it, and only the reduced
+ * value is branched on, so ranks that see the flag at different times still leave the loop together. */
 CORB_API int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile uint8_t* stop, int robust, int device,
                            corb_ba_result* result, corb_allreduce_fn allreduce, void* allreduce_user);
 

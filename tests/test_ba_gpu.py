@@ -65,12 +65,41 @@ def test_ba_free_gauge_and_rejected_steps():
     prob = ba_problem(15, 800, seed=9, n_fusion=0)
     prob["pose_fixed"][:] = 0
     _check(prob, iters=5, rms_tol=1e-4)
-    # a badly perturbed start provokes rejected trials; the accept/reject sequence must still agree
+    # a badly perturbed start (every trial is still accepted: Gauss-Newton steps on a consistent problem keep reducing chi2)
     prob = ba_problem(15, 800, seed=11, n_fusion=0)
     rng = np.random.default_rng(1)
     prob["point_xyz"] += rng.normal(0, 1.5, prob["point_xyz"].shape)
     prob["pose_t"][1:] += rng.normal(0, 0.8, prob["pose_t"][1:].shape)
     o_info, g_info, _ = _check(prob, iters=10, rms_tol=1e-3)
+
+
+def _with_gross_outliers(prob, seed, fraction=0.2, sigma=300.0):
+    """Wrong data associations: `fraction` of the observations are off by hundreds of pixels. The problem is inconsistent, chi2
+    is noise dominated and LM REJECTS trials (rho < 0, lambda *= nu, nu *= 2) - the only way found to make the
+    accept/reject gate non-trivial (perturbing the start alone never produced a rejection, at any size)."""
+    p = dict(prob)
+    p["edge_obs"] = prob["edge_obs"].copy()
+    rng = np.random.default_rng(seed)
+    bad = rng.choice(len(p["edge_obs"]), int(len(p["edge_obs"]) * fraction), replace=False)
+    p["edge_obs"][bad, :2] += rng.normal(0, sigma, (len(bad), 2))
+    return p
+
+
+@pytest.mark.parametrize("stereo_fraction,robust", [(0.0, False), (0.8, False), (0.8, True)])
+def test_ba_rejected_trials_sequence_is_identical(stereo_fraction, robust):
+    prob = _with_gross_outliers(ba_problem(60, 3000, seed=11, n_fusion=0, stereo_fraction=stereo_fraction), 1)
+    o_info, g_info, _ = _check(prob, iters=10, robust=robust, rms_tol=1e-3)
+    assert 0 in o_info["trial_accepted"] and 1 in o_info["trial_accepted"] and o_info["n_trials"] > o_info["iterations"]
+
+
+def test_ba_headline_size_with_rejected_trials():
+    """The bench problem (P = 2000 keyframes, L = 200 k landmarks, ~1 M observations, BASELINE.json config 5) against the
+    oracle: once as the bench runs it, once with gross outliers so that trials are rejected at this size too."""
+    prob = ba_problem(2000, 200000, seed=7)
+    o_info, g_info, rms = _check(prob, iters=10)
+    assert rms < 1.1 and g_info["band_chunks"] > 1
+    o_info, g_info, _ = _check(_with_gross_outliers(prob, 3), iters=10, rms_tol=1e-3)
+    assert 0 in o_info["trial_accepted"] and o_info["n_trials"] > o_info["iterations"]
 
 
 def test_ba_stop_flag_and_degenerate_inputs():
