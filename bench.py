@@ -4,15 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One process per GPU (torchrun for N > 1); every rank is one `corbslam_client` stream pinned to its GPU (replicas:
-frames of different robots are independent, SURVEY.md §8e), so scaling is weak and there is no data-path collective.
-A step = one stereo frame through ORBextractor::operator() for the left and the right image (Frame.cc:78-81).
+frames of different robots are independent, SURVEY.md section 8e), so scaling is weak and there is no data-path collective.
+A STEP = FRAMES_PER_STEP (64) stereo frames, in both arms; a frame = ORBextractor::operator() on the left and the right
+image (Frame.cc:78-81). The client keeps two frames in flight (two handle pairs, corb_orb_extract_pair_submit/_wait):
+frame i + 1 is extracted while the tracking thread would consume frame i.
 
-  value : frames/s with both images already resident in HBM and results left in HBM (CUDA-event timed per step,
-          L2 flushed between steps, max over ranks)
-  e2e   : frames/s through the reference-facing C-ABI call with HOST buffers (H2D image, D2H keypoints+descriptors
-          inside the timed region, wall clock)
-  --impl reference : the CPU oracle port of the reference path (the reference itself cannot be built here: no
-          OpenCV/Eigen/ROS), left and right image on two threads per client like Frame.cc:78-81.
+  value : frames/s with the images already resident in HBM (a pool of 160 distinct stereo pairs = 149 MB, larger than the
+          126 MB L2, walked cyclically; L2 also flushed between steps) and results left in HBM; CUDA events around every
+          step on the extractor streams, max over ranks
+  e2e   : frames/s through the reference-facing C-ABI calls with HOST buffers (page-locked images read over PCIe, keypoints +
+          descriptors back to the host, inside the timed region; wall clock)
+  roofline : the whole stereo frame against the measured HBM copy bandwidth (algorithmic bytes of SURVEY.md section 8d), plus
+          the per-kernel table with each kernel's own algorithmic bytes and its duration measured live (CUDA events) and
+          in the committed ncu capture (profiles/r02_*)
+  --impl reference : the reference's own ORBextractor.cc (oracle/_ref/libref.so, compiled unmodified from the reference tree;
+          the oracle port if that library was not shipped), left and right image on two threads per client like Frame.cc:78-81.
 """
 import argparse
 import json
@@ -29,8 +35,41 @@ sys.path.insert(0, ROOT)
 
 W, H = 1242, 375
 ORB_PARAMS = (2000, 1.2, 8, 20, 7)  # KITTI00-02.yaml:38-51
-N_POOL = 8  # distinct synthetic frames cycled through
-ALGO_BYTES_PER_IMAGE = W * H + 1441432 + 60 * 2000  # SURVEY.md §8d: input + pyramid + 60 B per keypoint (K = 2000)
+N_BASE = 16           # distinct synthetic scenes ...
+N_POOL = 160          # ... shifted into 160 distinct stereo pairs: 160 x 2 x 465 750 B = 149 MB > 126 MB of L2
+FRAMES_PER_STEP = 64  # one step = 64 stereo frames, in both arms
+ALGO_BYTES_PER_IMAGE = W * H + 1441432 + 60 * 2000  # SURVEY.md section 8d: input + pyramid + 60 B per keypoint (K = 2000)
+WORKLOAD = "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7"
+
+
+def bench_config():
+    """The same dictionary in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "clients_per_gpu": 1, "frames_in_flight": 2,
+            "frame_pool": "%d distinct stereo pairs (%d MB, larger than L2), walked cyclically" % (N_POOL, N_POOL * 2 * W * H // 1000000),
+            "l2": "inputs larger than L2 and a 256 MiB flush between timed steps",
+            "timing": "CUDA events around every step on the extractor streams, sum over steps, max over ranks"}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def frame_pool(rank):
+    """N_POOL distinct stereo pairs: N_BASE generated scenes, each also rolled by multiples of 37 columns."""
+    from corb_slam_b200.synth import stereo_frame, frame_seed
+    base = [stereo_frame(frame_seed(i + 100 * rank)) for i in range(N_BASE)]
+    out = []
+    for k in range(N_POOL):
+        l, r = base[k % N_BASE]
+        sh = 37 * (k // N_BASE)
+        out.append((np.ascontiguousarray(np.roll(l, sh, axis=1)), np.ascontiguousarray(np.roll(r, sh, axis=1))) if sh else (l, r))
+    return out
 
 
 def peaks():
@@ -79,42 +118,89 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic(kernel_label):
-    """DRAM bytes per launch of `kernel_label` ("k_octtree[3]") from the committed ncu --set full capture of one stereo
-    frame (profiles/r01b_stereo_frame_ncu_full.csv; every launch there covers both images of the pair, so the figure is
-    halved to match the per-image algorithmic bytes). None when the capture is missing."""
+def _ncu_rows(path):
     import csv
-    path = os.path.join(ROOT, "profiles", "r01b_stereo_frame_ncu_full.csv")
     if not os.path.exists(path):
-        return None
-    base = kernel_label.split("[")[0]
-    idx = int(kernel_label.split("[")[1].rstrip("]")) if "[" in kernel_label else 0
-    if base == "k_resize":
-        idx -= 1  # levels 1..7
-    rows = list(csv.reader(open(path)))
-    hdr = rows[0]
-    rd = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum")]
-    wr = [i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum")]
-    if not rd or not wr:
-        return None
-
-    def to_bytes(v, h):
-        unit = h[h.index("[") + 1:h.index("]")] if "[" in h else "byte"
-        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-    hits = [r for r in rows[1:] if r and r[0].startswith(base)]
-    if idx >= len(hits):
-        return None
-    r = hits[idx]
-    return 0.5 * (to_bytes(r[rd[0]], hdr[rd[0]]) + to_bytes(r[wr[0]], hdr[wr[0]]))
+        return None, None
+    rows = [r for r in csv.reader(open(path)) if len(r) > 4]
+    return rows[0], rows[1:]
 
 
-def cpu_extract_fps(n_frames, clients=1, stereo=False):
-    """Oracle port of the reference path: `clients` concurrent clients, each running left/right on two threads
-    (Frame.cc:78-81); with stereo=True also Frame::ComputeStereoMatches (Frame.cc:90) on the calling thread."""
+def ncu_frame_capture():
+    """Per-kernel duration and DRAM bytes of ONE stereo frame from the committed `ncu --set full` capture
+    (profiles/r02_stereo_frame_ncu_full.csv, written by tools/summarize_ncu.py; every launch covers both images of the pair).
+    -> {kernel label: {"us": duration, "dram_bytes": read + write}} or {} when the capture is missing."""
+    hdr, rows = _ncu_rows(os.path.join(ROOT, "profiles", "r02_stereo_frame_ncu_full.csv"))
+    if hdr is None:
+        hdr, rows = _ncu_rows(os.path.join(ROOT, "profiles", "r01c_stereo_frame_ncu_full.csv"))
+    if hdr is None:
+        return {}, None
+
+    def col(prefix):
+        hits = [i for i, h in enumerate(hdr) if h.startswith(prefix)]
+        return hits[0] if hits else None
+
+    def scaled(v, h):
+        unit = h[h.index("[") + 1:h.index("]")] if "[" in h else ""
+        return float(v) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3,
+                           "msecond": 1e3}.get(unit, 1.0)
+    cd, cr, cw = col("gpu__time_duration.sum"), col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+    out, seen = {}, {}
+    for r in rows:
+        base = r[0].split("(")[0].replace("corb::", "").strip()
+        k = seen.get(base, 0)
+        seen[base] = k + 1
+        if base == "k_resize":
+            k += 1
+        label = "%s[%d]" % (base, k) if base in ("k_resize", "k_fast_cells", "k_octtree") else base
+        if label in out:
+            continue  # the first frame of the capture only
+        try:
+            out[label] = {"us": scaled(r[cd], hdr[cd]) if cd is not None else None,
+                          "dram_bytes": (scaled(r[cr], hdr[cr]) + scaled(r[cw], hdr[cw])) if cr is not None and cw is not None else None}
+        except (ValueError, IndexError):
+            pass
+    return out, "profiles/r02_stereo_frame_ncu_full.csv" if os.path.exists(os.path.join(ROOT, "profiles", "r02_stereo_frame_ncu_full.csv")) \
+        else "profiles/r01c_stereo_frame_ncu_full.csv"
+
+
+def kernel_algorithmic_bytes(ex, counts):
+    """Each kernel's OWN algorithmic bytes for one image. counts: per-level (candidates, kept)."""
+    sizes = [ex.level_size(l, W, H) for l in range(ex.nlevels)]
+    px = [w * h for w, h in sizes]
+    out = {"k_import": 2 * px[0], "k_blur": 2 * sum(px), "k_orient_desc": sum(k for _, k in counts) * (961 + 512 + 60)}
+    for l in range(ex.nlevels):
+        if l:
+            out["k_resize[%d]" % l] = px[l - 1] + px[l]
+        out["k_fast_cells[%d]" % l] = px[l] + 8 * counts[l][0]
+        out["k_octtree[%d]" % l] = 8 * (counts[l][0] + counts[l][1])
+    return out
+
+
+def reference_extractors(n):
+    """`n` (left, right) extractor pairs of the CPU arm: the reference's own ORBextractor.cc when oracle/_ref/libref.so is
+    there ("reference"), else the oracle port ("port")."""
+    from oracle import ref
+    if ref.available():
+        return [(ref.ORBextractor(*ORB_PARAMS), ref.ORBextractor(*ORB_PARAMS)) for _ in range(n)], "reference"
     import oracle
+    return [(oracle.OrbExtractor(*ORB_PARAMS), oracle.OrbExtractor(*ORB_PARAMS)) for _ in range(n)], "port"
+
+
+def cpu_extract_fps(n_frames, clients=1, stereo=False, exs=None):
+    """The reference path on the host cores: `clients` concurrent clients, each running left / right on two threads
+    (Frame.cc:78-81); with stereo=True also Frame::ComputeStereoMatches (Frame.cc:90) on the calling thread (oracle port).
+    -> (frames/s, seconds, kind)."""
     from corb_slam_b200.synth import stereo_frame, frame_seed
-    frames = [stereo_frame(frame_seed(i)) for i in range(min(n_frames, N_POOL))]
-    exs = [(oracle.OrbExtractor(*ORB_PARAMS), oracle.OrbExtractor(*ORB_PARAMS)) for _ in range(clients)]
+    frames = [stereo_frame(frame_seed(i)) for i in range(min(n_frames, N_BASE))]
+    kind = "port"
+    if stereo:
+        import oracle
+        exs = [(oracle.OrbExtractor(*ORB_PARAMS), oracle.OrbExtractor(*ORB_PARAMS)) for _ in range(clients)]
+    elif exs is None:
+        exs, kind = reference_extractors(clients)
+    else:
+        exs, kind = exs
     for exl, exr in exs:
         exl(frames[0][0]); exr(frames[0][1])
 
@@ -137,7 +223,7 @@ def cpu_extract_fps(n_frames, clients=1, stereo=False):
     for t in ths:
         t.join()
     dt = time.perf_counter() - t0
-    return clients * n_frames / dt, dt
+    return clients * n_frames / dt, dt, kind
 
 
 BA_P, BA_L, BA_ITERS = 2000, 200000, 10  # SURVEY.md §8d / BASELINE.json config #5 synthetic global-BA problem
@@ -164,40 +250,70 @@ def cpu_ba(n_poses, n_points):
             "iterations": info["iterations"], "chi2_final": info["chi2_final"], "rms_px": B.chi2(out)[1]}
 
 
-def matcher_workload(seed=3, n_feat=2000, n_cand=32):
-    """Synthetic matching/BoW workload: a k=10, L=5 vocabulary (111 110 nodes), one query frame of
-    2000 descriptors and `n_cand` candidate keyframes that are noisy re-observations of it."""
-    import oracle
-    from oracle import _match_bind as M
-    oracle.lib()
-    spec = M.random_vocabulary(10, 5, seed)
-    rng = np.random.default_rng(seed)
-    base = rng.integers(0, 256, (n_feat, 32), dtype=np.uint8)
+def vocabulary_text(stripped=False):
+    """The reference's ORBvoc.txt (corbslam_client/Vocabulary/ORBvoc.txt.tar.gz; a copy travels in oracle/_ref/), untarred once
+    into a temp directory. stripped: without the trailing newline (what the reference's own loader needs, see oracle/ref.py)."""
+    import tarfile
+    import tempfile
+    cache = os.path.join(tempfile.gettempdir(), "corb_voc_%d" % os.getuid())
+    full = os.path.join(cache, "ORBvoc.txt")
+    if not os.path.exists(full):
+        src = [q for q in (os.path.join(ROOT, "oracle", "_ref", "ORBvoc.txt.tar.gz"),
+                           "/root/reference/corbslam_client/Vocabulary/ORBvoc.txt.tar.gz") if os.path.exists(q)]
+        if not src:
+            return None
+        os.makedirs(cache, exist_ok=True)
+        with tarfile.open(src[0]) as t:
+            t.extract("ORBvoc.txt", cache + ".tmp", filter="data")
+        os.replace(os.path.join(cache + ".tmp", "ORBvoc.txt"), full)
+    if not stripped:
+        return full
+    cut = os.path.join(cache, "ORBvoc_stripped.txt")
+    if not os.path.exists(cut):
+        data = open(full, "rb").read().rstrip()
+        with open(cut + ".tmp", "wb") as f:
+            f.write(data)
+        os.replace(cut + ".tmp", cut)
+    return cut
+
+
+def matcher_workload(device, n_cand=32):
+    """Matching / BoW workload on the REAL vocabulary: the query is a bench frame, the `n_cand` candidate keyframes are the
+    same scene seen again (shifted by a few pixels, sensor noise) - descriptors extracted by the GPU extractor."""
+    from corb_slam_b200 import ORBextractor
+    from corb_slam_b200.synth import stereo_frame, frame_seed
+    ex = ORBextractor(*ORB_PARAMS, device=device)
+    base = stereo_frame(frame_seed(0))[0]
+    rng = np.random.default_rng(3)
+    q = tuple(a.copy() for a in ex(base))
     cands = []
     for c in range(n_cand):
-        d = base[rng.permutation(n_feat)].copy()
-        flips = rng.integers(0, 256, (n_feat, 6))
-        for j in range(6):
-            d[np.arange(n_feat), flips[:, j] >> 3] ^= (1 << (flips[:, j] & 7)).astype(np.uint8)
-        cands.append(d)
-    return spec, base, cands
+        img = np.roll(base, int(rng.integers(-12, 13)), axis=1).astype(np.int16) + rng.normal(0, 2.5, base.shape).round().astype(np.int16)
+        cands.append(tuple(a.copy() for a in ex(img.clip(0, 255).astype(np.uint8))))
+    ex.close()
+    return q, cands
 
 
 def bench_matcher(device, with_cpu=True):
     """Calls/s and Hamming pairs/s of SearchByBoW (batched over candidates), descriptors/s of the vocabulary descent,
-    scores/s of the L1 BoW score; each beside the oracle port on one host thread."""
-    import oracle
-    from oracle import _match_bind as M
+    scores/s of the L1 BoW score on ORBvoc.txt (k = 10, L = 6, 1 082 073 nodes, levelsup = 4 as Frame.cc:404); each beside the
+    reference's own DBoW2 / ORBmatcher.cc (oracle/_ref) on one host thread."""
     from corb_slam_b200 import BowFeatures, ORBmatcher, ORBVocabulary
-    spec, base, cands = matcher_workload()
-    gvoc = ORBVocabulary.from_arrays(*spec, device=device)
-    ovoc = M.Vocabulary.from_arrays(*spec)
-    levelsup = 3  # L - 3 = level 2 nodes -> 100 groups, like ORBvoc (L = 6, levelsup = 4)
+    path = vocabulary_text()
+    if path is None:
+        return {"unavailable": "ORBvoc.txt.tar.gz was not shipped (oracle/_ref/)"}
+    (qk, base), cand_kd = matcher_workload(device)
+    cands = [d for _, d in cand_kd]
+    gvoc = ORBVocabulary(device=device)
+    t0 = time.perf_counter()
+    if not gvoc.loadFromTextFile(path):
+        return {"unavailable": "corb_voc_load_text failed"}
+    load_s = time.perf_counter() - t0
+    levelsup = 4
     n = len(base)
     rng = np.random.default_rng(0)
-    ang = rng.uniform(0, 360, n).astype(np.float32)
-    valid = (rng.random(n) < 0.7).astype(np.uint8)
-    out = {}
+    ang = qk["angle"]
+    out = {"vocabulary": {"k": gvoc.k, "L": gvoc.L, "nodes": gvoc.n_nodes, "words": gvoc.n_words, "load_s": load_s}}
     # ---- transform (voc->transform, Frame.cc:404)
     gvoc.transform(base, levelsup)
     reps = 20
@@ -205,11 +321,14 @@ def bench_matcher(device, with_cpu=True):
     for _ in range(reps):
         qb = gvoc.transform(base, levelsup)
     dt = (time.perf_counter() - t0) / reps
-    out["transform"] = {"descriptors_per_s": n / dt, "ms_per_call": dt * 1e3}
+    out["transform"] = {"descriptors_per_s": n / dt, "ms_per_call": dt * 1e3, "descriptors": n,
+                        "roofline": {"bound": "hbm", "algorithmic_bytes": 48 * n, "achieved": 48 * n / dt / 1e9, "unit": "GB/s",
+                                     "note": "32 B in + 16 B out per descriptor (SURVEY.md section 8d); the call is host-overhead bound"}}
     cb = [gvoc.transform(c, levelsup) for c in cands]
     # ---- SearchByBoW, batched over candidates (MapFusion.cpp:691 / Tracking.cc:1405)
     m = ORBmatcher(0.75, True, device=device)
-    A = [BowFeatures(c, b[2], b[3], b[4], valid=valid, angles=ang) for c, b in zip(cands, cb)]
+    valids = [(rng.random(len(c)) < 0.7).astype(np.uint8) for c in cands]
+    A = [BowFeatures(c, b[2], b[3], b[4], valid=v, angles=k["angle"]) for (k, c), b, v in zip(cand_kd, cb, valids)]
     B = [BowFeatures(base, qb[2], qb[3], qb[4], angles=ang) for _ in cands]
     pairs = 0
     for a_, b_ in zip(cb, [qb] * len(cb)):  # Hamming evaluations = sum over common nodes of nA * nB
@@ -220,8 +339,11 @@ def bench_matcher(device, with_cpu=True):
     for _ in range(reps):
         res = m.SearchByBoWBatch(0, A, B)
     dt = (time.perf_counter() - t0) / reps
+    bow_bytes = sum(36 * (len(c) + n) + 4 * n for c in cands)
     out["search_by_bow"] = {"calls_per_s": len(A) / dt, "hamming_pairs_per_s": pairs / dt, "ms_per_batch": dt * 1e3,
-                            "batch": len(A), "matches_per_call": float(np.mean([r[1] for r in res]))}
+                            "batch": len(A), "matches_per_call": float(np.mean([r[1] for r in res])),
+                            "roofline": {"bound": "hbm", "algorithmic_bytes": bow_bytes, "achieved": bow_bytes / dt / 1e9, "unit": "GB/s",
+                                         "note": "36 (N_A + N_B) + 4 N_out bytes per call (SURVEY.md section 8d)"}}
     # ---- L1 score, one query against all candidates (KeyFrameDatabase.cc:238)
     cvecs = [(b[0], b[1]) for b in cb] * 8
     gvoc.score_batch((qb[0], qb[1]), cvecs)
@@ -231,22 +353,34 @@ def bench_matcher(device, with_cpu=True):
     dt = (time.perf_counter() - t0) / reps
     out["l1_score"] = {"scores_per_s": len(cvecs) / dt, "ms_per_batch": dt * 1e3, "batch": len(cvecs)}
     if with_cpu:
-        t0 = time.perf_counter(); oq = ovoc.transform(base, levelsup); dt = time.perf_counter() - t0
+        from oracle import ref
+        from oracle import _match_bind as M
+        if ref.available():
+            rvoc = ref.ORBVocabulary(vocabulary_text(stripped=True))
+            cpu_transform, cpu_score, cpu_bow, kind = rvoc.transform, rvoc.score, ref.search_by_bow, "reference"
+        else:
+            import oracle
+            oracle.lib()
+            ovoc = M.Vocabulary.load_text(path)
+            cpu_transform, cpu_score, cpu_bow, kind = ovoc.transform, M.Vocabulary.score, M.search_by_bow, "port"
+        t0 = time.perf_counter(); oq = cpu_transform(base, levelsup); dt = time.perf_counter() - t0
+        assert all(x.tobytes() == y.tobytes() for x, y in zip(oq, qb)), "transform differs from the CPU reference"
         out["transform"]["cpu_descriptors_per_s"] = n / dt
-        oA = [M.Side(c, b[2], b[3], b[4], valid=valid, angles=ang) for c, b in zip(cands, cb)]
+        oA = [M.Side(c, b[2], b[3], b[4], valid=v, angles=k["angle"]) for (k, c), b, v in zip(cand_kd, cb, valids)]
         oB = M.Side(base, qb[2], qb[3], qb[4], angles=ang)
         t0 = time.perf_counter()
-        for a_ in oA:
-            M.search_by_bow(0, a_, oB, 0.75, True)
+        cres = [cpu_bow(0, a_, oB, 0.75, True) for a_ in oA]
         dt = time.perf_counter() - t0
+        assert all(g[1] == c[1] and np.array_equal(g[0], c[0]) for g, c in zip(res, cres)), "SearchByBoW differs from the CPU reference"
         out["search_by_bow"]["cpu_calls_per_s"] = len(oA) / dt
         out["search_by_bow"]["cpu_hamming_pairs_per_s"] = pairs / dt
         t0 = time.perf_counter()
-        for c in cvecs:
-            M.bow_score_l1(qb[0], qb[1], c[0], c[1])
+        csc = [cpu_score((qb[0], qb[1]), c) for c in cvecs]
         dt = time.perf_counter() - t0
+        assert np.asarray(csc).tobytes() == np.asarray(sc).tobytes(), "L1 scores differ from the CPU reference"
         out["l1_score"]["cpu_scores_per_s"] = len(cvecs) / dt
-        out["cpu"] = "oracle port, 1 thread (includes the ctypes call overhead of one call per candidate)"
+        out["cpu"] = {"kind": kind, "threads": 1,
+                      "note": "the reference's own DBoW2 / ORBmatcher.cc (oracle/_ref/libref.so)" if kind == "reference" else "oracle port"}
     # ---- SearchByProjection (TrackWithMotionModel / SearchLocalPoints: every tracked frame)
     from corb_slam_b200 import FrameView
     from corb_slam_b200.synth import projection_scene
@@ -284,7 +418,7 @@ def bench_matcher(device, with_cpu=True):
         out["search_by_projection"]["cpu_map_points_calls_per_s"] = reps / (t2 - t1)
     pm.close()
     out["pnp_ransac"] = bench_pnp(device, with_cpu)
-    out["workload"] = "k=10 L=5 synthetic vocabulary, 2000 descriptors per frame, 32 candidate keyframes, level-2 node groups"
+    out["workload"] = "ORBvoc.txt (k=10, L=6, 1 082 073 nodes, levelsup 4), %d descriptors of a bench frame, 32 candidate keyframes = the scene seen again" % n
     m.close(); gvoc.close()
     return out
 
@@ -362,27 +496,24 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.gpus
-    total = 0.0
-    t_all = 0.0
-    per_step = max(4, min(32, args.sample_frames // max(1, args.steps)))
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_extract_fps(2, clients=n)
-    t0 = time.perf_counter()
-    frames = 0
+    exs = reference_extractors(n)
+    cpu_extract_fps(2, clients=n, exs=exs)  # warm-up
+    t_all, frames, per = 0.0, 0, []
     for _ in range(args.steps):
-        fps, dt = cpu_extract_fps(per_step, clients=n)
-        frames += n * per_step
+        fps, dt, kind = cpu_extract_fps(FRAMES_PER_STEP, clients=n, exs=exs)
+        frames += n * FRAMES_PER_STEP
         t_all += dt
+        per.append(dt)
     fps = frames / t_all
     line = {
         "impl": "reference", "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": n,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7",
-                   "clients": n, "frames_per_step": per_step},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 2 * n, "kind": "port",
-                         "sample": "%d stereo frames per client, %d client(s), L/R on two threads each (Frame.cc:78-81); "
-                                   "oracle port because the reference needs OpenCV/Eigen/ROS to build" % (per_step * args.steps, n),
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": bench_config(),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 2 * n, "kind": kind, "cpu_model": cpu_model(),
+                         "sample": "%d steps x %d stereo frames per client, %d client(s), L/R on two threads each (Frame.cc:78-81); %s"
+                                   % (args.steps, FRAMES_PER_STEP, n,
+                                      "the reference's own ORBextractor.cc compiled unmodified (oracle/_ref/libref.so)" if kind == "reference"
+                                      else "oracle port (oracle/_ref/libref.so was not shipped)"),
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -394,8 +525,8 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from corb_slam_b200 import ORBextractor, extract_stereo, extract_stereo_device, frame_stereo
-    from corb_slam_b200.synth import stereo_frame, frame_seed
+    from corb_slam_b200 import (ORBextractor, extract_stereo, extract_stereo_device, extract_stereo_submit, extract_stereo_wait,
+                                frame_stereo_submit, frame_stereo_wait)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -411,39 +542,55 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    exl = ORBextractor(*ORB_PARAMS, device=local)
-    exr = ORBextractor(*ORB_PARAMS, device=local)
-    exl.copy_outputs = exr.copy_outputs = False
-    frames = [stereo_frame(frame_seed(i + 100 * rank)) for i in range(N_POOL)]
+    # two handle pairs = two stereo frames in flight
+    pairs = [(ORBextractor(*ORB_PARAMS, device=local), ORBextractor(*ORB_PARAMS, device=local)) for _ in range(2)]
+    for a_, b_ in pairs:
+        a_.copy_outputs = b_.copy_outputs = False
+    exl, exr = pairs[0]
+    frames = frame_pool(rank)
     pinned = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()) for l, r in frames]
     dev = [(a.cuda(), b.cuda()) for a, b in pinned]
     npin = [(a.numpy(), b.numpy()) for a, b in pinned]  # numpy views of the page-locked frames
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    sl = torch.cuda.ExternalStream(exl.stream())
-    sr = torch.cuda.ExternalStream(exr.stream())
+    streams = [torch.cuda.ExternalStream(p_[0].stream()) for p_ in pairs]  # a pair runs on its left handle's stream
+    F = FRAMES_PER_STEP
+    mbf, mb = 386.1448, 386.1448 / 718.856
 
-    def step_device(i, ev0=None, ev1=None):
-        l, r = dev[i % N_POOL]
-        if ev0 is not None:
-            ev0.record(sl)
-            sr.wait_event(ev0)
-        extract_stereo_device(exl, exr, l.data_ptr(), r.data_ptr(), W, H, W)
-        if ev1 is not None:
-            evr = torch.cuda.Event()
-            evr.record(sr)
-            sl.wait_event(evr)
-            ev1.record(sl)
+    def step_device(step, ev0, ev1):
+        """F stereo frames, alternating between the two handle pairs; events bracket the whole step on both streams."""
+        ev0.record(streams[0])
+        streams[1].wait_event(ev0)
+        for f in range(F):
+            i = (step * F + f) % N_POOL
+            a_, b_ = pairs[f & 1]
+            extract_stereo_device(a_, b_, dev[i][0].data_ptr(), dev[i][1].data_ptr(), W, H, W)
+        evb = torch.cuda.Event()
+        evb.record(streams[1])
+        streams[0].wait_event(evb)
+        ev1.record(streams[0])
 
-    def step_host(i, pyr=False):
-        l, r = pinned[i % N_POOL]
-        return extract_stereo(exl, exr, npin[i % N_POOL][0], npin[i % N_POOL][1], want_pyramid=pyr)
+    def step_host(step, submit, wait):
+        """F stereo frames through the split C-ABI calls from this one thread, two in flight; returns keypoints seen."""
+        nk = 0
+        base = step * F
+        submit(*pairs[0], *npin[base % N_POOL])
+        for f in range(F):
+            if f + 1 < F:
+                submit(*pairs[(f + 1) & 1], *npin[(base + f + 1) % N_POOL])
+            res = wait(*pairs[f & 1])
+            nk += len(res[0][0]) + len(res[1][0])
+        return nk
 
-    # ---- warm-up
-    for i in range(max(args.warmup, 3)):
-        step_device(i)
-        exl.sync(); exr.sync()
-        step_host(i)
-    # ---- HBM-resident throughput: per-step CUDA events, L2 flushed between steps
+    sub_frame = lambda a_, b_, l, r: frame_stereo_submit(a_, b_, l, r, mbf, mb)
+    # ---- warm-up (plans, graphs, page-locked buffers of both pairs)
+    for w_ in range(max(args.warmup, 3)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_device(w_, e0, e1)
+        torch.cuda.synchronize()
+    step_host(0, extract_stereo_submit, extract_stereo_wait)
+    step_host(0, sub_frame, frame_stereo_wait)
+    extract_stereo(exl, exr, *npin[0])
+    # ---- HBM-resident throughput
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     evs = []
@@ -453,69 +600,58 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         step_device(i, e0, e1)
         evs.append((e0, e1))
-        exl.sync(); exr.sync()
+        torch.cuda.synchronize()
     barrier()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    # ---- end to end through the C ABI with host buffers (wall clock; H2D + D2H inside)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    dev_ms = sum(step_ms)
+    # ---- latency of ONE frame alone on the GPU (no second frame in flight), CUDA events per frame
+    lat = []
+    for i in range(min(200, 4 * F)):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(streams[0])
+        extract_stereo_device(exl, exr, dev[i % N_POOL][0].data_ptr(), dev[i % N_POOL][1].data_ptr(), W, H, W)
+        e1.record(streams[0])
+        torch.cuda.synchronize()
+        lat.append(1e3 * e0.elapsed_time(e1))
+    # ---- end to end through the C ABI with host buffers (wall clock; H2D + D2H inside), two frames in flight
     barrier()
     t0 = time.perf_counter()
     nk = 0
     for i in range(args.steps):
-        kl, kr = step_host(i)
-        nk += len(kl[0]) + len(kr[0])
-    torch.cuda.synchronize()
+        nk += step_host(i, extract_stereo_submit, extract_stereo_wait)
     e2e_s = time.perf_counter() - t0
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_host(i, pyr=True)
-    e2e_pyr_s = time.perf_counter() - t0
+    for i in range(args.steps):  # the same frames through the blocking call (one frame in flight)
+        for f in range(F):
+            extract_stereo(exl, exr, *npin[(i * F + f) % N_POOL])
+    e2e_block_s = time.perf_counter() - t0
     barrier()
     t0 = time.perf_counter()
     n_stereo = 0
     for i in range(args.steps):  # the stereo Frame constructor: ExtractORB x2 + ComputeStereoMatches, pyramids stay in HBM
-        fr = frame_stereo(exl, exr, npin[i % N_POOL][0], npin[i % N_POOL][1], 386.1448, 386.1448 / 718.856)
-        n_stereo += int((fr[2] >= 0).sum())
+        base = i * F
+        sub_frame(*pairs[0], *npin[base % N_POOL])
+        for f in range(F):
+            if f + 1 < F:
+                sub_frame(*pairs[(f + 1) & 1], *npin[(base + f + 1) % N_POOL])
+            fr = frame_stereo_wait(*pairs[f & 1])
+            n_stereo += int((fr[2] >= 0).sum())
     e2e_frame_s = time.perf_counter() - t0
-    # ---- several clients sharing one GPU (capacity, not the headline): C threads, each with its own handle pair,
-    #      each running the same host-buffer e2e call; ctypes releases the GIL inside the C ABI
-    multi = None
-    if args.clients_per_gpu > 1:
-        C_ = args.clients_per_gpu
-        pairs = [(ORBextractor(*ORB_PARAMS, device=local), ORBextractor(*ORB_PARAMS, device=local)) for _ in range(C_)]
-        for a_, b_ in pairs:
-            a_.copy_outputs = b_.copy_outputs = False
-            extract_stereo(a_, b_, npin[0][0], npin[0][1])
-        start = threading.Barrier(C_ + 1)
-
-        def client(idx):
-            a_, b_ = pairs[idx]
-            start.wait()
-            for i in range(args.steps):
-                extract_stereo(a_, b_, npin[(i + idx) % N_POOL][0], npin[(i + idx) % N_POOL][1])
-
-        ths = [threading.Thread(target=client, args=(c,)) for c in range(C_)]
-        [t_.start() for t_ in ths]
-        start.wait()
-        t0 = time.perf_counter()
-        [t_.join() for t_ in ths]
-        dt = time.perf_counter() - t0
-        multi = {"clients_per_gpu": C_, "value": C_ * args.steps / dt, "unit": "frames/s",
-                 "note": "aggregate e2e frames/s of %d independent clients (threads) sharing this GPU; not the headline" % C_}
-        for a_, b_ in pairs:
-            a_.close(); b_.close()
     clocks = sampler.stop() if sampler else None
+    n_frames = args.steps * F
 
     # ---- global BA (second half of the BASELINE.json metric): landmark-sharded over the ranks, reduced camera system
     #      all-reduced over NCCL from inside corb_ba_solve when more than one GPU is attached
-    ba_info, ba_ms, ba_rms, ba_edges, ba_allreduce = None, 0.0, None, 0, None
+    ba_info, ba_ms, ba_rms, ba_edges, ba_allreduce, ba_parity = None, 0.0, None, 0, None, None
     if not args.no_ba:
         from corb_slam_b200 import Optimizer, torch_allreduce
         from corb_slam_b200.synth import ba_problem, ba_shard
         prob = ba_problem(BA_P, BA_L, seed=7)
         ba_edges = len(prob["edge_pose"])
         mine = ba_shard(prob, rank, world) if world > 1 else prob
-        cb = torch_allreduce() if world > 1 else None
+        cb = torch_allreduce(device=local) if world > 1 else None
         Optimizer.BundleAdjustment(ba_shard(ba_problem(50, 2000, seed=1), rank, world) if world > 1 else ba_problem(50, 2000, seed=1),
                                    2, bRobust=False, device=local, allreduce=cb)  # warm-up (context, NCCL channels)
         # second warm-up at the measured size, one LM iteration: sizes the library's per-device memory arena, as in a
@@ -533,8 +669,28 @@ def run_ours(args):
             oracle.lib()
             ba_rms = B.chi2(ba_out)[1]  # checker only: RMS reprojection error of the GPU solution
         if world > 1:
+            # multi-GPU parity inside the driver-run bench: rank spread of the replicated poses, and on rank 0 the sharded
+            # result against the unsharded solve on one GPU (accept / reject sequence, poses, landmarks)
+            poses = torch.from_numpy(np.concatenate([ba_out["pose_q"], ba_out["pose_t"]], 1)).cuda()
+            pmax, pmin = poses.clone(), poses.clone()
+            dist.all_reduce(pmax, op=dist.ReduceOp.MAX); dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+            pts = torch.zeros((BA_L, 3), dtype=torch.float64, device="cuda")
+            pts[torch.from_numpy(mine["_point_ids"]).cuda()] = torch.from_numpy(ba_out["point_xyz"]).cuda()
+            dist.all_reduce(pts)
+            if rank == 0:
+                Optimizer.BundleAdjustment(prob, 1, bRobust=False, device=local)
+                t0 = time.perf_counter()
+                full, finfo = Optimizer.BundleAdjustment(prob, BA_ITERS, bRobust=False, device=local)
+                single_ms = (time.perf_counter() - t0) * 1e3
+                ba_parity = {"accept_sequence_equal": ba_info["trial_accepted"] == finfo["trial_accepted"],
+                             "max_abs_pose_t": float(np.abs(ba_out["pose_t"] - full["pose_t"]).max()),
+                             "max_abs_pose_q": float(np.abs(ba_out["pose_q"] - full["pose_q"]).max()),
+                             "max_abs_point": float(np.abs(pts.cpu().numpy() - full["point_xyz"]).max()),
+                             "rank_spread": float((pmax - pmin).abs().max()),
+                             "chi2_final_single": finfo["chi2_final"], "ms_single_gpu_same_run": single_ms}
+            barrier()
             # the one exchange step of the sharded BA on its own: all-reduce(sum, fp64) of [S | bschur] (36 doubles per block of
-            # the reduced camera system + 6 per pose), timed with CUDA events, against the NVLink roofline (SURVEY.md §8d)
+            # the reduced camera system + 6 per pose), timed with CUDA events, against the NVLink roofline (SURVEY.md section 8d)
             n_red = 36 * int(ba_info["reduced_blocks"]) + 6 * BA_P
             buf = torch.zeros(n_red, dtype=torch.float64, device="cuda")
             for _ in range(3):
@@ -550,62 +706,73 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ba_allreduce = {"message_bytes": 8 * n_red, "ms": float(tt.item())}
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_pyr_s * 1e3, ba_ms, e2e_frame_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_block_s * 1e3, ba_ms, e2e_frame_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_pyr_ms, ba_ms, e2e_frame_ms = [float(x) for x in t.tolist()]
+    dev_ms, e2e_ms, e2e_block_ms, ba_ms, e2e_frame_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
-        # per-kernel times of one image (eager replay with events) for the roofline of the dominant kernel
+        # per-kernel times of one image (eager replay with events between the launches) and the per-level counts
         exl.extract_device(dev[0][0].data_ptr(), W, H, W)
         exl.sync()
-        prof = exl.profile(reps=20)
-        agg = {}
-        for name, ms in prof:
-            base = name.split("[")[0]
-            agg[base] = agg.get(base, 0.0) + ms
-        top = max(prof, key=lambda kv: kv[1])  # the single longest launch (per-level launches run concurrently in the graph)
+        counts = [(len(exl.tap_candidates(l)), exl.tap_level_count(l)) for l in range(exl.nlevels)]
+        prof = dict(exl.profile(reps=20))
+        kbytes = kernel_algorithmic_bytes(exl, counts)
+        cap, cap_src = ncu_frame_capture()
         pk, pk_kind = peaks()
-        achieved = ALGO_BYTES_PER_IMAGE / (top[1] * 1e-3) / 1e9
-        fps = world * args.steps / (dev_ms * 1e-3)
-        kp_per_frame = nk / max(1, args.steps)
-        h2d = 2 * W * H
-        d2h = int(kp_per_frame * 60) + 16
-        cpu_fps, cpu_dt = cpu_extract_fps(args.sample_frames, clients=1)
-        cpu_fps_frame, _ = cpu_extract_fps(max(8, args.sample_frames // 4), clients=1, stereo=True)
+        fps = world * n_frames / (dev_ms * 1e-3)
+        kernels = {}
+        for name, nbytes in kbytes.items():
+            ent = {"algorithmic_bytes": nbytes, "ms_live": prof.get(name)}
+            if name in cap and cap[name]["us"]:
+                n_img = 2  # every launch of the capture covers both images of the pair
+                ent["us_ncu"] = cap[name]["us"]
+                ent["frac_ncu"] = n_img * nbytes / (cap[name]["us"] * 1e-6) / 1e9 / pk["hbm_gbs"]
+                ent["dram_bytes_ncu"] = cap[name]["dram_bytes"]
+            kernels[name] = ent
+        with_ncu = {k: v for k, v in kernels.items() if "us_ncu" in v}
+        dom = max(with_ncu, key=lambda k: with_ncu[k]["us_ncu"]) if with_ncu else max(prof, key=prof.get)
+        traffic = sum(v["dram_bytes_ncu"] for v in with_ncu.values() if v.get("dram_bytes_ncu")) if with_ncu else None
+        achieved = 2 * ALGO_BYTES_PER_IMAGE * (fps / world) / 1e9
+        kp_per_frame = nk / max(1, n_frames)
+        h2d = 2 * W * H * F
+        d2h = int(kp_per_frame * 60 + 16) * F
+        cpu_fps, cpu_dt, cpu_kind = cpu_extract_fps(args.sample_frames, clients=1)
+        cpu_fps_frame, _, _ = cpu_extract_fps(max(8, args.sample_frames // 4), clients=1, stereo=True)
+        lat.sort()
         line = {
             "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7",
-                       "clients_per_gpu": 1, "frame_pool": N_POOL, "l2": "flushed (256 MiB write) between timed steps",
-                       "timing": "CUDA events per step on the extractor streams, sum over steps, max over ranks"},
-            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
-                    "note": "corb_orb_extract_pair on two handles: page-locked host images in, host keypoints+descriptors out"},
-            "e2e_with_pyramid": {"value": world * args.steps / (e2e_pyr_ms * 1e-3), "unit": "frames/s",
-                                 "d2h_bytes_per_step": d2h + 2 * 1441432, "ms_per_step": e2e_pyr_ms / args.steps,
-                                 "note": "also copies mvImagePyramid to the host (needed while ComputeStereoMatches is on the CPU)"},
-            "e2e_stereo_frame": {"value": world * args.steps / (e2e_frame_ms * 1e-3), "unit": "frames/s",
-                                 "ms_per_step": e2e_frame_ms / args.steps, "stereo_matches_per_frame": n_stereo / max(1, args.steps),
-                                 "d2h_bytes_per_step": d2h + 8 * int(kp_per_frame / 2),
-                                 "note": "corb_frame_stereo: ExtractORB left+right and Frame::ComputeStereoMatches on the GPU; "
-                                         "the pyramids never leave HBM"},
-            "multi_client": multi,
-            "gpu_launches": exl.launches_per_extract() * args.steps,  # one set of launches per stereo pair (grid z = 2)
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": bench_config(),
+            "us_per_frame": {"throughput": 1e3 * dev_ms / n_frames, "step_median": 1e3 * float(np.median(step_ms)) / F,
+                             "step_p95": 1e3 * float(np.percentile(step_ms, 95)) / F,
+                             "latency_median": lat[len(lat) // 2], "latency_p95": lat[int(len(lat) * 0.95)],
+                             "note": "throughput = two frames in flight; latency = one frame alone on the GPU, CUDA events per frame"},
+            "e2e": {"value": world * n_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "us_per_frame": 1e3 * e2e_ms / n_frames,
+                    "note": "corb_orb_extract_pair_submit / _wait on two handle pairs from one thread: page-locked host images in, "
+                            "host keypoints + descriptors out (read in place from the handles' page-locked result buffers)"},
+            "e2e_one_in_flight": {"value": world * n_frames / (e2e_block_ms * 1e-3), "unit": "frames/s",
+                                  "us_per_frame": 1e3 * e2e_block_ms / n_frames, "note": "the blocking corb_orb_extract_pair"},
+            "e2e_stereo_frame": {"value": world * n_frames / (e2e_frame_ms * 1e-3), "unit": "frames/s",
+                                 "us_per_frame": 1e3 * e2e_frame_ms / n_frames, "stereo_matches_per_frame": n_stereo / max(1, n_frames),
+                                 "note": "corb_frame_stereo_submit / _wait: ExtractORB left+right and Frame::ComputeStereoMatches on the "
+                                         "GPU, two frames in flight; the pyramids never leave HBM"},
+            "gpu_launches": exl.launches_per_extract() * n_frames,  # one set of launches per stereo pair (grid z = 2)
             "tma": exl.uses_tma(),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic(top[0]), "peak_source": pk_kind,
-                         "traffic_source": "profiles/r01b_stereo_frame_ncu_full.csv (ncu --set full, dram read + write of that launch / 2 images)",
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_IMAGE, "kernel_ms": top[1],
-                         "whole_frame_frac": 2 * ALGO_BYTES_PER_IMAGE * fps / world / 1e9 / pk["hbm_gbs"],
-                         "per_kernel_ms_sum_over_levels": {k: round(v, 5) for k, v in agg.items()},
-                         "per_launch_ms": {k: round(v, 5) for k, v in prof}},
-            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 2, "kind": "port",
-                             "sample": "%d stereo frames, oracle port, L/R on two threads (Frame.cc:78-81), %.1f s"
-                                       % (args.sample_frames, cpu_dt), "host_cores_available": os.cpu_count(),
-                             "stereo_frame_value": cpu_fps_frame},
+            "roofline": {"bound": "hbm", "scope": "whole stereo frame (every kernel of the path)", "achieved": achieved,
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                         "peak_source": pk_kind, "algorithmic_bytes_per_frame": 2 * ALGO_BYTES_PER_IMAGE,
+                         "how": "achieved = 4 054 364 B (SURVEY.md section 8d) x frames/s per GPU; traffic = dram read + write summed over "
+                                "the launches of one stereo frame in the committed ncu --set full capture",
+                         "traffic_source": cap_src, "dominant_kernel": dom, "kernels": kernels},
+            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 2, "kind": cpu_kind, "cpu_model": cpu_model(),
+                             "sample": "%d stereo frames, %s, L/R on two threads (Frame.cc:78-81), %.1f s"
+                                       % (args.sample_frames, "the reference's own ORBextractor.cc (oracle/_ref/libref.so)"
+                                          if cpu_kind == "reference" else "oracle port", cpu_dt),
+                             "host_cores_available": os.cpu_count(), "stereo_frame_value": cpu_fps_frame,
+                             "stereo_frame_kind": "port (Frame::ComputeStereoMatches needs the oracle's pyramids)"},
             "keypoints_per_frame": kp_per_frame,
         }
         if not args.no_matcher:
@@ -621,14 +788,16 @@ def run_ours(args):
                            "sharding": "landmarks l %% N per rank, poses replicated, all-reduce(sum, fp64) of the reduced "
                                        "camera system per LM trial" if world > 1 else "single GPU, no collective"},
                 "ms_total": ba_ms, "ms_in_library": ba_info["ms_total"], "ms_reduced_camera_solves": ba_info["ms_solve"],
+                "ms_setup": ba_info["ms_setup"],
                 "iterations": ba_info["iterations"], "trials": ba_info["n_trials"], "trial_accepted": ba_info["trial_accepted"],
                 "chi2_initial": ba_info["chi2_initial"], "chi2_final": ba_info["chi2_final"], "rms_px": ba_rms,
-                "reduced_blocks": ba_info["reduced_blocks"],
+                "reduced_blocks": ba_info["reduced_blocks"], "band_chunks": ba_info["band_chunks"], "border_poses": ba_info["border_poses"],
+                "parity_vs_single": ba_parity,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                              "algorithmic_bytes_per_iteration": ba_bytes // max(1, ba_info["iterations"]),
                              "note": "whole-call wall time incl. host structure build and H2D/D2H; the reduced-camera solve "
                                      "(chunked block-skyline Cholesky) is bound by the serial latency of a block column"},
-                "cpu_baseline": cpu_ba(BA_P, BA_L) if not args.no_cpu_ba else None,
+                "cpu_baseline": dict(cpu_ba(BA_P, BA_L), cpu_model=cpu_model()) if not args.no_cpu_ba else None,
             }
             if ba_allreduce is not None:
                 S, ms = ba_allreduce["message_bytes"], ba_allreduce["ms"]
@@ -639,7 +808,8 @@ def run_ours(args):
                     "note": "NCCL all-reduce(sum, fp64) of the reduced camera system [S | bschur], one per LM trial; bus bandwidth "
                             "2(n-1)/n * S / t against 900 GB/s per direction (NVLink 5); a %.1f MB message is latency bound" % (S / 1e6)}
         print(json.dumps(line))
-    exl.close(); exr.close()
+    for a_, b_ in pairs:
+        a_.close(); b_.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -647,13 +817,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20, help="timed steps of %d stereo frames each" % FRAMES_PER_STEP)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sample-frames", type=int, default=200, help="stereo frames of the bounded CPU baseline sample")
+    ap.add_argument("--sample-frames", type=int, default=128, help="stereo frames of the bounded CPU baseline sample")
     ap.add_argument("--no-ba", action="store_true", help="skip the global-BA half of the metric")
     ap.add_argument("--no-cpu-ba", action="store_true", help="skip the CPU BA baseline (about 10 s)")
-    ap.add_argument("--clients-per-gpu", type=int, default=4, help="extra capacity measurement with this many clients on one GPU (1 = skip)")
     ap.add_argument("--no-matcher", action="store_true", help="skip the SearchByBoW / vocabulary / score section")
     args = ap.parse_args()
     if args.impl == "reference":

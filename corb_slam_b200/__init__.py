@@ -5,7 +5,7 @@ reference classes that own the path (ORBextractor, ORBmatcher, ORBVocabulary, Pn
 """
 from ._lib import CorbError, KP_DTYPE, LIB_PATH  # noqa: F401
 from .orbextractor import (ORBextractor, compute_stereo_matches, extract_stereo, extract_stereo_device,  # noqa: F401
-                           frame_stereo)
+                           extract_stereo_submit, extract_stereo_wait, frame_stereo, frame_stereo_submit, frame_stereo_wait)
 from .orbmatcher import ORBmatcher, BowFeatures  # noqa: F401
 from .orbvocabulary import ORBVocabulary  # noqa: F401
 from .frame import FrameView  # noqa: F401

@@ -107,6 +107,10 @@ def lib():
         L.corb_orb_extract_pair_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
         L.corb_stereo_match.argtypes = [vp, vp, C.c_float, C.c_float, C.c_int, vp, vp]
         L.corb_frame_stereo.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, i32p, vp, vp, i32p, vp, vp]
+        L.corb_orb_extract_pair_submit.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.corb_orb_extract_pair_wait.argtypes = [vp, vp, vp, vp, i32p, vp, vp, i32p, C.POINTER(vp), C.POINTER(vp)]
+        L.corb_frame_stereo_submit.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        L.corb_frame_stereo_wait.argtypes = [vp, vp, vp, vp, i32p, vp, vp, i32p, vp, vp]
         L.corb_orb_extract_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
         L.corb_orb_sync.argtypes = [vp]
         L.corb_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]

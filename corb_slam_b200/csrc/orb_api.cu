@@ -78,6 +78,7 @@ struct corb_orb {
     uint8_t* d_out = nullptr;
     size_t out_bytes = 0;
     bool pending = false, pending_pyr = false, pending_empty = false;
+    int pending_pair = 0;  // on the left handle of a pair: 1 = corb_orb_extract_pair_submit, 2 = corb_frame_stereo_submit in flight
     bool own_dirty = false;  // work enqueued on the handle's own stream has not been synchronised yet
 
     // one graph for a stereo pair (this handle = left): [right frame || left frame] (-> stereo matching) (-> D2H)
@@ -967,12 +968,54 @@ int corb_orb_extract(corb_orb* h, const uint8_t* img, int w, int hgt, int stride
 // frames are one CUDA graph on the left handle's stream (two parallel branches), i.e. one driver launch per stereo frame.
 static int pair_prepare(corb_orb* hl, corb_orb* hr, int w, int hgt) {
     CORB_CHECK(hl && hr && hl != hr, CORB_ERR_INVALID, "two distinct handles are required");
-    CORB_CHECK(!hl->pending && !hr->pending, CORB_ERR_INVALID, "a submitted extraction has not been waited for");
+    CORB_CHECK(!hl->pending && !hr->pending && !hl->pending_pair, CORB_ERR_INVALID, "a submitted extraction has not been waited for");
     CORB_CHECK(hl->device == hr->device, CORB_ERR_INVALID, "left and right handle must live on the same device");
     CORB_CUDA(cudaSetDevice(hl->device));
     int rc = make_plan(hl, w, hgt);
     if (rc != CORB_OK) return rc;
     return make_plan(hr, w, hgt);
+}
+
+// pending_pair: 0 none, 1 extract_pair submitted, 2 frame_stereo submitted (state lives on the left handle)
+int corb_orb_extract_pair_submit(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride,
+                                 int want_pyramid) {
+    CORB_CHECK(hl && hr, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(img_l && img_r && w >= 1 && hgt >= 1, CORB_ERR_INVALID, "the split form needs two non-empty images");
+    CORB_CHECK(stride >= w, CORB_ERR_INVALID, "stride %d < width %d", stride, w);
+    CORB_CHECK(!hl->pending_pair, CORB_ERR_INVALID, "a submitted stereo pair has not been waited for");
+    int rc = pair_prepare(hl, hr, w, hgt);
+    if (rc != CORB_OK) return rc;
+    if ((rc = ensure_pair_graph(hl, hr, 1, 0.f, 0.f)) != CORB_OK) return rc;
+    const uint8_t *sl, *sr;
+    int stl, str_;
+    stage_input(hl, img_l, w, hgt, stride, &sl, &stl);
+    stage_input(hr, img_r, w, hgt, stride, &sr, &str_);
+    if ((rc = launch_pair(hl, hr, 1, sl, stl, sr, str_)) != CORB_OK) return rc;
+    if (want_pyramid) {
+        CORB_CUDA(cudaMemcpyAsync(hl->h_pyr, hl->buf.pyr, hl->pyr_bytes, cudaMemcpyDeviceToHost, hl->stream));
+        CORB_CUDA(cudaMemcpyAsync(hr->h_pyr, hr->buf.pyr, hr->pyr_bytes, cudaMemcpyDeviceToHost, hl->stream));
+    }
+    hl->pending_pair = 1;
+    hl->pending_pyr = want_pyramid != 0;
+    return CORB_OK;
+}
+
+int corb_orb_extract_pair_wait(corb_orb* hl, corb_orb* hr, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r,
+                               uint8_t* desc_r, int* n_r, uint8_t* const* pyr_l, uint8_t* const* pyr_r) {
+    CORB_CHECK(hl && hr && n_l && n_r, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(hl->pending_pair == 1, CORB_ERR_INVALID, "no stereo pair was submitted on these handles");
+    CORB_CHECK(!(pyr_l || pyr_r) || hl->pending_pyr, CORB_ERR_INVALID, "pyramid requested at wait but not at submit");
+    hl->pending_pair = 0;
+    CORB_CUDA(cudaSetDevice(hl->device));
+    CORB_CUDA(cudaStreamSynchronize(hl->stream));
+    hl->own_dirty = false;
+    hr->busy_stream = nullptr;
+    int rc;
+    if ((rc = collect(hl, kps_l, desc_l, n_l)) != CORB_OK) return rc;
+    if ((rc = collect(hr, kps_r, desc_r, n_r)) != CORB_OK) return rc;
+    if (pyr_l) copy_pyramid(hl, pyr_l);
+    if (pyr_r) copy_pyramid(hr, pyr_r);
+    return CORB_OK;
 }
 
 int corb_orb_extract_pair(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride,
@@ -984,25 +1027,9 @@ int corb_orb_extract_pair(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, cons
         if (rc != CORB_OK) return rc;
         return corb_orb_extract(hr, img_r, w, hgt, stride, kps_r, desc_r, n_r, pyr_r);
     }
-    CORB_CHECK(stride >= w, CORB_ERR_INVALID, "stride %d < width %d", stride, w);
-    int rc = pair_prepare(hl, hr, w, hgt);
+    int rc = corb_orb_extract_pair_submit(hl, hr, img_l, img_r, w, hgt, stride, pyr_l || pyr_r);
     if (rc != CORB_OK) return rc;
-    if ((rc = ensure_pair_graph(hl, hr, 1, 0.f, 0.f)) != CORB_OK) return rc;
-    const uint8_t *sl, *sr;
-    int stl, str_;
-    stage_input(hl, img_l, w, hgt, stride, &sl, &stl);
-    stage_input(hr, img_r, w, hgt, stride, &sr, &str_);
-    if ((rc = launch_pair(hl, hr, 1, sl, stl, sr, str_)) != CORB_OK) return rc;
-    if (pyr_l) CORB_CUDA(cudaMemcpyAsync(hl->h_pyr, hl->buf.pyr, hl->pyr_bytes, cudaMemcpyDeviceToHost, hl->stream));
-    if (pyr_r) CORB_CUDA(cudaMemcpyAsync(hr->h_pyr, hr->buf.pyr, hr->pyr_bytes, cudaMemcpyDeviceToHost, hl->stream));
-    CORB_CUDA(cudaStreamSynchronize(hl->stream));
-    hl->own_dirty = false;
-    hr->busy_stream = nullptr;
-    if ((rc = collect(hl, kps_l, desc_l, n_l)) != CORB_OK) return rc;
-    if ((rc = collect(hr, kps_r, desc_r, n_r)) != CORB_OK) return rc;
-    if (pyr_l) copy_pyramid(hl, pyr_l);
-    if (pyr_r) copy_pyramid(hr, pyr_r);
-    return CORB_OK;
+    return corb_orb_extract_pair_wait(hl, hr, kps_l, desc_l, n_l, kps_r, desc_r, n_r, pyr_l, pyr_r);
 }
 
 int corb_orb_extract_pair_device(corb_orb* hl, corb_orb* hr, const uint8_t* d_img_l, const uint8_t* d_img_r, int w, int hgt,
@@ -1044,6 +1071,42 @@ int corb_stereo_match(corb_orb* left, corb_orb* right, float mbf, float mb, int 
     return CORB_OK;
 }
 
+int corb_frame_stereo_submit(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride,
+                             float mbf, float mb) {
+    CORB_CHECK(hl && hr && hl != hr, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(img_l && img_r && w >= 1 && hgt >= 1, CORB_ERR_INVALID, "the split form needs two non-empty images");
+    CORB_CHECK(mb > 0.f && mbf > 0.f, CORB_ERR_INVALID, "mbf and mb must be positive");
+    CORB_CHECK(stride >= w, CORB_ERR_INVALID, "stride %d < width %d", stride, w);
+    CORB_CHECK(!hl->pending_pair, CORB_ERR_INVALID, "a submitted stereo pair has not been waited for");
+    int rc = pair_prepare(hl, hr, w, hgt);
+    if (rc != CORB_OK) return rc;
+    if ((rc = ensure_pair_graph(hl, hr, 2, mbf, mb)) != CORB_OK) return rc;  // extraction x2 + stereo matching + D2H, one launch
+    const uint8_t *sl, *sr;
+    int stl, str_;
+    stage_input(hl, img_l, w, hgt, stride, &sl, &stl);
+    stage_input(hr, img_r, w, hgt, stride, &sr, &str_);
+    if ((rc = launch_pair(hl, hr, 2, sl, stl, sr, str_)) != CORB_OK) return rc;
+    hl->pending_pair = 2;
+    return CORB_OK;
+}
+
+int corb_frame_stereo_wait(corb_orb* hl, corb_orb* hr, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r,
+                           uint8_t* desc_r, int* n_r, float* u_right, float* depth) {
+    CORB_CHECK(hl && hr && n_l && n_r && u_right && depth, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(hl->pending_pair == 2, CORB_ERR_INVALID, "no stereo frame was submitted on these handles");
+    hl->pending_pair = 0;
+    CORB_CUDA(cudaSetDevice(hl->device));
+    CORB_CUDA(cudaStreamSynchronize(hl->stream));
+    hl->own_dirty = false;
+    hr->busy_stream = nullptr;
+    int rc;
+    if ((rc = collect(hl, kps_l, desc_l, n_l)) != CORB_OK) return rc;
+    if ((rc = collect(hr, kps_r, desc_r, n_r)) != CORB_OK) return rc;
+    memcpy(u_right, hl->h_stereo, *n_l * sizeof(float));
+    memcpy(depth, hl->h_stereo + hl->geom.kp_cap, *n_l * sizeof(float));
+    return CORB_OK;
+}
+
 int corb_frame_stereo(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride, float mbf,
                       float mb, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r, uint8_t* desc_r, int* n_r,
                       float* u_right, float* depth) {
@@ -1053,23 +1116,9 @@ int corb_frame_stereo(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const ui
         *n_l = *n_r = 0;
         return CORB_OK;
     }
-    CORB_CHECK(stride >= w, CORB_ERR_INVALID, "stride %d < width %d", stride, w);
-    int rc = pair_prepare(hl, hr, w, hgt);
+    int rc = corb_frame_stereo_submit(hl, hr, img_l, img_r, w, hgt, stride, mbf, mb);
     if (rc != CORB_OK) return rc;
-    if ((rc = ensure_pair_graph(hl, hr, 2, mbf, mb)) != CORB_OK) return rc;  // extraction x2 + stereo matching + D2H, one launch
-    const uint8_t *sl, *sr;
-    int stl, str_;
-    stage_input(hl, img_l, w, hgt, stride, &sl, &stl);
-    stage_input(hr, img_r, w, hgt, stride, &sr, &str_);
-    if ((rc = launch_pair(hl, hr, 2, sl, stl, sr, str_)) != CORB_OK) return rc;
-    CORB_CUDA(cudaStreamSynchronize(hl->stream));
-    hl->own_dirty = false;
-    hr->busy_stream = nullptr;
-    if ((rc = collect(hl, kps_l, desc_l, n_l)) != CORB_OK) return rc;
-    if ((rc = collect(hr, kps_r, desc_r, n_r)) != CORB_OK) return rc;
-    memcpy(u_right, hl->h_stereo, *n_l * sizeof(float));
-    memcpy(depth, hl->h_stereo + hl->geom.kp_cap, *n_l * sizeof(float));
-    return CORB_OK;
+    return corb_frame_stereo_wait(hl, hr, kps_l, desc_l, n_l, kps_r, desc_r, n_r, u_right, depth);
 }
 
 int corb_orb_extract_device(corb_orb* h, const uint8_t* d_img, int w, int hgt, int stride) {

@@ -255,6 +255,47 @@ def extract_stereo(ex_left, ex_right, left, right, want_pyramid=False):
     return tuple(res)
 
 
+def extract_stereo_submit(ex_left, ex_right, left, right):
+    """corb_orb_extract_pair_submit: enqueue one stereo pair (page-locked or pageable host images) and return. One client
+    thread keeps two frames in flight by alternating between two handle pairs; extract_stereo_wait collects."""
+    h, w = left.shape
+    ex_left._shape = ex_right._shape = (h, w)
+    ex_left._keep_pair = (left, right)
+    check(lib().corb_orb_extract_pair_submit(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0], 0))
+
+
+def extract_stereo_wait(ex_left, ex_right):
+    """-> ((kps_l, desc_l), (kps_r, desc_r)) as views of the handles' page-locked result buffers (valid until the next
+    extraction on these handles)."""
+    nl, nr = C.c_int32(), C.c_int32()
+    check(lib().corb_orb_extract_pair_wait(ex_left._h, ex_right._h, None, None, C.byref(nl), None, None, C.byref(nr), None, None))
+    ex_left._keep_pair = None
+    return ex_left._host_view(nl.value, ex_left._shape), ex_right._host_view(nr.value, ex_right._shape)
+
+
+def frame_stereo_submit(ex_left, ex_right, left, right, mbf, mb):
+    """corb_frame_stereo_submit (ExtractORB x2 + ComputeStereoMatches enqueued as one graph launch)."""
+    h, w = left.shape
+    ex_left._shape = ex_right._shape = (h, w)
+    ex_left._keep_pair = (left, right)
+    check(lib().corb_frame_stereo_submit(ex_left._h, ex_right._h, left.ctypes.data, right.ctypes.data, w, h, left.strides[0],
+                                         float(mbf), float(mb)))
+
+
+def frame_stereo_wait(ex_left, ex_right):
+    """-> ((kps_l, desc_l), (kps_r, desc_r), mvuRight, mvDepth); keypoints / descriptors are views of the result buffers."""
+    cap = ex_left.capacity(ex_left._shape[1], ex_left._shape[0])
+    if getattr(ex_left, "_stereo_out", None) is None or len(ex_left._stereo_out[0]) != cap:
+        ex_left._stereo_out = (np.empty(cap, np.float32), np.empty(cap, np.float32))
+    ur, dp = ex_left._stereo_out
+    nl, nr = C.c_int32(), C.c_int32()
+    check(lib().corb_frame_stereo_wait(ex_left._h, ex_right._h, None, None, C.byref(nl), None, None, C.byref(nr), ur.ctypes.data,
+                                       dp.ctypes.data))
+    ex_left._keep_pair = None
+    return (ex_left._host_view(nl.value, ex_left._shape), ex_right._host_view(nr.value, ex_right._shape), ur[:nl.value],
+            dp[:nl.value])
+
+
 def extract_stereo_device(ex_left, ex_right, d_left, d_right, w, h, stride):
     if (h, w) != ex_left._shape_v or (h, w) != ex_right._shape_v:
         ex_left._hv_shape = ex_right._hv_shape = None  # another size rebuilds the plans

@@ -89,6 +89,14 @@ CORB_API int corb_orb_extract_wait(corb_orb* h, corb_keypoint* kps, uint8_t* des
 CORB_API int corb_orb_extract_pair(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt,
                                    int stride, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r,
                                    uint8_t* desc_r, int* n_r, uint8_t* const* pyr_l, uint8_t* const* pyr_r);
+/* Split form of corb_orb_extract_pair, so that ONE client thread keeps two stereo frames in flight on two handle pairs
+ * (frame i + 1 is read over PCIe and extracted while the caller consumes frame i): _submit enqueues everything on the left
+ * handle's stream and returns, _wait blocks and fills the outputs (NULL kps / desc: read them in place through
+ * corb_orb_host_results). Both images must be non-empty. */
+CORB_API int corb_orb_extract_pair_submit(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt,
+                                          int stride, int want_pyramid);
+CORB_API int corb_orb_extract_pair_wait(corb_orb* hl, corb_orb* hr, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l,
+                                        corb_keypoint* kps_r, uint8_t* desc_r, int* n_r, uint8_t* const* pyr_l, uint8_t* const* pyr_r);
 CORB_API int corb_orb_extract_pair_device(corb_orb* hl, corb_orb* hr, const uint8_t* d_img_l, const uint8_t* d_img_r, int w,
                                           int hgt, int stride);
 
@@ -102,6 +110,12 @@ CORB_API int corb_stereo_match(corb_orb* left, corb_orb* right, float mbf, float
 CORB_API int corb_frame_stereo(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride,
                                float mbf, float mb, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r,
                                uint8_t* desc_r, int* n_r, float* u_right, float* depth);
+
+/* Split form of corb_frame_stereo (see corb_orb_extract_pair_submit). */
+CORB_API int corb_frame_stereo_submit(corb_orb* hl, corb_orb* hr, const uint8_t* img_l, const uint8_t* img_r, int w, int hgt, int stride,
+                                      float mbf, float mb);
+CORB_API int corb_frame_stereo_wait(corb_orb* hl, corb_orb* hr, corb_keypoint* kps_l, uint8_t* desc_l, int* n_l, corb_keypoint* kps_r,
+                                    uint8_t* desc_r, int* n_r, float* u_right, float* depth);
 
 /* Device-resident form: `d_img` is already in HBM (pitch `stride`), results stay in HBM for on-GPU consumers
  * (matcher, stereo). Enqueued on the handle's stream; corb_orb_sync() waits for it. */

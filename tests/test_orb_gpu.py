@@ -282,3 +282,44 @@ def test_repeated_and_concurrent_extraction_is_deterministic():
     [t.join() for t in ths]
     assert not errors, errors
     ref.close()
+
+
+def test_two_stereo_frames_in_flight_from_one_thread():
+    """corb_orb_extract_pair_submit / _wait and corb_frame_stereo_submit / _wait on two handle pairs: frame i + 1 is in flight
+    while frame i is collected; results equal the blocking calls (and therefore the oracle) bit for bit."""
+    from corb_slam_b200 import (extract_stereo, extract_stereo_submit, extract_stereo_wait, frame_stereo, frame_stereo_submit,
+                                frame_stereo_wait)
+    from corb_slam_b200 import _lib
+    frames = [stereo_frame(1300 + i) for i in range(5)]
+    pairs = [(ORBextractor(*PARAMS), ORBextractor(*PARAMS)) for _ in range(2)]
+    ref_pair = (ORBextractor(*PARAMS), ORBextractor(*PARAMS))
+    for a, b in pairs:
+        a.copy_outputs = b.copy_outputs = False
+    mbf, mb = 386.1448, np.float32(386.1448) / np.float32(718.856)
+    want = [tuple((k.copy(), d.copy()) for k, d in extract_stereo(*ref_pair, l, r)) for l, r in frames]
+    extract_stereo_submit(*pairs[0], *frames[0])
+    for i in range(len(frames)):
+        if i + 1 < len(frames):
+            extract_stereo_submit(*pairs[(i + 1) % 2], *frames[i + 1])
+        (kl, dl), (kr, dr) = extract_stereo_wait(*pairs[i % 2])
+        assert kl.tobytes() == want[i][0][0].tobytes() and np.array_equal(dl, want[i][0][1])
+        assert kr.tobytes() == want[i][1][0].tobytes() and np.array_equal(dr, want[i][1][1])
+    wantf = []
+    for l, r in frames:
+        (kl, dl), (kr, dr), ur, dp = frame_stereo(*ref_pair, l, r, mbf, mb)
+        wantf.append((kl.copy(), ur.copy(), dp.copy()))
+    frame_stereo_submit(*pairs[0], *frames[0], mbf, mb)
+    for i in range(len(frames)):
+        if i + 1 < len(frames):
+            frame_stereo_submit(*pairs[(i + 1) % 2], *frames[i + 1], mbf, mb)
+        (kl, dl), (kr, dr), ur, dp = frame_stereo_wait(*pairs[i % 2])
+        assert kl.tobytes() == wantf[i][0].tobytes() and ur.tobytes() == wantf[i][1].tobytes() and dp.tobytes() == wantf[i][2].tobytes()
+    # misuse is reported, not ignored
+    extract_stereo_submit(*pairs[0], *frames[0])
+    with pytest.raises(_lib.CorbError):
+        extract_stereo_submit(*pairs[0], *frames[1])
+    with pytest.raises(_lib.CorbError):
+        frame_stereo_wait(*pairs[0])
+    extract_stereo_wait(*pairs[0])
+    for a, b in pairs + [ref_pair]:
+        a.close(); b.close()
