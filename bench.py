@@ -38,13 +38,14 @@ ORB_PARAMS = (2000, 1.2, 8, 20, 7)  # KITTI00-02.yaml:38-51
 N_BASE = 16           # distinct synthetic scenes ...
 N_POOL = 160          # ... shifted into 160 distinct stereo pairs: 160 x 2 x 465 750 B = 149 MB > 126 MB of L2
 FRAMES_PER_STEP = 64  # one step = 64 stereo frames, in both arms
+IN_FLIGHT = int(os.environ.get("CORB_BENCH_IN_FLIGHT", "2"))  # stereo frames a client keeps in flight (handle pairs)
 ALGO_BYTES_PER_IMAGE = W * H + 1441432 + 60 * 2000  # input + pyramid + 60 B per keypoint (K = 2000)
 WORKLOAD = "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7"
 
 
 def bench_config():
     """The same dictionary in both arms (the driver compares them)."""
-    return {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "clients_per_gpu": 1, "frames_in_flight": 2,
+    return {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "clients_per_gpu": 1, "frames_in_flight": IN_FLIGHT,
             "frame_pool": "%d distinct stereo pairs (%d MB, larger than L2), walked cyclically" % (N_POOL, N_POOL * 2 * W * H // 1000000),
             "l2": "inputs larger than L2 and a 256 MiB flush between timed steps",
             "timing": "CUDA events around every step on the extractor streams, sum over steps, max over ranks"}
@@ -542,8 +543,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # two handle pairs = two stereo frames in flight
-    pairs = [(ORBextractor(*ORB_PARAMS, device=local), ORBextractor(*ORB_PARAMS, device=local)) for _ in range(2)]
+    # IN_FLIGHT handle pairs = that many stereo frames in flight
+    NP = IN_FLIGHT
+    pairs = [(ORBextractor(*ORB_PARAMS, device=local), ORBextractor(*ORB_PARAMS, device=local)) for _ in range(NP)]
     for a_, b_ in pairs:
         a_.copy_outputs = b_.copy_outputs = False
     exl, exr = pairs[0]
@@ -559,25 +561,28 @@ def run_ours(args):
     def step_device(step, ev0, ev1):
         """F stereo frames, alternating between the two handle pairs; events bracket the whole step on both streams."""
         ev0.record(streams[0])
-        streams[1].wait_event(ev0)
+        for st in streams[1:]:
+            st.wait_event(ev0)
         for f in range(F):
             i = (step * F + f) % N_POOL
-            a_, b_ = pairs[f & 1]
+            a_, b_ = pairs[f % NP]
             extract_stereo_device(a_, b_, dev[i][0].data_ptr(), dev[i][1].data_ptr(), W, H, W)
-        evb = torch.cuda.Event()
-        evb.record(streams[1])
-        streams[0].wait_event(evb)
+        for st in streams[1:]:
+            evb = torch.cuda.Event()
+            evb.record(st)
+            streams[0].wait_event(evb)
         ev1.record(streams[0])
 
     def step_host(step, submit, wait):
         """F stereo frames through the split C-ABI calls from this one thread, two in flight; returns keypoints seen."""
         nk = 0
         base = step * F
-        submit(*pairs[0], *npin[base % N_POOL])
+        for f in range(min(NP - 1, F)):
+            submit(*pairs[f % NP], *npin[(base + f) % N_POOL])
         for f in range(F):
-            if f + 1 < F:
-                submit(*pairs[(f + 1) & 1], *npin[(base + f + 1) % N_POOL])
-            res = wait(*pairs[f & 1])
+            if f + NP - 1 < F:
+                submit(*pairs[(f + NP - 1) % NP], *npin[(base + f + NP - 1) % N_POOL])
+            res = wait(*pairs[f % NP])
             nk += len(res[0][0]) + len(res[1][0])
         return nk
 
@@ -632,11 +637,12 @@ def run_ours(args):
     n_stereo = 0
     for i in range(args.steps):  # the stereo Frame constructor: ExtractORB x2 + ComputeStereoMatches, pyramids stay in HBM
         base = i * F
-        sub_frame(*pairs[0], *npin[base % N_POOL])
+        for f in range(min(NP - 1, F)):
+            sub_frame(*pairs[f % NP], *npin[(base + f) % N_POOL])
         for f in range(F):
-            if f + 1 < F:
-                sub_frame(*pairs[(f + 1) & 1], *npin[(base + f + 1) % N_POOL])
-            fr = frame_stereo_wait(*pairs[f & 1])
+            if f + NP - 1 < F:
+                sub_frame(*pairs[(f + NP - 1) % NP], *npin[(base + f + NP - 1) % N_POOL])
+            fr = frame_stereo_wait(*pairs[f % NP])
             n_stereo += int((fr[2] >= 0).sum())
     e2e_frame_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None

@@ -30,6 +30,14 @@ class Cache;
 class KeyFrameDatabase;
 class MapPoint;
 
+class Cache { /* Cache.h:107-108: the update queues Optimizer.cc:230,254 feed (recorded, nothing else) */
+public:
+    void addUpdateKeyframe(KeyFrame* pKF) { updatedKFs.push_back(pKF); }
+    void addUpdateMapPoint(MapPoint* pMP) { updatedMPs.push_back(pMP); }
+    std::vector<KeyFrame*> updatedKFs;
+    std::vector<MapPoint*> updatedMPs;
+};
+
 class LightMapPoint { /* LightMapPoint.h:33-68; the cache lookup is replaced by the pointer itself */
 public:
     LightMapPoint() : mnMapPointId(0), mpCache(0), mp(0) {}
@@ -55,7 +63,16 @@ public:
 class MapPoint { /* MapPoint.h:83-165 */
 public:
     MapPoint() : mnId(0), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mbTrackInView(false), mnTrackScaleLevel(0),
-                 mTrackViewCos(0), mnLastFrameSeen(0), nObs(0), bad(false), mfMinDistance(0), mfMaxDistance(0) {}
+                 mTrackViewCos(0), mnLastFrameSeen(0), mnBAGlobalForKF(0), nObs(0), bad(false), fixed(false), mfMinDistance(0),
+                 mfMaxDistance(0), cache(0), nNormalUpdates(0) {}
+    /* members Optimizer::BundleAdjustment touches (MapPoint.h:81-176) */
+    void SetWorldPos(const cv::Mat& Pos) { Pos.copyTo(mWorldPos); }
+    bool getFixed() { return fixed; }
+    std::map<KeyFrame*, size_t> GetObservations() { return obs; }
+    void UpdateNormalAndDepth() { nNormalUpdates++; }
+    Cache* getCache() { return cache; }
+    cv::Mat mPosGBA;
+    long unsigned int mnBAGlobalForKF;
     cv::Mat GetWorldPos() { return mWorldPos.clone(); }
     cv::Mat GetNormal() { return mNormalVector.clone(); }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
@@ -79,15 +96,27 @@ public:
     /* plain data behind the getters */
     cv::Mat mWorldPos, mNormalVector, mDescriptor;
     int nObs;
-    bool bad;
+    bool bad, fixed;
     float mfMinDistance, mfMaxDistance;
     std::map<KeyFrame*, size_t> obs;
+    Cache* cache;
+    int nNormalUpdates;
 };
 
 class KeyFrame { /* KeyFrame.h:101-274 */
 public:
     KeyFrame() : mnId(0), fx(0), fy(0), cx(0), cy(0), invfx(0), invfy(0), mbf(0), mb(0), mThDepth(0), N(0), mnScaleLevels(0),
-                 mfScaleFactor(0), mfLogScaleFactor(0), mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0) {}
+                 mfScaleFactor(0), mfLogScaleFactor(0), mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0), mnBAGlobalForKF(0), mpCacher(0),
+                 bad(false), fixed(false) {}
+    /* members Optimizer::BundleAdjustment touches (KeyFrame.h:95-111,194,244-246,286) */
+    void SetPose(const cv::Mat& Tcw_) { Tcw_.copyTo(Tcw); }
+    cv::Mat GetPose() { return Tcw.clone(); }
+    bool isBad() { return bad; }
+    bool getFixed() { return fixed; }
+    cv::Mat mTcwGBA;
+    long unsigned int mnBAGlobalForKF;
+    Cache* mpCacher;
+    bool bad, fixed;
     cv::Mat GetCameraCenter() { return Ow.clone(); }
     cv::Mat GetRotation() { return Tcw.rowRange(0, 3).colRange(0, 3).clone(); }
     cv::Mat GetTranslation() { return Tcw.rowRange(0, 3).col(3).clone(); }
