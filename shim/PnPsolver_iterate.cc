@@ -34,6 +34,9 @@ cv::Mat PnPsolver::iterate(int nIterations, bool& bNoMore, vector<bool>& vbInlie
         std::lock_guard<std::mutex> lock(g_mu);
         draws = &g_draws[this];
     }
+    // a solver that has not iterated yet starts a new stream: the destructor (reference code) cannot drop the map entry, and a
+    // new object may live at the address of a destroyed one
+    if (mnIterations == 0) draws->clear();
     corb_pnp_problem p;
     p.n = N;
     static const float zero3[3] = {0, 0, 0};
