@@ -1357,6 +1357,8 @@ __global__ void __launch_bounds__(256) k_ba_scale(BaDev d, double lambda, int nb
 
 }  // namespace corb
 
+#include "ba_border_chol.cuh"
+
 using namespace corb;
 
 namespace {
@@ -1436,6 +1438,9 @@ struct BaHost {
     size_t band_idx_bytes = 0;
     size_t border_dense_bytes = 0;
     bool border_dense_ok = false;  // the left-looking border kernel's shared staging fits
+    bool border_tiled = false;     // tiled multi-CTA border factorisation (k_ba_border_chol) usable
+    int border_grid = 1;
+    size_t border_tiled_bytes = 0;
     int n_chunks = 1;           // independent band chunks (columns chunk_start[q] .. chunk_start[q + 1])  // first[] / rowoff[] of the band rows staged by the border-row and band-backward kernels     // longest band envelope (blocks left of the diagonal)
     int n_band = 0;        // free keyframes before the border block (== Pf when there is no border)
     corb_allreduce_fn ar = nullptr;
@@ -1602,7 +1607,15 @@ struct BaHost {
                 const int npairs = nbord * (nbord + 1) / 2;
                 k_ba_border_syrk<<<(int)(((size_t)npairs * n_chunks * 32 + 255) / 256), 256, 0, stream>>>(d, n_band, n_chunks);
                 k_ba_border_syrk_apply<<<(npairs * 32 + 255) / 256, 256, 0, stream>>>(d, n_band, n_chunks);
-                if (getenv("CORB_BA_BORDER_RL") || !border_dense_ok) {  // A/B switch / border too large for the staging buffer
+                if (border_tiled) {
+                    // the dense border block on the whole GPU: tiled Cholesky with fp64 tensor-core updates + the border's
+                    // forward / backward substitution, then the border solution's contribution to the band right-hand side
+                    BaDev dd = d;
+                    int nb_arg = n_band;
+                    void* args[] = {&dd, &nb_arg};
+                    CORB_CUDA(cudaLaunchCooperativeKernel((void*)k_ba_border_chol, dim3(border_grid), dim3(kBcThreads), args, border_tiled_bytes, stream));
+                    k_ba_border_to_band<<<(n_band * 32 + 255) / 256, 256, 0, stream>>>(d, n_band);
+                } else if (getenv("CORB_BA_BORDER_RL") || !border_dense_ok) {  // A/B switch / border too large for the staging buffer
                     k_ba_solve<<<1, kSolveThreads, sm, stream>>>(d, lact_cap, n_band, d.Pf, n_band, 4 | 16, -1);
                 } else {
                     k_ba_border_dense<<<1, 1024, border_dense_bytes, stream>>>(d, n_band);
@@ -1961,7 +1974,9 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     lap("ordering (border, chunks)");
     std::vector<int> first(Pf), rowoff(Pf + 1, 0), coloff(Pf + 1, 0);
     for (int j = 0; j < Pf; j++) {
-        first[j] = (int)firstd[j];
+        // a border row stores every border column to its left (the tiled dense factorisation of the border block addresses
+        // all of its lower triangle); its band envelope is what the couplings say
+        first[j] = j >= H.n_band ? std::min((int)firstd[j], H.n_band) : (int)firstd[j];
         rowoff[j + 1] = rowoff[j] + (j - first[j] + 1);
     }
     const long long nblocks = Pf ? rowoff[Pf] : 0;
@@ -1989,6 +2004,18 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         H.border_dense_ok = nbord > 0 && dense_bytes <= 200 * 1024;
         if (H.border_dense_ok)
             CORB_SMEM_OPT_IN(k_ba_border_dense);
+        if (nbord > 0 && !getenv("CORB_BA_BORDER_OLD")) {
+            const int nt = ((int)nbord + kBTB - 1) / kBTB;
+            H.border_tiled_bytes = ((size_t)2 * kBT * kBLd + kBT + (size_t)nt * kBT) * sizeof(double);
+            int dev = 0, sms = 0, coop = 0, per_sm = 0;
+            CORB_CUDA(cudaGetDevice(&dev));
+            CORB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            CORB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+            CORB_SMEM_OPT_IN(k_ba_border_chol);
+            CORB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_border_chol, kBcThreads, H.border_tiled_bytes));
+            H.border_tiled = coop && per_sm > 0 && H.border_tiled_bytes <= 200 * 1024;
+            H.border_grid = std::max(1, std::min(sms * per_sm, std::max(nt - 1, nt * (nt - 1) / 2)));
+        }
     }
     // the same lists without the border rows in the band columns: the band sweep of the bordered solve
     std::vector<int> coloff_b(Pf + 1, 0), col_rows_b(col_rows.size());

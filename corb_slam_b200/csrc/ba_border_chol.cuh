@@ -1,0 +1,344 @@
+// Dense border block of the reduced camera system (the keyframes ordered last: separators of the band chunks and the ends of
+// long-range loop / map-fusion links) on the WHOLE GPU with fp64 tensor-core MMA - the dense part of what
+// g2o's LinearSolverEigen::solve (linear_solver_eigen.h:94-124) does for the reduced camera block.
+//
+//   k_ba_border_chol  : tiled right-looking Cholesky, in place in the block skyline. Tile = 48 x 48 doubles (8 keyframes).
+//                       Per tile column K: every CTA factors tile (K, K) in shared memory (redundantly: no barrier between
+//                       POTRF and TRSM) and solves its tiles X_IK = A_IK L_KK^-T; grid barrier; the trailing updates
+//                       A_IJ -= X_IK X_JK^T run as m8n8k4 fp64 MMA (DMMA), one CTA per tile; grid barrier.
+//                       Then one CTA substitutes forward and backward through the factor for the border right-hand side.
+//   k_ba_border_to_band: x_band -= sum_j L_j,band^T x_j over the border rows j, one warp per band column.
+//
+// Together they replace the one-CTA left-looking sweep + the one-CTA backward pass over the border rows (0.77 + 0.61 ms
+// per LM trial at P = 2000 in profiles/r01d_launches_ba.csv).
+#pragma once
+#include <cooperative_groups.h>
+
+namespace corb {
+
+constexpr int kBT = 48;         // tile edge in doubles (8 pose blocks of 6)
+constexpr int kBTB = kBT / 6;   // pose blocks per tile edge
+constexpr int kBLd = kBT + 1;   // shared-memory leading dimension (odd: column walks are conflict free)
+constexpr int kBcThreads = 256;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct BorderView {
+    BaDev d;
+    int n_band, nbord, nt;
+    // block (a, k) of the border matrix (border-local indices, k <= a) in the skyline
+    __device__ __forceinline__ double* blk(int a, int k) const {
+        const int j = n_band + a;
+        return d.S + ((size_t)(d.rowoff[j] - d.first[j]) + n_band + k) * 36;
+    }
+};
+
+// tile (I, K), I >= K, into shared memory as a dense 48 x 48 array; padding rows / columns continue the identity
+__device__ __forceinline__ void border_load_tile(const BorderView& v, int I, int K, double* s, int tid) {
+    for (int e = tid; e < kBTB * kBTB * 36; e += kBcThreads) {
+        const int bb = e / 36, w = e - bb * 36;
+        const int br = bb / kBTB, bc = bb - br * kBTB;
+        const int a = I * kBTB + br, k = K * kBTB + bc;
+        const int r = br * 6 + w / 6, c = bc * 6 + w % 6;
+        double x = 0.0;
+        if (a < v.nbord && k < v.nbord) {
+            if (k < a || (k == a && w / 6 >= w % 6)) x = v.blk(a, k)[w];
+        } else if (I == K && r == c) {
+            x = 1.0;
+        }
+        s[r * kBLd + c] = x;
+    }
+}
+
+// Cholesky of a 48 x 48 tile in shared memory (lower; the strict upper part is left untouched), 6 columns per step.
+// inv[c] = 1 / L_cc. Returns false (uniformly) when a pivot is not positive.
+__device__ __forceinline__ bool border_potrf(double* s, double* inv, int* fail, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int b = 0; b < kBTB; b++) {
+        const int c0 = b * 6;
+        if (warp == 0) {
+            for (int k = 0; k < 6; k++) {
+                const double piv = s[(c0 + k) * kBLd + c0 + k];
+                const bool ok = piv > 0.0;
+                const double iv = rsqrt(ok ? piv : 1.0);
+                if (!ok && lane == 0) *fail = 1;
+                __syncwarp();
+                if (lane == 0) { s[(c0 + k) * kBLd + c0 + k] = (ok ? piv : 1.0) * iv; inv[c0 + k] = iv; }
+                if (lane > k && lane < 6) s[(c0 + lane) * kBLd + c0 + k] *= iv;
+                __syncwarp();
+                if (lane < 21) {  // the 21 lower-triangle entries of the 6 x 6 block, one per lane
+                    const int r = lane >= 15 ? 5 : lane >= 10 ? 4 : lane >= 6 ? 3 : lane >= 3 ? 2 : lane >= 1 ? 1 : 0;
+                    const int c = lane - r * (r + 1) / 2;
+                    if (c > k) s[(c0 + r) * kBLd + c0 + c] -= s[(c0 + r) * kBLd + c0 + k] * s[(c0 + c) * kBLd + c0 + k];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        const int below = kBT - c0 - 6;
+        if (tid < below) {  // panel rows: x L_bb^T = a, one row per thread
+            double* row = s + (c0 + 6 + tid) * kBLd + c0;
+            double x[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double t = row[c];
+#pragma unroll
+                for (int p = 0; p < c; p++) t -= x[p] * s[(c0 + c) * kBLd + c0 + p];
+                x[c] = t * inv[c0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 6; c++) row[c] = x[c];
+        }
+        __syncthreads();
+        for (int e = tid; e < below * below; e += kBcThreads) {  // trailing update (lower part)
+            const int r = e / below, c = e - r * below;
+            if (c > r) continue;
+            const double* pr = s + (c0 + 6 + r) * kBLd + c0;
+            const double* pc = s + (c0 + 6 + c) * kBLd + c0;
+            double t = 0;
+#pragma unroll
+            for (int p = 0; p < 6; p++) t += pr[p] * pc[p];
+            s[(c0 + 6 + r) * kBLd + c0 + 6 + c] -= t;
+        }
+        __syncthreads();
+    }
+    return *fail == 0;
+}
+
+// X <- X L^-T for a 48 x 48 tile X (in place), L lower with reciprocal diagonal inv; 6 columns per step
+__device__ __forceinline__ void border_trsm(double* x, const double* l, const double* inv, int tid) {
+    for (int b = 0; b < kBTB; b++) {
+        const int c0 = b * 6;
+        for (int e = tid; e < kBT * 6; e += kBcThreads) {  // x[r][c0 + c] -= sum_{p < c0} x[r][p] l[c0 + c][p]
+            const int r = e / 6, c = e - r * 6;
+            const double* xr = x + r * kBLd;
+            const double* lc = l + (c0 + c) * kBLd;
+            double t = 0;
+            for (int p = 0; p < c0; p++) t += xr[p] * lc[p];
+            x[r * kBLd + c0 + c] -= t;
+        }
+        __syncthreads();
+        if (tid < kBT) {
+            double* row = x + tid * kBLd + c0;
+            double v[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double t = row[c];
+#pragma unroll
+                for (int p = 0; p < c; p++) t -= v[p] * l[(c0 + c) * kBLd + c0 + p];
+                v[c] = t * inv[c0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 6; c++) row[c] = v[c];
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void border_store_tile(const BorderView& v, int I, int K, const double* s, int tid, bool diag_zero_upper) {
+    for (int e = tid; e < kBTB * kBTB * 36; e += kBcThreads) {
+        const int bb = e / 36, w = e - bb * 36;
+        const int br = bb / kBTB, bc = bb - br * kBTB;
+        const int a = I * kBTB + br, k = K * kBTB + bc;
+        if (a >= v.nbord || k >= v.nbord || k > a) continue;
+        const int r = br * 6 + w / 6, c = bc * 6 + w % 6;
+        double x = s[r * kBLd + c];
+        if (k == a && w / 6 < w % 6) { if (!diag_zero_upper) continue; x = 0.0; }
+        v.blk(a, k)[w] = x;
+    }
+}
+
+__global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_band) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double bsm[];
+    double* sA = bsm;                 // diagonal tile / X_I
+    double* sB = sA + kBT * kBLd;     // X tile being solved / X_J
+    double* sinv = sB + kBT * kBLd;   // [48]
+    double* sv = sinv + kBT;          // [nbord * 6 padded] right-hand side
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    BorderView v;
+    v.d = d; v.n_band = n_band; v.nbord = d.Pf - n_band; v.nt = (v.nbord + kBTB - 1) / kBTB;
+    const int nt = v.nt, G = gridDim.x, me = blockIdx.x;
+    if (tid == 0) s_fail = d.scalars[4] != 0.0;
+    __syncthreads();
+    bool dead = s_fail != 0;  // the band factorisation failed: nothing to do (uniform over the grid)
+    for (int K = 0; K < nt && !dead; K++) {
+        // ---- POTRF (K, K) in every CTA that has a TRSM tile (CTA 0 always, it owns the write-back) + TRSM of column K
+        const int ntr = nt - K - 1;
+        const bool work = me == 0 || me < ntr;
+        if (work) {
+            border_load_tile(v, K, K, sA, tid);
+            __syncthreads();
+            border_potrf(sA, sinv, &s_fail, tid);
+            if (me == 0) {
+                border_store_tile(v, K, K, sA, tid, true);
+                for (int c = tid; c < kBT; c += kBcThreads)
+                    if (K * kBT + c < v.nbord * 6) d.invd[(size_t)n_band * 6 + K * kBT + c] = sinv[c];
+                if (tid == 0 && s_fail) d.scalars[4] = 1.0;
+            }
+            for (int t = me; t < ntr; t += G) {
+                const int I = K + 1 + t;
+                border_load_tile(v, I, K, sB, tid);
+                __syncthreads();
+                border_trsm(sB, sA, sinv, tid);
+                border_store_tile(v, I, K, sB, tid, false);
+                __syncthreads();
+            }
+        }
+        __threadfence();
+        grid.sync();
+        if (d.scalars[4] != 0.0) { dead = true; break; }  // a pivot failed somewhere: every CTA sees it after the barrier
+        // ---- trailing updates A_IJ -= X_IK X_JK^T (K < J <= I), one tile per CTA, fp64 MMA
+        const int m = nt - K - 1, ntask = m * (m + 1) / 2;
+        for (int t = me; t < ntask; t += G) {
+            int ii = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (ii * (ii + 1) / 2 > t) ii--;
+            while ((ii + 1) * (ii + 2) / 2 <= t) ii++;
+            const int jj = t - ii * (ii + 1) / 2;
+            const int I = K + 1 + ii, J = K + 1 + jj;
+            border_load_tile(v, I, K, sA, tid);
+            if (J != I) border_load_tile(v, J, K, sB, tid);
+            __syncthreads();
+            const double* xi = sA;
+            const double* xj = J == I ? sA : sB;
+            const int g = lane >> 2, q = lane & 3;
+            for (int sub = warp; sub < 36; sub += kBcThreads / 32) {  // 6 x 6 output sub-tiles of 8 x 8
+                const int si = sub / 6, sj = sub - si * 6;
+                if (J == I && sj > si) continue;
+                const int r = si * 8 + g, c = sj * 8 + 2 * q;  // this lane's two outputs: (r, c), (r, c + 1)
+                const int a = I * kBTB + r / 6, k = J * kBTB + c / 6;
+                const bool live = a < v.nbord && k < v.nbord && k <= a;
+                double* out = live ? v.blk(a, k) + (r % 6) * 6 + c % 6 : nullptr;
+                double c0 = live ? out[0] : 0.0, c1 = live ? out[1] : 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < kBT; k0 += 4)
+                    dmma_m8n8k4(c0, c1, -xi[(si * 8 + g) * kBLd + k0 + q], xj[(sj * 8 + g) * kBLd + k0 + q]);
+                if (live) { out[0] = c0; out[1] = c1; }
+            }
+            __syncthreads();
+        }
+        __threadfence();
+        grid.sync();
+    }
+    if (me != 0 || dead) return;
+    // ---- L y = b, L^T x = y for the border right-hand side (xp of the border rows), tile by tile
+    const int n6 = v.nbord * 6;
+    for (int i = tid; i < nt * kBT; i += kBcThreads) sv[i] = i < n6 ? d.xp[(size_t)n_band * 6 + i] : 0.0;
+    __syncthreads();
+    for (int K = 0; K < nt; K++) {  // forward
+        border_load_tile(v, K, K, sA, tid);
+        for (int c = tid; c < kBT; c += kBcThreads) sinv[c] = K * kBT + c < n6 ? d.invd[(size_t)n_band * 6 + K * kBT + c] : 1.0;
+        __syncthreads();
+        for (int b = 0; b < kBTB; b++) {
+            const int c0 = b * 6;
+            if (tid < 6) {  // y[c0 + tid] -= sum_{p < c0} L[c0 + tid][p] y[p]
+                double t = 0;
+                for (int p = 0; p < c0; p++) t += sA[(c0 + tid) * kBLd + p] * sv[K * kBT + p];
+                sv[K * kBT + c0 + tid] -= t;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double y[6];
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    double t = sv[K * kBT + c0 + r];
+#pragma unroll
+                    for (int p = 0; p < r; p++) t -= sA[(c0 + r) * kBLd + c0 + p] * y[p];
+                    y[r] = t * sinv[c0 + r];
+                }
+#pragma unroll
+                for (int r = 0; r < 6; r++) sv[K * kBT + c0 + r] = y[r];
+            }
+            __syncthreads();
+        }
+        // b_I -= L_IK y_K for the tiles below: one thread per row
+        for (int r = tid; r < (nt - K - 1) * kBT; r += kBcThreads) {
+            const int I = K + 1 + r / kBT, rr = r % kBT;
+            const int a = I * kBTB + rr / 6;
+            if (a >= v.nbord) continue;
+            double t = 0;
+            for (int bc = 0; bc < kBTB; bc++) {
+                const int k = K * kBTB + bc;
+                if (k >= v.nbord) break;
+                const double* L = v.blk(a, k) + (rr % 6) * 6;
+#pragma unroll
+                for (int p = 0; p < 6; p++) t += L[p] * sv[K * kBT + bc * 6 + p];
+            }
+            sv[I * kBT + rr] -= t;
+        }
+        __syncthreads();
+    }
+    for (int K = nt - 1; K >= 0; K--) {  // backward: x_K = L_KK^-T (y_K - sum_{I > K} L_IK^T x_I)
+        for (int c = tid; c < kBT; c += kBcThreads) {
+            const int k = K * kBTB + c / 6;
+            double t = 0;
+            if (k < v.nbord)
+                for (int a = (K + 1) * kBTB; a < v.nbord; a++) {
+                    const double* L = v.blk(a, k) + c % 6;
+                    const double* x = sv + (a / kBTB) * kBT + (a % kBTB) * 6;
+#pragma unroll
+                    for (int p = 0; p < 6; p++) t += L[p * 6] * x[p];
+                }
+            sv[K * kBT + c] -= t;
+        }
+        border_load_tile(v, K, K, sA, tid);
+        for (int c = tid; c < kBT; c += kBcThreads) sinv[c] = K * kBT + c < n6 ? d.invd[(size_t)n_band * 6 + K * kBT + c] : 1.0;
+        __syncthreads();
+        for (int b = kBTB - 1; b >= 0; b--) {
+            const int c0 = b * 6;
+            if (tid < 6) {  // x[c0 + tid] -= sum_{p >= c0 + 6} L[p][c0 + tid] x[p]
+                double t = 0;
+                for (int p = c0 + 6; p < kBT; p++) t += sA[p * kBLd + c0 + tid] * sv[K * kBT + p];
+                sv[K * kBT + c0 + tid] -= t;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double x[6];
+#pragma unroll
+                for (int r = 5; r >= 0; r--) {
+                    double t = sv[K * kBT + c0 + r];
+#pragma unroll
+                    for (int p = r + 1; p < 6; p++) t -= sA[(c0 + p) * kBLd + c0 + r] * x[p];
+                    x[r] = t * sinv[c0 + r];
+                }
+#pragma unroll
+                for (int r = 0; r < 6; r++) sv[K * kBT + c0 + r] = x[r];
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n6; i += kBcThreads) d.xp[(size_t)n_band * 6 + i] = sv[i];
+}
+
+// x_i -= sum_j L_ji^T x_j for every band column i over the border rows j whose envelope reaches i (descending j)
+__global__ void __launch_bounds__(256) k_ba_border_to_band(BaDev d, int n_band) {
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_band || d.scalars[4] != 0.0) return;
+    const int nbord = d.Pf - n_band;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int a = nbord - 1 - lane; a >= 0; a -= 32) {
+        const int j = n_band + a;
+        if (d.first[j] > i) continue;
+        const double* L = d.S + ((size_t)(d.rowoff[j] - d.first[j]) + i) * 36;
+        const double* x = d.xp + (size_t)j * 6;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            const double xr = x[r];
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[c] += L[r * 6 + c] * xr;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[c] += __shfl_down_sync(0xffffffffu, acc[c], o);
+    if (lane == 0)
+#pragma unroll
+        for (int c = 0; c < 6; c++) d.xp[(size_t)i * 6 + c] -= acc[c];
+}
+
+}  // namespace corb
