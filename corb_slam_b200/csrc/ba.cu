@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <climits>
 #include <atomic>
 #include <chrono>
 #include <numeric>
@@ -144,6 +145,8 @@ struct BaDev {
     const int *coloff_b, *col_rows_b;
     const int *chunk_start;        // [n_chunks + 1] band columns of each independent chunk
     double *syrk_part;             // [border pairs][n_chunks][36] per-chunk parts of the border x border update
+    const int* bstart;             // [n_border][n_chunks] first band column of chunk q a border row is coupled with (INT_MAX: none):
+                                   // left of it the row's blocks in that chunk are structurally zero (fill-in only runs forward)
     double *bpart;                 // [n_border][n_chunks][6] per-chunk parts of the border rows' forward substitution  // same lists without the border rows in the band columns (bordered solve)
     double *S, *bs;                // reduced system: [S | bs] contiguous
     double *invd;                  // [Pf * 6] reciprocals of the diagonal of the Cholesky factor (triangular solves multiply)
@@ -945,6 +948,36 @@ __global__ void __launch_bounds__(1024) k_ba_border_dense(BaDev d, int n_band) {
     if (s_fail && tid == 0) d.scalars[4] = 1.0;
 }
 
+// ---- border structure: bstart[b][q] = the first band column of chunk q that border row b shares a landmark with
+__global__ void __launch_bounds__(256) k_ba_border_starts(BaDev d, int n_band, int nq, int* __restrict__ bstart) {
+    const int l = blockIdx.x * 256 + threadIdx.x;
+    if (l >= d.L) return;
+    const int e0 = d.lm_off[l], e1 = d.lm_off[l + 1];
+    bool any = false;
+    for (int e = e0; e < e1; e++) any |= d.pfree[d.e_pose[e]] >= n_band;
+    if (!any) return;
+    for (int eb = e0; eb < e1; eb++) {
+        const int b = d.pfree[d.e_pose[eb]];
+        if (b < n_band) continue;
+        for (int e = e0; e < e1; e++) {
+            const int p = d.pfree[d.e_pose[e]];
+            if (p < 0 || p >= n_band) continue;
+            int q = 0;
+            while (q + 1 < nq && d.chunk_start[q + 1] <= p) q++;
+            atomicMin(&bstart[(size_t)(b - n_band) * nq + q], p);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_ba_fill_int(int* p, int n, int v) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void __launch_bounds__(256) k_ba_int_to_double(const int* a, double* b, int n, int back, int* a_out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (back) a_out[i] = (int)b[i]; else b[i] = (double)a[i];
+}
+
 // ---- K12c: the border rows (keyframes with long-range links, ordered last) against the finished band factor.
 //      L_jk = (A_jk - sum_{c<k} L_jc L_kc^T) L_kk^-T only needs row j itself and the band rows, so every border row is
 //      swept left to right on its own: one small CTA per border row, all rows concurrently, instead of riding along as
@@ -1022,7 +1055,12 @@ __global__ void __launch_bounds__(64) k_ba_border_rows(BaDev d, int n_band, int 
     };
     double a_cur = 0;
     double bj = 0.0;  // this chunk's part of sum_k L_jk y_k (k_ba_border_rhs subtracts the parts in chunk order)
-    const int k_lo = max(fj, d.chunk_start[q]), k_hi = min(d.chunk_start[q + 1], n_band);
+    // the row has no entry in this chunk left of its first coupling there (bstart); columns skipped that way read as zero
+    // from the ring, and their blocks in the skyline stay zero from the memset of the trial
+    const int k_hi = min(d.chunk_start[q + 1], n_band);
+    const int k_lo = min(k_hi, max(max(fj, d.chunk_start[q]), d.bstart[(size_t)blockIdx.x * nq + q]));
+    for (int i = tid; i < kBorderRing * 36; i += 64) ring[0][i] = 0.0;
+    __syncthreads();
     if (k_lo < k_hi) {
         fetch_issue(k_lo, 0);
         fetch_commit(k_lo, 0);
@@ -1217,7 +1255,8 @@ __global__ void __launch_bounds__(256) k_ba_border_syrk(BaDev d, int n_band, int
     while ((a + 1) * (a + 2) / 2 <= p) a++;
     const int b = p - a * (a + 1) / 2;
     const int j = n_band + a, i = n_band + b;
-    const int k0 = max(max(d.first[j], d.first[i]), d.chunk_start[q]), k1 = min(n_band, d.chunk_start[q + 1]);
+    const int k1 = min(n_band, d.chunk_start[q + 1]);
+    const int k0 = min(k1, max(max(max(d.first[j], d.first[i]), d.chunk_start[q]), max(d.bstart[(size_t)a * nq + q], d.bstart[(size_t)b * nq + q])));
     const double* Lj = d.S + (size_t)(d.rowoff[j] - d.first[j]) * 36;
     const double* Li = d.S + (size_t)(d.rowoff[i] - d.first[i]) * 36;
     const int r0 = lane / 6, c0 = lane - r0 * 6, c1 = 2 + lane;
@@ -2069,6 +2108,24 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     AL(S, H.s_doubles + (size_t)Pf * 6);
     AL(xp, (size_t)Pf * 6); AL(xl, (size_t)L * 3); AL(invd, (size_t)Pf * 6 + 6);
     AL(bpart, (size_t)std::max(1, Pf - H.n_band) * H.n_chunks * 6);
+    {
+        const int nbs = std::max(1, Pf - H.n_band) * H.n_chunks;
+        int* bstart = nullptr;
+        if ((rc = H.alloc(&bstart, (size_t)nbs)) != CORB_OK) return rc;
+        k_ba_fill_int<<<(nbs + 255) / 256, 256, 0, H.stream>>>(bstart, nbs, INT_MAX);
+        d.bstart = bstart;
+        if (Pf > H.n_band && L > 0) {
+            k_ba_border_starts<<<(L + 255) / 256, 256, 0, H.stream>>>(d, H.n_band, H.n_chunks, bstart);
+            if (allreduce) {  // every rank sees its own landmarks only: the structure is the union (minimum) over the ranks
+                double* tmp = nullptr;
+                if ((rc = H.alloc(&tmp, (size_t)nbs)) != CORB_OK) return rc;
+                k_ba_int_to_double<<<(nbs + 255) / 256, 256, 0, H.stream>>>(bstart, tmp, nbs, 0, nullptr);
+                if ((rc = H.reduce(tmp, (size_t)nbs, 1)) != CORB_OK) return rc;
+                k_ba_int_to_double<<<(nbs + 255) / 256, 256, 0, H.stream>>>(nullptr, tmp, nbs, 1, bstart);
+            }
+        }
+        CORB_CUDA(cudaGetLastError());
+    }
     {
         const size_t nb = (size_t)(Pf - H.n_band);
         AL(syrk_part, std::max<size_t>(1, nb * (nb + 1) / 2 * H.n_chunks * 36));

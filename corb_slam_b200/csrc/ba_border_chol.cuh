@@ -272,19 +272,7 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
         }
         __syncthreads();
     }
-    for (int K = nt - 1; K >= 0; K--) {  // backward: x_K = L_KK^-T (y_K - sum_{I > K} L_IK^T x_I)
-        for (int c = tid; c < kBT; c += kBcThreads) {
-            const int k = K * kBTB + c / 6;
-            double t = 0;
-            if (k < v.nbord)
-                for (int a = (K + 1) * kBTB; a < v.nbord; a++) {
-                    const double* L = v.blk(a, k) + c % 6;
-                    const double* x = sv + (a / kBTB) * kBT + (a % kBTB) * 6;
-#pragma unroll
-                    for (int p = 0; p < 6; p++) t += L[p * 6] * x[p];
-                }
-            sv[K * kBT + c] -= t;
-        }
+    for (int K = nt - 1; K >= 0; K--) {  // backward, right-looking: x_K = L_KK^-T y_K, then y_J -= L_KJ^T x_K for the tiles J < K
         border_load_tile(v, K, K, sA, tid);
         for (int c = tid; c < kBT; c += kBcThreads) sinv[c] = K * kBT + c < n6 ? d.invd[(size_t)n_band * 6 + K * kBT + c] : 1.0;
         __syncthreads();
@@ -310,6 +298,21 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
             }
             __syncthreads();
         }
+        // every entry (block column k < 8 K, component c) of the rows above takes its 48 terms: the blocks (a, k) of a row a
+        // are contiguous in the skyline, so neighbouring threads read neighbouring memory
+        const int a_lo = K * kBTB, a_hi = min(v.nbord, a_lo + kBTB);
+        for (int o = tid; o < K * kBT; o += kBcThreads) {
+            const int k = o / 6, c = o - k * 6;
+            double t = 0;
+            for (int a = a_lo; a < a_hi; a++) {
+                const double* L = v.blk(a, k) + c;
+                const double* x = sv + K * kBT + (a - a_lo) * 6;
+#pragma unroll
+                for (int p = 0; p < 6; p++) t += L[p * 6] * x[p];
+            }
+            sv[o] -= t;
+        }
+        __syncthreads();
     }
     for (int i = tid; i < n6; i += kBcThreads) d.xp[(size_t)n_band * 6 + i] = sv[i];
 }
