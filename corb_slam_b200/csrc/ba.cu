@@ -371,45 +371,76 @@ constexpr int kAccSlots = 16, kBaseSlots = 32;
 // fit go to `row` in global memory when allowed (single-warp use only), else *overflow is raised and the term is dropped
 __device__ __forceinline__ void schur_accumulate(const BaDev& d, int pi, int j, int w0, int step, double (*acc)[36], int* tags, int& nslots,
                                                  double& coeff, double* row, int fj, bool global_ok, int* overflow) {
+    // Every edge costs a chain of dependent index loads (pose_edges -> e_point -> lfree / lm_off, then e_pose -> pfree per
+    // co-observing keyframe). The chains of 32 edges are walked by the 32 lanes at once and handed round with shuffles; the
+    // co-observers' indices of a landmark are fetched the same way, and the landmark's W blocks (contiguous: edges are
+    // grouped by landmark) are prefetched while they resolve. A warp takes batches of 32 consecutive edges of the row
+    // (batch w0, w0 + step, ...), inside a batch in order: a fixed summation order.
     const int lane = threadIdx.x & 31;
     const int r0 = lane / 6, c0 = lane - r0 * 6;  // entry `lane`
     const int c1 = 2 + lane;                      // entry 32 + lane = (5, 2 + lane) for lane < 4
-    for (int k = d.pose_off[pi] + w0; k < d.pose_off[pi + 1]; k += step) {
-        const int e = d.pose_edges[k];
-        const int l = d.e_point[e];
-        if (d.lfree[l] < 0) continue;
-        const double* Di = d.Dinv + (size_t)l * 9;
-        const double* We = d.W + (size_t)e * 18;
-        double bd0[3], bd1[3];
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            bd0[m] = We[r0 * 3] * Di[m] + We[r0 * 3 + 1] * Di[3 + m] + We[r0 * 3 + 2] * Di[6 + m];
-            bd1[m] = We[15] * Di[m] + We[16] * Di[3 + m] + We[17] * Di[6 + m];
-        }
-        if (lane < 6) {
-            const double* dbl = d.db + (size_t)l * 3;
-            coeff += We[lane * 3] * dbl[0] + We[lane * 3 + 1] * dbl[1] + We[lane * 3 + 2] * dbl[2];
-        }
-        for (int e2 = d.lm_off[l]; e2 < d.lm_off[l + 1]; e2++) {
-            const int j2 = d.pfree[d.e_pose[e2]];
-            if (j2 < 0 || j2 > j) continue;
-            const double* W2 = d.W + (size_t)e2 * 18;
-            int slot = -1;  // warp-uniform lookup (j2 is the same for every lane)
-            const int tg = lane < kAccSlots ? tags[lane] : -2;
-            const unsigned hit = __ballot_sync(0xffffffffu, tg == j2);
-            if (hit) {
-                slot = __ffs(hit) - 1;
-            } else if (nslots < kAccSlots) {
-                slot = nslots++;
-                if (lane == 0) tags[slot] = j2;
-                __syncwarp();
+    const int k_end = d.pose_off[pi + 1];
+    for (int kb = d.pose_off[pi] + 32 * w0; kb < k_end; kb += 32 * step) {
+        int e_l = -1, l_l = 0, o0_l = 0, o1_l = 0;
+        if (kb + lane < k_end) {
+            e_l = d.pose_edges[kb + lane];
+            l_l = d.e_point[e_l];
+            if (d.lfree[l_l] < 0) {
+                e_l = -1;
+            } else {
+                o0_l = d.lm_off[l_l];
+                o1_l = d.lm_off[l_l + 1];
             }
-            double* blk;
-            if (slot >= 0) blk = acc[slot];
-            else if (global_ok) blk = row + (size_t)(j2 - fj) * 36;
-            else { if (lane == 0) *overflow = 1; continue; }
-            blk[lane] -= bd0[0] * W2[c0 * 3] + bd0[1] * W2[c0 * 3 + 1] + bd0[2] * W2[c0 * 3 + 2];
-            if (lane < 4) blk[32 + lane] -= bd1[0] * W2[c1 * 3] + bd1[1] * W2[c1 * 3 + 1] + bd1[2] * W2[c1 * 3 + 2];
+        }
+        const int cnt = min(32, k_end - kb);
+        for (int i = 0; i < cnt; i++) {
+            const int e = __shfl_sync(0xffffffffu, e_l, i);
+            if (e < 0) continue;
+            const int l = __shfl_sync(0xffffffffu, l_l, i), p0 = __shfl_sync(0xffffffffu, o0_l, i), p1 = __shfl_sync(0xffffffffu, o1_l, i);
+            {   // the landmark's W blocks, 144 B per edge: one 128-byte line per lane
+                const char* wb = reinterpret_cast<const char*>(d.W + (size_t)p0 * 18);
+                const size_t bytes = (size_t)(p1 - p0) * 144;
+                if ((size_t)lane * 128 < bytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + (size_t)lane * 128));
+            }
+            int j2_l = -1;
+            if (p0 + lane < p1) j2_l = d.pfree[d.e_pose[p0 + lane]];
+            const double* Di = d.Dinv + (size_t)l * 9;
+            const double* We = d.W + (size_t)e * 18;
+            double bd0[3], bd1[3];
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                bd0[m] = We[r0 * 3] * Di[m] + We[r0 * 3 + 1] * Di[3 + m] + We[r0 * 3 + 2] * Di[6 + m];
+                bd1[m] = We[15] * Di[m] + We[16] * Di[3 + m] + We[17] * Di[6 + m];
+            }
+            if (lane < 6) {
+                const double* dbl = d.db + (size_t)l * 3;
+                coeff += We[lane * 3] * dbl[0] + We[lane * 3 + 1] * dbl[1] + We[lane * 3 + 2] * dbl[2];
+            }
+            for (int cb = p0; cb < p1; cb += 32) {
+                if (cb != p0) j2_l = cb + lane < p1 ? d.pfree[d.e_pose[cb + lane]] : -1;
+                const int m2 = min(32, p1 - cb);
+                for (int t = 0; t < m2; t++) {
+                    const int j2 = __shfl_sync(0xffffffffu, j2_l, t);
+                    if (j2 < 0 || j2 > j) continue;
+                    const double* W2 = d.W + (size_t)(cb + t) * 18;
+                    int slot = -1;  // warp-uniform lookup (j2 is the same for every lane)
+                    const int tg = lane < kAccSlots ? tags[lane] : -2;
+                    const unsigned hit = __ballot_sync(0xffffffffu, tg == j2);
+                    if (hit) {
+                        slot = __ffs(hit) - 1;
+                    } else if (nslots < kAccSlots) {
+                        slot = nslots++;
+                        if (lane == 0) tags[slot] = j2;
+                        __syncwarp();
+                    }
+                    double* blk;
+                    if (slot >= 0) blk = acc[slot];
+                    else if (global_ok) blk = row + (size_t)(j2 - fj) * 36;
+                    else { if (lane == 0) *overflow = 1; continue; }
+                    blk[lane] -= bd0[0] * W2[c0 * 3] + bd0[1] * W2[c0 * 3 + 1] + bd0[2] * W2[c0 * 3 + 2];
+                    if (lane < 4) blk[32 + lane] -= bd1[0] * W2[c1 * 3] + bd1[1] * W2[c1 * 3 + 1] + bd1[2] * W2[c1 * 3 + 2];
+                }
+            }
         }
     }
 }
@@ -1978,7 +2009,9 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         int wmax = 0;
         for (int j = 0; j < H.n_band; j++) wmax = std::max(wmax, j - (int)firstd[j]);
         const char* qenv = getenv("CORB_BA_CHUNKS");
-        int Q = qenv ? atoi(qenv) : 8;  // measured on B200 (P = 2000): 4 -> 4.4, 6 -> 3.9, 8 -> 4.1, 12 -> 5.3, 16 -> 7.5 ms per solve
+        // chunks of ~120 band columns: measured on B200 at P = 2000 with the tiled border solver: Q = 8 -> 2.2, 12 -> 1.8, 16 -> 1.5,
+        // 24 -> 1.5, 31 -> 1.9 ms per solve (more chunks shorten the serial sweeps and grow the dense border block)
+        int Q = qenv ? atoi(qenv) : std::min(24, H.n_band / 120);
         Q = std::min(Q, H.n_band / 64);
         if (wmax >= 1 && wmax <= 8 && Q >= 2 && H.n_band - (Q - 1) * wmax >= Q) {
             const int nb0 = H.n_band, nbord0 = Pf - nb0;
@@ -2045,7 +2078,7 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             CORB_SMEM_OPT_IN(k_ba_border_dense);
         if (nbord > 0 && !getenv("CORB_BA_BORDER_OLD")) {
             const int nt = ((int)nbord + kBTB - 1) / kBTB;
-            H.border_tiled_bytes = ((size_t)2 * kBT * kBLd + kBT + (size_t)nt * kBT) * sizeof(double);
+            H.border_tiled_bytes = ((size_t)2 * kBT * kBLd + kBT + (size_t)nt * kBT + (size_t)nt * kBTB) * sizeof(double);
             int dev = 0, sms = 0, coop = 0, per_sm = 0;
             CORB_CUDA(cudaGetDevice(&dev));
             CORB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -28,11 +28,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 struct BorderView {
     BaDev d;
     int n_band, nbord, nt;
+    const long long* rowbase;  // shared memory: block offset of (a, 0) in the skyline, per border row a
     // block (a, k) of the border matrix (border-local indices, k <= a) in the skyline
-    __device__ __forceinline__ double* blk(int a, int k) const {
-        const int j = n_band + a;
-        return d.S + ((size_t)(d.rowoff[j] - d.first[j]) + n_band + k) * 36;
-    }
+    __device__ __forceinline__ double* blk(int a, int k) const { return d.S + (size_t)(rowbase[a] + k) * 36; }
 };
 
 // tile (I, K), I >= K, into shared memory as a dense 48 x 48 array; padding rows / columns continue the identity
@@ -58,23 +56,25 @@ __device__ __forceinline__ bool border_potrf(double* s, double* inv, int* fail, 
     const int lane = tid & 31, warp = tid >> 5;
     for (int b = 0; b < kBTB; b++) {
         const int c0 = b * 6;
-        if (warp == 0) {
-            for (int k = 0; k < 6; k++) {
-                const double piv = s[(c0 + k) * kBLd + c0 + k];
-                const bool ok = piv > 0.0;
-                const double iv = rsqrt(ok ? piv : 1.0);
-                if (!ok && lane == 0) *fail = 1;
-                __syncwarp();
-                if (lane == 0) { s[(c0 + k) * kBLd + c0 + k] = (ok ? piv : 1.0) * iv; inv[c0 + k] = iv; }
-                if (lane > k && lane < 6) s[(c0 + lane) * kBLd + c0 + k] *= iv;
-                __syncwarp();
-                if (lane < 21) {  // the 21 lower-triangle entries of the 6 x 6 block, one per lane
-                    const int r = lane >= 15 ? 5 : lane >= 10 ? 4 : lane >= 6 ? 3 : lane >= 3 ? 2 : lane >= 1 ? 1 : 0;
-                    const int c = lane - r * (r + 1) / 2;
-                    if (c > k) s[(c0 + r) * kBLd + c0 + c] -= s[(c0 + r) * kBLd + c0 + k] * s[(c0 + c) * kBLd + c0 + k];
-                }
-                __syncwarp();
+        if (warp == 0) {  // the 6 x 6 diagonal block in registers: lane = one of its 21 lower-triangle entries
+            int r = 0, c = 0;
+            if (lane < 21) {
+                r = lane >= 15 ? 5 : lane >= 10 ? 4 : lane >= 6 ? 3 : lane >= 3 ? 2 : lane >= 1 ? 1 : 0;
+                c = lane - r * (r + 1) / 2;
             }
+            double a = lane < 21 ? s[(c0 + r) * kBLd + c0 + c] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                double akk = __shfl_sync(0xffffffffu, a, k * (k + 1) / 2 + k);
+                if (!(akk > 0.0)) { if (lane == 0) *fail = 1; akk = 1.0; }
+                const double iv = rsqrt(akk), dk = akk * iv;
+                if (lane == 0) inv[c0 + k] = iv;
+                if (lane < 21 && c == k) a = (r == k) ? dk : a * iv;
+                const double lrk = __shfl_sync(0xffffffffu, a, r * (r + 1) / 2 + min(k, r));
+                const double lck = __shfl_sync(0xffffffffu, a, c * (c + 1) / 2 + min(k, c));
+                if (lane < 21 && c > k) a -= lrk * lck;
+            }
+            if (lane < 21) s[(c0 + r) * kBLd + c0 + c] = a;
         }
         __syncthreads();
         const int below = kBT - c0 - 6;
@@ -163,6 +163,9 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
     BorderView v;
     v.d = d; v.n_band = n_band; v.nbord = d.Pf - n_band; v.nt = (v.nbord + kBTB - 1) / kBTB;
     const int nt = v.nt, G = gridDim.x, me = blockIdx.x;
+    long long* rowbase = reinterpret_cast<long long*>(sv + (size_t)nt * kBT);
+    for (int a = tid; a < v.nbord; a += kBcThreads) rowbase[a] = (long long)(d.rowoff[n_band + a] - d.first[n_band + a]) + n_band;
+    v.rowbase = rowbase;
     if (tid == 0) s_fail = d.scalars[4] != 0.0;
     __syncthreads();
     bool dead = s_fail != 0;  // the band factorisation failed: nothing to do (uniform over the grid)
@@ -180,12 +183,47 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
                     if (K * kBT + c < v.nbord * 6) d.invd[(size_t)n_band * 6 + K * kBT + c] = sinv[c];
                 if (tid == 0 && s_fail) d.scalars[4] = 1.0;
             }
+            // forward substitution rides along: y_K = L_KK^-1 b_K (every working CTA, redundantly), b_I -= X_IK y_K by the
+            // CTA that owns tile row I in this step
+            double* sy = sv;  // [48]
+            for (int c = tid; c < kBT; c += kBcThreads) sy[c] = K * kBT + c < v.nbord * 6 ? d.xp[(size_t)n_band * 6 + K * kBT + c] : 0.0;
+            __syncthreads();
+            for (int b = 0; b < kBTB; b++) {
+                const int c0 = b * 6;
+                if (tid < 6) {
+                    double t = 0;
+                    for (int p = 0; p < c0; p++) t += sA[(c0 + tid) * kBLd + p] * sy[p];
+                    sy[c0 + tid] -= t;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    double y[6];
+#pragma unroll
+                    for (int r = 0; r < 6; r++) {
+                        double t = sy[c0 + r];
+#pragma unroll
+                        for (int p = 0; p < r; p++) t -= sA[(c0 + r) * kBLd + c0 + p] * y[p];
+                        y[r] = t * sinv[c0 + r];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 6; r++) sy[c0 + r] = y[r];
+                }
+                __syncthreads();
+            }
+            if (me == 0)
+                for (int c = tid; c < kBT; c += kBcThreads)
+                    if (K * kBT + c < v.nbord * 6) d.xp[(size_t)n_band * 6 + K * kBT + c] = sy[c];
             for (int t = me; t < ntr; t += G) {
                 const int I = K + 1 + t;
                 border_load_tile(v, I, K, sB, tid);
                 __syncthreads();
                 border_trsm(sB, sA, sinv, tid);
                 border_store_tile(v, I, K, sB, tid, false);
+                if (tid < kBT && I * kBT + tid < v.nbord * 6) {
+                    double acc = 0;
+                    for (int p = 0; p < kBT; p++) acc += sB[tid * kBLd + p] * sy[p];
+                    d.xp[(size_t)n_band * 6 + I * kBT + tid] -= acc;
+                }
                 __syncthreads();
             }
         }
@@ -225,53 +263,10 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
         grid.sync();
     }
     if (me != 0 || dead) return;
-    // ---- L y = b, L^T x = y for the border right-hand side (xp of the border rows), tile by tile
+    // ---- L^T x = y for the border right-hand side (y was formed along the factorisation), tile by tile
     const int n6 = v.nbord * 6;
     for (int i = tid; i < nt * kBT; i += kBcThreads) sv[i] = i < n6 ? d.xp[(size_t)n_band * 6 + i] : 0.0;
     __syncthreads();
-    for (int K = 0; K < nt; K++) {  // forward
-        border_load_tile(v, K, K, sA, tid);
-        for (int c = tid; c < kBT; c += kBcThreads) sinv[c] = K * kBT + c < n6 ? d.invd[(size_t)n_band * 6 + K * kBT + c] : 1.0;
-        __syncthreads();
-        for (int b = 0; b < kBTB; b++) {
-            const int c0 = b * 6;
-            if (tid < 6) {  // y[c0 + tid] -= sum_{p < c0} L[c0 + tid][p] y[p]
-                double t = 0;
-                for (int p = 0; p < c0; p++) t += sA[(c0 + tid) * kBLd + p] * sv[K * kBT + p];
-                sv[K * kBT + c0 + tid] -= t;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                double y[6];
-#pragma unroll
-                for (int r = 0; r < 6; r++) {
-                    double t = sv[K * kBT + c0 + r];
-#pragma unroll
-                    for (int p = 0; p < r; p++) t -= sA[(c0 + r) * kBLd + c0 + p] * y[p];
-                    y[r] = t * sinv[c0 + r];
-                }
-#pragma unroll
-                for (int r = 0; r < 6; r++) sv[K * kBT + c0 + r] = y[r];
-            }
-            __syncthreads();
-        }
-        // b_I -= L_IK y_K for the tiles below: one thread per row
-        for (int r = tid; r < (nt - K - 1) * kBT; r += kBcThreads) {
-            const int I = K + 1 + r / kBT, rr = r % kBT;
-            const int a = I * kBTB + rr / 6;
-            if (a >= v.nbord) continue;
-            double t = 0;
-            for (int bc = 0; bc < kBTB; bc++) {
-                const int k = K * kBTB + bc;
-                if (k >= v.nbord) break;
-                const double* L = v.blk(a, k) + (rr % 6) * 6;
-#pragma unroll
-                for (int p = 0; p < 6; p++) t += L[p] * sv[K * kBT + bc * 6 + p];
-            }
-            sv[I * kBT + rr] -= t;
-        }
-        __syncthreads();
-    }
     for (int K = nt - 1; K >= 0; K--) {  // backward, right-looking: x_K = L_KK^-T y_K, then y_J -= L_KJ^T x_K for the tiles J < K
         border_load_tile(v, K, K, sA, tid);
         for (int c = tid; c < kBT; c += kBcThreads) sinv[c] = K * kBT + c < n6 ? d.invd[(size_t)n_band * 6 + K * kBT + c] : 1.0;
