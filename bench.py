@@ -650,7 +650,7 @@ def run_ours(args):
 
     # ---- global BA (second half of the BASELINE.json metric): landmark-sharded over the ranks, reduced camera system
     #      all-reduced over NCCL from inside corb_ba_solve when more than one GPU is attached
-    ba_info, ba_ms, ba_rms, ba_edges, ba_allreduce, ba_parity = None, 0.0, None, 0, None, None
+    ba_info, ba_ms, ba_rms, ba_edges, ba_allreduce, ba_parity, ba_server = None, 0.0, None, 0, None, None, None
     if not args.no_ba:
         from corb_slam_b200 import Optimizer, torch_allreduce
         from corb_slam_b200.synth import ba_problem, ba_shard
@@ -694,6 +694,36 @@ def run_ours(args):
                              "max_abs_point": float(np.abs(pts.cpu().numpy() - full["point_xyz"]).max()),
                              "rank_spread": float((pmax - pmin).abs().max()),
                              "chi2_final_single": finfo["chi2_final"], "ms_single_gpu_same_run": single_ms}
+            barrier()
+            # the server's own shape of the same thing: ONE process, N threads, N ncclComm_t, ncclAllReduce hook in C
+            # (tests/host_harness/ba_nccl.cpp = what corbslam_server's GBA thread would call); the other ranks wait on the
+            # rendezvous store (a host-side wait: a NCCL barrier would spin on the GPUs the harness is using)
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                import tempfile
+                from corb_slam_b200.ba_file import read_result, write_problem
+                exe = os.path.join(ROOT, "tests", "host_harness", "ba_nccl")
+                if not os.path.exists(exe):
+                    subprocess.run(["make", "-C", os.path.dirname(exe)], capture_output=True)
+                tmp = tempfile.mkdtemp()
+                try:
+                    write_problem(os.path.join(tmp, "p.bin"), prob)
+                    r = subprocess.run([exe, str(world), os.path.join(tmp, "p.bin"), os.path.join(tmp, "r.bin"), str(BA_ITERS)],
+                                       capture_output=True, text=True, timeout=600)
+                    if r.returncode == 0:
+                        res = read_result(os.path.join(tmp, "r.bin"), BA_P, BA_L)
+                        ba_server = {"ms_total": res["ms_total"], "value": res["ms_total"] / (BA_L / 1e4), "unit": "ms/10k landmarks",
+                                     "accept_sequence_equal_to_torchrun_path": res["trial_accepted"] == ba_info["trial_accepted"],
+                                     "max_abs_pose_t_vs_torchrun_path": float(np.abs(res["pose_t"] - ba_out["pose_t"]).max()),
+                                     "rank_spread": res["rank_spread"], "chi2_final": res["chi2_final"],
+                                     "how": "one process, %d threads, %d ncclComm_t (ncclCommInitAll), ncclAllReduce hook" % (world, world)}
+                    else:
+                        ba_server = {"failed": (r.stdout + r.stderr)[-400:]}
+                except Exception as ex:  # the harness is an extra measurement, never the headline
+                    ba_server = {"failed": repr(ex)}
+                store.set("corb_ba_server_done", "1")
+            else:
+                store.wait(["corb_ba_server_done"])
             barrier()
             # the one exchange step of the sharded BA on its own: all-reduce(sum, fp64) of [S | bschur] (36 doubles per block of
             # the reduced camera system + 6 per pose), timed with CUDA events, against the NVLink roofline
@@ -798,7 +828,7 @@ def run_ours(args):
                 "iterations": ba_info["iterations"], "trials": ba_info["n_trials"], "trial_accepted": ba_info["trial_accepted"],
                 "chi2_initial": ba_info["chi2_initial"], "chi2_final": ba_info["chi2_final"], "rms_px": ba_rms,
                 "reduced_blocks": ba_info["reduced_blocks"], "band_chunks": ba_info["band_chunks"], "border_poses": ba_info["border_poses"],
-                "parity_vs_single": ba_parity,
+                "parity_vs_single": ba_parity, "server_path_one_process": ba_server,
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                              "algorithmic_bytes_per_iteration": ba_bytes // max(1, ba_info["iterations"]),
                              "note": "whole-call wall time incl. host structure build and H2D/D2H; the reduced-camera solve "
