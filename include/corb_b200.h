@@ -395,6 +395,25 @@ typedef int (*corb_allreduce_fn)(void* user, double* d_buf, size_t n, int op, vo
 CORB_API int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile uint8_t* stop, int robust, int device,
                            corb_ba_result* result, corb_allreduce_fn allreduce, void* allreduce_user);
 
+/* ------------------------------------------------------------------------------------------------ keyframe payload */
+
+/* Binary form of the extractor-produced part of a KeyFrame on the wire - mvKeys, mvKeysUn, mvuRight, mvDepth, mDescriptors,
+ * mBowVec, mFeatVec - instead of the decimal text boost::archive::text_oarchive writes for the same members
+ * [KeyFrame.h:61-87 (serialize), SerializeObject.h:34-61 (cv::Mat / cv::KeyPoint), DataDriver.cc:40-238]. One little-endian
+ * blob: 40-byte header (magic "CKF\1", version, flags, counts, CRC-32 of the body) + SoA arrays; bit-exact round trip,
+ * ~76 bytes per keypoint (61 without the BoW / feature vectors) instead of >= 236 characters. It travels inside the existing srv `DATA` string (version tag = the
+ * magic; a boost text archive never starts with it), so the ROS srv/msg surface is unchanged. Host code (no GPU needed).
+ * keys_un may be NULL or equal keys (rectified stereo: mvKeysUn == mvKeys, Frame.cc:410-414) and is then not stored. */
+CORB_API size_t corb_kf_payload_bound(int n, int n_bow, int n_fv, int n_fv_idx);
+CORB_API int corb_kf_payload_encode(const corb_keypoint* keys, const corb_keypoint* keys_un, const float* u_right, const float* depth,
+                                    const uint8_t* desc, int n, const uint32_t* bow_words, const double* bow_vals, int n_bow,
+                                    const uint32_t* fv_nodes, const int32_t* fv_off, const uint32_t* fv_idx, int n_fv, uint8_t* out,
+                                    size_t cap, size_t* written);
+CORB_API int corb_kf_payload_info(const uint8_t* buf, size_t len, int* n, int* n_bow, int* n_fv, int* n_fv_idx, int* same_un);
+CORB_API int corb_kf_payload_decode(const uint8_t* buf, size_t len, corb_keypoint* keys, corb_keypoint* keys_un, float* u_right,
+                                    float* depth, uint8_t* desc, uint32_t* bow_words, double* bow_vals, uint32_t* fv_nodes,
+                                    int32_t* fv_off, uint32_t* fv_idx);
+
 #ifdef __cplusplus
 }
 #endif
