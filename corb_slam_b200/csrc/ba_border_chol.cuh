@@ -150,6 +150,11 @@ __device__ __forceinline__ void border_store_tile(const BorderView& v, int I, in
     }
 }
 
+#ifdef CORB_CHOL_TRACE
+#define CH_T(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _n = clock64(); ch_t[i] += _n - ch_last; ch_last = _n; } } while (0)
+#else
+#define CH_T(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_band) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -169,6 +174,9 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
     if (tid == 0) s_fail = d.scalars[4] != 0.0;
     __syncthreads();
     bool dead = s_fail != 0;  // the band factorisation failed: nothing to do (uniform over the grid)
+#ifdef CORB_CHOL_TRACE
+    long long ch_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ch_last = clock64();
+#endif
     for (int K = 0; K < nt && !dead; K++) {
         // ---- POTRF (K, K) in every CTA that has a TRSM tile (CTA 0 always, it owns the write-back) + TRSM of column K
         const int ntr = nt - K - 1;
@@ -176,7 +184,9 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
         if (work) {
             border_load_tile(v, K, K, sA, tid);
             __syncthreads();
+            CH_T(0);
             border_potrf(sA, sinv, &s_fail, tid);
+            CH_T(1);
             if (me == 0) {
                 border_store_tile(v, K, K, sA, tid, true);
                 for (int c = tid; c < kBT; c += kBcThreads)
@@ -213,6 +223,7 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
             if (me == 0)
                 for (int c = tid; c < kBT; c += kBcThreads)
                     if (K * kBT + c < v.nbord * 6) d.xp[(size_t)n_band * 6 + K * kBT + c] = sy[c];
+            CH_T(2);
             for (int t = me; t < ntr; t += G) {
                 const int I = K + 1 + t;
                 border_load_tile(v, I, K, sB, tid);
@@ -227,8 +238,10 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
                 __syncthreads();
             }
         }
+        CH_T(3);
         __threadfence();
         grid.sync();
+        CH_T(4);
         if (d.scalars[4] != 0.0) { dead = true; break; }  // a pivot failed somewhere: every CTA sees it after the barrier
         // ---- trailing updates A_IJ -= X_IK X_JK^T (K < J <= I), one tile per CTA, fp64 MMA
         const int m = nt - K - 1, ntask = m * (m + 1) / 2;
@@ -259,8 +272,10 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
             }
             __syncthreads();
         }
+        CH_T(5);
         __threadfence();
         grid.sync();
+        CH_T(6);
     }
     if (me != 0 || dead) return;
     // ---- L^T x = y for the border right-hand side (y was formed along the factorisation), tile by tile
@@ -310,6 +325,10 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
         __syncthreads();
     }
     for (int i = tid; i < n6; i += kBcThreads) d.xp[(size_t)n_band * 6 + i] = sv[i];
+    CH_T(7);
+#ifdef CORB_CHOL_TRACE
+    if (tid == 0) printf("k_ba_border_chol nt=%d grid=%d: load diag %lld potrf %lld store+y %lld trsm %lld sync1 %lld update %lld sync2 %lld backward %lld cycles\n", nt, G, ch_t[0], ch_t[1], ch_t[2], ch_t[3], ch_t[4], ch_t[5], ch_t[6], ch_t[7]);
+#endif
 }
 
 // x_i -= sum_j L_ji^T x_j for every band column i over the border rows j whose envelope reaches i (descending j)
