@@ -50,6 +50,26 @@ __device__ __forceinline__ void border_load_tile(const BorderView& v, int I, int
     }
 }
 
+// Rank-6 update inside a shared-memory tile on the tensor cores: C[r][c] -= sum_{p < 6} A[r][p] B[c][p] for r < nr, c < nc (and
+// c <= r when `lower`), as 8 x 8 output tiles of m8n8k4 fp64 MMA with the k = 6 panel padded to 8. A, B, C are row-major with
+// leading dimension kBLd; every output element has exactly one owner lane, so the read-modify-write needs no atomics.
+__device__ __forceinline__ void border_rank6_update(double* C, const double* A, const double* B, int nr, int nc, bool lower, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int tr = (nr + 7) >> 3, tc = (nc + 7) >> 3;
+    for (int t = warp; t < tr * tc; t += kBcThreads / 32) {
+        const int ti = t / tc, tj = t - ti * tc;
+        if (lower && tj > ti) continue;
+        const int r = ti * 8 + g, c = tj * 8 + 2 * q;      // outputs (r, c) and (r, c + 1)
+        const int ra = min(ti * 8 + g, nr - 1), rb = min(tj * 8 + g, nc - 1);  // operand rows, clamped (their products are not stored)
+        const bool ok0 = r < nr && c < nc && (!lower || c <= r), ok1 = r < nr && c + 1 < nc && (!lower || c + 1 <= r);
+        double c0 = ok0 ? C[r * kBLd + c] : 0.0, c1 = ok1 ? C[r * kBLd + c + 1] : 0.0;
+        dmma_m8n8k4(c0, c1, -A[ra * kBLd + q], B[rb * kBLd + q]);
+        dmma_m8n8k4(c0, c1, q < 2 ? -A[ra * kBLd + 4 + q] : 0.0, q < 2 ? B[rb * kBLd + 4 + q] : 0.0);
+        if (ok0) C[r * kBLd + c] = c0;
+        if (ok1) C[r * kBLd + c + 1] = c1;
+    }
+}
+
 // Cholesky of a 48 x 48 tile in shared memory (lower; the strict upper part is left untouched), 6 columns per step.
 // inv[c] = 1 / L_cc. Returns false (uniformly) when a pivot is not positive.
 __device__ __forceinline__ bool border_potrf(double* s, double* inv, int* fail, int tid) {
@@ -92,34 +112,19 @@ __device__ __forceinline__ bool border_potrf(double* s, double* inv, int* fail, 
             for (int c = 0; c < 6; c++) row[c] = x[c];
         }
         __syncthreads();
-        for (int e = tid; e < below * below; e += kBcThreads) {  // trailing update (lower part)
-            const int r = e / below, c = e - r * below;
-            if (c > r) continue;
-            const double* pr = s + (c0 + 6 + r) * kBLd + c0;
-            const double* pc = s + (c0 + 6 + c) * kBLd + c0;
-            double t = 0;
-#pragma unroll
-            for (int p = 0; p < 6; p++) t += pr[p] * pc[p];
-            s[(c0 + 6 + r) * kBLd + c0 + 6 + c] -= t;
-        }
+        // trailing update (lower part): S[c0 + 6 + r][c0 + 6 + c] -= panel[r] . panel[c]
+        border_rank6_update(s + (c0 + 6) * kBLd + c0 + 6, s + (c0 + 6) * kBLd + c0, s + (c0 + 6) * kBLd + c0, below, below, true, tid);
         __syncthreads();
     }
     return *fail == 0;
 }
 
-// X <- X L^-T for a 48 x 48 tile X (in place), L lower with reciprocal diagonal inv; 6 columns per step
+// X <- X L^-T for a 48 x 48 tile X (in place), L lower with reciprocal diagonal inv. Right-looking, 6 columns per step: the
+// block column is solved (one row per thread, a chain of 6), then every remaining column takes its six terms at once
+// (8 x 8 output tiles on the tensor cores).
 __device__ __forceinline__ void border_trsm(double* x, const double* l, const double* inv, int tid) {
     for (int b = 0; b < kBTB; b++) {
         const int c0 = b * 6;
-        for (int e = tid; e < kBT * 6; e += kBcThreads) {  // x[r][c0 + c] -= sum_{p < c0} x[r][p] l[c0 + c][p]
-            const int r = e / 6, c = e - r * 6;
-            const double* xr = x + r * kBLd;
-            const double* lc = l + (c0 + c) * kBLd;
-            double t = 0;
-            for (int p = 0; p < c0; p++) t += xr[p] * lc[p];
-            x[r * kBLd + c0 + c] -= t;
-        }
-        __syncthreads();
         if (tid < kBT) {
             double* row = x + tid * kBLd + c0;
             double v[6];
@@ -132,6 +137,54 @@ __device__ __forceinline__ void border_trsm(double* x, const double* l, const do
             }
 #pragma unroll
             for (int c = 0; c < 6; c++) row[c] = v[c];
+        }
+        __syncthreads();
+        // X[:, c0 + 6 + c] -= X[:, c0 .. c0 + 5] . L[c0 + 6 + c][c0 .. c0 + 5] for the remaining columns
+        border_rank6_update(x + c0 + 6, x + c0, l + (c0 + 6) * kBLd + c0, kBT, kBT - c0 - 6, false, tid);
+        __syncthreads();
+    }
+}
+
+// y <- L^-1 y (forward) or y <- L^-T y (backward) for one tile, right-looking: solve 6 entries, then update the rest of the tile
+__device__ __forceinline__ void border_trsv(double* y, const double* l, const double* inv, int tid, bool transposed) {
+    for (int s6 = 0; s6 < kBTB; s6++) {
+        const int b = transposed ? kBTB - 1 - s6 : s6, c0 = b * 6;
+        if (tid == 0) {
+            double v[6];
+            if (!transposed) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) {
+                    double t = y[c0 + r];
+#pragma unroll
+                    for (int p = 0; p < r; p++) t -= l[(c0 + r) * kBLd + c0 + p] * v[p];
+                    v[r] = t * inv[c0 + r];
+                }
+            } else {
+#pragma unroll
+                for (int r = 5; r >= 0; r--) {
+                    double t = y[c0 + r];
+#pragma unroll
+                    for (int p = r + 1; p < 6; p++) t -= l[(c0 + p) * kBLd + c0 + r] * v[p];
+                    v[r] = t * inv[c0 + r];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 6; r++) y[c0 + r] = v[r];
+        }
+        __syncthreads();
+        if (!transposed) {  // y[i] -= sum_p L[i][c0 + p] y[c0 + p] for the entries below
+            const int i = c0 + 6 + tid;
+            if (i < kBT) {
+                double t = 0;
+#pragma unroll
+                for (int p = 0; p < 6; p++) t += l[i * kBLd + c0 + p] * y[c0 + p];
+                y[i] -= t;
+            }
+        } else if (tid < c0) {  // y[i] -= sum_p L[c0 + p][i] y[c0 + p] for the entries above
+            double t = 0;
+#pragma unroll
+            for (int p = 0; p < 6; p++) t += l[(c0 + p) * kBLd + tid] * y[c0 + p];
+            y[tid] -= t;
         }
         __syncthreads();
     }
@@ -198,28 +251,7 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
             double* sy = sv;  // [48]
             for (int c = tid; c < kBT; c += kBcThreads) sy[c] = K * kBT + c < v.nbord * 6 ? d.xp[(size_t)n_band * 6 + K * kBT + c] : 0.0;
             __syncthreads();
-            for (int b = 0; b < kBTB; b++) {
-                const int c0 = b * 6;
-                if (tid < 6) {
-                    double t = 0;
-                    for (int p = 0; p < c0; p++) t += sA[(c0 + tid) * kBLd + p] * sy[p];
-                    sy[c0 + tid] -= t;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    double y[6];
-#pragma unroll
-                    for (int r = 0; r < 6; r++) {
-                        double t = sy[c0 + r];
-#pragma unroll
-                        for (int p = 0; p < r; p++) t -= sA[(c0 + r) * kBLd + c0 + p] * y[p];
-                        y[r] = t * sinv[c0 + r];
-                    }
-#pragma unroll
-                    for (int r = 0; r < 6; r++) sy[c0 + r] = y[r];
-                }
-                __syncthreads();
-            }
+            border_trsv(sy, sA, sinv, tid, false);
             if (me == 0)
                 for (int c = tid; c < kBT; c += kBcThreads)
                     if (K * kBT + c < v.nbord * 6) d.xp[(size_t)n_band * 6 + K * kBT + c] = sy[c];
@@ -286,28 +318,7 @@ __global__ void __launch_bounds__(kBcThreads) k_ba_border_chol(BaDev d, int n_ba
         border_load_tile(v, K, K, sA, tid);
         for (int c = tid; c < kBT; c += kBcThreads) sinv[c] = K * kBT + c < n6 ? d.invd[(size_t)n_band * 6 + K * kBT + c] : 1.0;
         __syncthreads();
-        for (int b = kBTB - 1; b >= 0; b--) {
-            const int c0 = b * 6;
-            if (tid < 6) {  // x[c0 + tid] -= sum_{p >= c0 + 6} L[p][c0 + tid] x[p]
-                double t = 0;
-                for (int p = c0 + 6; p < kBT; p++) t += sA[p * kBLd + c0 + tid] * sv[K * kBT + p];
-                sv[K * kBT + c0 + tid] -= t;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                double x[6];
-#pragma unroll
-                for (int r = 5; r >= 0; r--) {
-                    double t = sv[K * kBT + c0 + r];
-#pragma unroll
-                    for (int p = r + 1; p < 6; p++) t -= sA[(c0 + p) * kBLd + c0 + r] * x[p];
-                    x[r] = t * sinv[c0 + r];
-                }
-#pragma unroll
-                for (int r = 0; r < 6; r++) sv[K * kBT + c0 + r] = x[r];
-            }
-            __syncthreads();
-        }
+        border_trsv(sv + K * kBT, sA, sinv, tid, true);
         // every entry (block column k < 8 K, component c) of the rows above takes its 48 terms: the blocks (a, k) of a row a
         // are contiguous in the skyline, so neighbouring threads read neighbouring memory
         const int a_lo = K * kBTB, a_hi = min(v.nbord, a_lo + kBTB);
