@@ -307,8 +307,8 @@ static int make_plan(corb_orb* h, int w, int hgt) {
     b.oct_fast = getenv("CORB_OCT_GENERIC") ? 0 : 1;
     {
         CUtensorMap* d_maps;
-        A2(d_maps, kMaxLevels);
-        CORB_CUDA(cudaMemcpy(d_maps, h->tma.m, sizeof(h->tma.m), cudaMemcpyHostToDevice));
+        A2(d_maps, 2 * kMaxLevels);  // m[] then mb[]
+        CORB_CUDA(cudaMemcpy(d_maps, &h->tma, sizeof(h->tma), cudaMemcpyHostToDevice));
         b.tma_dev = d_maps;
         std::vector<int> ptab;
         build_pyr_plan(g, xofs.data(), yofs.data(), 0, &b.pyr_plan, &ptab);

@@ -431,6 +431,8 @@ constexpr int kRoiPitch = 96;  // bytes per ROI row in shared memory = TMA box w
                                // because the innermost TMA coordinate must be 16-byte aligned (measured: any other x traps
                                // with 'illegal instruction' on sm_100a), so the box starts at iniX & ~15
 constexpr int kRoiPitchRaw = kRoiPitch;
+constexpr int kBlurTW = 64, kBlurTH = 16;               // blur output tile
+constexpr int kBlurBoxW = 96, kBlurBoxH = kBlurTH + 6;   // its input box: columns x0 - 16 .. x0 + 79 (16-byte aligned start), rows y0 - 3 .. y0 + 18
 constexpr int kRoiTmaBytes = kRoiPitch * kCellRoiMax;  // one 96 x 66 box per cell
 
 // ---- TMA (cp.async.bulk.tensor) + mbarrier primitives, sm_90+/sm_100a PTX
@@ -715,6 +717,191 @@ __global__ void __launch_bounds__(256, 6) k_fast_cells(OrbGeom g, const __grid_c
     TR_PRINT("fast", cell == 100 || cell == 900 || cell == 1200);
 }
 
+// ---- The same per-cell FAST, kFastG cells per CTA (64 threads = 2 warps per cell). One cell per CTA leaves every fixed cost -
+// the launch slot, the TMA round trip, eight block barriers, the scan - to be paid for ~1000 pixels (4 per thread): a cell CTA
+// lives ~10 us whatever its size, and the 2 462 cell CTAs of a stereo pair were ~28 of the ~46 us of GPU time a frame occupies.
+// Four cells share those costs here (16 pixels per thread, a quarter of the CTAs); each cell keeps its own ROI, score tile,
+// survivor list, masks and TMA barrier, and the iniTh -> minTh fallback is still decided per cell. Same results bit for bit.
+constexpr int kFastG = 4;
+constexpr int kFastTpg = 256 / kFastG;  // threads per cell
+struct FastCellSmem {
+    uint8_t roi_raw[kCellRoiMax * kRoiPitchRaw + 16];
+    uint8_t sc[kScDim * kScPitch];
+    uint32_t row_ini[128];
+    uint16_t surv[60 * 60];
+    int row_off[66];
+    int n_surv, any, active, pad;
+    uint64_t tma_bar;
+    uint8_t tail[112];  // keeps every cell's ROI 128-byte aligned (the TMA destination)
+};
+static_assert(sizeof(FastCellSmem) % 128 == 0, "per-cell shared block must keep the ROI 128-byte aligned");
+
+__global__ void __launch_bounds__(256, 3) k_fast_cells_g(OrbGeom g, const __grid_constant__ CUtensorMap tmap, int use_tma,
+                                                      const uint8_t* __restrict__ pyr, int* __restrict__ cell_count,
+                                                      uint32_t* __restrict__ cand_xy, uint32_t* __restrict__ cand_ro,
+                                                      int* __restrict__ level_cand, int* __restrict__ status, int cell_begin, int cell_end,
+                                                      const CUtensorMap* __restrict__ tmap_dev, FastImage2 im1,
+                                                      const __grid_constant__ CUtensorMap tmap1) {
+    extern __shared__ __align__(128) uint8_t fsm_raw[];
+    const int tid = threadIdx.x, grp = tid / kFastTpg, tig = tid - grp * kFastTpg;
+    const int lane = tid & 31, wg = tig >> 5;
+    constexpr int kWpg = kFastTpg / 32;
+    FastCellSmem& S = reinterpret_cast<FastCellSmem*>(fsm_raw)[grp];
+    const int cell = cell_begin + blockIdx.x * kFastG + grp;
+    const bool in_range = cell < cell_end;
+    int l = 0;
+    {
+        const int cl = in_range ? cell : cell_end - 1;
+        while (l + 1 < g.n_levels && cl >= g.lv[l + 1].cell_base) l++;
+    }
+    TL_SCOPE(16 + l);
+    pdl_release();  // the quadtree launch behind this one may be scheduled; it waits for this grid in pdl_wait()
+    const CUtensorMap* tm = &tmap;
+    if (blockIdx.z) {  // second image of a stereo pair
+        pyr = im1.pyr; cell_count = im1.cell_count; cand_xy = im1.cand_xy; cand_ro = im1.cand_ro; level_cand = im1.level_cand;
+        status = im1.status;
+        tmap_dev = im1.tmap_dev;
+        tm = &tmap1;
+    }
+    const LevelGeom L = g.lv[l];
+    const int c = (in_range ? cell : cell_end - 1) - L.cell_base;
+    const int ci = c / L.n_cols, cj = c - ci * L.n_cols;
+    const int iniX = kBorder + cj * L.w_cell, iniY = kBorder + ci * L.h_cell;
+    const int maxX = min(iniX + L.w_cell + 6, L.max_bx), maxY = min(iniY + L.h_cell + 6, L.max_by);
+    const int rw = maxX - iniX, rh = maxY - iniY;
+    const int vw = rw - 6, vh = rh - 6;
+    const bool live = in_range && vw > 0 && vh > 0;  // covers the reference's skip rules (:795,:803) and ROIs cv::FAST cannot process
+    if (in_range && !live && tig == 0) cell_count[cell] = 0;
+    const uint8_t* roi;
+    if (use_tma) {
+        if (tig == 0) mbar_init(&S.tma_bar, 1);
+        __syncthreads();
+        if (tig == 0 && live) {
+            mbar_expect_tx(&S.tma_bar, kRoiTmaBytes);
+            tma_load_2d(S.roi_raw, tmap_dev ? tmap_dev + l : tm, iniX & ~15, iniY, &S.tma_bar);
+        }
+        roi = S.roi_raw + (iniX & 15);
+    } else {
+        const int ax = iniX & ~3, shift = iniX - ax;
+        const int nw = (rw + shift + 3) >> 2;
+        const uint8_t* srow = pyr + L.img_off + (size_t)iniY * L.pitch + ax;
+        const int xw = tig & 31;
+        if (live && xw < nw)
+            for (int y = tig >> 5; y < rh; y += kWpg)
+                reinterpret_cast<uint32_t*>(S.roi_raw + y * kRoiPitchRaw)[xw] = *reinterpret_cast<const uint32_t*>(srow + (size_t)y * L.pitch + 4 * xw);
+        roi = S.roi_raw + shift;
+    }
+    if (use_tma && live) mbar_wait(&S.tma_bar, 0);
+    if (tig == 0) S.active = live;
+    int th = g.ini_th;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const bool run = live && (attempt == 0 || S.active);
+        if (run) {
+            for (int i = tig; i < kScDim * kScPitch / 4; i += kFastTpg) reinterpret_cast<uint32_t*>(S.sc)[i] = 0;
+            if (tig == 0) { S.n_surv = 0; S.any = 0; }
+            for (int i = tig; i < 128; i += kFastTpg) S.row_ini[i] = 0;
+        }
+        __syncthreads();
+        if (run) {
+            for (int y = wg; y < vh; y += kWpg) {
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    if (half && vw <= 32) break;
+                    const int x = lane + 32 * half;
+                    bool pass = false;
+                    if (x < vw) {
+                        const uint8_t* cp = roi + (y + 3) * kRoiPitch + (x + 3);
+                        const int v = cp[0], r0 = cp[3 * kRoiPitch], r4 = cp[3], r8 = cp[-3 * kRoiPitch], r12 = cp[-3];
+                        const int hi = v + th, lo = v - th;
+                        pass = (r0 > hi) + (r4 > hi) + (r8 > hi) + (r12 > hi) >= 2 || (r0 < lo) + (r4 < lo) + (r8 < lo) + (r12 < lo) >= 2;
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                    if (m) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&S.n_surv, __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (pass) S.surv[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(y << 6 | x);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (run) {
+            const int ns = S.n_surv;
+            for (int i = tig; i < ns; i += kFastTpg) {
+                const int y = S.surv[i] >> 6, x = S.surv[i] & 63;
+                S.sc[(y + 1) * kScPitch + (x + 1)] = (uint8_t)fast_score_dev(roi + (y + 3) * kRoiPitch + (x + 3), th);
+            }
+        }
+        __syncthreads();
+        if (run) {
+            const int ns = S.n_surv;
+            bool any_local = false;
+            for (int i = tig; i < ns; i += kFastTpg) {
+                const int y = S.surv[i] >> 6, x = S.surv[i] & 63;
+                const uint8_t* q = S.sc + (y + 1) * kScPitch + (x + 1);
+                const int sv = q[0];
+                if (sv != 0 && sv > q[-kScPitch - 1] && sv > q[-kScPitch] && sv > q[-kScPitch + 1] && sv > q[-1] && sv > q[1] &&
+                    sv > q[kScPitch - 1] && sv > q[kScPitch] && sv > q[kScPitch + 1]) {
+                    atomicOr(&S.row_ini[y * 2 + (x >> 5)], 1u << (x & 31));
+                    any_local = true;
+                }
+            }
+            if (any_local) S.any = 1;
+        }
+        __syncthreads();
+        // a cell without any corner is redone at minTh (:809-815); the other cells of the CTA sit the second round out
+        const bool retry = run && !S.any && g.min_th < g.ini_th && attempt == 0;
+        const int again = __syncthreads_or(retry);
+        if (tig == 0) S.active = retry;
+        if (!again) break;
+        th = g.min_th;
+        __syncthreads();
+    }
+    if (live && wg == 0) {  // exclusive scan of the per-row counts (vh <= 60 rows: two per lane)
+        const uint32_t* rowm = S.row_ini;
+        const int y0 = 2 * lane, y1 = 2 * lane + 1;
+        const int c0 = y0 < vh ? __popc(rowm[y0 * 2]) + __popc(rowm[y0 * 2 + 1]) : 0;
+        const int c1 = y1 < vh ? __popc(rowm[y1 * 2]) + __popc(rowm[y1 * 2 + 1]) : 0;
+        int inc = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (y0 < vh) S.row_off[y0] = inc - c0 - c1;
+        if (y1 < vh) S.row_off[y1] = inc - c1;
+        if (lane == 31) {
+            S.row_off[64] = inc;
+            S.row_off[65] = inc > 0 && inc <= L.slot ? atomicAdd(&level_cand[l], inc) : 0;
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    const int total = S.row_off[64];
+    if (total > L.slot) {  // impossible; never truncate silently
+        if (tig == 0) { atomicExch(status, 101); cell_count[cell] = 0; }
+        return;
+    }
+    const int base = L.cand_base + S.row_off[65];
+    const uint32_t order0 = 0xffffffu - (uint32_t)(c * L.slot);
+    for (int y = wg; y < vh; y += kWpg) {
+        const uint32_t m0 = S.row_ini[y * 2], m1 = S.row_ini[y * 2 + 1];
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t m = half ? m1 : m0;
+            if (m >> lane & 1u) {
+                const int x = lane + 32 * half;
+                const int pos = S.row_off[y] + (half ? __popc(m0) : 0) + __popc(m & lt);
+                cand_xy[base + pos] = (uint32_t)(x + 3 + cj * L.w_cell) | (uint32_t)(y + 3 + ci * L.h_cell) << 16;
+                cand_ro[base + pos] = (uint32_t)S.sc[(y + 1) * kScPitch + (x + 1)] << 24 | (order0 - (uint32_t)pos);
+            }
+        }
+    }
+    if (tig == 0) cell_count[cell] = total;
+}
+
 // cuTensorMapEncodeTiled is a driver-API symbol; it is resolved at run time through the runtime so that the library
 // does not link libcuda (and still loads on a machine without a driver, where every compute call fails loudly).
 bool encode_tma_maps(const OrbGeom& g, uint8_t* pyr, TmaMaps* out) {
@@ -738,6 +925,11 @@ bool encode_tma_maps(const OrbGeom& g, uint8_t* pyr, TmaMaps* out) {
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return false;
+        const cuuint32_t bbox[2] = {(cuuint32_t)kBlurBoxW, (cuuint32_t)kBlurBoxH};
+        const CUresult rb = ((EncodeFn)fn)(&out->mb[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, pyr + L.img_off, dims, strides, bbox, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rb != CUDA_SUCCESS) return false;
     }
     return true;
 }
@@ -753,14 +945,28 @@ static FastImage2 fast_image2(const OrbBuffers* b1, bool dev_maps) {
     return im;
 }
 
+static bool fast_grouped() {  // CORB_FAST_GROUP=0: one cell per CTA (the A/B switch; same results)
+    static const bool on = [] {
+        const char* e = getenv("CORB_FAST_GROUP");
+        if (e && atoi(e) == 0) return false;
+        return cudaFuncSetAttribute(k_fast_cells_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFastG * sizeof(FastCellSmem))) == cudaSuccess;
+    }();
+    return on;
+}
+
 void launch_fast_cells(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s, const OrbBuffers* b1) {
     // one launch per level: the level's tensor map travels as a __grid_constant__ parameter (the form TMA expects)
     const int l0 = level < 0 ? 0 : level, l1 = level < 0 ? g.n_levels : level + 1;
     for (int l = l0; l < l1; l++) {
         const int n = g.lv[l].n_cols * g.lv[l].n_rows;
-        k_fast_cells<<<dim3(n, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b.tma_maps->m[l], b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_ro,
-                                                            b.level_cand, b.status, g.lv[l].cell_base, nullptr, fast_image2(b1, false),
-                                                            (b1 ? b1 : &b)->tma_maps->m[l]);
+        if (fast_grouped())
+            k_fast_cells_g<<<dim3((n + kFastG - 1) / kFastG, 1, b1 ? 2 : 1), 256, kFastG * sizeof(FastCellSmem), s>>>(
+                g, b.tma_maps->m[l], b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_ro, b.level_cand, b.status, g.lv[l].cell_base,
+                g.lv[l].cell_base + n, nullptr, fast_image2(b1, false), (b1 ? b1 : &b)->tma_maps->m[l]);
+        else
+            k_fast_cells<<<dim3(n, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b.tma_maps->m[l], b.use_tma, b.pyr, b.cell_count, b.cand_xy, b.cand_ro,
+                                                                b.level_cand, b.status, g.lv[l].cell_base, nullptr, fast_image2(b1, false),
+                                                                (b1 ? b1 : &b)->tma_maps->m[l]);
     }
 }
 
@@ -774,7 +980,6 @@ void launch_fast_all(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, cons
 // ------------------------------------------------------------------------------------------------ K5 Gaussian 7x7
 // cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on u8 (ORBextractor.cc:1086): fixed-point taps
 // {18,34,48,56,48,34,18}/256 on both axes, exact accumulation, one rounding (s + 2^15) >> 16.
-constexpr int kBlurTW = 64, kBlurTH = 16;
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (p < 0) p = -p;
@@ -783,10 +988,14 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
-                                              const uint8_t* __restrict__ pyr1, uint8_t* __restrict__ blur1) {
-    if (blockIdx.z) { pyr = pyr1; blur = blur1; }
-    __shared__ uint8_t in[kBlurTH + 6][kBlurTW + 8];
+                                              const uint8_t* __restrict__ pyr1, uint8_t* __restrict__ blur1,
+                                              const CUtensorMap* __restrict__ maps, const CUtensorMap* __restrict__ maps1) {
+    if (blockIdx.z) { pyr = pyr1; blur = blur1; maps = maps1; }
+    // input box of the tile: [kBlurBoxH][kBlurBoxW], pixel (x0 - 16 + xx, y0 - 3 + yy); one TMA box load (maps != NULL) or
+    // 32-bit loads. What lies outside the image arrives as zeros and is rewritten with the REFLECT_101 pixels below.
+    __shared__ __align__(128) uint8_t in[kBlurBoxH][kBlurBoxW];
     __shared__ uint16_t hb[kBlurTH + 6][kBlurTW];
+    __shared__ __align__(8) uint64_t bar;
     TL_SCOPE(48);
     const int tid = threadIdx.x;
     int l = 0;
@@ -795,18 +1004,54 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
     const int t = blockIdx.x - L.blur_tile_base;
     const int ty = t / L.blur_tiles_x, tx = t - ty * L.blur_tiles_x;
     const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
-    const uint8_t* src = pyr + L.img_off;
-    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
-        const int yy = i / (kBlurTW + 6), xx = i - yy * (kBlurTW + 6);
-        const int gy = reflect101(min(max(y0 + yy - 3, -3), L.h + 2), L.h);
-        const int gx = reflect101(min(max(x0 + xx - 3, -3), L.w + 2), L.w);
-        in[yy][xx] = src[(size_t)gy * L.pitch + gx];
+    if (maps) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, kBlurBoxW * kBlurBoxH);
+            tma_load_2d(&in[0][0], maps + l, x0 - 16, y0 - 3, &bar);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        const uint8_t* src = pyr + L.img_off;
+        for (int i = tid; i < kBlurBoxH * (kBlurBoxW / 4); i += 256) {
+            const int yy = i / (kBlurBoxW / 4), xw = i - yy * (kBlurBoxW / 4);
+            const int gy = y0 - 3 + yy, gx = x0 - 16 + 4 * xw;
+            uint32_t v = 0;
+            if (gy >= 0 && gy < L.h && gx >= 0 && gx < L.pitch) v = *reinterpret_cast<const uint32_t*>(src + (size_t)gy * L.pitch + gx);
+            reinterpret_cast<uint32_t*>(&in[yy][0])[xw] = v;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-        const int yy = i / kBlurTW, xx = i - yy * kBlurTW;
-        const uint8_t* p = &in[yy][xx];
-        hb[yy][xx] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    // tiles on the image border: the frame of 3 pixels outside the image is the reflection of pixels inside this box
+    const bool edge = x0 < 3 || y0 < 3 || x0 + kBlurTW + 3 > L.w || y0 + kBlurTH + 3 > L.h;
+    if (edge) {
+        for (int i = tid; i < kBlurBoxH * (kBlurTW + 6); i += 256) {
+            const int yy = i / (kBlurTW + 6), xx = 13 + (i - yy * (kBlurTW + 6));
+            const int gy = y0 - 3 + yy, gx = x0 - 16 + xx;
+            if ((gy < 0 || gy >= L.h || gx < 0 || gx >= L.w) && gy >= -3 && gy <= L.h + 2 && gx >= -3 && gx <= L.w + 2) {
+                const int sy = reflect101(gy, L.h) - (y0 - 3), sx = reflect101(gx, L.w) - (x0 - 16);
+                in[yy][xx] = in[sy][sx];  // sources are inside the image, destinations outside: no overlap
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW / 4); i += 256) {  // horizontal pass, 4 outputs per thread from 3 words
+        const int yy = i / (kBlurTW / 4), xq = i - yy * (kBlurTW / 4);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&in[yy][12 + 4 * xq]);  // pixels x0 - 4 + 4 xq .. + 11
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        uint8_t p[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { p[k] = (w0 >> (8 * k)) & 0xff; p[4 + k] = (w1 >> (8 * k)) & 0xff; p[8 + k] = (w2 >> (8 * k)) & 0xff; }
+        uint32_t o01 = 0, o23 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // output pixel x0 + 4 xq + k takes p[k + 1 .. k + 7]
+            const uint32_t v = 18u * (p[k + 1] + p[k + 7]) + 34u * (p[k + 2] + p[k + 6]) + 48u * (p[k + 3] + p[k + 5]) + 56u * p[k + 4];
+            if (k < 2) o01 |= v << (16 * k); else o23 |= v << (16 * (k - 2));
+        }
+        uint32_t* o = reinterpret_cast<uint32_t*>(&hb[yy][4 * xq]);
+        o[0] = o01;
+        o[1] = o23;
     }
     __syncthreads();
     const int lx = (tid & 15) * 4, ly = tid >> 4;
@@ -825,7 +1070,10 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
 }
 
 void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const OrbBuffers* b1) {
-    k_blur<<<dim3(g.blur_tiles, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b.pyr, b.blur, b1 ? b1->pyr : nullptr, b1 ? b1->blur : nullptr);
+    const CUtensorMap* m0 = b.use_tma && b.tma_dev ? b.tma_dev + kMaxLevels : nullptr;
+    const CUtensorMap* m1 = b1 && b1->use_tma && b1->tma_dev ? b1->tma_dev + kMaxLevels : nullptr;
+    if (b1 && !m1) m0 = nullptr;  // both images take the same path
+    k_blur<<<dim3(g.blur_tiles, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b.pyr, b.blur, b1 ? b1->pyr : nullptr, b1 ? b1->blur : nullptr, m0, b1 ? m1 : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 quadtree

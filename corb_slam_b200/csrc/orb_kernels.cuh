@@ -13,7 +13,8 @@ namespace corb {
 
 // one tensor map per pyramid level (u8, {w, h}, row pitch), box = 80 x 66 bytes: the FAST cell ROI
 struct TmaMaps {
-    CUtensorMap m[kMaxLevels];
+    CUtensorMap m[kMaxLevels];   // FAST: one 96 x 66 box per grid cell
+    CUtensorMap mb[kMaxLevels];  // blur: one 96 x 22 box per 64 x 16 output tile
 };
 
 // second image of a pair for k_fast_cells
