@@ -7,7 +7,7 @@ from ._lib import CorbError, KP_DTYPE, LIB_PATH  # noqa: F401
 from .orbextractor import (ORBextractor, compute_stereo_matches, extract_stereo, extract_stereo_device,  # noqa: F401
                            extract_stereo_submit, extract_stereo_wait, frame_stereo, frame_stereo_submit, frame_stereo_wait)
 from .orbmatcher import ORBmatcher, BowFeatures  # noqa: F401
-from .orbvocabulary import ORBVocabulary  # noqa: F401
+from .orbvocabulary import BowRecord, ORBVocabulary  # noqa: F401
 from .frame import FrameView  # noqa: F401
 from .pnpsolver import PnPsolver  # noqa: F401
 from .optimizer import Optimizer, torch_allreduce  # noqa: F401

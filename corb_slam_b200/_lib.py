@@ -107,6 +107,16 @@ def lib():
         L.corb_orb_extract_pair_device.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int]
         L.corb_stereo_match.argtypes = [vp, vp, C.c_float, C.c_float, C.c_int, vp, vp]
         L.corb_frame_stereo.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, i32p, vp, vp, i32p, vp, vp]
+        L.corb_bow_store_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+        L.corb_bow_store_destroy.argtypes = [vp]
+        L.corb_bow_store_destroy.restype = None
+        L.corb_bow_store_fill.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        L.corb_frame_bow.argtypes = [vp, vp, C.c_int, vp]
+        L.corb_bow_store_side.argtypes = [vp, vp, C.POINTER(BowSide), i32p]
+        L.corb_bow_store_download.argtypes = [vp, vp, vp, i32p, vp, vp, vp, i32p]
+        L.corb_bow_score_stores.argtypes = [vp, vp, C.c_int, C.POINTER(vp), vp]
+        L.corb_bow_match_stores.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_float, C.c_int,
+                                            C.POINTER(vp), i32p]
         L.corb_orb_extract_pair_submit.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.corb_orb_extract_pair_wait.argtypes = [vp, vp, vp, vp, i32p, vp, vp, i32p, C.POINTER(vp), C.POINTER(vp)]
         L.corb_frame_stereo_submit.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]

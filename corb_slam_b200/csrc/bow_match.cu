@@ -785,4 +785,357 @@ int corb_bow_score_batch(corb_voc* v, const uint32_t* q_words, const double* q_v
     return CORB_OK;
 }
 
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ device-resident BoW record
+// A frame's / keyframe's matching record kept in HBM: descriptors, keypoint angles, BowVector and FeatureVector, built from
+// the extractor's device-resident results without a trip through the host (Frame::ComputeBoW, Frame.cc:399-406, is
+// transform() on the descriptors the extractor just produced). The std::map bookkeeping of BowVector::addWeight /
+// FeatureVector::addFeature / normalize (BowVector.cpp:34-84, FeatureVector.cpp:31-45) becomes, in one CTA: a bitonic sort
+// of (word, feature) keys, per-word sums in feature order, the L1 norm summed in ascending word order by one thread (the
+// order the reference's loop has: the fp64 bits are the same), and a second sort of (node, feature) keys for the CSR.
+namespace corb {
+
+constexpr int kBowCap = 4096;  // features per record (shared-memory sort)
+
+struct BowStoreDev {
+    uint8_t* desc;      // [cap * 32]
+    float* angles;      // [cap]
+    uint32_t* word;     // [cap] per feature
+    double* weight;     // [cap]
+    uint32_t* node;     // [cap]
+    uint32_t* bow_words; double* bow_vals;              // [cap]
+    uint32_t* fv_nodes; int32_t* fv_off; uint32_t* fv_idx;  // [cap], [cap + 1], [cap]
+    int32_t* counts;    // [4]: n_bow, n_fv, n_fv_idx, n
+};
+
+__global__ void __launch_bounds__(256) k_bow_gather(const corb_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+                                                    BowStoreDev st) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) st.angles[i] = kps ? kps[i].angle : 0.f;
+    const uint4* s4 = reinterpret_cast<const uint4*>(desc);
+    uint4* d4 = reinterpret_cast<uint4*>(st.desc);
+    if (i < 2 * n && desc != st.desc) d4[i] = s4[i];
+    if (i + 256 * gridDim.x < 2 * n && desc != st.desc) d4[i + 256 * gridDim.x] = s4[i + 256 * gridDim.x];
+}
+
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* a, int N, int tid, int nt) {
+    for (int k = 2; k <= N; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < N / 2; t += nt) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // the lower index of the pair
+                const int p = i | j;
+                const bool up = (i & k) == 0;
+                const unsigned long long x = a[i], y = a[p];
+                if ((x > y) == up) { a[i] = y; a[p] = x; }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(1024) k_bow_build(BowStoreDev st, int n) {
+    extern __shared__ unsigned long long keys[];  // [N] | double vals[N] | int flags[N + 1]
+    int N = 32;
+    while (N < n) N <<= 1;
+    double* vals = reinterpret_cast<double*>(keys + N);
+    int* flag = reinterpret_cast<int*>(vals + N);
+    __shared__ int s_total[2];
+    __shared__ double s_norm;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned long long kNone = ~0ull;
+    for (int pass = 0; pass < 2; pass++) {  // 0: BowVector from (word, feature); 1: FeatureVector from (node, feature)
+        for (int i = tid; i < N; i += nt)
+            keys[i] = (i < n && st.weight[i] > 0.0) ? ((unsigned long long)(pass ? st.node[i] : st.word[i]) << 32 | (unsigned)i) : kNone;
+        __syncthreads();
+        bitonic_sort_u64(keys, N, tid, nt);
+        // heads of runs with the same upper word; valid keys come first
+        for (int i = tid; i < N; i += nt) flag[i] = keys[i] != kNone && (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32));
+        __syncthreads();
+        // exclusive scan of the flags (N <= 4096: each thread scans a run of N / nt, then a block scan of the run totals)
+        {
+            const int per = (N + nt - 1) / nt;
+            const int b0 = tid * per;
+            int sum = 0;
+            for (int i = b0; i < min(b0 + per, N); i++) sum += flag[i];
+            __shared__ int wsum[32];
+            int inc = sum;
+            const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) wsum[wid] = inc;
+            __syncthreads();
+            if (wid == 0) {
+                int w = lane < (nt >> 5) ? wsum[lane] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, w, o);
+                    if (lane >= o) w += u;
+                }
+                wsum[lane] = w;
+            }
+            __syncthreads();
+            int run = (wid ? wsum[wid - 1] : 0) + inc - sum;
+            for (int i = b0; i < min(b0 + per, N); i++) {
+                const int f = flag[i];
+                flag[i] = f ? run : -1;  // index of the run this head starts, -1 for non-heads
+                run += f;
+            }
+            if (tid == nt - 1) s_total[pass] = run;
+            __syncthreads();
+        }
+        if (pass == 0) {
+            for (int i = tid; i < N; i += nt) {
+                const int u = flag[i];
+                if (u < 0) continue;
+                const unsigned w = (unsigned)(keys[i] >> 32);
+                double sum = 0.0;  // addWeight in feature order (keys are sorted by feature index inside a word)
+                for (int j = i; j < N && keys[j] != kNone && (unsigned)(keys[j] >> 32) == w; j++) sum += st.weight[(unsigned)keys[j]];
+                st.bow_words[u] = w;
+                vals[u] = sum;
+            }
+            __syncthreads();
+            const int nb = s_total[0];
+            if (tid == 0) {  // BowVector::normalize(L1): norm += fabs(value) in ascending word order
+                double norm = 0.0;
+                for (int u = 0; u < nb; u++) norm += fabs(vals[u]);
+                s_norm = norm;
+            }
+            __syncthreads();
+            const double norm = s_norm;
+            for (int u = tid; u < nb; u += nt) st.bow_vals[u] = norm > 0.0 ? vals[u] / norm : vals[u];
+            __syncthreads();
+        } else {
+            for (int i = tid; i < N; i += nt) {
+                if (keys[i] == kNone) continue;
+                st.fv_idx[i] = (unsigned)keys[i];
+                const int u = flag[i];
+                if (u >= 0) { st.fv_nodes[u] = (unsigned)(keys[i] >> 32); st.fv_off[u] = i; }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int cnt = 0;  // valid keys come first after the sort: binary search of the first kNone
+                int lo = 0, hi = N;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] != kNone) lo = mid + 1; else hi = mid; }
+                cnt = lo;
+                st.fv_off[s_total[1]] = cnt;
+                st.counts[0] = s_total[0]; st.counts[1] = s_total[1]; st.counts[2] = cnt; st.counts[3] = n;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bow_score_ptr(const uint32_t* __restrict__ qw, const double* __restrict__ qv, int nq,
+                                                       const uint32_t* const* __restrict__ cw, const double* const* __restrict__ cv,
+                                                       const int* __restrict__ cn, int ncand, double* __restrict__ scores) {
+    const int cand = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (cand >= ncand) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t* w_ = cw[cand];
+    const double* v_ = cv[cand];
+    const int end = cn[cand];
+    double score = 0.0;
+    for (int base = 0; base < end; base += 32) {
+        const int i = base + lane;
+        double term = 0.0;
+        bool has = false;
+        if (i < end) {
+            const uint32_t w = w_[i];
+            int lo = 0, hi = nq;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (qw[mid] < w) lo = mid + 1; else hi = mid;
+            }
+            if (lo < nq && qw[lo] == w) {
+                const double vi = qv[lo], wi = v_[i];
+                term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
+                has = true;
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, has);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            score = __dadd_rn(score, __shfl_sync(0xffffffffu, term, src));
+        }
+    }
+    if (lane == 0) scores[cand] = -score / 2.0;
+}
+
+}  // namespace corb
+
+struct corb_bow_store {
+    int device, cap;
+    uint8_t* base = nullptr;
+    BowStoreDev dev;
+    int32_t* h_counts = nullptr;  // pinned [4]
+    int n = 0, n_bow = 0, n_fv = 0, n_fv_idx = 0;
+    cudaStream_t last_stream = nullptr;
+};
+
+extern "C" {
+
+int corb_bow_store_create(int device, int capacity, corb_bow_store** out) {
+    CORB_CHECK(out && capacity >= 1 && capacity <= kBowCap, CORB_ERR_INVALID, "capacity must be 1..%d features", kBowCap);
+    CORB_CUDA(cudaSetDevice(device));
+    corb_bow_store* s = new corb_bow_store;
+    s->device = device;
+    s->cap = capacity;
+    Packer p;
+    const size_t c = capacity;
+    const size_t oD = p.take(c * 32), oA = p.take(c * 4), oW = p.take(c * 4), oWt = p.take(c * 8), oN = p.take(c * 4), oBW = p.take(c * 4),
+                 oBV = p.take(c * 8), oFN = p.take(c * 4), oFO = p.take((c + 1) * 4), oFI = p.take(c * 4), oC = p.take(16);
+    if (cudaMalloc((void**)&s->base, p.off) != cudaSuccess || cudaMallocHost((void**)&s->h_counts, 16) != cudaSuccess) {
+        if (s->base) cudaFree(s->base);
+        delete s;
+        CORB_CHECK(false, CORB_ERR_CUDA, "allocating a BoW record of %d features failed", capacity);
+    }
+    uint8_t* b = s->base;
+    s->dev.desc = b + oD; s->dev.angles = (float*)(b + oA); s->dev.word = (uint32_t*)(b + oW); s->dev.weight = (double*)(b + oWt);
+    s->dev.node = (uint32_t*)(b + oN); s->dev.bow_words = (uint32_t*)(b + oBW); s->dev.bow_vals = (double*)(b + oBV);
+    s->dev.fv_nodes = (uint32_t*)(b + oFN); s->dev.fv_off = (int32_t*)(b + oFO); s->dev.fv_idx = (uint32_t*)(b + oFI);
+    s->dev.counts = (int32_t*)(b + oC);
+    *out = s;
+    return CORB_OK;
+}
+
+void corb_bow_store_destroy(corb_bow_store* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->base) cudaFree(s->base);
+    if (s->h_counts) cudaFreeHost(s->h_counts);
+    delete s;
+}
+
+int corb_bow_store_fill(corb_bow_store* s, corb_voc* v, const corb_keypoint* d_kps, const uint8_t* d_desc, int n, int levelsup,
+                        void* stream) {
+    CORB_CHECK(s && v && n >= 0 && n <= s->cap && (n == 0 || d_desc), CORB_ERR_INVALID, "bad argument (n = %d, capacity %d)", n,
+               s ? s->cap : 0);
+    CORB_CHECK(v->device == s->device, CORB_ERR_INVALID, "vocabulary and record live on different devices");
+    CORB_CHECK(((uintptr_t)d_desc & 15) == 0, CORB_ERR_INVALID, "device descriptors must be 16-byte aligned");
+    CORB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : v->stream;
+    s->last_stream = st;
+    s->n = n;
+    if (n == 0) {
+        s->n_bow = s->n_fv = s->n_fv_idx = 0;
+        CORB_CUDA(cudaMemsetAsync(s->dev.counts, 0, 16, st));
+        CORB_CUDA(cudaMemsetAsync(s->dev.fv_off, 0, 4, st));
+        return CORB_OK;
+    }
+    k_bow_gather<<<(n + 255) / 256, 256, 0, st>>>(d_kps, d_desc, n, s->dev);
+    k_voc_transform<<<(n * 16 + 255) / 256, 256, 0, st>>>(v->dev, (const uint4*)s->dev.desc, n, v->L - levelsup, s->dev.word, s->dev.weight,
+                                                           s->dev.node);
+    int N = 32;
+    while (N < n) N <<= 1;
+    const size_t smem = (size_t)N * 16 + (size_t)(N + 1) * 4;
+    static std::atomic<unsigned long long> opt{0};
+    if (smem > 48 * 1024 && !(opt.load() & (1ull << (s->device & 63)))) {
+        CORB_CUDA(cudaFuncSetAttribute(k_bow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kBowCap * 16 + (kBowCap + 1) * 4));
+        opt.fetch_or(1ull << (s->device & 63));
+    }
+    k_bow_build<<<1, 1024, smem, st>>>(s->dev, n);
+    CORB_CUDA(cudaGetLastError());
+    CORB_CUDA(cudaMemcpyAsync(s->h_counts, s->dev.counts, 16, cudaMemcpyDeviceToHost, st));
+    CORB_CUDA(cudaStreamSynchronize(st));
+    s->n_bow = s->h_counts[0]; s->n_fv = s->h_counts[1]; s->n_fv_idx = s->h_counts[2];
+    return CORB_OK;
+}
+
+int corb_bow_store_side(const corb_bow_store* s, const uint8_t* d_valid, corb_bow_side* side, int* n_bow) {
+    CORB_CHECK(s && side, CORB_ERR_INVALID, "bad argument");
+    side->desc = s->dev.desc; side->n = s->n;
+    side->fv_nodes = s->dev.fv_nodes; side->fv_off = s->dev.fv_off; side->fv_idx = s->dev.fv_idx; side->fv_n = s->n_fv;
+    side->valid = d_valid; side->angles = s->dev.angles;
+    if (n_bow) *n_bow = s->n_bow;
+    return CORB_OK;
+}
+
+int corb_bow_store_download(const corb_bow_store* s, uint32_t* bow_words, double* bow_vals, int* n_bow, uint32_t* fv_nodes,
+                            int32_t* fv_off, uint32_t* fv_idx, int* n_fv) {
+    CORB_CHECK(s && n_bow && n_fv, CORB_ERR_INVALID, "bad argument");
+    CORB_CUDA(cudaSetDevice(s->device));
+    *n_bow = s->n_bow; *n_fv = s->n_fv;
+    if (bow_words && s->n_bow) CORB_CUDA(cudaMemcpy(bow_words, s->dev.bow_words, (size_t)s->n_bow * 4, cudaMemcpyDeviceToHost));
+    if (bow_vals && s->n_bow) CORB_CUDA(cudaMemcpy(bow_vals, s->dev.bow_vals, (size_t)s->n_bow * 8, cudaMemcpyDeviceToHost));
+    if (fv_nodes && s->n_fv) CORB_CUDA(cudaMemcpy(fv_nodes, s->dev.fv_nodes, (size_t)s->n_fv * 4, cudaMemcpyDeviceToHost));
+    if (fv_off) CORB_CUDA(cudaMemcpy(fv_off, s->dev.fv_off, ((size_t)s->n_fv + 1) * 4, cudaMemcpyDeviceToHost));
+    if (fv_idx && s->n_fv_idx) CORB_CUDA(cudaMemcpy(fv_idx, s->dev.fv_idx, (size_t)s->n_fv_idx * 4, cudaMemcpyDeviceToHost));
+    return CORB_OK;
+}
+
+int corb_bow_score_stores(corb_voc* v, const corb_bow_store* query, int ncand, const corb_bow_store* const* cands, double* scores) {
+    CORB_CHECK(v && query && ncand >= 0 && (ncand == 0 || (cands && scores)), CORB_ERR_INVALID, "bad argument");
+    if (ncand == 0) return CORB_OK;
+    CORB_CUDA(cudaSetDevice(v->device));
+    Packer p;
+    const size_t oW = p.take((size_t)ncand * 8), oV = p.take((size_t)ncand * 8), oN = p.take((size_t)ncand * 4), oS = p.take((size_t)ncand * 8);
+    int rc = v->arena.reserve(p.off);
+    if (rc != CORB_OK) return rc;
+    uint8_t *h = v->arena.h, *d = v->arena.d;
+    for (int i = 0; i < ncand; i++) {
+        CORB_CHECK(cands[i] && cands[i]->device == v->device, CORB_ERR_INVALID, "candidate %d is NULL or on another device", i);
+        ((const uint32_t**)(h + oW))[i] = cands[i]->dev.bow_words;
+        ((const double**)(h + oV))[i] = cands[i]->dev.bow_vals;
+        ((int*)(h + oN))[i] = cands[i]->n_bow;
+    }
+    CORB_CUDA(cudaMemcpyAsync(d, h, oS, cudaMemcpyHostToDevice, v->stream));
+    k_bow_score_ptr<<<(ncand * 32 + 255) / 256, 256, 0, v->stream>>>(query->dev.bow_words, query->dev.bow_vals, query->n_bow,
+                                                                     (const uint32_t* const*)(d + oW), (const double* const*)(d + oV),
+                                                                     (const int*)(d + oN), ncand, (double*)(d + oS));
+    CORB_CUDA(cudaGetLastError());
+    CORB_CUDA(cudaMemcpyAsync(h + oS, d + oS, (size_t)ncand * 8, cudaMemcpyDeviceToHost, v->stream));
+    CORB_CUDA(cudaStreamSynchronize(v->stream));
+    memcpy(scores, h + oS, (size_t)ncand * 8);
+    return CORB_OK;
+}
+
+
+/* SearchByBoW x3 between device-resident records: only the MapPoint liveness bytes go up and the match arrays come down. */
+int corb_bow_match_stores(corb_matcher* m, int variant, int ncalls, const corb_bow_store* const* A, const uint8_t* const* validA,
+                          const corb_bow_store* const* B, const uint8_t* const* validB, float nnratio, int check_ori,
+                          int32_t* const* match, int32_t* nmatches) {
+    CORB_CHECK(m && A && B && match && nmatches && ncalls >= 1, CORB_ERR_INVALID, "bad argument");
+    CORB_CHECK(variant >= 0 && variant <= 2, CORB_ERR_INVALID, "unknown variant %d", variant);
+    CORB_CUDA(cudaSetDevice(m->device));
+    const bool kfkf = variant == 2;
+    Packer p;
+    std::vector<size_t> oVA(ncalls), oVB(ncalls), oM(ncalls);
+    for (int i = 0; i < ncalls; i++) {
+        CORB_CHECK(A[i] && B[i] && A[i]->device == m->device && B[i]->device == m->device, CORB_ERR_INVALID, "call %d: records missing or on another device", i);
+        oVA[i] = p.take(validA && validA[i] ? A[i]->n : 0);
+        oVB[i] = p.take(kfkf && validB && validB[i] ? B[i]->n : 0);
+    }
+    const size_t in_bytes = p.off;
+    for (int i = 0; i < ncalls; i++) oM[i] = p.take((size_t)(kfkf ? A[i]->n : B[i]->n) * 4);
+    const size_t oNm = p.take((size_t)ncalls * 4), oPtr = p.take((size_t)ncalls * 8);
+    int rc = m->arena.reserve(p.off);
+    if (rc != CORB_OK) return rc;
+    uint8_t *h = m->arena.h, *d = m->arena.d;
+    std::vector<corb_bow_side> sa(ncalls), sb(ncalls);
+    std::vector<int32_t*> dm(ncalls);
+    for (int i = 0; i < ncalls; i++) {
+        const uint8_t *va = nullptr, *vb = nullptr;
+        if (validA && validA[i]) { memcpy(h + oVA[i], validA[i], A[i]->n); va = d + oVA[i]; }
+        if (kfkf && validB && validB[i]) { memcpy(h + oVB[i], validB[i], B[i]->n); vb = d + oVB[i]; }
+        corb_bow_store_side(A[i], va, &sa[i], nullptr);
+        corb_bow_store_side(B[i], vb, &sb[i], nullptr);
+        dm[i] = (int32_t*)(d + oM[i]);
+    }
+    if (in_bytes) CORB_CUDA(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, m->stream));
+    rc = corb_bow_match_batch_device(m, variant, ncalls, sa.data(), sb.data(), nnratio, check_ori, dm.data(), (int32_t*)(d + oNm));
+    if (rc != CORB_OK) return rc;
+    CORB_CUDA(cudaMemcpyAsync(h + oM[0], d + oM[0], oPtr - oM[0], cudaMemcpyDeviceToHost, m->stream));
+    CORB_CUDA(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < ncalls; i++) {
+        memcpy(match[i], h + oM[i], (size_t)(kfkf ? A[i]->n : B[i]->n) * 4);
+        nmatches[i] = ((int32_t*)(h + oNm))[i];
+    }
+    return CORB_OK;
+}
+
 }  // extern "C"

@@ -1148,6 +1148,19 @@ int corb_orb_device_results(const corb_orb* h, const corb_keypoint** d_kps, cons
     return CORB_OK;
 }
 
+int corb_frame_bow(corb_orb* h, corb_voc* v, int levelsup, corb_bow_store* s) {
+    CORB_CHECK(h && v && s && h->plan_w, CORB_ERR_INVALID, "bad argument or no extraction has run on this handle");
+    CORB_CHECK(!h->pending && !h->pending_pair, CORB_ERR_INVALID, "wait for the submitted extraction first");
+    CORB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->busy_stream ? h->busy_stream : h->stream;
+    // the keypoint count of the last extraction, read behind it on its stream (device-resident extractions never told the host)
+    int n = 0;
+    CORB_CUDA(cudaMemcpyAsync(&n, h->buf.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CORB_CUDA(cudaStreamSynchronize(st));
+    CORB_CHECK(n >= 0 && n <= h->geom.kp_cap, CORB_ERR_INVALID, "keypoint count %d out of range", n);
+    return corb_bow_store_fill(s, v, h->buf.kps, h->buf.desc, n, levelsup, (void*)st);
+}
+
 int corb_orb_host_results(const corb_orb* h, const corb_keypoint** kps, const uint8_t** desc, int* n) {
     CORB_CHECK(h && h->plan_w && h->h_scalars, CORB_ERR_INVALID, "no extraction has run on this handle");
     CORB_CHECK(h->h_scalars[1] == 0, CORB_ERR_CAPACITY, "device-side consistency check %d failed", h->h_scalars[1]);

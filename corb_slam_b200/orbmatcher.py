@@ -127,6 +127,30 @@ class ORBmatcher:
                                          nm.ctypes.data_as(_lib.i32p)))
         return [(o[:(a.n if variant == KF_KF else b.n)], int(k)) for o, a, b, k in zip(outs, As, Bs, nm)]
 
+    def SearchByBoWRecords(self, variant, recsA, validA, recsB, validB=None):
+        """SearchByBoW between device-resident BowRecords (corb_bow_match_stores): validA / validB = lists of host byte masks
+        (or None). -> [(match, nmatches)] like SearchByBoWBatch."""
+        n = len(recsA)
+        keep = []
+
+        def masks(recs, valids):
+            arr = (C.c_void_p * n)()
+            for i in range(n):
+                if valids is not None and valids[i] is not None:
+                    v = np.ascontiguousarray(valids[i], np.uint8)
+                    keep.append(v)
+                    arr[i] = v.ctypes.data
+            return arr
+        ra = (C.c_void_p * n)(*[r._h for r in recsA])
+        rb = (C.c_void_p * n)(*[r._h for r in recsB])
+        sizes = [(a.side()[0].n if variant == KF_KF else b.side()[0].n) for a, b in zip(recsA, recsB)]
+        outs = [np.empty(max(1, k), np.int32) for k in sizes]
+        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        nm = np.zeros(n, np.int32)
+        check(lib().corb_bow_match_stores(self._h, variant, n, ra, masks(recsA, validA), rb, masks(recsB, validB), self.mfNNratio,
+                                          int(self.mbCheckOrientation), ptrs, nm.ctypes.data_as(_lib.i32p)))
+        return [(o[:k], int(c)) for o, k, c in zip(outs, sizes, nm)]
+
     def SearchByBoW(self, kf, frame):
         """SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches): -> (match[F.N] = KF feature index or -1, nmatches)."""
         return self._batch(KF_FRAME, [kf], [frame])[0]

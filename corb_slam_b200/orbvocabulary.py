@@ -94,3 +94,56 @@ class ORBVocabulary:
         check(lib().corb_bow_score_batch(self._h, qw.ctypes.data, qv.ctypes.data, len(qw), n, pw, pv, cn.ctypes.data,
                                          out.ctypes.data))
         return out
+
+
+class BowRecord:
+    """Device-resident matching record of a Frame / KeyFrame (corb_bow_store): descriptors, angles, BowVector and
+    FeatureVector stay in HBM (reference: Frame::ComputeBoW, Frame.cc:399-406; KeyFrame::ComputeBoW, KeyFrame.cc:70-77)."""
+
+    def __init__(self, capacity=2048, device=0):
+        self._h = C.c_void_p()
+        check(lib().corb_bow_store_create(int(device), int(capacity), C.byref(self._h)))
+        self.device, self.capacity = int(device), int(capacity)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().corb_bow_store_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def from_extractor(self, extractor, voc, levelsup=4):
+        """corb_frame_bow: record <- the extractor's last (device-resident) result."""
+        check(lib().corb_frame_bow(extractor._h, voc._h, int(levelsup), self._h))
+        return self
+
+    def from_device(self, voc, d_desc, n, levelsup=4, d_kps=None, stream=None):
+        check(lib().corb_bow_store_fill(self._h, voc._h, d_kps, d_desc, int(n), int(levelsup), stream))
+        return self
+
+    def side(self, d_valid=None):
+        """corb_bow_side of device pointers (for ORBmatcher.SearchByBoWDevice) and the BowVector length."""
+        s, nb = _lib.BowSide(), C.c_int32()
+        check(lib().corb_bow_store_side(self._h, d_valid, C.byref(s), C.byref(nb)))
+        return s, nb.value
+
+    def download(self):
+        """-> (bow_words, bow_vals, fv_nodes, fv_off, fv_idx) like ORBVocabulary.transform."""
+        cap = self.capacity
+        bw, bv = np.empty(cap, np.uint32), np.empty(cap, np.float64)
+        fn, fo, fi = np.empty(cap, np.uint32), np.empty(cap + 1, np.int32), np.empty(cap, np.uint32)
+        nb, nf = C.c_int32(), C.c_int32()
+        check(lib().corb_bow_store_download(self._h, bw.ctypes.data, bv.ctypes.data, C.byref(nb), fn.ctypes.data, fo.ctypes.data,
+                                            fi.ctypes.data, C.byref(nf)))
+        g = nf.value
+        return bw[:nb.value].copy(), bv[:nb.value].copy(), fn[:g].copy(), fo[:g + 1].copy(), fi[:fo[g] if g else 0].copy()
+
+    @staticmethod
+    def score(voc, query, candidates):
+        """voc.score(query, c) for every candidate record, one launch."""
+        n = len(candidates)
+        arr = (C.c_void_p * max(n, 1))(*[c._h for c in candidates])
+        out = np.empty(n, np.float64)
+        check(lib().corb_bow_score_stores(voc._h, query._h, n, arr, out.ctypes.data))
+        return out

@@ -395,6 +395,34 @@ typedef int (*corb_allreduce_fn)(void* user, double* d_buf, size_t n, int op, vo
 CORB_API int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile uint8_t* stop, int robust, int device,
                            corb_ba_result* result, corb_allreduce_fn allreduce, void* allreduce_user);
 
+/* ------------------------------------------------------------------------------------------------ device-resident BoW record */
+
+/* The matching record of a Frame / KeyFrame kept in HBM: descriptors, keypoint angles, BowVector, FeatureVector. It is what
+ * Frame::ComputeBoW [Frame.cc:399-406] / KeyFrame::ComputeBoW [KeyFrame.cc:70-77] produce, built straight from the extractor's
+ * device-resident results (no descriptor round trip through the host, no std::map rebuild), and what SearchByBoW and the
+ * L1 score then read in place: relocalisation / map-fusion candidates stay on the GPU between calls.
+ *   corb_frame_bow        : record <- last extraction of `h` (must be complete) through vocabulary `v`, levelsup as Frame.cc:404
+ *   corb_bow_store_fill   : the same from any device arrays (d_kps may be NULL: angles 0)
+ *   corb_bow_store_side   : the record as a corb_bow_side of DEVICE pointers for corb_bow_match_batch_device (d_valid: device
+ *                           bytes, MapPoint liveness, or NULL)
+ *   corb_bow_store_download: BowVector / FeatureVector to the host (key order of the std::maps; fp64 bits of DBoW2)
+ *   corb_bow_score_stores : voc.score(query, cand[i]) for records [KeyFrameDatabase.cc:238], one launch */
+typedef struct corb_bow_store corb_bow_store;
+CORB_API int corb_bow_store_create(int device, int capacity, corb_bow_store** out);
+CORB_API void corb_bow_store_destroy(corb_bow_store* s);
+CORB_API int corb_bow_store_fill(corb_bow_store* s, corb_voc* v, const corb_keypoint* d_kps, const uint8_t* d_desc, int n, int levelsup,
+                                 void* stream);
+CORB_API int corb_frame_bow(corb_orb* h, corb_voc* v, int levelsup, corb_bow_store* s);
+CORB_API int corb_bow_store_side(const corb_bow_store* s, const uint8_t* d_valid, corb_bow_side* side, int* n_bow);
+CORB_API int corb_bow_store_download(const corb_bow_store* s, uint32_t* bow_words, double* bow_vals, int* n_bow, uint32_t* fv_nodes,
+                                     int32_t* fv_off, uint32_t* fv_idx, int* n_fv);
+/* SearchByBoW (variant as corb_bow_match) between records: validA[i] / validB[i] are HOST byte masks (MapPoint liveness, may be
+ * NULL), match[i] / nmatches are HOST outputs; the descriptors and feature vectors never leave the GPU. */
+CORB_API int corb_bow_match_stores(corb_matcher* m, int variant, int ncalls, const corb_bow_store* const* A, const uint8_t* const* validA,
+                                   const corb_bow_store* const* B, const uint8_t* const* validB, float nnratio, int check_ori,
+                                   int32_t* const* match, int32_t* nmatches);
+CORB_API int corb_bow_score_stores(corb_voc* v, const corb_bow_store* query, int ncand, const corb_bow_store* const* cands, double* scores);
+
 /* ------------------------------------------------------------------------------------------------ keyframe payload */
 
 /* Binary form of the extractor-produced part of a KeyFrame on the wire - mvKeys, mvKeysUn, mvuRight, mvDepth, mDescriptors,

@@ -168,3 +168,57 @@ def test_l1_score_batch_bit_exact():
     assert exp[-1] == pytest.approx(1.0) and exp[-2] == 0.0
     assert gvoc.score(q, cands[1]) == exp[1]
     gvoc.close()
+
+
+def test_device_resident_bow_records_equal_the_host_path():
+    """corb_frame_bow / corb_bow_store_*: BowVector + FeatureVector built on the device from the extractor's resident
+    descriptors equal corb_voc_transform (and therefore DBoW2) bit for bit; SearchByBoW and the L1 score between records
+    equal the host-array entry points."""
+    from corb_slam_b200 import BowRecord, ORBextractor
+    from corb_slam_b200.synth import stereo_frame
+    ovoc, gvoc = _voc(10, 4, 5)
+    ex = ORBextractor(2000, 1.2, 8, 20, 7)
+    rng = np.random.default_rng(2)
+    base = stereo_frame(1234)[0]
+    imgs = [base, (np.roll(base, 4, axis=1).astype(np.int16) + rng.normal(0, 3, base.shape).round().astype(np.int16)).clip(0, 255).astype(np.uint8),
+            stereo_frame(1235)[0]]
+    recs, host = [], []
+    for img in imgs:
+        k, d = ex(img)
+        k, d = k.copy(), d.copy()
+        r = BowRecord(2048).from_extractor(ex, gvoc, 2)
+        got, exp = r.download(), gvoc.transform(d, 2)
+        for a, b in zip(got, exp):
+            assert a.dtype == b.dtype and a.tobytes() == b.tobytes()
+        for a, b in zip(got, ovoc.transform(d, 2)):
+            assert a.tobytes() == b.tobytes()
+        recs.append(r); host.append((k, d, exp))
+    # L1 scores between records
+    sc = BowRecord.score(gvoc, recs[0], recs)
+    exp = gvoc.score_batch(host[0][2][:2], [h[2][:2] for h in host])
+    assert sc.tobytes() == exp.tobytes() and sc[0] == pytest.approx(1.0)
+    # SearchByBoW between records vs host arrays, all variants
+    valid = [(rng.random(len(h[0])) < 0.7).astype(np.uint8) for h in host]
+    for variant in (0, 1, 2):
+        m = ORBmatcher(0.75, True)
+        pairs = [(0, 1), (1, 0), (0, 2)]
+        got = m.SearchByBoWRecords(variant, [recs[i] for i, _ in pairs], [valid[i] for i, _ in pairs], [recs[j] for _, j in pairs],
+                                   [valid[j] for _, j in pairs])
+        A = [BowFeatures(host[i][1], *host[i][2][2:], valid=valid[i], angles=host[i][0]["angle"]) for i, _ in pairs]
+        B = [BowFeatures(host[j][1], *host[j][2][2:], valid=valid[j], angles=host[j][0]["angle"]) for _, j in pairs]
+        exp = m.SearchByBoWBatch(variant, A, B)
+        for (gm, gn), (em, en) in zip(got, exp):
+            assert gn == en and np.array_equal(gm, em)
+        assert exp[0][1] > 100
+        m.close()
+    # an empty record and a record filled from plain device arrays
+    import torch
+    e = BowRecord(64).from_device(gvoc, None, 0, 2)
+    assert all(len(a) == 0 for a in e.download()[:3])
+    d = torch.from_numpy(host[2][1][:50].copy()).cuda()
+    r = BowRecord(64).from_device(gvoc, d.data_ptr(), 50, 2)
+    for a, b in zip(r.download(), gvoc.transform(host[2][1][:50], 2)):
+        assert a.tobytes() == b.tobytes()
+    for r_ in recs:
+        r_.close()
+    ex.close(); gvoc.close()
