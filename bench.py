@@ -353,6 +353,48 @@ def bench_matcher(device, with_cpu=True):
         sc = gvoc.score_batch((qb[0], qb[1]), cvecs)
     dt = (time.perf_counter() - t0) / reps
     out["l1_score"] = {"scores_per_s": len(cvecs) / dt, "ms_per_batch": dt * 1e3, "batch": len(cvecs)}
+    # ---- the same three operations on device-resident records (corb_frame_bow / corb_bow_match_stores / corb_bow_score_stores):
+    #      descriptors and BoW / feature vectors never leave HBM, only liveness masks go up and match arrays / scores come down
+    from corb_slam_b200 import BowRecord, ORBextractor
+    from corb_slam_b200.synth import stereo_frame, frame_seed
+    ex = ORBextractor(*ORB_PARAMS, device=device)
+    img0 = stereo_frame(frame_seed(0))[0]
+    ex(img0)
+    qrec = BowRecord(2048, device=device).from_extractor(ex, gvoc, levelsup)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        qrec.from_extractor(ex, gvoc, levelsup)
+    dt = (time.perf_counter() - t0) / reps
+    got = qrec.download()
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(got, qb)), "device-built BoW differs from corb_voc_transform"
+    crecs = []
+    import torch
+    for (ck, cd) in cand_kd:
+        dd = torch.from_numpy(np.ascontiguousarray(cd)).cuda()
+        dk = torch.from_numpy(np.ascontiguousarray(ck).view(np.uint8)).cuda()
+        crecs.append(BowRecord(2048, device=device).from_device(gvoc, dd.data_ptr(), len(cd), levelsup, d_kps=dk.data_ptr()))
+    rres = m.SearchByBoWRecords(0, crecs, valids, [qrec] * len(crecs))
+    assert all(g[1] == r_[1] and np.array_equal(g[0], r_[0]) for g, r_ in zip(res, rres)), "record SearchByBoW differs from the host-array path"
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m.SearchByBoWRecords(0, crecs, valids, [qrec] * len(crecs))
+    dt_m = (time.perf_counter() - t0) / reps
+    rsc = BowRecord.score(gvoc, qrec, crecs * 8)
+    assert rsc.tobytes() == np.asarray(sc).tobytes(), "record L1 scores differ from the host-array path"
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        BowRecord.score(gvoc, qrec, crecs * 8)
+    dt_s = (time.perf_counter() - t0) / reps
+    out["device_records"] = {
+        "frame_bow_us": dt * 1e6, "frame_bow_descriptors_per_s": n / dt,
+        "search_by_bow": {"ms_per_batch": dt_m * 1e3, "calls_per_s": len(crecs) / dt_m, "hamming_pairs_per_s": pairs / dt_m,
+                          "roofline": {"bound": "hbm", "algorithmic_bytes": bow_bytes, "achieved": bow_bytes / dt_m / 1e9, "unit": "GB/s"}},
+        "l1_score": {"ms_per_batch": dt_s * 1e3, "scores_per_s": len(crecs) * 8 / dt_s},
+        "note": "corb_frame_bow (transform + BowVector / FeatureVector build on the device, one 16-byte D2H), "
+                "corb_bow_match_stores, corb_bow_score_stores; results asserted equal to the host-array entry points"}
+    for r_ in crecs + [qrec]:
+        r_.close()
+    ex.close()
     if with_cpu:
         from oracle import ref
         from oracle import _match_bind as M

@@ -143,7 +143,7 @@ class ORBmatcher:
             return arr
         ra = (C.c_void_p * n)(*[r._h for r in recsA])
         rb = (C.c_void_p * n)(*[r._h for r in recsB])
-        sizes = [(a.side()[0].n if variant == KF_KF else b.side()[0].n) for a, b in zip(recsA, recsB)]
+        sizes = [(a.n if variant == KF_KF else b.n) for a, b in zip(recsA, recsB)]
         outs = [np.empty(max(1, k), np.int32) for k in sizes]
         ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
         nm = np.zeros(n, np.int32)

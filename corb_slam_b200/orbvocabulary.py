@@ -103,8 +103,7 @@ class BowRecord:
     def __init__(self, capacity=2048, device=0):
         self._h = C.c_void_p()
         check(lib().corb_bow_store_create(int(device), int(capacity), C.byref(self._h)))
-        self.device, self.capacity = int(device), int(capacity)
-        self._keep = None
+        self.device, self.capacity, self.n = int(device), int(capacity), 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -116,10 +115,12 @@ class BowRecord:
     def from_extractor(self, extractor, voc, levelsup=4):
         """corb_frame_bow: record <- the extractor's last (device-resident) result."""
         check(lib().corb_frame_bow(extractor._h, voc._h, int(levelsup), self._h))
+        self.n = self.side()[0].n
         return self
 
     def from_device(self, voc, d_desc, n, levelsup=4, d_kps=None, stream=None):
         check(lib().corb_bow_store_fill(self._h, voc._h, d_kps, d_desc, int(n), int(levelsup), stream))
+        self.n = int(n)
         return self
 
     def side(self, d_valid=None):
