@@ -6,7 +6,7 @@
 One process per GPU (torchrun for N > 1); every rank is one `corbslam_client` stream pinned to its GPU (replicas:
 frames of different robots are independent), so scaling is weak and there is no data-path collective.
 A STEP = FRAMES_PER_STEP (64) stereo frames, in both arms; a frame = ORBextractor::operator() on the left and the right
-image (Frame.cc:78-81). The client keeps two frames in flight (two handle pairs, corb_orb_extract_pair_submit/_wait):
+image (Frame.cc:78-81). The client keeps IN_FLIGHT = 4 frames in flight (that many handle pairs, corb_orb_extract_pair_submit/_wait):
 frame i + 1 is extracted while the tracking thread would consume frame i.
 
   value : frames/s with the images already resident in HBM (a pool of 160 distinct stereo pairs = 149 MB, larger than the
@@ -38,7 +38,7 @@ ORB_PARAMS = (2000, 1.2, 8, 20, 7)  # KITTI00-02.yaml:38-51
 N_BASE = 16           # distinct synthetic scenes ...
 N_POOL = 160          # ... shifted into 160 distinct stereo pairs: 160 x 2 x 465 750 B = 149 MB > 126 MB of L2
 FRAMES_PER_STEP = 64  # one step = 64 stereo frames, in both arms
-IN_FLIGHT = int(os.environ.get("CORB_BENCH_IN_FLIGHT", "2"))  # stereo frames a client keeps in flight (handle pairs)
+IN_FLIGHT = int(os.environ.get("CORB_BENCH_IN_FLIGHT", "4"))  # stereo frames a client keeps in flight (handle pairs)
 ALGO_BYTES_PER_IMAGE = W * H + 1441432 + 60 * 2000  # input + pyramid + 60 B per keypoint (K = 2000)
 WORKLOAD = "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7"
 
@@ -539,22 +539,29 @@ def run_reference(args):
     if rank != 0:
         return
     n = args.gpus
-    exs = reference_extractors(n)
-    cpu_extract_fps(2, clients=n, exs=exs)  # warm-up
+    cores = os.cpu_count() or 2
+    # as many concurrent reference clients as our arm keeps frames in flight (IN_FLIGHT per GPU), two threads each
+    # (Frame.cc:78-81), bounded by the host cores: all the host threads this path can use for the same concurrency
+    clients = max(1, min(n * IN_FLIGHT, cores // 2))
+    per_client = max(1, (n * FRAMES_PER_STEP) // clients)
+    exs = reference_extractors(clients)
+    cpu_extract_fps(2, clients=clients, exs=exs)  # warm-up
     t_all, frames, per = 0.0, 0, []
     for _ in range(args.steps):
-        fps, dt, kind = cpu_extract_fps(FRAMES_PER_STEP, clients=n, exs=exs)
-        frames += n * FRAMES_PER_STEP
+        fps, dt, kind = cpu_extract_fps(per_client, clients=clients, exs=exs)
+        frames += clients * per_client
         t_all += dt
         per.append(dt)
+    one_fps = cpu_extract_fps(16, clients=1, exs=(exs[0][:1], exs[1]))[0]  # one client alone, as the reference runs it
     fps = frames / t_all
     line = {
         "impl": "reference", "metric": "stereo_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": n,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": bench_config(),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 2 * n, "kind": kind, "cpu_model": cpu_model(),
-                         "sample": "%d steps x %d stereo frames per client, %d client(s), L/R on two threads each (Frame.cc:78-81); %s"
-                                   % (args.steps, FRAMES_PER_STEP, n,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 2 * clients, "kind": kind, "cpu_model": cpu_model(),
+                         "one_client_value": one_fps,
+                         "sample": "%d steps x %d stereo frames per client, %d concurrent client(s), L/R on two threads each (Frame.cc:78-81); %s"
+                                   % (args.steps, per_client, clients,
                                       "the reference's own ORBextractor.cc compiled unmodified (oracle/_ref/libref.so)" if kind == "reference"
                                       else "oracle port (oracle/_ref/libref.so was not shipped)"),
                          "host_cores_available": os.cpu_count()},
@@ -601,7 +608,7 @@ def run_ours(args):
     mbf, mb = 386.1448, 386.1448 / 718.856
 
     def step_device(step, ev0, ev1):
-        """F stereo frames, alternating between the two handle pairs; events bracket the whole step on both streams."""
+        """F stereo frames, round-robin over the IN_FLIGHT handle pairs; events bracket the whole step on all their streams."""
         ev0.record(streams[0])
         for st in streams[1:]:
             st.wait_event(ev0)
@@ -616,7 +623,7 @@ def run_ours(args):
         ev1.record(streams[0])
 
     def step_host(step, submit, wait):
-        """F stereo frames through the split C-ABI calls from this one thread, two in flight; returns keypoints seen."""
+        """F stereo frames through the split C-ABI calls from this one thread, IN_FLIGHT in flight; returns keypoints seen."""
         nk = 0
         base = step * F
         for f in range(min(NP - 1, F)):
@@ -661,7 +668,7 @@ def run_ours(args):
         e1.record(streams[0])
         torch.cuda.synchronize()
         lat.append(1e3 * e0.elapsed_time(e1))
-    # ---- end to end through the C ABI with host buffers (wall clock; H2D + D2H inside), two frames in flight
+    # ---- end to end through the C ABI with host buffers (wall clock; H2D + D2H inside), IN_FLIGHT frames in flight
     barrier()
     t0 = time.perf_counter()
     nk = 0
@@ -815,7 +822,9 @@ def run_ours(args):
         kp_per_frame = nk / max(1, n_frames)
         h2d = 2 * W * H * F
         d2h = int(kp_per_frame * 60 + 16) * F
-        cpu_fps, cpu_dt, cpu_kind = cpu_extract_fps(args.sample_frames, clients=1)
+        cpu_clients = max(1, min(IN_FLIGHT, (os.cpu_count() or 2) // 2))  # the concurrency our arm has in flight, on host cores
+        cpu_fps, cpu_dt, cpu_kind = cpu_extract_fps(max(2, args.sample_frames // cpu_clients), clients=cpu_clients)
+        cpu_one_fps = cpu_extract_fps(min(32, args.sample_frames), clients=1)[0]
         cpu_fps_frame, _, _ = cpu_extract_fps(max(8, args.sample_frames // 4), clients=1, stereo=True)
         lat.sort()
         line = {
@@ -825,17 +834,17 @@ def run_ours(args):
             "us_per_frame": {"throughput": 1e3 * dev_ms / n_frames, "step_median": 1e3 * float(np.median(step_ms)) / F,
                              "step_p95": 1e3 * float(np.percentile(step_ms, 95)) / F,
                              "latency_median": lat[len(lat) // 2], "latency_p95": lat[int(len(lat) * 0.95)],
-                             "note": "throughput = two frames in flight; latency = one frame alone on the GPU, CUDA events per frame"},
+                             "note": "throughput = " + str(IN_FLIGHT) + " frames in flight; latency = one frame alone on the GPU, CUDA events per frame"},
             "e2e": {"value": world * n_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "us_per_frame": 1e3 * e2e_ms / n_frames,
-                    "note": "corb_orb_extract_pair_submit / _wait on two handle pairs from one thread: page-locked host images in, "
+                    "note": "corb_orb_extract_pair_submit / _wait on " + str(IN_FLIGHT) + " handle pairs from one thread: page-locked host images in, "
                             "host keypoints + descriptors out (read in place from the handles' page-locked result buffers)"},
             "e2e_one_in_flight": {"value": world * n_frames / (e2e_block_ms * 1e-3), "unit": "frames/s",
                                   "us_per_frame": 1e3 * e2e_block_ms / n_frames, "note": "the blocking corb_orb_extract_pair"},
             "e2e_stereo_frame": {"value": world * n_frames / (e2e_frame_ms * 1e-3), "unit": "frames/s",
                                  "us_per_frame": 1e3 * e2e_frame_ms / n_frames, "stereo_matches_per_frame": n_stereo / max(1, n_frames),
                                  "note": "corb_frame_stereo_submit / _wait: ExtractORB left+right and Frame::ComputeStereoMatches on the "
-                                         "GPU, two frames in flight; the pyramids never leave HBM"},
+                                         "GPU, " + str(IN_FLIGHT) + " frames in flight; the pyramids never leave HBM"},
             "gpu_launches": exl.launches_per_extract() * n_frames,  # one set of launches per stereo pair (grid z = 2)
             "tma": exl.uses_tma(),
             "clocks": clocks,
@@ -845,9 +854,10 @@ def run_ours(args):
                          "how": "achieved = 4 054 364 B (SURVEY.md section 8d) x frames/s per GPU; traffic = dram read + write summed over "
                                 "the launches of one stereo frame in the committed ncu --set full capture",
                          "traffic_source": cap_src, "dominant_kernel": dom, "kernels": kernels},
-            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 2, "kind": cpu_kind, "cpu_model": cpu_model(),
-                             "sample": "%d stereo frames, %s, L/R on two threads (Frame.cc:78-81), %.1f s"
-                                       % (args.sample_frames, "the reference's own ORBextractor.cc (oracle/_ref/libref.so)"
+            "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 2 * cpu_clients, "kind": cpu_kind, "cpu_model": cpu_model(),
+                             "one_client_value": cpu_one_fps,
+                             "sample": "%d stereo frames over %d concurrent clients, %s, L/R on two threads each (Frame.cc:78-81), %.1f s"
+                                       % (max(2, args.sample_frames // cpu_clients) * cpu_clients, cpu_clients, "the reference's own ORBextractor.cc (oracle/_ref/libref.so)"
                                           if cpu_kind == "reference" else "oracle port", cpu_dt),
                              "host_cores_available": os.cpu_count(), "stereo_frame_value": cpu_fps_frame,
                              "stereo_frame_kind": "port (Frame::ComputeStereoMatches needs the oracle's pyramids)"},
