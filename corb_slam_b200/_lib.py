@@ -45,7 +45,7 @@ class BaResult(C.Structure):
                 ("lambda_final", C.c_double), ("trial_accepted", C.c_uint8 * 256), ("trial_chi2", C.c_double * 256),
                 ("ms_total", C.c_double), ("ms_solve", C.c_double), ("reduced_blocks", C.c_int64),
                 ("border_poses", C.c_int32), ("max_active_rows", C.c_int32), ("ms_setup", C.c_double),
-                ("band_chunks", C.c_int32), ("separator_poses", C.c_int32)]
+                ("band_chunks", C.c_int32), ("separator_poses", C.c_int32), ("schur_pair_lists", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class PnpProblem(C.Structure):

@@ -537,6 +537,346 @@ __global__ void __launch_bounds__(256) k_ba_schur_rows(BaDev d) {
     if (lane < 6) d.bs[(size_t)j * 6 + lane] = d.bp[(size_t)j * 6 + lane] - coeff;
 }
 
+// ---- K11c: the same block rows from SORTED PAIR LISTS (default; k_ba_schur_rows above stays as the fallback and the A/B arm).
+//      Profile of K11b at the bench size (profiles/r02_ba_schur_rows_ncu.txt): 319 M warp instructions for 2.8 M block products -
+//      117 per edge for the index chains, 61 per (edge, co-observer) visit for six useful DFMA: instruction bound, not bandwidth.
+//      The structure (which edge of keyframe j meets which edge of keyframe j2 <= j in a landmark) does not change between LM
+//      iterations, so it is enumerated ONCE per BA: per keyframe the list of (own edge k, co-observer edge p) pairs sorted by
+//      (block column j2, k), cut into items of <= 32 consecutive pairs of one column. An iteration then is
+//        phase 1  T_k = W_k Dinv_l for the row's edges into shared memory (thread per edge) and the ordered sum for bs
+//        phase 2  nine lanes per item (lane = a 2 x 2 piece of the 6 x 6 block): acc += T_k W_p^T over the item's pairs in order,
+//                 three 128-bit loads from shared memory and three from L2 per 12 DFMA; a column with one item is written to S,
+//                 the others leave their partial sums in shared-memory slots
+//        phase 3  columns with several items add their slots in item order
+//      - every block has one writer and a fixed summation order (deterministic, no floating-point atomics).
+struct SchurPairs {
+    const int* row_pair_off;   // [P + 1] pairs of keyframe pi: [row_pair_off[pi], row_pair_off[pi + 1])
+    const int* row_item_off;   // [P + 1] first item slot of keyframe pi (offsets by upper bound)
+    int* row_item_cnt;         // [P] items of keyframe pi (a sentinel item with .y = end of the pairs follows them)
+    uint2* pairs;              // x = position p of the co-observer's edge, y = local index k of the own edge in the row
+    int4* items;               // x = block column j2, y = first pair (absolute), z = meta, w = 0
+    int* info;                 // [0] max edges per row, [1] max pairs per row, [2] max slots per row, [3] cap exceeded
+};
+constexpr int kSpThreads = 512, kSpPairCap = 8192, kSpChunk = 32;
+constexpr int kSpMulti = 1 << 6, kSpFirst = 1 << 7, kSpLast = 1 << 8;
+
+// exclusive scan of one int per thread over a 512-thread block (thread order); *total = block sum
+__device__ __forceinline__ int sp_block_scan(int v, int* warp_tmp, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < kSpThreads / 32 ? warp_tmp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        warp_tmp[lane] = w;
+    }
+    __syncthreads();
+    const int base = wid ? warp_tmp[wid - 1] : 0;
+    *total = warp_tmp[kSpThreads / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+// pairs of one edge of row j: co-observers of its landmark in keyframes j2 with 0 <= j2 <= j
+__device__ __forceinline__ int sp_edge_pairs(const BaDev& d, int e, int j) {
+    const int l = d.e_point[e];
+    if (d.lfree[l] < 0) return 0;
+    int n = 0;
+    for (int p = d.lm_off[l]; p < d.lm_off[l + 1]; p++) {
+        const int j2 = d.pfree[d.e_pose[p]];
+        n += j2 >= 0 && j2 <= j;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256) k_ba_pairs_count(BaDev d, int* __restrict__ row_np, int* __restrict__ row_bound, int* __restrict__ info) {
+    __shared__ int sm[8];
+    const int pi = blockIdx.x, j = d.pfree[pi];
+    const int k0 = d.pose_off[pi], ne = d.pose_off[pi + 1] - k0;
+    int n = 0;
+    if (j >= 0)
+        for (int k = threadIdx.x; k < ne; k += 256) n += sp_edge_pairs(d, d.pose_edges[k0 + k], j);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int np = 0;
+        for (int w = 0; w < 8; w++) np += sm[w];
+        row_np[pi] = np;
+        // items <= distinct columns + cuts at multiples of kSpChunk, + the sentinel
+        row_bound[pi] = j < 0 ? 0 : (np + kSpChunk - 1) / kSpChunk + min(np, j - d.first[j] + 1) + 1;
+        if (j >= 0) {
+            atomicMax(&info[0], ne);
+            atomicMax(&info[1], np);
+        }
+    }
+}
+
+// exclusive scans of the two per-row arrays (one block; P is a few thousand keyframes)
+__global__ void __launch_bounds__(1024) k_ba_pairs_scan(const int* __restrict__ a, const int* __restrict__ b, int n, int* __restrict__ oa,
+                                                        int* __restrict__ ob) {
+    __shared__ int wa[32], wb[32], base[2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base[0] = base[1] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const int va = i < n ? a[i] : 0, vb = i < n ? b[i] : 0;
+        int ia = va, ib = vb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ua; ib += ub; }
+        }
+        if (lane == 31) { wa[wid] = ia; wb[wid] = ib; }
+        __syncthreads();
+        if (wid == 0) {
+            int xa = wa[lane], xb = wb[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ua = __shfl_up_sync(0xffffffffu, xa, o), ub = __shfl_up_sync(0xffffffffu, xb, o);
+                if (lane >= o) { xa += ua; xb += ub; }
+            }
+            wa[lane] = xa; wb[lane] = xb;
+        }
+        __syncthreads();
+        const int ba = base[0] + (wid ? wa[wid - 1] : 0), bb = base[1] + (wid ? wb[wid - 1] : 0);
+        if (i < n) { oa[i] = ba + ia - va; ob[i] = bb + ib - vb; }
+        __syncthreads();
+        if (threadIdx.x == 0) { base[0] += wa[31]; base[1] += wb[31]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { oa[n] = base[0]; ob[n] = base[1]; }
+}
+
+// one CTA per keyframe: enumerate the pairs in edge order, sort by (column, position) in shared memory, emit pairs and items
+__global__ void __launch_bounds__(kSpThreads) k_ba_pairs_build(BaDev d, SchurPairs sp) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(sp_smem);            // [n2]
+    uint2* tmp = reinterpret_cast<uint2*>(sp_smem + (size_t)kSpPairCap * 4);  // [np]
+    __shared__ int warp_tmp[32];
+    __shared__ int run_base;
+    const int pi = blockIdx.x, j = d.pfree[pi], tid = threadIdx.x;
+    if (j < 0) { if (tid == 0) sp.row_item_cnt[pi] = 0; return; }
+    const int off = sp.row_pair_off[pi], np = sp.row_pair_off[pi + 1] - off;
+    const int item0 = sp.row_item_off[pi];
+    if (np > kSpPairCap || d.Pf >= (1 << 19)) {
+        if (tid == 0) { sp.info[3] = 1; sp.row_item_cnt[pi] = 0; }
+        return;
+    }
+    const int k0 = d.pose_off[pi], ne = d.pose_off[pi + 1] - k0, fj = d.first[j];
+    int n2 = 1;
+    while (n2 < np) n2 <<= 1;
+    if (tid == 0) run_base = 0;
+    for (int i = np + tid; i < n2; i += kSpThreads) keys[i] = 0xffffffffu;
+    __syncthreads();
+    for (int kb = 0; kb < ne; kb += kSpThreads) {  // enumeration in edge order: positions from a block scan
+        const int k = kb + tid;
+        int e = -1, cnt = 0;
+        if (k < ne) { e = d.pose_edges[k0 + k]; cnt = sp_edge_pairs(d, e, j); }
+        int total;
+        int pos = run_base + sp_block_scan(cnt, warp_tmp, &total);
+        if (cnt) {
+            const int l = d.e_point[e];
+            for (int p = d.lm_off[l]; p < d.lm_off[l + 1]; p++) {
+                const int j2 = d.pfree[d.e_pose[p]];
+                if (j2 >= 0 && j2 <= j) {
+                    keys[pos] = (uint32_t)(j2 - fj) << 13 | (uint32_t)pos;
+                    tmp[pos] = make_uint2((unsigned)p, (unsigned)k);
+                    pos++;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) run_base += total;
+        __syncthreads();
+    }
+    for (int kk = 2; kk <= n2; kk <<= 1)  // bitonic sort, ascending
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            for (int i = tid; i < (n2 >> 1); i += kSpThreads) {
+                const int lo = ((i & ~(jj - 1)) << 1) | (i & (jj - 1)), hi = lo | jj;
+                const bool up = (lo & kk) == 0;
+                const uint32_t a = keys[lo], b = keys[hi];
+                if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    // pairs in sorted order; an item starts where the column changes and at every multiple of kSpChunk
+    if (tid == 0) run_base = 0;
+    __syncthreads();
+    for (int ib = 0; ib < np; ib += kSpThreads) {
+        const int i = ib + tid;
+        int head = 0, col = 0;
+        if (i < np) {
+            const uint32_t key = keys[i];
+            col = (int)(key >> 13);
+            sp.pairs[off + i] = tmp[key & 8191u];
+            head = i == 0 || (i & (kSpChunk - 1)) == 0 || (int)(keys[i - 1] >> 13) != col;
+        }
+        int total;
+        const int it = run_base + sp_block_scan(head, warp_tmp, &total);
+        if (head) sp.items[item0 + it] = make_int4(col + fj, off + i, 0, 0);
+        __syncthreads();
+        if (tid == 0) run_base += total;
+        __syncthreads();
+    }
+    const int n_items = run_base;
+    if (tid == 0) {
+        sp.items[item0 + n_items] = make_int4(-1, off + np, 0, 0);  // sentinel: end of the last item
+        sp.row_item_cnt[pi] = n_items;
+    }
+    __syncthreads();
+    // meta: columns with several items keep partial sums in slots (consecutive in item order)
+    if (tid == 0) run_base = 0;
+    __syncthreads();
+    for (int ib = 0; ib < n_items; ib += kSpThreads) {
+        const int it = ib + tid;
+        int multi = 0, first = 0, last = 0;
+        if (it < n_items) {
+            const int c = sp.items[item0 + it].x;
+            const bool same_prev = it > 0 && sp.items[item0 + it - 1].x == c;
+            const bool same_next = it + 1 < n_items && sp.items[item0 + it + 1].x == c;
+            multi = same_prev || same_next;
+            first = multi && !same_prev;
+            last = multi && !same_next;
+        }
+        int total;
+        const int slot = run_base + sp_block_scan(multi, warp_tmp, &total);
+        if (it < n_items) sp.items[item0 + it].z = (multi ? kSpMulti : 0) | (first ? kSpFirst : 0) | (last ? kSpLast : 0) | slot << 16;
+        __syncthreads();
+        if (tid == 0) run_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) atomicMax(&sp.info[2], run_base);
+}
+
+__global__ void __launch_bounds__(kSpThreads) k_ba_schur_pairs(BaDev d, SchurPairs sp, int t_cap) {
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    double* T = reinterpret_cast<double*>(sp_smem);          // [t_cap][18]
+    double* part = T + (size_t)t_cap * 18;                    // [slots][36]
+    __shared__ double red[kSpThreads / 32][6];
+    const int pi = blockIdx.x, j = d.pfree[pi];
+    if (j < 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k0 = d.pose_off[pi], ne = d.pose_off[pi + 1] - k0;
+    // ---- phase 1: T_k = W_k Dinv_l, and bs(j) = bp(j) - sum_k W_k (Dinv_l bl)
+    double cf[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = tid; k < ne; k += kSpThreads) {
+        const int e = d.pose_edges[k0 + k];
+        const int l = d.e_point[e];
+        double2* Tk = reinterpret_cast<double2*>(T + (size_t)k * 18);
+        if (d.lfree[l] < 0) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) Tk[i] = make_double2(0.0, 0.0);
+            continue;
+        }
+        double w[18], di[9], db[3];
+        const double2* Wg = reinterpret_cast<const double2*>(d.W + (size_t)e * 18);
+#pragma unroll
+        for (int i = 0; i < 9; i++) { const double2 v = Wg[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+#pragma unroll
+        for (int i = 0; i < 9; i++) di[i] = d.Dinv[(size_t)l * 9 + i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) db[i] = d.db[(size_t)l * 3 + i];
+        double t[18];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+            for (int m = 0; m < 3; m++) t[r * 3 + m] = w[r * 3] * di[m] + w[r * 3 + 1] * di[3 + m] + w[r * 3 + 2] * di[6 + m];
+            cf[r] += w[r * 3] * db[0] + w[r * 3 + 1] * db[1] + w[r * 3 + 2] * db[2];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) Tk[i] = make_double2(t[2 * i], t[2 * i + 1]);
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) cf[r] += __shfl_down_sync(0xffffffffu, cf[r], o);
+        if (lane == 0) red[warp][r] = cf[r];
+    }
+    __syncthreads();
+    if (tid < 6) {
+        double c = 0.0;
+        for (int w = 0; w < kSpThreads / 32; w++) c += red[w][tid];
+        d.bs[(size_t)j * 6 + tid] = d.bp[(size_t)j * 6 + tid] - c;
+    }
+    // ---- phase 2: items
+    const int item0 = sp.row_item_off[pi], n_items = sp.row_item_cnt[pi];
+    const int fj = d.first[j];
+    double* row = d.S + (size_t)d.rowoff[j] * 36;
+    const int g = warp * 3 + lane / 9, gl = lane % 9, rr = gl / 3, cc = gl - rr * 3;
+    const bool act = lane < 27;
+    const double* Hj = d.Hpp + (size_t)j * 36;
+    if (act)
+        for (int it = g; it < n_items; it += (kSpThreads / 32) * 3) {
+            const int4 I = sp.items[item0 + it];
+            const int end = sp.items[item0 + it + 1].y;
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll 4
+            for (int i = I.y; i < end; i++) {
+                const uint2 pr = sp.pairs[i];
+                const double2* Tp = reinterpret_cast<const double2*>(T + (size_t)pr.y * 18 + rr * 6);
+                const double2* Wp = reinterpret_cast<const double2*>(d.W + (size_t)pr.x * 18 + cc * 6);
+                const double2 w0 = __ldg(Wp), w1 = __ldg(Wp + 1), w2 = __ldg(Wp + 2);
+                const double2 t0 = Tp[0], t1 = Tp[1], t2 = Tp[2];
+                // T rows 2rr: (t0.x, t0.y, t1.x), 2rr + 1: (t1.y, t2.x, t2.y); W rows 2cc: (w0.x, w0.y, w1.x), 2cc + 1: (w1.y, w2.x, w2.y)
+                a00 += t0.x * w0.x + t0.y * w0.y + t1.x * w1.x;
+                a01 += t0.x * w1.y + t0.y * w2.x + t1.x * w2.y;
+                a10 += t1.y * w0.x + t2.x * w0.y + t2.y * w1.x;
+                a11 += t1.y * w1.y + t2.x * w2.x + t2.y * w2.y;
+            }
+            const int e0 = (2 * rr) * 6 + 2 * cc;  // entries (2rr, 2cc), (2rr, 2cc+1), (2rr+1, 2cc), (2rr+1, 2cc+1)
+            if (I.z & kSpMulti) {
+                double* ps = part + (size_t)(I.z >> 16) * 36;
+                ps[e0] = a00; ps[e0 + 1] = a01; ps[e0 + 6] = a10; ps[e0 + 7] = a11;
+            } else {
+                double* blk = row + (size_t)(I.x - fj) * 36;
+                const bool dg = I.x == j;
+                blk[e0] = (dg ? Hj[e0] : 0.0) - a00;
+                blk[e0 + 1] = (dg ? Hj[e0 + 1] : 0.0) - a01;
+                blk[e0 + 6] = (dg ? Hj[e0 + 6] : 0.0) - a10;
+                blk[e0 + 7] = (dg ? Hj[e0 + 7] : 0.0) - a11;
+            }
+        }
+    __syncthreads();
+    // ---- phase 3: columns with several items: their slots in item order
+    if (act)
+        for (int it = g; it < n_items; it += (kSpThreads / 32) * 3) {
+            const int4 I = sp.items[item0 + it];
+            if (!(I.z & kSpFirst)) continue;
+            const int e0 = (2 * rr) * 6 + 2 * cc;
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            int z = I.z;
+            for (int q = it;; q++) {
+                const double* ps = part + (size_t)(z >> 16) * 36;
+                a00 += ps[e0]; a01 += ps[e0 + 1]; a10 += ps[e0 + 6]; a11 += ps[e0 + 7];
+                if (z & kSpLast) break;
+                z = sp.items[item0 + q + 1].z;
+            }
+            double* blk = row + (size_t)(I.x - fj) * 36;
+            const bool dg = I.x == j;
+            blk[e0] = (dg ? Hj[e0] : 0.0) - a00;
+            blk[e0 + 1] = (dg ? Hj[e0 + 1] : 0.0) - a01;
+            blk[e0 + 6] = (dg ? Hj[e0 + 6] : 0.0) - a10;
+            blk[e0 + 7] = (dg ? Hj[e0 + 7] : 0.0) - a11;
+        }
+    // a keyframe without any free landmark: the diagonal is Hpp alone (the diagonal column sorts last)
+    if (n_items == 0 || sp.items[item0 + n_items - 1].x != j) {
+        if (tid < 36) row[(size_t)(j - fj) * 36 + tid] = Hj[tid];
+    }
+}
+
 __global__ void __launch_bounds__(256) k_ba_add_lambda(BaDev d, double lambda) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= d.Pf * 6) return;
@@ -1513,6 +1853,10 @@ struct BaHost {
     size_t border_tiled_bytes = 0;
     int n_chunks = 1;           // independent band chunks (columns chunk_start[q] .. chunk_start[q + 1])  // first[] / rowoff[] of the band rows staged by the border-row and band-backward kernels     // longest band envelope (blocks left of the diagonal)
     int n_band = 0;        // free keyframes before the border block (== Pf when there is no border)
+    SchurPairs sp = {};      // sorted pair lists of the Schur rows (k_ba_schur_pairs); sp_ok: built and within the kernel's limits
+    bool sp_ok = false;
+    int sp_tcap = 0;
+    size_t sp_smem = 0;
     corb_allreduce_fn ar = nullptr;
     void* ar_user = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1583,6 +1927,38 @@ struct BaHost {
         }
         d.pose_off = off;
         d.pose_edges = vals_out;
+        return CORB_OK;
+    }
+    // Sorted pair lists for k_ba_schur_pairs, once per call (the structure is the same in every LM iteration).
+    // `pairs_bound` = sum over landmarks of k (k + 1) / 2 observations pairs (exact when nothing is fixed), `nblocks` = envelope blocks.
+    int build_schur_pairs(size_t pairs_bound, size_t nblocks) {
+        sp_ok = false;
+        const char* env = getenv("CORB_BA_SCHUR");
+        if ((env && !strcmp(env, "old")) || d.P <= 0 || d.E <= 0 || pairs_bound == 0 || pairs_bound > ((size_t)1 << 30)) return CORB_OK;
+        const size_t items_bound = pairs_bound / kSpChunk + nblocks + 2 * (size_t)d.P + 16;
+        int *row_np, *row_bound, *pair_off, *item_off, *item_cnt, *info;
+        uint2* pairs;
+        int4* items;
+        int rc;
+        if ((rc = alloc(&row_np, (size_t)d.P)) != CORB_OK || (rc = alloc(&row_bound, (size_t)d.P)) != CORB_OK ||
+            (rc = alloc(&pair_off, (size_t)d.P + 1)) != CORB_OK || (rc = alloc(&item_off, (size_t)d.P + 1)) != CORB_OK ||
+            (rc = alloc(&item_cnt, (size_t)d.P)) != CORB_OK || (rc = alloc(&info, 4)) != CORB_OK ||
+            (rc = alloc(&pairs, pairs_bound)) != CORB_OK || (rc = alloc(&items, items_bound)) != CORB_OK)
+            return rc;
+        CORB_CUDA(cudaMemsetAsync(info, 0, 4 * sizeof(int), stream));
+        k_ba_pairs_count<<<d.P, 256, 0, stream>>>(d, row_np, row_bound, info);
+        k_ba_pairs_scan<<<1, 1024, 0, stream>>>(row_np, row_bound, d.P, pair_off, item_off);
+        sp.row_pair_off = pair_off; sp.row_item_off = item_off; sp.row_item_cnt = item_cnt; sp.pairs = pairs; sp.items = items; sp.info = info;
+        CORB_SMEM_OPT_IN(k_ba_pairs_build);
+        CORB_SMEM_OPT_IN(k_ba_schur_pairs);
+        k_ba_pairs_build<<<d.P, kSpThreads, (size_t)kSpPairCap * 12, stream>>>(d, sp);
+        CORB_CUDA(cudaGetLastError());
+        int h_info[4] = {0, 0, 0, 1};
+        CORB_CUDA(cudaMemcpyAsync(h_info, info, sizeof(h_info), cudaMemcpyDeviceToHost, stream));
+        CORB_CUDA(cudaStreamSynchronize(stream));
+        sp_tcap = std::max(1, h_info[0]);
+        sp_smem = ((size_t)sp_tcap * 18 + (size_t)std::max(1, h_info[2]) * 36) * sizeof(double);
+        sp_ok = !h_info[3] && sp_smem <= 200 * 1024;
         return CORB_OK;
     }
     template <typename T>
@@ -1657,7 +2033,8 @@ struct BaHost {
         if (d.L > 0) k_ba_dinv<<<(d.L + 255) / 256, 256, 0, stream>>>(d, lambda);
         if (d.P > 0) {
             CORB_CUDA(cudaMemsetAsync(d.S, 0, s_doubles * sizeof(double), stream));  // rows are accumulated into, not zeroed, by the kernel
-            k_ba_schur_rows<<<d.P, 256, 0, stream>>>(d);  // one CTA per keyframe
+            if (sp_ok) k_ba_schur_pairs<<<d.P, kSpThreads, sp_smem, stream>>>(d, sp, sp_tcap);  // one CTA per keyframe, sorted pair lists
+            else k_ba_schur_rows<<<d.P, 256, 0, stream>>>(d);                                    // one CTA per keyframe, edge walk
         }
         int rc = reduce(d.S, s_doubles + (size_t)d.Pf * 6, 0);
         if (rc != CORB_OK) return rc;
@@ -2166,6 +2543,15 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     const size_t npart = (size_t)std::max(std::max((E + 255) / 256, (L * 3 + 255) / 256), 2048) * 2 + 16;
     AL(partial, npart); AL(scalars, 8);
 #undef AL
+    {
+        size_t pairs_bound = 0;
+        for (int l = 0; l < L; l++) {
+            const size_t k = (size_t)(lm_off[l + 1] - lm_off[l]);
+            pairs_bound += k * (k + 1) / 2;
+        }
+        if ((rc = H.build_schur_pairs(pairs_bound, (size_t)nblocks)) != CORB_OK) return rc;
+        res->schur_pair_lists = H.sp_ok ? 1 : 0;
+    }
     d.bs = d.S + H.s_doubles;
     CORB_CUDA(cudaMemcpyAsync(d.q, p->pose_q, (size_t)P * 4 * sizeof(double), cudaMemcpyHostToDevice, H.stream));
     CORB_CUDA(cudaMemcpyAsync(d.t, p->pose_t, (size_t)P * 3 * sizeof(double), cudaMemcpyHostToDevice, H.stream));

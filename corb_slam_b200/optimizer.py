@@ -79,7 +79,7 @@ class Optimizer:
                 "trial_chi2": [float(res.trial_chi2[i]) for i in range(n)], "ms_total": res.ms_total,
                 "ms_solve": res.ms_solve, "reduced_blocks": res.reduced_blocks, "border_poses": res.border_poses,
                 "max_active_rows": res.max_active_rows, "ms_setup": res.ms_setup, "band_chunks": res.band_chunks,
-                "separator_poses": res.separator_poses}
+                "separator_poses": res.separator_poses, "schur_pair_lists": res.schur_pair_lists}
         out = dict(problem)
         out["pose_q"], out["pose_t"], out["point_xyz"] = keep["pose_q"], keep["pose_t"], keep["point_xyz"]
         return out, info

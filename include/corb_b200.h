@@ -373,6 +373,8 @@ typedef struct {
     double ms_setup;             /* host structure build + uploads before the first LM iteration */
     int32_t band_chunks;         /* independent chunks the band was cut into (separator keyframes join the border) */
     int32_t separator_poses;     /* keyframes ordered last only to decouple the chunks */
+    int32_t schur_pair_lists;    /* 1: Schur rows from the sorted pair lists built once per call; 0: per-iteration edge walk (fallback) */
+    int32_t reserved0;
 } corb_ba_result;
 
 /* corb_ba_solve keeps its device buffers in a per-device arena between calls (a global BA allocates ~40 buffers; the
