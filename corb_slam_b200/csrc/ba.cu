@@ -556,8 +556,10 @@ struct SchurPairs {
     uint2* pairs;              // x = position p of the co-observer's edge, y = local index k of the own edge in the row
     int4* items;               // x = block column j2, y = first pair (absolute), z = meta, w = 0
     int* info;                 // [0] max edges per row, [1] max pairs per row, [2] max slots per row, [3] cap exceeded
+    int chunk;                 // pairs per item at most (a power of two: 32 or 64)
+    int2* row_el;              // [E] in pose-CSR order: x = edge position e, y = landmark l (-1: fixed landmark) - the row's index chain, resolved once
 };
-constexpr int kSpThreads = 512, kSpPairCap = 8192, kSpChunk = 32;
+constexpr int kSpThreads = 512, kSpPairCap = 8192, kSpChunkMax = 64;
 constexpr int kSpMulti = 1 << 6, kSpFirst = 1 << 7, kSpLast = 1 << 8;
 
 // exclusive scan of one int per thread over a 512-thread block (thread order); *total = block sum
@@ -599,13 +601,18 @@ __device__ __forceinline__ int sp_edge_pairs(const BaDev& d, int e, int j) {
     return n;
 }
 
-__global__ void __launch_bounds__(256) k_ba_pairs_count(BaDev d, int* __restrict__ row_np, int* __restrict__ row_bound, int* __restrict__ info) {
+__global__ void __launch_bounds__(256) k_ba_pairs_count(BaDev d, int* __restrict__ row_np, int* __restrict__ row_bound, int* __restrict__ info, int chunk,
+                                                        int2* __restrict__ row_el) {
     __shared__ int sm[8];
     const int pi = blockIdx.x, j = d.pfree[pi];
     const int k0 = d.pose_off[pi], ne = d.pose_off[pi + 1] - k0;
     int n = 0;
     if (j >= 0)
-        for (int k = threadIdx.x; k < ne; k += 256) n += sp_edge_pairs(d, d.pose_edges[k0 + k], j);
+        for (int k = threadIdx.x; k < ne; k += 256) {
+            const int e = d.pose_edges[k0 + k], l = d.e_point[e];
+            row_el[k0 + k] = make_int2(e, d.lfree[l] < 0 ? -1 : l);
+            n += sp_edge_pairs(d, e, j);
+        }
 #pragma unroll
     for (int o = 16; o; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = n;
@@ -614,8 +621,8 @@ __global__ void __launch_bounds__(256) k_ba_pairs_count(BaDev d, int* __restrict
         int np = 0;
         for (int w = 0; w < 8; w++) np += sm[w];
         row_np[pi] = np;
-        // items <= distinct columns + cuts at multiples of kSpChunk, + the sentinel
-        row_bound[pi] = j < 0 ? 0 : (np + kSpChunk - 1) / kSpChunk + min(np, j - d.first[j] + 1) + 1;
+        // items <= distinct columns + cuts at multiples of the chunk, + the sentinel
+        row_bound[pi] = j < 0 ? 0 : (np + chunk - 1) / chunk + min(np, j - d.first[j] + 1) + 1;
         if (j >= 0) {
             atomicMax(&info[0], ne);
             atomicMax(&info[1], np);
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(kSpThreads) k_ba_pairs_build(BaDev d, SchurPai
             }
             __syncthreads();
         }
-    // pairs in sorted order; an item starts where the column changes and at every multiple of kSpChunk
+    // pairs in sorted order; an item starts where the column changes and at every multiple of the chunk
     if (tid == 0) run_base = 0;
     __syncthreads();
     for (int ib = 0; ib < np; ib += kSpThreads) {
@@ -722,7 +729,7 @@ __global__ void __launch_bounds__(kSpThreads) k_ba_pairs_build(BaDev d, SchurPai
             const uint32_t key = keys[i];
             col = (int)(key >> 13);
             sp.pairs[off + i] = tmp[key & 8191u];
-            head = i == 0 || (i & (kSpChunk - 1)) == 0 || (int)(keys[i - 1] >> 13) != col;
+            head = i == 0 || (i & (sp.chunk - 1)) == 0 || (int)(keys[i - 1] >> 13) != col;
         }
         int total;
         const int it = run_base + sp_block_scan(head, warp_tmp, &total);
@@ -761,22 +768,25 @@ __global__ void __launch_bounds__(kSpThreads) k_ba_pairs_build(BaDev d, SchurPai
     if (tid == 0) atomicMax(&sp.info[2], run_base);
 }
 
-__global__ void __launch_bounds__(kSpThreads) k_ba_schur_pairs(BaDev d, SchurPairs sp, int t_cap) {
+template <int TH, int CH>
+__global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) k_ba_schur_pairs(BaDev d, SchurPairs sp, int t_cap) {
+    constexpr int NR = (CH + 8) / 9;  // record registers per lane
     extern __shared__ __align__(16) unsigned char sp_smem[];
     double* T = reinterpret_cast<double*>(sp_smem);          // [t_cap][18]
     double* part = T + (size_t)t_cap * 18;                    // [slots][36]
-    __shared__ double red[kSpThreads / 32][6];
+    __shared__ double red[TH / 32][6];
     const int pi = blockIdx.x, j = d.pfree[pi];
     if (j < 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k0 = d.pose_off[pi], ne = d.pose_off[pi + 1] - k0;
     // ---- phase 1: T_k = W_k Dinv_l, and bs(j) = bp(j) - sum_k W_k (Dinv_l bl)
     double cf[6] = {0, 0, 0, 0, 0, 0};
-    for (int k = tid; k < ne; k += kSpThreads) {
-        const int e = d.pose_edges[k0 + k];
-        const int l = d.e_point[e];
+#pragma unroll 2
+    for (int k = tid; k < ne; k += TH) {
+        const int2 el = sp.row_el[k0 + k];
+        const int e = el.x, l = el.y;
         double2* Tk = reinterpret_cast<double2*>(T + (size_t)k * 18);
-        if (d.lfree[l] < 0) {
+        if (l < 0) {
 #pragma unroll
             for (int i = 0; i < 9; i++) Tk[i] = make_double2(0.0, 0.0);
             continue;
@@ -808,7 +818,7 @@ __global__ void __launch_bounds__(kSpThreads) k_ba_schur_pairs(BaDev d, SchurPai
     __syncthreads();
     if (tid < 6) {
         double c = 0.0;
-        for (int w = 0; w < kSpThreads / 32; w++) c += red[w][tid];
+        for (int w = 0; w < TH / 32; w++) c += red[w][tid];
         d.bs[(size_t)j * 6 + tid] = d.bp[(size_t)j * 6 + tid] - c;
     }
     // ---- phase 2: items
@@ -818,24 +828,63 @@ __global__ void __launch_bounds__(kSpThreads) k_ba_schur_pairs(BaDev d, SchurPai
     const int g = warp * 3 + lane / 9, gl = lane % 9, rr = gl / 3, cc = gl - rr * 3;
     const bool act = lane < 27;
     const double* Hj = d.Hpp + (size_t)j * 36;
-    if (act)
-        for (int it = g; it < n_items; it += (kSpThreads / 32) * 3) {
-            const int4 I = sp.items[item0 + it];
-            const int end = sp.items[item0 + it + 1].y;
-            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-#pragma unroll 4
-            for (int i = I.y; i < end; i++) {
-                const uint2 pr = sp.pairs[i];
-                const double2* Tp = reinterpret_cast<const double2*>(T + (size_t)pr.y * 18 + rr * 6);
-                const double2* Wp = reinterpret_cast<const double2*>(d.W + (size_t)pr.x * 18 + cc * 6);
-                const double2 w0 = __ldg(Wp), w1 = __ldg(Wp + 1), w2 = __ldg(Wp + 2);
-                const double2 t0 = Tp[0], t1 = Tp[1], t2 = Tp[2];
-                // T rows 2rr: (t0.x, t0.y, t1.x), 2rr + 1: (t1.y, t2.x, t2.y); W rows 2cc: (w0.x, w0.y, w1.x), 2cc + 1: (w1.y, w2.x, w2.y)
-                a00 += t0.x * w0.x + t0.y * w0.y + t1.x * w1.x;
-                a01 += t0.x * w1.y + t0.y * w2.x + t1.x * w2.y;
-                a10 += t1.y * w0.x + t2.x * w0.y + t2.y * w1.x;
-                a11 += t1.y * w1.y + t2.x * w2.x + t2.y * w2.y;
+    // Every warp takes three items per round (one per group of nine lanes). The item's <= 32 pair records are fetched by the
+    // group's lanes in one go (record i sits in register i / 9 of lane i % 9) and handed round with shuffles, so the W blocks
+    // of six pairs (18 independent 128-bit loads per lane) are in flight together: one L2 round trip per six block products.
+    const int gbase = (lane / 9) * 9;
+    for (int itb = 0; itb < n_items; itb += (TH / 32) * 3) {
+        const int it = itb + g;
+        const bool valid = act && it < n_items;
+        int4 I = make_int4(0, 0, 0, 0);
+        int cnt = 0;
+        if (valid) {
+            I = sp.items[item0 + it];
+            cnt = sp.items[item0 + it + 1].y - I.y;
+        }
+        uint2 R[NR];
+#pragma unroll
+        for (int q = 0; q < NR; q++) {
+            const int i = gl + 9 * q;
+            R[q] = valid && i < cnt ? sp.pairs[I.y + i] : make_uint2(0u, 0u);
+        }
+        int cmax = cnt;
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, 16));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, 8));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, 4));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, 2));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, 1));
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll
+        for (int b6 = 0; b6 < NR * 9; b6 += 6) {
+            if (b6 >= cmax) break;  // warp-uniform
+            unsigned pp[6], kk[6];
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const int i = b6 + u;  // compile-time: register i / 9, source lane i % 9 of the group
+                const int q = i / 9 < NR ? i / 9 : NR - 1;
+                pp[u] = __shfl_sync(0xffffffffu, R[q].x, gbase + i % 9);
+                kk[u] = __shfl_sync(0xffffffffu, R[q].y, gbase + i % 9);
             }
+            double2 w0[6], w1[6], w2[6];
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const double2* Wp = reinterpret_cast<const double2*>(d.W + (size_t)pp[u] * 18 + cc * 6);
+                if (b6 + u < cnt) { w0[u] = __ldg(Wp); w1[u] = __ldg(Wp + 1); w2[u] = __ldg(Wp + 2); }
+            }
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                if (b6 + u < cnt) {
+                    const double2* Tp = reinterpret_cast<const double2*>(T + (size_t)kk[u] * 18 + rr * 6);
+                    const double2 t0 = Tp[0], t1 = Tp[1], t2 = Tp[2];
+                    // T rows 2rr: (t0.x, t0.y, t1.x), 2rr + 1: (t1.y, t2.x, t2.y); W rows 2cc: (w0.x, w0.y, w1.x), 2cc + 1: (w1.y, w2.x, w2.y)
+                    a00 += t0.x * w0[u].x + t0.y * w0[u].y + t1.x * w1[u].x;
+                    a01 += t0.x * w1[u].y + t0.y * w2[u].x + t1.x * w2[u].y;
+                    a10 += t1.y * w0[u].x + t2.x * w0[u].y + t2.y * w1[u].x;
+                    a11 += t1.y * w1[u].y + t2.x * w2[u].x + t2.y * w2[u].y;
+                }
+            }
+        }
+        if (valid) {
             const int e0 = (2 * rr) * 6 + 2 * cc;  // entries (2rr, 2cc), (2rr, 2cc+1), (2rr+1, 2cc), (2rr+1, 2cc+1)
             if (I.z & kSpMulti) {
                 double* ps = part + (size_t)(I.z >> 16) * 36;
@@ -849,10 +898,11 @@ __global__ void __launch_bounds__(kSpThreads) k_ba_schur_pairs(BaDev d, SchurPai
                 blk[e0 + 7] = (dg ? Hj[e0 + 7] : 0.0) - a11;
             }
         }
+    }
     __syncthreads();
     // ---- phase 3: columns with several items: their slots in item order
     if (act)
-        for (int it = g; it < n_items; it += (kSpThreads / 32) * 3) {
+        for (int it = g; it < n_items; it += (TH / 32) * 3) {
             const int4 I = sp.items[item0 + it];
             if (!(I.z & kSpFirst)) continue;
             const int e0 = (2 * rr) * 6 + 2 * cc;
@@ -1855,7 +1905,7 @@ struct BaHost {
     int n_band = 0;        // free keyframes before the border block (== Pf when there is no border)
     SchurPairs sp = {};      // sorted pair lists of the Schur rows (k_ba_schur_pairs); sp_ok: built and within the kernel's limits
     bool sp_ok = false;
-    int sp_tcap = 0;
+    int sp_tcap = 0, sp_threads = 512;
     size_t sp_smem = 0;
     corb_allreduce_fn ar = nullptr;
     void* ar_user = nullptr;
@@ -1935,22 +1985,33 @@ struct BaHost {
         sp_ok = false;
         const char* env = getenv("CORB_BA_SCHUR");
         if ((env && !strcmp(env, "old")) || d.P <= 0 || d.E <= 0 || pairs_bound == 0 || pairs_bound > ((size_t)1 << 30)) return CORB_OK;
-        const size_t items_bound = pairs_bound / kSpChunk + nblocks + 2 * (size_t)d.P + 16;
+        int th = 512, ch = 32;  // CORB_BA_SP=threads,chunk: A/B switch of the kernel shape
+        if (const char* e2 = getenv("CORB_BA_SP")) sscanf(e2, "%d,%d", &th, &ch);
+        if (th != 256) th = 512;
+        if (ch != 64) ch = 32;
+        sp_threads = th;
+        sp.chunk = ch;
+        const size_t items_bound = pairs_bound / ch + nblocks + 2 * (size_t)d.P + 16;
         int *row_np, *row_bound, *pair_off, *item_off, *item_cnt, *info;
+        int2* row_el;
         uint2* pairs;
         int4* items;
         int rc;
         if ((rc = alloc(&row_np, (size_t)d.P)) != CORB_OK || (rc = alloc(&row_bound, (size_t)d.P)) != CORB_OK ||
             (rc = alloc(&pair_off, (size_t)d.P + 1)) != CORB_OK || (rc = alloc(&item_off, (size_t)d.P + 1)) != CORB_OK ||
             (rc = alloc(&item_cnt, (size_t)d.P)) != CORB_OK || (rc = alloc(&info, 4)) != CORB_OK ||
-            (rc = alloc(&pairs, pairs_bound)) != CORB_OK || (rc = alloc(&items, items_bound)) != CORB_OK)
+            (rc = alloc(&pairs, pairs_bound)) != CORB_OK || (rc = alloc(&items, items_bound)) != CORB_OK ||
+            (rc = alloc(&row_el, (size_t)d.E)) != CORB_OK)
             return rc;
         CORB_CUDA(cudaMemsetAsync(info, 0, 4 * sizeof(int), stream));
-        k_ba_pairs_count<<<d.P, 256, 0, stream>>>(d, row_np, row_bound, info);
+        k_ba_pairs_count<<<d.P, 256, 0, stream>>>(d, row_np, row_bound, info, ch, row_el);
         k_ba_pairs_scan<<<1, 1024, 0, stream>>>(row_np, row_bound, d.P, pair_off, item_off);
-        sp.row_pair_off = pair_off; sp.row_item_off = item_off; sp.row_item_cnt = item_cnt; sp.pairs = pairs; sp.items = items; sp.info = info;
+        sp.row_pair_off = pair_off; sp.row_item_off = item_off; sp.row_item_cnt = item_cnt; sp.pairs = pairs; sp.items = items; sp.info = info; sp.row_el = row_el;
         CORB_SMEM_OPT_IN(k_ba_pairs_build);
-        CORB_SMEM_OPT_IN(k_ba_schur_pairs);
+        CORB_SMEM_OPT_IN((k_ba_schur_pairs<512, 32>));
+        CORB_SMEM_OPT_IN((k_ba_schur_pairs<512, 64>));
+        CORB_SMEM_OPT_IN((k_ba_schur_pairs<256, 32>));
+        CORB_SMEM_OPT_IN((k_ba_schur_pairs<256, 64>));
         k_ba_pairs_build<<<d.P, kSpThreads, (size_t)kSpPairCap * 12, stream>>>(d, sp);
         CORB_CUDA(cudaGetLastError());
         int h_info[4] = {0, 0, 0, 1};
@@ -2033,7 +2094,12 @@ struct BaHost {
         if (d.L > 0) k_ba_dinv<<<(d.L + 255) / 256, 256, 0, stream>>>(d, lambda);
         if (d.P > 0) {
             CORB_CUDA(cudaMemsetAsync(d.S, 0, s_doubles * sizeof(double), stream));  // rows are accumulated into, not zeroed, by the kernel
-            if (sp_ok) k_ba_schur_pairs<<<d.P, kSpThreads, sp_smem, stream>>>(d, sp, sp_tcap);  // one CTA per keyframe, sorted pair lists
+            if (sp_ok) {  // one CTA per keyframe, sorted pair lists
+                if (sp_threads == 512 && sp.chunk == 32) k_ba_schur_pairs<512, 32><<<d.P, 512, sp_smem, stream>>>(d, sp, sp_tcap);
+                else if (sp_threads == 512) k_ba_schur_pairs<512, 64><<<d.P, 512, sp_smem, stream>>>(d, sp, sp_tcap);
+                else if (sp.chunk == 32) k_ba_schur_pairs<256, 32><<<d.P, 256, sp_smem, stream>>>(d, sp, sp_tcap);
+                else k_ba_schur_pairs<256, 64><<<d.P, 256, sp_smem, stream>>>(d, sp, sp_tcap);
+            }
             else k_ba_schur_rows<<<d.P, 256, 0, stream>>>(d);                                    // one CTA per keyframe, edge walk
         }
         int rc = reduce(d.S, s_doubles + (size_t)d.Pf * 6, 0);
