@@ -210,8 +210,8 @@ static int make_plan(corb_orb* h, int w, int hgt) {
         L.ytab_off = ytab;
         if (l > 0) { xtab += L.w; ytab += L.h; }
         L.blur_tile_base = tiles;
-        L.blur_tiles_x = (L.w + 63) / 64;
-        tiles += L.blur_tiles_x * ((L.h + 15) / 16);
+        L.blur_tiles_x = (L.w + kBlurTW - 1) / kBlurTW;
+        tiles += L.blur_tiles_x * ((L.h + kBlurTH - 1) / kBlurTH);
     }
     CORB_CHECK(img_off < (1u << 30) && cand_base < (1 << 24), CORB_ERR_UNSUPPORTED, "image too large");
     g.n_cells = cell_base;

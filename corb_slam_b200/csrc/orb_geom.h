@@ -8,7 +8,8 @@ constexpr int kMaxLevels = 16;
 constexpr int kEdge = 19;        // EDGE_THRESHOLD  (ORBextractor.cc:74)
 constexpr int kBorder = kEdge - 3;  // minBorderX/Y = 16 (:775-776)
 constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE (:73)
-constexpr int kPatch = 31;       // PATCH_SIZE      (:72)
+constexpr int kPatch = 31;
+constexpr int kBlurTW = 64, kBlurTH = 32;  // output tile of the Gaussian blur launch (host tile counts and the kernel agree on it)       // PATCH_SIZE      (:72)
 constexpr int kCellRoiMax = 66;  // wCell + 6 < 60 + 6 (W = 30 => wCell = ceil(width / floor(width/30)) < 60)
 
 struct LevelGeom {

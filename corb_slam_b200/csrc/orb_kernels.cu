@@ -431,8 +431,7 @@ constexpr int kRoiPitch = 96;  // bytes per ROI row in shared memory = TMA box w
                                // because the innermost TMA coordinate must be 16-byte aligned (measured: any other x traps
                                // with 'illegal instruction' on sm_100a), so the box starts at iniX & ~15
 constexpr int kRoiPitchRaw = kRoiPitch;
-constexpr int kBlurTW = 64, kBlurTH = 16;               // blur output tile
-constexpr int kBlurBoxW = 96, kBlurBoxH = kBlurTH + 6;   // its input box: columns x0 - 16 .. x0 + 79 (16-byte aligned start), rows y0 - 3 .. y0 + 18
+constexpr int kBlurBoxW = 96, kBlurBoxH = kBlurTH + 6;   // input box of a blur tile (orb_geom.h): columns x0 - 16 .. x0 + 79 (16-byte aligned start), rows y0 - 3 .. y0 + kBlurTH + 2
 constexpr int kRoiTmaBytes = kRoiPitch * kCellRoiMax;  // one 96 x 66 box per cell
 
 // ---- TMA (cp.async.bulk.tensor) + mbarrier primitives, sm_90+/sm_100a PTX
@@ -840,17 +839,8 @@ __global__ void __launch_bounds__(256, 3) k_fast_cells_g(OrbGeom g, const __grid
                     const int left = vw - 4 * q;  // valid pixels of this quad
                     if (left < 4) m &= (1u << (8 * left)) - 1u;
                 }
-                const int cnt = __popc(m);
-                if (__any_sync(0xffffffffu, cnt)) {
-                    int inc = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int u = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += u;
-                    }
-                    int base = 0;
-                    if (lane == 31) base = atomicAdd(&S.n_surv, inc);
-                    base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+                if (m) {  // the survivor list is a set (scores land by position, NMS sets mask bits): any order will do
+                    int base = atomicAdd(&S.n_surv, __popc(m));
                     while (m) {
                         const int k = (__ffs(m) - 1) >> 3;
                         m &= m - 1;
@@ -919,17 +909,19 @@ __global__ void __launch_bounds__(256, 3) k_fast_cells_g(OrbGeom g, const __grid
     }
     const int base = L.cand_base + S.row_off[65];
     const uint32_t order0 = 0xffffffu - (uint32_t)(c * L.slot);
-    for (int y = wg; y < vh; y += kWpg) {
-        const uint32_t m0 = S.row_ini[y * 2], m1 = S.row_ini[y * 2 + 1];
-        const uint32_t lt = (1u << lane) - 1u;
+    if (tig < vh) {  // a cell keeps a handful of corners: one thread per row walks that row's mask bits (raster order inside the row)
+        const int y = tig;
+        int pos = S.row_off[y];
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            const uint32_t m = half ? m1 : m0;
-            if (m >> lane & 1u) {
-                const int x = lane + 32 * half;
-                const int pos = S.row_off[y] + (half ? __popc(m0) : 0) + __popc(m & lt);
+            uint32_t m = S.row_ini[y * 2 + half];
+            while (m) {
+                const int x = __ffs(m) - 1 + 32 * half;
+                m &= m - 1;
+                // coordinates relative to (minBorderX, minBorderY): FAST's ROI coordinate + j*wCell (:822-823)
                 cand_xy[base + pos] = (uint32_t)(x + 3 + cj * L.w_cell) | (uint32_t)(y + 3 + ci * L.h_cell) << 16;
                 cand_ro[base + pos] = (uint32_t)S.sc[(y + 1) * kScPitch + (x + 1)] << 24 | (order0 - (uint32_t)pos);
+                pos++;
             }
         }
     }
@@ -1028,7 +1020,7 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
     // input box of the tile: [kBlurBoxH][kBlurBoxW], pixel (x0 - 16 + xx, y0 - 3 + yy); one TMA box load (maps != NULL) or
     // 32-bit loads. What lies outside the image arrives as zeros and is rewritten with the REFLECT_101 pixels below.
     __shared__ __align__(128) uint8_t in[kBlurBoxH][kBlurBoxW];
-    __shared__ uint16_t hb[kBlurTH + 6][kBlurTW];
+    __shared__ __align__(16) uint16_t hb[kBlurTH + 6][kBlurTW];
     __shared__ __align__(8) uint64_t bar;
     TL_SCOPE(48);
     const int tid = threadIdx.x;
@@ -1070,36 +1062,41 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
         }
         __syncthreads();
     }
-    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW / 4); i += 256) {  // horizontal pass, 4 outputs per thread from 3 words
+    // horizontal pass, 4 outputs per item from 3 words: output pixel k takes the bytes p[k + 1 .. k + 7] of the 12 loaded ones as two
+    // byte windows (funnel shifts) and two dot products with the taps packed as bytes (DP4A): 18 34 48 56 | 48 34 18 0
+    constexpr uint32_t kTapA = 18u | 34u << 8 | 48u << 16 | 56u << 24, kTapB = 48u | 34u << 8 | 18u << 16;
+    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW / 4); i += 256) {
         const int yy = i / (kBlurTW / 4), xq = i - yy * (kBlurTW / 4);
         const uint32_t* w = reinterpret_cast<const uint32_t*>(&in[yy][12 + 4 * xq]);  // pixels x0 - 4 + 4 xq .. + 11
         const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-        uint8_t p[12];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { p[k] = (w0 >> (8 * k)) & 0xff; p[4 + k] = (w1 >> (8 * k)) & 0xff; p[8 + k] = (w2 >> (8 * k)) & 0xff; }
-        uint32_t o01 = 0, o23 = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {  // output pixel x0 + 4 xq + k takes p[k + 1 .. k + 7]
-            const uint32_t v = 18u * (p[k + 1] + p[k + 7]) + 34u * (p[k + 2] + p[k + 6]) + 48u * (p[k + 3] + p[k + 5]) + 56u * p[k + 4];
-            if (k < 2) o01 |= v << (16 * k); else o23 |= v << (16 * (k - 2));
-        }
-        uint32_t* o = reinterpret_cast<uint32_t*>(&hb[yy][4 * xq]);
-        o[0] = o01;
-        o[1] = o23;
+        const uint32_t v0 = __dp4a(__funnelshift_r(w1, w2, 8), kTapB, __dp4a(__funnelshift_r(w0, w1, 8), kTapA, 0u));
+        const uint32_t v1 = __dp4a(__funnelshift_r(w1, w2, 16), kTapB, __dp4a(__funnelshift_r(w0, w1, 16), kTapA, 0u));
+        const uint32_t v2 = __dp4a(__funnelshift_r(w1, w2, 24), kTapB, __dp4a(__funnelshift_r(w0, w1, 24), kTapA, 0u));
+        const uint32_t v3 = __dp4a(w2, kTapB, __dp4a(w1, kTapA, 0u));
+        *reinterpret_cast<uint2*>(&hb[yy][4 * xq]) = make_uint2(v0 | v1 << 16, v2 | v3 << 16);
     }
     __syncthreads();
-    const int lx = (tid & 15) * 4, ly = tid >> 4;
-    const int gx = x0 + lx, gy = y0 + ly;
-    if (gy < L.h && gx < L.w) {
-        uint32_t packed = 0;
+    // vertical pass: a thread owns 2 columns x 4 rows; the 10 rows it needs slide through registers (one 32-bit load per row)
+    const int lx = (tid & 31) * 2, ly = (tid >> 5) * 4;
+    const int gx = x0 + lx;
+    if (gx < L.w) {
+        uint32_t lo[10], hi[10];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int x = lx + k;
-            const uint32_t acc = 18u * ((uint32_t)hb[ly][x] + hb[ly + 6][x]) + 34u * ((uint32_t)hb[ly + 1][x] + hb[ly + 5][x]) +
-                                 48u * ((uint32_t)hb[ly + 2][x] + hb[ly + 4][x]) + 56u * (uint32_t)hb[ly + 3][x];
-            packed |= ((acc + 32768u) >> 16) << (8 * k);
+        for (int r = 0; r < 10; r++) {
+            const uint32_t h2 = *reinterpret_cast<const uint32_t*>(&hb[ly + r][lx]);
+            lo[r] = h2 & 0xffffu;
+            hi[r] = h2 >> 16;
         }
-        *reinterpret_cast<uint32_t*>(blur + L.img_off + (size_t)gy * L.pitch + gx) = packed;
+        uint8_t* out = blur + L.img_off + (size_t)(y0 + ly) * L.pitch + gx;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (y0 + ly + r < L.h) {
+                const uint32_t a = 18u * (lo[r] + lo[r + 6]) + 34u * (lo[r + 1] + lo[r + 5]) + 48u * (lo[r + 2] + lo[r + 4]) + 56u * lo[r + 3];
+                const uint32_t c = 18u * (hi[r] + hi[r + 6]) + 34u * (hi[r + 1] + hi[r + 5]) + 48u * (hi[r + 2] + hi[r + 4]) + 56u * hi[r + 3];
+                // the pitch is a multiple of 128 and gx is even: a 16-bit store; pixel L.w (odd widths) falls into the row padding
+                *reinterpret_cast<uint16_t*>(out + (size_t)r * L.pitch) = (uint16_t)(((a + 32768u) >> 16) | (((c + 32768u) >> 16) << 8));
+            }
+        }
     }
 }
 
