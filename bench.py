@@ -742,7 +742,9 @@ def run_ours(args):
                              "max_abs_pose_q": float(np.abs(ba_out["pose_q"] - full["pose_q"]).max()),
                              "max_abs_point": float(np.abs(pts.cpu().numpy() - full["point_xyz"]).max()),
                              "rank_spread": float((pmax - pmin).abs().max()),
-                             "chi2_final_single": finfo["chi2_final"], "ms_single_gpu_same_run": single_ms}
+                             "chi2_final_single": finfo["chi2_final"], "ms_single_gpu_same_run": single_ms,
+                             "speedup_vs_single_gpu_same_run": single_ms / ba_ms,
+                             "strong_scaling_efficiency": single_ms / ba_ms / world}
             barrier()
             # the server's own shape of the same thing: ONE process, N threads, N ncclComm_t, ncclAllReduce hook in C
             # (tests/host_harness/ba_nccl.cpp = what corbslam_server's GBA thread would call); the other ranks wait on the

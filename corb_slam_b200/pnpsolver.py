@@ -84,7 +84,15 @@ class PnPsolver:
         self.mvMaxError = np.ascontiguousarray(self.mvSigma2 * np.float32(th2), np.float32)
 
     def _need_draws(self, it_end):
-        """RandomInt(0, vAvailableIndices.size()-1) for the four picks of every iteration up to it_end (:231-233)."""
+        """RandomInt(0, vAvailableIndices.size()-1) for the four picks of every iteration up to it_end (:231-233).
+
+        Deviation from the reference, by design: the draws for ALL iterations up to it_end are taken from the process-global
+        rand() stream up front (the batched kernel evaluates every hypothesis), while the reference consumes four per EXECUTED
+        iteration and stops drawing at an early Refine() return. A single solver that runs to the end sees the reference's
+        draws; with several candidate solvers in one process (Tracking.cc:1432, MapFusion.cpp:720) the solvers after the first
+        start at a later stream position than they would in the reference process. The result is still a valid RANSAC over
+        the same distribution; bit parity with the reference holds for given draws (set_draws, and the tests that replay the
+        reference's own rand() stream through one solver)."""
         have = len(self._draws)
         if it_end > have:
             new = np.empty((it_end - have, 4), np.int32)

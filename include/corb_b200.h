@@ -298,7 +298,10 @@ CORB_API int corb_pnp_ransac_params(int N, double probability, int min_inliers, 
  * of RANSAC iteration `it` (0-based over the life of the solver object), i.e. 0 <= draws[4 * it + k] < n - k. The shim
  * draws them with the same RandomInt calls, for iterations [0, it_end), it_end = max(max_its, iterations_done +
  * n_iterations) - the loop condition of iterate() (:223). The call is stateless: iterations [0, iterations_done) are
- * recomputed (the best-so-far state of the reference object is a function of them). */
+ * recomputed (the best-so-far state of the reference object is a function of them).
+ * Deviation: drawing for all iterations up front consumes more of the process-global rand() stream than the reference, which
+ * draws four values per EXECUTED iteration and stops at an early Refine() return; a second solver in the same process
+ * therefore starts at a later stream position than it would in the reference process (same distribution, different draws). */
 typedef struct {
     int32_t n;               /* N = mvP2D.size() */
     const float* p2d;        /* [n][2] mvP2D: undistorted keypoint positions */
