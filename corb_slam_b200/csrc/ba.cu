@@ -559,7 +559,7 @@ struct SchurPairs {
     int chunk;                 // pairs per item at most (a power of two: 32 or 64)
     int2* row_el;              // [E] in pose-CSR order: x = edge position e, y = landmark l (-1: fixed landmark) - the row's index chain, resolved once
 };
-constexpr int kSpThreads = 512, kSpPairCap = 8192, kSpChunkMax = 64;
+constexpr int kSpThreads = 512, kSpPairCap = 8192;
 constexpr int kSpMulti = 1 << 6, kSpFirst = 1 << 7, kSpLast = 1 << 8;
 
 // exclusive scan of one int per thread over a 512-thread block (thread order); *total = block sum

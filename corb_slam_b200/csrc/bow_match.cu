@@ -48,6 +48,7 @@ struct BowCall {  // everything is a device pointer
 };
 
 constexpr int kThLow = 50, kHistoLength = 30;  // ORBmatcher.cc:37-39
+constexpr int kNodeRegs = 4;                   // B features of a vocabulary node a lane keeps in registers (nodes up to 128 features)
 
 __global__ void __launch_bounds__(256) k_bow_init(const BowCall* __restrict__ calls) {
     const BowCall c = calls[blockIdx.y];
@@ -79,6 +80,80 @@ __global__ void __launch_bounds__(128) k_bow_match(const BowCall* __restrict__ c
         if (lo < c.nnB && c.nodesB[lo] == node) {
             const int b_beg = c.offB[lo], nbg = c.offB[lo + 1] - b_beg;
             const float factor = 1.0f / kHistoLength;
+            if (nbg <= 32 * kNodeRegs) {
+                // The node's B features live in registers (feature j = lane + 32 s in slot s of its lane): descriptor, index and
+                // an "available" bit that replaces the matchedB bytes - a B feature belongs to exactly one node, so only this warp
+                // ever looks at it. Per A feature that leaves one descriptor load (fetched one feature ahead) and the reduction.
+                uint4 q0[kNodeRegs], q1[kNodeRegs];
+                int bb[kNodeRegs];
+                bool ok[kNodeRegs];
+#pragma unroll
+                for (int s = 0; s < kNodeRegs; s++) {
+                    const int j = lane + 32 * s;
+                    ok[s] = false; bb[s] = -1;
+                    q0[s] = q1[s] = make_uint4(0u, 0u, 0u, 0u);
+                    if (j < nbg) {
+                        const int b = (int)c.idxB[b_beg + j];
+                        bb[s] = b;
+                        ok[s] = !(kfkf && c.validB && !c.validB[b]);
+                        q0[s] = c.descB[2 * b];
+                        q1[s] = c.descB[2 * b + 1];
+                    }
+                }
+                const int i_beg = c.offA[ga], i_end = c.offA[ga + 1];
+                int a_n = i_beg < i_end ? (int)c.idxA[i_beg] : 0;
+                bool va_n = i_beg < i_end && !(c.validA && !c.validA[a_n]);
+                uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+                if (va_n) { n0 = c.descA[2 * a_n]; n1 = c.descA[2 * a_n + 1]; }
+                for (int i1 = i_beg; i1 < i_end; i1++) {
+                    const int a = a_n;
+                    const bool va = va_n;
+                    const uint4 a0 = n0, a1 = n1;
+                    if (i1 + 1 < i_end) {  // the next A feature's descriptor is on its way while this one is matched
+                        a_n = (int)c.idxA[i1 + 1];
+                        va_n = !(c.validA && !c.validA[a_n]);
+                        if (va_n) { n0 = c.descA[2 * a_n]; n1 = c.descA[2 * a_n + 1]; }
+                    }
+                    if (!va) continue;
+                    int b1 = 256, p1 = INT_MAX, b2 = 256, bi = -1;
+#pragma unroll
+                    for (int s = 0; s < kNodeRegs; s++) {  // ascending j per lane, like the scan over the node's list
+                        if (ok[s]) {
+                            const int d = __popc(a0.x ^ q0[s].x) + __popc(a0.y ^ q0[s].y) + __popc(a0.z ^ q0[s].z) + __popc(a0.w ^ q0[s].w) +
+                                          __popc(a1.x ^ q1[s].x) + __popc(a1.y ^ q1[s].y) + __popc(a1.z ^ q1[s].z) + __popc(a1.w ^ q1[s].w);
+                            if (d < b1) { b2 = b1; b1 = d; p1 = lane + 32 * s; bi = bb[s]; }
+                            else if (d < b2) b2 = d;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        const int ob1 = __shfl_xor_sync(0xffffffffu, b1, o), op1 = __shfl_xor_sync(0xffffffffu, p1, o);
+                        const int ob2 = __shfl_xor_sync(0xffffffffu, b2, o), obi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        const bool other = ob1 < b1 || (ob1 == b1 && op1 < p1);
+                        const int loser = other ? b1 : ob1;
+                        if (other) { b1 = ob1; p1 = op1; bi = obi; }
+                        b2 = min(min(b2, ob2), loser);
+                    }
+                    const bool near = kfkf ? b1 < kThLow : b1 <= kThLow;  // :231 / :733
+                    if (near && (float)b1 < __fmul_rn(nnratio, (float)b2)) {
+#pragma unroll
+                        for (int s = 0; s < kNodeRegs; s++)
+                            if (p1 == lane + 32 * s) ok[s] = false;
+                        if (lane == 0) {
+                            const int slot = kfkf ? a : bi;
+                            c.match[slot] = kfkf ? bi : a;
+                            if (check_ori) {
+                                float rot = __fsub_rn(c.angA[a], c.angB[bi]);
+                                if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                                int bin = (int)roundf(__fmul_rn(rot, factor));
+                                if (bin == kHistoLength) bin = 0;
+                                c.bin[slot] = (uint8_t)bin;
+                                if (bin >= 0 && bin < kHistoLength) atomicAdd(&c.hist[bin], 1);
+                            }
+                        }
+                    }
+                }
+            } else
             for (int i1 = c.offA[ga]; i1 < c.offA[ga + 1]; i1++) {
                 const int a = (int)c.idxA[i1];
                 if (c.validA && !c.validA[a]) continue;
@@ -205,41 +280,73 @@ __global__ void __launch_bounds__(256) k_voc_transform(VocDev v, const uint4* __
     }
 }
 
-// One warp per candidate BowVector. Terms fabs(vi-wi)-fabs(vi)-fabs(wi) are formed in parallel (binary search of the
-// candidate's word in the query) and accumulated strictly in ascending common-word order, like the merge walk.
-__global__ void __launch_bounds__(256) k_bow_score(const uint32_t* __restrict__ qw, const double* __restrict__ qv, int nq,
-                                                   const uint32_t* __restrict__ cw, const double* __restrict__ cv,
-                                                   const int* __restrict__ coff, int ncand, double* __restrict__ scores) {
-    const int cand = (blockIdx.x * 256 + threadIdx.x) >> 5;
-    if (cand >= ncand) return;
-    const int lane = threadIdx.x & 31;
-    const int beg = coff[cand], end = coff[cand + 1];
-    double score = 0.0;
-    for (int base = beg; base < end; base += 32) {
-        const int i = base + lane;
+// One CTA (128 threads) per candidate BowVector. The terms fabs(vi-wi)-fabs(vi)-fabs(wi) of the common words are formed in
+// parallel (binary search of the candidate's word in the query) and compacted, in ascending word order, into shared memory;
+// one thread then adds them strictly in that order, like the merge walk of L1Scoring::score - the chain of dependent fp64
+// additions is the whole cost (a warp-wide shuffle per term made it six times longer).
+constexpr int kScoreThreads = 128, kScoreCap = 4096;
+__device__ __forceinline__ void bow_score_one(const uint32_t* __restrict__ qw, const double* __restrict__ qv, int nq,
+                                              const uint32_t* __restrict__ w_, const double* __restrict__ v_, int n, double* out) {
+    __shared__ double terms[kScoreCap];
+    __shared__ int wcnt[kScoreThreads / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    double carry = 0.0;  // thread 0: sum of the terms flushed so far (only when a vector has more than kScoreCap common words)
+    for (int base = 0; base < n; base += kScoreThreads) {
+        const int i = base + tid;
         double term = 0.0;
         bool has = false;
-        if (i < end) {
-            const uint32_t w = cw[i];
+        if (i < n) {
+            const uint32_t w = w_[i];
             int lo = 0, hi = nq;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if (qw[mid] < w) lo = mid + 1; else hi = mid;
             }
             if (lo < nq && qw[lo] == w) {
-                const double vi = qv[lo], wi = cv[i];
+                const double vi = qv[lo], wi = v_[i];
                 term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
                 has = true;
             }
         }
-        unsigned m = __ballot_sync(0xffffffffu, has);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            score = __dadd_rn(score, __shfl_sync(0xffffffffu, term, src));
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) wcnt[warp] = __popc(m);
+        __syncthreads();
+        int pos = s_base + __popc(m & ((1u << lane) - 1u));
+        for (int w2 = 0; w2 < warp; w2++) pos += wcnt[w2];
+        int total = 0;
+        for (int w2 = 0; w2 < kScoreThreads / 32; w2++) total += wcnt[w2];
+        if (s_base + total > kScoreCap) {  // flush (never on ORB frames: a BowVector has at most as many words as features)
+            __syncthreads();
+            if (tid == 0) {
+                for (int k = 0; k < s_base; k++) carry = __dadd_rn(carry, terms[k]);
+                s_base = 0;
+            }
+            __syncthreads();
+            pos = __popc(m & ((1u << lane) - 1u));
+            for (int w2 = 0; w2 < warp; w2++) pos += wcnt[w2];
         }
+        if (has) terms[pos] = term;
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
     }
-    if (lane == 0) scores[cand] = -score / 2.0;
+    if (tid == 0) {
+        double score = carry;
+        const int cnt = s_base;
+        for (int k = 0; k < cnt; k++) score = __dadd_rn(score, terms[k]);
+        *out = -score / 2.0;
+    }
+}
+
+__global__ void __launch_bounds__(kScoreThreads) k_bow_score(const uint32_t* __restrict__ qw, const double* __restrict__ qv, int nq,
+                                                             const uint32_t* __restrict__ cw, const double* __restrict__ cv,
+                                                             const int* __restrict__ coff, int ncand, double* __restrict__ scores) {
+    const int cand = blockIdx.x;
+    const int beg = coff[cand], end = coff[cand + 1];
+    bow_score_one(qw, qv, nq, cw + beg, cv + beg, end - beg, scores + cand);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -775,7 +882,7 @@ int corb_bow_score_batch(corb_voc* v, const uint32_t* q_words, const double* q_v
     }
     offs[ncand] = (int)run;
     CORB_CUDA(cudaMemcpyAsync(d, h, oS, cudaMemcpyHostToDevice, v->stream));
-    k_bow_score<<<(ncand * 32 + 255) / 256, 256, 0, v->stream>>>((const uint32_t*)(d + oQW), (const double*)(d + oQV), nq,
+    k_bow_score<<<ncand, kScoreThreads, 0, v->stream>>>((const uint32_t*)(d + oQW), (const double*)(d + oQV), nq,
                                                                  (const uint32_t*)(d + oCW), (const double*)(d + oCV),
                                                                  (const int*)(d + oOff), ncand, (double*)(d + oS));
     CORB_CUDA(cudaGetLastError());
@@ -840,11 +947,12 @@ __global__ void __launch_bounds__(1024) k_bow_build(BowStoreDev st, int n) {
     while (N < n) N <<= 1;
     double* vals = reinterpret_cast<double*>(keys + N);
     int* flag = reinterpret_cast<int*>(vals + N);
-    __shared__ int s_total[2];
+    __shared__ int s_total[1];
     __shared__ double s_norm;
     const int tid = threadIdx.x, nt = blockDim.x;
     const unsigned long long kNone = ~0ull;
-    for (int pass = 0; pass < 2; pass++) {  // 0: BowVector from (word, feature); 1: FeatureVector from (node, feature)
+    {   // CTA 0: BowVector from (word, feature); CTA 1: FeatureVector from (node, feature) - independent, side by side
+        const int pass = blockIdx.x;
         for (int i = tid; i < N; i += nt)
             keys[i] = (i < n && st.weight[i] > 0.0) ? ((unsigned long long)(pass ? st.node[i] : st.word[i]) << 32 | (unsigned)i) : kNone;
         __syncthreads();
@@ -884,7 +992,7 @@ __global__ void __launch_bounds__(1024) k_bow_build(BowStoreDev st, int n) {
                 flag[i] = f ? run : -1;  // index of the run this head starts, -1 for non-heads
                 run += f;
             }
-            if (tid == nt - 1) s_total[pass] = run;
+            if (tid == nt - 1) s_total[0] = run;
             __syncthreads();
         }
         if (pass == 0) {
@@ -899,6 +1007,7 @@ __global__ void __launch_bounds__(1024) k_bow_build(BowStoreDev st, int n) {
             }
             __syncthreads();
             const int nb = s_total[0];
+            if (tid == 0) st.counts[0] = nb;
             if (tid == 0) {  // BowVector::normalize(L1): norm += fabs(value) in ascending word order
                 double norm = 0.0;
                 for (int u = 0; u < nb; u++) norm += fabs(vals[u]);
@@ -921,49 +1030,19 @@ __global__ void __launch_bounds__(1024) k_bow_build(BowStoreDev st, int n) {
                 int lo = 0, hi = N;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] != kNone) lo = mid + 1; else hi = mid; }
                 cnt = lo;
-                st.fv_off[s_total[1]] = cnt;
-                st.counts[0] = s_total[0]; st.counts[1] = s_total[1]; st.counts[2] = cnt; st.counts[3] = n;
+                st.fv_off[s_total[0]] = cnt;
+                st.counts[1] = s_total[0]; st.counts[2] = cnt; st.counts[3] = n;
             }
         }
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256) k_bow_score_ptr(const uint32_t* __restrict__ qw, const double* __restrict__ qv, int nq,
-                                                       const uint32_t* const* __restrict__ cw, const double* const* __restrict__ cv,
-                                                       const int* __restrict__ cn, int ncand, double* __restrict__ scores) {
-    const int cand = (blockIdx.x * 256 + threadIdx.x) >> 5;
-    if (cand >= ncand) return;
-    const int lane = threadIdx.x & 31;
-    const uint32_t* w_ = cw[cand];
-    const double* v_ = cv[cand];
-    const int end = cn[cand];
-    double score = 0.0;
-    for (int base = 0; base < end; base += 32) {
-        const int i = base + lane;
-        double term = 0.0;
-        bool has = false;
-        if (i < end) {
-            const uint32_t w = w_[i];
-            int lo = 0, hi = nq;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (qw[mid] < w) lo = mid + 1; else hi = mid;
-            }
-            if (lo < nq && qw[lo] == w) {
-                const double vi = qv[lo], wi = v_[i];
-                term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
-                has = true;
-            }
-        }
-        unsigned m = __ballot_sync(0xffffffffu, has);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            score = __dadd_rn(score, __shfl_sync(0xffffffffu, term, src));
-        }
-    }
-    if (lane == 0) scores[cand] = -score / 2.0;
+__global__ void __launch_bounds__(kScoreThreads) k_bow_score_ptr(const uint32_t* __restrict__ qw, const double* __restrict__ qv, int nq,
+                                                                 const uint32_t* const* __restrict__ cw, const double* const* __restrict__ cv,
+                                                                 const int* __restrict__ cn, int ncand, double* __restrict__ scores) {
+    const int cand = blockIdx.x;
+    bow_score_one(qw, qv, nq, cw[cand], cv[cand], cn[cand], scores + cand);
 }
 
 }  // namespace corb
@@ -1038,7 +1117,7 @@ int corb_bow_store_fill(corb_bow_store* s, corb_voc* v, const corb_keypoint* d_k
         CORB_CUDA(cudaFuncSetAttribute(k_bow_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kBowCap * 16 + (kBowCap + 1) * 4));
         opt.fetch_or(1ull << (s->device & 63));
     }
-    k_bow_build<<<1, 1024, smem, st>>>(s->dev, n);
+    k_bow_build<<<2, 1024, smem, st>>>(s->dev, n);
     CORB_CUDA(cudaGetLastError());
     CORB_CUDA(cudaMemcpyAsync(s->h_counts, s->dev.counts, 16, cudaMemcpyDeviceToHost, st));
     CORB_CUDA(cudaStreamSynchronize(st));
@@ -1084,7 +1163,7 @@ int corb_bow_score_stores(corb_voc* v, const corb_bow_store* query, int ncand, c
         ((int*)(h + oN))[i] = cands[i]->n_bow;
     }
     CORB_CUDA(cudaMemcpyAsync(d, h, oS, cudaMemcpyHostToDevice, v->stream));
-    k_bow_score_ptr<<<(ncand * 32 + 255) / 256, 256, 0, v->stream>>>(query->dev.bow_words, query->dev.bow_vals, query->n_bow,
+    k_bow_score_ptr<<<ncand, kScoreThreads, 0, v->stream>>>(query->dev.bow_words, query->dev.bow_vals, query->n_bow,
                                                                      (const uint32_t* const*)(d + oW), (const double* const*)(d + oV),
                                                                      (const int*)(d + oN), ncand, (double*)(d + oS));
     CORB_CUDA(cudaGetLastError());
