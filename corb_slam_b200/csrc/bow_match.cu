@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(128) k_bow_match(const BowCall* __restrict__ c
     __shared__ int s_keep[3];
     __shared__ int s_cnt[4];
     __shared__ int s_last;
+    __shared__ uint4 s_ad[4][32][2];  // per warp: descriptors of the next 32 A features of its node
+    __shared__ int s_ai[4][32];       //           their indices (-1: not a live MapPoint)
     const BowCall c = calls[blockIdx.y];
     const bool kfkf = variant == 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -101,20 +103,23 @@ __global__ void __launch_bounds__(128) k_bow_match(const BowCall* __restrict__ c
                     }
                 }
                 const int i_beg = c.offA[ga], i_end = c.offA[ga + 1];
-                int a_n = i_beg < i_end ? (int)c.idxA[i_beg] : 0;
-                bool va_n = i_beg < i_end && !(c.validA && !c.validA[a_n]);
-                uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
-                if (va_n) { n0 = c.descA[2 * a_n]; n1 = c.descA[2 * a_n + 1]; }
                 for (int i1 = i_beg; i1 < i_end; i1++) {
-                    const int a = a_n;
-                    const bool va = va_n;
-                    const uint4 a0 = n0, a1 = n1;
-                    if (i1 + 1 < i_end) {  // the next A feature's descriptor is on its way while this one is matched
-                        a_n = (int)c.idxA[i1 + 1];
-                        va_n = !(c.validA && !c.validA[a_n]);
-                        if (va_n) { n0 = c.descA[2 * a_n]; n1 = c.descA[2 * a_n + 1]; }
+                    const int t = (i1 - i_beg) & 31;
+                    if (t == 0) {  // the next 32 A features of the node: every lane fetches one into the warp's shared-memory stage
+                        __syncwarp();
+                        const int ii = i1 + lane;
+                        int ax = -1;
+                        if (ii < i_end) {
+                            ax = (int)c.idxA[ii];
+                            if (c.validA && !c.validA[ax]) ax = -1;
+                        }
+                        s_ai[warp][lane] = ax;
+                        if (ax >= 0) { s_ad[warp][lane][0] = c.descA[2 * ax]; s_ad[warp][lane][1] = c.descA[2 * ax + 1]; }
+                        __syncwarp();
                     }
-                    if (!va) continue;
+                    const int a = s_ai[warp][t];
+                    if (a < 0) continue;
+                    const uint4 a0 = s_ad[warp][t][0], a1 = s_ad[warp][t][1];
                     int b1 = 256, p1 = INT_MAX, b2 = 256, bi = -1;
 #pragma unroll
                     for (int s = 0; s < kNodeRegs; s++) {  // ascending j per lane, like the scan over the node's list
@@ -280,65 +285,56 @@ __global__ void __launch_bounds__(256) k_voc_transform(VocDev v, const uint4* __
     }
 }
 
-// One CTA (128 threads) per candidate BowVector. The terms fabs(vi-wi)-fabs(vi)-fabs(wi) of the common words are formed in
-// parallel (binary search of the candidate's word in the query) and compacted, in ascending word order, into shared memory;
-// one thread then adds them strictly in that order, like the merge walk of L1Scoring::score - the chain of dependent fp64
-// additions is the whole cost (a warp-wide shuffle per term made it six times longer).
+// One CTA (128 threads) per candidate BowVector. Both vectors are sorted by word, so a thread takes a contiguous run of the
+// candidate's words, finds its start in the query with one binary search and walks both lists like the merge of
+// L1Scoring::score; the term fabs(vi-wi)-fabs(vi)-fabs(wi) of a common word (strictly negative: the weights are positive)
+// goes to the word's slot in shared memory, 0 elsewhere. One thread then adds the non-zero slots strictly in ascending word
+// order - the reference's summation order, so the fp64 bits are DBoW2's.
 constexpr int kScoreThreads = 128, kScoreCap = 4096;
 __device__ __forceinline__ void bow_score_one(const uint32_t* __restrict__ qw, const double* __restrict__ qv, int nq,
                                               const uint32_t* __restrict__ w_, const double* __restrict__ v_, int n, double* out) {
     __shared__ double terms[kScoreCap];
-    __shared__ int wcnt[kScoreThreads / 32];
-    __shared__ int s_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    double carry = 0.0;  // thread 0: sum of the terms flushed so far (only when a vector has more than kScoreCap common words)
-    for (int base = 0; base < n; base += kScoreThreads) {
-        const int i = base + tid;
-        double term = 0.0;
-        bool has = false;
-        if (i < n) {
-            const uint32_t w = w_[i];
+    const int tid = threadIdx.x;
+    double score = 0.0;
+    for (int base = 0; base < n; base += kScoreCap) {  // one round unless a vector has more than kScoreCap words
+        const int m = min(kScoreCap, n - base);
+        const int per = (m + kScoreThreads - 1) / kScoreThreads;
+        const int i0 = base + tid * per, i1 = min(base + m, i0 + per);
+        if (i0 < i1) {
+            const uint32_t wf = w_[i0];
             int lo = 0, hi = nq;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (qw[mid] < w) lo = mid + 1; else hi = mid;
+                if (qw[mid] < wf) lo = mid + 1; else hi = mid;
             }
-            if (lo < nq && qw[lo] == w) {
-                const double vi = qv[lo], wi = v_[i];
-                term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
-                has = true;
+            for (int i = i0; i < i1; i++) {
+                const uint32_t w = w_[i];
+                while (lo < nq && qw[lo] < w) lo++;
+                double term = 0.0;
+                if (lo < nq && qw[lo] == w) {
+                    const double vi = qv[lo], wi = v_[i];
+                    term = __dsub_rn(__dsub_rn(fabs(__dsub_rn(vi, wi)), fabs(vi)), fabs(wi));
+                }
+                terms[i - base] = term;
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, has);
-        if (lane == 0) wcnt[warp] = __popc(m);
         __syncthreads();
-        int pos = s_base + __popc(m & ((1u << lane) - 1u));
-        for (int w2 = 0; w2 < warp; w2++) pos += wcnt[w2];
-        int total = 0;
-        for (int w2 = 0; w2 < kScoreThreads / 32; w2++) total += wcnt[w2];
-        if (s_base + total > kScoreCap) {  // flush (never on ORB frames: a BowVector has at most as many words as features)
-            __syncthreads();
-            if (tid == 0) {
-                for (int k = 0; k < s_base; k++) carry = __dadd_rn(carry, terms[k]);
-                s_base = 0;
+        if (tid == 0) {
+            int k = 0;
+            for (; k + 8 <= m; k += 8) {  // loads first: only the additions of common words sit on the dependent chain
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) t[u] = terms[k + u];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (t[u] != 0.0) score = __dadd_rn(score, t[u]);
             }
-            __syncthreads();
-            pos = __popc(m & ((1u << lane) - 1u));
-            for (int w2 = 0; w2 < warp; w2++) pos += wcnt[w2];
+            for (; k < m; k++)
+                if (terms[k] != 0.0) score = __dadd_rn(score, terms[k]);
         }
-        if (has) terms[pos] = term;
-        __syncthreads();
-        if (tid == 0) s_base += total;
         __syncthreads();
     }
-    if (tid == 0) {
-        double score = carry;
-        const int cnt = s_base;
-        for (int k = 0; k < cnt; k++) score = __dadd_rn(score, terms[k]);
-        *out = -score / 2.0;
-    }
+    if (tid == 0) *out = -score / 2.0;
 }
 
 __global__ void __launch_bounds__(kScoreThreads) k_bow_score(const uint32_t* __restrict__ qw, const double* __restrict__ qv, int nq,
