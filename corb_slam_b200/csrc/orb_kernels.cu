@@ -1052,10 +1052,23 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
     // tiles on the image border: the frame of 3 pixels outside the image is the reflection of pixels inside this box
     const bool edge = x0 < 3 || y0 < 3 || x0 + kBlurTW + 3 > L.w || y0 + kBlurTH + 3 > L.h;
     if (edge) {
-        for (int i = tid; i < kBlurBoxH * (kBlurTW + 6); i += 256) {
-            const int yy = i / (kBlurTW + 6), xx = 13 + (i - yy * (kBlurTW + 6));
-            const int gy = y0 - 3 + yy, gx = x0 - 16 + xx;
-            if ((gy < 0 || gy >= L.h || gx < 0 || gx >= L.w) && gy >= -3 && gy <= L.h + 2 && gx >= -3 && gx <= L.w + 2) {
+        // only the frame itself is visited: the (at most) three columns left and right of the image and the three rows above and
+        // below it, as far as they fall into this box (corners are written by both strips with the same value)
+        constexpr int kColItems = 6 * kBlurBoxH, kRowItems = 6 * (kBlurTW + 6);
+        for (int i = tid; i < kColItems + kRowItems; i += 256) {
+            int gx, gy;
+            if (i < kColItems) {
+                const int c = i / kBlurBoxH;
+                gy = y0 - 3 + (i - c * kBlurBoxH);
+                gx = c < 3 ? c - 3 : L.w + c - 3;
+            } else {
+                const int k = i - kColItems, r = k / (kBlurTW + 6);
+                gx = x0 - 3 + (k - r * (kBlurTW + 6));
+                gy = r < 3 ? r - 3 : L.h + r - 3;
+            }
+            const int yy = gy - (y0 - 3), xx = gx - (x0 - 16);
+            if (yy >= 0 && yy < kBlurBoxH && xx >= 13 && xx < 13 + kBlurTW + 6 && gy >= -3 && gy <= L.h + 2 && gx >= -3 && gx <= L.w + 2 &&
+                (gy < 0 || gy >= L.h || gx < 0 || gx >= L.w)) {
                 const int sy = reflect101(gy, L.h) - (y0 - 3), sx = reflect101(gx, L.w) - (x0 - 16);
                 in[yy][xx] = in[sy][sx];  // sources are inside the image, destinations outside: no overlap
             }
