@@ -1013,7 +1013,8 @@ __device__ __forceinline__ int reflect101(int p, int n) {
     return p;
 }
 
-__global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
+constexpr int kBlurThreads = 128;  // 64 x 32 outputs per CTA: 16 per thread, so the per-thread prologue is paid once per 16 pixels
+__global__ void __launch_bounds__(kBlurThreads) k_blur(OrbGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur,
                                               const uint8_t* __restrict__ pyr1, uint8_t* __restrict__ blur1,
                                               const CUtensorMap* __restrict__ maps, const CUtensorMap* __restrict__ maps1) {
     if (blockIdx.z) { pyr = pyr1; blur = blur1; maps = maps1; }
@@ -1040,7 +1041,7 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
         mbar_wait(&bar, 0);
     } else {
         const uint8_t* src = pyr + L.img_off;
-        for (int i = tid; i < kBlurBoxH * (kBlurBoxW / 4); i += 256) {
+        for (int i = tid; i < kBlurBoxH * (kBlurBoxW / 4); i += kBlurThreads) {
             const int yy = i / (kBlurBoxW / 4), xw = i - yy * (kBlurBoxW / 4);
             const int gy = y0 - 3 + yy, gx = x0 - 16 + 4 * xw;
             uint32_t v = 0;
@@ -1055,7 +1056,7 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
         // only the frame itself is visited: the (at most) three columns left and right of the image and the three rows above and
         // below it, as far as they fall into this box (corners are written by both strips with the same value)
         constexpr int kColItems = 6 * kBlurBoxH, kRowItems = 6 * (kBlurTW + 6);
-        for (int i = tid; i < kColItems + kRowItems; i += 256) {
+        for (int i = tid; i < kColItems + kRowItems; i += kBlurThreads) {
             int gx, gy;
             if (i < kColItems) {
                 const int c = i / kBlurBoxH;
@@ -1078,7 +1079,7 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
     // horizontal pass, 4 outputs per item from 3 words: output pixel k takes the bytes p[k + 1 .. k + 7] of the 12 loaded ones as two
     // byte windows (funnel shifts) and two dot products with the taps packed as bytes (DP4A): 18 34 48 56 | 48 34 18 0
     constexpr uint32_t kTapA = 18u | 34u << 8 | 48u << 16 | 56u << 24, kTapB = 48u | 34u << 8 | 18u << 16;
-    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW / 4); i += 256) {
+    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW / 4); i += kBlurThreads) {
         const int yy = i / (kBlurTW / 4), xq = i - yy * (kBlurTW / 4);
         const uint32_t* w = reinterpret_cast<const uint32_t*>(&in[yy][12 + 4 * xq]);  // pixels x0 - 4 + 4 xq .. + 11
         const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
@@ -1089,26 +1090,28 @@ __global__ void __launch_bounds__(256) k_blur(OrbGeom g, const uint8_t* __restri
         *reinterpret_cast<uint2*>(&hb[yy][4 * xq]) = make_uint2(v0 | v1 << 16, v2 | v3 << 16);
     }
     __syncthreads();
-    // vertical pass: a thread owns 2 columns x 4 rows; the 10 rows it needs slide through registers (one 32-bit load per row)
-    const int lx = (tid & 31) * 2, ly = (tid >> 5) * 4;
+    // vertical pass: a thread owns 2 columns x 8 rows; the 14 rows it needs slide through registers (one 32-bit load per row)
+    const int lx = (tid & 31) * 2, ly = (tid >> 5) * 8;
     const int gx = x0 + lx;
     if (gx < L.w) {
-        uint32_t lo[10], hi[10];
+        uint32_t lo[14], hi[14];
 #pragma unroll
-        for (int r = 0; r < 10; r++) {
+        for (int r = 0; r < 14; r++) {
             const uint32_t h2 = *reinterpret_cast<const uint32_t*>(&hb[ly + r][lx]);
             lo[r] = h2 & 0xffffu;
             hi[r] = h2 >> 16;
         }
         uint8_t* out = blur + L.img_off + (size_t)(y0 + ly) * L.pitch + gx;
+        const int rows = min(8, L.h - (y0 + ly));
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            if (y0 + ly + r < L.h) {
+        for (int r = 0; r < 8; r++) {
+            if (r < rows) {
                 const uint32_t a = 18u * (lo[r] + lo[r + 6]) + 34u * (lo[r + 1] + lo[r + 5]) + 48u * (lo[r + 2] + lo[r + 4]) + 56u * lo[r + 3];
                 const uint32_t c = 18u * (hi[r] + hi[r + 6]) + 34u * (hi[r + 1] + hi[r + 5]) + 48u * (hi[r + 2] + hi[r + 4]) + 56u * hi[r + 3];
                 // the pitch is a multiple of 128 and gx is even: a 16-bit store; pixel L.w (odd widths) falls into the row padding
-                *reinterpret_cast<uint16_t*>(out + (size_t)r * L.pitch) = (uint16_t)(((a + 32768u) >> 16) | (((c + 32768u) >> 16) << 8));
+                *reinterpret_cast<uint16_t*>(out) = (uint16_t)(((a + 32768u) >> 16) | (((c + 32768u) >> 16) << 8));
             }
+            out += L.pitch;
         }
     }
 }
@@ -1117,7 +1120,7 @@ void launch_blur(const OrbGeom& g, const OrbBuffers& b, cudaStream_t s, const Or
     const CUtensorMap* m0 = b.use_tma && b.tma_dev ? b.tma_dev + kMaxLevels : nullptr;
     const CUtensorMap* m1 = b1 && b1->use_tma && b1->tma_dev ? b1->tma_dev + kMaxLevels : nullptr;
     if (b1 && !m1) m0 = nullptr;  // both images take the same path
-    k_blur<<<dim3(g.blur_tiles, 1, b1 ? 2 : 1), 256, 0, s>>>(g, b.pyr, b.blur, b1 ? b1->pyr : nullptr, b1 ? b1->blur : nullptr, m0, b1 ? m1 : nullptr);
+    k_blur<<<dim3(g.blur_tiles, 1, b1 ? 2 : 1), kBlurThreads, 0, s>>>(g, b.pyr, b.blur, b1 ? b1->pyr : nullptr, b1 ? b1->blur : nullptr, m0, b1 ? m1 : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ K3 quadtree
