@@ -6,7 +6,7 @@
 One process per GPU (torchrun for N > 1); every rank is one `corbslam_client` stream pinned to its GPU (replicas:
 frames of different robots are independent), so scaling is weak and there is no data-path collective.
 A STEP = FRAMES_PER_STEP (64) stereo frames, in both arms; a frame = ORBextractor::operator() on the left and the right
-image (Frame.cc:78-81). The client keeps IN_FLIGHT = 4 frames in flight (that many handle pairs, corb_orb_extract_pair_submit/_wait):
+image (Frame.cc:78-81). The client keeps IN_FLIGHT = 8 frames in flight (that many handle pairs, corb_orb_extract_pair_submit/_wait):
 frame i + 1 is extracted while the tracking thread would consume frame i.
 
   value : frames/s with the images already resident in HBM (a pool of 160 distinct stereo pairs = 149 MB, larger than the
@@ -38,7 +38,7 @@ ORB_PARAMS = (2000, 1.2, 8, 20, 7)  # KITTI00-02.yaml:38-51
 N_BASE = 16           # distinct synthetic scenes ...
 N_POOL = 160          # ... shifted into 160 distinct stereo pairs: 160 x 2 x 465 750 B = 149 MB > 126 MB of L2
 FRAMES_PER_STEP = 64  # one step = 64 stereo frames, in both arms
-IN_FLIGHT = int(os.environ.get("CORB_BENCH_IN_FLIGHT", "4"))  # stereo frames a client keeps in flight (handle pairs)
+IN_FLIGHT = int(os.environ.get("CORB_BENCH_IN_FLIGHT", "8"))  # stereo frames a client keeps in flight (handle pairs)
 ALGO_BYTES_PER_IMAGE = W * H + 1441432 + 60 * 2000  # input + pyramid + 60 B per keypoint (K = 2000)
 WORKLOAD = "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7"
 
@@ -540,9 +540,9 @@ def run_reference(args):
         return
     n = args.gpus
     cores = os.cpu_count() or 2
-    # as many concurrent reference clients as our arm keeps frames in flight (IN_FLIGHT per GPU), two threads each
-    # (Frame.cc:78-81), bounded by the host cores: all the host threads this path can use for the same concurrency
-    clients = max(1, min(n * IN_FLIGHT, cores // 2))
+    # concurrent reference clients on ALL the host cores, two threads each (Frame.cc:78-81): the reference's own code with all
+    # the host threads it can use (our arm keeps IN_FLIGHT frames per GPU in flight; one client alone is reported beside it)
+    clients = max(1, cores // 2)
     per_client = max(1, (n * FRAMES_PER_STEP) // clients)
     exs = reference_extractors(clients)
     cpu_extract_fps(2, clients=clients, exs=exs)  # warm-up
@@ -824,7 +824,7 @@ def run_ours(args):
         kp_per_frame = nk / max(1, n_frames)
         h2d = 2 * W * H * F
         d2h = int(kp_per_frame * 60 + 16) * F
-        cpu_clients = max(1, min(IN_FLIGHT, (os.cpu_count() or 2) // 2))  # the concurrency our arm has in flight, on host cores
+        cpu_clients = max(1, (os.cpu_count() or 2) // 2)  # all host cores, two threads per client like the reference
         cpu_fps, cpu_dt, cpu_kind = cpu_extract_fps(max(2, args.sample_frames // cpu_clients), clients=cpu_clients)
         cpu_one_fps = cpu_extract_fps(min(32, args.sample_frames), clients=1)[0]
         cpu_fps_frame, _, _ = cpu_extract_fps(max(8, args.sample_frames // 4), clients=1, stereo=True)
