@@ -188,15 +188,18 @@ __global__ void __launch_bounds__(256) k_resize(LevelGeom src, LevelGeom dst, co
     if (blockIdx.z) { pyr_src = pyr_src1; pyr_dst = pyr_dst1; }
     pdl_release();
     pdl_wait();  // level l - 1 comes from the previous launch of the chain
+    // a thread produces 4 pixels of two consecutive rows: the x tables (source column, coefficients) are fetched once for both
     const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int dy = blockIdx.y * 8 + threadIdx.y;
+    const int dy = (blockIdx.y * 8 + threadIdx.y) * 2;
     if (dy >= dst.h || dx0 >= dst.w) return;
-    const int sy = yofs[dy];
-    const int sy0 = min(max(sy, 0), src.h - 1), sy1 = min(max(sy + 1, 0), src.h - 1);
-    const short2 bb = beta[dy];
-    const uint8_t* s0 = pyr_src + (size_t)sy0 * src.pitch;
-    const uint8_t* s1 = pyr_src + (size_t)sy1 * src.pitch;
-    uint32_t packed = 0;
+    const bool two = dy + 1 < dst.h;
+    const int sya = yofs[dy], syb = yofs[two ? dy + 1 : dy];
+    const short2 ba = beta[dy], bb = beta[two ? dy + 1 : dy];
+    const uint8_t* a0p = pyr_src + (size_t)min(max(sya, 0), src.h - 1) * src.pitch;
+    const uint8_t* a1p = pyr_src + (size_t)min(max(sya + 1, 0), src.h - 1) * src.pitch;
+    const uint8_t* b0p = pyr_src + (size_t)min(max(syb, 0), src.h - 1) * src.pitch;
+    const uint8_t* b1p = pyr_src + (size_t)min(max(syb + 1, 0), src.h - 1) * src.pitch;
+    uint32_t pa = 0, pb = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int dx = dx0 + k;
@@ -204,19 +207,29 @@ __global__ void __launch_bounds__(256) k_resize(LevelGeom src, LevelGeom dst, co
             const int sx = xofs[dx];
             const int sx1 = min(sx + 1, src.w - 1);
             const short2 a = alpha[dx];
-            const int r0 = (int)s0[sx] * a.x + (int)s0[sx1] * a.y;
-            const int r1 = (int)s1[sx] * a.x + (int)s1[sx1] * a.y;
-            const int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
-            packed |= (uint32_t)(v & 0xff) << (8 * k);
+            {
+                const int r0 = (int)a0p[sx] * a.x + (int)a0p[sx1] * a.y;
+                const int r1 = (int)a1p[sx] * a.x + (int)a1p[sx1] * a.y;
+                const int v = ((((int)ba.x * (r0 >> 4)) >> 16) + (((int)ba.y * (r1 >> 4)) >> 16) + 2) >> 2;
+                pa |= (uint32_t)(v & 0xff) << (8 * k);
+            }
+            {
+                const int r0 = (int)b0p[sx] * a.x + (int)b0p[sx1] * a.y;
+                const int r1 = (int)b1p[sx] * a.x + (int)b1p[sx1] * a.y;
+                const int v = ((((int)bb.x * (r0 >> 4)) >> 16) + (((int)bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
+                pb |= (uint32_t)(v & 0xff) << (8 * k);
+            }
         }
     }
-    *reinterpret_cast<uint32_t*>(pyr_dst + (size_t)dy * dst.pitch + dx0) = packed;  // pitch % 128 == 0, dx0 % 4 == 0
+    uint8_t* o = pyr_dst + (size_t)dy * dst.pitch + dx0;  // pitch % 128 == 0, dx0 % 4 == 0
+    *reinterpret_cast<uint32_t*>(o) = pa;
+    if (two) *reinterpret_cast<uint32_t*>(o + dst.pitch) = pb;
 }
 
 void launch_resize(const OrbGeom& g, const OrbBuffers& b, int level, cudaStream_t s, const OrbBuffers* b1) {
     const LevelGeom& src = g.lv[level - 1];
     const LevelGeom& dst = g.lv[level];
-    dim3 block(32, 8), grid((dst.w + 127) / 128, (dst.h + 7) / 8, b1 ? 2 : 1);
+    dim3 block(32, 8), grid((dst.w + 127) / 128, (dst.h + 15) / 16, b1 ? 2 : 1);
     launch_chain(k_resize, grid, block, 0, s, src, dst, (const uint8_t*)(b.pyr + src.img_off), b.pyr + dst.img_off, b.xofs + dst.xtab_off,
                  b.alpha + dst.xtab_off, b.yofs + dst.ytab_off, b.beta + dst.ytab_off,
                  (const uint8_t*)(b1 ? b1->pyr + src.img_off : nullptr), b1 ? b1->pyr + dst.img_off : nullptr);
