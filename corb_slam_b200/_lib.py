@@ -130,6 +130,8 @@ def lib():
         L.corb_orb_stream.restype = vp
         L.corb_orb_launches_per_extract.argtypes = [vp]
         L.corb_orb_uses_tma.argtypes = [vp]
+        L.corb_orb_set_host_transfer.argtypes = [vp, C.c_int]
+        L.corb_orb_host_transfer.argtypes = [vp]
         L.corb_orb_profile.argtypes = [vp, C.c_int, f32p, C.c_int, i32p]
         L.corb_orb_kernel_name.argtypes = [vp, C.c_int]
         L.corb_orb_kernel_name.restype = C.c_char_p

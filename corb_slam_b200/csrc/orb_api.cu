@@ -53,8 +53,8 @@ struct corb_orb {
     size_t pyr_bytes = 0;
     int cand_total = 0;
     int key_smem_cap = 0, oct_smem = 0;
-    bool h2d_node = false;  // CORB_H2D_NODE=1: host images enter through a copy-engine memcpy node instead of k_import's
-                            // loads from mapped host memory (measured equal on B200 + PCIe 5; kept for other hosts)
+    bool h2d_node = getenv("CORB_H2D_NODE") != nullptr;  // corb_orb_set_host_transfer / CORB_H2D_NODE=1: host images enter through a copy-engine memcpy node instead of k_import's
+                            // loads from mapped host memory (equal for one blocking frame, ~25 % more frames/s with 8 in flight)
     int tail_base = 0;      // chain graph: levels tail_base + 1 .. are produced by one k_pyramid launch (0 = resize launches only)
     int graph_mode = 0;  // 0: fused pyramid + per-level FAST/quadtree branches, 1: four fused launches, 2: resize chain + branches
     std::vector<void*> dev_allocs;
@@ -333,7 +333,6 @@ static int make_plan(corb_orb* h, int w, int hgt) {
             CORB_CHECK(pe == cudaSuccess, CORB_ERR_CUDA, "pyramid kernel shared memory: %s", cudaGetErrorString(pe));
         }
     }
-    h->h2d_node = getenv("CORB_H2D_NODE") != nullptr;
     {   // CORB_GRAPH=fused|hybrid selects the alternative per-frame graph shapes (kept for A/B measurements)
         const char* gm = getenv("CORB_GRAPH");
         h->graph_mode = gm && !strcmp(gm, "fused") ? 1 : gm && !strcmp(gm, "hybrid") ? 0 : 2;
@@ -1249,6 +1248,28 @@ const char* corb_orb_kernel_name(const corb_orb* h, int i) {
 void* corb_orb_stream(const corb_orb* h) { return h ? (void*)h->stream : nullptr; }
 int corb_orb_launches_per_extract(const corb_orb* h) { return h ? h->kernel_launches : 0; }
 int corb_orb_uses_tma(const corb_orb* h) { return h && h->plan_w ? h->buf.use_tma : 0; }
+
+int corb_orb_set_host_transfer(corb_orb* h, int mode) {
+    CORB_CHECK(h && (mode == 0 || mode == 1), CORB_ERR_INVALID, "mode must be 0 (mapped reads) or 1 (copy engine)");
+    CORB_CHECK(!h->pending && !h->pending_pair, CORB_ERR_INVALID, "wait for the submitted extraction first");
+    if (h->h2d_node == (mode == 1)) return CORB_OK;
+    CORB_CUDA(cudaSetDevice(h->device));
+    int rc = settle(h);
+    if (rc != CORB_OK) return rc;
+    CORB_CUDA(cudaStreamSynchronize(h->stream));
+    h->h2d_node = mode == 1;
+    // the captured graphs embed the transfer form: drop them, they are rebuilt on the next call
+    for (int v = 0; v < 3; v++) {
+        if (h->pair_exec[v]) cudaGraphExecDestroy(h->pair_exec[v]), h->pair_exec[v] = nullptr;
+        if (h->pair_graph[v]) cudaGraphDestroy(h->pair_graph[v]), h->pair_graph[v] = nullptr;
+    }
+    for (int v = 0; v < 2; v++) {
+        if (h->graph_exec[v]) cudaGraphExecDestroy(h->graph_exec[v]), h->graph_exec[v] = nullptr;
+        if (h->graph[v]) cudaGraphDestroy(h->graph[v]), h->graph[v] = nullptr;
+    }
+    return CORB_OK;
+}
+int corb_orb_host_transfer(const corb_orb* h) { return h && h->h2d_node ? 1 : 0; }
 
 int corb_orb_tap(corb_orb* h, int what, int level, void* out, size_t out_bytes, int* n) {
     CORB_CHECK(h && h->plan_w && level >= 0 && level < h->nlevels, CORB_ERR_INVALID, "bad argument or no plan");

@@ -172,6 +172,15 @@ class ORBextractor:
     def uses_tma(self):
         return bool(lib().corb_orb_uses_tma(self._h))
 
+    def set_host_transfer(self, mode):
+        """corb_orb_set_host_transfer: 0 = the import kernel reads page-locked images in place (lowest latency of one blocking
+        frame, default), 1 = copy-engine memcpy nodes (highest throughput with frames in flight). Set on both handles of a pair."""
+        check(lib().corb_orb_set_host_transfer(self._h, int(mode)))
+        return self
+
+    def host_transfer(self):
+        return int(lib().corb_orb_host_transfer(self._h))
+
     def launches_per_extract(self):
         return lib().corb_orb_launches_per_extract(self._h)
 

@@ -139,6 +139,15 @@ CORB_API int corb_orb_launches_per_extract(const corb_orb* h);
 /* 1 if the FAST kernel stages its tiles with TMA (cp.async.bulk.tensor) for the current plan; 0 if the driver entry point
  * was unavailable or CORB_NO_TMA is set in the environment (plain vector loads then; same results) */
 CORB_API int corb_orb_uses_tma(const corb_orb* h);
+/* How page-locked host images reach the GPU (the results are the same):
+ *   0 (default)  the import kernel reads them in place over PCIe (mapped memory) and every image gets its own launches, so the
+ *                left image's pipeline starts while the right one is still arriving: lowest latency of ONE blocking frame
+ *   1            copy-engine memcpy nodes into a staging buffer, both images in every launch: the DMA engines sustain about
+ *                twice the PCIe rate of SM loads, which is what counts with several frames in flight (submit / wait on
+ *                independent handle pairs): 25 k -> 31 k stereo frames/s through host buffers on a B200, 8 in flight
+ * Set it on BOTH handles of a pair. CORB_H2D_NODE=1 in the environment makes 1 the default. */
+CORB_API int corb_orb_set_host_transfer(corb_orb* h, int mode);
+CORB_API int corb_orb_host_transfer(const corb_orb* h);
 
 /* Per-kernel device time (ms, averaged over `reps` eager replays with CUDA events between launches) of one extraction
  * of the image currently resident; *n kernels in launch order, named by corb_orb_kernel_name(). For roofline reports. */

@@ -323,3 +323,25 @@ def test_two_stereo_frames_in_flight_from_one_thread():
     extract_stereo_wait(*pairs[0])
     for a, b in pairs + [ref_pair]:
         a.close(); b.close()
+
+
+def test_host_transfer_modes_agree():
+    """corb_orb_set_host_transfer: mapped reads by the import kernel and copy-engine memcpy nodes give the same stereo pair,
+    through the blocking call and through submit / wait, and the mode can be switched on live handles."""
+    from corb_slam_b200 import extract_stereo, extract_stereo_submit, extract_stereo_wait
+    left, right = stereo_frame(1262)
+    exl, exr = ORBextractor(*PARAMS), ORBextractor(*PARAMS)
+    (k0l, d0l), (k0r, d0r) = extract_stereo(exl, exr, left, right)
+    assert exl.host_transfer() == 0
+    exl.set_host_transfer(1); exr.set_host_transfer(1)
+    assert exl.host_transfer() == 1
+    (k1l, d1l), (k1r, d1r) = extract_stereo(exl, exr, left, right)
+    extract_stereo_submit(exl, exr, left, right)
+    (k2l, d2l), (k2r, d2r) = extract_stereo_wait(exl, exr)
+    for k, d in ((k1l, d1l), (k2l, d2l)):
+        assert k.tobytes() == k0l.tobytes() and np.array_equal(d, d0l)
+    for k, d in ((k1r, d1r), (k2r, d2r)):
+        assert k.tobytes() == k0r.tobytes() and np.array_equal(d, d0r)
+    exl.set_host_transfer(0); exr.set_host_transfer(0)
+    (k3l, d3l), (k3r, d3r) = extract_stereo(exl, exr, left, right)
+    assert k3l.tobytes() == k0l.tobytes() and np.array_equal(d3r, d0r)
