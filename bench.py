@@ -5,7 +5,7 @@
 
 One process per GPU (torchrun for N > 1); every rank is one `corbslam_client` stream pinned to its GPU (replicas:
 frames of different robots are independent), so scaling is weak and there is no data-path collective.
-A STEP = FRAMES_PER_STEP (64) stereo frames, in both arms; a frame = ORBextractor::operator() on the left and the right
+A STEP = FRAMES_PER_STEP (128) stereo frames, in both arms; a frame = ORBextractor::operator() on the left and the right
 image (Frame.cc:78-81). The client keeps IN_FLIGHT = 8 frames in flight (that many handle pairs, corb_orb_extract_pair_submit/_wait):
 frame i + 1 is extracted while the tracking thread would consume frame i.
 
@@ -37,7 +37,7 @@ W, H = 1242, 375
 ORB_PARAMS = (2000, 1.2, 8, 20, 7)  # KITTI00-02.yaml:38-51
 N_BASE = 16           # distinct synthetic scenes ...
 N_POOL = 160          # ... shifted into 160 distinct stereo pairs: 160 x 2 x 465 750 B = 149 MB > 126 MB of L2
-FRAMES_PER_STEP = 64  # one step = 64 stereo frames, in both arms
+FRAMES_PER_STEP = 128  # one step = 128 stereo frames, in both arms (20 steps = 2 560 frames = ~75 ms of GPU time)
 IN_FLIGHT = int(os.environ.get("CORB_BENCH_IN_FLIGHT", "8"))  # stereo frames a client keeps in flight (handle pairs)
 ALGO_BYTES_PER_IMAGE = W * H + 1441432 + 60 * 2000  # input + pyramid + 60 B per keypoint (K = 2000)
 WORKLOAD = "config#2: synthetic 1242x375 stereo, 2000 ORB features/frame, 8 levels, FAST 20/7"
@@ -363,7 +363,8 @@ def bench_matcher(device, with_cpu=True):
     qrec = BowRecord(2048, device=device).from_extractor(ex, gvoc, levelsup)
     t0 = time.perf_counter()
     for _ in range(reps):
-        qrec.from_extractor(ex, gvoc, levelsup)
+        qrec.from_extractor(ex, gvoc, levelsup)  # enqueues; the records are built back to back on the extractor's stream
+    qrec.sync()
     dt = (time.perf_counter() - t0) / reps
     got = qrec.download()
     assert all(a.tobytes() == b.tobytes() for a, b in zip(got, qb)), "device-built BoW differs from corb_voc_transform"

@@ -1050,6 +1050,7 @@ struct corb_bow_store {
     int32_t* h_counts = nullptr;  // pinned [4]
     int n = 0, n_bow = 0, n_fv = 0, n_fv_idx = 0;
     cudaStream_t last_stream = nullptr;
+    bool counts_pending = false;  // the fill is in flight: the counts are read (and the fill waited for) by the first consumer
 };
 
 extern "C" {
@@ -1097,6 +1098,7 @@ int corb_bow_store_fill(corb_bow_store* s, corb_voc* v, const corb_keypoint* d_k
     s->last_stream = st;
     s->n = n;
     if (n == 0) {
+        s->counts_pending = false;
         s->n_bow = s->n_fv = s->n_fv_idx = 0;
         CORB_CUDA(cudaMemsetAsync(s->dev.counts, 0, 16, st));
         CORB_CUDA(cudaMemsetAsync(s->dev.fv_off, 0, 4, st));
@@ -1116,13 +1118,32 @@ int corb_bow_store_fill(corb_bow_store* s, corb_voc* v, const corb_keypoint* d_k
     k_bow_build<<<2, 1024, smem, st>>>(s->dev, n);
     CORB_CUDA(cudaGetLastError());
     CORB_CUDA(cudaMemcpyAsync(s->h_counts, s->dev.counts, 16, cudaMemcpyDeviceToHost, st));
-    CORB_CUDA(cudaStreamSynchronize(st));
-    s->n_bow = s->h_counts[0]; s->n_fv = s->h_counts[1]; s->n_fv_idx = s->h_counts[2];
+    s->counts_pending = true;  // no wait here: the record is built behind the caller; consumers settle it first
     return CORB_OK;
+}
+
+// waits for a record's fill and takes its counts over; every consumer calls it before it reads the record or launches on it
+static int bow_store_settle(const corb_bow_store* cs) {
+    corb_bow_store* s = const_cast<corb_bow_store*>(cs);
+    if (!s->counts_pending) return CORB_OK;
+    CORB_CUDA(cudaSetDevice(s->device));
+    CORB_CUDA(cudaStreamSynchronize(s->last_stream));
+    s->n_bow = s->h_counts[0]; s->n_fv = s->h_counts[1]; s->n_fv_idx = s->h_counts[2];
+    s->counts_pending = false;
+    return CORB_OK;
+}
+
+int corb_bow_store_sync(corb_bow_store* s) {
+    CORB_CHECK(s, CORB_ERR_INVALID, "bad argument");
+    return bow_store_settle(s);
 }
 
 int corb_bow_store_side(const corb_bow_store* s, const uint8_t* d_valid, corb_bow_side* side, int* n_bow) {
     CORB_CHECK(s && side, CORB_ERR_INVALID, "bad argument");
+    {
+        const int rc = bow_store_settle(s);
+        if (rc != CORB_OK) return rc;
+    }
     side->desc = s->dev.desc; side->n = s->n;
     side->fv_nodes = s->dev.fv_nodes; side->fv_off = s->dev.fv_off; side->fv_idx = s->dev.fv_idx; side->fv_n = s->n_fv;
     side->valid = d_valid; side->angles = s->dev.angles;
@@ -1133,6 +1154,10 @@ int corb_bow_store_side(const corb_bow_store* s, const uint8_t* d_valid, corb_bo
 int corb_bow_store_download(const corb_bow_store* s, uint32_t* bow_words, double* bow_vals, int* n_bow, uint32_t* fv_nodes,
                             int32_t* fv_off, uint32_t* fv_idx, int* n_fv) {
     CORB_CHECK(s && n_bow && n_fv, CORB_ERR_INVALID, "bad argument");
+    {
+        const int rc = bow_store_settle(s);
+        if (rc != CORB_OK) return rc;
+    }
     CORB_CUDA(cudaSetDevice(s->device));
     *n_bow = s->n_bow; *n_fv = s->n_fv;
     if (bow_words && s->n_bow) CORB_CUDA(cudaMemcpy(bow_words, s->dev.bow_words, (size_t)s->n_bow * 4, cudaMemcpyDeviceToHost));
@@ -1152,8 +1177,10 @@ int corb_bow_score_stores(corb_voc* v, const corb_bow_store* query, int ncand, c
     int rc = v->arena.reserve(p.off);
     if (rc != CORB_OK) return rc;
     uint8_t *h = v->arena.h, *d = v->arena.d;
+    if ((rc = bow_store_settle(query)) != CORB_OK) return rc;
     for (int i = 0; i < ncand; i++) {
         CORB_CHECK(cands[i] && cands[i]->device == v->device, CORB_ERR_INVALID, "candidate %d is NULL or on another device", i);
+        if ((rc = bow_store_settle(cands[i])) != CORB_OK) return rc;
         ((const uint32_t**)(h + oW))[i] = cands[i]->dev.bow_words;
         ((const double**)(h + oV))[i] = cands[i]->dev.bow_vals;
         ((int*)(h + oN))[i] = cands[i]->n_bow;

@@ -92,6 +92,7 @@ struct corb_orb {
     cudaGraphNode_t pair_imp_l[3] = {nullptr, nullptr, nullptr}, pair_imp_r[3] = {nullptr, nullptr, nullptr};
     bool pair_split[3] = {false, false, false};  // the pair graph has separate launches (and import nodes) per image
     int plan_serial = 0;          // bumped whenever the plan (device buffers) is rebuilt
+    bool host_count = false;      // the last extraction on this handle also delivered its keypoint count to h_scalars[0]
     cudaEvent_t ev_busy = nullptr; // recorded on the stream that last ran work touching this handle's buffers
     cudaStream_t busy_stream = nullptr;
 
@@ -614,6 +615,7 @@ static int launch_frame(corb_orb* h, int variant, const uint8_t* src, int stride
     rc = patch_import(h->graph_exec[variant], h->import_node[variant], h, src, stride, nullptr, nullptr, 0, nullptr, &h->import_at[variant]);
     if (rc != CORB_OK) return rc;
     CORB_CUDA(cudaGraphLaunch(h->graph_exec[variant], h->stream));
+    h->host_count = variant >= 1;  // the host variants end with the D2H of keypoints, descriptors and the count
     h->own_dirty = true;
     return CORB_OK;
 }
@@ -760,6 +762,7 @@ static int launch_pair(corb_orb* hl, corb_orb* hr, int variant, const uint8_t* s
         return rc;
     }
     CORB_CUDA(cudaGraphLaunch(hl->pair_exec[variant], hl->stream));
+    hl->host_count = hr->host_count = variant >= 1;
     hl->own_dirty = true;
     hr->busy_stream = hl->stream;
     return CORB_OK;
@@ -1152,10 +1155,15 @@ int corb_frame_bow(corb_orb* h, corb_voc* v, int levelsup, corb_bow_store* s) {
     CORB_CHECK(!h->pending && !h->pending_pair, CORB_ERR_INVALID, "wait for the submitted extraction first");
     CORB_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->busy_stream ? h->busy_stream : h->stream;
-    // the keypoint count of the last extraction, read behind it on its stream (device-resident extractions never told the host)
+    // the keypoint count of the last extraction: already on the host after a host-result extraction (which has been waited
+    // for), else read behind the extraction on its stream (device-resident extractions never told the host)
     int n = 0;
-    CORB_CUDA(cudaMemcpyAsync(&n, h->buf.count, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CORB_CUDA(cudaStreamSynchronize(st));
+    if (h->host_count && h->h_scalars && !h->own_dirty) {
+        n = h->h_scalars[0];
+    } else {
+        CORB_CUDA(cudaMemcpyAsync(&n, h->buf.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CORB_CUDA(cudaStreamSynchronize(st));
+    }
     CORB_CHECK(n >= 0 && n <= h->geom.kp_cap, CORB_ERR_INVALID, "keypoint count %d out of range", n);
     return corb_bow_store_fill(s, v, h->buf.kps, h->buf.desc, n, levelsup, (void*)st);
 }

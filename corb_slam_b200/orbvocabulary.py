@@ -123,6 +123,11 @@ class BowRecord:
         self.n = int(n)
         return self
 
+    def sync(self):
+        """corb_bow_store_sync: wait for the record's fill (from_extractor / from_device only enqueue it)."""
+        check(lib().corb_bow_store_sync(self._h))
+        return self
+
     def side(self, d_valid=None):
         """corb_bow_side of device pointers (for ORBmatcher.SearchByBoWDevice) and the BowVector length."""
         s, nb = _lib.BowSide(), C.c_int32()
