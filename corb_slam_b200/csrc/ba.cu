@@ -1841,6 +1841,8 @@ struct BaArena {
     bool release_when_idle = false;
     // the call's stream, timing events and pinned scalar mailbox live with the arena too (~2 ms of driver calls per BA otherwise)
     cudaStream_t stream = nullptr;
+    cudaStream_t up_stream = nullptr;  // edge uploads of a sharded solve: beside the collectives of the set-up, not behind them
+    cudaEvent_t ev_up = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double* h_scalars = nullptr;
     // page-locked staging slots for the upload of the caller's (pageable) edge arrays: kStageSlots threads each copy
@@ -1860,6 +1862,8 @@ struct BaArena {
         if (ev0) cudaEventDestroy(ev0), ev0 = nullptr;
         if (ev1) cudaEventDestroy(ev1), ev1 = nullptr;
         if (stream) cudaStreamDestroy(stream), stream = nullptr;
+        if (up_stream) cudaStreamDestroy(up_stream), up_stream = nullptr;
+        if (ev_up) cudaEventDestroy(ev_up), ev_up = nullptr;
     }
     std::vector<std::pair<char*, size_t>> slabs;
     size_t cur = 0, off = 0;
@@ -2250,6 +2254,10 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         if (!A.stream) CORB_CUDA(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
         if (!A.ev0) CORB_CUDA(cudaEventCreate(&A.ev0));
         if (!A.ev1) CORB_CUDA(cudaEventCreate(&A.ev1));
+        if (allreduce && !A.up_stream) {
+            CORB_CUDA(cudaStreamCreateWithFlags(&A.up_stream, cudaStreamNonBlocking));
+            CORB_CUDA(cudaEventCreateWithFlags(&A.ev_up, cudaEventDisableTiming));
+        }
         if (!A.h_scalars) CORB_CUDA(cudaMallocHost(&A.h_scalars, 8 * sizeof(double)));
         if (!A.h_stage && (size_t)E * 40 >= 4 * BaArena::kStageBytes) {
             CORB_CUDA(cudaMallocHost(&A.h_stage, BaArena::kStageSlots * BaArena::kStageBytes));
@@ -2326,7 +2334,10 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         std::thread t;
         ~Joiner() { if (t.joinable()) t.join(); }
     } uploader;
-    const bool early_upload = !allreduce && E > 0;
+    // with an all-reduce hook the ordering synchronises on the call's stream (collectives): the copies then go to the arena's
+    // upload stream and the call's stream waits for them once, before the first kernel that reads the edges
+    cudaStream_t up_st = allreduce ? (H.arena ? H.arena->up_stream : nullptr) : H.stream;
+    const bool early_upload = E > 0 && up_st != nullptr;
     if (early_upload) {
         int *q_pose, *q_point;
         double *q_obs, *q_info;
@@ -2335,7 +2346,7 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             (rc0 = H.alloc(&q_obs, (size_t)E * 3)) != CORB_OK || (rc0 = H.alloc(&q_info, (size_t)E)) != CORB_OK)
             return rc0;
         d.e_pose = q_pose; d.e_point = q_point; d.e_obs = q_obs; d.e_info = q_info;
-        cudaStream_t st = H.stream;
+        cudaStream_t st = up_st;
         BaArena* stage = H.arena && H.arena->h_stage ? H.arena : nullptr;
         uploader.t = std::thread([=, &up_err] {
             struct Job { char* dst; const char* src; size_t bytes; };
@@ -2565,6 +2576,10 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     if (early_upload) {
         uploader.t.join();
         CORB_CHECK(up_err == cudaSuccess, CORB_ERR_CUDA, "uploading the edge arrays failed: %s", cudaGetErrorString(up_err));
+        if (up_st != H.stream) {
+            CORB_CUDA(cudaEventRecord(H.arena->ev_up, up_st));
+            CORB_CUDA(cudaStreamWaitEvent(H.stream, H.arena->ev_up, 0));
+        }
     } else if ((rc = H.upload_raw(&d.e_pose, ep, (size_t)E)) != CORB_OK || (rc = H.upload_raw(&d.e_point, ept, (size_t)E)) != CORB_OK ||
                (rc = H.upload_raw(&d.e_obs, eobs, (size_t)E * 3)) != CORB_OK || (rc = H.upload_raw(&d.e_info, einfo, (size_t)E)) != CORB_OK) {
         return rc;
