@@ -1393,6 +1393,34 @@ __global__ void __launch_bounds__(256) k_ba_fill_int(int* p, int n, int v) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < n) p[i] = v;
 }
+// ---- set-up: neighbour ranges of the keyframes on the device. nbr[j] = smallest, nbr[Pf + j] = largest free keyframe (in the
+//      numbering `idx`) that shares a free landmark with keyframe j. The ordering derives the border, the chunks and the
+//      envelope from them; it asks three times (natural order, border last, separators last), and walking the 1 M edges on
+//      the host each time was half of the set-up.
+__global__ void __launch_bounds__(256) k_ba_nbr_init(int* __restrict__ nbr, int Pf) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j < Pf) { nbr[j] = j; nbr[Pf + j] = j; }
+}
+__global__ void __launch_bounds__(256) k_ba_nbr_range(const int* __restrict__ e_pose, const int* __restrict__ lm_off, const int* __restrict__ lfree,
+                                                      const int* __restrict__ idx, int L, int Pf, int* __restrict__ nbr) {
+    const int l = blockIdx.x * 256 + threadIdx.x;
+    if (l >= L || lfree[l] < 0) return;
+    const int k0 = lm_off[l], k1 = lm_off[l + 1];
+    int lo = Pf, hi = -1;
+    for (int k = k0; k < k1; k++) {
+        const int pj = idx[e_pose[k]];
+        if (pj >= 0) { lo = min(lo, pj); hi = max(hi, pj); }
+    }
+    if (hi < 0) return;
+    for (int k = k0; k < k1; k++) {
+        const int pj = idx[e_pose[k]];
+        if (pj >= 0) {
+            if (lo < pj) atomicMin(&nbr[pj], lo);  // (min / max commute: the result does not depend on the order of the atomics)
+            if (hi > pj) atomicMax(&nbr[Pf + pj], hi);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_ba_int_to_double(const int* a, double* b, int n, int back, int* a_out) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
@@ -1847,8 +1875,8 @@ struct BaArena {
     double* h_scalars = nullptr;
     // page-locked staging slots for the upload of the caller's (pageable) edge arrays: kStageSlots threads each copy
     // chunks into their slot and enqueue the DMA from there - several times the rate of cudaMemcpy from pageable memory
-    static constexpr int kStageSlots = 4;
-    static constexpr size_t kStageBytes = (size_t)4 << 20;
+    static constexpr int kStageSlots = 8;
+    static constexpr size_t kStageBytes = (size_t)1 << 20;
     uint8_t* h_stage = nullptr;
     cudaEvent_t stage_ev[kStageSlots] = {};
     void free_slabs() {  // caller holds mu and the arena is idle
@@ -2254,12 +2282,12 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         if (!A.stream) CORB_CUDA(cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking));
         if (!A.ev0) CORB_CUDA(cudaEventCreate(&A.ev0));
         if (!A.ev1) CORB_CUDA(cudaEventCreate(&A.ev1));
-        if (allreduce && !A.up_stream) {
+        if (!A.up_stream) {
             CORB_CUDA(cudaStreamCreateWithFlags(&A.up_stream, cudaStreamNonBlocking));
             CORB_CUDA(cudaEventCreateWithFlags(&A.ev_up, cudaEventDisableTiming));
         }
         if (!A.h_scalars) CORB_CUDA(cudaMallocHost(&A.h_scalars, 8 * sizeof(double)));
-        if (!A.h_stage && (size_t)E * 40 >= 4 * BaArena::kStageBytes) {
+        if (!A.h_stage && (size_t)E * 40 >= ((size_t)16 << 20)) {
             CORB_CUDA(cudaMallocHost(&A.h_stage, BaArena::kStageSlots * BaArena::kStageBytes));
             for (auto& e : A.stage_ev) CORB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
@@ -2334,9 +2362,10 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         std::thread t;
         ~Joiner() { if (t.joinable()) t.join(); }
     } uploader;
-    // with an all-reduce hook the ordering synchronises on the call's stream (collectives): the copies then go to the arena's
-    // upload stream and the call's stream waits for them once, before the first kernel that reads the edges
-    cudaStream_t up_st = allreduce ? (H.arena ? H.arena->up_stream : nullptr) : H.stream;
+    // The bulk of the edge arrays goes up on the arena's upload stream while the ordering is derived; the call's stream - which
+    // carries the ordering's own device work and, in a sharded solve, its collectives - waits for them once, before the first
+    // kernel that reads the edges. The keyframe indices of the edges (what the ordering needs) go first, on the call's stream.
+    cudaStream_t up_st = H.arena ? H.arena->up_stream : nullptr;
     const bool early_upload = E > 0 && up_st != nullptr;
     if (early_upload) {
         int *q_pose, *q_point;
@@ -2346,12 +2375,13 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             (rc0 = H.alloc(&q_obs, (size_t)E * 3)) != CORB_OK || (rc0 = H.alloc(&q_info, (size_t)E)) != CORB_OK)
             return rc0;
         d.e_pose = q_pose; d.e_point = q_point; d.e_obs = q_obs; d.e_info = q_info;
+        CORB_CUDA(cudaMemcpyAsync(q_pose, ep, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, H.stream));
         cudaStream_t st = up_st;
         BaArena* stage = H.arena && H.arena->h_stage ? H.arena : nullptr;
         uploader.t = std::thread([=, &up_err] {
             struct Job { char* dst; const char* src; size_t bytes; };
-            const Job jobs[4] = {{(char*)q_obs, (const char*)eobs, (size_t)E * 3 * sizeof(double)}, {(char*)q_info, (const char*)einfo, (size_t)E * sizeof(double)},
-                                 {(char*)q_pose, (const char*)ep, (size_t)E * sizeof(int)}, {(char*)q_point, (const char*)ept, (size_t)E * sizeof(int)}};
+            const Job jobs[3] = {{(char*)q_obs, (const char*)eobs, (size_t)E * 3 * sizeof(double)}, {(char*)q_info, (const char*)einfo, (size_t)E * sizeof(double)},
+                                 {(char*)q_point, (const char*)ept, (size_t)E * sizeof(int)}};
             if (!stage) {
                 cudaError_t e = cudaSetDevice(device);
                 for (const Job& j : jobs)
@@ -2393,9 +2423,45 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     int rc;
     double* d_tmp = nullptr;
     if (allreduce && Pf > 0 && (rc = H.alloc(&d_tmp, 2 * (size_t)Pf)) != CORB_OK) return rc;
+    // device form of the neighbour ranges (k_ba_nbr_range): needs the edges' keyframe indices, already on their way up
+    const bool dev_ranges = early_upload && Pf > 0 && L > 0;
+    int *d_idx = nullptr, *d_nbr = nullptr;
+    std::vector<int> h_nbr;
+    if (dev_ranges) {
+        int *q_lmoff, *q_lfree;
+        if ((rc = H.alloc(&q_lmoff, (size_t)L + 1)) != CORB_OK || (rc = H.alloc(&q_lfree, (size_t)L)) != CORB_OK ||
+            (rc = H.alloc(&d_idx, (size_t)P)) != CORB_OK || (rc = H.alloc(&d_nbr, 2 * (size_t)Pf)) != CORB_OK)
+            return rc;
+        CORB_CUDA(cudaMemcpyAsync(q_lmoff, lm_off.data(), ((size_t)L + 1) * sizeof(int), cudaMemcpyHostToDevice, H.stream));
+        CORB_CUDA(cudaMemcpyAsync(q_lfree, lfree.data(), (size_t)L * sizeof(int), cudaMemcpyHostToDevice, H.stream));
+        d.lm_off = q_lmoff;
+        d.lfree = q_lfree;
+        h_nbr.resize(2 * (size_t)Pf);
+    }
     auto neighbour_range = [&](const std::vector<int>& idx, std::vector<double>& mn, std::vector<double>& mx) -> int {
         mn.assign(std::max(Pf, 1), 0.0);
         mx.assign(std::max(Pf, 1), 0.0);
+        if (dev_ranges) {
+            CORB_CUDA(cudaMemcpyAsync(d_idx, idx.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice, H.stream));
+            k_ba_nbr_init<<<(Pf + 255) / 256, 256, 0, H.stream>>>(d_nbr, Pf);
+            k_ba_nbr_range<<<(L + 255) / 256, 256, 0, H.stream>>>(d.e_pose, d.lm_off, d.lfree, d_idx, L, Pf, d_nbr);
+            CORB_CUDA(cudaGetLastError());
+            if (allreduce) {  // all ranks must agree on the structure of the reduced system
+                k_ba_int_to_double<<<(2 * Pf + 255) / 256, 256, 0, H.stream>>>(d_nbr, d_tmp, 2 * Pf, 0, nullptr);
+                int r2 = H.reduce(d_tmp, Pf, 1);
+                if (r2 != CORB_OK) return r2;
+                r2 = H.reduce(d_tmp + Pf, Pf, 2);
+                if (r2 != CORB_OK) return r2;
+                CORB_CUDA(cudaMemcpyAsync(mn.data(), d_tmp, Pf * sizeof(double), cudaMemcpyDeviceToHost, H.stream));
+                CORB_CUDA(cudaMemcpyAsync(mx.data(), d_tmp + Pf, Pf * sizeof(double), cudaMemcpyDeviceToHost, H.stream));
+                CORB_CUDA(cudaStreamSynchronize(H.stream));
+            } else {
+                CORB_CUDA(cudaMemcpyAsync(h_nbr.data(), d_nbr, 2 * (size_t)Pf * sizeof(int), cudaMemcpyDeviceToHost, H.stream));
+                CORB_CUDA(cudaStreamSynchronize(H.stream));
+                for (int j = 0; j < Pf; j++) { mn[j] = h_nbr[j]; mx[j] = h_nbr[Pf + j]; }
+            }
+            return CORB_OK;
+        }
         for (int j = 0; j < Pf; j++) mn[j] = mx[j] = j;
         std::mutex merge;
         host_parallel_for(L, [&](int l0, int l1) {
@@ -2572,7 +2638,8 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     lap("envelope lists");
     // ---- device buffers
 #define UP(field, vec) if ((rc = H.upload(&d.field, vec)) != CORB_OK) return rc
-    UP(pfree, pfree); UP(lfree, lfree);
+    UP(pfree, pfree);
+    if (!dev_ranges) { UP(lfree, lfree); }
     if (early_upload) {
         uploader.t.join();
         CORB_CHECK(up_err == cudaSuccess, CORB_ERR_CUDA, "uploading the edge arrays failed: %s", cudaGetErrorString(up_err));
@@ -2585,7 +2652,8 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         return rc;
     }
     if ((rc = H.build_pose_csr()) != CORB_OK) return rc;  // CSR by keyframe, built on the device from the uploaded e_pose
-    UP(lm_off, lm_off); UP(first, first); UP(rowoff, rowoff);
+    if (!dev_ranges) { UP(lm_off, lm_off); }
+    UP(first, first); UP(rowoff, rowoff);
     UP(coloff, coloff); UP(col_rows, col_rows); UP(coloff_b, coloff_b); UP(col_rows_b, col_rows_b); UP(chunk_start, chunk_start);
 #undef UP
     {
