@@ -209,3 +209,30 @@ def test_ba_large_problem_staged_upload_equals_plain_upload(monkeypatch):
         bad["edge_pose"] = prob["edge_pose"].copy()
         bad["edge_pose"][len(perm) // 2] = 500
         Optimizer.BundleAdjustment(bad, 1, bRobust=False)
+
+
+def test_ba_schur_pair_lists_equal_the_edge_walk(monkeypatch):
+    """The Schur rows from the sorted pair lists (k_ba_schur_pairs, built once per call) against the per-iteration edge walk
+    (k_ba_schur_rows, CORB_BA_SCHUR=old): same accept / reject sequence, chi2 to 1e-10, poses to 1e-8 - with fixed keyframes,
+    fixed landmarks, fusion links and both kernel shapes; and the pair lists are what runs by default, reproducibly bit for bit."""
+    prob = ba_problem(600, 20000, seed=23, n_fusion=12)
+    prob["pose_fixed"][:2] = 1
+    prob["point_fixed"][::11] = 1
+    monkeypatch.setenv("CORB_BA_SCHUR", "old")
+    out_o, info_o = Optimizer.BundleAdjustment(prob, 5, bRobust=False)
+    monkeypatch.delenv("CORB_BA_SCHUR")
+    assert info_o["schur_pair_lists"] == 0
+    out_n, info_n = Optimizer.BundleAdjustment(prob, 5, bRobust=False)
+    out_n2, info_n2 = Optimizer.BundleAdjustment(prob, 5, bRobust=False)
+    assert info_n["schur_pair_lists"] == 1
+    assert info_n["trial_accepted"] == info_o["trial_accepted"]
+    assert info_n["chi2_final"] == pytest.approx(info_o["chi2_final"], rel=1e-10)
+    np.testing.assert_allclose(out_n["pose_t"], out_o["pose_t"], atol=1e-8)
+    np.testing.assert_allclose(out_n["point_xyz"], out_o["point_xyz"], atol=1e-7)
+    assert out_n["pose_t"].tobytes() == out_n2["pose_t"].tobytes() and info_n["chi2_final"] == info_n2["chi2_final"]  # fixed summation order
+    monkeypatch.setenv("CORB_BA_SP", "256,64")
+    out_s, info_s = Optimizer.BundleAdjustment(prob, 5, bRobust=False)
+    monkeypatch.delenv("CORB_BA_SP")
+    assert info_s["schur_pair_lists"] == 1 and info_s["trial_accepted"] == info_o["trial_accepted"]
+    assert info_s["chi2_final"] == pytest.approx(info_o["chi2_final"], rel=1e-10)
+    _check(prob, iters=5)
