@@ -706,11 +706,12 @@ def run_ours(args):
     #      all-reduced over NCCL from inside corb_ba_solve when more than one GPU is attached
     ba_info, ba_ms, ba_rms, ba_edges, ba_allreduce, ba_parity, ba_server = None, 0.0, None, 0, None, None, None
     if not args.no_ba:
-        from corb_slam_b200 import Optimizer, torch_allreduce
+        from corb_slam_b200 import Optimizer, page_locked, torch_allreduce
         from corb_slam_b200.synth import ba_problem, ba_shard
         prob = ba_problem(BA_P, BA_L, seed=7)
         ba_edges = len(prob["edge_pose"])
-        mine = ba_shard(prob, rank, world) if world > 1 else prob
+        # the flat edge arrays live in page-locked memory, like the buffers the C++ shim flattens the graph into (shim/Optimizer_gba.h)
+        mine = page_locked(ba_shard(prob, rank, world) if world > 1 else prob)
         cb = torch_allreduce(device=local) if world > 1 else None
         Optimizer.BundleAdjustment(ba_shard(ba_problem(50, 2000, seed=1), rank, world) if world > 1 else ba_problem(50, 2000, seed=1),
                                    2, bRobust=False, device=local, allreduce=cb)  # warm-up (context, NCCL channels)
@@ -738,9 +739,10 @@ def run_ours(args):
             pts[torch.from_numpy(mine["_point_ids"]).cuda()] = torch.from_numpy(ba_out["point_xyz"]).cuda()
             dist.all_reduce(pts)
             if rank == 0:
-                Optimizer.BundleAdjustment(prob, 1, bRobust=False, device=local)
+                prob_pl = page_locked(prob)
+                Optimizer.BundleAdjustment(prob_pl, 1, bRobust=False, device=local)
                 t0 = time.perf_counter()
-                full, finfo = Optimizer.BundleAdjustment(prob, BA_ITERS, bRobust=False, device=local)
+                full, finfo = Optimizer.BundleAdjustment(prob_pl, BA_ITERS, bRobust=False, device=local)
                 single_ms = (time.perf_counter() - t0) * 1e3
                 ba_parity = {"accept_sequence_equal": ba_info["trial_accepted"] == finfo["trial_accepted"],
                              "max_abs_pose_t": float(np.abs(ba_out["pose_t"] - full["pose_t"]).max()),
@@ -880,7 +882,7 @@ def run_ours(args):
                 "metric": "global_ba_ms_per_10k_landmarks", "value": ba_ms / (BA_L / 1e4), "unit": "ms/10k landmarks",
                 "higher_is_better": False, "n_gpus": world, "scaling": "strong", "dtype": "f64",
                 "config": {"workload": "synthetic street BA: P=%d keyframes, L=%d landmarks, E=%d observations (80%% stereo), "
-                                       "%d LM iterations, bRobust=false, seed 7" % (BA_P, BA_L, ba_edges, BA_ITERS),
+                                       "%d LM iterations, bRobust=false, seed 7; edge arrays in page-locked host memory" % (BA_P, BA_L, ba_edges, BA_ITERS),
                            "sharding": "landmarks l %% N per rank, poses replicated, all-reduce(sum, fp64) of the reduced "
                                        "camera system per LM trial" if world > 1 else "single GPU, no collective"},
                 "ms_total": ba_ms, "ms_in_library": ba_info["ms_total"], "ms_reduced_camera_solves": ba_info["ms_solve"],

@@ -10,4 +10,4 @@ from .orbmatcher import ORBmatcher, BowFeatures  # noqa: F401
 from .orbvocabulary import BowRecord, ORBVocabulary  # noqa: F401
 from .frame import FrameView  # noqa: F401
 from .pnpsolver import PnPsolver  # noqa: F401
-from .optimizer import Optimizer, torch_allreduce  # noqa: F401
+from .optimizer import Optimizer, page_locked, torch_allreduce  # noqa: F401

@@ -163,6 +163,8 @@ def lib():
         L.corb_pnp_ransac_params.argtypes = [C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_float, i32p, i32p]
         L.corb_pnp_iterate_batch.argtypes = [vp, C.c_int, C.POINTER(PnpProblem), C.POINTER(PnpResult), C.POINTER(vp)]
         L.corb_ba_release_cache.argtypes = [C.c_int]
+        L.corb_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.corb_host_free.argtypes = [C.c_void_p]
         L.corb_ba_solve.argtypes = [C.POINTER(BaProblem), C.c_int, vp, C.c_int, C.c_int, C.POINTER(BaResult), vp, vp]
         _lib = L
     return _lib

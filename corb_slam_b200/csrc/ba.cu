@@ -2207,6 +2207,19 @@ static void host_parallel_for(int n, F fn) {
     for (auto& t : th) t.join();
 }
 
+extern "C" int corb_host_alloc(size_t bytes, void** out) {
+    CORB_CHECK(out, CORB_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    void* p = nullptr;
+    CORB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable));
+    *out = p;
+    return CORB_OK;
+}
+extern "C" int corb_host_free(void* p) {
+    if (p) CORB_CUDA(cudaFreeHost(p));
+    return CORB_OK;
+}
+
 extern "C" int corb_ba_release_cache(int device) {
     CORB_CHECK(device >= 0 && device < 16, CORB_ERR_INVALID, "device %d out of range", device);
     std::lock_guard<std::mutex> lk(g_arena[device].mu);
@@ -2382,17 +2395,25 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             struct Job { char* dst; const char* src; size_t bytes; };
             const Job jobs[3] = {{(char*)q_obs, (const char*)eobs, (size_t)E * 3 * sizeof(double)}, {(char*)q_info, (const char*)einfo, (size_t)E * sizeof(double)},
                                  {(char*)q_point, (const char*)ept, (size_t)E * sizeof(int)}};
-            if (!stage) {
-                cudaError_t e = cudaSetDevice(device);
-                for (const Job& j : jobs)
-                    if (e == cudaSuccess) e = cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice, st);
-                up_err = e;
-                return;
-            }
+            // page-locked caller arrays (corb_host_alloc: what the C++ shim flattens into) are read by the DMA engines in place;
+            // pageable ones go through the staging slots
+            cudaError_t e0 = cudaSetDevice(device);
             std::vector<Job> chunks;
-            for (const Job& j : jobs)
+            for (const Job& j : jobs) {
+                cudaPointerAttributes at;
+                const bool locked = cudaPointerGetAttributes(&at, j.src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+                if (!locked) cudaGetLastError();
+                if (locked || !stage) {
+                    if (e0 == cudaSuccess) e0 = cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyHostToDevice, st);
+                    continue;
+                }
                 for (size_t o = 0; o < j.bytes; o += BaArena::kStageBytes)
                     chunks.push_back({j.dst + o, j.src + o, std::min(BaArena::kStageBytes, j.bytes - o)});
+            }
+            if (chunks.empty() || e0 != cudaSuccess) {
+                up_err = e0;
+                return;
+            }
             cudaError_t errs[BaArena::kStageSlots];
             std::vector<std::thread> th;
             for (int t = 0; t < BaArena::kStageSlots; t++)
@@ -2651,7 +2672,9 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
                (rc = H.upload_raw(&d.e_obs, eobs, (size_t)E * 3)) != CORB_OK || (rc = H.upload_raw(&d.e_info, einfo, (size_t)E)) != CORB_OK) {
         return rc;
     }
+    lap("edge upload joined");
     if ((rc = H.build_pose_csr()) != CORB_OK) return rc;  // CSR by keyframe, built on the device from the uploaded e_pose
+    lap("pose CSR enqueued");
     if (!dev_ranges) { UP(lm_off, lm_off); }
     UP(first, first); UP(rowoff, rowoff);
     UP(coloff, coloff); UP(col_rows, col_rows); UP(coloff_b, coloff_b); UP(col_rows_b, col_rows_b); UP(chunk_start, chunk_start);
@@ -2698,7 +2721,9 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
             const size_t k = (size_t)(lm_off[l + 1] - lm_off[l]);
             pairs_bound += k * (k + 1) / 2;
         }
+        lap("buffers allocated");
         if ((rc = H.build_schur_pairs(pairs_bound, (size_t)nblocks)) != CORB_OK) return rc;
+        lap("pair lists built (sync)");
         res->schur_pair_lists = H.sp_ok ? 1 : 0;
     }
     d.bs = d.S + H.s_doubles;

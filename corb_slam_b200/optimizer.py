@@ -16,6 +16,39 @@ _DT = {"pose_q": np.float64, "pose_t": np.float64, "pose_fixed": np.uint8, "pose
        "edge_inv_sigma2": np.float64}
 
 
+class _PageLocked:
+    """Owns one corb_host_alloc block; `array` is a numpy view of it."""
+
+    def __init__(self, like):
+        like = np.ascontiguousarray(like)
+        self._p = C.c_void_p()
+        check(lib().corb_host_alloc(max(1, like.nbytes), C.byref(self._p)))
+        buf = (C.c_char * max(1, like.nbytes)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=like.dtype, count=like.size).reshape(like.shape)
+        self.array[...] = like
+
+    def __del__(self):
+        try:
+            if self._p:
+                lib().corb_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
+def page_locked(problem):
+    """A copy of `problem` whose edge arrays live in page-locked memory (corb_host_alloc), like the buffers the C++ shim flattens
+    the graph into: corb_ba_solve then uploads them with the DMA engines in place instead of staging them."""
+    out = dict(problem)
+    keep = []
+    for k in ("edge_pose", "edge_point", "edge_obs", "edge_inv_sigma2"):
+        h = _PageLocked(np.asarray(problem[k], _DT[k]))
+        keep.append(h)
+        out[k] = h.array
+    out["_page_locked"] = keep  # owners of the blocks: live as long as the problem dict
+    return out
+
+
 class _DevArray:
     """Wraps a raw device pointer as a __cuda_array_interface__ object so torch can view it without a copy."""
 

@@ -393,6 +393,11 @@ typedef struct {
  * cudaMalloc / cudaFree pairs cost as much as the optimisation). This returns the arena of `device` to the driver;
  * a call that is running on the device keeps its memory and the arena is released when it ends. */
 CORB_API int corb_ba_release_cache(int device);
+/* Page-locked host memory for the caller's flat arrays. corb_ba_solve uploads page-locked edge arrays with the DMA engines in
+ * place (40 B per observation: 0.8 ms instead of ~4 ms per million observations out of pageable memory, which is most of the
+ * set-up of a global BA); the C++ shim flattens the graph into such buffers (shim/Optimizer_gba.h). Pageable arrays work too. */
+CORB_API int corb_host_alloc(size_t bytes, void** out);
+CORB_API int corb_host_free(void* p);
 
 /* All-reduce hook for landmark-sharded BA: `buf` is a DEVICE pointer to n doubles, reduced in place over
  * all ranks with op 0 = sum, 1 = min, 2 = max, ordered on CUDA stream `stream` (a cudaStream_t). The C++ server passes

@@ -98,6 +98,12 @@ void FlatBA::build(const vector<ORB_SLAM2::KeyFrame*>& vpKFs, const vector<ORB_S
         pose_cam.insert(pose_cam.end(), cam, cam + 5);
     }
     not_included.assign(vpMP.size(), true);  // vbNotIncludedMP (:63-64, :106)
+    {   // one page-locked block per edge array (PageLocked): an upper bound of the observations is reserved up front
+        size_t n_obs = 0;
+        for (size_t i = 0; i < vpMP.size(); i++)
+            if (vpMP[i] && !vpMP[i]->isBad()) n_obs += (size_t)vpMP[i]->Observations();
+        edge_pose.reserve(n_obs); edge_point.reserve(n_obs); edge_inv_sigma2.reserve(n_obs); edge_obs.reserve(3 * n_obs);
+    }
     for (size_t i = 0; i < vpMP.size(); i++) {
         MapPoint* pMP = vpMP[i];
         if (!pMP || pMP->isBad()) continue;  // :107-109
