@@ -2382,19 +2382,23 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     const bool early_upload = E > 0 && up_st != nullptr;
     if (early_upload) {
         int *q_pose, *q_point;
-        double *q_obs, *q_info;
+        double *q_obs, *q_info, *q_X;
         int rc0;
         if ((rc0 = H.alloc(&q_pose, (size_t)E)) != CORB_OK || (rc0 = H.alloc(&q_point, (size_t)E)) != CORB_OK ||
-            (rc0 = H.alloc(&q_obs, (size_t)E * 3)) != CORB_OK || (rc0 = H.alloc(&q_info, (size_t)E)) != CORB_OK)
+            (rc0 = H.alloc(&q_obs, (size_t)E * 3)) != CORB_OK || (rc0 = H.alloc(&q_info, (size_t)E)) != CORB_OK ||
+            (rc0 = H.alloc(&q_X, (size_t)L * 3)) != CORB_OK)
             return rc0;
+        d.X = q_X;  // the landmark estimates (24 B each) travel with the edge arrays
+        const double* src_X = p->point_xyz;
+        const size_t bytes_X = (size_t)L * 3 * sizeof(double);
         d.e_pose = q_pose; d.e_point = q_point; d.e_obs = q_obs; d.e_info = q_info;
         CORB_CUDA(cudaMemcpyAsync(q_pose, ep, (size_t)E * sizeof(int), cudaMemcpyHostToDevice, H.stream));
         cudaStream_t st = up_st;
         BaArena* stage = H.arena && H.arena->h_stage ? H.arena : nullptr;
         uploader.t = std::thread([=, &up_err] {
             struct Job { char* dst; const char* src; size_t bytes; };
-            const Job jobs[3] = {{(char*)q_obs, (const char*)eobs, (size_t)E * 3 * sizeof(double)}, {(char*)q_info, (const char*)einfo, (size_t)E * sizeof(double)},
-                                 {(char*)q_point, (const char*)ept, (size_t)E * sizeof(int)}};
+            const Job jobs[4] = {{(char*)q_obs, (const char*)eobs, (size_t)E * 3 * sizeof(double)}, {(char*)q_info, (const char*)einfo, (size_t)E * sizeof(double)},
+                                 {(char*)q_point, (const char*)ept, (size_t)E * sizeof(int)}, {(char*)q_X, (const char*)src_X, bytes_X}};
             // page-locked caller arrays (corb_host_alloc: what the C++ shim flattens into) are read by the DMA engines in place;
             // pageable ones go through the staging slots
             cudaError_t e0 = cudaSetDevice(device);
@@ -2684,7 +2688,9 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
         if ((rc = H.upload(&d.cam, cam)) != CORB_OK) return rc;
     }
 #define AL(field, n) if ((rc = H.alloc(&d.field, (n))) != CORB_OK) return rc
-    AL(q, (size_t)P * 4); AL(t, (size_t)P * 3); AL(X, (size_t)L * 3); AL(q0, (size_t)P * 4); AL(t0, (size_t)P * 3); AL(X0, (size_t)L * 3);
+    AL(q, (size_t)P * 4); AL(t, (size_t)P * 3);
+    if (!early_upload) { AL(X, (size_t)L * 3); }
+    AL(q0, (size_t)P * 4); AL(t0, (size_t)P * 3); AL(X0, (size_t)L * 3);
     AL(Hpp, (size_t)Pf * 36); AL(bp, (size_t)Pf * 6); AL(Hll, (size_t)L * 9); AL(bl, (size_t)L * 3); AL(W, (size_t)E * 18);
     AL(Dinv, (size_t)L * 9); AL(db, (size_t)L * 3);
     AL(S, H.s_doubles + (size_t)Pf * 6);
@@ -2729,7 +2735,7 @@ extern "C" int corb_ba_solve(corb_ba_problem* p, int iterations, const volatile 
     d.bs = d.S + H.s_doubles;
     CORB_CUDA(cudaMemcpyAsync(d.q, p->pose_q, (size_t)P * 4 * sizeof(double), cudaMemcpyHostToDevice, H.stream));
     CORB_CUDA(cudaMemcpyAsync(d.t, p->pose_t, (size_t)P * 3 * sizeof(double), cudaMemcpyHostToDevice, H.stream));
-    CORB_CUDA(cudaMemcpyAsync(d.X, p->point_xyz, (size_t)L * 3 * sizeof(double), cudaMemcpyHostToDevice, H.stream));
+    if (!early_upload) CORB_CUDA(cudaMemcpyAsync(d.X, p->point_xyz, (size_t)L * 3 * sizeof(double), cudaMemcpyHostToDevice, H.stream));
     CORB_CUDA(cudaMemsetAsync(d.scalars, 0, 8 * sizeof(double), H.stream));
 
     lap("uploads + allocations");
