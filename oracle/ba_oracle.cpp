@@ -15,7 +15,8 @@
  *
  * PARITY STATUS: parity unpinned (the only path left as a port: g2o and Optimizer.cc need Eigen3, which is not in the image,
  * so they cannot be compiled into oracle/_ref) — the reference ships no BA fixtures. Pinned by algebra instead: analytic
- * Jacobians vs central differences, chi2 monotone over accepted steps, LM constants from the source (tests/test_ba_oracle.py).
+ * Jacobians vs central differences, chi2 monotone over accepted steps, LM constants from the source, and the converged minimum
+ * against scipy.optimize.least_squares on an independently written residual (tests/test_oracle_cpu.py).
  *
  * Landmarks may be sharded over ranks: every rank holds all poses and a subset of landmarks with their edges; the
  * reduced system is summed through the caller's all-reduce callback.

@@ -307,3 +307,54 @@ def test_search_by_projection_semantics():
     # a larger search window (th = 3, Tracking.cc:1208) cannot lose candidates
     _, n3 = PB.search_by_projection_map(cs, fv.n, s["in_view"], None, s["proj"], s["level"], s["view_cos"], s["mp_desc"], 3.0, 0.8)
     assert n3 >= n2 - 5
+
+
+def test_ba_minimum_equals_scipy_least_squares():
+    """Independent pin of the BA port (g2o / Optimizer.cc cannot be compiled here: no Eigen3): the minimum the oracle's LM
+    converges to is the minimum scipy.optimize.least_squares finds for a residual written independently in numpy from the
+    reference's edge definitions (types_six_dof_expmap.cpp:103-234: u = fx x/z + cx, v = fy y/z + cy, ur = u - bf/z, weighted
+    by invSigma2) - same objective, same local minimum from the same start, whatever path each optimiser takes."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+    from corb_slam_b200.synth import ba_problem
+    from oracle import _ba_bind as B
+    oracle.lib()
+    prob = ba_problem(8, 60, seed=5, obs_per_point=4, n_fusion=2)
+    P, L = len(prob["pose_t"]), len(prob["point_xyz"])
+    ep, el = prob["edge_pose"], prob["edge_point"]
+    obs, w = prob["edge_obs"], np.sqrt(prob["edge_inv_sigma2"])
+    cam = prob["pose_cam"]
+    stereo = obs[:, 2] >= 0
+    free_p = np.nonzero(prob["pose_fixed"] == 0)[0]
+    rv0 = Rotation.from_quat(prob["pose_q"]).as_rotvec()   # (x, y, z, w), world -> camera
+
+    def unpack(x):
+        rv, t = rv0.copy(), prob["pose_t"].copy()
+        rv[free_p] = x[:3 * len(free_p)].reshape(-1, 3)
+        t[free_p] = x[3 * len(free_p):6 * len(free_p)].reshape(-1, 3)
+        return rv, t, x[6 * len(free_p):].reshape(L, 3)
+
+    def residual(x):
+        rv, t, X = unpack(x)
+        R = Rotation.from_rotvec(rv).as_matrix()
+        Xc = np.einsum("eij,ej->ei", R[ep], X[el]) + t[ep]
+        fx, fy, cx, cy, bf = (cam[ep, k] for k in range(5))
+        u = fx * Xc[:, 0] / Xc[:, 2] + cx
+        v = fy * Xc[:, 1] / Xc[:, 2] + cy
+        r = [w * (obs[:, 0] - u), w * (obs[:, 1] - v), np.where(stereo, w * (obs[:, 2] - (u - bf / Xc[:, 2])), 0.0)]
+        return np.concatenate(r)
+
+    x0 = np.concatenate([rv0[free_p].ravel(), prob["pose_t"][free_p].ravel(), prob["point_xyz"].ravel()])
+    chi2_0 = float((residual(x0) ** 2).sum())
+    o0, _ = B.chi2(prob)
+    # the same function up to the float32 reciprocal the reference keeps in the stereo projection (1.0f / z, :151): 5e-8 relative
+    assert o0 == pytest.approx(chi2_0, rel=1e-6)
+    sol = least_squares(residual, x0, method="lm", xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=4000)
+    o_out, o_info = B.solve(prob, 60, robust=False)
+    o_min, _ = B.chi2(o_out)
+    assert o_min < 0.5 * chi2_0
+    assert o_min == pytest.approx(float((sol.fun ** 2).sum()), rel=1e-5)
+    rv, t, X = unpack(sol.x)
+    assert np.abs(o_out["pose_t"] - t).max() < 1e-4
+    # (a weakly constrained landmark - two nearly parallel rays - sits in a flat valley: compare the bulk, not the worst one)
+    assert np.percentile(np.abs(o_out["point_xyz"] - X).max(axis=1), 90) < 1e-3
