@@ -2016,7 +2016,7 @@ struct BaHost {
     int build_schur_pairs(size_t pairs_bound, size_t nblocks) {
         sp_ok = false;
         const char* env = getenv("CORB_BA_SCHUR");
-        if ((env && !strcmp(env, "old")) || d.P <= 0 || d.E <= 0 || pairs_bound == 0 || pairs_bound > ((size_t)1 << 30)) return CORB_OK;
+        if ((env && !strcmp(env, "old")) || d.P <= 0 || d.E <= 0 || pairs_bound == 0 || pairs_bound > ((size_t)1 << 27)) return CORB_OK;  // (1 GB of pair records at most; denser maps keep the edge walk)
         int th = 512, ch = 32;  // CORB_BA_SP=threads,chunk: A/B switch of the kernel shape
         if (const char* e2 = getenv("CORB_BA_SP")) sscanf(e2, "%d,%d", &th, &ch);
         if (th != 256) th = 512;
