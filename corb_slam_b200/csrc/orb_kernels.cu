@@ -853,12 +853,11 @@ __global__ void __launch_bounds__(256, 3) k_fast_cells_g(OrbGeom g, const __grid
                     if (left < 4) m &= (1u << (8 * left)) - 1u;
                 }
                 if (m) {  // the survivor list is a set (scores land by position, NMS sets mask bits): any order will do
-                    int base = atomicAdd(&S.n_surv, __popc(m));
-                    while (m) {
-                        const int k = (__ffs(m) - 1) >> 3;
-                        m &= m - 1;
-                        S.surv[base++] = (uint16_t)(y << 6 | (4 * q + k));
-                    }
+                    const int base = atomicAdd(&S.n_surv, __popc(m));
+                    const uint32_t code = (uint32_t)(y << 6 | 4 * q);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)  // predicated stores instead of a divergent bit loop
+                        if (m & (0x80u << (8 * k))) S.surv[base + __popc(m & ((0x80u << (8 * k)) - 1u))] = (uint16_t)(code + k);
                 }
             }
         }
