@@ -492,10 +492,9 @@ __device__ __forceinline__ int fast_score_dev(const uint8_t* c, int th) {
     constexpr int P = kRoiPitch;
     const int v = c[0];
     int r[16];
+    // (no compass-point early exit here: the callers' pre-tests have removed the bulk, half of what is left are corners, and
+    // the nine-arc test below implies it)
     r[0] = c[3 * P]; r[4] = c[3]; r[8] = c[-3 * P]; r[12] = c[-3];
-    const int hi0 = v + th, lo0 = v - th;
-    if ((r[0] > hi0) + (r[4] > hi0) + (r[8] > hi0) + (r[12] > hi0) < 2 && (r[0] < lo0) + (r[4] < lo0) + (r[8] < lo0) + (r[12] < lo0) < 2)
-        return 0;
     r[1] = c[3 * P + 1];   r[2] = c[2 * P + 2];   r[3] = c[P + 3];
     r[5] = c[-P + 3];      r[6] = c[-2 * P + 2];  r[7] = c[-3 * P + 1];
     r[9] = c[-3 * P - 1];  r[10] = c[-2 * P - 2]; r[11] = c[-P - 3];
