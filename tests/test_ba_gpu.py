@@ -236,3 +236,14 @@ def test_ba_schur_pair_lists_equal_the_edge_walk(monkeypatch):
     assert info_s["schur_pair_lists"] == 1 and info_s["trial_accepted"] == info_o["trial_accepted"]
     assert info_s["chi2_final"] == pytest.approx(info_o["chi2_final"], rel=1e-10)
     _check(prob, iters=5)
+
+
+def test_ba_page_locked_edge_arrays_equal_pageable():
+    """Edge arrays in page-locked memory (corb_host_alloc: what the C++ shim flattens into) are uploaded by the DMA engines in
+    place, pageable ones through the staging slots: same bits either way."""
+    from corb_slam_b200 import page_locked
+    prob = ba_problem(400, 30000, seed=29, n_fusion=6)
+    out_a, info_a = Optimizer.BundleAdjustment(prob, 4, bRobust=False)
+    out_b, info_b = Optimizer.BundleAdjustment(page_locked(prob), 4, bRobust=False)
+    assert info_a["trial_accepted"] == info_b["trial_accepted"] and info_a["chi2_final"] == info_b["chi2_final"]
+    assert out_a["pose_t"].tobytes() == out_b["pose_t"].tobytes() and out_a["point_xyz"].tobytes() == out_b["point_xyz"].tobytes()
