@@ -358,3 +358,29 @@ def test_ba_minimum_equals_scipy_least_squares():
     assert np.abs(o_out["pose_t"] - t).max() < 1e-4
     # (a weakly constrained landmark - two nearly parallel rays - sits in a flat valley: compare the bulk, not the worst one)
     assert np.percentile(np.abs(o_out["point_xyz"] - X).max(axis=1), 90) < 1e-3
+
+
+def test_fast_pretest_of_the_cuda_kernel_is_a_superset_of_the_corners():
+    """k_fast_cells_g rejects a pixel before the exact score unless (|r0-v| > th or |r8-v| > th) and (|r4-v| > th or |r12-v| > th)
+    (DESIGN.md section 4.1). Every FAST-9/16 corner must pass that filter - checked here against the oracle's cv2-pinned
+    detector (without NMS every positive score is a corner) on textured, noisy and synthetic bench images, at both thresholds."""
+    from corb_slam_b200.synth import stereo_frame
+    rng = np.random.default_rng(11)
+    imgs = [stereo_frame(1234)[0][:200, :300], rng.integers(0, 256, (120, 160)).astype(np.uint8),
+            (rng.integers(0, 2, (90, 130)) * 200 + rng.integers(0, 40, (90, 130))).astype(np.uint8)]
+    n_corners = 0
+    for img in imgs:
+        I = img.astype(np.int32)
+        v = I[3:-3, 3:-3]
+        r0, r8, r4, r12 = I[6:, 3:-3], I[:-6, 3:-3], I[3:-3, 6:], I[3:-3, :-6]
+        for th in (20, 7):
+            far = lambda r: np.abs(r - v) > th
+            keep = (far(r0) | far(r8)) & (far(r4) | far(r12))
+            kps = oracle.fast_detect(img, th)           # (x, y, response) after NMS: a subset of the corners
+            xs, ys = np.asarray([k[0] for k in kps], int), np.asarray([k[1] for k in kps], int)
+            assert keep[ys - 3, xs - 3].all()
+            # and every corner before NMS: response = (max over nine-arcs of the arc minimum) - 1, a corner at th iff response >= th
+            sc = oracle.fast_score(img).astype(np.int32)[3:-3, 3:-3]
+            assert keep[sc >= th].all()
+            n_corners += int((sc >= th).sum())
+    assert n_corners > 5000
