@@ -114,6 +114,7 @@ def lib():
         L.corb_frame_bow.argtypes = [vp, vp, C.c_int, vp]
         L.corb_bow_store_side.argtypes = [vp, vp, C.POINTER(BowSide), i32p]
         L.corb_bow_store_sync.argtypes = [vp]
+        L.corb_bow_store_features.argtypes = [vp]
         L.corb_bow_store_download.argtypes = [vp, vp, vp, i32p, vp, vp, vp, i32p]
         L.corb_bow_score_stores.argtypes = [vp, vp, C.c_int, C.POINTER(vp), vp]
         L.corb_bow_match_stores.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.c_float, C.c_int,

@@ -208,30 +208,43 @@ __global__ void __launch_bounds__(128) k_bow_match(const BowCall* __restrict__ c
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        // the 30 bins arrive in one round trip (a lane each) and go to lane 0 through shuffles; the scan itself is sequential
+        const int mine = check_ori && lane < kHistoLength ? __ldcg(&c.hist[lane]) : 0;
         int ind1 = -1, ind2 = -1, ind3 = -1;
-        if (check_ori) {  // ComputeThreeMaxima (:1746-1787)
-            int max1 = 0, max2 = 0, max3 = 0;
-            for (int i = 0; i < kHistoLength; i++) {
-                const int s = __ldcg(&c.hist[i]);
-                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
-                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
-                else if (s > max3) { max3 = s; ind3 = i; }
-            }
+        int max1 = 0, max2 = 0, max3 = 0;
+#pragma unroll
+        for (int i = 0; i < kHistoLength; i++) {  // ComputeThreeMaxima (:1746-1787)
+            const int s = __shfl_sync(0xffffffffu, mine, i);
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (check_ori) {
             if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
             else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+        } else {
+            ind1 = ind2 = ind3 = -1;
         }
-        s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+        if (lane == 0) { s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3; }
     }
     __syncthreads();
     int cnt = 0;
-    for (int s = threadIdx.x; s < c.nOut; s += blockDim.x) {
-        if (__ldcg(&c.match[s]) < 0) continue;
-        if (check_ori) {
-            const int bin = __ldcg(reinterpret_cast<const unsigned char*>(&c.bin[s]));
-            if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { c.match[s] = -1; continue; }
+    const int k0 = s_keep[0], k1 = s_keep[1], k2 = s_keep[2];
+    for (int s0 = threadIdx.x; s0 < c.nOut; s0 += 4 * blockDim.x) {  // four entries per thread in flight: the loads first
+        int mt[4], bn[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int s = s0 + u * blockDim.x;
+            mt[u] = s < c.nOut ? __ldcg(&c.match[s]) : -1;
+            bn[u] = check_ori && s < c.nOut ? (int)__ldcg(reinterpret_cast<const unsigned char*>(&c.bin[s])) : 0;
         }
-        cnt++;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (mt[u] < 0) continue;
+            if (check_ori && bn[u] != k0 && bn[u] != k1 && bn[u] != k2) { c.match[s0 + u * blockDim.x] = -1; continue; }
+            cnt++;
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -1132,6 +1145,8 @@ static int bow_store_settle(const corb_bow_store* cs) {
     s->counts_pending = false;
     return CORB_OK;
 }
+
+int corb_bow_store_features(const corb_bow_store* s) { return s ? s->n : 0; }
 
 int corb_bow_store_sync(corb_bow_store* s) {
     CORB_CHECK(s, CORB_ERR_INVALID, "bad argument");

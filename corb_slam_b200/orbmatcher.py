@@ -129,27 +129,37 @@ class ORBmatcher:
 
     def SearchByBoWRecords(self, variant, recsA, validA, recsB, validB=None):
         """SearchByBoW between device-resident BowRecords (corb_bow_match_stores): validA / validB = lists of host byte masks
-        (or None). -> [(match, nmatches)] like SearchByBoWBatch."""
+        (or None). -> [(match, nmatches)] like SearchByBoWBatch. The marshalling is vectorised (one output block, pointer
+        tables built with numpy): at ~70 us of kernel time per batch of 32 calls the Python side is what is left to trim."""
         n = len(recsA)
         keep = []
 
-        def masks(recs, valids):
-            arr = (C.c_void_p * n)()
-            for i in range(n):
-                if valids is not None and valids[i] is not None:
-                    v = np.ascontiguousarray(valids[i], np.uint8)
-                    keep.append(v)
-                    arr[i] = v.ctypes.data
-            return arr
-        ra = (C.c_void_p * n)(*[r._h for r in recsA])
-        rb = (C.c_void_p * n)(*[r._h for r in recsB])
-        sizes = [(a.n if variant == KF_KF else b.n) for a, b in zip(recsA, recsB)]
-        outs = [np.empty(max(1, k), np.int32) for k in sizes]
-        ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        def masks(valids):
+            tab = np.zeros(n, np.uint64)
+            if valids is not None:
+                for i, v in enumerate(valids):
+                    if v is not None:
+                        v = np.ascontiguousarray(v, np.uint8)
+                        keep.append(v)
+                        tab[i] = v.__array_interface__["data"][0]
+            keep.append(tab)
+            return (C.c_void_p * n).from_buffer(tab)
+
+        def handles(recs):
+            tab = np.fromiter((r._h.value for r in recs), np.uint64, n)
+            keep.append(tab)
+            return (C.c_void_p * n).from_buffer(tab)
+
+        sizes = np.fromiter(((a.n if variant == KF_KF else b.n) for a, b in zip(recsA, recsB)), np.int64, n)
+        offs = np.zeros(n + 1, np.int64)
+        np.cumsum(np.maximum(sizes, 1), out=offs[1:])
+        out = np.empty(int(offs[-1]), np.int32)
+        ptab = (out.__array_interface__["data"][0] + 4 * offs[:-1]).astype(np.uint64)
         nm = np.zeros(n, np.int32)
-        check(lib().corb_bow_match_stores(self._h, variant, n, ra, masks(recsA, validA), rb, masks(recsB, validB), self.mfNNratio,
-                                          int(self.mbCheckOrientation), ptrs, nm.ctypes.data_as(_lib.i32p)))
-        return [(o[:k], int(c)) for o, k, c in zip(outs, sizes, nm)]
+        check(lib().corb_bow_match_stores(self._h, variant, n, handles(recsA), masks(validA), handles(recsB), masks(validB),
+                                          self.mfNNratio, int(self.mbCheckOrientation), (C.c_void_p * n).from_buffer(ptab),
+                                          nm.ctypes.data_as(_lib.i32p)))
+        return [(out[offs[i]:offs[i] + sizes[i]], int(nm[i])) for i in range(n)]
 
     def SearchByBoW(self, kf, frame):
         """SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches): -> (match[F.N] = KF feature index or -1, nmatches)."""

@@ -115,7 +115,7 @@ class BowRecord:
     def from_extractor(self, extractor, voc, levelsup=4):
         """corb_frame_bow: record <- the extractor's last (device-resident) result."""
         check(lib().corb_frame_bow(extractor._h, voc._h, int(levelsup), self._h))
-        self.n = self.side()[0].n
+        self.n = int(lib().corb_bow_store_features(self._h))  # known when the fill is enqueued: no wait here
         return self
 
     def from_device(self, voc, d_desc, n, levelsup=4, d_kps=None, stream=None):

@@ -436,6 +436,7 @@ CORB_API int corb_frame_bow(corb_orb* h, corb_voc* v, int levelsup, corb_bow_sto
  * first (corb_bow_store_side / _download, corb_bow_match_stores, corb_bow_score_stores), and so does this one explicitly.
  * A record that several threads will read must be synced once by the thread that filled it before it is shared. */
 CORB_API int corb_bow_store_sync(corb_bow_store* s);
+CORB_API int corb_bow_store_features(const corb_bow_store* s);  /* features of the last fill (known when it is enqueued) */
 CORB_API int corb_bow_store_side(const corb_bow_store* s, const uint8_t* d_valid, corb_bow_side* side, int* n_bow);
 CORB_API int corb_bow_store_download(const corb_bow_store* s, uint32_t* bow_words, double* bow_vals, int* n_bow, uint32_t* fv_nodes,
                                      int32_t* fv_off, uint32_t* fv_idx, int* n_fv);
